@@ -1,0 +1,181 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes front-end of oracle/liboracle.so (built by oracle/Makefile).
+
+Each function cites the reference code it restates (paths relative to the reference root).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    """Compile the C++ restatement (g++ only; no reference sources are compiled or copied)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        L = C.CDLL(so)
+        L.orc_beam_ctor.argtypes = [f64p, f64p, f64p, f64p, f64p]
+        L.orc_beam_ctor.restype = C.c_int
+        L.orc_beam_residual.argtypes = [f64p, C.c_int, C.c_int, f64p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, f64p, f64p]
+        L.orc_beam_residual.restype = C.c_int
+        L.orc_sinc1k.argtypes = [C.c_int, C.c_double]
+        L.orc_sinc1k.restype = C.c_double
+        L.orc_scac_d.argtypes = [C.c_int, C.c_double]
+        L.orc_scac_d.restype = C.c_double
+        L.orc_rodrigues_roundtrip.argtypes = [f64p, f64p, f64p, f64p]
+        L.orc_sweepx_assemble_beams.argtypes = [C.c_int64, f64p, i64p, i64p, i64p, C.c_int, C.c_int, f64p, C.c_void_p, C.c_void_p,
+                                                f64p, f64p, f64p, f64p]
+        L.orc_sweepx_assemble_beams.restype = C.c_int
+        L.orc_beams_iter_elementwise.argtypes = [C.c_int64, f64p, i64p, C.c_int, f64p, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p, C.c_int]
+        L.orc_beams_iter_elementwise.restype = C.c_int
+        L.orc_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# BeamCrossSection field order, toolbox/BeamElement.jl:6-23
+MAT_FIELDS = ("EA", "EI2", "EI3", "GJ", "mu", "iota1", "w", "Ca1", "Cl1", "Cq1", "Ca2", "Cl2", "Cq2", "Ca3", "Cl3", "Cq3")
+
+
+def beam_cross_section(**kw):
+    """BeamCrossSection(;EA,EI₂,EI₃,GJ,μ,ι₁,w=0,...)  toolbox/BeamElement.jl:25 → 16 doubles."""
+    m = np.zeros(16)
+    for k, v in kw.items():
+        m[MAT_FIELDS.index(k)] = v
+    return m
+
+
+# layout of the 69-double EulerBeam3D struct, toolbox/BeamElement.jl:87-103
+BEAM_LAYOUT = dict(cm=(0, 3), rm=(3, 12), zgp=(12, 16), znod=(16, 18), tgm=(18, 21), tge=(21, 24), ya=(24, 28), yu=(28, 32),
+                   yv=(32, 36), ka=(36, 40), ku=(40, 44), kv=(44, 48), L=(48, 49), dL=(49, 53), mat=(53, 69))
+
+
+def beam_ctor(c1, c2, mat, orient2=(0., 1., 0.)):
+    """EulerBeam3D(nod; mat, orient2)  toolbox/BeamElement.jl:121-148 → 69 doubles (rm column-major)."""
+    out = np.zeros(69)
+    rc = lib().orc_beam_ctor(np.ascontiguousarray(c1, float), np.ascontiguousarray(c2, float), np.ascontiguousarray(orient2, float),
+                             np.ascontiguousarray(mat, float), out)
+    if rc:
+        raise ValueError("Provide a 'orient' input that is not nearly parallel to the element")
+    return out
+
+
+def beam_field(e, name):
+    a, b = BEAM_LAYOUT[name]
+    v = e[..., a:b]
+    if name == "rm":
+        return v.reshape(v.shape[:-1] + (3, 3)).swapaxes(-1, -2)  # column-major → [i,j]
+    return v
+
+
+def beam_residual(elem, X, Xseed=None, U=None, Useed=None):
+    """Muscade.residual(o::EulerBeam3D,X,U,A,t,SP,dbg)  toolbox/BeamElement.jl:151-174 with first-order seeds.
+
+    X: (nd,12) values; Xseed: (nd,12,np) partials; U: (3,) or None; Useed (3,np).  Returns R (12,), dR (12,np)."""
+    X = np.ascontiguousarray(np.atleast_2d(X), float)
+    nd = X.shape[0]
+    if Xseed is None:
+        Xseed = np.zeros((nd, 12, 0))
+    Xseed = np.ascontiguousarray(Xseed, float)
+    np_ = Xseed.shape[2]
+    udof = U is not None
+    if udof:
+        U = np.ascontiguousarray(U, float)
+        Useed = np.zeros((3, np_)) if Useed is None else np.ascontiguousarray(Useed, float)
+    R = np.zeros(12)
+    dR = np.zeros((12, max(np_, 1)))
+    rc = lib().orc_beam_residual(np.ascontiguousarray(elem, float), nd, np_, X, _ptr(Xseed) if np_ else None, int(udof),
+                                 _ptr(U), _ptr(Useed), R, dR)
+    if rc < 0:
+        raise ValueError("bad arguments")
+    return R, dR[:, :np_], rc
+
+
+def diffed_residual(elem, X, U=None):
+    """Muscade.diffed_residual(ele;X,U,A)  src/Diagnostic.jl:929-961: revariate{1}((;X,U,A)) unit seeds, flat ordering
+    X₀ X₁ X₂ U₀ ; returns R and the list ∇R[X][ider] (12×12 each) (+ ∇R[U][0] 12×3)."""
+    X = np.atleast_2d(np.asarray(X, float))
+    nd = X.shape[0]
+    nu = 0 if U is None else 3
+    np_ = 12 * nd + nu
+    Xseed = np.zeros((nd, 12, np_))
+    for d in range(nd):
+        for i in range(12):
+            Xseed[d, i, 12 * d + i] = 1.
+    Useed = None
+    if U is not None:
+        Useed = np.zeros((3, np_))
+        for i in range(3):
+            Useed[i, 12 * nd + i] = 1.
+    R, dR, rc = beam_residual(elem, X, Xseed, U, Useed)
+    gX = [dR[:, 12 * d:12 * d + 12] for d in range(nd)]
+    gU = dR[:, 12 * nd:] if U is not None else None
+    return R, gX, gU
+
+
+def sinc1k(k, x):
+    """sinc1, sinc1′, … sinc1⁗  toolbox/Rotations.jl:13-44"""
+    return lib().orc_sinc1k(k, float(x))
+
+
+def scac_d(n, x):
+    """n-th derivative of scac by nested duals  toolbox/Rotations.jl:61-68, test/TestRotations.jl:35-60"""
+    return lib().orc_scac_d(n, float(x))
+
+
+def rodrigues_roundtrip(v):
+    """Rodrigues, Rodrigues⁻¹ and ∂w/∂v  toolbox/Rotations.jl:105,131-135"""
+    M = np.zeros(9); w = np.zeros(3); dw = np.zeros(9)
+    lib().orc_rodrigues_roundtrip(np.ascontiguousarray(v, float), M, w, dw)
+    return M.reshape(3, 3).T, w, dw.reshape(3, 3)
+
+
+def sweepx_assemble_beams(elems, idx, asm1, asm2, OX, mission, X, scaleX, newmark, Llambda, nzval):
+    """assemble_!{mission} + addin!{mission}(::AssemblySweepX{OX}) over one EulerBeam3D element type
+    (src/Assemble.jl:478-487, src/SweepX.jl:45-96). idx/asm1/asm2 are (nele,12|12|144) int64, 1-based; accumulates."""
+    nele = elems.shape[0]
+    X = [np.ascontiguousarray(x, float) for x in X]
+    rc = lib().orc_sweepx_assemble_beams(nele, np.ascontiguousarray(elems), np.ascontiguousarray(idx, np.int64),
+                                         np.ascontiguousarray(asm1, np.int64), np.ascontiguousarray(asm2, np.int64), OX,
+                                         {"step": 0, "iter": 1}[mission], X[0], _ptr(X[1]) if OX >= 1 else None,
+                                         _ptr(X[2]) if OX >= 2 else None, np.ascontiguousarray(scaleX, float),
+                                         np.ascontiguousarray(newmark, float), Llambda, nzval)
+    if rc:
+        raise FloatingPointError("residual(EulerBeam3D,...) returned NaN in R, FB or derivatives (iele=%d)" % rc)
+
+
+def beams_iter_elementwise(elems, idx, OX, X, scaleX, newmark, nthreads=1):
+    nele = elems.shape[0]
+    Re = np.zeros((nele, 12)); Ke = np.zeros((nele, 144))
+    X = [np.ascontiguousarray(x, float) for x in X]
+    bad = lib().orc_beams_iter_elementwise(nele, np.ascontiguousarray(elems), np.ascontiguousarray(idx, np.int64), OX, X[0],
+                                           _ptr(X[1]) if OX >= 1 else None, _ptr(X[2]) if OX >= 2 else None,
+                                           np.ascontiguousarray(scaleX, float), np.ascontiguousarray(newmark, float), Re, Ke, nthreads)
+    return Re, Ke, bad
+
+
+def newmark_coefficients(OX, dt, beta=0.25, gamma=0.5):
+    """Newmarkβcoefficients{OX}(Δt,β,γ)  src/SweepX.jl:12-15 → (a1,a2,a3,b1,b2,b3,Δt)"""
+    if OX == 0:
+        return np.array([0., 0., 0., 0., 0., 0., dt])
+    if OX == 1:
+        return np.array([1 / (gamma * dt), 1 / gamma, 0., 0., 0., 0., dt])
+    return np.array([gamma / (beta * dt), gamma / beta, (gamma / (2 * beta) - 1) * dt, 1 / (beta * dt ** 2), 1 / (beta * dt), 1 / (2 * beta), dt])
