@@ -1,0 +1,378 @@
+// EulerBeam3D residual + tangent, B200 formulation.
+//
+// What the reference computes (toolbox/BeamElement.jl:151-174):
+//     R_j = Σ_gp dL_gp [ fᵢ·∂ε/∂X₀ⱼ + mᵢ·∂κ_gp/∂X₀ⱼ + fₑ·∂x_gp/∂X₀ⱼ + mₑ·∂vₛₘ/∂X₀ⱼ ]          (virtual work)
+// as a ∂ℝ{1,Np} whose partials are the tangent.  It obtains the Jacobians AND their partials (Hessian·seed) from a
+// second-order forward pass in 12 variables with a 3→6→12 chain rule (Taylor.jl:225-323) — 6.5e5 flops/element.
+//
+// Same mathematics here, evaluated as forward-over-reverse:
+//   1. forward sweep of the corotated kinematics (BeamElement.jl:176-208) in the lane's number type
+//        S = Dual<W>            (static)        or   Jet<Dual<W>>  (Newmark / DirectXUA: value, velocity, acceleration)
+//      giving the resultants fᵢ,mᵢ,fₑ,mₑ (BeamElement.jl:28-64) with their directional partials;
+//   2. reverse (adjoint) sweep of the order-0 kinematics with cotangents w = dL·(fᵢ,mᵢ,fₑ,mₑ), in Dual<W>:
+//      the value part is R = Jᵀw, the dual part is ∂R/∂seed = Jᵀ∂w + (∂Jᵀ)w, i.e. material + geometric tangent.
+// Each lane carries W of the Np seed directions; no second-order dual, no McLaurin expansion, nothing leaves registers.
+// Branches of the reference's special functions (sinc1 family thresholds, scac series, norm3 cutoff, drag sign)
+// are reproduced on VALUE, as the reference does (Adiff.jl:198-202).
+#pragma once
+#include "dual.cuh"
+
+namespace mb {
+
+template <class T> struct Vec3 { T a[3]; MB_HD T& operator[](int i) { return a[i]; } MB_HD const T& operator[](int i) const { return a[i]; } };
+template <class T> struct Mat3 { T a[9]; MB_HD T& operator()(int i, int j) { return a[i + 3 * j]; } MB_HD const T& operator()(int i, int j) const { return a[i + 3 * j]; } };
+
+template <class A, class B> MB_HD auto mul(const Mat3<A>& a, const Mat3<B>& b) -> Mat3<decltype(a.a[0] * b.a[0])> {
+    Mat3<decltype(a.a[0] * b.a[0])> c;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) c(i, j) = (a(i, 0) * b(0, j) + a(i, 1) * b(1, j)) + a(i, 2) * b(2, j);
+    return c;
+}
+// a * bᵀ
+template <class A, class B> MB_HD auto mul_nt(const Mat3<A>& a, const Mat3<B>& b) -> Mat3<decltype(a.a[0] * b.a[0])> {
+    Mat3<decltype(a.a[0] * b.a[0])> c;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) c(i, j) = (a(i, 0) * b(j, 0) + a(i, 1) * b(j, 1)) + a(i, 2) * b(j, 2);
+    return c;
+}
+// aᵀ * b
+template <class A, class B> MB_HD auto mul_tn(const Mat3<A>& a, const Mat3<B>& b) -> Mat3<decltype(a.a[0] * b.a[0])> {
+    Mat3<decltype(a.a[0] * b.a[0])> c;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) c(i, j) = (a(0, i) * b(0, j) + a(1, i) * b(1, j)) + a(2, i) * b(2, j);
+    return c;
+}
+template <class A, class B> MB_HD auto mulv(const Mat3<A>& a, const Vec3<B>& b) -> Vec3<decltype(a.a[0] * b.a[0])> {
+    Vec3<decltype(a.a[0] * b.a[0])> c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c[i] = (a(i, 0) * b[0] + a(i, 1) * b[1]) + a(i, 2) * b[2];
+    return c;
+}
+// aᵀ * v
+template <class A, class B> MB_HD auto mulv_t(const Mat3<A>& a, const Vec3<B>& b) -> Vec3<decltype(a.a[0] * b.a[0])> {
+    Vec3<decltype(a.a[0] * b.a[0])> c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c[i] = (a(0, i) * b[0] + a(1, i) * b[1]) + a(2, i) * b[2];
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ rotations (forward)
+// Rodrigues(v) = I + sinc1(θ)·S + ½sinc1(θ/2)²·S²   (toolbox/Rotations.jl:131-135, spin² :114-122, norm3 :106-112)
+template <class T> struct RodAux { T a, b; bool small; };     // what the adjoint needs again
+template <class T> MB_HD Mat3<T> rodrigues(const Vec3<T>& v, RodAux<T>& aux) {
+    T t2 = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+    T a, b;
+    T th = mb_sqrt(t2);
+    aux.small = value(th) < 1e-14;
+    if (aux.small) { a = Make<T>::c(1.0); b = Make<T>::c(0.5); }                 // θ := 0 without partials
+    else { a = sinc1k<0>(th); T c = sinc1k<0>(th * 0.5); b = sqr_ref(c) * 0.5; }
+    aux.a = a; aux.b = b;
+    T v00 = v[0] * v[0], v11 = v[1] * v[1], v22 = v[2] * v[2];
+    T b01 = b * (v[0] * v[1]), b02 = b * (v[0] * v[2]), b12 = b * (v[1] * v[2]);
+    T a0 = a * v[0], a1 = a * v[1], a2 = a * v[2];
+    Mat3<T> r;
+    r(0, 0) = 1.0 - b * (v11 + v22); r(1, 1) = 1.0 - b * (v00 + v22); r(2, 2) = 1.0 - b * (v00 + v11);
+    r(1, 0) = b01 + a2; r(0, 1) = b01 - a2;
+    r(2, 0) = b02 - a1; r(0, 2) = b02 + a1;
+    r(2, 1) = b12 + a0; r(1, 2) = b12 - a0;
+    return r;
+}
+// scac(x) = sinc1(acos x) with its series about 1 (Rotations.jl:61-68), K-th derivative in generic arithmetic
+template <class T> MB_HD T scac(const T& x) {
+    T dx = x - 1.0;
+    if (fabs(value(dx)) > 1e-3) return sinc1k<0>(mb_acos(x));
+    return 1.0 + dx * (1. / 3 + dx * (-2. / 90 + dx * (0.0052911879917544626 + dx * (-0.0016229317117234072 + dx * 0.0005625))));
+}
+template <class T> MB_HD T scac1(const T& x) {                                    // d scac / dx, same branches
+    T dx = x - 1.0;
+    if (fabs(value(dx)) > 1e-3) { T w = 1.0 - x * x; return -(sinc1k<1>(mb_acos(x)) / mb_sqrt(w)); }
+    return 1. / 3 + dx * (2 * (-2. / 90) + dx * (3 * 0.0052911879917544626 + dx * (4 * -0.0016229317117234072 + dx * (5 * 0.0005625))));
+}
+// Rodrigues⁻¹(m) = spin⁻¹(m)/scac((tr m − 1)/2)   (Rotations.jl:90,105)
+template <class T> struct RinvAux { T x, s; };
+template <class T> MB_HD Vec3<T> rodrigues_inv(const Mat3<T>& m, RinvAux<T>& aux) {
+    T x = (((m(0, 0) + m(1, 1)) + m(2, 2)) - 1.0) * 0.5;
+    T s = scac(x);
+    aux.x = x; aux.s = s;
+    T is = mb_rcp(s);
+    Vec3<T> v;
+    v[0] = ((m(2, 1) - m(1, 2)) * 0.5) * is;
+    v[1] = ((m(0, 2) - m(2, 0)) * 0.5) * is;
+    v[2] = ((m(1, 0) - m(0, 1)) * 0.5) * is;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ rotations (adjoint)
+// v̄ += ∂Rodrigues(v)ᵀ·R̄
+template <class S> MB_HD void rodrigues_adj(const Vec3<S>& v, const RodAux<S>& aux, const Mat3<S>& Rb, Vec3<S>& vb) {
+    const S &a = aux.a, &b = aux.b;
+    S k0 = Rb(2, 1) - Rb(1, 2), k1 = Rb(0, 2) - Rb(2, 0), k2 = Rb(1, 0) - Rb(0, 1);          // skew part
+    S s01 = Rb(0, 1) + Rb(1, 0), s02 = Rb(0, 2) + Rb(2, 0), s12 = Rb(1, 2) + Rb(2, 1);        // symmetric part
+    S d0 = Rb(1, 1) + Rb(2, 2), d1 = Rb(0, 0) + Rb(2, 2), d2 = Rb(0, 0) + Rb(1, 1);
+    S g0 = (s01 * v[1] + s02 * v[2]) - 2.0 * (v[0] * d0);                                     // ∂(S²:R̄)/∂v
+    S g1 = (s01 * v[0] + s12 * v[2]) - 2.0 * (v[1] * d1);
+    S g2 = (s02 * v[0] + s12 * v[1]) - 2.0 * (v[2] * d2);
+    vb[0] = vb[0] + (a * k0 + b * g0);
+    vb[1] = vb[1] + (a * k1 + b * g1);
+    vb[2] = vb[2] + (a * k2 + b * g2);
+    if (!aux.small) {
+        S ab = (v[0] * k0 + v[1] * k1) + v[2] * k2;                                           // ā = S:R̄
+        S bb = 0.5 * ((v[0] * g0 + v[1] * g1) + v[2] * g2);                                   // b̄ = S²:R̄ (Euler: homogeneous degree 2)
+        S th = mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+        S hth = th * 0.5;
+        S da = sinc1k<1>(th);
+        S db = (sinc1k<0>(hth) * sinc1k<1>(hth)) * 0.5;
+        S tb = (ab * da + bb * db) / th;                                                      // θ̄/θ
+        vb[0] = vb[0] + tb * v[0]; vb[1] = vb[1] + tb * v[1]; vb[2] = vb[2] + tb * v[2];
+    }
+}
+// M̄ += ∂Rodrigues⁻¹(M)ᵀ·v̄ , v = Rodrigues⁻¹(M)
+template <class S> MB_HD void rodrigues_inv_adj(const Vec3<S>& v, const RinvAux<S>& aux, const Vec3<S>& vb, Mat3<S>& Mb) {
+    S is = mb_rcp(aux.s);
+    S sb = -(((vb[0] * v[0] + vb[1] * v[1]) + vb[2] * v[2]) * is);
+    S xb = (sb * scac1(aux.x)) * 0.5;
+    S w0 = (vb[0] * is) * 0.5, w1 = (vb[1] * is) * 0.5, w2 = (vb[2] * is) * 0.5;
+    Mb(0, 0) = Mb(0, 0) + xb; Mb(1, 1) = Mb(1, 1) + xb; Mb(2, 2) = Mb(2, 2) + xb;
+    Mb(2, 1) = Mb(2, 1) + w0; Mb(1, 2) = Mb(1, 2) - w0;
+    Mb(0, 2) = Mb(0, 2) + w1; Mb(2, 0) = Mb(2, 0) - w1;
+    Mb(1, 0) = Mb(1, 0) + w2; Mb(0, 1) = Mb(0, 1) - w2;
+}
+
+// ------------------------------------------------------------------------------------------------ element data
+constexpr int NGP = 4;
+struct BeamMat { double EA, EI2, EI3, GJ, mu, iota1, w, Ca1, Cl1, Cq1, Ca2, Cl2, Cq2, Ca3, Cl3, Cq3; };   // BeamElement.jl:6-23
+struct BeamGeo { double cm[3]; Mat3<double> rm; double tgm[3]; double L; };                                // the non-constant part of BeamElement.jl:87-103
+
+// Gauss abscissae, weights/L and shape values that the reference stores per element (BeamElement.jl:141-146) are compile-time
+// constants times powers of L.
+struct BeamConst { double zgp[NGP], wgp[NGP], ya[NGP], yu[NGP], yv[NGP], ku[NGP]; };
+MB_HD BeamConst beam_const() {
+    BeamConst c;
+    const double s65 = 1.0954451150103321;    // sqrt(6/5)
+    const double s30 = 5.477225575051661;     // sqrt(30)
+    const double zo = 0.5 * sqrt(3. / 7 + 2. / 7 * s65), zi = 0.5 * sqrt(3. / 7 - 2. / 7 * s65);
+    c.zgp[0] = -zo; c.zgp[1] = -zi; c.zgp[2] = zi; c.zgp[3] = zo;
+    const double wo = 0.5 * (18 - s30) / 36, wi = 0.5 * (18 + s30) / 36;
+    c.wgp[0] = wo; c.wgp[1] = wi; c.wgp[2] = wi; c.wgp[3] = wo;
+#pragma unroll
+    for (int g = 0; g < NGP; ++g) {
+        double z = c.zgp[g];
+        c.ya[g] = 2 * z; c.yu[g] = -4 * (z * z * z) + 3 * z; c.yv[g] = z * z - 0.25; c.ku[g] = -24 * z;
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ forward kinematics
+template <class T> struct BeamFwd {
+    Vec3<T> v1, v2, dv, vsm, ul, vl, dp;      // dp = uᵧ₂ + tgₘ/2 − cₛ
+    Mat3<T> r1, r2, rd, r;                    // rₛ₁, rₛ₂, Rodrigues(Δvᵧ), rₛₘ
+    RodAux<T> a1, a2, ad;
+    RinvAux<T> im, ir;
+    Vec3<T> cs;                               // cₛ + cₘ
+    T eps, qn; Vec3<T> q;                     // q = uₗ₂ + (L/2,0,0), qn = |q|
+};
+// corotated{:direct} + ε  (BeamElement.jl:181,192-208)
+template <class T> MB_HD void beam_forward(const BeamGeo& g, const T* X, BeamFwd<T>& f) {
+    Vec3<T> u1{X[0], X[1], X[2]}, u2{X[6], X[7], X[8]};
+    f.v1 = Vec3<T>{X[3], X[4], X[5]}; f.v2 = Vec3<T>{X[9], X[10], X[11]};
+    f.r1 = rodrigues(f.v1, f.a1);
+    f.r2 = rodrigues(f.v2, f.a2);
+    Mat3<T> M = mul_nt(f.r2, f.r1);
+    Vec3<T> h = rodrigues_inv(M, f.im);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) f.dv[i] = 0.5 * h[i];
+    f.rd = rodrigues(f.dv, f.ad);
+    f.r = mul(mul(f.rd, f.r1), g.rm);
+    f.vsm = rodrigues_inv(f.r, f.ir);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        T cs = 0.5 * (u1[i] + u2[i]);
+        f.dp[i] = (u2[i] + g.tgm[i] * 0.5) - cs;
+        f.cs[i] = cs + g.cm[i];
+    }
+    f.ul = mulv_t(f.r, f.dp);
+    f.ul[0] = f.ul[0] - g.L * 0.5;
+    f.vl = mulv_t(f.r, f.dv);
+    f.q = f.ul; f.q[0] = f.q[0] + g.L * 0.5;
+    f.qn = mb_sqrt((f.q[0] * f.q[0] + f.q[1] * f.q[1]) + f.q[2] * f.q[2]);
+    f.eps = f.qn * (2.0 / g.L) - 1.0;
+}
+// Gauss point position x = rₛₘ(tgₑζ + y) + cₛₘ  (BeamElement.jl:183-187)
+template <class T> MB_HD Vec3<T> beam_gp_local(const BeamConst& c, double L, int gp, const Vec3<T>& ul, const Vec3<T>& vl) {
+    Vec3<T> p;
+    double yv = c.yv[gp] * L;
+    p[0] = c.ya[gp] * ul[0] + L * c.zgp[gp];
+    p[1] = c.yu[gp] * ul[1] + yv * vl[2];
+    p[2] = c.yu[gp] * ul[2] - yv * vl[1];
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ resultants → cotangents
+// Cotangents of the order-0 kinematic outputs, already multiplied by dL (BeamElement.jl:163-171)
+template <class S> struct BeamCot { S eps; Vec3<S> kap[NGP]; Vec3<S> x[NGP]; Vec3<S> vsm; };
+
+// external force at a Gauss point (BeamElement.jl:28-58) from position-velocity-acceleration of the point and the frame rₛₘ
+template <class S> MB_HD Vec3<S> beam_fe(const BeamMat& m, const Mat3<S>& r0, const Vec3<S>& x1, const Vec3<S>& x2) {
+    Vec3<S> xl1 = mulv_t(r0, x1), xl2 = mulv_t(r0, x2);
+    const double Ca[3] = {m.Ca1, m.Ca2, m.Ca3}, Cl[3] = {m.Cl1, m.Cl2, m.Cl3}, Cq[3] = {m.Cq1, m.Cq2, m.Cq3};
+    Vec3<S> fl;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        S fq = Cq[i] * (xl1[i] * xl1[i]);
+        if (value(xl1[i]) < 0) fq = -fq;
+        fl[i] = (Ca[i] * xl2[i] + Cl[i] * xl1[i]) + fq;
+    }
+    Vec3<S> fg = mulv(r0, fl);
+    Vec3<S> fe;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fe[i] = m.mu * x2[i] + fg[i];
+    fe[2] = fe[2] + m.w;
+    return fe;
+}
+
+// ------------------------------------------------------------------------------------------------ reverse sweep
+// Given order-0 forward state f (in S) and cotangents w, accumulate X̄[12] = Jᵀ w.
+template <class S> MB_HD void beam_reverse(const BeamGeo& g, const BeamConst& c, const BeamFwd<S>& f, const BeamCot<S>& w, S* Xb) {
+    const double L = g.L;
+    S z = Make<S>::c(0.);
+    Mat3<S> rb; for (int i = 0; i < 9; ++i) rb.a[i] = z;
+    Vec3<S> ulb{z, z, z}, vlb{z, z, z}, cb{z, z, z};
+    // x_gp = r p_gp + c ;  κ_gp, y_gp linear in (uₗ,vₗ)
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) {
+        Vec3<S> p = beam_gp_local(c, L, gp, f.ul, f.vl);
+        const Vec3<S>& xb = w.x[gp];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rb(i, j) = rb(i, j) + xb[i] * p[j];
+        Vec3<S> pb = mulv_t(f.r, xb);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cb[i] = cb[i] + xb[i];
+        double yv = c.yv[gp] * L, ka = 2.0 / L, ku = c.ku[gp] / (L * L), kv = 2.0 / L;
+        const Vec3<S>& kb = w.kap[gp];
+        ulb[0] = ulb[0] + c.ya[gp] * pb[0];
+        ulb[1] = ulb[1] + (c.yu[gp] * pb[1] + ku * kb[1]);
+        ulb[2] = ulb[2] + (c.yu[gp] * pb[2] + ku * kb[2]);
+        vlb[0] = vlb[0] + ka * kb[0];
+        vlb[1] = vlb[1] - (yv * pb[2] + kv * kb[2]);
+        vlb[2] = vlb[2] + (yv * pb[1] + kv * kb[1]);
+    }
+    // ε = 2|q|/L − 1
+    {
+        S k = (w.eps * (2.0 / L)) / f.qn;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ulb[i] = ulb[i] + k * f.q[i];
+    }
+    // uₗ = rᵀ d' − tgₑ/2 ; vₗ = rᵀ Δv
+    Vec3<S> dvb = mulv(f.r, vlb);
+    Vec3<S> dpb = mulv(f.r, ulb);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rb(i, j) = rb(i, j) + (f.dp[i] * ulb[j] + f.dv[i] * vlb[j]);
+    // vₛₘ = Rodrigues⁻¹(r)
+    rodrigues_inv_adj(f.vsm, f.ir, w.vsm, rb);
+    // r = rd · r1 · rm
+    Mat3<S> t = mul_nt(rb, g.rm);                  // r̄ rₘᵀ
+    Mat3<S> rdb = mul_nt(t, f.r1);                 // (r̄ rₘᵀ) r₁ᵀ
+    Mat3<S> r1b = mul_tn(f.rd, t);                 // r_dᵀ (r̄ rₘᵀ)
+    // rd = Rodrigues(Δv)
+    rodrigues_adj(f.dv, f.ad, rdb, dvb);
+    // Δv = ½ Rodrigues⁻¹(M), M = r2 r1ᵀ
+    Mat3<S> Mb; for (int i = 0; i < 9; ++i) Mb.a[i] = z;
+    Vec3<S> hb{0.5 * dvb[0], 0.5 * dvb[1], 0.5 * dvb[2]};
+    Vec3<S> h{2.0 * f.dv[0], 2.0 * f.dv[1], 2.0 * f.dv[2]};
+    rodrigues_inv_adj(h, f.im, hb, Mb);
+    Mat3<S> r2b = mul(Mb, f.r1);                   // M̄ r₁
+    Mat3<S> r1b2 = mul_tn(Mb, f.r2);               // M̄ᵀ r₂
+    for (int i = 0; i < 9; ++i) r1b.a[i] = r1b.a[i] + r1b2.a[i];
+    Vec3<S> v1b{z, z, z}, v2b{z, z, z};
+    rodrigues_adj(f.v1, f.a1, r1b, v1b);
+    rodrigues_adj(f.v2, f.a2, r2b, v2b);
+    // d' = (u₂ + tgₘ/2) − ½(u₁+u₂) ; cₛₘ = ½(u₁+u₂) + cₘ
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        S hcs = 0.5 * (cb[i] - dpb[i]);
+        Xb[i] = hcs; Xb[3 + i] = v1b[i]; Xb[6 + i] = hcs + dpb[i]; Xb[9 + i] = v2b[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ whole element
+// ND = 1 (static), 2 (first order), 3 (Newmark / DirectXUA second order).
+// X[ider][12], U0[3] carry the lane's seeds. Returns R[12] as Dual<W>: value = residual, d = ∂R/∂(lane's directions).
+template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMat& m, const Dual<W> (*X)[12], bool udof, const Dual<W>* U0, Dual<W>* R) {
+    using S = Dual<W>;
+    const BeamConst c = beam_const();
+    const double L = g.L;
+    BeamFwd<S> f;
+    BeamCot<S> w;
+    if (ND == 1) {
+        beam_forward<S>(g, X[0], f);
+#pragma unroll
+        for (int gp = 0; gp < NGP; ++gp) {
+            double dL = c.wgp[gp] * L;
+            w.x[gp] = Vec3<S>{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(m.w * dL)};
+            if (udof) for (int i = 0; i < 3; ++i) w.x[gp][i] = w.x[gp][i] - dL * U0[i];
+        }
+        w.vsm = Vec3<S>{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(0.)};
+    } else {
+        using J = Jet<S>;
+        J XJ[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { XJ[i].c0 = X[0][i]; XJ[i].c1 = X[1][i]; XJ[i].c2 = (ND >= 3) ? X[2][i] : Make<S>::c(0.); }
+        BeamFwd<J> fj;
+        beam_forward<J>(g, XJ, fj);
+        // external loads at the Gauss points from (x, ẋ, ẍ) and rₛₘ
+        Mat3<S> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
+#pragma unroll
+        for (int gp = 0; gp < NGP; ++gp) {
+            Vec3<J> p = beam_gp_local(c, L, gp, fj.ul, fj.vl);
+            Vec3<J> x = mulv(fj.r, p);
+            Vec3<S> x1, x2;
+            for (int i = 0; i < 3; ++i) { x1[i] = x[i].c1 + fj.cs[i].c1; x2[i] = (ND >= 3) ? (x[i].c2 + fj.cs[i].c2) : Make<S>::c(0.); }   // ∂2(x) is zero when the solver gives no acceleration (ElementAPI.jl:48)
+            Vec3<S> fe = beam_fe(m, r0, x1, x2);
+            double dL = c.wgp[gp] * L;
+            for (int i = 0; i < 3; ++i) { if (udof) fe[i] = fe[i] - U0[i]; w.x[gp][i] = dL * fe[i]; }
+        }
+        // roll inertia: mₑ = rₛₘ[:,1]·ι₁·vᵢ₂[1], vᵢ₂ = spin⁻¹(ṙᵀṙ + rᵀr̈)  (Rotations.jl:177-182; the symmetric ṙᵀṙ drops out of spin⁻¹)
+        S vi2 = Make<S>::c(0.);
+        if (ND >= 3) {
+            S m21 = (fj.r(0, 2).c0 * fj.r(0, 1).c2 + fj.r(1, 2).c0 * fj.r(1, 1).c2) + fj.r(2, 2).c0 * fj.r(2, 1).c2;   // (rᵀr̈)[3,2]
+            S m12 = (fj.r(0, 1).c0 * fj.r(0, 2).c2 + fj.r(1, 1).c0 * fj.r(1, 2).c2) + fj.r(2, 1).c0 * fj.r(2, 2).c2;   // (rᵀr̈)[2,3]
+            vi2 = (m21 - m12) * 0.5;
+        }
+        S m1l = (m.iota1 * L) * vi2;                                         // Σ_gp dL = L
+        for (int i = 0; i < 3; ++i) w.vsm[i] = r0(i, 0) * m1l;
+        // order-0 state for the reverse sweep
+        for (int i = 0; i < 3; ++i) {
+            f.v1[i] = fj.v1[i].c0; f.v2[i] = fj.v2[i].c0; f.dv[i] = fj.dv[i].c0; f.vsm[i] = fj.vsm[i].c0;
+            f.ul[i] = fj.ul[i].c0; f.vl[i] = fj.vl[i].c0; f.dp[i] = fj.dp[i].c0; f.q[i] = fj.q[i].c0;
+        }
+        for (int i = 0; i < 9; ++i) { f.r1.a[i] = fj.r1.a[i].c0; f.r2.a[i] = fj.r2.a[i].c0; f.rd.a[i] = fj.rd.a[i].c0; f.r.a[i] = r0.a[i]; }
+        f.a1.a = fj.a1.a.c0; f.a1.b = fj.a1.b.c0; f.a1.small = fj.a1.small;
+        f.a2.a = fj.a2.a.c0; f.a2.b = fj.a2.b.c0; f.a2.small = fj.a2.small;
+        f.ad.a = fj.ad.a.c0; f.ad.b = fj.ad.b.c0; f.ad.small = fj.ad.small;
+        f.im.x = fj.im.x.c0; f.im.s = fj.im.s.c0; f.ir.x = fj.ir.x.c0; f.ir.s = fj.ir.s.c0;
+        f.eps = fj.eps.c0; f.qn = fj.qn.c0;
+    }
+    // internal loads (BeamElement.jl:59-63)
+    w.eps = (m.EA * L) * f.eps;                                              // Σ_gp dL·fᵢ
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) {
+        double dL = c.wgp[gp] * L, ka = 2.0 / L, ku = c.ku[gp] / (L * L), kv = 2.0 / L;
+        S k0 = ka * f.vl[0];
+        S k1 = ku * f.ul[1] + kv * f.vl[2];
+        S k2 = ku * f.ul[2] - kv * f.vl[1];
+        w.kap[gp][0] = (m.GJ * dL) * k0; w.kap[gp][1] = (m.EI3 * dL) * k1; w.kap[gp][2] = (m.EI2 * dL) * k2;
+    }
+    beam_reverse<S>(g, c, f, w, R);
+}
+
+}  // namespace mb

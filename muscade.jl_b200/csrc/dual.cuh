@@ -1,0 +1,177 @@
+// Statically unrolled dual arithmetic kept in registers.
+//
+// Replaces the reference's generic ∂ℝ{P,N,R} (src/Adiff.jl:13-304) on the GPU path by two fixed-shape number types:
+//   Dual<W>  : value + W directional partials (the lane's share of the solver's seed directions, SweepX.jl:46-63)
+//   Jet<S>   : second-order Taylor number in time (q, q̇, q̈) over S, standing for the reference's
+//              motion{P} packing ∂ℝ{P+1,1,∂ℝ{P,1,·}} (src/Taylor.jl:24-29) without its duplicated q̇ slot.
+// Differentiation rules are the reference's (Adiff.jl:223-266) with FMA contraction allowed.
+//
+// The header compiles for the device (nvcc) and for the host (g++, used by tests/ to validate the kernel's
+// formulation against the oracle without a GPU).
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define MB_HD __host__ __device__ __forceinline__
+#else
+#define MB_HD inline
+#endif
+
+namespace mb {
+
+// ------------------------------------------------------------------------------------------------ double helpers
+MB_HD double mb_sinpi(double x) {
+#ifdef __CUDA_ARCH__
+    return sinpi(x);
+#else
+    double n = nearbyint(x), r = x - n;
+    double s = sin(3.141592653589793 * r);
+    return (((long long)n) & 1) ? -s : s;
+#endif
+}
+MB_HD void mb_sincos(double x, double* s, double* c) {
+#ifdef __CUDA_ARCH__
+    sincos(x, s, c);
+#else
+    *s = sin(x); *c = cos(x);
+#endif
+}
+
+// sinc1 and its derivatives on Float64, with the reference's branch thresholds (toolbox/Rotations.jl:13-44)
+// and Julia Base.sinc's small-argument polynomial (|x/π| < 1e-3).
+template <int K> MB_HD double sinc1k(double x);
+template <> MB_HD double sinc1k<0>(double x) {
+    const double PI = 3.141592653589793;
+    double y = x / PI;
+    if (fabs(y) < 0.001) {
+        double y2 = y * y;
+        return fma(y2, fma(y2, (PI * PI) * (PI * PI) / 120, -(PI * PI) / 6), 1.0);
+    }
+    return mb_sinpi(y) / (PI * y);
+}
+template <> MB_HD double sinc1k<1>(double x) {
+    if (fabs(x) > 1e-3) { double s, c; mb_sincos(x, &s, &c); return c / x - s / (x * x); }
+    double x2 = x * x;
+    return x * (-1. / 3 + x2 / 30);
+}
+template <> MB_HD double sinc1k<2>(double x) {
+    if (fabs(x) > 1e-1) { double s, c; mb_sincos(x, &s, &c); return -s / x - 2 * c / (x * x) + 2 * s / (x * x * x); }
+    double x2 = x * x;
+    return -1. / 3 + x2 * (1. / 10 + x2 * (-1. / 168 + x2 * (1. / 6480)));
+}
+template <> MB_HD double sinc1k<3>(double x) {
+    if (fabs(x) > 0.4) {
+        double s, c; mb_sincos(x, &s, &c);
+        double x2 = x * x;
+        return -c / x + 3 * s / x2 + 6 * c / (x * x2) - 6 * s / (x2 * x2);
+    }
+    double x2 = x * x;
+    return x * (1. / 5 + x2 * (-1. / 42 + x2 * (1. / 1080 + x2 * (-1. / 55440 + x2 * (1. / 4717440)))));
+}
+template <> MB_HD double sinc1k<4>(double x) {
+    double x2 = x * x;
+    return 1. / 5 + x2 * (-1. / 14 + x2 * (1. / 216 + x2 * (-1. / 7920 + x2 * (1. / 524160 + x2 * (-1. / 54432000 + x2 * (1. / 54432000 + x2 * (-1. / 8143027200. + x2 * (1. / 1656387532800.))))))));
+}
+template <> MB_HD double sinc1k<5>(double x) { return x * NAN; }
+template <> MB_HD double sinc1k<6>(double x) { return x * NAN; }
+
+MB_HD double value(double a) { return a; }
+MB_HD double mb_sqrt(double a) { return sqrt(a); }
+MB_HD double mb_acos(double a) { return acos(a); }
+MB_HD double mb_rcp(double a) { return 1.0 / a; }
+template <class T> struct Make { static MB_HD T c(double v); };
+template <> struct Make<double> { static MB_HD double c(double v) { return v; } };
+
+// ------------------------------------------------------------------------------------------------ Dual<W>
+template <int W> struct Dual {
+    double v;
+    double d[W];
+};
+template <int W> struct Make<Dual<W>> {
+    static MB_HD Dual<W> c(double v) { Dual<W> r; r.v = v;
+#pragma unroll
+        for (int i = 0; i < W; ++i) r.d[i] = 0.; return r; }
+};
+template <int W> MB_HD double value(const Dual<W>& a) { return a.v; }
+
+#define MB_FORW _Pragma("unroll") for (int i = 0; i < W; ++i)
+
+template <int W> MB_HD Dual<W> operator+(const Dual<W>& a, const Dual<W>& b) { Dual<W> r; r.v = a.v + b.v; MB_FORW r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int W> MB_HD Dual<W> operator+(const Dual<W>& a, double b) { Dual<W> r = a; r.v = a.v + b; return r; }
+template <int W> MB_HD Dual<W> operator+(double a, const Dual<W>& b) { Dual<W> r = b; r.v = a + b.v; return r; }
+template <int W> MB_HD Dual<W> operator-(const Dual<W>& a, const Dual<W>& b) { Dual<W> r; r.v = a.v - b.v; MB_FORW r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int W> MB_HD Dual<W> operator-(const Dual<W>& a, double b) { Dual<W> r = a; r.v = a.v - b; return r; }
+template <int W> MB_HD Dual<W> operator-(double a, const Dual<W>& b) { Dual<W> r; r.v = a - b.v; MB_FORW r.d[i] = -b.d[i]; return r; }
+template <int W> MB_HD Dual<W> operator-(const Dual<W>& a) { Dual<W> r; r.v = -a.v; MB_FORW r.d[i] = -a.d[i]; return r; }
+template <int W> MB_HD Dual<W> operator*(const Dual<W>& a, const Dual<W>& b) {
+    Dual<W> r; r.v = a.v * b.v; MB_FORW r.d[i] = fma(a.v, b.d[i], a.d[i] * b.v); return r;
+}
+template <int W> MB_HD Dual<W> operator*(const Dual<W>& a, double b) { Dual<W> r; r.v = a.v * b; MB_FORW r.d[i] = a.d[i] * b; return r; }
+template <int W> MB_HD Dual<W> operator*(double a, const Dual<W>& b) { Dual<W> r; r.v = a * b.v; MB_FORW r.d[i] = a * b.d[i]; return r; }
+template <int W> MB_HD Dual<W> mb_rcp(const Dual<W>& a) { Dual<W> r; r.v = 1.0 / a.v; double m = -r.v * r.v; MB_FORW r.d[i] = m * a.d[i]; return r; }
+template <int W> MB_HD Dual<W> operator/(const Dual<W>& a, const Dual<W>& b) {
+    Dual<W> r; double inv = 1.0 / b.v; r.v = a.v * inv; MB_FORW r.d[i] = (a.d[i] - r.v * b.d[i]) * inv; return r;
+}
+template <int W> MB_HD Dual<W> operator/(const Dual<W>& a, double b) { return a * (1.0 / b); }
+template <int W> MB_HD Dual<W> operator/(double a, const Dual<W>& b) { Dual<W> r; double inv = 1.0 / b.v; r.v = a * inv; double m = -r.v * inv; MB_FORW r.d[i] = m * b.d[i]; return r; }
+template <int W> MB_HD Dual<W> mb_sqrt(const Dual<W>& a) { Dual<W> r; r.v = sqrt(a.v); double m = 0.5 / r.v; MB_FORW r.d[i] = m * a.d[i]; return r; }
+template <int W> MB_HD Dual<W> mb_acos(const Dual<W>& a) { Dual<W> r; r.v = acos(a.v); double m = -1.0 / sqrt(1.0 - a.v * a.v); MB_FORW r.d[i] = m * a.d[i]; return r; }
+// chained rule sinc1⁽ᵏ⁾(a) = (sinc1⁽ᵏ⁾(a.v), sinc1⁽ᵏ⁺¹⁾(a.v)·a.d)   (Rotations.jl:47-51)
+template <int K, int W> MB_HD Dual<W> sinc1k(const Dual<W>& a) { Dual<W> r; r.v = sinc1k<K>(a.v); double m = sinc1k<K + 1>(a.v); MB_FORW r.d[i] = m * a.d[i]; return r; }
+
+// ------------------------------------------------------------------------------------------------ Jet<S>  (q, q̇, q̈)
+template <class S> struct Jet {
+    S c0, c1, c2;
+};
+template <class S> struct Make<Jet<S>> {
+    static MB_HD Jet<S> c(double v) { Jet<S> r; r.c0 = Make<S>::c(v); r.c1 = Make<S>::c(0.); r.c2 = Make<S>::c(0.); return r; }
+};
+template <class S> MB_HD double value(const Jet<S>& a) { return value(a.c0); }
+template <class S> MB_HD Jet<S> operator+(const Jet<S>& a, const Jet<S>& b) { Jet<S> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; r.c2 = a.c2 + b.c2; return r; }
+template <class S> MB_HD Jet<S> operator+(const Jet<S>& a, double b) { Jet<S> r = a; r.c0 = a.c0 + b; return r; }
+template <class S> MB_HD Jet<S> operator+(double a, const Jet<S>& b) { Jet<S> r = b; r.c0 = a + b.c0; return r; }
+template <class S> MB_HD Jet<S> operator-(const Jet<S>& a, const Jet<S>& b) { Jet<S> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; r.c2 = a.c2 - b.c2; return r; }
+template <class S> MB_HD Jet<S> operator-(const Jet<S>& a, double b) { Jet<S> r = a; r.c0 = a.c0 - b; return r; }
+template <class S> MB_HD Jet<S> operator-(double a, const Jet<S>& b) { Jet<S> r; r.c0 = a - b.c0; r.c1 = -b.c1; r.c2 = -b.c2; return r; }
+template <class S> MB_HD Jet<S> operator-(const Jet<S>& a) { Jet<S> r; r.c0 = -a.c0; r.c1 = -a.c1; r.c2 = -a.c2; return r; }
+template <class S> MB_HD Jet<S> operator*(const Jet<S>& a, const Jet<S>& b) {
+    Jet<S> r;
+    r.c0 = a.c0 * b.c0;
+    r.c1 = a.c0 * b.c1 + a.c1 * b.c0;
+    r.c2 = (a.c0 * b.c2 + a.c2 * b.c0) + 2.0 * (a.c1 * b.c1);
+    return r;
+}
+template <class S> MB_HD Jet<S> operator*(const Jet<S>& a, double b) { Jet<S> r; r.c0 = a.c0 * b; r.c1 = a.c1 * b; r.c2 = a.c2 * b; return r; }
+template <class S> MB_HD Jet<S> operator*(double a, const Jet<S>& b) { Jet<S> r; r.c0 = a * b.c0; r.c1 = a * b.c1; r.c2 = a * b.c2; return r; }
+// compose a univariate function with S-valued derivatives f, f′, f″ taken at x.c0
+template <class S> MB_HD Jet<S> jet_compose(const Jet<S>& x, const S& f0, const S& f1, const S& f2) {
+    Jet<S> r; r.c0 = f0; r.c1 = f1 * x.c1; r.c2 = f2 * (x.c1 * x.c1) + f1 * x.c2; return r;
+}
+template <class S> MB_HD Jet<S> mb_rcp(const Jet<S>& a) { S f0 = mb_rcp(a.c0); S f1 = -(f0 * f0); S f2 = -2.0 * (f1 * f0); return jet_compose(a, f0, f1, f2); }
+template <class S> MB_HD Jet<S> operator/(const Jet<S>& a, const Jet<S>& b) { return a * mb_rcp(b); }
+template <class S> MB_HD Jet<S> operator/(const Jet<S>& a, double b) { return a * (1.0 / b); }
+template <class S> MB_HD Jet<S> operator/(double a, const Jet<S>& b) { return a * mb_rcp(b); }
+template <class S> MB_HD Jet<S> mb_sqrt(const Jet<S>& a) { S f0 = mb_sqrt(a.c0); S f1 = 0.5 / f0; S f2 = -0.5 * (f1 / a.c0); return jet_compose(a, f0, f1, f2); }
+template <class S> MB_HD Jet<S> mb_acos(const Jet<S>& a) {
+    S f0 = mb_acos(a.c0);
+    S w = 1.0 / (1.0 - a.c0 * a.c0);          // 1/(1-x²)
+    S f1 = -mb_sqrt(w);                       // -1/√(1-x²)
+    S f2 = f1 * a.c0 * w;                     // -x/(1-x²)^{3/2}
+    return jet_compose(a, f0, f1, f2);
+}
+template <int K, class S> MB_HD Jet<S> sinc1k(const Jet<S>& a) { return jet_compose(a, sinc1k<K>(a.c0), sinc1k<K + 1>(a.c0), sinc1k<K + 2>(a.c0)); }
+
+template <class T> MB_HD T sqr(const T& a) { return a * a; }
+
+// a^2 exactly as the reference evaluates it (src/Adiff.jl:230):  ∂ℝ(a.x^b, a.dx*b*a.x^(b-1))  with  b==0 ? zero(a).
+// On numbers nested three deep (time-packed by motion{P}, Taylor.jl:24-29, over the solver's ∂ℝ{1,Np}) the inner a.x^1 hits
+// "x^0 → zero" one level down and loses its partial, so the second time derivative comes out as 2·a·ä instead of
+// 2·a·ä + 2·ȧ².  Only toolbox/Rotations.jl:134 (sinc1(θ/2)^2) feeds such a square into results that are used.
+// Reproduced here because parity with the reference is the contract; plain numbers and Dual<W> square normally.
+MB_HD double sqr_ref(double a) { return a * a; }
+template <int W> MB_HD Dual<W> sqr_ref(const Dual<W>& a) { return a * a; }
+template <class S> MB_HD Jet<S> sqr_ref(const Jet<S>& a) {
+    Jet<S> r; r.c0 = a.c0 * a.c0; r.c1 = 2.0 * (a.c0 * a.c1); r.c2 = 2.0 * (a.c0 * a.c2); return r;
+}
+
+}  // namespace mb

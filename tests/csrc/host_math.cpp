@@ -1,0 +1,40 @@
+// Test harness: compiles the PRODUCT's device math header for the host (g++) so that the kernel's forward-over-reverse
+// formulation can be checked against the oracle without a GPU.  Not shipped, not used by the product.
+#include "../../muscade.jl_b200/csrc/beam_math.cuh"
+#include <cstring>
+using namespace mb;
+
+template <int ND, int W>
+static void run(const BeamGeo& g, const BeamMat& m, int np, const double* Xval, const double* Xseed, int udof, const double* Uval,
+                const double* Useed, double* R, double* dR) {
+    for (int p0 = 0; p0 < np || p0 == 0; p0 += W) {
+        Dual<W> X[3][12], U[3], Rv[12];
+        for (int d = 0; d < 3; ++d) for (int i = 0; i < 12; ++i) {
+            X[d][i] = Make<Dual<W>>::c(d < ND ? Xval[d * 12 + i] : 0.);
+            for (int k = 0; k < W; ++k) X[d][i].d[k] = (d < ND && p0 + k < np) ? Xseed[(d * 12 + i) * np + p0 + k] : 0.;
+        }
+        for (int i = 0; i < 3; ++i) {
+            U[i] = Make<Dual<W>>::c(udof ? Uval[i] : 0.);
+            for (int k = 0; k < W; ++k) U[i].d[k] = (udof && p0 + k < np) ? Useed[i * np + p0 + k] : 0.;
+        }
+        beam_residual<ND, W>(g, m, X, udof != 0, U, Rv);
+        for (int i = 0; i < 12; ++i) {
+            R[i] = Rv[i].v;
+            for (int k = 0; k < W; ++k) if (p0 + k < np) dR[i * np + p0 + k] = Rv[i].d[k];
+        }
+        if (np == 0) break;
+    }
+}
+
+extern "C" int mbh_beam_residual(const double* geo16, const double* mat16, int nd, int w, int np, const double* Xval, const double* Xseed,
+                                 int udof, const double* Uval, const double* Useed, double* R, double* dR) {
+    BeamGeo g; BeamMat m;
+    for (int i = 0; i < 3; ++i) g.cm[i] = geo16[i];
+    for (int i = 0; i < 9; ++i) g.rm.a[i] = geo16[3 + i];
+    for (int i = 0; i < 3; ++i) g.tgm[i] = geo16[12 + i];
+    g.L = geo16[15];
+    std::memcpy(&m, mat16, sizeof m);
+#define CASE(ND_, W_) if (nd == ND_ && w == W_) { run<ND_, W_>(g, m, np, Xval, Xseed, udof, Uval, Useed, R, dR); return 0; }
+    CASE(1, 1) CASE(1, 4) CASE(2, 1) CASE(3, 1) CASE(3, 3) CASE(1, 12)
+    return -1;
+}
