@@ -1,0 +1,95 @@
+/* muscade_b200.h — C ABI of the B200 element-evaluation-and-assembly engine.
+ *
+ * Drop-in boundary for ONE path of SINTEF/Muscade.jl (v0.7.0): what `assemble!{mission}(out,asm,dis,model,state,Δt,dbg)`
+ * (src/Assemble.jl:470-487) does for the solvers SweepX{0,1,2} (src/SweepX.jl:24-96) and DirectXUA (src/DirectXUA.jl:22-120,
+ * 316-356): gather element dofs, evaluate every element's residual with first-order forward-mode partials, scatter-add
+ * values into the gradient vector and partials into the sparse matrix.  The reference has no FFI; a Julia host binds these
+ * entry points with `ccall` from new `Assembly` subtypes.  All arrays crossing the boundary are the
+ * reference's own: Float64, Int64, 1-based indices, column-major.
+ *
+ * Conventions: every function returns int32 status (MB_OK = 0). No exception crosses the ABI. Host pointers unless the name
+ * says `_dev`. A handle is single-caller (the reference calls assemble! from one task, State/out are not thread safe).
+ * There is no CPU fallback: without a CUDA device mb_create fails with MB_ERR_CUDA.
+ */
+#ifndef MUSCADE_B200_H
+#define MUSCADE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb_handle mb_handle;
+
+enum { MB_OK = 0, MB_ERR_CUDA = 1, MB_ERR_ARG = 2, MB_ERR_NAN = 3, MB_ERR_STATE = 4, MB_ERR_TOOBIG = 5, MB_ERR_NCCL = 6 };
+
+/* Where the first NaN was found, in element order (deterministic).  Replaces the MuscadeException thrown at
+ * src/Assemble.jl:625,630 ("residual(...) returned NaN in R, FB or derivatives"); the wrapper rethrows with (ieletyp,iele). */
+typedef struct { int32_t kind; int32_t ieletyp; int64_t iele; } mb_errinfo;      /* 1-based ieletyp / iele, 0 = none */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------------ */
+int32_t     mb_create(int32_t device, mb_handle** out);
+int32_t     mb_destroy(mb_handle* h);
+const char* mb_last_error(const mb_handle* h);
+int32_t     mb_version(void);
+
+/* ---- element groups: one per reference element type, in model.eleobj order (src/ModelDescription.jl:212-219) ------------ */
+/* EulerBeam3D{BeamCrossSection,Udof} (toolbox/BeamElement.jl:87-103).
+ *   eleobj : nele × 69 Float64 — the reference's isbits Vector{EulerBeam3D{BeamCrossSection,Udof}} as it lies in memory
+ *            (cₘ3 rₘ9(col-major) ζgp4 ζnod2 tgₘ3 tgₑ3 yₐ4 yᵤ4 yᵥ4 κₐ4 κᵤ4 κᵥ4 L dL4 mat16).
+ *   idxX   : 12 × nele Int64, dis.dis[ityp].index[iele].X (src/Assemble.jl:15,96); idxU: 3 × nele or NULL when !udof.
+ *   scaleX : 12, scaleU : 3 — dis.dis[ityp].scale.X/.U (src/Assemble.jl:68). */
+int32_t mb_add_eulerbeam3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t udof, const int64_t* idxX, const int64_t* idxU,
+                           const double* scaleX, const double* scaleU, int32_t* ieletyp_out);
+/* Bar3D{AxisymmetricBarCrossSection,Udof} (toolbox/BarElement.jl:89-101): nele × 39 Float64
+ *   (cₘ3 tgₘ3 tgₑ3 L₀ Lₛ mat9 wgp4 ζgp4 ζnod2 ψ₁4 ψ₂4); idxX 6 × nele. */
+int32_t mb_add_bar3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t udof, const int64_t* idxX, const int64_t* idxU,
+                     const double* scaleX, const double* scaleU, int32_t* ieletyp_out);
+/* SoilContact (toolbox/SoilContact.jl:2-8): nele × 5 Float64 (z₀ Kh Kv Ch Cv); idxX 3 × nele. */
+int32_t mb_add_soilcontact(mb_handle* h, int64_t nele, const double* eleobj, const int64_t* idxX, const double* scaleX,
+                           int32_t* ieletyp_out);
+/* Any other element type with X-dofs only (Hold, DofLoad, DofConstraint{:X}, …; src/BasicElements.jl): the host evaluates it
+ * (user closures cannot cross a C ABI) and hands dense, already scaled element contributions before each assemble:
+ *   Re : nx × nele     (Lλ .* scale.X, SweepX.jl:55)      Rp : nx × nele, the :step predictor partial, or NULL
+ *   Ke : nx·nx × nele  (column-major i + nx·(j−1), Lλ[i].dx[j]) */
+int32_t mb_add_host_elements(mb_handle* h, int64_t nele, int32_t nx, const int64_t* idxX, int32_t* ieletyp_out);
+int32_t mb_set_host_elements(mb_handle* h, int32_t ieletyp, const double* Re, const double* Rp, const double* Ke);
+
+/* ---- SweepX: prepare(AssemblySweepX{OX},model,dis) (src/SweepX.jl:24-33) ----------------------------------------------- */
+/* Builds on the device, bit-identical to asmvec! / asmmat! (src/Assemble.jl:340-357, 373-448):
+ *   asm[1,ityp], asm[2,ityp], and the CSC pattern (colptr, rowval) of Lλx; plus the nnz-sorted contributor lists used by the
+ *   atomics-free segmented reduction. ndofX = getndof(model,:X). */
+int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out);
+int32_t mb_sweepx_get_pattern(mb_handle* h, int64_t* colptr /* ndofX+1 */, int64_t* rowval /* nnz */);
+int32_t mb_sweepx_get_asm(mb_handle* h, int32_t ieletyp, int64_t* asm1 /* nx × nele */, int64_t* asm2 /* nx² × nele */);
+
+/* assemble!{:step|:iter}(out::AssemblySweepX{OX},…) (src/Assemble.jl:470, src/SweepX.jl:45-96).
+ *   mission : 0 = :step, 1 = :iter.   X0,X1,X2 : state.X[1..OX+1] (ndofX each; X1/X2 may be NULL when OX is lower).
+ *   U0 : state.U[1] (only read by Udof elements; may be NULL).   newmark : a₁ a₂ a₃ b₁ b₂ b₃ Δt (src/SweepX.jl:3-15).
+ *   Llambda (ndofX) and nzval (nnz) receive out.Lλ and out.Lλx.nzval; either may be NULL to leave the result on the device. */
+int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const double* X0, const double* X1, const double* X2,
+                           const double* U0, double t, const double* newmark, double* Llambda, double* nzval, mb_errinfo* where);
+/* Same with the state already resident on the device (see mb_state_ptrs_dev) and results left there. Asynchronous on the
+ * handle's stream; mb_sync waits and reports NaN. */
+int32_t mb_sweepx_assemble_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark);
+int32_t mb_sync(mb_handle* h, mb_errinfo* where);
+
+/* Device buffers owned by the handle, so that a device sparse solver (cuDSS) and the state update can consume them without a
+ * host round-trip: X0,X1,X2 (ndofX), U0, Llambda (ndofX), nzval (nnz), colptr32/rowval32 (0-based int32 CSC). */
+typedef struct { double *X0, *X1, *X2, *U0, *Llambda, *nzval; int32_t *colptr0, *rowval0; int64_t ndofX, ndofU, nnz; } mb_dev_ptrs;
+int32_t mb_get_device_ptrs(mb_handle* h, mb_dev_ptrs* out);
+int32_t mb_set_ndofU(mb_handle* h, int64_t ndofU);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------------------------------------------ */
+/* Times one launch set of the last assemble configuration with CUDA events on the handle's stream:
+ *   ms[0] = element kernels, ms[1] = segmented reduction into nzval/Lλ. */
+int32_t mb_sweepx_time_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark, int32_t reps, float* ms);
+/* Sustained FP64 FMA throughput of this device (dependent-chain-free DFMA loop), TFLOP/s — the FP64 roofline denominator. */
+int32_t mb_measure_fp64_tflops(mb_handle* h, double* tflops);
+/* Device copy bandwidth (read+write bytes / time), GB/s. */
+int32_t mb_measure_copy_gbs(mb_handle* h, double* gbs);
+int64_t mb_launch_count(const mb_handle* h);      /* kernels of this library launched so far on this handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,9 @@
+"""muscade_b200 — B200-native element-evaluation-and-assembly path of SINTEF/Muscade.jl.
+
+Host-side mirror of the reference interface for this path (Model / addnode! / addelement! / initialize! / prepare /
+assemble! / solve(SweepX)), over the C ABI in include/muscade_b200.h.  The directory name contains a dot, so the package
+is imported through the loader `muscade_b200.py` at the repository root (`import muscade_b200`).
+"""
+from . import _lib, toolbox, synthetic  # noqa: F401
+from ._lib import MuscadeB200Error, build  # noqa: F401
+from .engine import Engine  # noqa: F401

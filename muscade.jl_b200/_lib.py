@@ -1,0 +1,94 @@
+"""ctypes binding of libmuscade_b200.so (include/muscade_b200.h).  No fallback: if the CUDA library is missing or no
+device is present, every compute entry point raises."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libmuscade_b200.so")
+_LIB = None
+
+MB_OK, MB_ERR_CUDA, MB_ERR_ARG, MB_ERR_NAN, MB_ERR_STATE, MB_ERR_TOOBIG, MB_ERR_NCCL = range(7)
+
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+class ErrInfo(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ieletyp", C.c_int32), ("iele", C.c_int64)]
+
+
+class DevPtrs(C.Structure):
+    _fields_ = [("X0", C.c_void_p), ("X1", C.c_void_p), ("X2", C.c_void_p), ("U0", C.c_void_p), ("Llambda", C.c_void_p),
+                ("nzval", C.c_void_p), ("colptr0", C.c_void_p), ("rowval0", C.c_void_p), ("ndofX", C.c_int64), ("ndofU", C.c_int64),
+                ("nnz", C.c_int64)]
+
+
+# every symbol include/muscade_b200.h declares: name → (restype, argtypes)
+H = C.c_void_p
+SYMBOLS = {
+    "mb_create": (C.c_int32, [C.c_int32, C.POINTER(H)]),
+    "mb_destroy": (C.c_int32, [H]),
+    "mb_last_error": (C.c_char_p, [H]),
+    "mb_version": (C.c_int32, []),
+    "mb_add_eulerbeam3d": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mb_add_bar3d": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mb_add_soilcontact": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mb_add_host_elements": (C.c_int32, [H, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mb_set_host_elements": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_sweepx_prepare": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_int64)]),
+    "mb_sweepx_get_pattern": (C.c_int32, [H, i64p, i64p]),
+    "mb_sweepx_get_asm": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_sweepx_assemble": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, f64p,
+                                        C.c_void_p, C.c_void_p, C.POINTER(ErrInfo)]),
+    "mb_sweepx_assemble_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p]),
+    "mb_sync": (C.c_int32, [H, C.POINTER(ErrInfo)]),
+    "mb_get_device_ptrs": (C.c_int32, [H, C.POINTER(DevPtrs)]),
+    "mb_set_ndofU": (C.c_int32, [H, C.c_int64]),
+    "mb_sweepx_time_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p, C.c_int32, f32p]),
+    "mb_measure_fp64_tflops": (C.c_int32, [H, C.POINTER(C.c_double)]),
+    "mb_measure_copy_gbs": (C.c_int32, [H, C.POINTER(C.c_double)]),
+    "mb_launch_count": (C.c_int64, [H]),
+}
+
+
+def build(force=False):
+    """nvcc build of the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    if force or not os.path.exists(SO_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j8", "-s"] + (["-B"] if force else []))
+    return SO_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError("libmuscade_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class MuscadeB200Error(RuntimeError):
+    """Mirror of MuscadeException (src/Exceptions.jl:2-16): message + where (dbg) it happened."""
+
+    def __init__(self, msg, dbg=None):
+        super().__init__(msg + ("" if not dbg else "  " + repr(dbg)))
+        self.dbg = dbg or {}
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def check(h, rc, dbg=None):
+    if rc != MB_OK:
+        msg = lib().mb_last_error(h).decode() if h else "mb_create failed: no CUDA device / library (no CPU fallback)"
+        raise MuscadeB200Error("muscade_b200 [%d]: %s" % (rc, msg), dbg)

@@ -1,0 +1,546 @@
+// C ABI of the B200 assembly engine (include/muscade_b200.h). Owns all device memory; no PyTorch, no CPU fallback.
+#include "../../include/muscade_b200.h"
+#include "kernels.cuh"
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mb;
+
+namespace {
+
+enum GroupKind { G_BEAM = 1, G_BAR = 2, G_SOIL = 3, G_HOST = 4 };
+
+struct Group {
+    int kind = 0;
+    int64_t nele = 0;
+    int nx = 0, nu = 0, udof = 0;
+    double* geo = nullptr;
+    BeamMat* mats = nullptr;
+    int32_t* mat_id = nullptr;
+    int32_t* idxX = nullptr;     // [nele][nx] 0-based
+    int32_t* idxU = nullptr;
+    double scaleX[12] = {0}, scaleU[3] = {0};
+    int64_t pair_base = 0;       // offset of this group's nx²·nele tangent entries in Ke_all
+    int64_t vec_base = 0;        // offset of this group's nx·nele residual entries in Re_all
+};
+
+}  // namespace
+
+struct mb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<Group> groups;
+    // model sizes
+    int64_t ndofX = 0, ndofU = 0, nnz = 0, npair = 0, nvec = 0;
+    bool prepared = false;
+    // state and outputs
+    double *X0 = nullptr, *X1 = nullptr, *X2 = nullptr, *U0 = nullptr, *Ll = nullptr, *nzval = nullptr;
+    // element outputs
+    double *Ke = nullptr, *Re = nullptr, *Rp = nullptr;
+    // maps
+    int32_t *asm2 = nullptr, *colptr0 = nullptr, *rowval0 = nullptr;
+    uint32_t *cstart = nullptr, *src = nullptr, *vstart = nullptr, *vsrc = nullptr;
+    unsigned long long* nanflag = nullptr;
+    unsigned long long* nanflag_host = nullptr;   // pinned
+    int64_t launches = 0;
+    int beamW = 1;
+    std::vector<void*> owned;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return MB_ERR_CUDA;                                                                          \
+        }                                                                                                \
+    } while (0)
+#define ARG(cond, msg)                                                                                   \
+    do {                                                                                                 \
+        if (!(cond)) { h->err = msg; return MB_ERR_ARG; }                                                \
+    } while (0)
+
+template <class T> static cudaError_t dalloc(mb_handle* h, T** p, int64_t n) {
+    *p = nullptr;
+    if (n <= 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
+    if (e == cudaSuccess) h->owned.push_back(*p);
+    return e;
+}
+static void dfree(mb_handle* h, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < h->owned.size(); ++i)
+        if (h->owned[i] == p) { h->owned.erase(h->owned.begin() + i); break; }
+    cudaFree(p);
+}
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// Int64 1-based [nele][n] (reference memory order) → int32 0-based on the device
+static int32_t upload_index(mb_handle* h, const int64_t* src, int64_t n, int64_t limit, int32_t** dst) {
+    std::vector<int32_t> tmp((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = src[i];
+        if (v < 1 || (limit > 0 && v > limit) || v > INT32_MAX) { h->err = "dof index out of range (expects 1-based Int64)"; return MB_ERR_ARG; }
+        tmp[(size_t)i] = (int32_t)(v - 1);
+    }
+    CK(dalloc(h, dst, n));
+    CK(cudaMemcpy(*dst, tmp.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return MB_OK;
+}
+
+extern "C" {
+
+int32_t mb_version(void) { return 100; }
+
+int32_t mb_create(int32_t device, mb_handle** out) {
+    if (!out) return MB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return MB_ERR_CUDA;
+    mb_handle* h = new mb_handle();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
+    if (cudaMalloc((void**)&h->nanflag, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost((void**)&h->nanflag_host, sizeof(unsigned long long)) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
+    const char* w = getenv("MB_BEAM_W");
+    if (w) h->beamW = atoi(w);
+    *out = h;
+    return MB_OK;
+}
+
+int32_t mb_destroy(mb_handle* h) {
+    if (!h) return MB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->owned) cudaFree(p);
+    cudaFree(h->nanflag);
+    cudaFreeHost(h->nanflag_host);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MB_OK;
+}
+
+const char* mb_last_error(const mb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t mb_launch_count(const mb_handle* h) { return h ? h->launches : 0; }
+
+int32_t mb_add_eulerbeam3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t udof, const int64_t* idxX, const int64_t* idxU,
+                           const double* scaleX, const double* scaleU, int32_t* ieletyp_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared, "groups must be added before prepare");
+    ARG(nele >= 0 && eleobj && idxX && scaleX, "null argument");
+    ARG(!udof || (idxU && scaleU), "Udof element type needs idxU and scaleU");
+    CK(cudaSetDevice(h->device));
+    Group g;
+    g.kind = G_BEAM; g.nele = nele; g.nx = 12; g.nu = udof ? 3 : 0; g.udof = udof;
+    // split the reference AoS struct (69 doubles, toolbox/BeamElement.jl:87-103) into geometry lines + a de-duplicated material table
+    std::vector<double> geo((size_t)nele * 16);
+    std::vector<BeamMat> mats;
+    std::vector<int32_t> mat_id((size_t)nele);
+    std::map<std::string, int32_t> seen;
+    for (int64_t e = 0; e < nele; ++e) {
+        const double* o = eleobj + e * 69;
+        double* q = geo.data() + e * 16;
+        for (int k = 0; k < 12; ++k) q[k] = o[k];          // cₘ, rₘ
+        for (int k = 0; k < 3; ++k) q[12 + k] = o[18 + k];  // tgₘ
+        q[15] = o[48];                                      // L
+        std::string key((const char*)(o + 53), 16 * sizeof(double));
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            BeamMat m; std::memcpy(&m, o + 53, sizeof m);
+            it = seen.emplace(key, (int32_t)mats.size()).first;
+            mats.push_back(m);
+        }
+        mat_id[(size_t)e] = it->second;
+    }
+    CK(dalloc(h, &g.geo, nele * 16));
+    CK(cudaMemcpy(g.geo, geo.data(), geo.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(dalloc(h, &g.mats, (int64_t)mats.size()));
+    CK(cudaMemcpy(g.mats, mats.data(), mats.size() * sizeof(BeamMat), cudaMemcpyHostToDevice));
+    if (mats.size() > 1) {
+        CK(dalloc(h, &g.mat_id, nele));
+        CK(cudaMemcpy(g.mat_id, mat_id.data(), mat_id.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    int32_t rc = upload_index(h, idxX, nele * 12, 0, &g.idxX);
+    if (rc) return rc;
+    if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU); if (rc) return rc; }
+    for (int i = 0; i < 12; ++i) g.scaleX[i] = scaleX[i];
+    if (udof) for (int i = 0; i < 3; ++i) g.scaleU[i] = scaleU[i];
+    h->groups.push_back(g);
+    if (ieletyp_out) *ieletyp_out = (int32_t)h->groups.size();
+    return MB_OK;
+}
+
+int32_t mb_add_host_elements(mb_handle* h, int64_t nele, int32_t nx, const int64_t* idxX, int32_t* ieletyp_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared, "groups must be added before prepare");
+    ARG(nele >= 0 && nx >= 0 && nx <= 64 && (idxX || nele * nx == 0), "bad argument");
+    CK(cudaSetDevice(h->device));
+    Group g;
+    g.kind = G_HOST; g.nele = nele; g.nx = nx;
+    int32_t rc = upload_index(h, idxX, nele * nx, 0, &g.idxX);
+    if (rc) return rc;
+    h->groups.push_back(g);
+    if (ieletyp_out) *ieletyp_out = (int32_t)h->groups.size();
+    return MB_OK;
+}
+
+int32_t mb_set_host_elements(mb_handle* h, int32_t ieletyp, const double* Re, const double* Rp, const double* Ke) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared, "call mb_sweepx_prepare first");
+    ARG(ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size() && h->groups[ieletyp - 1].kind == G_HOST, "not a host-evaluated element type");
+    CK(cudaSetDevice(h->device));
+    const Group& g = h->groups[ieletyp - 1];
+    const size_t nv = (size_t)g.nele * g.nx, nk = nv * g.nx;
+    if (Re) CK(cudaMemcpyAsync(h->Re + g.vec_base, Re, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->Re + g.vec_base, 0, nv * sizeof(double), h->stream));
+    if (Rp) CK(cudaMemcpyAsync(h->Rp + g.vec_base, Rp, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->Rp + g.vec_base, 0, nv * sizeof(double), h->stream));
+    if (Ke) CK(cudaMemcpyAsync(h->Ke + g.pair_base, Ke, nk * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->Ke + g.pair_base, 0, nk * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
+
+int32_t mb_set_ndofU(mb_handle* h, int64_t ndofU) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared && ndofU >= 0, "set ndofU before prepare");
+    h->ndofU = ndofU;
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------ prepare
+int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared, "already prepared");
+    ARG(ndofX >= 1 && ndofX < INT32_MAX, "ndofX out of range");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->ndofX = ndofX;
+    int64_t npair = 0, nvec = 0;
+    for (Group& g : h->groups) { g.pair_base = npair; g.vec_base = nvec; npair += g.nele * g.nx * g.nx; nvec += g.nele * g.nx; }
+    if (npair >= (int64_t)UINT32_MAX) { h->err = "more than 2^32 element-matrix entries on one device"; return MB_ERR_TOOBIG; }
+    h->npair = npair; h->nvec = nvec;
+
+    CK(dalloc(h, &h->X0, ndofX)); CK(dalloc(h, &h->X1, ndofX)); CK(dalloc(h, &h->X2, ndofX)); CK(dalloc(h, &h->U0, h->ndofU));
+    CK(cudaMemsetAsync(h->X0, 0, ndofX * sizeof(double), st)); CK(cudaMemsetAsync(h->X1, 0, ndofX * sizeof(double), st));
+    CK(cudaMemsetAsync(h->X2, 0, ndofX * sizeof(double), st)); CK(cudaMemsetAsync(h->U0, 0, (h->ndofU > 0 ? h->ndofU : 1) * sizeof(double), st));
+    CK(dalloc(h, &h->Ll, ndofX));
+    CK(dalloc(h, &h->Ke, npair)); CK(dalloc(h, &h->Re, nvec)); CK(dalloc(h, &h->Rp, nvec));
+    CK(cudaMemsetAsync(h->Ke, 0, (npair > 0 ? npair : 1) * sizeof(double), st));
+    CK(cudaMemsetAsync(h->Re, 0, (nvec > 0 ? nvec : 1) * sizeof(double), st));
+    CK(cudaMemsetAsync(h->Rp, 0, (nvec > 0 ? nvec : 1) * sizeof(double), st));
+    CK(dalloc(h, &h->asm2, npair)); CK(dalloc(h, &h->src, npair));
+    CK(dalloc(h, &h->colptr0, ndofX + 1));
+    CK(dalloc(h, &h->vstart, ndofX + 1)); CK(dalloc(h, &h->vsrc, nvec));
+    CK(cudaMemsetAsync(h->colptr0, 0, (ndofX + 1) * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(h->vstart, 0, (ndofX + 1) * sizeof(uint32_t), st));
+
+    // ---- matrix pattern: sort (j,i) pairs, unique, number them (asmmat!, src/Assemble.jl:373-448)
+    int64_t nnz = 0;
+    if (npair > 0) {
+        uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *inz = nullptr;
+        CK(dalloc(h, &keys, npair)); CK(dalloc(h, &keys2, npair)); CK(dalloc(h, &vals, npair)); CK(dalloc(h, &inz, npair));
+        for (const Group& g : h->groups) {
+            const int64_t n = g.nele * g.nx * g.nx;
+            if (n == 0) continue;
+            make_pair_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(g.nele, g.nx, g.idxX, (uint64_t)ndofX, keys, vals, (uint32_t)g.pair_base);
+            h->launches++;
+        }
+        int end_bit = 1; while (end_bit < 64 && ((uint64_t)ndofX * (uint64_t)ndofX) >> end_bit) ++end_bit;
+        void* tmp = nullptr; size_t tmpsz = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, h->src, npair, 0, end_bit, st));
+        CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, h->src, npair, 0, end_bit, st));
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+        // inclusive scan of "new non-zero" flags → inz per sorted pair
+        cub::CountingInputIterator<int64_t> cnt(0);
+        cub::TransformInputIterator<uint32_t, KeyFlag, cub::CountingInputIterator<int64_t>> flags(cnt, KeyFlag{keys2});
+        tmp = nullptr; tmpsz = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmpsz, flags, inz, npair, st));
+        CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+        CK(cub::DeviceScan::InclusiveSum(tmp, tmpsz, flags, inz, npair, st));
+        uint32_t last = 0;
+        CK(cudaMemcpyAsync(&last, inz + (npair - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+        nnz = last;
+        CK(dalloc(h, &h->rowval0, nnz)); CK(dalloc(h, &h->cstart, nnz + 1));
+        finish_pattern_kernel<<<nblk(npair, 256), 256, 0, st>>>(npair, keys2, h->src, inz, (uint64_t)ndofX, h->asm2, h->rowval0, h->cstart);
+        colptr_kernel<<<nblk(nnz, 256), 256, 0, st>>>(nnz, keys2, h->cstart, (uint64_t)ndofX, h->colptr0);
+        h->launches += 2;
+        CK(cudaStreamSynchronize(st));
+        dfree(h, keys); dfree(h, keys2); dfree(h, vals); dfree(h, inz);
+    } else {
+        CK(dalloc(h, &h->rowval0, 1)); CK(dalloc(h, &h->cstart, 1));
+        CK(cudaMemsetAsync(h->cstart, 0, sizeof(uint32_t), st));
+    }
+    h->nnz = nnz;
+    CK(dalloc(h, &h->nzval, nnz));
+
+    // ---- vector map: contributors of every dof in element order (asmvec!, src/Assemble.jl:340-357)
+    if (nvec > 0) {
+        uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
+        CK(dalloc(h, &keys, nvec)); CK(dalloc(h, &keys2, nvec)); CK(dalloc(h, &vals, nvec));
+        for (const Group& g : h->groups) {
+            const int64_t n = g.nele * g.nx;
+            if (n == 0) continue;
+            make_vec_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(n, g.idxX, keys, vals, (uint32_t)g.vec_base);
+            h->launches++;
+        }
+        int end_bit = 1; while (end_bit < 32 && ((uint64_t)ndofX >> end_bit)) ++end_bit;
+        void* tmp = nullptr; size_t tmpsz = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, h->vsrc, nvec, 0, end_bit, st));
+        CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, h->vsrc, nvec, 0, end_bit, st));
+        vstart_kernel<<<nblk(nvec, 256), 256, 0, st>>>(nvec, keys2, ndofX, h->vstart);
+        h->launches++;
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+        dfree(h, keys); dfree(h, keys2); dfree(h, vals);
+    }
+    CK(cudaGetLastError());
+    h->prepared = true;
+    if (nnz_out) *nnz_out = nnz;
+    return MB_OK;
+}
+
+int32_t mb_sweepx_get_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && colptr && rowval, "not prepared / null");
+    CK(cudaSetDevice(h->device));
+    // widen on the device in chunks, 1-based like SparseMatrixCSC
+    const int64_t CH = 1 << 24;
+    int64_t* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, CH * sizeof(int64_t)));
+    auto widen = [&](const int32_t* in, int64_t n, int64_t* out) -> cudaError_t {
+        for (int64_t o = 0; o < n; o += CH) {
+            const int64_t m = (n - o < CH) ? n - o : CH;
+            widen_plus1_kernel<<<nblk(m, 256), 256, 0, h->stream>>>(m, in + o, buf, 1);
+            h->launches++;
+            cudaError_t e = cudaMemcpyAsync(out + o, buf, m * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    cudaError_t e1 = widen(h->colptr0, h->ndofX + 1, colptr);
+    cudaError_t e2 = (e1 == cudaSuccess) ? widen(h->rowval0, h->nnz, rowval) : e1;
+    cudaFree(buf);
+    CK(e2);
+    return MB_OK;
+}
+
+int32_t mb_sweepx_get_asm(mb_handle* h, int32_t ieletyp, int64_t* asm1, int64_t* asm2) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size(), "bad element type / not prepared");
+    CK(cudaSetDevice(h->device));
+    const Group& g = h->groups[ieletyp - 1];
+    const int64_t CH = 1 << 24;
+    int64_t* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, CH * sizeof(int64_t)));
+    auto widen = [&](const int32_t* in, int64_t n, int64_t* out, int add) -> cudaError_t {
+        for (int64_t o = 0; o < n; o += CH) {
+            const int64_t m = (n - o < CH) ? n - o : CH;
+            widen_plus1_kernel<<<nblk(m, 256), 256, 0, h->stream>>>(m, in + o, buf, add);
+            h->launches++;
+            cudaError_t e = cudaMemcpyAsync(out + o, buf, m * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    cudaError_t e = cudaSuccess;
+    if (asm1) e = widen(g.idxX, g.nele * g.nx, asm1, 1);                                   // asm[1]: X-dof group is the identity map
+    if (asm2 && e == cudaSuccess) e = widen(h->asm2 + g.pair_base, g.nele * g.nx * g.nx, asm2, 0);
+    cudaFree(buf);
+    CK(e);
+    return MB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------ assemble
+template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group& g, const BeamGroupDev& gd, const StateDev& sd, const NewmarkDev& nm,
+                                                       unsigned long long nanbase) {
+    BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->beamW, h->stream};
+    launch_beam<ND, STEP>(a);
+    h->launches++;
+}
+
+static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm) {
+    const bool step = (mission == 0) && OX > 0;
+    StateDev sd{h->X0, h->X1, h->X2, h->ndofU > 0 ? h->U0 : nullptr};
+    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+        const Group& g = h->groups[ig];
+        if (g.nele == 0) continue;
+        const unsigned long long nanbase = ((unsigned long long)ig) << 40;
+        if (g.kind == G_BEAM) {
+            BeamGroupDev gd;
+            gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+            for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
+            for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+            if (OX == 0) launch_beam_w<1, false>(h, g, gd, sd, nm, nanbase);
+            else if (OX == 1) { if (step) launch_beam_w<2, true>(h, g, gd, sd, nm, nanbase); else launch_beam_w<2, false>(h, g, gd, sd, nm, nanbase); }
+            else { if (step) launch_beam_w<3, true>(h, g, gd, sd, nm, nanbase); else launch_beam_w<3, false>(h, g, gd, sd, nm, nanbase); }
+        }
+        // G_HOST: contributions were uploaded by mb_set_host_elements
+    }
+    return MB_OK;
+}
+static void launch_gather(mb_handle* h, bool step) {
+    if (h->nnz > 0) { gather_nz_kernel<<<nblk(h->nnz, 256), 256, 0, h->stream>>>(h->nnz, h->cstart, h->src, h->Ke, h->nzval); h->launches++; }
+    gather_vec_kernel<<<nblk(h->ndofX, 256), 256, 0, h->stream>>>(h->ndofX, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll);
+    h->launches++;
+}
+
+extern "C" {
+
+int32_t mb_sweepx_assemble_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared, "call mb_sweepx_prepare first");
+    ARG(OX >= 0 && OX <= 2 && (mission == 0 || mission == 1) && newmark, "bad OX / mission / newmark");
+    CK(cudaSetDevice(h->device));
+    (void)t;
+    NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
+    CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
+    int32_t rc = launch_elements(h, OX, mission, nm);
+    if (rc) return rc;
+    launch_gather(h, mission == 0 && OX > 0);
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+
+int32_t mb_sync(mb_handle* h, mb_errinfo* where) {
+    if (!h) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->nanflag_host, h->nanflag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (where) { where->kind = 0; where->ieletyp = 0; where->iele = 0; }
+    const unsigned long long f = *h->nanflag_host;
+    if (f != ~0ULL) {
+        if (where) { where->kind = MB_ERR_NAN; where->ieletyp = (int32_t)(f >> 40) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; }
+        h->err = "residual(...) returned NaN in R, FB or derivatives";
+        return MB_ERR_NAN;
+    }
+    return MB_OK;
+}
+
+int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const double* X0, const double* X1, const double* X2,
+                           const double* U0, double t, const double* newmark, double* Llambda, double* nzval, mb_errinfo* where) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared, "call mb_sweepx_prepare first");
+    ARG(X0 && (OX < 1 || X1) && (OX < 2 || X2), "state vectors missing for this OX");
+    CK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)h->ndofX * sizeof(double);
+    CK(cudaMemcpyAsync(h->X0, X0, nb, cudaMemcpyHostToDevice, h->stream));
+    if (OX >= 1) CK(cudaMemcpyAsync(h->X1, X1, nb, cudaMemcpyHostToDevice, h->stream));
+    if (OX >= 2) CK(cudaMemcpyAsync(h->X2, X2, nb, cudaMemcpyHostToDevice, h->stream));
+    if (U0 && h->ndofU > 0) CK(cudaMemcpyAsync(h->U0, U0, (size_t)h->ndofU * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int32_t rc = mb_sweepx_assemble_dev(h, OX, mission, t, newmark);
+    if (rc) return rc;
+    if (Llambda) CK(cudaMemcpyAsync(Llambda, h->Ll, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (nzval && h->nnz > 0) CK(cudaMemcpyAsync(nzval, h->nzval, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return mb_sync(h, where);
+}
+
+int32_t mb_get_device_ptrs(mb_handle* h, mb_dev_ptrs* out) {
+    if (!h || !out) return MB_ERR_ARG;
+    ARG(h->prepared, "not prepared");
+    out->X0 = h->X0; out->X1 = h->X1; out->X2 = h->X2; out->U0 = h->U0; out->Llambda = h->Ll; out->nzval = h->nzval;
+    out->colptr0 = h->colptr0; out->rowval0 = h->rowval0; out->ndofX = h->ndofX; out->ndofU = h->ndofU; out->nnz = h->nnz;
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------ measurement
+int32_t mb_sweepx_time_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark, int32_t reps, float* ms) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && reps >= 1 && ms && newmark, "bad argument");
+    CK(cudaSetDevice(h->device));
+    (void)t;
+    NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    float tel = 0, tga = 0;
+    CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
+    for (int r = 0; r < reps; ++r) {
+        CK(cudaEventRecord(e0, h->stream));
+        launch_elements(h, OX, mission, nm);
+        CK(cudaEventRecord(e1, h->stream));
+        launch_gather(h, mission == 0 && OX > 0);
+        CK(cudaEventRecord(e2, h->stream));
+        CK(cudaEventSynchronize(e2));
+        float a, b;
+        CK(cudaEventElapsedTime(&a, e0, e1)); CK(cudaEventElapsedTime(&b, e1, e2));
+        tel += a; tga += b;
+    }
+    ms[0] = tel / reps; ms[1] = tga / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+
+int32_t mb_measure_fp64_tflops(mb_handle* h, double* tflops) {
+    if (!h || !tflops) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, h->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double* out = nullptr;
+    CK(cudaMalloc((void**)&out, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CK(cudaEventRecord(e0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(out, iters);
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float msv; CK(cudaEventElapsedTime(&msv, e0, e1));
+        if (r > 0 && msv < best) best = msv;
+        h->launches++;
+    }
+    *tflops = 2.0 * 8.0 * iters * (double)threads * blocks / (best * 1e-3) / 1e12;
+    cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return MB_OK;
+}
+
+int32_t mb_measure_copy_gbs(mb_handle* h, double* gbs) {
+    if (!h || !gbs) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    const int64_t n = (int64_t)1 << 27;   // 2 GiB of double2 in, 2 GiB out
+    double2 *a = nullptr, *b = nullptr;
+    CK(cudaMalloc((void**)&a, n * sizeof(double2))); CK(cudaMalloc((void**)&b, n * sizeof(double2)));
+    CK(cudaMemsetAsync(a, 0, n * sizeof(double2), h->stream));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, h->device));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        CK(cudaEventRecord(e0, h->stream));
+        copy_kernel<<<prop.multiProcessorCount * 16, 512, 0, h->stream>>>(a, b, n);
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float msv; CK(cudaEventElapsedTime(&msv, e0, e1));
+        if (r > 0 && msv < best) best = msv;
+        h->launches++;
+    }
+    *gbs = 2.0 * n * sizeof(double2) / (best * 1e-3) / 1e9;
+    cudaFree(a); cudaFree(b); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return MB_OK;
+}
+
+// not yet implemented element types: fail loudly rather than silently skipping physics
+int32_t mb_add_bar3d(mb_handle* h, int64_t, const double*, int32_t, const int64_t*, const int64_t*, const double*, const double*, int32_t*) {
+    if (h) h->err = "Bar3D device kernel not built into this library yet";
+    return MB_ERR_STATE;
+}
+int32_t mb_add_soilcontact(mb_handle* h, int64_t, const double*, const int64_t*, const double*, int32_t*) {
+    if (h) h->err = "SoilContact device kernel not built into this library yet";
+    return MB_ERR_STATE;
+}
+
+}  // extern "C"

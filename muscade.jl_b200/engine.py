@@ -1,0 +1,136 @@
+"""Thin object wrapper over the C ABI (include/muscade_b200.h): one `Engine` = one `mb_handle` = one GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ErrInfo, DevPtrs, check, ptr, MuscadeB200Error
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.L = _lib.lib()
+        self.h = C.c_void_p()
+        rc = self.L.mb_create(int(device), C.byref(self.h))
+        if rc != _lib.MB_OK:
+            self.h = None
+            check(None, rc)
+        self.groups = []          # (kind, nele, nx)
+        self.ndofX = 0
+        self.nnz = 0
+
+    def close(self):
+        if self.h:
+            self.L.mb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- element types -------------------------------------------------------------------------------------------------
+    def add_eulerbeam3d(self, eleobj, idxX, scaleX, udof=False, idxU=None, scaleU=None):
+        """eleobj (nele,69); idxX (nele,12) Int64 1-based = dis.index[iele].X; scaleX (12,)"""
+        eleobj = _f64(eleobj); idxX = _i64(idxX); scaleX = _f64(scaleX)
+        nele = eleobj.shape[0]
+        assert eleobj.shape == (nele, 69) and idxX.shape == (nele, 12)
+        idxU = _i64(idxU) if udof else None
+        scaleU = _f64(scaleU) if udof else None
+        ityp = C.c_int32()
+        check(self.h, self.L.mb_add_eulerbeam3d(self.h, nele, ptr(eleobj), int(bool(udof)), ptr(idxX), ptr(idxU), ptr(scaleX), ptr(scaleU), C.byref(ityp)))
+        self.groups.append(("eulerbeam3d", nele, 12))
+        return ityp.value
+
+    def add_host_elements(self, idxX):
+        idxX = _i64(idxX)
+        nele, nx = idxX.shape
+        ityp = C.c_int32()
+        check(self.h, self.L.mb_add_host_elements(self.h, nele, nx, ptr(idxX), C.byref(ityp)))
+        self.groups.append(("host", nele, nx))
+        return ityp.value
+
+    def set_host_elements(self, ityp, Re, Rp, Ke):
+        """Re (nele,nx), Rp (nele,nx) or None, Ke (nele,nx*nx) with entry i+nx*j (column-major element matrix)."""
+        check(self.h, self.L.mb_set_host_elements(self.h, ityp, ptr(_f64(Re)), ptr(_f64(Rp)), ptr(_f64(Ke))))
+
+    def set_ndofU(self, n):
+        check(self.h, self.L.mb_set_ndofU(self.h, int(n)))
+
+    # ---- SweepX -------------------------------------------------------------------------------------------------------------
+    def sweepx_prepare(self, ndofX):
+        nnz = C.c_int64()
+        check(self.h, self.L.mb_sweepx_prepare(self.h, int(ndofX), C.byref(nnz)))
+        self.ndofX = int(ndofX); self.nnz = nnz.value
+        return self.nnz
+
+    def sweepx_pattern(self):
+        colptr = np.zeros(self.ndofX + 1, np.int64); rowval = np.zeros(self.nnz, np.int64)
+        check(self.h, self.L.mb_sweepx_get_pattern(self.h, colptr, rowval))
+        return colptr, rowval
+
+    def sweepx_asm(self, ityp, want2=True):
+        _, nele, nx = self.groups[ityp - 1]
+        asm1 = np.zeros((nele, nx), np.int64)
+        asm2 = np.zeros((nele, nx * nx), np.int64) if want2 else None
+        check(self.h, self.L.mb_sweepx_get_asm(self.h, ityp, ptr(asm1), ptr(asm2)))
+        return asm1, asm2
+
+    def sweepx_assemble(self, OX, mission, X, newmark, U0=None, t=0., Llambda=None, nzval=None, dbg=None):
+        """assemble!{mission}: host state in, host Lλ / nzval out (pass preallocated arrays to avoid allocation)."""
+        X = [_f64(x) for x in X]
+        if Llambda is None:
+            Llambda = np.empty(self.ndofX)
+        if nzval is None:
+            nzval = np.empty(self.nnz)
+        where = ErrInfo()
+        rc = self.L.mb_sweepx_assemble(self.h, OX, {"step": 0, "iter": 1}[mission], ptr(X[0]), ptr(X[1]) if OX >= 1 else None,
+                                       ptr(X[2]) if OX >= 2 else None, ptr(_f64(U0)), float(t), _f64(newmark), ptr(Llambda), ptr(nzval),
+                                       C.byref(where))
+        if rc == _lib.MB_ERR_NAN:
+            d = dict(dbg or {}); d.update(ieletyp=where.ieletyp, iele=where.iele)
+            raise MuscadeB200Error("residual(...) returned NaN in R, FB or derivatives", d)
+        check(self.h, rc, dbg)
+        return Llambda, nzval
+
+    def sweepx_assemble_dev(self, OX, mission, newmark, t=0.):
+        check(self.h, self.L.mb_sweepx_assemble_dev(self.h, OX, {"step": 0, "iter": 1}[mission], float(t), _f64(newmark)))
+
+    def sync(self):
+        where = ErrInfo()
+        rc = self.L.mb_sync(self.h, C.byref(where))
+        if rc == _lib.MB_ERR_NAN:
+            raise MuscadeB200Error("residual(...) returned NaN in R, FB or derivatives", dict(ieletyp=where.ieletyp, iele=where.iele))
+        check(self.h, rc)
+
+    def device_ptrs(self):
+        p = DevPtrs()
+        check(self.h, self.L.mb_get_device_ptrs(self.h, C.byref(p)))
+        return p
+
+    def time_dev(self, OX, mission, newmark, reps=3):
+        ms = np.zeros(2, np.float32)
+        check(self.h, self.L.mb_sweepx_time_dev(self.h, OX, {"step": 0, "iter": 1}[mission], 0., _f64(newmark), reps, ms))
+        return float(ms[0]), float(ms[1])
+
+    def fp64_tflops(self):
+        v = C.c_double()
+        check(self.h, self.L.mb_measure_fp64_tflops(self.h, C.byref(v)))
+        return v.value
+
+    def copy_gbs(self):
+        v = C.c_double()
+        check(self.h, self.L.mb_measure_copy_gbs(self.h, C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        return int(self.L.mb_launch_count(self.h))

@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference toolbox element *constructors* (setup time, numpy-vectorised over elements).
+
+The element physics (`residual`) lives in the CUDA kernels (csrc/beam_math.cuh …); here are only the as-meshed data the
+kernels consume, laid out exactly like the reference's isbits structs so the same arrays could come from Julia.
+"""
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------ EulerBeam3D
+MAT_FIELDS = ("EA", "EI2", "EI3", "GJ", "mu", "iota1", "w", "Ca1", "Cl1", "Cq1", "Ca2", "Cl2", "Cq2", "Ca3", "Cl3", "Cq3")
+_MAT_ALIASES = {"EI₂": "EI2", "EI₃": "EI3", "μ": "mu", "ι₁": "iota1", "Ca₁": "Ca1", "Cl₁": "Cl1", "Cq₁": "Cq1", "Ca₂": "Ca2",
+                "Cl₂": "Cl2", "Cq₂": "Cq2", "Ca₃": "Ca3", "Cl₃": "Cl3", "Cq₃": "Cq3"}
+
+
+def BeamCrossSection(**kw):
+    """BeamCrossSection(;EA,EI₂,EI₃,GJ,μ,ι₁,w=0.,Ca₁=0.,…)  toolbox/BeamElement.jl:6-25 → 16 Float64 in field order."""
+    m = np.zeros(16)
+    for k, v in kw.items():
+        m[MAT_FIELDS.index(_MAT_ALIASES.get(k, k))] = v
+    for req in ("EA", "EI2", "EI3", "GJ", "mu", "iota1"):
+        if _MAT_ALIASES.get(req, req) not in [_MAT_ALIASES.get(k, k) for k in kw]:
+            raise TypeError("BeamCrossSection: keyword argument %s not assigned" % req)
+    return m
+
+
+BEAM_STRUCT_LEN = 69  # cₘ3 rₘ9 ζgp4 ζnod2 tgₘ3 tgₑ3 yₐ4 yᵤ4 yᵥ4 κₐ4 κᵤ4 κᵥ4 L dL4 mat16   (toolbox/BeamElement.jl:87-103)
+
+
+def eulerbeam3d_structs(c1, c2, mat, orient2=(0., 1., 0.)):
+    """EulerBeam3D{Udof}(nod;mat,orient2) for many elements at once  (toolbox/BeamElement.jl:121-148).
+
+    c1, c2: (nele,3) node coordinates.  Returns (nele,69) Float64, the memory image of Vector{EulerBeam3D{BeamCrossSection,·}}."""
+    c1 = np.atleast_2d(np.asarray(c1, float)); c2 = np.atleast_2d(np.asarray(c2, float))
+    n = c1.shape[0]
+    out = np.zeros((n, BEAM_STRUCT_LEN))
+    cm = (c1 + c2) / 2
+    tgm = c2 - c1
+    L = np.sqrt((tgm[:, 0] * tgm[:, 0] + tgm[:, 1] * tgm[:, 1]) + tgm[:, 2] * tgm[:, 2])
+    t = tgm / L[:, None]
+    o2 = np.asarray(orient2, float)
+    o2 = o2 / np.sqrt((o2[0] * o2[0] + o2[1] * o2[1]) + o2[2] * o2[2])
+    d = (o2[0] * t[:, 0] + o2[1] * t[:, 1]) + o2[2] * t[:, 2]
+    nn_ = o2[None, :] - t * d[:, None]
+    nn = np.sqrt((nn_[:, 0] * nn_[:, 0] + nn_[:, 1] * nn_[:, 1]) + nn_[:, 2] * nn_[:, 2])
+    if not np.all(nn > 1e-3):
+        raise ValueError("Provide a 'orient' input that is not nearly parallel to the element")
+    nv = nn_ / nn[:, None]
+    b = np.stack([t[:, 1] * nv[:, 2] - t[:, 2] * nv[:, 1], t[:, 2] * nv[:, 0] - t[:, 0] * nv[:, 2], t[:, 0] * nv[:, 1] - t[:, 1] * nv[:, 0]], axis=1)
+    out[:, 0:3] = cm
+    out[:, 3:6] = t; out[:, 6:9] = nv; out[:, 9:12] = b          # SMatrix(t...,n...,b...): column-major
+    s65 = np.sqrt(6. / 5); s30 = np.sqrt(30.)
+    zgp = np.array([-1. / 2 * np.sqrt(3. / 7 + 2. / 7 * s65), -1. / 2 * np.sqrt(3. / 7 - 2. / 7 * s65),
+                    +1. / 2 * np.sqrt(3. / 7 - 2. / 7 * s65), +1. / 2 * np.sqrt(3. / 7 + 2. / 7 * s65)])
+    out[:, 12:16] = zgp
+    out[:, 16:18] = (-0.5, 0.5)
+    out[:, 18:21] = tgm
+    out[:, 21] = L
+    out[:, 24:28] = 2 * zgp
+    out[:, 28:32] = -4 * (zgp * zgp * zgp) + 3 * zgp
+    out[:, 32:36] = ((zgp * zgp) - 1. / 4)[None, :] * L[:, None]
+    out[:, 36:40] = (2. / L)[:, None]
+    out[:, 40:44] = (-24 * zgp)[None, :] / (L * L)[:, None]
+    out[:, 44:48] = (2. / L)[:, None]
+    out[:, 48] = L
+    out[:, 49] = L / 2 * (18 - s30) / 36; out[:, 50] = L / 2 * (18 + s30) / 36
+    out[:, 51] = L / 2 * (18 + s30) / 36; out[:, 52] = L / 2 * (18 - s30) / 36
+    out[:, 53:69] = np.asarray(mat, float)
+    return out
+
+
+class ElementType:
+    """Base of the Python stand-ins for `E<:AbstractElement` (src/ModelDescription.jl:14).  Subclasses give `doflist()`
+    (src/ElementAPI.jl:99), a vectorised constructor `construct(coords, **kw)` and a `typekey` that plays the role of
+    the concrete Julia type (one element *type* per distinct key, src/ModelDescription.jl:205-213)."""
+    kind = "host"
+
+    @classmethod
+    def doflist(cls, **kw):
+        raise NotImplementedError("method 'doflist' must be provided for elements of type %s" % cls.__name__)
+
+
+class EulerBeam3D(ElementType):
+    kind = "eulerbeam3d"
+
+    @classmethod
+    def doflist(cls, Udof=False, **kw):
+        inod = (1,) * 6 + (2,) * 6
+        clas = ("X",) * 12
+        field = ("t1", "t2", "t3", "r1", "r2", "r3") * 2
+        if Udof:
+            inod += (3, 3, 3); clas += ("U",) * 3; field += ("t1", "t2", "t3")
+        return inod, clas, field
+
+    @classmethod
+    def typekey(cls, Udof=False, **kw):
+        return ("EulerBeam3D", "BeamCrossSection", bool(Udof))
+
+    @classmethod
+    def construct(cls, coords, mat, orient2=(0., 1., 0.), Udof=False):
+        return eulerbeam3d_structs(coords[:, 0, :], coords[:, 1, :], mat, orient2)
+
+
+# ------------------------------------------------------------------------------------------------ boundary elements (host evaluated)
+class Hold(ElementType):
+    """Hold(nod;field,λfield=Symbol(:λ,field)) = DofConstraint{:X,1,…} with gap(v,t)=v[1], mode=equal (src/BasicElements.jl:484-488).
+    residual (:425-438): R = (−λ, −x), ∂R/∂X = [[0,−1],[−1,0]]."""
+
+    @classmethod
+    def doflist(cls, field, λfield=None, **kw):
+        return (1, 1), ("X", "X"), (field, λfield or "λ" + field)
+
+    @classmethod
+    def typekey(cls, field, λfield=None, **kw):
+        return ("DofConstraint", "X", 1, 0, 0, (1,), (field,), 1, λfield or "λ" + field, "Hold.gap", "equal")
+
+    @classmethod
+    def construct(cls, coords, **kw):
+        return np.zeros((coords.shape[0], 0))
+
+    @staticmethod
+    def residual(eleobj, X, t):
+        """X: (nder, nele, 2) element dofs. Returns R (nele,2), dR/dX0 (nele,2,2), dR/dX1, dR/dX2 (None = zero)."""
+        x = X[0]
+        R = np.stack([-x[:, 1], -x[:, 0]], axis=1)
+        K = np.zeros((x.shape[0], 2, 2)); K[:, 0, 1] = -1.; K[:, 1, 0] = -1.
+        return R, K, None, None
+
+
+class DofLoad(ElementType):
+    """DofLoad(nod;field,value)  (src/BasicElements.jl:275-284): R = (−value(t)); plain Float64 residual ⇒ no tangent."""
+
+    @classmethod
+    def doflist(cls, field, **kw):
+        return (1,), ("X",), (field,)
+
+    @classmethod
+    def typekey(cls, field, value, **kw):
+        return ("DofLoad", field, id(value))
+
+    @classmethod
+    def construct(cls, coords, field, value, args=()):
+        return np.zeros((coords.shape[0], 0)), dict(value=value, args=args)
+
+    @staticmethod
+    def residual(extra, X, t):
+        n = X[0].shape[0]
+        F = float(extra["value"](t, *extra["args"]))
+        return np.full((n, 1), -F), np.zeros((n, 1, 1)), None, None

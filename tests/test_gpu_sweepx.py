@@ -1,0 +1,89 @@
+"""GPU parity, SweepX path: CUDA engine (through the C ABI) vs the oracle on the same seeded inputs.
+
+Bars: integer structures bit-exact (colptr, rowval, asm maps); floats max|Δ| ≤ 1e-12·max|ref| per assembled array
+(SURVEY.md §8d "Parity measure"; north_star: 1e-12 relative in FP64)."""
+import numpy as np
+import pytest
+
+from oracle import elements as OE
+from oracle import pattern as OP
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b, floor=0.):
+    """max|a-b| / max(max|b|, floor).  For the gradient Lλ the floor is max|nzval|: at an equilibrium state (e.g. all-zero)
+    Lλ is pure round-off of terms of the tangent's magnitude, and a ratio of two noises says nothing."""
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-300)
+
+
+def oracle_assemble(eleobj, idx, ndof, OX, mission, X, scale, nm):
+    dis = [dict(X=idx, U=np.zeros((idx.shape[0], 0), np.int64), A=np.zeros((idx.shape[0], 0), np.int64))]
+    asm1, asm2, colptr, rowval = OP.prepare_sweepx(dis, ndof, 0, 0)
+    L = np.zeros(ndof); nz = np.zeros(len(rowval))
+    OE.sweepx_assemble_beams(eleobj, idx, asm1[0].T, asm2[0].T, OX, mission, X, scale, nm, L, nz)
+    return asm1[0].T, asm2[0].T, colptr, rowval, L, nz
+
+
+@pytest.mark.parametrize("OX,mission", [(0, "iter"), (1, "iter"), (1, "step"), (2, "iter"), (2, "step")])
+@pytest.mark.parametrize("zero", [False, True])
+def test_chain_parity(mb, engine_factory, OX, mission, zero):
+    N = 500
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=OX > 0)
+    X = mb.synthetic.state(ndof, nder=OX + 1, zero=zero)
+    scale = np.ones(12)
+    nm = mb.synthetic.newmark_coefficients(OX, 0.3)
+    eng = engine_factory()
+    ityp = eng.add_eulerbeam3d(eleobj, idx, scale)
+    nnz = eng.sweepx_prepare(ndof)
+    a1, a2, colptr, rowval, Lref, nzref = oracle_assemble(eleobj, idx, ndof, OX, mission, X, scale, nm)
+    assert nnz == len(rowval) == 108 * N + 36
+    cp, rv = eng.sweepx_pattern()
+    assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    g1, g2 = eng.sweepx_asm(ityp)
+    assert np.array_equal(g1, a1) and np.array_equal(g2, a2)
+    L, nz = eng.sweepx_assemble(OX, mission, X, nm)
+    assert rel(L, Lref, np.abs(nzref).max()) <= TOL, rel(L, Lref)
+    assert rel(nz, nzref) <= TOL, rel(nz, nzref)
+    # determinism: bit-identical on repetition (no atomics in the reduction)
+    L2, nz2 = eng.sweepx_assemble(OX, mission, X, nm)
+    assert np.array_equal(L, L2) and np.array_equal(nz, nz2)
+
+
+def test_scaled_and_shuffled(mb, engine_factory):
+    """non-unit scales (X:(t=10,r=1)) and a non-chain dof numbering / element order"""
+    N = 300
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=True)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(ndof)
+    idx = (perm[idx - 1] + 1).astype(np.int64)
+    order = rng.permutation(N)
+    eleobj, idx = eleobj[order], idx[order]
+    X = [x[np.argsort(perm)] * 0 + x for x in mb.synthetic.state(ndof, nder=3)]
+    scale = np.array([10., 10., 10., 1., 1., 1.] * 2)
+    nm = mb.synthetic.newmark_coefficients(2, 0.3)
+    eng = engine_factory()
+    ityp = eng.add_eulerbeam3d(eleobj, idx, scale)
+    eng.sweepx_prepare(ndof)
+    a1, a2, colptr, rowval, Lref, nzref = oracle_assemble(eleobj, idx, ndof, 2, "step", X, scale, nm)
+    cp, rv = eng.sweepx_pattern()
+    assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    g1, g2 = eng.sweepx_asm(ityp)
+    assert np.array_equal(g1, a1) and np.array_equal(g2, a2)
+    L, nz = eng.sweepx_assemble(2, "step", X, nm)
+    assert rel(L, Lref, np.abs(nzref).max()) <= TOL and rel(nz, nzref) <= TOL
+
+
+def test_nan_reported_with_location(mb, engine_factory):
+    """NaN guard of getresidual (src/Assemble.jl:630): first offending element, 1-based, deterministic"""
+    N = 64
+    eleobj, idx, ndof = mb.synthetic.chain(N)
+    X = mb.synthetic.state(ndof)
+    X[0][6 * 40 + 1] = np.nan
+    eng = engine_factory()
+    eng.add_eulerbeam3d(eleobj, idx, np.ones(12))
+    eng.sweepx_prepare(ndof)
+    with pytest.raises(mb.MuscadeB200Error) as ei:
+        eng.sweepx_assemble(0, "iter", X, mb.synthetic.newmark_coefficients(0, 0.))
+    assert ei.value.dbg["ieletyp"] == 1 and ei.value.dbg["iele"] == 40
