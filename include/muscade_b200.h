@@ -79,6 +79,11 @@ typedef struct { double *X0, *X1, *X2, *U0, *Llambda, *nzval; int32_t *colptr0, 
 int32_t mb_get_device_ptrs(mb_handle* h, mb_dev_ptrs* out);
 int32_t mb_set_ndofU(mb_handle* h, int64_t ndofU);
 
+/* Page-lock / unlock a host array the caller owns (Julia: the Vector behind out.Lλx.nzval), so that the copies inside
+ * mb_sweepx_assemble run at PCIe speed. */
+int32_t mb_host_register(mb_handle* h, void* p, int64_t bytes);
+int32_t mb_host_unregister(mb_handle* h, void* p);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------------------------------------------ */
 /* Times one launch set of the last assemble configuration with CUDA events on the handle's stream:
  *   ms[0] = element kernels, ms[1] = segmented reduction into nzval/Lλ. */

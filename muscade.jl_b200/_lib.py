@@ -52,6 +52,8 @@ SYMBOLS = {
     "mb_measure_fp64_tflops": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_measure_copy_gbs": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_launch_count": (C.c_int64, [H]),
+    "mb_host_register": (C.c_int32, [H, C.c_void_p, C.c_int64]),
+    "mb_host_unregister": (C.c_int32, [H, C.c_void_p]),
 }
 
 

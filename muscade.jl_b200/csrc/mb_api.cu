@@ -533,6 +533,20 @@ int32_t mb_measure_copy_gbs(mb_handle* h, double* gbs) {
     return MB_OK;
 }
 
+int32_t mb_host_register(mb_handle* h, void* p, int64_t bytes) {
+    if (!h) return MB_ERR_ARG;
+    ARG(p && bytes > 0, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+    return MB_OK;
+}
+int32_t mb_host_unregister(mb_handle* h, void* p) {
+    if (!h) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaHostUnregister(p));
+    return MB_OK;
+}
+
 // not yet implemented element types: fail loudly rather than silently skipping physics
 int32_t mb_add_bar3d(mb_handle* h, int64_t, const double*, int32_t, const int64_t*, const int64_t*, const double*, const double*, int32_t*) {
     if (h) h->err = "Bar3D device kernel not built into this library yet";

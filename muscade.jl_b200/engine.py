@@ -132,5 +132,12 @@ class Engine:
         check(self.h, self.L.mb_measure_copy_gbs(self.h, C.byref(v)))
         return v.value
 
+    def pin(self, a):
+        """page-lock a numpy array in place (cudaHostRegister)"""
+        check(self.h, self.L.mb_host_register(self.h, ptr(a), a.nbytes))
+
+    def unpin(self, a):
+        check(self.h, self.L.mb_host_unregister(self.h, ptr(a)))
+
     def launch_count(self):
         return int(self.L.mb_launch_count(self.h))

@@ -43,6 +43,8 @@ def lib():
         L.orc_beams_iter_elementwise.argtypes = [C.c_int64, f64p, i64p, C.c_int, f64p, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p, C.c_int]
         L.orc_beams_iter_elementwise.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
+        L.orc_sweepx_assemble_beams_mt.argtypes = [C.c_int64, f64p, i64p, i64p, i64p, C.c_int, f64p, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p, C.c_int]
+        L.orc_sweepx_assemble_beams_mt.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -160,6 +162,21 @@ def sweepx_assemble_beams(elems, idx, asm1, asm2, OX, mission, X, scaleX, newmar
                                          np.ascontiguousarray(newmark, float), Llambda, nzval)
     if rc:
         raise FloatingPointError("residual(EulerBeam3D,...) returned NaN in R, FB or derivatives (iele=%d)" % rc)
+
+
+def sweepx_assemble_beams_mt(elems, idx, asm1, asm2, OX, X, scaleX, newmark, Llambda, nzval, nthreads):
+    """:iter assembly with the element loop spread over host threads (bench.py --impl reference)"""
+    X = [np.ascontiguousarray(x, float) for x in X]
+    rc = lib().orc_sweepx_assemble_beams_mt(elems.shape[0], np.ascontiguousarray(elems), np.ascontiguousarray(idx, np.int64),
+                                            np.ascontiguousarray(asm1, np.int64), np.ascontiguousarray(asm2, np.int64), OX, X[0],
+                                            _ptr(X[1]) if OX >= 1 else None, _ptr(X[2]) if OX >= 2 else None,
+                                            np.ascontiguousarray(scaleX, float), np.ascontiguousarray(newmark, float), Llambda, nzval, nthreads)
+    if rc:
+        raise FloatingPointError("NaN in %d elements" % rc)
+
+
+def max_threads():
+    return lib().orc_max_threads()
 
 
 def beams_iter_elementwise(elems, idx, OX, X, scaleX, newmark, nthreads=1):

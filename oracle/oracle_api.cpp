@@ -229,6 +229,22 @@ int orc_beams_iter_elementwise(int64_t nele, const double* elems69, const int64_
     return bad;
 }
 
+// Reference algorithm with the element loop parallelised over host threads (NOT something Muscade does: its loop
+// src/Assemble.jl:479 is serial), followed by the serial scatter in element order. Used by `bench.py --impl reference`.
+int orc_sweepx_assemble_beams_mt(int64_t nele, const double* elems69, const int64_t* idx, const int64_t* asm1, const int64_t* asm2,
+                                 int OX, const double* X0, const double* X1, const double* X2, const double* scaleX,
+                                 const double* newmark, double* Llambda, double* nzval, int nthreads) {
+    std::vector<double> Re((size_t)nele * 12), Ke((size_t)nele * 144);
+    int bad = orc_beams_iter_elementwise(nele, elems69, idx, OX, X0, X1, X2, scaleX, newmark, Re.data(), Ke.data(), nthreads);
+    if (bad) return bad;
+    for (int64_t e = 0; e < nele; ++e) {
+        const int64_t* m1 = asm1 + 12 * e; const int64_t* m2 = asm2 + 144 * e;
+        for (int i = 0; i < 12; ++i) if (m1[i]) Llambda[m1[i] - 1] += Re[12 * e + i];
+        for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) { int64_t k = m2[i + 12 * j]; if (k) nzval[k - 1] += Ke[144 * e + i + 12 * j]; }
+    }
+    return 0;
+}
+
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
