@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmuscade_b200.so")
+SO_PATH = os.environ.get("MB_LIB") or os.path.join(_HERE, "libmuscade_b200.so")   # MB_LIB: experiment builds only
 _LIB = None
 
 MB_OK, MB_ERR_CUDA, MB_ERR_ARG, MB_ERR_NAN, MB_ERR_STATE, MB_ERR_TOOBIG, MB_ERR_NCCL = range(7)

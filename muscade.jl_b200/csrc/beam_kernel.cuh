@@ -21,78 +21,79 @@ struct BeamGroupDev {
 };
 struct StateDev { const double *X0, *X1, *X2, *U0; };
 
-// Seed directions (src/SweepX.jl:46-53,62-63,92): p<12 → δX_p (scaled); p==12 (STEP) → δr.
-// Thread t ↔ (element t / LPE, lane t % LPE); lane l owns directions l·W … l·W+W−1.
-template <int ND, int W, bool STEP>
-__global__ void __launch_bounds__(128)
-beam_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke, double* __restrict__ Re, double* __restrict__ Rp,
-            unsigned long long* nanflag, unsigned long long nanbase) {
-    constexpr int NDIR = 12 + (STEP ? 1 : 0);
-    constexpr int LPE = (NDIR + W - 1) / W;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t e = t / LPE;
-    const int lane = (int)(t - e * LPE);
-    if (e >= g.nele) return;
+#ifndef MB_MINB
+#define MB_MINB 1
+#endif
+#ifndef MB_BLOCK
+#define MB_BLOCK 128
+#endif
 
-    BeamGeo geo;
-    {
-        const double2* p = reinterpret_cast<const double2*>(g.geo + e * 16);
-        double buf[16];
+MB_HD void load_geo(const double* __restrict__ p16, BeamGeo& geo) {
+    const double2* p = reinterpret_cast<const double2*>(p16);
+    double buf[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { double2 v = __ldg(p + k); buf[2 * k] = v.x; buf[2 * k + 1] = v.y; }
-        geo.cm[0] = buf[0]; geo.cm[1] = buf[1]; geo.cm[2] = buf[2];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) geo.rm.a[k] = buf[3 + k];
-        geo.tgm[0] = buf[12]; geo.tgm[1] = buf[13]; geo.tgm[2] = buf[14];
-        geo.L = buf[15];
+    for (int k = 0; k < 8; ++k) {
+#ifdef __CUDA_ARCH__
+        double2 v = __ldg(p + k);
+#else
+        double2 v = p[k];
+#endif
+        buf[2 * k] = v.x; buf[2 * k + 1] = v.y;
     }
-    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    geo.cm[0] = buf[0]; geo.cm[1] = buf[1]; geo.cm[2] = buf[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) geo.rm.a[k] = buf[3 + k];
+    geo.tgm[0] = buf[12]; geo.tgm[1] = buf[13]; geo.tgm[2] = buf[14];
+    geo.L = buf[15];
+}
 
-    using S = Dual<W>;
-    S X[3][12], U[3], R[12];
+// K1/K2 main kernel. Thread t ↔ (element t/6, lane t%6); lane l carries the seed directions
+//   slot 0: rotation dof l  (element dofs r1,r2,r3 of node 1 then node 2)      slot 1: translation dof l (t1,t2,t3 of node 1, node 2)
+// of δX (src/SweepX.jl:63,84,92): X₀+δX, X₁+a₁δX, X₂+b₁δX with δX_p = scale.X[p]·e_p, and writes the two columns of the element
+// tangent they produce (rows scaled: Lλ .* scale.X, SweepX.jl:55,65). Lane 0 also writes the residual.
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke, double* __restrict__ Re,
+               unsigned long long* nanflag, unsigned long long nanbase) {
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 6;
+    const int lane = (int)(t - e * 6);
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    TU Xu[3][6], U[3]; TR Xv[3][6]; TS R[12];
     {
         const int32_t* ix = g.idxX + e * 12;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const int32_t d = __ldg(ix + i);
-            const double x0 = st.X0[d];
-            const double x1 = (ND >= 2) ? st.X1[d] : 0.;
-            const double x2 = (ND >= 3) ? st.X2[d] : 0.;
-            X[0][i].v = x0; X[1][i].v = x1; X[2][i].v = x2;
-            const double ar = nm.a2 * x1 + nm.a3 * x2;      // a = a₂x′ + a₃x″
-            const double br = nm.b2 * x1 + nm.b3 * x2;      // b = b₂x′ + b₃x″
-#pragma unroll
-            for (int k = 0; k < W; ++k) {
-                const int p = lane * W + k;
-                const double s = (p == i) ? g.scaleX[i] : 0.;
-                X[0][i].d[k] = s;
-                X[1][i].d[k] = (STEP && p == 12) ? ar : nm.a1 * s;
-                X[2][i].d[k] = (STEP && p == 12) ? br : nm.b1 * s;
-            }
+        for (int i = 0; i < 6; ++i) {
+            const int iu = (i < 3) ? i : i + 3, iv = iu + 3;            // element dof numbers of translation / rotation i
+            const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iv);
+            const double su = (i == lane) ? g.scaleX[iu] : 0., sv = (i == lane) ? g.scaleX[iv] : 0.;
+            Xu[0][i].v = st.X0[du]; Xu[0][i].d1 = su;
+            Xv[0][i].v = st.X0[dv]; Xv[0][i].d0 = sv;
+            Xu[1][i].v = (ND >= 2) ? st.X1[du] : 0.; Xu[1][i].d1 = nm.a1 * su;
+            Xv[1][i].v = (ND >= 2) ? st.X1[dv] : 0.; Xv[1][i].d0 = nm.a1 * sv;
+            Xu[2][i].v = (ND >= 3) ? st.X2[du] : 0.; Xu[2][i].d1 = nm.b1 * su;
+            Xv[2][i].v = (ND >= 3) ? st.X2[dv] : 0.; Xv[2][i].d0 = nm.b1 * sv;
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            U[i] = Make<S>::c((g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.);
-        }
+        for (int i = 0; i < 3; ++i) { U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
     }
-    beam_residual<ND, W>(geo, m, X, g.udof != 0, U, R);
+    beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
 
     bool bad = false;
+    const int cu = (lane < 3) ? lane : lane + 3, cv = cu + 3;          // tangent columns of this lane
     double* ke = Ke + e * 144;
 #pragma unroll
-    for (int k = 0; k < W; ++k) {
-        const int p = lane * W + k;
-        if (p < 12) {
-#pragma unroll
-            for (int i = 0; i < 12; i += 2) {
-                double2 v; v.x = R[i].d[k] * g.scaleX[i]; v.y = R[i + 1].d[k] * g.scaleX[i + 1];
-                bad |= (v.x != v.x) | (v.y != v.y);
-                *reinterpret_cast<double2*>(ke + 12 * p + i) = v;
-            }
-        } else if (STEP && p == 12) {
-#pragma unroll
-            for (int i = 0; i < 12; ++i) { double v = R[i].d[k] * g.scaleX[i]; bad |= (v != v); Rp[e * 12 + i] = v; }
-        }
+    for (int i = 0; i < 12; i += 2) {
+        double2 a, b;
+        a.x = R[i].d1 * g.scaleX[i]; a.y = R[i + 1].d1 * g.scaleX[i + 1];
+        b.x = R[i].d0 * g.scaleX[i]; b.y = R[i + 1].d0 * g.scaleX[i + 1];
+        bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
+        *reinterpret_cast<double2*>(ke + 12 * cu + i) = a;
+        *reinterpret_cast<double2*>(ke + 12 * cv + i) = b;
     }
     if (lane == 0) {
 #pragma unroll
@@ -101,6 +102,36 @@ beam_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke,
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
+// :step mission only (src/SweepX.jl:46-57,69-78): the extra seed direction δr carries the Newmark predictor
+//   vx′ = x′ + a₁δX + a·δr,  vx″ = x″ + b₁δX + b·δr,  a = a₂x′+a₃x″,  b = b₂x′+b₃x″ ;   Rp = ∂(Lλ)/∂r is subtracted from the rhs.
+// One thread per element, dense one-direction dual.
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_dr_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Rp, unsigned long long* nanflag, unsigned long long nanbase) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    using S = Dual<1>;
+    S X[3][12], U[3], R[12];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int32_t d = __ldg(ix + i);
+        const double x0 = st.X0[d], x1 = (ND >= 2) ? st.X1[d] : 0., x2 = (ND >= 3) ? st.X2[d] : 0.;
+        X[0][i].v = x0; X[0][i].d[0] = 0.;
+        X[1][i].v = x1; X[1][i].d[0] = nm.a2 * x1 + nm.a3 * x2;
+        X[2][i].v = x2; X[2][i].d[0] = nm.b2 * x1 + nm.b3 * x2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U[i] = Make<S>::c((g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.);
+    beam_residual<ND, 1>(geo, m, X, g.udof != 0, U, R);
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { double v = R[i].d[0] * g.scaleX[i]; bad |= (v != v); Rp[e * 12 + i] = v; }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
 
 // host-side launcher, one translation unit per (ND,STEP) so that the instantiations compile in parallel
 struct BeamLaunch {
@@ -108,11 +139,12 @@ struct BeamLaunch {
     double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream;
 };
 template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
-#define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                          \
-    template <> void launch_beam<ND_, STEP_>(const BeamLaunch& a) {                                                              \
-        constexpr int NDIR = 12 + (STEP_ ? 1 : 0);                                                                               \
-        const int64_t nt = a.g.nele * NDIR;                                                                                      \
-        beam_kernel<ND_, 1, STEP_><<<(unsigned)((nt + 127) / 128), 128, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.Rp, a.nanflag, a.nanbase); \
+#define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \
+    template <> void launch_beam<ND_, STEP_>(const BeamLaunch& a) {                                                                   \
+        const int64_t nt = a.g.nele * 6;                                                                                              \
+        beam_kernel_sd<ND_><<<(unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase); \
+        if (STEP_)                                                                                                                    \
+            beam_dr_kernel<ND_><<<(unsigned)((a.g.nele + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Rp, a.nanflag, a.nanbase); \
     }
 
 }  // namespace mb

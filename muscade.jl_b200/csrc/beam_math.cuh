@@ -11,11 +11,15 @@
 //      giving the resultants fᵢ,mᵢ,fₑ,mₑ (BeamElement.jl:28-64) with their directional partials;
 //   2. reverse (adjoint) sweep of the order-0 kinematics with cotangents w = dL·(fᵢ,mᵢ,fₑ,mₑ), in Dual<W>:
 //      the value part is R = Jᵀw, the dual part is ∂R/∂seed = Jᵀ∂w + (∂Jᵀ)w, i.e. material + geometric tangent.
-// Each lane carries W of the Np seed directions; no second-order dual, no McLaurin expansion, nothing leaves registers.
+// Each lane carries a few of the Np seed directions; no second-order dual, no McLaurin expansion, nothing leaves registers.
+// The code is generic over three number types (struct Num): TR for what depends on the rotation dofs only, TU for what
+// depends on translation dofs / U only, TS for everything else.  With Num = NumSD they are SD<1,0>, SD<0,1>, SD<1,1>
+// (sdual.cuh): one lane carries (rotation dof l, translation dof l) and the rotation algebra costs one direction, not two.
+// With Num = NumDual<W> all three are the dense Dual<W>.
 // Branches of the reference's special functions (sinc1 family thresholds, scac series, norm3 cutoff, drag sign)
 // are reproduced on VALUE, as the reference does (Adiff.jl:198-202).
 #pragma once
-#include "dual.cuh"
+#include "sdual.cuh"
 
 namespace mb {
 
@@ -65,7 +69,7 @@ template <class A, class B> MB_HD auto mulv_t(const Mat3<A>& a, const Vec3<B>& b
 // ------------------------------------------------------------------------------------------------ rotations (forward)
 // Rodrigues(v) = I + sinc1(θ)·S + ½sinc1(θ/2)²·S²   (toolbox/Rotations.jl:131-135, spin² :114-122, norm3 :106-112)
 template <class T> struct RodAux { T a, b; bool small; };     // what the adjoint needs again
-template <class T> MB_HD Mat3<T> rodrigues(const Vec3<T>& v, RodAux<T>& aux) {
+template <class T> MB_FN Mat3<T> rodrigues(const Vec3<T>& v, RodAux<T>& aux) {
     T t2 = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
     T a, b;
     T th = mb_sqrt(t2);
@@ -96,7 +100,7 @@ template <class T> MB_HD T scac1(const T& x) {                                  
 }
 // Rodrigues⁻¹(m) = spin⁻¹(m)/scac((tr m − 1)/2)   (Rotations.jl:90,105)
 template <class T> struct RinvAux { T x, s; };
-template <class T> MB_HD Vec3<T> rodrigues_inv(const Mat3<T>& m, RinvAux<T>& aux) {
+template <class T> MB_FN Vec3<T> rodrigues_inv(const Mat3<T>& m, RinvAux<T>& aux) {
     T x = (((m(0, 0) + m(1, 1)) + m(2, 2)) - 1.0) * 0.5;
     T s = scac(x);
     aux.x = x; aux.s = s;
@@ -108,36 +112,42 @@ template <class T> MB_HD Vec3<T> rodrigues_inv(const Mat3<T>& m, RinvAux<T>& aux
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------ number-type bundles
+template <class TR_, class TU_, class TS_> struct Num { using TR = TR_; using TU = TU_; using TS = TS_; };
+template <int W> using NumDual = Num<Dual<W>, Dual<W>, Dual<W>>;
+using NumSD = Num<SD<true, false>, SD<false, true>, SD<true, true>>;
+template <class N> using NumJet = Num<Jet<typename N::TR>, Jet<typename N::TU>, Jet<typename N::TS>>;
+
 // ------------------------------------------------------------------------------------------------ rotations (adjoint)
-// v̄ += ∂Rodrigues(v)ᵀ·R̄
-template <class S> MB_HD void rodrigues_adj(const Vec3<S>& v, const RodAux<S>& aux, const Mat3<S>& Rb, Vec3<S>& vb) {
-    const S &a = aux.a, &b = aux.b;
-    S k0 = Rb(2, 1) - Rb(1, 2), k1 = Rb(0, 2) - Rb(2, 0), k2 = Rb(1, 0) - Rb(0, 1);          // skew part
-    S s01 = Rb(0, 1) + Rb(1, 0), s02 = Rb(0, 2) + Rb(2, 0), s12 = Rb(1, 2) + Rb(2, 1);        // symmetric part
-    S d0 = Rb(1, 1) + Rb(2, 2), d1 = Rb(0, 0) + Rb(2, 2), d2 = Rb(0, 0) + Rb(1, 1);
-    S g0 = (s01 * v[1] + s02 * v[2]) - 2.0 * (v[0] * d0);                                     // ∂(S²:R̄)/∂v
-    S g1 = (s01 * v[0] + s12 * v[2]) - 2.0 * (v[1] * d1);
-    S g2 = (s02 * v[0] + s12 * v[1]) - 2.0 * (v[2] * d2);
+// v̄ += ∂Rodrigues(v)ᵀ·R̄          (v, aux in TR;  R̄, v̄ in TS)
+template <class TR, class TS> MB_FN void rodrigues_adj(const Vec3<TR>& v, const RodAux<TR>& aux, const Mat3<TS>& Rb, Vec3<TS>& vb) {
+    const TR &a = aux.a, &b = aux.b;
+    TS k0 = Rb(2, 1) - Rb(1, 2), k1 = Rb(0, 2) - Rb(2, 0), k2 = Rb(1, 0) - Rb(0, 1);          // skew part
+    TS s01 = Rb(0, 1) + Rb(1, 0), s02 = Rb(0, 2) + Rb(2, 0), s12 = Rb(1, 2) + Rb(2, 1);        // symmetric part
+    TS d0 = Rb(1, 1) + Rb(2, 2), d1 = Rb(0, 0) + Rb(2, 2), d2 = Rb(0, 0) + Rb(1, 1);
+    TS g0 = (s01 * v[1] + s02 * v[2]) - 2.0 * (v[0] * d0);                                     // ∂(S²:R̄)/∂v
+    TS g1 = (s01 * v[0] + s12 * v[2]) - 2.0 * (v[1] * d1);
+    TS g2 = (s02 * v[0] + s12 * v[1]) - 2.0 * (v[2] * d2);
     vb[0] = vb[0] + (a * k0 + b * g0);
     vb[1] = vb[1] + (a * k1 + b * g1);
     vb[2] = vb[2] + (a * k2 + b * g2);
     if (!aux.small) {
-        S ab = (v[0] * k0 + v[1] * k1) + v[2] * k2;                                           // ā = S:R̄
-        S bb = 0.5 * ((v[0] * g0 + v[1] * g1) + v[2] * g2);                                   // b̄ = S²:R̄ (Euler: homogeneous degree 2)
-        S th = mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
-        S hth = th * 0.5;
-        S da = sinc1k<1>(th);
-        S db = (sinc1k<0>(hth) * sinc1k<1>(hth)) * 0.5;
-        S tb = (ab * da + bb * db) / th;                                                      // θ̄/θ
+        TS ab = (v[0] * k0 + v[1] * k1) + v[2] * k2;                                           // ā = S:R̄
+        TS bb = 0.5 * ((v[0] * g0 + v[1] * g1) + v[2] * g2);                                   // b̄ = S²:R̄ (Euler: homogeneous degree 2)
+        TR th = mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+        TR hth = th * 0.5;
+        TR da = sinc1k<1>(th);
+        TR db = (sinc1k<0>(hth) * sinc1k<1>(hth)) * 0.5;
+        TS tb = (ab * da + bb * db) / th;                                                      // θ̄/θ
         vb[0] = vb[0] + tb * v[0]; vb[1] = vb[1] + tb * v[1]; vb[2] = vb[2] + tb * v[2];
     }
 }
 // M̄ += ∂Rodrigues⁻¹(M)ᵀ·v̄ , v = Rodrigues⁻¹(M)
-template <class S> MB_HD void rodrigues_inv_adj(const Vec3<S>& v, const RinvAux<S>& aux, const Vec3<S>& vb, Mat3<S>& Mb) {
-    S is = mb_rcp(aux.s);
-    S sb = -(((vb[0] * v[0] + vb[1] * v[1]) + vb[2] * v[2]) * is);
-    S xb = (sb * scac1(aux.x)) * 0.5;
-    S w0 = (vb[0] * is) * 0.5, w1 = (vb[1] * is) * 0.5, w2 = (vb[2] * is) * 0.5;
+template <class TR, class TS> MB_FN void rodrigues_inv_adj(const Vec3<TR>& v, const RinvAux<TR>& aux, const Vec3<TS>& vb, Mat3<TS>& Mb) {
+    TR is = mb_rcp(aux.s);
+    TS sb = -(((vb[0] * v[0] + vb[1] * v[1]) + vb[2] * v[2]) * is);
+    TS xb = (sb * scac1(aux.x)) * 0.5;
+    TS w0 = (vb[0] * is) * 0.5, w1 = (vb[1] * is) * 0.5, w2 = (vb[2] * is) * 0.5;
     Mb(0, 0) = Mb(0, 0) + xb; Mb(1, 1) = Mb(1, 1) + xb; Mb(2, 2) = Mb(2, 2) + xb;
     Mb(2, 1) = Mb(2, 1) + w0; Mb(1, 2) = Mb(1, 2) - w0;
     Mb(0, 2) = Mb(0, 2) + w1; Mb(2, 0) = Mb(2, 0) - w1;
@@ -169,22 +179,24 @@ MB_HD BeamConst beam_const() {
 }
 
 // ------------------------------------------------------------------------------------------------ forward kinematics
-template <class T> struct BeamFwd {
-    Vec3<T> v1, v2, dv, vsm, ul, vl, dp;      // dp = uᵧ₂ + tgₘ/2 − cₛ
-    Mat3<T> r1, r2, rd, r;                    // rₛ₁, rₛ₂, Rodrigues(Δvᵧ), rₛₘ
-    RodAux<T> a1, a2, ad;
-    RinvAux<T> im, ir;
-    Vec3<T> cs;                               // cₛ + cₘ
-    T eps, qn; Vec3<T> q;                     // q = uₗ₂ + (L/2,0,0), qn = |q|
+template <class N> struct BeamFwd {
+    using TR = typename N::TR; using TU = typename N::TU; using TS = typename N::TS;
+    Vec3<TR> v1, v2, dv, vsm, vl;             // rotation-only quantities; vl = rₛₘᵀΔvᵧ
+    Mat3<TR> r1, r2, rd, r;                   // rₛ₁, rₛ₂, Rodrigues(Δvᵧ), rₛₘ
+    RodAux<TR> a1, a2, ad;
+    RinvAux<TR> im, ir;
+    Vec3<TU> dp, cs;                          // dp = uᵧ₂ + tgₘ/2 − cₛ ; cs = cₛ + cₘ
+    Vec3<TS> ul, q; TS eps, qn;               // q = uₗ₂ + (L/2,0,0), qn = |q|
 };
-// corotated{:direct} + ε  (BeamElement.jl:181,192-208)
-template <class T> MB_HD void beam_forward(const BeamGeo& g, const T* X, BeamFwd<T>& f) {
-    Vec3<T> u1{X[0], X[1], X[2]}, u2{X[6], X[7], X[8]};
-    f.v1 = Vec3<T>{X[3], X[4], X[5]}; f.v2 = Vec3<T>{X[9], X[10], X[11]};
+// corotated{:direct} + ε  (BeamElement.jl:181,192-208).  u1,u2: translations (TU); v1,v2: rotation vectors (TR)
+template <class N> MB_HD void beam_forward(const BeamGeo& g, const Vec3<typename N::TU>& u1, const Vec3<typename N::TR>& v1,
+                                           const Vec3<typename N::TU>& u2, const Vec3<typename N::TR>& v2, BeamFwd<N>& f) {
+    using TR = typename N::TR; using TU = typename N::TU;
+    f.v1 = v1; f.v2 = v2;
     f.r1 = rodrigues(f.v1, f.a1);
     f.r2 = rodrigues(f.v2, f.a2);
-    Mat3<T> M = mul_nt(f.r2, f.r1);
-    Vec3<T> h = rodrigues_inv(M, f.im);
+    Mat3<TR> M = mul_nt(f.r2, f.r1);
+    Vec3<TR> h = rodrigues_inv(M, f.im);
 #pragma unroll
     for (int i = 0; i < 3; ++i) f.dv[i] = 0.5 * h[i];
     f.rd = rodrigues(f.dv, f.ad);
@@ -192,22 +204,21 @@ template <class T> MB_HD void beam_forward(const BeamGeo& g, const T* X, BeamFwd
     f.vsm = rodrigues_inv(f.r, f.ir);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        T cs = 0.5 * (u1[i] + u2[i]);
+        TU cs = 0.5 * (u1[i] + u2[i]);
         f.dp[i] = (u2[i] + g.tgm[i] * 0.5) - cs;
         f.cs[i] = cs + g.cm[i];
     }
-    f.ul = mulv_t(f.r, f.dp);
-    f.ul[0] = f.ul[0] - g.L * 0.5;
+    f.q = mulv_t(f.r, f.dp);
+    f.ul = f.q; f.ul[0] = f.ul[0] - g.L * 0.5;
     f.vl = mulv_t(f.r, f.dv);
-    f.q = f.ul; f.q[0] = f.q[0] + g.L * 0.5;
     f.qn = mb_sqrt((f.q[0] * f.q[0] + f.q[1] * f.q[1]) + f.q[2] * f.q[2]);
     f.eps = f.qn * (2.0 / g.L) - 1.0;
 }
-// Gauss point position x = rₛₘ(tgₑζ + y) + cₛₘ  (BeamElement.jl:183-187)
-template <class T> MB_HD Vec3<T> beam_gp_local(const BeamConst& c, double L, int gp, const Vec3<T>& ul, const Vec3<T>& vl) {
-    Vec3<T> p;
+// Gauss point position in the corotated frame  p = tgₑζ + y  (BeamElement.jl:183-187)
+template <class A, class B> MB_HD auto beam_gp_local(const BeamConst& c, double L, int gp, const Vec3<A>& ul, const Vec3<B>& vl) -> Vec3<decltype(ul[0] + vl[0])> {
+    Vec3<decltype(ul[0] + vl[0])> p;
     double yv = c.yv[gp] * L;
-    p[0] = c.ya[gp] * ul[0] + L * c.zgp[gp];
+    p[0] = widen<decltype(ul[0] + vl[0])>(c.ya[gp] * ul[0] + L * c.zgp[gp]);
     p[1] = c.yu[gp] * ul[1] + yv * vl[2];
     p[2] = c.yu[gp] * ul[2] - yv * vl[1];
     return p;
@@ -217,8 +228,8 @@ template <class T> MB_HD Vec3<T> beam_gp_local(const BeamConst& c, double L, int
 // Cotangents of the order-0 kinematic outputs, already multiplied by dL (BeamElement.jl:163-171)
 template <class S> struct BeamCot { S eps; Vec3<S> kap[NGP]; Vec3<S> x[NGP]; Vec3<S> vsm; };
 
-// external force at a Gauss point (BeamElement.jl:28-58) from position-velocity-acceleration of the point and the frame rₛₘ
-template <class S> MB_HD Vec3<S> beam_fe(const BeamMat& m, const Mat3<S>& r0, const Vec3<S>& x1, const Vec3<S>& x2) {
+// external force at a Gauss point (BeamElement.jl:28-58) from velocity/acceleration of the point and the frame rₛₘ
+template <class TR, class S> MB_HD Vec3<S> beam_fe(const BeamMat& m, const Mat3<TR>& r0, const Vec3<S>& x1, const Vec3<S>& x2) {
     Vec3<S> xl1 = mulv_t(r0, x1), xl2 = mulv_t(r0, x2);
     const double Ca[3] = {m.Ca1, m.Ca2, m.Ca3}, Cl[3] = {m.Cl1, m.Cl2, m.Cl3}, Cq[3] = {m.Cq1, m.Cq2, m.Cq3};
     Vec3<S> fl;
@@ -237,8 +248,9 @@ template <class S> MB_HD Vec3<S> beam_fe(const BeamMat& m, const Mat3<S>& r0, co
 }
 
 // ------------------------------------------------------------------------------------------------ reverse sweep
-// Given order-0 forward state f (in S) and cotangents w, accumulate X̄[12] = Jᵀ w.
-template <class S> MB_HD void beam_reverse(const BeamGeo& g, const BeamConst& c, const BeamFwd<S>& f, const BeamCot<S>& w, S* Xb) {
+// Given the order-0 forward state f and cotangents w (TS), accumulate X̄[12] = Jᵀ w.
+template <class N> MB_HD void beam_reverse(const BeamGeo& g, const BeamConst& c, const BeamFwd<N>& f, const BeamCot<typename N::TS>& w, typename N::TS* Xb) {
+    using S = typename N::TS;
     const double L = g.L;
     S z = Make<S>::c(0.);
     Mat3<S> rb; for (int i = 0; i < 9; ++i) rb.a[i] = z;
@@ -288,7 +300,7 @@ template <class S> MB_HD void beam_reverse(const BeamGeo& g, const BeamConst& c,
     // Δv = ½ Rodrigues⁻¹(M), M = r2 r1ᵀ
     Mat3<S> Mb; for (int i = 0; i < 9; ++i) Mb.a[i] = z;
     Vec3<S> hb{0.5 * dvb[0], 0.5 * dvb[1], 0.5 * dvb[2]};
-    Vec3<S> h{2.0 * f.dv[0], 2.0 * f.dv[1], 2.0 * f.dv[2]};
+    Vec3<typename N::TR> h{2.0 * f.dv[0], 2.0 * f.dv[1], 2.0 * f.dv[2]};
     rodrigues_inv_adj(h, f.im, hb, Mb);
     Mat3<S> r2b = mul(Mb, f.r1);                   // M̄ r₁
     Mat3<S> r1b2 = mul_tn(Mb, f.r2);               // M̄ᵀ r₂
@@ -306,15 +318,18 @@ template <class S> MB_HD void beam_reverse(const BeamGeo& g, const BeamConst& c,
 
 // ------------------------------------------------------------------------------------------------ whole element
 // ND = 1 (static), 2 (first order), 3 (Newmark / DirectXUA second order).
-// X[ider][12], U0[3] carry the lane's seeds. Returns R[12] as Dual<W>: value = residual, d = ∂R/∂(lane's directions).
-template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMat& m, const Dual<W> (*X)[12], bool udof, const Dual<W>* U0, Dual<W>* R) {
-    using S = Dual<W>;
+// Xu[ider][6] = translations of node 1,2 (TU), Xv[ider][6] = rotation vectors of node 1,2 (TR), U0[3] (TU) carry the lane's
+// seeds.  Returns R[12] in TS (element dof order t1..r3 of node 1, then node 2): value = residual, partials = ∂R/∂(lane's directions).
+template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+                                                     bool udof, const typename N::TU* U0, typename N::TS* R) {
+    using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
     const BeamConst c = beam_const();
     const double L = g.L;
-    BeamFwd<S> f;
+    BeamFwd<N> f;
     BeamCot<S> w;
     if (ND == 1) {
-        beam_forward<S>(g, X[0], f);
+        beam_forward<N>(g, Vec3<TU>{Xu[0][0], Xu[0][1], Xu[0][2]}, Vec3<TR>{Xv[0][0], Xv[0][1], Xv[0][2]},
+                        Vec3<TU>{Xu[0][3], Xu[0][4], Xu[0][5]}, Vec3<TR>{Xv[0][3], Xv[0][4], Xv[0][5]}, f);
 #pragma unroll
         for (int gp = 0; gp < NGP; ++gp) {
             double dL = c.wgp[gp] * L;
@@ -323,33 +338,41 @@ template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMa
         }
         w.vsm = Vec3<S>{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(0.)};
     } else {
-        using J = Jet<S>;
-        J XJ[12];
+        using NJ = NumJet<N>;
+        using JR = typename NJ::TR; using JU = typename NJ::TU; using JS = typename NJ::TS;
+        JU XuJ[6]; JR XvJ[6];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) { XJ[i].c0 = X[0][i]; XJ[i].c1 = X[1][i]; XJ[i].c2 = (ND >= 3) ? X[2][i] : Make<S>::c(0.); }
-        BeamFwd<J> fj;
-        beam_forward<J>(g, XJ, fj);
+        for (int i = 0; i < 6; ++i) {
+            XuJ[i].c0 = Xu[0][i]; XuJ[i].c1 = Xu[1][i]; XuJ[i].c2 = (ND >= 3) ? Xu[2][i] : Make<TU>::c(0.);
+            XvJ[i].c0 = Xv[0][i]; XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
+        }
+        BeamFwd<NJ> fj;
+        beam_forward<NJ>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JR>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]},
+                         Vec3<JR>{XvJ[3], XvJ[4], XvJ[5]}, fj);
         // external loads at the Gauss points from (x, ẋ, ẍ) and rₛₘ
-        Mat3<S> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
+        Mat3<TR> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
 #pragma unroll
         for (int gp = 0; gp < NGP; ++gp) {
-            Vec3<J> p = beam_gp_local(c, L, gp, fj.ul, fj.vl);
-            Vec3<J> x = mulv(fj.r, p);
+            Vec3<JS> p = beam_gp_local(c, L, gp, fj.ul, fj.vl);
+            Vec3<JS> x = mulv(fj.r, p);
             Vec3<S> x1, x2;
-            for (int i = 0; i < 3; ++i) { x1[i] = x[i].c1 + fj.cs[i].c1; x2[i] = (ND >= 3) ? (x[i].c2 + fj.cs[i].c2) : Make<S>::c(0.); }   // ∂2(x) is zero when the solver gives no acceleration (ElementAPI.jl:48)
+            for (int i = 0; i < 3; ++i) {
+                x1[i] = x[i].c1 + fj.cs[i].c1;
+                x2[i] = (ND >= 3) ? (x[i].c2 + fj.cs[i].c2) : Make<S>::c(0.);   // ∂2(x) is zero when the solver gives no acceleration (ElementAPI.jl:48)
+            }
             Vec3<S> fe = beam_fe(m, r0, x1, x2);
             double dL = c.wgp[gp] * L;
             for (int i = 0; i < 3; ++i) { if (udof) fe[i] = fe[i] - U0[i]; w.x[gp][i] = dL * fe[i]; }
         }
         // roll inertia: mₑ = rₛₘ[:,1]·ι₁·vᵢ₂[1], vᵢ₂ = spin⁻¹(ṙᵀṙ + rᵀr̈)  (Rotations.jl:177-182; the symmetric ṙᵀṙ drops out of spin⁻¹)
-        S vi2 = Make<S>::c(0.);
+        TR vi2 = Make<TR>::c(0.);
         if (ND >= 3) {
-            S m21 = (fj.r(0, 2).c0 * fj.r(0, 1).c2 + fj.r(1, 2).c0 * fj.r(1, 1).c2) + fj.r(2, 2).c0 * fj.r(2, 1).c2;   // (rᵀr̈)[3,2]
-            S m12 = (fj.r(0, 1).c0 * fj.r(0, 2).c2 + fj.r(1, 1).c0 * fj.r(1, 2).c2) + fj.r(2, 1).c0 * fj.r(2, 2).c2;   // (rᵀr̈)[2,3]
+            TR m21 = (fj.r(0, 2).c0 * fj.r(0, 1).c2 + fj.r(1, 2).c0 * fj.r(1, 1).c2) + fj.r(2, 2).c0 * fj.r(2, 1).c2;   // (rᵀr̈)[3,2]
+            TR m12 = (fj.r(0, 1).c0 * fj.r(0, 2).c2 + fj.r(1, 1).c0 * fj.r(1, 2).c2) + fj.r(2, 1).c0 * fj.r(2, 2).c2;   // (rᵀr̈)[2,3]
             vi2 = (m21 - m12) * 0.5;
         }
-        S m1l = (m.iota1 * L) * vi2;                                         // Σ_gp dL = L
-        for (int i = 0; i < 3; ++i) w.vsm[i] = r0(i, 0) * m1l;
+        TR m1l = (m.iota1 * L) * vi2;                                         // Σ_gp dL = L
+        for (int i = 0; i < 3; ++i) w.vsm[i] = widen<S>(r0(i, 0) * m1l);
         // order-0 state for the reverse sweep
         for (int i = 0; i < 3; ++i) {
             f.v1[i] = fj.v1[i].c0; f.v2[i] = fj.v2[i].c0; f.dv[i] = fj.dv[i].c0; f.vsm[i] = fj.vsm[i].c0;
@@ -367,12 +390,22 @@ template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMa
 #pragma unroll
     for (int gp = 0; gp < NGP; ++gp) {
         double dL = c.wgp[gp] * L, ka = 2.0 / L, ku = c.ku[gp] / (L * L), kv = 2.0 / L;
-        S k0 = ka * f.vl[0];
+        TR k0 = ka * f.vl[0];
         S k1 = ku * f.ul[1] + kv * f.vl[2];
         S k2 = ku * f.ul[2] - kv * f.vl[1];
-        w.kap[gp][0] = (m.GJ * dL) * k0; w.kap[gp][1] = (m.EI3 * dL) * k1; w.kap[gp][2] = (m.EI2 * dL) * k2;
+        w.kap[gp][0] = widen<S>((m.GJ * dL) * k0); w.kap[gp][1] = (m.EI3 * dL) * k1; w.kap[gp][2] = (m.EI2 * dL) * k2;
     }
-    beam_reverse<S>(g, c, f, w, R);
+    beam_reverse<N>(g, c, f, w, R);
+}
+
+// dense Dual<W> front-end (element dof order X[ider][12]); used by the δr lane of the :step mission and by the host tests
+template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMat& m, const Dual<W> (*X)[12], bool udof, const Dual<W>* U0, Dual<W>* R) {
+    Dual<W> Xu[3][6], Xv[3][6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { Xu[d][i] = X[d][i]; Xv[d][i] = X[d][3 + i]; Xu[d][3 + i] = X[d][6 + i]; Xv[d][3 + i] = X[d][9 + i]; }
+    beam_residual_n<ND, NumDual<W>>(g, m, Xu, Xv, udof, U0, R);
 }
 
 }  // namespace mb

@@ -16,6 +16,20 @@
 #else
 #define MB_HD inline
 #endif
+// MB_FN: larger building blocks (rotations, adjoints) — optionally kept out of line on the device to shrink the instruction footprint
+#if defined(__CUDACC__) && defined(MB_NOINLINE)
+#define MB_FN __host__ __device__ __noinline__
+#else
+#define MB_FN MB_HD
+#endif
+
+// MB_ALIGN(): block-wide rendezvous between the big phases of a kernel whose straight-line code is far larger than the
+// instruction caches: it keeps the warps of a CTA on the same code region so that instruction lines are fetched once per CTA.
+#if defined(__CUDA_ARCH__) && defined(MB_PHASE_SYNC)
+#define MB_ALIGN() __syncthreads()
+#else
+#define MB_ALIGN() ((void)0)
+#endif
 
 namespace mb {
 
@@ -127,15 +141,15 @@ template <class S> struct Make<Jet<S>> {
     static MB_HD Jet<S> c(double v) { Jet<S> r; r.c0 = Make<S>::c(v); r.c1 = Make<S>::c(0.); r.c2 = Make<S>::c(0.); return r; }
 };
 template <class S> MB_HD double value(const Jet<S>& a) { return value(a.c0); }
-template <class S> MB_HD Jet<S> operator+(const Jet<S>& a, const Jet<S>& b) { Jet<S> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; r.c2 = a.c2 + b.c2; return r; }
+template <class S1, class S2> MB_HD auto operator+(const Jet<S1>& a, const Jet<S2>& b) -> Jet<decltype(a.c0 + b.c0)> { Jet<decltype(a.c0 + b.c0)> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; r.c2 = a.c2 + b.c2; return r; }
 template <class S> MB_HD Jet<S> operator+(const Jet<S>& a, double b) { Jet<S> r = a; r.c0 = a.c0 + b; return r; }
 template <class S> MB_HD Jet<S> operator+(double a, const Jet<S>& b) { Jet<S> r = b; r.c0 = a + b.c0; return r; }
-template <class S> MB_HD Jet<S> operator-(const Jet<S>& a, const Jet<S>& b) { Jet<S> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; r.c2 = a.c2 - b.c2; return r; }
+template <class S1, class S2> MB_HD auto operator-(const Jet<S1>& a, const Jet<S2>& b) -> Jet<decltype(a.c0 - b.c0)> { Jet<decltype(a.c0 - b.c0)> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; r.c2 = a.c2 - b.c2; return r; }
 template <class S> MB_HD Jet<S> operator-(const Jet<S>& a, double b) { Jet<S> r = a; r.c0 = a.c0 - b; return r; }
 template <class S> MB_HD Jet<S> operator-(double a, const Jet<S>& b) { Jet<S> r; r.c0 = a - b.c0; r.c1 = -b.c1; r.c2 = -b.c2; return r; }
 template <class S> MB_HD Jet<S> operator-(const Jet<S>& a) { Jet<S> r; r.c0 = -a.c0; r.c1 = -a.c1; r.c2 = -a.c2; return r; }
-template <class S> MB_HD Jet<S> operator*(const Jet<S>& a, const Jet<S>& b) {
-    Jet<S> r;
+template <class S1, class S2> MB_HD auto operator*(const Jet<S1>& a, const Jet<S2>& b) -> Jet<decltype(a.c0 * b.c0)> {
+    Jet<decltype(a.c0 * b.c0)> r;
     r.c0 = a.c0 * b.c0;
     r.c1 = a.c0 * b.c1 + a.c1 * b.c0;
     r.c2 = (a.c0 * b.c2 + a.c2 * b.c0) + 2.0 * (a.c1 * b.c1);
@@ -148,7 +162,7 @@ template <class S> MB_HD Jet<S> jet_compose(const Jet<S>& x, const S& f0, const 
     Jet<S> r; r.c0 = f0; r.c1 = f1 * x.c1; r.c2 = f2 * (x.c1 * x.c1) + f1 * x.c2; return r;
 }
 template <class S> MB_HD Jet<S> mb_rcp(const Jet<S>& a) { S f0 = mb_rcp(a.c0); S f1 = -(f0 * f0); S f2 = -2.0 * (f1 * f0); return jet_compose(a, f0, f1, f2); }
-template <class S> MB_HD Jet<S> operator/(const Jet<S>& a, const Jet<S>& b) { return a * mb_rcp(b); }
+template <class S1, class S2> MB_HD auto operator/(const Jet<S1>& a, const Jet<S2>& b) -> decltype(a * mb_rcp(b)) { return a * mb_rcp(b); }
 template <class S> MB_HD Jet<S> operator/(const Jet<S>& a, double b) { return a * (1.0 / b); }
 template <class S> MB_HD Jet<S> operator/(double a, const Jet<S>& b) { return a * mb_rcp(b); }
 template <class S> MB_HD Jet<S> mb_sqrt(const Jet<S>& a) { S f0 = mb_sqrt(a.c0); S f1 = 0.5 / f0; S f2 = -0.5 * (f1 / a.c0); return jet_compose(a, f0, f1, f2); }
@@ -162,6 +176,17 @@ template <class S> MB_HD Jet<S> mb_acos(const Jet<S>& a) {
 template <int K, class S> MB_HD Jet<S> sinc1k(const Jet<S>& a) { return jet_compose(a, sinc1k<K>(a.c0), sinc1k<K + 1>(a.c0), sinc1k<K + 2>(a.c0)); }
 
 template <class T> MB_HD T sqr(const T& a) { return a * a; }
+
+// widen<To>(x): embed a number into a type with more partial slots (missing slots are zero)
+template <class To, class From> struct Widen;
+template <class T> struct Widen<T, T> { static MB_HD T w(const T& x) { return x; } };
+template <class To> struct Widen<To, double> { static MB_HD To w(double x) { return Make<To>::c(x); } };
+template <> struct Widen<double, double> { static MB_HD double w(double x) { return x; } };
+template <class To, class From> MB_HD To widen(const From& x) { return Widen<To, From>::w(x); }
+template <class S1, class S2> struct Widen<Jet<S1>, Jet<S2>> {
+    static MB_HD Jet<S1> w(const Jet<S2>& x) { Jet<S1> r; r.c0 = widen<S1>(x.c0); r.c1 = widen<S1>(x.c1); r.c2 = widen<S1>(x.c2); return r; }
+};
+template <class S> struct Widen<Jet<S>, Jet<S>> { static MB_HD Jet<S> w(const Jet<S>& x) { return x; } };
 
 // a^2 exactly as the reference evaluates it (src/Adiff.jl:230):  ∂ℝ(a.x^b, a.dx*b*a.x^(b-1))  with  b==0 ? zero(a).
 // On numbers nested three deep (time-packed by motion{P}, Taylor.jl:24-29, over the solver's ∂ℝ{1,Np}) the inner a.x^1 hits

@@ -371,7 +371,7 @@ template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group
                                                        unsigned long long nanbase) {
     BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->beamW, h->stream};
     launch_beam<ND, STEP>(a);
-    h->launches++;
+    h->launches += STEP ? 2 : 1;
 }
 
 static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm) {
