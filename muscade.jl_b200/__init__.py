@@ -4,6 +4,8 @@ Host-side mirror of the reference interface for this path (Model / addnode! / ad
 assemble! / solve(SweepX)), over the C ABI in include/muscade_b200.h.  The directory name contains a dot, so the package
 is imported through the loader `muscade_b200.py` at the repository root (`import muscade_b200`).
 """
-from . import _lib, toolbox, synthetic  # noqa: F401
+from . import _lib, toolbox, synthetic, model, sweepx  # noqa: F401
 from ._lib import MuscadeB200Error, build  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .model import Model, addnode, addelement, setscale, initialize, Disassembler, State, getdof  # noqa: F401
+from .toolbox import BeamCrossSection, EulerBeam3D, Hold, DofLoad, ElementType  # noqa: F401

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's model description and disassembler (setup time; integer structures reproduced exactly).
+
+  Model / addnode! / addelement! / setscale! / initialize!      src/ModelDescription.jl:15-324
+  Disassembler / EletypDisassembler / State                     src/Assemble.jl:3-159
+
+Julia's `!` names become `addnode`, `addelement`, `setscale`, `initialize`.  All dof / node / element numbers are 1-based
+as in the reference.  `addelement` is vectorised over the rows of `nodID` (a 10M-element mesh is one call), but assigns dof
+numbers in exactly the reference's order of first appearance (element-major, then element-dof order, per class;
+ModelDescription.jl:226-249).  Per-node / per-dof element lists (Node.eleID, Dof.eleID), only used by `describe`, are not kept.
+"""
+import numpy as np
+
+from ._lib import MuscadeB200Error
+
+CLASSES = ("X", "U", "A")
+
+
+def muscadeerror(msg, dbg=None):
+    raise MuscadeB200Error(msg, dbg)
+
+
+class DofTyp:
+    def __init__(self, clas, field):
+        self.clas, self.field, self.scale = clas, field, 1.0
+        self.dofID = []          # list of arrays of idof (appended per addelement call)
+
+
+class EleTyp:
+    """One entry of model.ele / model.eleobj: all elements of one concrete element type."""
+
+    def __init__(self, ElType, key, doflist):
+        self.ElType, self.key = ElType, key
+        self.inod, self.clas, self.field = doflist
+        self.nodID = np.zeros((0, max(self.inod) if self.inod else 0), np.int64)
+        self.dofID = np.zeros((0, len(self.inod)), np.int64)      # idof within its class, per element dof
+        self.eleobj = None                                        # ElType-specific batch (e.g. (nele,69) array)
+        self.extra = None
+
+    @property
+    def nele(self):
+        return self.dofID.shape[0]
+
+    def idof(self, clas):
+        return [j for j, c in enumerate(self.clas) if c == clas]
+
+
+class Model:
+    def __init__(self, ID="muscade_model"):
+        self.ID = ID
+        self.coord = []                      # model.nod[inod].coord
+        self.ele = []                        # list of EleTyp  (model.ele / model.eleobj)
+        self.ndof = dict(X=0, U=0, A=0)      # length(model.dof[class])
+        self.dof_nod = dict(X=[], U=[], A=[])   # model.dof[class][idof].nodID   (list of arrays)
+        self.dof_typ = dict(X=[], U=[], A=[])   # model.dof[class][idof].idoftyp
+        self.doftyp = []
+        self.nod_dof = []                    # per idoftyp: array over nodes → idof (0 = node has no such dof)
+        self.scaleΛ = 1.0
+        self.locked = False
+
+    # -- accessors (ModelDescription.jl:84-133)
+    def getndof(self, clas=None):
+        if clas is None:
+            return sum(self.ndof.values())
+        if isinstance(clas, (tuple, list)):
+            return tuple(self.ndof[c] for c in clas)
+        return self.ndof[clas]
+
+    def getnele(self, ieletyp=None):
+        return sum(e.nele for e in self.ele) if ieletyp is None else self.ele[ieletyp - 1].nele
+
+    def getneletyp(self):
+        return len(self.ele)
+
+    def getidoftyp(self, clas, field):
+        for i, d in enumerate(self.doftyp):
+            if d.clas == clas and d.field == field:
+                return i + 1
+        return 0
+
+    def getdoftyp(self, clas, field):
+        i = self.getidoftyp(clas, field)
+        if i == 0:
+            muscadeerror("The model has no dof of class %s and field %s." % (clas, field))
+        return self.doftyp[i - 1]
+
+    def nnod(self):
+        return len(self.coord)
+
+    def assert_unlocked(self):
+        if self.locked:
+            muscadeerror("model %s is initialized and can no longer be edited" % self.ID)
+
+
+def addnode(model, coord):
+    """nodid = addnode!(model,coord)  (ModelDescription.jl:166-173): a vector adds one node, a matrix one node per row."""
+    model.assert_unlocked()
+    coord = np.asarray(coord, float)
+    if coord.ndim == 1:
+        model.coord.append(coord.copy())
+        return len(model.coord)
+    first = len(model.coord) + 1
+    model.coord.extend(list(coord))
+    return np.arange(first, first + coord.shape[0], dtype=np.int64)
+
+
+def addelement(model, ElType, nodID, **kwargs):
+    """eleid = addelement!(model,ElType,nodid;kwargs...)  (ModelDescription.jl:195-263).
+
+    nodID: vector → one element, returns (ieletyp,iele); matrix (nele × nnod) → many, returns (ieletyp, array of iele)."""
+    model.assert_unlocked()
+    nodID = np.asarray(nodID, np.int64)
+    single = nodID.ndim == 1
+    if single:
+        nodID = nodID[None, :]
+    nele_new, nnod = nodID.shape
+    key = ElType.typekey(**kwargs)
+    doflist = ElType.doflist(**kwargs)
+    inod, clas, field = doflist
+    if nnod != (max(inod) if inod else 0):
+        muscadeerror("Connecting element of type %s: Second dimension of inod (%d) must be equal to element's nnod (%d)" %
+                     (ElType.__name__, nnod, max(inod) if inod else 0))
+    # element objects first (the reference constructs ele1 before touching the model, so constructor errors leave it intact)
+    if nele_new and all(len(model.coord[n - 1]) == len(model.coord[nodID[0, 0] - 1]) for n in nodID[0]):
+        try:
+            coords = np.asarray([model.coord[n - 1] for n in nodID.reshape(-1)], float).reshape(nele_new, nnod, -1)
+        except ValueError:
+            coords = np.zeros((nele_new, nnod, 0))
+    else:
+        coords = np.zeros((nele_new, nnod, 0))
+    built = ElType.construct(coords, **kwargs)
+    eleobj, extra = built if isinstance(built, tuple) else (built, None)
+    # element type (getieletyp, ModelDescription.jl:205-213)
+    ieletyp = 0
+    for i, e in enumerate(model.ele):
+        if e.key == key:
+            ieletyp = i + 1
+    if ieletyp == 0:
+        model.ele.append(EleTyp(ElType, key, doflist))
+        ieletyp = len(model.ele)
+    et = model.ele[ieletyp - 1]
+    iele_sofar = et.nele
+    neledof = len(inod)
+    # dof types, in doflist order (created while visiting the first element)
+    idoftyp = np.zeros(neledof, np.int64)
+    for j in range(neledof):
+        t = model.getidoftyp(clas[j], field[j])
+        if t == 0:
+            model.doftyp.append(DofTyp(clas[j], field[j]))
+            model.nod_dof.append(np.zeros(0, np.int64))
+            t = len(model.doftyp)
+        idoftyp[j] = t
+    nn = model.nnod()
+    for t in set(idoftyp.tolist()):
+        tab = model.nod_dof[t - 1]
+        if tab.size < nn + 1:
+            model.nod_dof[t - 1] = np.concatenate([tab, np.zeros(nn + 1 - tab.size, np.int64)])
+    # dofs: existing ones are looked up, new ones numbered per class in order of first appearance (element-major, eledof-minor)
+    node = nodID[:, np.asarray(inod, np.int64) - 1] if neledof else np.zeros((nele_new, 0), np.int64)      # (nele, neledof)
+    typ = np.broadcast_to(idoftyp[None, :], node.shape)
+    existing = np.zeros(node.shape, np.int64)
+    for j in range(neledof):
+        existing[:, j] = model.nod_dof[idoftyp[j] - 1][node[:, j]]
+    dof = existing.copy()
+    newmask = existing == 0
+    if newmask.any():
+        code = (typ.astype(np.int64) * (nn + 1) + node).reshape(-1)
+        flat_new = np.flatnonzero(newmask.reshape(-1))
+        uniq, first = np.unique(code[flat_new], return_index=True)
+        order = np.argsort(first, kind="stable")
+        uniq = uniq[order]                                 # new (doftyp,node) keys in order of first appearance
+        utyp = uniq // (nn + 1); unod = uniq % (nn + 1)
+        uclass = np.array([model.doftyp[t - 1].clas for t in utyp])
+        newid = np.zeros(uniq.size, np.int64)
+        for c in CLASSES:
+            sel = np.flatnonzero(uclass == c)
+            newid[sel] = model.ndof[c] + 1 + np.arange(sel.size)
+            if sel.size:
+                model.ndof[c] += sel.size
+                model.dof_nod[c].append(unod[sel]); model.dof_typ[c].append(utyp[sel])
+        for t in np.unique(utyp):
+            sel = utyp == t
+            model.nod_dof[t - 1][unod[sel]] = newid[sel]
+            model.doftyp[t - 1].dofID.append(newid[sel])
+        for j in range(neledof):
+            dof[:, j] = model.nod_dof[idoftyp[j] - 1][node[:, j]]
+    et.nodID = np.concatenate([et.nodID, nodID]) if et.nodID.shape[1] == nnod else nodID
+    et.dofID = np.concatenate([et.dofID, dof])
+    if et.eleobj is None:
+        et.eleobj, et.extra = eleobj, extra
+    else:
+        et.eleobj = np.concatenate([et.eleobj, eleobj])
+    iele = iele_sofar + np.arange(1, nele_new + 1)
+    return (ieletyp, int(iele[0])) if single else (ieletyp, iele)
+
+
+def setscale(model, scale=None, Λscale=None):
+    """setscale!(model;scale,Λscale)  (ModelDescription.jl:287-299); scale = dict(X=dict(tx=10,rx=1), A=dict(drag=3.))"""
+    model.assert_unlocked()
+    if scale is not None:
+        for d in model.doftyp:
+            if d.clas in scale and d.field in scale[d.clas]:
+                d.scale = float(scale[d.clas][d.field])
+    if Λscale is not None:
+        model.scaleΛ = float(Λscale)
+
+
+class EletypDisassembler:
+    """dis.dis[ieletyp]: index[iele].X|U|A (here (nele,n) int64 arrays) and scale.Λ|X|U|A  (Assemble.jl:14-17)."""
+
+    def __init__(self, X, U, A, sΛ, sX, sU, sA):
+        self.X, self.U, self.A = X, U, A
+        self.scaleΛ, self.scaleX, self.scaleU, self.scaleA = sΛ, sX, sU, sA
+
+
+class Disassembler:
+    """Disassembler(model)  (Assemble.jl:32-99)"""
+
+    def __init__(self, model):
+        NX, NU, NA = model.getndof(("X", "U", "A"))
+        self.scaleΛ = np.zeros(NX); self.scaleX = np.zeros(NX); self.scaleU = np.zeros(NU); self.scaleA = np.zeros(NA)
+        self.fieldX = [None] * NX; self.fieldU = [None] * NU; self.fieldA = [None] * NA
+        self.dis = []
+        for et in model.ele:
+            jX, jU, jA = et.idof("X"), et.idof("U"), et.idof("A")
+            sc = np.array([model.getdoftyp(c, f).scale for c, f in zip(et.clas, et.field)])
+            sX = sc[jX]; sΛ = sX * model.scaleΛ; sU = sc[jU]; sA = sc[jA]
+            iX = np.ascontiguousarray(et.dofID[:, jX]); iU = np.ascontiguousarray(et.dofID[:, jU]); iA = np.ascontiguousarray(et.dofID[:, jA])
+            if et.nele:
+                self.scaleΛ[iX - 1] = sΛ[None, :]; self.scaleX[iX - 1] = sX[None, :]
+                self.scaleU[iU - 1] = sU[None, :]; self.scaleA[iA - 1] = sA[None, :]
+                for cls, jj, idx, fl in (("X", jX, iX, self.fieldX), ("U", jU, iU, self.fieldU), ("A", jA, iA, self.fieldA)):
+                    for k, j in enumerate(jj):
+                        for d in np.unique(idx[:, k]):
+                            fl[d - 1] = et.field[j]
+            self.dis.append(EletypDisassembler(iX, iU, iA, sΛ, sX, sU, sA))
+
+
+class State:
+    """State{nΛder,nXder,nUder,TSP}  (Assemble.jl:106-159): time, Λ, X, U (tuples of vectors), A, SP, model, dis."""
+
+    def __init__(self, time, Λ, X, U, A, SP, model, dis):
+        self.time, self.Λ, self.X, self.U, self.A, self.SP, self.model, self.dis = time, list(Λ), list(X), list(U), A, SP, model, dis
+
+    @classmethod
+    def zeros(cls, model, dis, nΛder=1, nXder=1, nUder=1, time=-np.inf):
+        nX, nU, nA = model.getndof(("X", "U", "A"))
+        return cls(time, [np.zeros(nX) for _ in range(nΛder)], [np.zeros(nX) for _ in range(nXder)], [np.zeros(nU) for _ in range(nUder)],
+                   np.zeros(nA), None, model, dis)
+
+    def with_orders(self, nΛder, nXder, nUder, SP=None):
+        """State{nΛder,nXder,nUder}(s): shallow copy that drops or zero-pads derivatives (Assemble.jl:131-144, ∂n → zeros)."""
+        def fit(v, n):
+            return [v[i] if i < len(v) else np.zeros_like(v[0]) for i in range(n)]
+        return State(self.time, fit(self.Λ, nΛder), fit(self.X, nXder), fit(self.U, nUder), self.A, self.SP if SP is None else SP, self.model, self.dis)
+
+    def copy(self, time=None, SP=None):
+        """Base.copy(s::State): deep copy except SP, model, dis (Assemble.jl:159)"""
+        return State(self.time if time is None else time, [v.copy() for v in self.Λ], [v.copy() for v in self.X], [v.copy() for v in self.U],
+                     self.A.copy(), self.SP if SP is None else SP, self.model, self.dis)
+
+
+def initialize(model, nΛder=1, nXder=1, nUder=1, time=-np.inf):
+    """initialstate = initialize!(model)  (ModelDescription.jl:319-324)"""
+    model.assert_unlocked()
+    model.locked = True
+    dis = Disassembler(model)
+    return State.zeros(model, dis, nΛder, nXder, nUder, time)
+
+
+def getdof(state, field, nodID=None, clas="X", order=0):
+    """getdof(state;class,field,nodID,order)  (src/Output.jl:21-54), minimal: values of the dofs of one field at the given nodes."""
+    model = state.model
+    t = model.getidoftyp(clas, field)
+    if t == 0:
+        muscadeerror("The model has no dof of class %s and field %s." % (clas, field))
+    tab = model.nod_dof[t - 1]
+    nodes = np.arange(1, model.nnod() + 1) if nodID is None else np.atleast_1d(np.asarray(nodID, np.int64))
+    idof = tab[nodes]
+    if (idof == 0).any():
+        muscadeerror("some nodes have no dof of field %s" % field)
+    vec = {"X": state.X, "U": state.U}[clas][order] if clas in ("X", "U") else state.A
+    return vec[idof - 1]

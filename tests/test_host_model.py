@@ -1,0 +1,102 @@
+"""Host logic (no GPU): model description, dof numbering, Disassembler — against the reference's own integer pins
+(test/TestModelDescription.jl, test/TestAssemble.jl:53-67) and against the closed-form chain numbering used by the bench."""
+import numpy as np
+import pytest
+
+
+class _Gen:
+    """Stand-in element type defined only by its doflist (enough for every integer structure)."""
+    kind = "host"
+    LIST = None
+    NAME = None
+
+    @classmethod
+    def doflist(cls, **kw): return cls.LIST
+    @classmethod
+    def typekey(cls, **kw): return (cls.NAME,)
+    @classmethod
+    def construct(cls, coords, **kw): return np.zeros((coords.shape[0], 0))
+
+
+class Turbine(_Gen):      # test/SomeElements.jl:54-56
+    NAME = "Turbine"; LIST = ((1, 1, 2, 2), ("X", "X", "A", "A"), ("tx1", "tx2", "Δseadrag", "Δskydrag"))
+
+
+class AnchorLine(_Gen):   # test/SomeElements.jl:74-76
+    NAME = "AnchorLine"; LIST = ((1, 1, 1, 2, 2), ("X", "X", "X", "A", "A"), ("tx1", "tx2", "rx3", "ΔL", "Δbuoyancy"))
+
+
+def test_disassembler_pins(mb):
+    """test/TestAssemble.jl:41-67"""
+    model = mb.Model("TestModel")
+    n1 = mb.addnode(model, [0, 0, 100.]); n2 = mb.addnode(model, []); n3 = mb.addnode(model, [])
+    e1 = mb.addelement(model, Turbine, [n1, n2]); e2 = mb.addelement(model, AnchorLine, [n1, n3])
+    assert e1 == (1, 1) and e2 == (2, 1)
+    dis = mb.Disassembler(model)
+    assert dis.dis[0].X.tolist() == [[1, 2]] and dis.dis[0].U.shape == (1, 0) and dis.dis[0].A.tolist() == [[1, 2]]
+    assert dis.dis[1].X.tolist() == [[1, 2, 3]] and dis.dis[1].A.tolist() == [[3, 4]]
+    assert np.allclose(dis.scaleX, 1) and np.allclose(dis.scaleΛ, 1) and dis.scaleU.size == 0 and np.allclose(dis.scaleA, [1, 1, 1, 1])
+    assert dis.fieldX == ["tx1", "tx2", "rx3"] and dis.fieldU == [] and dis.fieldA == ["Δseadrag", "Δskydrag", "ΔL", "Δbuoyancy"]
+
+
+def test_model_description_pins(mb):
+    """test/TestModelDescription.jl: node/element/dof numbering after addelement!"""
+    model = mb.Model("TestModel")
+    n1 = mb.addnode(model, [0, 0, 100.]); n2 = mb.addnode(model, []); n3 = mb.addnode(model, [])
+    mb.addelement(model, Turbine, [n1, n2]); mb.addelement(model, AnchorLine, [n1, n3])
+    assert (n1, n2, n3) == (1, 2, 3)
+    assert model.getndof() == 7 and model.getndof(("X", "U", "A")) == (3, 0, 4)
+    # model.ele[·][1].dofID  (TestModelDescription.jl:47-58): Turbine X1 X2 A1 A2 ; AnchorLine X1 X2 X3 A3 A4
+    assert model.ele[0].dofID.tolist() == [[1, 2, 1, 2]] and model.ele[0].clas == ("X", "X", "A", "A")
+    assert model.ele[1].dofID.tolist() == [[1, 2, 3, 3, 4]] and model.ele[1].nodID.tolist() == [[1, 3]]
+    # model.dof[DofID].nodID / idoftyp  (:60-80)
+    nodX = np.concatenate(model.dof_nod["X"]); typX = np.concatenate(model.dof_typ["X"])
+    nodA = np.concatenate(model.dof_nod["A"]); typA = np.concatenate(model.dof_typ["A"])
+    assert nodX.tolist() == [1, 1, 1] and typX.tolist() == [1, 2, 5]
+    assert nodA.tolist() == [2, 2, 3, 3] and typA.tolist() == [3, 4, 6, 7]
+    # model.doftyp[·].dofID (:83-99)
+    assert np.concatenate(model.doftyp[0].dofID).tolist() == [1] and np.concatenate(model.doftyp[2].dofID).tolist() == [1]
+    assert np.concatenate(model.doftyp[4].dofID).tolist() == [3]
+    assert model.getnele() == 2 and model.getneletyp() == 2
+    assert [(d.clas, d.field) for d in model.doftyp] == [("X", "tx1"), ("X", "tx2"), ("A", "Δseadrag"), ("A", "Δskydrag"), ("X", "rx3"), ("A", "ΔL"), ("A", "Δbuoyancy")]
+    mb.setscale(model, scale=dict(X=dict(tx1=10., rx3=2.)), Λscale=1e3)
+    dis = mb.Disassembler(model)
+    assert dis.scaleX.tolist() == [10., 1., 2.] and dis.scaleΛ.tolist() == [1e4, 1e3, 2e3]
+    st = mb.initialize(model)
+    with pytest.raises(mb.MuscadeB200Error):
+        mb.addnode(model, [0.])        # model is initialized and can no longer be edited
+    assert st.X[0].shape == (3,) and st.A.shape == (4,) and st.time == -np.inf
+
+
+def test_chain_numbering_matches_generic_addelement(mb):
+    """the bench's closed-form chain (synthetic.chain) is what addnode!/addelement! produce"""
+    N = 37
+    eleobj, idx, ndof = mb.synthetic.chain(N)
+    model = mb.Model()
+    k = np.arange(N + 1)[:, None] * np.array([0.8, 0.6, 0.0])[None, :]
+    nod = mb.addnode(model, k)
+    mesh = np.stack([nod[:-1], nod[1:]], axis=1)
+    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1.)
+    ityp, iele = mb.addelement(model, mb.EulerBeam3D, mesh, mat=mat, orient2=(0., 1., 0.))
+    dis = mb.Disassembler(model)
+    assert ityp == 1 and iele.tolist() == list(range(1, N + 1))
+    assert model.getndof("X") == ndof and np.array_equal(dis.dis[0].X, idx)
+    assert np.array_equal(model.ele[0].eleobj, eleobj)
+    assert dis.fieldX[:6] == ["t1", "t2", "t3", "r1", "r2", "r3"]
+
+
+def test_shared_dofs_and_multiple_types(mb):
+    """StaticBeamAnalysis-like model: beams + 6 Hold types + DofLoad ⇒ 8 element types, λ dofs appended after beam dofs"""
+    nel = 8
+    model = mb.Model()
+    th = 3 * np.pi / 2 + np.arange(nel + 1) / nel * np.pi / 4
+    nod = mb.addnode(model, np.stack([100 * np.cos(th), np.zeros(nel + 1), 100 + 100 * np.sin(th)], axis=1))
+    mat = mb.BeamCrossSection(EA=1e9, EI2=833.33e3, EI3=833.33e3, GJ=705e3, mu=1., iota1=1.)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:]], axis=1), mat=mat)
+    for f in ["t1", "t2", "t3", "r1", "r2", "r3"]:
+        mb.addelement(model, mb.Hold, [nod[0]], field=f)
+    mb.addelement(model, mb.DofLoad, [nod[-1]], field="t2", value=lambda t: 300. * t)
+    assert model.getneletyp() == 8 and model.getndof("X") == 6 * (nel + 1) + 6
+    dis = mb.Disassembler(model)
+    assert dis.dis[1].X.tolist() == [[1, 55]] and dis.dis[6].X.tolist() == [[6, 60]] and dis.dis[7].X.tolist() == [[50]]
+    assert dis.fieldX[54:] == ["λt1", "λt2", "λt3", "λr1", "λr2", "λr3"]
