@@ -40,7 +40,7 @@ int32_t     mb_version(void);
  *   scaleX : 12, scaleU : 3 — dis.dis[ityp].scale.X/.U (src/Assemble.jl:68). */
 int32_t mb_add_eulerbeam3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t udof, const int64_t* idxX, const int64_t* idxU,
                            const double* scaleX, const double* scaleU, int32_t* ieletyp_out);
-/* Bar3D{AxisymmetricBarCrossSection,Udof} (toolbox/BarElement.jl:89-101): nele × 39 Float64
+/* Bar3D{AxisymmetricBarCrossSection,Udof} (toolbox/BarElement.jl:89-101): nele × 38 Float64
  *   (cₘ3 tgₘ3 tgₑ3 L₀ Lₛ mat9 wgp4 ζgp4 ζnod2 ψ₁4 ψ₂4); idxX 6 × nele. */
 int32_t mb_add_bar3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t udof, const int64_t* idxX, const int64_t* idxU,
                      const double* scaleX, const double* scaleU, int32_t* ieletyp_out);

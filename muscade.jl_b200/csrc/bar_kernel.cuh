@@ -1,0 +1,136 @@
+// K4/K5: Bar3D and SoilContact element kernels (sm_100a) — HBM-bound elements, one thread per element, dense Dual<NDIR>.
+//   Bar3D       toolbox/BarElement.jl:136-202   (axial strain + inertia / added mass / drag at 4 Gauss points)
+//   SoilContact toolbox/SoilContact.jl:10-20    (penalty springs/dampers below z₀)
+#pragma once
+#include "beam_kernel.cuh"
+
+namespace mb {
+
+struct BarMat { double EA, mu, w, Cat, Clt, Cqt, Can, Cln, Cqn; };      // AxisymmetricBarCrossSection, BarElement.jl:36-46
+struct BarGroupDev {
+    int64_t nele;
+    const double* geo;        // [nele][8]  cₘ3 tgₘ3 L₀ Lₛ
+    const BarMat* mats;
+    const int32_t* mat_id;
+    const int32_t* idxX;      // [nele][6]
+    const int32_t* idxU;      // [nele][3] or nullptr
+    double scaleX[6];
+    int udof;
+};
+
+// residual(o::Bar3D,…) for one element. X[ider][6] carry the seeds; the Gauss point motion x = c + tg·ζ is linear in the nodal motion,
+// so velocity/acceleration are ψ₁·u̇₁ + ψ₂·u̇₂ (the reference reaches the same through motion{P}/motion⁻¹, BarElement.jl:170,189).
+template <int ND, class S> MB_HD void bar_residual(const double* geo8, const BarMat& m, const S (*X)[6], bool udof, const S* U0, double t, S* R) {
+    const double L0 = geo8[6], Ls = geo8[7];
+    Vec3<S> tg;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tg[i] = (geo8[3 + i] + X[0][3 + i]) - X[0][i];
+    S L = mb_sqrt((tg[0] * tg[0] + tg[1] * tg[1]) + tg[2] * tg[2]);
+    S iL = mb_rcp(L);
+    Vec3<S> d0{tg[0] * iL, tg[1] * iL, tg[2] * iL};
+    S fint = m.EA * (L * (1.0 / Ls) - 1.0);
+    const double fwz = (fmin(t, -5.) + 10) / 5 * m.w;
+    S z = Make<S>::c(0.);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) R[j] = z;
+    S sumw_fint = z;
+#pragma unroll
+    for (int g = 0; g < NGP; ++g) {
+        const GpConst c = gp_const(g);
+        const double p1 = -c.z + 0.5, p2 = c.z + 0.5, wg = c.w * L0;
+        Vec3<S> fe{z, z, z};
+        if (ND >= 2) {
+            Vec3<S> v, a;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                v[i] = p1 * X[1][i] + p2 * X[1][3 + i];
+                a[i] = (ND >= 3) ? (p1 * X[2][i] + p2 * X[2][3 + i]) : z;
+            }
+            S at = (a[0] * d0[0] + a[1] * d0[1]) + a[2] * d0[2];
+            S vt = (v[0] * d0[0] + v[1] * d0[1]) + v[2] * d0[2];
+            S an1 = a[1] - at * d0[1], an2 = a[2] - at * d0[2];
+            S vn1 = v[1] - vt * d0[1], vn2 = v[2] - vt * d0[2];
+            S fqt = m.Cqt * (vt * vt); if (value(vt) < 0) fqt = -fqt;
+            S fq1 = m.Cqn * (vn1 * vn1); if (value(vn1) < 0) fq1 = -fq1;
+            S fq2 = m.Cqn * (vn2 * vn2); if (value(vn2) < 0) fq2 = -fq2;
+            fe[0] = (m.mu * a[0] + m.Cat * at) + (m.Clt * vt + fqt);
+            fe[1] = (m.mu * a[1] + m.Can * an1) + (m.Cln * vn1 + fq1);
+            fe[2] = (m.mu * a[2] + m.Can * an2) + (m.Cln * vn2 + fq2);
+        }
+        fe[2] = fe[2] + fwz;
+        if (udof) for (int i = 0; i < 3; ++i) fe[i] = fe[i] - U0[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { R[i] = R[i] + (wg * p1) * fe[i]; R[3 + i] = R[3 + i] + (wg * p2) * fe[i]; }
+        sumw_fint = sumw_fint + wg * fint;
+    }
+    // fᵢ ∘₀ ε∂X₀ with ε∂X₀ = (−δ₀, δ₀)/L₀  (BarElement.jl:181)
+    S k = sumw_fint * (1.0 / L0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { S q = k * d0[i]; R[i] = R[i] - q; R[3 + i] = R[3 + i] + q; }
+}
+
+template <int ND, bool STEP>
+__global__ void __launch_bounds__(128)
+bar_kernel(BarGroupDev g, StateDev st, NewmarkDev nm, double t, double* __restrict__ Ke, double* __restrict__ Re, double* __restrict__ Rp,
+           unsigned long long* nanflag, unsigned long long nanbase) {
+    constexpr int W = 6 + (STEP ? 1 : 0);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    using S = Dual<W>;
+    double geo8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) geo8[k] = g.geo[e * 8 + k];
+    const BarMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    S X[3][6], U[3], R[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int32_t d = g.idxX[e * 6 + i];
+        const double x0 = st.X0[d], x1 = (ND >= 2) ? st.X1[d] : 0., x2 = (ND >= 3) ? st.X2[d] : 0.;
+        X[0][i] = Make<S>::c(x0); X[1][i] = Make<S>::c(x1); X[2][i] = Make<S>::c(x2);
+        X[0][i].d[i] = g.scaleX[i]; X[1][i].d[i] = nm.a1 * g.scaleX[i]; X[2][i].d[i] = nm.b1 * g.scaleX[i];
+        if (STEP) { X[1][i].d[W - 1] = nm.a2 * x1 + nm.a3 * x2; X[2][i].d[W - 1] = nm.b2 * x1 + nm.b3 * x2; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U[i] = Make<S>::c((g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.);
+    bar_residual<ND, S>(geo8, m, X, g.udof != 0, U, t, R);
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double s = g.scaleX[i];
+        double v = R[i].v * s; bad |= (v != v); Re[e * 6 + i] = v;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { double k = R[i].d[j] * s; bad |= (k != k); Ke[e * 36 + i + 6 * j] = k; }
+        if (STEP) { double p = R[i].d[W - 1] * s; bad |= (p != p); Rp[e * 6 + i] = p; }
+    }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+
+struct SoilGroupDev { int64_t nele; const double* par; const int32_t* idxX; double scaleX[3]; };   // par [nele][5] z₀ Kh Kv Ch Cv
+template <int ND, bool STEP>
+__global__ void soil_kernel(SoilGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke, double* __restrict__ Re, double* __restrict__ Rp,
+                            unsigned long long* nanflag, unsigned long long nanbase) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    const double z0 = g.par[e * 5], Kh = g.par[e * 5 + 1], Kv = g.par[e * 5 + 2], Ch = g.par[e * 5 + 3], Cv = g.par[e * 5 + 4];
+    double x[3], xp[3], xpp[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int32_t d = g.idxX[e * 3 + i];
+        x[i] = st.X0[d]; xp[i] = (ND >= 2) ? st.X1[d] : 0.; xpp[i] = (ND >= 3) ? st.X2[d] : 0.;
+    }
+    const bool contact = x[2] < z0;                                // if z < o.z₀  (SoilContact.jl:14); else R = SVector(0,0,0) and no partials
+    const double K[3] = {Kh, Kh, Kv}, Cc[3] = {Ch, Ch, Cv};
+    bool bad = (x[0] != x[0]) | (x[1] != x[1]) | (x[2] != x[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double s = g.scaleX[i];
+        const double r = contact ? (K[i] * (i == 2 ? x[2] - z0 : x[i]) + Cc[i] * xp[i]) : 0.;
+        Re[e * 3 + i] = r * s; bad |= (r != r);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ke[e * 9 + i + 3 * j] = (contact && i == j) ? s * (K[i] + nm.a1 * Cc[i]) * s : 0.;
+        if (STEP) Rp[e * 3 + i] = contact ? s * Cc[i] * (nm.a2 * xp[i] + nm.a3 * xpp[i]) : 0.;
+    }
+    if (bad && contact) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+
+}  // namespace mb

@@ -1,6 +1,7 @@
 // C ABI of the B200 assembly engine (include/muscade_b200.h). Owns all device memory; no PyTorch, no CPU fallback.
 #include "../../include/muscade_b200.h"
 #include "kernels.cuh"
+#include "bar_kernel.cuh"
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -11,6 +12,12 @@
 #include <vector>
 
 using namespace mb;
+namespace mb {
+void launch_bar(int ND, bool step, const BarGroupDev& g, const StateDev& st, const NewmarkDev& nm, double t, double* Ke, double* Re, double* Rp,
+                unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s);
+void launch_soil(int ND, bool step, const SoilGroupDev& g, const StateDev& st, const NewmarkDev& nm, double* Ke, double* Re, double* Rp,
+                 unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s);
+}
 
 namespace {
 
@@ -22,6 +29,7 @@ struct Group {
     int nx = 0, nu = 0, udof = 0;
     double* geo = nullptr;
     BeamMat* mats = nullptr;
+    BarMat* barmats = nullptr;
     int32_t* mat_id = nullptr;
     int32_t* idxX = nullptr;     // [nele][nx] 0-based
     int32_t* idxU = nullptr;
@@ -374,7 +382,7 @@ template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group
     h->launches += STEP ? 2 : 1;
 }
 
-static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm) {
+static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm, double tnow) {
     const bool step = (mission == 0) && OX > 0;
     StateDev sd{h->X0, h->X1, h->X2, h->ndofU > 0 ? h->U0 : nullptr};
     for (size_t ig = 0; ig < h->groups.size(); ++ig) {
@@ -389,6 +397,17 @@ static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkD
             if (OX == 0) launch_beam_w<1, false>(h, g, gd, sd, nm, nanbase);
             else if (OX == 1) { if (step) launch_beam_w<2, true>(h, g, gd, sd, nm, nanbase); else launch_beam_w<2, false>(h, g, gd, sd, nm, nanbase); }
             else { if (step) launch_beam_w<3, true>(h, g, gd, sd, nm, nanbase); else launch_beam_w<3, false>(h, g, gd, sd, nm, nanbase); }
+        }
+        else if (g.kind == G_BAR) {
+            BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+            for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
+            launch_bar(OX + 1, step, gd, sd, nm, tnow, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
+            h->launches++;
+        } else if (g.kind == G_SOIL) {
+            SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
+            for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
+            launch_soil(OX + 1, step, gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
+            h->launches++;
         }
         // G_HOST: contributions were uploaded by mb_set_host_elements
     }
@@ -407,10 +426,9 @@ int32_t mb_sweepx_assemble_dev(mb_handle* h, int32_t OX, int32_t mission, double
     ARG(h->prepared, "call mb_sweepx_prepare first");
     ARG(OX >= 0 && OX <= 2 && (mission == 0 || mission == 1) && newmark, "bad OX / mission / newmark");
     CK(cudaSetDevice(h->device));
-    (void)t;
     NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
     CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
-    int32_t rc = launch_elements(h, OX, mission, nm);
+    int32_t rc = launch_elements(h, OX, mission, nm, t);
     if (rc) return rc;
     launch_gather(h, mission == 0 && OX > 0);
     CK(cudaGetLastError());
@@ -463,7 +481,6 @@ int32_t mb_sweepx_time_dev(mb_handle* h, int32_t OX, int32_t mission, double t, 
     if (!h) return MB_ERR_ARG;
     ARG(h->prepared && reps >= 1 && ms && newmark, "bad argument");
     CK(cudaSetDevice(h->device));
-    (void)t;
     NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
     cudaEvent_t e0, e1, e2;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
@@ -471,7 +488,7 @@ int32_t mb_sweepx_time_dev(mb_handle* h, int32_t OX, int32_t mission, double t, 
     CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
     for (int r = 0; r < reps; ++r) {
         CK(cudaEventRecord(e0, h->stream));
-        launch_elements(h, OX, mission, nm);
+        launch_elements(h, OX, mission, nm, t);
         CK(cudaEventRecord(e1, h->stream));
         launch_gather(h, mission == 0 && OX > 0);
         CK(cudaEventRecord(e2, h->stream));
@@ -547,14 +564,56 @@ int32_t mb_host_unregister(mb_handle* h, void* p) {
     return MB_OK;
 }
 
-// not yet implemented element types: fail loudly rather than silently skipping physics
-int32_t mb_add_bar3d(mb_handle* h, int64_t, const double*, int32_t, const int64_t*, const int64_t*, const double*, const double*, int32_t*) {
-    if (h) h->err = "Bar3D device kernel not built into this library yet";
-    return MB_ERR_STATE;
+int32_t mb_add_bar3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t udof, const int64_t* idxX, const int64_t* idxU,
+                     const double* scaleX, const double* scaleU, int32_t* ieletyp_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared, "groups must be added before prepare");
+    ARG(nele >= 0 && eleobj && idxX && scaleX, "null argument");
+    ARG(!udof || (idxU && scaleU), "Udof element type needs idxU and scaleU");
+    CK(cudaSetDevice(h->device));
+    Group g;
+    g.kind = G_BAR; g.nele = nele; g.nx = 6; g.nu = udof ? 3 : 0; g.udof = udof;
+    // reference struct (38 doubles, toolbox/BarElement.jl:89-101): cₘ3 tgₘ3 tgₑ3 L₀ Lₛ mat9 wgp4 ζgp4 ζnod2 ψ₁4 ψ₂4
+    std::vector<double> geo((size_t)nele * 8);
+    std::vector<BarMat> mats; std::vector<int32_t> mat_id((size_t)nele);
+    std::map<std::string, int32_t> seen;
+    for (int64_t e = 0; e < nele; ++e) {
+        const double* o = eleobj + e * 38; double* q = geo.data() + e * 8;
+        for (int k = 0; k < 6; ++k) q[k] = o[k];
+        q[6] = o[9]; q[7] = o[10];
+        std::string key((const char*)(o + 11), 9 * sizeof(double));
+        auto it = seen.find(key);
+        if (it == seen.end()) { BarMat m; std::memcpy(&m, o + 11, sizeof m); it = seen.emplace(key, (int32_t)mats.size()).first; mats.push_back(m); }
+        mat_id[(size_t)e] = it->second;
+    }
+    CK(dalloc(h, &g.geo, nele * 8));
+    CK(cudaMemcpy(g.geo, geo.data(), geo.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(dalloc(h, &g.barmats, (int64_t)mats.size()));
+    CK(cudaMemcpy(g.barmats, mats.data(), mats.size() * sizeof(BarMat), cudaMemcpyHostToDevice));
+    if (mats.size() > 1) { CK(dalloc(h, &g.mat_id, nele)); CK(cudaMemcpy(g.mat_id, mat_id.data(), mat_id.size() * sizeof(int32_t), cudaMemcpyHostToDevice)); }
+    int32_t rc = upload_index(h, idxX, nele * 6, 0, &g.idxX);
+    if (rc) return rc;
+    if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU); if (rc) return rc; }
+    for (int i = 0; i < 6; ++i) g.scaleX[i] = scaleX[i];
+    h->groups.push_back(g);
+    if (ieletyp_out) *ieletyp_out = (int32_t)h->groups.size();
+    return MB_OK;
 }
-int32_t mb_add_soilcontact(mb_handle* h, int64_t, const double*, const int64_t*, const double*, int32_t*) {
-    if (h) h->err = "SoilContact device kernel not built into this library yet";
-    return MB_ERR_STATE;
+int32_t mb_add_soilcontact(mb_handle* h, int64_t nele, const double* eleobj, const int64_t* idxX, const double* scaleX, int32_t* ieletyp_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared, "groups must be added before prepare");
+    ARG(nele >= 0 && eleobj && idxX && scaleX, "null argument");
+    CK(cudaSetDevice(h->device));
+    Group g;
+    g.kind = G_SOIL; g.nele = nele; g.nx = 3;
+    CK(dalloc(h, &g.geo, nele * 5));
+    CK(cudaMemcpy(g.geo, eleobj, (size_t)nele * 5 * sizeof(double), cudaMemcpyHostToDevice));
+    int32_t rc = upload_index(h, idxX, nele * 3, 0, &g.idxX);
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) g.scaleX[i] = scaleX[i];
+    h->groups.push_back(g);
+    if (ieletyp_out) *ieletyp_out = (int32_t)h->groups.size();
+    return MB_OK;
 }
 
 }  // extern "C"

@@ -51,6 +51,28 @@ class Engine:
         self.groups.append(("eulerbeam3d", nele, 12))
         return ityp.value
 
+    def add_bar3d(self, eleobj, idxX, scaleX, udof=False, idxU=None, scaleU=None):
+        """eleobj (nele,38); idxX (nele,6)"""
+        eleobj = _f64(eleobj); idxX = _i64(idxX); scaleX = _f64(scaleX)
+        nele = eleobj.shape[0]
+        assert eleobj.shape == (nele, 38) and idxX.shape == (nele, 6)
+        idxU = _i64(idxU) if udof else None
+        scaleU = _f64(scaleU) if udof else None
+        ityp = C.c_int32()
+        check(self.h, self.L.mb_add_bar3d(self.h, nele, ptr(eleobj), int(bool(udof)), ptr(idxX), ptr(idxU), ptr(scaleX), ptr(scaleU), C.byref(ityp)))
+        self.groups.append(("bar3d", nele, 6))
+        return ityp.value
+
+    def add_soilcontact(self, eleobj, idxX, scaleX):
+        """eleobj (nele,5) = z₀ Kh Kv Ch Cv; idxX (nele,3)"""
+        eleobj = _f64(eleobj); idxX = _i64(idxX); scaleX = _f64(scaleX)
+        nele = eleobj.shape[0]
+        assert eleobj.shape == (nele, 5) and idxX.shape == (nele, 3)
+        ityp = C.c_int32()
+        check(self.h, self.L.mb_add_soilcontact(self.h, nele, ptr(eleobj), ptr(idxX), ptr(scaleX), C.byref(ityp)))
+        self.groups.append(("soilcontact", nele, 3))
+        return ityp.value
+
     def add_host_elements(self, idxX):
         idxX = _i64(idxX)
         nele, nx = idxX.shape

@@ -85,6 +85,11 @@ def prepare(OX, model, dis, device=0):
         if et.ElType.kind == "eulerbeam3d":
             udof = ed.U.shape[1] > 0
             eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+        elif et.ElType.kind == "bar3d":
+            udof = ed.U.shape[1] > 0
+            eng.add_bar3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+        elif et.ElType.kind == "soilcontact":
+            eng.add_soilcontact(et.eleobj, ed.X, ed.scaleX)
         else:
             if ed.U.shape[1] or ed.A.shape[1]:
                 muscadeerror("host-evaluated element types with U- or A-dofs are not supported in SweepX yet: %s" % (et.key,))

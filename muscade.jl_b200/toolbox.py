@@ -99,6 +99,73 @@ class EulerBeam3D(ElementType):
         return eulerbeam3d_structs(coords[:, 0, :], coords[:, 1, :], mat, orient2)
 
 
+# ------------------------------------------------------------------------------------------------ Bar3D, SoilContact
+BAR_MAT_FIELDS = ("EA", "mu", "w", "Cat", "Clt", "Cqt", "Can", "Cln", "Cqn")
+_BAR_ALIASES = {"μ": "mu", "Caₜ": "Cat", "Clₜ": "Clt", "Cqₜ": "Cqt", "Caₙ": "Can", "Clₙ": "Cln", "Cqₙ": "Cqn"}
+BAR_STRUCT_LEN = 38  # cₘ3 tgₘ3 tgₑ3 L₀ Lₛ mat9 wgp4 ζgp4 ζnod2 ψ₁4 ψ₂4   (toolbox/BarElement.jl:89-101)
+
+
+def AxisymmetricBarCrossSection(**kw):
+    """AxisymmetricBarCrossSection(;EA,μ,w=0.,Caₜ=0.,…)  toolbox/BarElement.jl:36-48 → 9 Float64"""
+    m = np.zeros(9)
+    for k, v in kw.items():
+        m[BAR_MAT_FIELDS.index(_BAR_ALIASES.get(k, k))] = v
+    return m
+
+
+def bar3d_structs(c1, c2, mat, eps_s=np.finfo(float).eps):
+    """Bar3D{Udof}(nod;mat,ϵₛ=eps())  toolbox/BarElement.jl:117-133 → (nele,38)"""
+    c1 = np.atleast_2d(np.asarray(c1, float)); c2 = np.atleast_2d(np.asarray(c2, float))
+    n = c1.shape[0]
+    out = np.zeros((n, BAR_STRUCT_LEN))
+    tgm = c2 - c1
+    L0 = np.sqrt((tgm[:, 0] * tgm[:, 0] + tgm[:, 1] * tgm[:, 1]) + tgm[:, 2] * tgm[:, 2])
+    out[:, 0:3] = (c1 + c2) / 2; out[:, 3:6] = tgm; out[:, 6] = L0; out[:, 9] = L0; out[:, 10] = (1 - eps_s) * L0
+    out[:, 11:20] = np.asarray(mat, float)
+    s65 = np.sqrt(6. / 5); s30 = np.sqrt(30.)
+    zgp = np.array([-1. / 2 * np.sqrt(3. / 7 + 2. / 7 * s65), -1. / 2 * np.sqrt(3. / 7 - 2. / 7 * s65),
+                    +1. / 2 * np.sqrt(3. / 7 - 2. / 7 * s65), +1. / 2 * np.sqrt(3. / 7 + 2. / 7 * s65)])
+    out[:, 20] = L0 / 2 * (18 - s30) / 36; out[:, 21] = L0 / 2 * (18 + s30) / 36; out[:, 22] = L0 / 2 * (18 + s30) / 36; out[:, 23] = L0 / 2 * (18 - s30) / 36
+    out[:, 24:28] = zgp; out[:, 28:30] = (-0.5, 0.5); out[:, 30:34] = -zgp + 1. / 2; out[:, 34:38] = zgp + 1. / 2
+    return out
+
+
+class Bar3D(ElementType):
+    kind = "bar3d"
+
+    @classmethod
+    def doflist(cls, Udof=False, **kw):
+        inod = (1, 1, 1, 2, 2, 2); clas = ("X",) * 6; field = ("t1", "t2", "t3") * 2
+        if Udof:
+            inod += (3, 3, 3); clas += ("U",) * 3; field += ("t1", "t2", "t3")
+        return inod, clas, field
+
+    @classmethod
+    def typekey(cls, Udof=False, **kw):
+        return ("Bar3D", "AxisymmetricBarCrossSection", bool(Udof))
+
+    @classmethod
+    def construct(cls, coords, mat, ϵₛ=np.finfo(float).eps, Udof=False):
+        return bar3d_structs(coords[:, 0, :], coords[:, 1, :], mat, ϵₛ)
+
+
+class SoilContact(ElementType):
+    """SoilContact(nod;z₀=0.,Kh=0.,Kv=0.,Ch=0.,Cv=0.)  toolbox/SoilContact.jl:2-9 → (nele,5)"""
+    kind = "soilcontact"
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1, 1), ("X", "X", "X"), ("t1", "t2", "t3")
+
+    @classmethod
+    def typekey(cls, **kw):
+        return ("SoilContact",)
+
+    @classmethod
+    def construct(cls, coords, z0=0., Kh=0., Kv=0., Ch=0., Cv=0.):
+        return np.tile(np.array([z0, Kh, Kv, Ch, Cv], float), (coords.shape[0], 1))
+
+
 # ------------------------------------------------------------------------------------------------ boundary elements (host evaluated)
 class Hold(ElementType):
     """Hold(nod;field,λfield=Symbol(:λ,field)) = DofConstraint{:X,1,…} with gap(v,t)=v[1], mode=equal (src/BasicElements.jl:484-488).

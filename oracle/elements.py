@@ -45,6 +45,11 @@ def lib():
         L.orc_max_threads.restype = C.c_int
         L.orc_sweepx_assemble_beams_mt.argtypes = [C.c_int64, f64p, i64p, i64p, i64p, C.c_int, f64p, C.c_void_p, C.c_void_p, f64p, f64p, f64p, f64p, C.c_int]
         L.orc_sweepx_assemble_beams_mt.restype = C.c_int
+        L.orc_bar_ctor.argtypes = [f64p, f64p, f64p, C.c_double, f64p]
+        L.orc_bar_residual.argtypes = [f64p, C.c_int, C.c_int, f64p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, f64p, f64p]
+        L.orc_bar_residual.restype = C.c_int
+        L.orc_soil_residual.argtypes = [f64p, C.c_int, C.c_int, f64p, C.c_void_p, f64p, f64p]
+        L.orc_soil_residual.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -196,3 +201,78 @@ def newmark_coefficients(OX, dt, beta=0.25, gamma=0.5):
     if OX == 1:
         return np.array([1 / (gamma * dt), 1 / gamma, 0., 0., 0., 0., dt])
     return np.array([gamma / (beta * dt), gamma / beta, (gamma / (2 * beta) - 1) * dt, 1 / (beta * dt ** 2), 1 / (beta * dt), 1 / (2 * beta), dt])
+
+
+# ------------------------------------------------------------------------------------------------ Bar3D / SoilContact
+BAR_MAT_FIELDS = ("EA", "mu", "w", "Cat", "Clt", "Cqt", "Can", "Cln", "Cqn")
+
+
+def bar_cross_section(**kw):
+    """AxisymmetricBarCrossSection  toolbox/BarElement.jl:36-48"""
+    m = np.zeros(9)
+    for k, v in kw.items():
+        m[BAR_MAT_FIELDS.index(k)] = v
+    return m
+
+
+def bar_ctor(c1, c2, mat, eps_s=np.finfo(float).eps):
+    """Bar3D(nod;mat,ϵₛ)  toolbox/BarElement.jl:117-133 → 38 doubles"""
+    out = np.zeros(38)
+    lib().orc_bar_ctor(np.ascontiguousarray(c1, float), np.ascontiguousarray(c2, float), np.ascontiguousarray(mat, float), float(eps_s), out)
+    return out
+
+
+def bar_residual(elem, X, Xseed=None, U=None, Useed=None, t=0.):
+    """residual(o::Bar3D,…)  toolbox/BarElement.jl:167-202 ; X (nd,6), Xseed (nd,6,np)"""
+    X = np.ascontiguousarray(np.atleast_2d(X), float); nd = X.shape[0]
+    Xseed = np.zeros((nd, 6, 0)) if Xseed is None else np.ascontiguousarray(Xseed, float)
+    np_ = Xseed.shape[2]
+    udof = U is not None
+    if udof:
+        U = np.ascontiguousarray(U, float); Useed = np.zeros((3, np_)) if Useed is None else np.ascontiguousarray(Useed, float)
+    R = np.zeros(6); dR = np.zeros((6, max(np_, 1)))
+    rc = lib().orc_bar_residual(np.ascontiguousarray(elem, float), nd, np_, X, _ptr(Xseed) if np_ else None, int(udof), _ptr(U), _ptr(Useed), float(t), R, dR)
+    return R, dR[:, :np_], rc
+
+
+def soil_residual(elem5, X, Xseed=None):
+    """residual(o::SoilContact,…)  toolbox/SoilContact.jl:10-20 ; X (nd,3)"""
+    X = np.ascontiguousarray(np.atleast_2d(X), float); nd = X.shape[0]
+    Xseed = np.zeros((nd, 3, 0)) if Xseed is None else np.ascontiguousarray(Xseed, float)
+    np_ = Xseed.shape[2]
+    R = np.zeros(3); dR = np.zeros((3, max(np_, 1)))
+    c = lib().orc_soil_residual(np.ascontiguousarray(elem5, float), nd, np_, X, _ptr(Xseed) if np_ else None, R, dR)
+    return R, dR[:, :np_], c
+
+
+def sweepx_addin_generic(residual_fn, nx, idx, asm1, asm2, OX, mission, X, scaleX, newmark, Llambda, nzval):
+    """addin!{mission}(out::AssemblySweepX{OX},…) (src/SweepX.jl:45-96) for any element given `residual_fn(iele, Xval (nd,nx), Xseed (nd,nx,np))`
+    → (R, dR); python loop over elements — small cases only.  idx/asm1 (nele,nx), asm2 (nele,nx²), 1-based."""
+    a1, a2, a3, b1, b2, b3 = newmark[:6]
+    step = mission == "step" and OX > 0
+    np_ = nx + (1 if step else 0)
+    nd = OX + 1
+    for e in range(idx.shape[0]):
+        xv = np.stack([X[d][idx[e] - 1] for d in range(nd)])
+        seed = np.zeros((nd, nx, np_))
+        for i in range(nx):
+            seed[0, i, i] = scaleX[i]
+            if OX >= 1: seed[1, i, i] = a1 * scaleX[i]
+            if OX >= 2: seed[2, i, i] = b1 * scaleX[i]
+        if step:
+            seed[1, :, nx] = a2 * xv[1] + (a3 * xv[2] if OX >= 2 else 0.)
+            if OX >= 2: seed[2, :, nx] = b2 * xv[1] + b3 * xv[2]
+        R, dR = residual_fn(e, xv, seed)
+        R = R * scaleX; dR = dR * scaleX[:, None]
+        for i in range(nx):
+            if asm1[e, i]:
+                Llambda[asm1[e, i] - 1] += R[i]
+        if step:
+            for i in range(nx):
+                if asm1[e, i]:
+                    Llambda[asm1[e, i] - 1] -= dR[i, nx]
+        for i in range(nx):
+            for j in range(nx):
+                k = asm2[e, i + nx * j]
+                if k:
+                    nzval[k - 1] += dR[i, j]

@@ -242,3 +242,45 @@ def test_directxua_prepare_and_big_pattern():
     assert bigasm["colptr"].tolist() == [1, 6, 14, 20, 25, 36, 42, 47, 61, 67, 72, 86, 92, 97, 108, 114, 119, 127, 133, 152]   # :132
     assert bigasm["nzval"][0].tolist() == [1, 2, 13, 14] and bigasm["nzval"][3].tolist() == [7, 8, 19, 20]       # :133-134
     assert bigasm["nzval"][150].tolist() == [595, 596, 615, 616, 635, 636, 655, 656, 681, 682, 707, 708]         # :135
+
+
+# ------------------------------------------------------------------------------------------------ test/TestBarElement.jl
+def test_bar_element_goldens():
+    EAb, L0, mub = 10., 2., 1.
+    b = OE.bar_ctor([0, 0, 0], [L0, 0, 0], OE.bar_cross_section(EA=EAb, mu=mub))
+    assert approx(b[0:3], [L0 / 2, 0, 0]) and approx(b[3:6], [L0, 0, 0]) and approx(b[9], L0)
+    assert approx(b[20:24], [0.34785484513745385, 0.6521451548625462, 0.6521451548625462, 0.34785484513745385])
+    assert approx(b[24:28], [-0.4305681557970263, -0.16999052179242816, 0.16999052179242816, 0.4305681557970263])
+    assert approx(b[30:34], [0.9305681557970262, 0.6699905217924281, 0.33000947820757187, 0.06943184420297371])
+    assert approx(b[34:38], [0.06943184420297371, 0.33000947820757187, 0.6699905217924281, 0.9305681557970262])
+    dx = .1
+    x = np.array([0, 0, 0, dx, 0, 0.])
+    assert approx(OE.bar_residual(b, [x])[0], [-EAb / L0 * dx, 0, 0, EAb / L0 * dx, 0, 0])
+    X = np.zeros((3, 6)); X[0] = x
+    seed = np.zeros((3, 6, 18))
+    for d in range(3):
+        seed[d, np.arange(6), 6 * d + np.arange(6)] = 1
+    R, dR, rc = OE.bar_residual(b, X, seed)
+    K, M = dR[:, :6], dR[:, 12:]
+    kt = (EAb / L0) * dx / (L0 + dx)
+    ap = lambda a, c: abs(a - c) <= RT * max(abs(a), abs(c))
+    assert ap(K[0, 0], EAb / L0) and ap(K[3, 3], EAb / L0) and ap(K[0, 3], -EAb / L0) and ap(K[3, 0], -EAb / L0)
+    for (i, j, v) in [(1, 1, kt), (2, 2, kt), (4, 4, kt), (5, 5, kt), (1, 4, -kt), (4, 1, -kt), (2, 5, -kt), (5, 2, -kt)]:
+        assert ap(K[i, j], v)
+    assert np.linalg.norm(K[np.ix_([0, 3], [1, 2, 4, 5])]) < 1e-12 and np.linalg.norm(K[np.ix_([1, 4], [0, 2, 3, 5])]) < 1e-12
+    for i in range(6):
+        assert ap(M[i, i], mub * L0 / 3) and ap(M[i, (i + 3) % 6], mub * L0 / 6)
+    w = 10
+    bw = OE.bar_ctor([0, 0, 0], [L0, 0, 0], OE.bar_cross_section(EA=EAb, mu=mub, w=w))
+    assert approx(OE.bar_residual(bw, [np.zeros(6)], t=0.)[0], [0, 0, w * L0 / 2, 0, 0, w * L0 / 2])
+
+
+def test_soil_contact_branches():
+    """toolbox/SoilContact.jl:14-18: springs/dampers only below z₀; above, an integer-zero residual without partials"""
+    p = np.array([0.5, 30., 200., 3., 7.])
+    X = np.array([[.1, .2, .3], [1., 2., 3.]]); seed = np.zeros((2, 3, 3)); seed[0, np.arange(3), np.arange(3)] = 1.; seed[1] = 2.5 * seed[0]
+    R, dR, c = OE.soil_residual(p, X, seed)
+    assert c == 1 and approx(R, [30 * .1 + 3 * 1, 30 * .2 + 3 * 2, 200 * (.3 - .5) + 7 * 3]) and approx(dR, np.diag([30 + 7.5, 30 + 7.5, 200 + 17.5]))
+    X[0, 2] = 0.5
+    R, dR, c = OE.soil_residual(p, X, seed)
+    assert c == 0 and np.all(R == 0) and np.all(dR == 0)
