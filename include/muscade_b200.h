@@ -24,7 +24,7 @@ enum { MB_OK = 0, MB_ERR_CUDA = 1, MB_ERR_ARG = 2, MB_ERR_NAN = 3, MB_ERR_STATE 
 
 /* Where the first NaN was found, in element order (deterministic).  Replaces the MuscadeException thrown at
  * src/Assemble.jl:625,630 ("residual(...) returned NaN in R, FB or derivatives"); the wrapper rethrows with (ieletyp,iele). */
-typedef struct { int32_t kind; int32_t ieletyp; int64_t iele; } mb_errinfo;      /* 1-based ieletyp / iele, 0 = none */
+typedef struct { int32_t kind; int32_t ieletyp; int64_t iele; int64_t step; } mb_errinfo;   /* 1-based ieletyp / iele / step, 0 = none */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------------ */
 int32_t     mb_create(int32_t device, mb_handle** out);
@@ -78,6 +78,32 @@ int32_t mb_sync(mb_handle* h, mb_errinfo* where);
 typedef struct { double *X0, *X1, *X2, *U0, *Llambda, *nzval; int32_t *colptr0, *rowval0; int64_t ndofX, ndofU, nnz; } mb_dev_ptrs;
 int32_t mb_get_device_ptrs(mb_handle* h, mb_dev_ptrs* out);
 int32_t mb_set_ndofU(mb_handle* h, int64_t ndofU);
+
+/* ---- DirectXUA{OX,OU,0}: prepare(AssemblyDirect) + preparebig + assemblebig! (src/DirectXUA.jl:22-56, 245-356) -------------------- */
+/* The handle owns the block columns of the time steps [step_lo,step_hi) (0-based) of nstep (one experiment) and stores the per-step
+ * blocks of [step_lo-2,step_hi+2)∩[0,nstep), which its finite-difference stencils reach (src/FiniteDifferences.jl).  Built on the device,
+ * bit-identical to the reference: the class-pair patterns/maps of asmmat! for Λ,X,U and the CSC structure of the owned columns of Lvv
+ * (SparseTools.prepare).  bcolptr/browval: CSC over BLOCKS of the owned block columns (3 per step: Λ,X,U), block row = 3·step+class, as
+ * makepattern (src/DirectXUA.jl:245-307) yields — computed by the host wrapper, a few entries per step.
+ * Element types must be EulerBeam3D (with or without Udof) in this version; IA = 0. */
+int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, int64_t ndofU, int64_t nstep, int64_t step_lo, int64_t step_hi,
+                          double dt, const int32_t* bcolptr, const int32_t* browval, int64_t* ncol_out, int64_t* nnz_out);
+/* class-pair patterns: which = 0 X×X (also Λ×X, X×Λ), 1 X×U (Λ×U), 2 U×X (U×Λ), 3 U×U ; 1-based CSC like SparseMatrixCSC */
+int32_t mb_direct_class_pattern(mb_handle* h, int32_t which, int64_t* nnz, int64_t* colptr, int64_t* rowval);
+/* asm[arrnum(α,β), ieletyp] for the pair type `which` (element entry → nz, 1-based; n_i·n_j × nele, column-major) */
+int32_t mb_direct_get_asm(mb_handle* h, int32_t ieletyp, int32_t which, int64_t* out);
+/* state[iexp][step] → device (X0..X_OX of ndofX, U0 of ndofU); step must be stored on this handle */
+int32_t mb_direct_set_state(mb_handle* h, int64_t step, const double* X0, const double* X1, const double* X2, const double* U0);
+/* assemblebig!{:matrices}: evaluates the steps [eval_lo,eval_hi) (eval_lo<0: all stored steps, i.e. owned + halo recomputed locally),
+ * then, if build_big, forms the owned columns of Lvv (nzval) and rows of Lv; host outputs may be NULL (results stay on the device). */
+int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32_t build_big, double* Lvv_nzval, double* Lv, mb_errinfo* where);
+int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr /* ncol+1 */, int64_t* rowval /* nnz, global rows */);
+/* out.L1/out.L2 of one stored step: which = 0 L1[Λ][1], 1 L2[Λ,X][1,der+1], 2 L2[X,Λ][der+1,1], 3 L2[Λ,U][1,1], 4 L2[U,Λ][1,1] */
+int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int32_t der, double* out);
+/* device pointers of the per-step blocks a neighbouring time-shard needs (halo exchange over NCCL): L2[Λ,X][1,:], L2[Λ,U][1,1], L1[Λ] */
+int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1);
+/* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build */
+int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
 
 /* Page-lock / unlock a host array the caller owns (Julia: the Vector behind out.Lλx.nzval), so that the copies inside
  * mb_sweepx_assemble run at PCIe speed. */

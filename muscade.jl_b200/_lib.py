@@ -18,7 +18,7 @@ f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 
 class ErrInfo(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("ieletyp", C.c_int32), ("iele", C.c_int64)]
+    _fields_ = [("kind", C.c_int32), ("ieletyp", C.c_int32), ("iele", C.c_int64), ("step", C.c_int64)]
 
 
 class DevPtrs(C.Structure):
@@ -52,6 +52,17 @@ SYMBOLS = {
     "mb_measure_fp64_tflops": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_measure_copy_gbs": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_launch_count": (C.c_int64, [H]),
+    "mb_direct_prepare": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mb_direct_class_pattern": (C.c_int32, [H, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "mb_direct_get_asm": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p]),
+    "mb_direct_set_state": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_direct_assemble": (C.c_int32, [H, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(ErrInfo)]),
+    "mb_direct_big_pattern": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
+    "mb_direct_get_step_block": (C.c_int32, [H, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "mb_direct_step_ptrs": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "mb_direct_time_dev": (C.c_int32, [H, C.c_int32, f32p]),
     "mb_host_register": (C.c_int32, [H, C.c_void_p, C.c_int64]),
     "mb_host_unregister": (C.c_int32, [H, C.c_void_p]),
 }

@@ -1,0 +1,2 @@
+#include "beam_kernel.cuh"
+namespace mb { MB_INSTANTIATE_BEAM_DIRECT(3) }

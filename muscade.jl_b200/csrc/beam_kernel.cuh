@@ -133,6 +133,71 @@ beam_dr_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
+// K3: DirectXUA first-order path (src/DirectXUA.jl:85-120, no_second_order elements). Seeds are revariate{1}((;X,U),(;X=scale.X,U=scale.U))
+// (src/Taylor.jl:158-166): one partial per X₀,X₁,…,X_OX dof and per U₀ dof. Lanes per element: 6 per X derivative order d — lane (d,l)
+// carries (rotation dof l of X_d, translation dof l of X_d) — plus 3 lanes for the U₀ dofs of Udof elements.
+// Output dR[e][p][i] = ∂R_i/∂seed_p with p in the reference's flat order X₀(12) X₁(12) X₂(12) U₀(3); R[e][i] unscaled (DirectXUA.jl:105).
+struct DirectStateDev { const double* X[3]; const double* U0; };
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_direct_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag, unsigned long long nanbase) {
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    const int LPE = 6 * ND + (g.udof ? 3 : 0);
+    const int NP = 12 * ND + (g.udof ? 3 : 0);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / LPE;
+    const int lane = (int)(t - e * LPE);
+    if (e >= g.nele) return;
+    const int d = lane / 6, l = lane - 6 * d;          // d == ND ⇒ U lane l (0..2)
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    TU Xu[3][6], U[3]; TR Xv[3][6]; TS Rv[12];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3, iv = iu + 3;
+        const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iv);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Xu[k][i].v = (k < ND) ? st.X[k][du] : 0.; Xu[k][i].d1 = (k == d && i == l) ? g.scaleX[iu] : 0.;
+            Xv[k][i].v = (k < ND) ? st.X[k][dv] : 0.; Xv[k][i].d0 = (k == d && i == l) ? g.scaleX[iv] : 0.;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { U[i].v = g.udof ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = (d == ND && i == l) ? g.scaleU[i] : 0.; }
+    beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, Rv);
+    bool bad = false;
+    double* out = dR + e * (int64_t)(12 * NP);
+    if (d < ND) {
+        const int cu = 12 * d + ((l < 3) ? l : l + 3), cv = cu + 3;
+#pragma unroll
+        for (int i = 0; i < 12; i += 2) {
+            double2 a, b; a.x = Rv[i].d1; a.y = Rv[i + 1].d1; b.x = Rv[i].d0; b.y = Rv[i + 1].d0;
+            bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
+            *reinterpret_cast<double2*>(out + 12 * cu + i) = a;
+            *reinterpret_cast<double2*>(out + 12 * cv + i) = b;
+        }
+    } else {
+        const int cu = 12 * ND + l;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { double v = Rv[i].d1; bad |= (v != v); out[12 * cu + i] = v; }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { double v = Rv[i].v; bad |= (v != v); R[e * 12 + i] = v; }
+    }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+template <int ND> void launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                                          unsigned long long nanbase, cudaStream_t s);
+#define MB_INSTANTIATE_BEAM_DIRECT(ND_)                                                                                              \
+    template <> void launch_beam_direct<ND_>(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R,                 \
+                                             unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s) {              \
+        const int64_t nt = g.nele * (6 * ND_ + (g.udof ? 3 : 0));                                                                    \
+        beam_direct_kernel<ND_><<<(unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase);    \
+    }
+
 // host-side launcher, one translation unit per (ND,STEP) so that the instantiations compile in parallel
 struct BeamLaunch {
     BeamGroupDev g; StateDev st; NewmarkDev nm;

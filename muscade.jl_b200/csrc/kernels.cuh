@@ -11,7 +11,7 @@ namespace mb {
 
 // nzval[k] = Σ_{s ∈ [cstart[k],cstart[k+1])} Ke[src[s]]  — contributions added in the reference's element order
 // (src/Assemble.jl:472,479 → add_∂! :572-588), one thread per non-zero, no atomics.
-__global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src,
+static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src,
                                  const double* __restrict__ Ke, double* __restrict__ nzval) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
@@ -21,7 +21,7 @@ __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
     nzval[k] = acc;
 }
 // Lλ[d] = Σ (Re[q] − Rp[q])  (add_value! then add_∂!{1,:minus}, src/SweepX.jl:56-57)
-__global__ void gather_vec_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc,
+static __global__ void gather_vec_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc,
                                   const double* __restrict__ Re, const double* __restrict__ Rp, double* __restrict__ out) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
@@ -38,7 +38,7 @@ __global__ void gather_vec_kernel(int64_t ndof, const uint32_t* __restrict__ vst
 // ---------------------------------------------------------------------------------------------- pattern construction
 // (jmoddof,imoddof) pairs in the reference's enumeration order: element, jeledof, ieledof (src/Assemble.jl:385-395),
 // packed as j·ndof + i so that an ascending sort is the lexicographic sortperm of (j,i) (:397).
-__global__ void make_pair_keys_kernel(int64_t nele, int nx, const int32_t* __restrict__ idx, uint64_t ndof, uint64_t* __restrict__ keys,
+static __global__ void make_pair_keys_kernel(int64_t nele, int nx, const int32_t* __restrict__ idx, uint64_t ndof, uint64_t* __restrict__ keys,
                                       uint32_t* __restrict__ vals, uint32_t base) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n2 = (int64_t)nx * nx;
@@ -50,7 +50,7 @@ __global__ void make_pair_keys_kernel(int64_t nele, int nx, const int32_t* __res
     keys[base + p] = dj * ndof + di;
     vals[base + p] = base + (uint32_t)p;
 }
-__global__ void make_vec_keys_kernel(int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
+static __global__ void make_vec_keys_kernel(int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     keys[base + q] = (uint32_t)idx[q];
@@ -61,7 +61,7 @@ struct KeyFlag {                      // 1 where a sorted key differs from its p
     __host__ __device__ uint32_t operator()(int64_t s) const { return (s == 0 || k[s] != k[s - 1]) ? 1u : 0u; }
 };
 // For every sorted pair s: asm2[vals[s]] = inz (1-based, src/Assemble.jl:432,444); at the first pair of a non-zero: rowval, cstart.
-__global__ void finish_pattern_kernel(int64_t npair, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+static __global__ void finish_pattern_kernel(int64_t npair, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                       const uint32_t* __restrict__ inz, uint64_t ndof, int32_t* __restrict__ asm2,
                                       int32_t* __restrict__ rowval0, uint32_t* __restrict__ cstart) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +76,7 @@ __global__ void finish_pattern_kernel(int64_t npair, const uint64_t* __restrict_
     if (s == npair - 1) cstart[k] = (uint32_t)npair;
 }
 // colptr0[c] = number of non-zeros in columns < c  (src/Assemble.jl:415-430)
-__global__ void colptr_kernel(int64_t nnz, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cstart, uint64_t ndof,
+static __global__ void colptr_kernel(int64_t nnz, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cstart, uint64_t ndof,
                               int32_t* __restrict__ colptr0) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
@@ -90,7 +90,7 @@ struct KeyFlag32 {
     __host__ __device__ uint32_t operator()(int64_t s) const { return (s == 0 || k[s] != k[s - 1]) ? 1u : 0u; }
 };
 // vstart[d] = first sorted contributor of dof d (dofs without contributors get an empty range)
-__global__ void vstart_kernel(int64_t nvec, const uint32_t* __restrict__ keys, int64_t ndof, uint32_t* __restrict__ vstart) {
+static __global__ void vstart_kernel(int64_t nvec, const uint32_t* __restrict__ keys, int64_t ndof, uint32_t* __restrict__ vstart) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nvec) return;
     const int64_t d = keys[s];
@@ -99,14 +99,14 @@ __global__ void vstart_kernel(int64_t nvec, const uint32_t* __restrict__ keys, i
     if (s == nvec - 1) for (int64_t c = d + 1; c <= ndof; ++c) vstart[c] = (uint32_t)nvec;
 }
 
-__global__ void widen_plus1_kernel(int64_t n, const int32_t* __restrict__ in, int64_t* __restrict__ out, int add) {
+static __global__ void widen_plus1_kernel(int64_t n, const int32_t* __restrict__ in, int64_t* __restrict__ out, int add) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int64_t)in[i] + add;
 }
 
 // ---------------------------------------------------------------------------------------------- measurement
 // FP64 FMA peak: 8 independent chains per thread, no memory traffic.
-__global__ void fp64_peak_kernel(double* out, int iters) {
+static __global__ void fp64_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double m = 1.0000001, c = 1e-9;
     for (int i = 0; i < iters; ++i) {
@@ -115,7 +115,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
     }
     out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
-__global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, int64_t n) {
+static __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 

@@ -1,0 +1,542 @@
+// DirectXUA{OX,OU,0} on the device: per-step `assemble!{:matrices}(out::AssemblyDirect,…)` for no_second_order elements
+// (src/DirectXUA.jl:85-120) and `assemblebig!` (src/DirectXUA.jl:316-356) of the owned time steps into the all-steps
+// system Lvv / Lv (block layout of makepattern/SparseTools.prepare, src/DirectXUA.jl:245-315, src/SparseTools.jl:32-94).
+//
+// Layout: a handle owns the block columns of time steps [lo,hi) (0-based) of nstep; it evaluates and stores the per-step
+// blocks L2[Λ,X][1,j], L2[X,Λ][j,1], L2[Λ,U][1,j], L2[U,Λ][j,1], L1[Λ] for the steps [elo,ehi) = [lo-2,hi+2)∩[0,nstep) whose
+// finite-difference stencils (src/FiniteDifferences.jl) reach its columns.  Lvv is never assembled by scattered adds:
+// one warp per Lvv column walks the blocks of that column and writes each value as the fixed-order weighted sum
+// Σ_der w·Δt^(−der)·block_der[ilv] — deterministic, no atomics, no nnz-sized index map (the map is implicit in the block layout).
+#include "mb_internal.h"
+#include <cub/cub.cuh>
+
+namespace mb {
+template <int ND> void launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                                          unsigned long long nanbase, cudaStream_t s);
+}
+
+namespace {
+
+enum { P_XX = 0, P_XU = 1, P_UX = 2, P_UU = 3 };
+
+struct PairPat {                  // one class-pair pattern of prepare(AssemblyDirect): asmmat! (src/Assemble.jl:373-448)
+    int64_t m = 0, n = 0, nnz = 0, npair = 0;
+    int32_t *colptr0 = nullptr, *rowval0 = nullptr, *asmK = nullptr;
+    uint32_t *cstart = nullptr, *src = nullptr;
+    std::vector<int64_t> gbase;   // per group: first pair id
+};
+
+constexpr int MAXG = 8;
+struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; };
+
+// ---------------------------------------------------------------------------------------------------------------- pattern build
+__global__ void pair_keys_kernel(int64_t nele, int ni, const int32_t* __restrict__ idxR, int nj, const int32_t* __restrict__ idxC, uint64_t nrows,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n2 = (int64_t)ni * nj;
+    if (p >= nele * n2) return;
+    const int64_t e = p / n2;
+    const int r = (int)(p - e * n2);
+    const int j = r / ni, i = r - j * ni;                      // jeledof outer, ieledof inner (src/Assemble.jl:389)
+    keys[base + p] = (uint64_t)idxC[e * nj + j] * nrows + (uint64_t)idxR[e * ni + i];
+    vals[base + p] = base + (uint32_t)p;
+}
+__global__ void finish_pat_kernel(int64_t npair, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ inz,
+                                  uint64_t nrows, int32_t* __restrict__ asmK, int32_t* __restrict__ rowval0, uint32_t* __restrict__ cstart) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npair) return;
+    const uint32_t k = inz[s];
+    asmK[vals[s]] = (int32_t)k;
+    const uint64_t key = keys[s];
+    if (s == 0 || key != keys[s - 1]) { rowval0[k - 1] = (int32_t)(key % nrows); cstart[k - 1] = (uint32_t)s; }
+    if (s == npair - 1) cstart[k] = (uint32_t)npair;
+}
+__global__ void colptr_pat_kernel(int64_t nnz, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cstart, uint64_t nrows, int64_t ncols,
+                                  int32_t* __restrict__ colptr0) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int64_t col = (int64_t)(keys[cstart[k]] / nrows);
+    const int64_t prev = (k == 0) ? -1 : (int64_t)(keys[cstart[k - 1]] / nrows);
+    for (int64_t c = prev + 1; c <= col; ++c) colptr0[c] = (int32_t)k;
+    if (k == nnz - 1) for (int64_t c = col + 1; c <= ncols; ++c) colptr0[c] = (int32_t)nnz;
+}
+struct KeyFlagD {
+    const uint64_t* k;
+    __host__ __device__ uint32_t operator()(int64_t s) const { return (s == 0 || k[s] != k[s - 1]) ? 1u : 0u; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------- per-step gathers
+__device__ __forceinline__ int find_group(const uint32_t* pbase, int n, uint32_t id) {
+    int g = 0;
+    while (g + 1 < n && id >= pbase[g + 1]) ++g;
+    return g;
+}
+// XX-type pattern: L2[Λ,X][1,der] and L2[X,Λ][der,1] of one step (add_∂!{1} and add_∂!{1,:plus,:transpose}, DirectXUA.jl:114-115)
+__global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd,
+                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    double a[3] = {0., 0., 0.}, b[3] = {0., 0., 0.};
+    for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
+        const uint32_t id = src[s];
+        const int g = find_group(G.pbase[P_XX], G.n, id);
+        const uint32_t loc = id - G.pbase[P_XX][g];
+        const int64_t e = loc / 144; const int r = (int)(loc - e * 144); const int jj = r / 12, i = r - 12 * jj;
+        const double* d = dR + G.drbase[g] + e * (int64_t)(12 * G.np[g]);
+        for (int der = 0; der < nd; ++der) { a[der] += d[(12 * der + jj) * 12 + i]; b[der] += d[(12 * der + i) * 12 + jj]; }
+    }
+    for (int der = 0; der < nd; ++der) { LX[der * nnz + k] = a[der]; XL[der * nnz + k] = b[der]; }
+}
+// XU-type (rows X dofs, cols U dofs): L2[Λ,U][1,1];  UX-type: L2[U,Λ][1,1].  Only ∂0(U) enters the toolbox elements.
+__global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd, int transposed,
+                                 const double* __restrict__ dR, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int pat = transposed ? P_UX : P_XU;
+    double a = 0.;
+    for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
+        const uint32_t id = src[s];
+        const int g = find_group(G.pbase[pat], G.n, id);
+        const uint32_t loc = id - G.pbase[pat][g];
+        const int64_t e = loc / 36; const int r = (int)(loc - e * 36);
+        int ix, ju;
+        if (!transposed) { ju = r / 12; ix = r - 12 * ju; }      // rows X (12), cols U (3): r = ix + 12·ju
+        else { ix = r / 3; ju = r - 3 * ix; }                     // rows U (3), cols X (12): r = ju + 3·ix
+        a += dR[G.drbase[g] + e * (int64_t)(12 * G.np[g]) + (12 * nd + ju) * 12 + ix];
+    }
+    out[k] = a;
+}
+__global__ void gather_l1_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ R,
+                                 double* __restrict__ out) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    double acc = 0.;
+    for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) acc += R[vsrc[s]];
+    out[d] = acc;
+}
+__global__ void vec_keys_kernel(int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    keys[base + q] = (uint32_t)idx[q]; vals[base + q] = base + (uint32_t)q;
+}
+__global__ void vstart2_kernel(int64_t nvec, const uint32_t* __restrict__ keys, int64_t ndof, uint32_t* __restrict__ vstart) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nvec) return;
+    const int64_t d = keys[s];
+    const int64_t prev = (s == 0) ? -1 : (int64_t)keys[s - 1];
+    for (int64_t c = prev + 1; c <= d; ++c) vstart[c] = (uint32_t)s;
+    if (s == nvec - 1) for (int64_t c = d + 1; c <= ndof; ++c) vstart[c] = (uint32_t)nvec;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- all-steps system
+struct BigDev {
+    int64_t nX, nU, W;             // W = 2nX+nU rows per step
+    int64_t nstep, lo, hi, elo;    // owned steps [lo,hi), stored steps start at elo (all 0-based)
+    int OX, OU;
+    double dt;
+    const int32_t* bcolptr;        // block pattern of the owned block columns (CSC over blocks), from makepattern
+    const int32_t* browval;        // global block row = 3·step + class (0 Λ, 1 X, 2 U)
+    const int32_t* pc[4]; const int32_t* pr[4];   // class-pair patterns colptr0 / rowval0
+    int64_t pnnz[4];
+    const double *LX, *XL, *LU, *UL, *L1L;        // stored per-step blocks
+    int64_t sLX, sLU, sUL;         // strides per stored step
+};
+__device__ __forceinline__ int pat_of(int ca, int cb) { return (ca == 2 ? 2 : 0) + (cb == 2 ? 1 : 0); }   // class 2 = U
+// finitediff(order,n,s) (src/FiniteDifferences.jl:2-31): weight of offset ds at 0-based step s, or 0 with found=false
+__device__ __forceinline__ bool fd_weight(int order, int64_t n, int64_t s, int64_t ds, double& w) {
+    if (order == 0) { w = 1.; return ds == 0; }
+    const int pos = (s == 0) ? 0 : (s == n - 1 ? 1 : 2);
+    if (order == 1) {
+        if (pos == 0) { if (ds == 0) { w = -1.; return true; } if (ds == 1) { w = 1.; return true; } return false; }
+        if (pos == 1) { if (ds == -1) { w = -1.; return true; } if (ds == 0) { w = 1.; return true; } return false; }
+        if (ds == -1) { w = -.5; return true; } if (ds == 1) { w = .5; return true; } return false;
+    }
+    if (pos == 0) { if (ds == 0) { w = 1.; return true; } if (ds == 1) { w = -2.; return true; } if (ds == 2) { w = 1.; return true; } return false; }
+    if (pos == 1) { if (ds == -2) { w = 1.; return true; } if (ds == -1) { w = -2.; return true; } if (ds == 0) { w = 1.; return true; } return false; }
+    if (ds == -1) { w = 1.; return true; } if (ds == 0) { w = -2.; return true; } if (ds == 1) { w = 1.; return true; } return false;
+}
+__device__ __forceinline__ void decode_col(const BigDev& B, int64_t c, int64_t& step, int& cls, int64_t& lc) {
+    step = B.lo + c / B.W; const int64_t r = c % B.W;
+    if (r < B.nX) { cls = 0; lc = r; } else if (r < 2 * B.nX) { cls = 1; lc = r - B.nX; } else { cls = 2; lc = r - 2 * B.nX; }
+}
+__global__ void big_count_kernel(BigDev B, int64_t ncol, int64_t* __restrict__ cnt) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    int64_t step, lc; int cb;
+    decode_col(B, c, step, cb, lc);
+    const int64_t bc = 3 * (step - B.lo) + cb;
+    int64_t n = 0;
+    for (int32_t q = B.bcolptr[bc]; q < B.bcolptr[bc + 1]; ++q) {
+        const int p = pat_of(B.browval[q] % 3, cb);
+        n += B.pc[p][lc + 1] - B.pc[p][lc];
+    }
+    cnt[c] = n;
+}
+// one warp per owned Lvv column: structure (rowval) and/or values
+template <bool STRUCT>
+__global__ void big_fill_kernel(BigDev B, int64_t ncol, const int64_t* __restrict__ colptr, int64_t* __restrict__ rowval, double* __restrict__ nzval) {
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= ncol) return;
+    int64_t tcol, lc; int cb;
+    decode_col(B, c, tcol, cb, lc);
+    const int64_t bc = 3 * (tcol - B.lo) + cb;
+    int64_t off = colptr[c];
+    for (int32_t q = B.bcolptr[bc]; q < B.bcolptr[bc + 1]; ++q) {
+        const int32_t br = B.browval[q];
+        const int ca = br % 3; const int64_t trow = br / 3;
+        const int p = pat_of(ca, cb);
+        const int32_t p0 = B.pc[p][lc], p1 = B.pc[p][lc + 1];
+        if (STRUCT) {
+            const int64_t g0 = trow * B.W + (ca == 0 ? 0 : (ca == 1 ? B.nX : 2 * B.nX));
+            for (int32_t k = p0 + lane; k < p1; k += 32) rowval[off + (k - p0)] = g0 + B.pr[p][k];
+        } else {
+            // which evaluated step feeds this block, and through which per-step array
+            const double* arr = nullptr; int64_t stride = 0, s = 0, t = 0; int nder = 0; int64_t nnzp = B.pnnz[p];
+            if (ca == 0 && cb != 0) { s = trow; t = tcol; if (cb == 1) { arr = B.LX; stride = B.sLX; nder = B.OX + 1; } else { arr = B.LU; stride = B.sLU; nder = 1; } }
+            else if (cb == 0 && ca != 0) { s = tcol; t = trow; if (ca == 1) { arr = B.XL; stride = B.sLX; nder = B.OX + 1; } else { arr = B.UL; stride = B.sUL; nder = 1; } }
+            double wd[3]; bool on[3] = {false, false, false};
+            double sc = 1.;
+            for (int der = 0; der < nder; ++der) { double w = 0.; on[der] = fd_weight(der, B.nstep, s, t - s, w); wd[der] = w * sc; sc /= B.dt; }
+            const double* a = arr ? arr + (s - B.elo) * stride : nullptr;
+            for (int32_t k = p0 + lane; k < p1; k += 32) {
+                double v = 0.;
+                if (a) for (int der = 0; der < nder; ++der) if (on[der]) v += a[der * nnzp + k] * wd[der];
+                nzval[off + (k - p0)] = v;
+            }
+        }
+        off += p1 - p0;
+    }
+}
+__global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    int64_t step, lc; int cls;
+    decode_col(B, c, step, cls, lc);
+    Lv[c] = (cls == 0) ? B.L1L[(step - B.elo) * B.nX + lc] : 0.;     // addin!(Lvasm,Lv,L1[Λ][1],Λblk)  (DirectXUA.jl:332-341)
+}
+
+}  // namespace
+
+struct DirectData {
+    int OX = 0, OU = 0;
+    int64_t nX = 0, nU = 0, nstep = 0, lo = 0, hi = 0, elo = 0, ehi = 0;
+    double dt = 1.;
+    PairPat pat[4];
+    uint32_t *vstart = nullptr, *vsrc = nullptr;
+    DirGroups G;
+    double *dR = nullptr, *R = nullptr;                 // element outputs of one step
+    double *X = nullptr, *U = nullptr;                  // stored states [step][3][nX], [step][nU]
+    double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
+    int32_t *bcolptr = nullptr, *browval = nullptr;
+    int64_t ncol = 0, nnzbig = 0;
+    int64_t *colptr = nullptr, *rowval = nullptr;
+    double *nzval = nullptr, *Lv = nullptr;
+};
+
+static int32_t build_pattern(mb_handle* h, PairPat& P, bool rowU, bool colU, int64_t nrows, int64_t ncols) {
+    cudaStream_t st = h->stream;
+    P.m = nrows; P.n = ncols; P.gbase.clear();
+    int64_t npair = 0;
+    for (const Group& g : h->groups) { P.gbase.push_back(npair); npair += g.nele * (rowU ? g.nu : g.nx) * (colU ? g.nu : g.nx); }
+    P.gbase.push_back(npair);
+    P.npair = npair;
+    if (npair >= (int64_t)UINT32_MAX) { h->err = "more than 2^32 element-matrix entries on one device"; return MB_ERR_TOOBIG; }
+    CK(dalloc(h, &P.colptr0, ncols + 1));
+    CK(cudaMemsetAsync(P.colptr0, 0, (ncols + 1) * sizeof(int32_t), st));
+    if (npair == 0 || nrows == 0 || ncols == 0) { P.nnz = 0; CK(dalloc(h, &P.rowval0, 1)); CK(dalloc(h, &P.cstart, 1)); CK(dalloc(h, &P.src, 1)); CK(dalloc(h, &P.asmK, 1));
+        CK(cudaMemsetAsync(P.cstart, 0, sizeof(uint32_t), st)); return MB_OK; }
+    uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *inz = nullptr;
+    CK(dalloc(h, &keys, npair)); CK(dalloc(h, &keys2, npair)); CK(dalloc(h, &vals, npair)); CK(dalloc(h, &inz, npair));
+    CK(dalloc(h, &P.src, npair)); CK(dalloc(h, &P.asmK, npair));
+    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+        const Group& g = h->groups[ig];
+        const int ni = rowU ? g.nu : g.nx, nj = colU ? g.nu : g.nx;
+        const int64_t n = g.nele * ni * nj;
+        if (n == 0) continue;
+        pair_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(g.nele, ni, rowU ? g.idxU : g.idxX, nj, colU ? g.idxU : g.idxX, (uint64_t)nrows, keys, vals, (uint32_t)P.gbase[ig]);
+        h->launches++;
+    }
+    int end_bit = 1; while (end_bit < 64 && ((uint64_t)nrows * (uint64_t)ncols) >> end_bit) ++end_bit;
+    void* tmp = nullptr; size_t tmpsz = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, P.src, npair, 0, end_bit, st));
+    CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, P.src, npair, 0, end_bit, st));
+    CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+    cub::CountingInputIterator<int64_t> cnt(0);
+    cub::TransformInputIterator<uint32_t, KeyFlagD, cub::CountingInputIterator<int64_t>> flags(cnt, KeyFlagD{keys2});
+    tmp = nullptr; tmpsz = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, tmpsz, flags, inz, npair, st));
+    CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+    CK(cub::DeviceScan::InclusiveSum(tmp, tmpsz, flags, inz, npair, st));
+    uint32_t last = 0;
+    CK(cudaMemcpyAsync(&last, inz + (npair - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+    P.nnz = last;
+    CK(dalloc(h, &P.rowval0, P.nnz)); CK(dalloc(h, &P.cstart, P.nnz + 1));
+    finish_pat_kernel<<<nblk(npair, 256), 256, 0, st>>>(npair, keys2, P.src, inz, (uint64_t)nrows, P.asmK, P.rowval0, P.cstart);
+    colptr_pat_kernel<<<nblk(P.nnz, 256), 256, 0, st>>>(P.nnz, keys2, P.cstart, (uint64_t)nrows, ncols, P.colptr0);
+    h->launches += 2;
+    CK(cudaStreamSynchronize(st));
+    dfree(h, keys); dfree(h, keys2); dfree(h, vals); dfree(h, inz);
+    return MB_OK;
+}
+
+static BigDev make_bigdev(const DirectData* D) {
+    BigDev B;
+    B.nX = D->nX; B.nU = D->nU; B.W = 2 * D->nX + D->nU; B.nstep = D->nstep; B.lo = D->lo; B.hi = D->hi; B.elo = D->elo; B.OX = D->OX; B.OU = D->OU; B.dt = D->dt;
+    B.bcolptr = D->bcolptr; B.browval = D->browval;
+    for (int p = 0; p < 4; ++p) { B.pc[p] = D->pat[p].colptr0; B.pr[p] = D->pat[p].rowval0; B.pnnz[p] = D->pat[p].nnz; }
+    B.LX = D->LX; B.XL = D->XL; B.LU = D->LU; B.UL = D->UL; B.L1L = D->L1L;
+    B.sLX = (int64_t)(D->OX + 1) * D->pat[P_XX].nnz; B.sLU = D->pat[P_XU].nnz; B.sUL = D->pat[P_UX].nnz;
+    return B;
+}
+
+void mb_direct_release(mb_handle* h) { if (h && h->direct) { delete h->direct; h->direct = nullptr; } }
+
+extern "C" {
+
+int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, int64_t ndofU, int64_t nstep, int64_t step_lo, int64_t step_hi, double dt,
+                          const int32_t* bcolptr, const int32_t* browval, int64_t* ncol_out, int64_t* nnz_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared && !h->direct, "already prepared");
+    ARG(OX >= 0 && OX <= 2 && OU >= 0 && OU <= 2 && ndofX >= 1 && ndofU >= 0 && nstep >= 1 && step_lo >= 0 && step_hi > step_lo && step_hi <= nstep, "bad argument");
+    ARG(bcolptr && browval, "block pattern missing");
+    ARG((int)h->groups.size() <= MAXG, "too many element types");
+    for (const Group& g : h->groups) ARG(g.kind == G_BEAM, "DirectXUA on the device supports EulerBeam3D element types in this version");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    DirectData* D = new DirectData();
+    h->direct = D;
+    D->OX = OX; D->OU = OU; D->nX = ndofX; D->nU = ndofU; D->nstep = nstep; D->lo = step_lo; D->hi = step_hi; D->dt = dt;
+    D->elo = step_lo - 2 < 0 ? 0 : step_lo - 2; D->ehi = step_hi + 2 > nstep ? nstep : step_hi + 2;
+    h->ndofX = ndofX; h->ndofU = ndofU;
+    int32_t rc;
+    if ((rc = build_pattern(h, D->pat[P_XX], false, false, ndofX, ndofX))) return rc;
+    if ((rc = build_pattern(h, D->pat[P_XU], false, true, ndofX, ndofU))) return rc;
+    if ((rc = build_pattern(h, D->pat[P_UX], true, false, ndofU, ndofX))) return rc;
+    if ((rc = build_pattern(h, D->pat[P_UU], true, true, ndofU, ndofU))) return rc;
+    // vector contributors (asmvec! for the Λ group)
+    int64_t nvec = 0, ndr = 0;
+    D->G.n = (int)h->groups.size();
+    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+        const Group& g = h->groups[ig];
+        for (int p = 0; p < 4; ++p) D->G.pbase[p][ig] = (uint32_t)D->pat[p].gbase[ig];
+        D->G.np[ig] = 12 * (OX + 1) + (g.udof ? 3 : 0); D->G.udof[ig] = g.udof;
+        D->G.drbase[ig] = ndr; D->G.rbase[ig] = nvec;
+        ndr += g.nele * 12 * D->G.np[ig]; nvec += g.nele * 12;
+    }
+    for (int p = 0; p < 4; ++p) D->G.pbase[p][h->groups.size()] = (uint32_t)D->pat[p].gbase[h->groups.size()];
+    CK(dalloc(h, &D->vstart, ndofX + 1)); CK(dalloc(h, &D->vsrc, nvec));
+    CK(cudaMemsetAsync(D->vstart, 0, (ndofX + 1) * sizeof(uint32_t), st));
+    if (nvec > 0) {
+        uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
+        CK(dalloc(h, &keys, nvec)); CK(dalloc(h, &keys2, nvec)); CK(dalloc(h, &vals, nvec));
+        for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+            const Group& g = h->groups[ig];
+            if (g.nele == 0) continue;
+            vec_keys_kernel<<<nblk(g.nele * 12, 256), 256, 0, st>>>(g.nele * 12, g.idxX, keys, vals, (uint32_t)D->G.rbase[ig]);
+            h->launches++;
+        }
+        int end_bit = 1; while (end_bit < 32 && ((uint64_t)ndofX >> end_bit)) ++end_bit;
+        void* tmp = nullptr; size_t tmpsz = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, D->vsrc, nvec, 0, end_bit, st));
+        CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, D->vsrc, nvec, 0, end_bit, st));
+        vstart2_kernel<<<nblk(nvec, 256), 256, 0, st>>>(nvec, keys2, ndofX, D->vstart);
+        h->launches++;
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+        dfree(h, keys); dfree(h, keys2); dfree(h, vals);
+    }
+    // buffers
+    const int64_t ns = D->ehi - D->elo;
+    CK(dalloc(h, &D->dR, ndr)); CK(dalloc(h, &D->R, nvec));
+    CK(dalloc(h, &D->X, ns * 3 * ndofX)); CK(dalloc(h, &D->U, ns * (ndofU > 0 ? ndofU : 1)));
+    CK(cudaMemsetAsync(D->X, 0, (size_t)(ns * 3 * ndofX) * sizeof(double), st));
+    CK(cudaMemsetAsync(D->U, 0, (size_t)(ns * (ndofU > 0 ? ndofU : 1)) * sizeof(double), st));
+    CK(dalloc(h, &D->LX, ns * (OX + 1) * D->pat[P_XX].nnz)); CK(dalloc(h, &D->XL, ns * (OX + 1) * D->pat[P_XX].nnz));
+    CK(dalloc(h, &D->LU, ns * D->pat[P_XU].nnz)); CK(dalloc(h, &D->UL, ns * D->pat[P_UX].nnz)); CK(dalloc(h, &D->L1L, ns * ndofX));
+    // block pattern of the owned block columns and the Lvv structure
+    const int64_t nbc = 3 * (step_hi - step_lo);
+    const int32_t nblocks = bcolptr[nbc];
+    CK(dalloc(h, &D->bcolptr, nbc + 1)); CK(dalloc(h, &D->browval, nblocks));
+    CK(cudaMemcpyAsync(D->bcolptr, bcolptr, (nbc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D->browval, browval, (size_t)nblocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    D->ncol = (step_hi - step_lo) * (2 * ndofX + ndofU);
+    CK(dalloc(h, &D->colptr, D->ncol + 1));
+    int64_t* cnt = nullptr; CK(dalloc(h, &cnt, D->ncol + 1));
+    CK(cudaMemsetAsync(cnt, 0, (D->ncol + 1) * sizeof(int64_t), st));
+    BigDev B = make_bigdev(D);
+    big_count_kernel<<<nblk(D->ncol, 256), 256, 0, st>>>(B, D->ncol, cnt);
+    h->launches++;
+    void* tmp = nullptr; size_t tmpsz = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpsz, cnt, D->colptr, D->ncol + 1, st));
+    CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tmpsz, cnt, D->colptr, D->ncol + 1, st));
+    CK(cudaMemcpyAsync(&D->nnzbig, D->colptr + D->ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); cudaFree(tmp); dfree(h, cnt);
+    CK(dalloc(h, &D->rowval, D->nnzbig)); CK(dalloc(h, &D->nzval, D->nnzbig)); CK(dalloc(h, &D->Lv, D->ncol));
+    big_fill_kernel<true><<<nblk(D->ncol * 32, 256), 256, 0, st>>>(B, D->ncol, D->colptr, D->rowval, nullptr);
+    h->launches++;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    h->prepared = true;
+    if (ncol_out) *ncol_out = D->ncol;
+    if (nnz_out) *nnz_out = D->nnzbig;
+    return MB_OK;
+}
+
+int32_t mb_direct_class_pattern(mb_handle* h, int32_t which, int64_t* nnz, int64_t* colptr, int64_t* rowval) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    ARG(which >= 0 && which < 4, "pattern id: 0 XX, 1 XU, 2 UX, 3 UU");
+    CK(cudaSetDevice(h->device));
+    const PairPat& P = h->direct->pat[which];
+    if (nnz) *nnz = P.nnz;
+    if (colptr) { std::vector<int32_t> t((size_t)P.n + 1); CK(cudaMemcpy(t.data(), P.colptr0, t.size() * 4, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < t.size(); ++i) colptr[i] = (int64_t)t[i] + 1; }
+    if (rowval && P.nnz) { std::vector<int32_t> t((size_t)P.nnz); CK(cudaMemcpy(t.data(), P.rowval0, t.size() * 4, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < t.size(); ++i) rowval[i] = (int64_t)t[i] + 1; }
+    return MB_OK;
+}
+int32_t mb_direct_get_asm(mb_handle* h, int32_t ieletyp, int32_t which, int64_t* out) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    ARG(which >= 0 && which < 4 && ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size() && out, "bad argument");
+    CK(cudaSetDevice(h->device));
+    const PairPat& P = h->direct->pat[which];
+    const int64_t n = P.gbase[ieletyp] - P.gbase[ieletyp - 1];
+    std::vector<int32_t> t((size_t)n);
+    if (n) CK(cudaMemcpy(t.data(), P.asmK + P.gbase[ieletyp - 1], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) out[i] = t[(size_t)i];
+    return MB_OK;
+}
+int32_t mb_direct_set_state(mb_handle* h, int64_t step, const double* X0, const double* X1, const double* X2, const double* U0) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi && X0, "step not stored on this handle");
+    CK(cudaSetDevice(h->device));
+    double* x = D->X + (step - D->elo) * 3 * D->nX;
+    const double* src[3] = {X0, X1, X2};
+    for (int d = 0; d <= D->OX; ++d) { ARG(src[d], "state derivative missing"); CK(cudaMemcpyAsync(x + d * D->nX, src[d], (size_t)D->nX * 8, cudaMemcpyHostToDevice, h->stream)); }
+    if (U0 && D->nU) CK(cudaMemcpyAsync(D->U + (step - D->elo) * D->nU, U0, (size_t)D->nU * 8, cudaMemcpyHostToDevice, h->stream));
+    return MB_OK;
+}
+
+static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
+    DirectData* D = h->direct;
+    cudaStream_t st = h->stream;
+    const int nd = D->OX + 1;
+    for (int64_t s = s0; s < s1; ++s) {
+        const int64_t k = s - D->elo;
+        DirectStateDev sd;
+        for (int d = 0; d < 3; ++d) sd.X[d] = D->X + (k * 3 + d) * D->nX;
+        sd.U0 = D->U + k * D->nU;
+        for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+            const Group& g = h->groups[ig];
+            if (g.nele == 0) continue;
+            BeamGroupDev gd;
+            gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+            for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
+            for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+            const unsigned long long nanbase = (((unsigned long long)s) << 44) | (((unsigned long long)ig) << 40);
+            double* dR = D->dR + D->G.drbase[ig]; double* R = D->R + D->G.rbase[ig];
+            if (nd == 1) launch_beam_direct<1>(gd, sd, dR, R, h->nanflag, nanbase, st);
+            else if (nd == 2) launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, st);
+            else launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, st);
+            h->launches++;
+        }
+        const PairPat& XX = D->pat[P_XX];
+        if (XX.nnz) { gather_xx_kernel<<<nblk(XX.nnz, 256), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz); h->launches++; }
+        const PairPat& XU = D->pat[P_XU];
+        if (XU.nnz) { gather_xu_kernel<<<nblk(XU.nnz, 256), 256, 0, st>>>(XU.nnz, XU.cstart, XU.src, D->G, nd, 0, D->dR, D->LU + k * XU.nnz); h->launches++; }
+        const PairPat& UX = D->pat[P_UX];
+        if (UX.nnz) { gather_xu_kernel<<<nblk(UX.nnz, 256), 256, 0, st>>>(UX.nnz, UX.cstart, UX.src, D->G, nd, 1, D->dR, D->UL + k * UX.nnz); h->launches++; }
+        gather_l1_kernel<<<nblk(D->nX, 256), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX);
+        h->launches++;
+    }
+    return MB_OK;
+}
+
+// assemblebig!{:matrices}: evaluate steps [eval_lo,eval_hi) (default: all stored steps, i.e. owned + halo), then build the owned columns of Lvv and Lv.
+int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32_t build_big, double* Lvv_nzval, double* Lv, mb_errinfo* where) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    CK(cudaSetDevice(h->device));
+    if (eval_lo < 0) { eval_lo = D->elo; eval_hi = D->ehi; }
+    ARG(eval_lo >= D->elo && eval_hi <= D->ehi && eval_lo <= eval_hi, "evaluation range outside the stored steps");
+    CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
+    int32_t rc = direct_eval_steps(h, eval_lo, eval_hi);
+    if (rc) return rc;
+    if (build_big) {
+        BigDev B = make_bigdev(D);
+        big_fill_kernel<false><<<nblk(D->ncol * 32, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, nullptr, D->nzval);
+        big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
+        h->launches += 2;
+        if (Lvv_nzval) CK(cudaMemcpyAsync(Lvv_nzval, D->nzval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (Lv) CK(cudaMemcpyAsync(Lv, D->Lv, (size_t)D->ncol * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaGetLastError());
+    rc = mb_sync(h, where);
+    if (rc == MB_ERR_NAN && where) {     // nanbase packs (step, ieletyp, iele)
+        const unsigned long long f = *h->nanflag_host;
+        where->ieletyp = (int32_t)((f >> 40) & 0xF) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = (int64_t)(f >> 44) + 1;
+    }
+    return rc;
+}
+int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    CK(cudaSetDevice(h->device));
+    if (colptr) { CK(cudaMemcpy(colptr, D->colptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
+    if (rowval) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1; }
+    return MB_OK;
+}
+// out.L1 / out.L2 blocks of one stored step: which = 0 L1[Λ] (nX), 1 L2[Λ,X][1,der] , 2 L2[X,Λ][der,1], 3 L2[Λ,U][1,1], 4 L2[U,Λ][1,1]
+int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int32_t der, double* out) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi && out && which >= 0 && which <= 4 && der >= 0 && der <= D->OX, "bad argument");
+    CK(cudaSetDevice(h->device));
+    const int64_t k = step - D->elo, nd = D->OX + 1;
+    const double* src = nullptr; int64_t n = 0;
+    if (which == 0) { src = D->L1L + k * D->nX; n = D->nX; }
+    else if (which == 1) { n = D->pat[P_XX].nnz; src = D->LX + (k * nd + der) * n; }
+    else if (which == 2) { n = D->pat[P_XX].nnz; src = D->XL + (k * nd + der) * n; }
+    else if (which == 3) { n = D->pat[P_XU].nnz; src = D->LU + k * n; }
+    else { n = D->pat[P_UX].nnz; src = D->UL + k * n; }
+    if (n) CK(cudaMemcpy(out, src, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return MB_OK;
+}
+// device pointers and sizes of the per-step blocks, for the halo exchange between time-shards (NCCL send/recv of whole steps)
+int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi, "step not stored on this handle");
+    const int64_t k = step - D->elo, nd = D->OX + 1;
+    if (LX) *LX = D->LX + k * nd * D->pat[P_XX].nnz; if (nLX) *nLX = nd * D->pat[P_XX].nnz;
+    if (LU) *LU = D->LU + k * D->pat[P_XU].nnz; if (nLU) *nLU = D->pat[P_XU].nnz;
+    if (L1L) *L1L = D->L1L + k * D->nX; if (nL1) *nL1 = D->nX;
+    return MB_OK;
+}
+int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms) {
+    if (!h || !h->direct || !ms) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    float a = 0, b = 0;
+    CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
+    for (int r = 0; r < reps; ++r) {
+        CK(cudaEventRecord(e0, h->stream));
+        direct_eval_steps(h, D->lo, D->hi);
+        CK(cudaEventRecord(e1, h->stream));
+        BigDev B = make_bigdev(D);
+        big_fill_kernel<false><<<nblk(D->ncol * 32, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, nullptr, D->nzval);
+        big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
+        h->launches += 2;
+        CK(cudaEventRecord(e2, h->stream));
+        CK(cudaEventSynchronize(e2));
+        float x, y; CK(cudaEventElapsedTime(&x, e0, e1)); CK(cudaEventElapsedTime(&y, e1, e2)); a += x; b += y;
+    }
+    ms[0] = a / reps; ms[1] = b / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return MB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Internal declarations shared by the translation units of libmuscade_b200.so (not part of the C ABI).
+#pragma once
+#include "../../include/muscade_b200.h"
+#include "kernels.cuh"
+#include "bar_kernel.cuh"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mb;
+
+struct mb_handle;
+void mb_direct_release(mb_handle* h);   // mb_direct.cu
+
+enum GroupKind { G_BEAM = 1, G_BAR = 2, G_SOIL = 3, G_HOST = 4 };
+
+struct Group {
+    int kind = 0;
+    int64_t nele = 0;
+    int nx = 0, nu = 0, udof = 0;
+    double* geo = nullptr;
+    BeamMat* mats = nullptr;
+    BarMat* barmats = nullptr;
+    int32_t* mat_id = nullptr;
+    int32_t* idxX = nullptr;     // [nele][nx] 0-based
+    int32_t* idxU = nullptr;
+    double scaleX[12] = {0}, scaleU[3] = {0};
+    int64_t pair_base = 0;       // offset of this group's nx²·nele tangent entries in Ke_all
+    int64_t vec_base = 0;        // offset of this group's nx·nele residual entries in Re_all
+};
+
+struct mb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<Group> groups;
+    // model sizes
+    int64_t ndofX = 0, ndofU = 0, nnz = 0, npair = 0, nvec = 0;
+    bool prepared = false;
+    // state and outputs
+    double *X0 = nullptr, *X1 = nullptr, *X2 = nullptr, *U0 = nullptr, *Ll = nullptr, *nzval = nullptr;
+    // element outputs
+    double *Ke = nullptr, *Re = nullptr, *Rp = nullptr;
+    // maps
+    int32_t *asm2 = nullptr, *colptr0 = nullptr, *rowval0 = nullptr;
+    uint32_t *cstart = nullptr, *src = nullptr, *vstart = nullptr, *vsrc = nullptr;
+    unsigned long long* nanflag = nullptr;
+    unsigned long long* nanflag_host = nullptr;   // pinned
+    int64_t launches = 0;
+    int beamW = 1;
+    std::vector<void*> owned;
+    struct DirectData* direct = nullptr;      // DirectXUA state (mb_direct.cu)
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return MB_ERR_CUDA;                                                                          \
+        }                                                                                                \
+    } while (0)
+#define ARG(cond, msg)                                                                                   \
+    do {                                                                                                 \
+        if (!(cond)) { h->err = msg; return MB_ERR_ARG; }                                                \
+    } while (0)
+
+template <class T> static inline cudaError_t dalloc(mb_handle* h, T** p, int64_t n) {
+    *p = nullptr;
+    if (n <= 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
+    if (e == cudaSuccess) h->owned.push_back(*p);
+    return e;
+}
+static inline void dfree(mb_handle* h, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < h->owned.size(); ++i)
+        if (h->owned[i] == p) { h->owned.erase(h->owned.begin() + i); break; }
+    cudaFree(p);
+}
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// Int64 1-based [nele][n] (reference memory order) → int32 0-based on the device
+static inline int32_t upload_index(mb_handle* h, const int64_t* src, int64_t n, int64_t limit, int32_t** dst) {
+    std::vector<int32_t> tmp((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = src[i];
+        if (v < 1 || (limit > 0 && v > limit) || v > INT32_MAX) { h->err = "dof index out of range (expects 1-based Int64)"; return MB_ERR_ARG; }
+        tmp[(size_t)i] = (int32_t)(v - 1);
+    }
+    CK(dalloc(h, dst, n));
+    CK(cudaMemcpy(*dst, tmp.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return MB_OK;
+}
+

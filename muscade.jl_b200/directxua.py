@@ -1,0 +1,134 @@
+"""DirectXUA on the B200 engine (IA = 0, no_second_order element types): host-side mirror of
+
+  prepare(AssemblyDirect{OX,OU,IA})     src/DirectXUA.jl:22-56    → class-pair patterns / maps built on the device
+  makepattern / preparebig              src/DirectXUA.jl:245-315  → block pattern here (a few entries per step), Lvv structure on the device
+  assemblebig!{:matrices}               src/DirectXUA.jl:316-356  → mb_direct_assemble
+  finitediff                            src/FiniteDifferences.jl:2-31
+
+Time steps are 0-based in this module's arguments (`lo`, `hi`, `step`); block numbers follow the reference: block of (step s, class α)
+is 3·s + α with α = 0 Λ, 1 X, 2 U.  A handle owns the block columns of steps [lo,hi) — the unit of sharding over GPUs.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ErrInfo, check, ptr, MuscadeB200Error
+from .engine import Engine, _f64
+from .model import muscadeerror
+
+_FD = [[[(0, 1.)]],
+       [[(0, -1.), (1, 1.)], [(-1, -1.), (0, 1.)], [(-1, -.5), (1, .5)]],
+       [[(0, 1.), (1, -2.), (2, 1.)], [(-2, 1.), (-1, -2.), (0, 1.)], [(-1, 1.), (0, -2.), (1, 1.)]]]
+
+
+def finitediff(order, n, s):
+    """finitediff(order,n,s): list of (Δs,w); s is the 1-based step as in the reference (src/FiniteDifferences.jl:8-31)"""
+    if order > 0 and n < 6:
+        muscadeerror("Number of steps must be ≥6")
+    if order == 0:
+        return _FD[0][0]
+    return _FD[order][0 if s == 1 else (1 if s == n else 2)]
+
+
+def block_pattern(OX, OU, nstep, lo, hi):
+    """makepattern(IA=0,[nstep],out) restricted to the block columns of steps [lo,hi): CSC over blocks (bcolptr, browval), 0-based block
+    numbers 3·step+class.  Which blocks exist depends only on (OX,OU) and the finite-difference stencils (src/DirectXUA.jl:253-275)."""
+    nder = (1, OX + 1, OU + 1)
+    cols = {}
+    for istep in range(max(1, lo + 1 - 2), min(nstep, hi + 2) + 1):            # evaluation steps that can reach the owned columns
+        for a in range(3):
+            for b in range(3):
+                if a == 0 and b == 0:
+                    continue                                                  # Lλλ is always zero (DirectXUA.jl:41)
+                for ad in range(1, nder[a] + 1):
+                    for bd in range(1, nder[b] + 1):
+                        for (das, _) in finitediff(ad - 1, nstep, istep):
+                            for (dbs, _) in finitediff(bd - 1, nstep, istep):
+                                sc = istep + dbs - 1
+                                if lo <= sc < hi:
+                                    cols.setdefault(3 * sc + b, set()).add(3 * (istep + das - 1) + a)
+    bcolptr = [0]; browval = []
+    for bc in range(3 * lo, 3 * hi):
+        rows = sorted(cols.get(bc, ()))
+        browval.extend(rows); bcolptr.append(len(browval))
+    return np.asarray(bcolptr, np.int32), np.asarray(browval, np.int32)
+
+
+class DirectEngine(Engine):
+    """Engine + the DirectXUA entry points of the C ABI"""
+
+    def direct_prepare(self, OX, OU, ndofX, ndofU, nstep, lo, hi, dt):
+        bcolptr, browval = block_pattern(OX, OU, nstep, lo, hi)
+        ncol, nnz = C.c_int64(), C.c_int64()
+        check(self.h, self.L.mb_direct_prepare(self.h, OX, OU, int(ndofX), int(ndofU), int(nstep), int(lo), int(hi), float(dt), ptr(bcolptr), ptr(browval),
+                                               C.byref(ncol), C.byref(nnz)))
+        self.OX, self.OU, self.ndofX, self.ndofU, self.nstep, self.lo, self.hi = OX, OU, int(ndofX), int(ndofU), nstep, lo, hi
+        self.ncol, self.nnzbig = ncol.value, nnz.value
+        return self.ncol, self.nnzbig
+
+    def class_pattern(self, which):
+        """which: 0 X×X (=Λ×X, X×Λ), 1 X×U, 2 U×X, 3 U×U → (colptr, rowval) 1-based"""
+        n = C.c_int64()
+        check(self.h, self.L.mb_direct_class_pattern(self.h, which, C.byref(n), None, None))
+        ncols = self.ndofU if which in (1, 3) else self.ndofX
+        colptr = np.zeros(ncols + 1, np.int64); rowval = np.zeros(n.value, np.int64)
+        check(self.h, self.L.mb_direct_class_pattern(self.h, which, C.byref(n), ptr(colptr), ptr(rowval)))
+        return colptr, rowval
+
+    def direct_asm(self, ityp, which):
+        nele = self.groups[ityp - 1][1]
+        ni = 3 if which in (2, 3) else 12; nj = 3 if which in (1, 3) else 12
+        out = np.zeros((nele, ni * nj), np.int64)
+        check(self.h, self.L.mb_direct_get_asm(self.h, ityp, which, ptr(out)))
+        return out
+
+    def set_state(self, step, X, U0=None):
+        X = [_f64(x) for x in X]
+        check(self.h, self.L.mb_direct_set_state(self.h, int(step), ptr(X[0]), ptr(X[1]) if len(X) > 1 else None, ptr(X[2]) if len(X) > 2 else None, ptr(_f64(U0))))
+
+    def direct_assemble(self, eval_range=None, build_big=True, Lvv=None, Lv=None):
+        where = ErrInfo()
+        lo, hi = (-1, -1) if eval_range is None else eval_range
+        rc = self.L.mb_direct_assemble(self.h, lo, hi, int(build_big), ptr(Lvv), ptr(Lv), C.byref(where))
+        if rc == _lib.MB_ERR_NAN:
+            raise MuscadeB200Error("residual(...) returned NaN in R, FB or derivatives", dict(step=where.step, ieletyp=where.ieletyp, iele=where.iele))
+        check(self.h, rc)
+
+    def big_pattern(self):
+        colptr = np.zeros(self.ncol + 1, np.int64); rowval = np.zeros(self.nnzbig, np.int64)
+        check(self.h, self.L.mb_direct_big_pattern(self.h, ptr(colptr), ptr(rowval)))
+        return colptr, rowval
+
+    def step_block(self, step, which, der=0):
+        n = {0: self.ndofX}.get(which)
+        if n is None:
+            nn = C.c_int64()
+            check(self.h, self.L.mb_direct_class_pattern(self.h, {1: 0, 2: 0, 3: 1, 4: 2}[which], C.byref(nn), None, None))
+            n = nn.value
+        out = np.zeros(n)
+        check(self.h, self.L.mb_direct_get_step_block(self.h, int(step), which, der, ptr(out)))
+        return out
+
+    def step_ptrs(self, step):
+        p = [C.c_void_p() for _ in range(3)]; n = [C.c_int64() for _ in range(3)]
+        check(self.h, self.L.mb_direct_step_ptrs(self.h, int(step), C.byref(p[0]), C.byref(n[0]), C.byref(p[1]), C.byref(n[1]), C.byref(p[2]), C.byref(n[2])))
+        return [(p[i].value, n[i].value) for i in range(3)]
+
+    def direct_time(self, reps=3):
+        ms = np.zeros(2, np.float32)
+        check(self.h, self.L.mb_direct_time_dev(self.h, reps, ms))
+        return float(ms[0]), float(ms[1])
+
+
+def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0):
+    """prepare(AssemblyDirect{OX,OU,0},model,dis) + preparebig(0,[nstep],out) for the owned steps [lo,hi)"""
+    hi = nstep if hi is None else hi
+    eng = DirectEngine(device)
+    for et, ed in zip(model.ele, dis.dis):
+        if et.ElType.kind != "eulerbeam3d":
+            muscadeerror("DirectXUA on the device supports EulerBeam3D element types in this version: %s" % (et.key,))
+        udof = ed.U.shape[1] > 0
+        eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+    eng.direct_prepare(OX, OU, model.getndof("X"), model.getndof("U"), nstep, lo, hi, dt)
+    return eng

@@ -48,6 +48,7 @@ class Model:
     def __init__(self, ID="muscade_model"):
         self.ID = ID
         self.coord = []                      # model.nod[inod].coord
+        self.coord_chunks = []               # (first inod, 2-D array) for nodes added as a matrix: vectorised lookup
         self.ele = []                        # list of EleTyp  (model.ele / model.eleobj)
         self.ndof = dict(X=0, U=0, A=0)      # length(model.dof[class])
         self.dof_nod = dict(X=[], U=[], A=[])   # model.dof[class][idof].nodID   (list of arrays)
@@ -100,7 +101,21 @@ def addnode(model, coord):
         return len(model.coord)
     first = len(model.coord) + 1
     model.coord.extend(list(coord))
+    model.coord_chunks.append((first, coord.copy()))
     return np.arange(first, first + coord.shape[0], dtype=np.int64)
+
+
+def _node_coords(model, ids):
+    """coordinates of many nodes at once: (n, dim) array; ragged dims (e.g. coordinate-less U/A nodes) give (n,0)"""
+    if len(ids) == 0:
+        return np.zeros((0, 0))
+    for first, arr in model.coord_chunks:
+        if ids.min() >= first and ids.max() < first + arr.shape[0]:
+            return arr[ids - first]
+    dims = {len(model.coord[n - 1]) for n in ids}
+    if len(dims) != 1:
+        return np.zeros((len(ids), 0))
+    return np.asarray([model.coord[n - 1] for n in ids], float).reshape(len(ids), dims.pop())
 
 
 def addelement(model, ElType, nodID, **kwargs):
@@ -120,13 +135,7 @@ def addelement(model, ElType, nodID, **kwargs):
         muscadeerror("Connecting element of type %s: Second dimension of inod (%d) must be equal to element's nnod (%d)" %
                      (ElType.__name__, nnod, max(inod) if inod else 0))
     # element objects first (the reference constructs ele1 before touching the model, so constructor errors leave it intact)
-    if nele_new and all(len(model.coord[n - 1]) == len(model.coord[nodID[0, 0] - 1]) for n in nodID[0]):
-        try:
-            coords = np.asarray([model.coord[n - 1] for n in nodID.reshape(-1)], float).reshape(nele_new, nnod, -1)
-        except ValueError:
-            coords = np.zeros((nele_new, nnod, 0))
-    else:
-        coords = np.zeros((nele_new, nnod, 0))
+    coords = [_node_coords(model, nodID[:, k]) for k in range(nnod)]      # coords[k][iele] = coord(nod)[k] of element iele
     built = ElType.construct(coords, **kwargs)
     eleobj, extra = built if isinstance(built, tuple) else (built, None)
     # element type (getieletyp, ModelDescription.jl:205-213)

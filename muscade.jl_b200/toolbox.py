@@ -96,7 +96,7 @@ class EulerBeam3D(ElementType):
 
     @classmethod
     def construct(cls, coords, mat, orient2=(0., 1., 0.), Udof=False):
-        return eulerbeam3d_structs(coords[:, 0, :], coords[:, 1, :], mat, orient2)
+        return eulerbeam3d_structs(coords[0], coords[1], mat, orient2)
 
 
 # ------------------------------------------------------------------------------------------------ Bar3D, SoilContact
@@ -146,7 +146,7 @@ class Bar3D(ElementType):
 
     @classmethod
     def construct(cls, coords, mat, ϵₛ=np.finfo(float).eps, Udof=False):
-        return bar3d_structs(coords[:, 0, :], coords[:, 1, :], mat, ϵₛ)
+        return bar3d_structs(coords[0], coords[1], mat, ϵₛ)
 
 
 class SoilContact(ElementType):
@@ -163,7 +163,7 @@ class SoilContact(ElementType):
 
     @classmethod
     def construct(cls, coords, z0=0., Kh=0., Kv=0., Ch=0., Cv=0.):
-        return np.tile(np.array([z0, Kh, Kv, Ch, Cv], float), (coords.shape[0], 1))
+        return np.tile(np.array([z0, Kh, Kv, Ch, Cv], float), (coords[0].shape[0], 1))
 
 
 # ------------------------------------------------------------------------------------------------ boundary elements (host evaluated)
@@ -181,7 +181,7 @@ class Hold(ElementType):
 
     @classmethod
     def construct(cls, coords, **kw):
-        return np.zeros((coords.shape[0], 0))
+        return np.zeros((coords[0].shape[0], 0))
 
     @staticmethod
     def residual(eleobj, X, t):
@@ -205,7 +205,7 @@ class DofLoad(ElementType):
 
     @classmethod
     def construct(cls, coords, field, value, args=()):
-        return np.zeros((coords.shape[0], 0)), dict(value=value, args=args)
+        return np.zeros((coords[0].shape[0], 0)), dict(value=value, args=args)
 
     @staticmethod
     def residual(extra, X, t):

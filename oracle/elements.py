@@ -50,6 +50,10 @@ def lib():
         L.orc_bar_residual.restype = C.c_int
         L.orc_soil_residual.argtypes = [f64p, C.c_int, C.c_int, f64p, C.c_void_p, f64p, f64p]
         L.orc_soil_residual.restype = C.c_int
+        L.orc_direct_addin_beams.argtypes = [C.c_int64, f64p, i64p, C.c_void_p, C.c_int, C.c_int, C.c_int, f64p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, f64p, C.c_void_p, i64p, i64p, i64p, C.c_void_p, C.c_void_p,
+                                             f64p, f64p, C.c_int64, f64p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_direct_addin_beams.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -276,3 +280,31 @@ def sweepx_addin_generic(residual_fn, nx, idx, asm1, asm2, OX, mission, X, scale
                 k = asm2[e, i + nx * j]
                 if k:
                     nzval[k - 1] += dR[i, j]
+
+
+# ------------------------------------------------------------------------------------------------ DirectXUA
+def direct_assemble_step_beams(elems, idxX, idxU, OX, OU, X, U, scaleX, scaleU, P, ityp):
+    """assemble!{:matrices}(out::AssemblyDirect{OX,OU,0},…) for one state (one time step), EulerBeam3D type `ityp` (0-based) of the
+    model whose prepare_direct() result is P (src/DirectXUA.jl:85-120, src/Assemble.jl:470-487).
+    Returns dict with L1[1] (Λ) and L2[(1,2)],L2[(2,1)] (lists over X derivative), L2[(1,3)],L2[(3,1)] (lists over U derivative)."""
+    from .pattern import arrnum
+    nd, ndu = OX + 1, OU + 1
+    udof = idxU is not None and idxU.shape[1] == 3
+    asm = P["asm"]
+    T = lambda a: np.ascontiguousarray(a.T, dtype=np.int64)
+    nnz = {ab: len(P["pat"][ab][3]) for ab in P["pat"]}
+    out = dict(L1={1: np.zeros(P["ndof"][0])}, L2={(1, 2): np.zeros((nd, nnz[(1, 2)])), (2, 1): np.zeros((nd, nnz[(2, 1)])),
+                                                  (1, 3): np.zeros((ndu, nnz[(1, 3)])), (3, 1): np.zeros((ndu, nnz[(3, 1)]))})
+    X = [np.ascontiguousarray(x, float) for x in X]; U = [np.ascontiguousarray(u, float) for u in U]
+    aLU = T(asm[arrnum(1, 3)][ityp]) if udof else None; aUL = T(asm[arrnum(3, 1)][ityp]) if udof else None
+    rc = lib().orc_direct_addin_beams(
+        elems.shape[0], np.ascontiguousarray(elems), np.ascontiguousarray(idxX, np.int64), _ptr(np.ascontiguousarray(idxU, np.int64)) if udof else None,
+        int(udof), OX, OU, X[0], _ptr(X[1]) if OX >= 1 else None, _ptr(X[2]) if OX >= 2 else None,
+        _ptr(U[0]) if udof else None, _ptr(U[1]) if (udof and OU >= 1) else None, _ptr(U[2]) if (udof and OU >= 2) else None,
+        np.ascontiguousarray(scaleX, float), _ptr(np.ascontiguousarray(scaleU, float)) if udof else None,
+        T(asm[arrnum(1)][ityp]), T(asm[arrnum(1, 2)][ityp]), T(asm[arrnum(2, 1)][ityp]), _ptr(aLU), _ptr(aUL),
+        out["L1"][1], out["L2"][(1, 2)], nnz[(1, 2)], out["L2"][(2, 1)], nnz[(2, 1)],
+        _ptr(out["L2"][(1, 3)]), nnz[(1, 3)], _ptr(out["L2"][(3, 1)]), nnz[(3, 1)])
+    if rc:
+        raise FloatingPointError("NaN or bad arguments (%d)" % rc)
+    return out

@@ -245,6 +245,53 @@ int orc_sweepx_assemble_beams_mt(int64_t nele, const double* elems69, const int6
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ DirectXUA assembly
+// addin!{:matrices}(out::AssemblyDirect{OX,OU,0},asm,iele,scale,eleobj,no_second_order=Val(true),Λ,X,U,A,…) for one EulerBeam3D type,
+// all elements of one time step (src/DirectXUA.jl:85-120; IA = 0).  Maps are asm[arrnum(·)] of prepare(AssemblyDirect) (1-based, 0 = skip):
+//   asmL 12×nele, asmLX/asmXL 144×nele, asmLU/asmUL 36×nele.  Outputs are ACCUMULATED:
+//   L1L[nΛ] ; L2LX[(OX+1)][nnzΛX], L2XL[(OX+1)][nnzXΛ], L2LU[(OU+1)][nnzΛU], L2UL[(OU+1)][nnzUΛ]  (row-major 2-D arrays)
+int orc_direct_addin_beams(int64_t nele, const double* elems69, const int64_t* idxX, const int64_t* idxU, int udof, int OX, int OU,
+                           const double* X0, const double* X1, const double* X2, const double* U0, const double* U1, const double* U2,
+                           const double* scaleX, const double* scaleU,
+                           const int64_t* asmL, const int64_t* asmLX, const int64_t* asmXL, const int64_t* asmLU, const int64_t* asmUL,
+                           double* L1L, double* L2LX, int64_t nnzLX, double* L2XL, int64_t nnzXL, double* L2LU, int64_t nnzLU, double* L2UL, int64_t nnzUL) {
+    const int nd = OX + 1, ndu = OU + 1;
+    const int np = 12 * nd + (udof ? 3 * ndu : 0);
+    if (np > DV_MAX) return -1;
+    DVctx::np = np;
+    const double* Xs[3] = {X0, X1, X2}; const double* Us[3] = {U0, U1, U2};
+    for (int64_t e = 0; e < nele; ++e) {
+        EulerBeam3D o; unpack_beam(elems69 + 69 * e, o);
+        DV X[3][12], U[3], R[12];
+        for (int d = 0; d < nd; ++d) for (int i = 0; i < 12; ++i) {       // revariate{1}((;X,U),(;X=scale.X,U=scale.U))  Taylor.jl:158-166
+            X[d][i] = DV(Xs[d][idxX[12 * e + i] - 1]);
+            X[d][i].dx[12 * d + i] = scaleX[i];
+        }
+        if (udof) for (int i = 0; i < 3; ++i) { U[i] = DV(Us[0][idxU[3 * e + i] - 1]); U[i].dx[12 * nd + i] = scaleU[i]; }
+        beam_dispatch(nd, [&](auto ND) { beam_residual<decltype(ND)::value>(o, X, udof != 0, U, R); });
+        for (int i = 0; i < 12; ++i) if (hasnan(R[i])) return int(1 + e);
+        const int64_t* mL = asmL + 12 * e;
+        for (int i = 0; i < 12; ++i) if (mL[i]) L1L[mL[i] - 1] += R[i].x;                       // add_value!(Lλ[1],…,R,iλ)
+        for (int j = 0; j < nd; ++j) {                                                          // β = X
+            const int64_t *mLX = asmLX + 144 * e, *mXL = asmXL + 144 * e;
+            for (int i = 0; i < 12; ++i) for (int jj = 0; jj < 12; ++jj) {
+                const double v = R[i].dx[12 * j + jj];
+                int64_t k = mLX[i + 12 * jj]; if (k) L2LX[j * nnzLX + k - 1] += v;              // add_∂!{1}
+                k = mXL[jj + 12 * i];        if (k) L2XL[j * nnzXL + k - 1] += v;               // add_∂!{1,:plus,:transpose}
+            }
+        }
+        if (udof) for (int j = 0; j < ndu; ++j) {                                               // β = U
+            const int64_t *mLU = asmLU + 36 * e, *mUL = asmUL + 36 * e;
+            for (int i = 0; i < 12; ++i) for (int jj = 0; jj < 3; ++jj) {
+                const double v = R[i].dx[12 * nd + 3 * j + jj];
+                int64_t k = mLU[i + 12 * jj]; if (k) L2LU[j * nnzLU + k - 1] += v;
+                k = mUL[jj + 3 * i];         if (k) L2UL[j * nnzUL + k - 1] += v;
+            }
+        }
+    }
+    return 0;
+}
+
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -285,3 +285,45 @@ def preparebig(IA, nstep, nL2, pat):
     nb = 3 * sum(nstep) + (1 if IA == 1 else 0)
     blocks = [(r, c, pat[ab]) for (r, c, ab) in blk]
     return sparsetools_prepare(nb, nb, blocks)
+
+
+def assemblebig(IA, nstep, dt, P, big, bigasm, pgr, outs):
+    """assemblebig!{:matrices}(Lvv,Lv,Lvvasm,Lvasm,…)  src/DirectXUA.jl:316-356 for one experiment and IA = 0.
+
+    outs[istep-1] = per-step `out`: dict(L1={α: (nder, ndofα) or (ndofα,)}, L2={(α,β): (nαder·nβder?, nnz)}) with only the blocks that carry
+    values; L2[(α,β)] is indexed [βder-1] for α==Λ, [αder-1] for β==Λ, and [(αder-1, βder-1)] tuples otherwise (host costs).
+    Returns (Lvv.nzval, Lv)."""
+    assert IA == 0
+    nz = np.zeros(len(big["rowval"])); Lv = np.zeros(big["m"])
+    nL2 = P["nL2"]; nL1 = P["nL1"]
+    for istep in range(1, nstep + 1):
+        out = outs[istep - 1]
+        for b in (1, 2, 3):
+            for bder in range(1, nL1[b] + 1):
+                v = out["L1"].get(b)
+                if v is None:
+                    continue
+                v = np.atleast_2d(v)
+                if bder > v.shape[0]:
+                    continue
+                s = dt ** (1 - bder)
+                for (ds, w) in finitediff(bder - 1, nstep, istep):
+                    addin_vec(pgr, Lv, v[bder - 1], 3 * (istep + ds - 1) + b, w * s)
+        for a in (1, 2, 3):
+            for b in (1, 2, 3):
+                na, nb = nL2[(a, b)]
+                blk = out["L2"].get((a, b))
+                for ad in range(1, na + 1):
+                    for bd in range(1, nb + 1):
+                        if blk is None:
+                            continue
+                        if a == 1: val = blk[bd - 1]
+                        elif b == 1: val = blk[ad - 1]
+                        else: val = blk.get((ad, bd)) if isinstance(blk, dict) else None
+                        if val is None:
+                            continue
+                        s = dt ** (2 - ad - bd)
+                        for (das, wa) in finitediff(ad - 1, nstep, istep):
+                            for (dbs, wb) in finitediff(bd - 1, nstep, istep):
+                                addin_block(bigasm, nz, val, 3 * (istep + das - 1) + a, 3 * (istep + dbs - 1) + b, wa * wb * s)
+    return nz, Lv

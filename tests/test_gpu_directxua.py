@@ -1,0 +1,104 @@
+"""GPU parity, DirectXUA{2,0,0} path (src/DirectXUA.jl:22-120, 245-356): class-pair patterns and maps, per-step out.L1/L2 blocks, the
+all-steps Lvv structure and values and Lv — whole problem on one handle and a time-shard of it — against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import elements as OE
+from oracle import pattern as OP
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel(a, b, floor=0.):
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-300)
+
+
+def udof_chain(mb, N, rng=None):
+    model = mb.Model()
+    coord = np.arange(N + 1)[:, None] * np.array([.8, .6, 0.])[None, :]
+    if rng is not None:
+        coord = coord + rng.uniform(-.1, .1, coord.shape)
+    nod = mb.addnode(model, coord)
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=2.5, GJ=4., mu=1., iota1=1.2, w=.3, Ca2=2., Ca3=1.5, Cq2=1., Cq3=.7, Cl1=.2)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], unod], axis=1), mat=mat, Udof=True)
+    return model
+
+
+def states(mb, nX, nU, nstep):
+    return [([mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.1 if d == 0 else 0.3) for d in range(3)], mb.synthetic.uniform_pm1(99 + s, nU)) for s in range(nstep)]
+
+
+def oracle_all(mb, model, dis, OX, OU, nstep, dt, st):
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+    outs = [OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, OX, OU, X[: OX + 1], [U], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0)
+            for (X, U) in st]
+    nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+    return P, big, outs, nz, Lv
+
+
+@pytest.mark.parametrize("OX", [2, 1, 0])
+def test_directxua_whole_problem(mb, OX):
+    OU, nstep, dt, N = 0, 7, 0.1, 9
+    model = udof_chain(mb, N, np.random.default_rng(1))
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)))
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU = model.getndof("X"), model.getndof("U")
+    st = states(mb, nX, nU, nstep)
+    P, big, outs, nz, Lv = oracle_all(mb, model, dis, OX, OU, nstep, dt, st)
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt)
+    # class-pair patterns and element→nz maps, bit-exact (asm[arrnum(α,β)] of prepare(AssemblyDirect))
+    for which, ab in [(0, (1, 2)), (0, (2, 1)), (0, (2, 2)), (1, (1, 3)), (1, (2, 3)), (2, (3, 1)), (2, (3, 2)), (3, (3, 3))]:
+        cp, rv = eng.class_pattern(which)
+        assert np.array_equal(cp, P["pat"][ab][2]) and np.array_equal(rv, P["pat"][ab][3]), ab
+        assert np.array_equal(eng.direct_asm(1, which).T, P["asm"][OP.arrnum(*ab)][0]), ab
+    # all-steps structure
+    assert eng.ncol == big["n"] and eng.nnzbig == len(big["rowval"])
+    cp, rv = eng.big_pattern()
+    assert np.array_equal(cp, big["colptr"]) and np.array_equal(rv, big["rowval"])
+    for s, (X, U) in enumerate(st):
+        eng.set_state(s, X[: OX + 1], U)
+    Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
+    eng.direct_assemble(Lvv=Lvv, Lv=Lvec)
+    for s in (0, 3, nstep - 1):
+        o = outs[s]
+        scale = max(np.abs(o["L2"][(1, 2)]).max(), 1e-300)
+        assert rel(eng.step_block(s, 0), o["L1"][1], scale) <= TOL
+        for der in range(OX + 1):
+            assert rel(eng.step_block(s, 1, der), o["L2"][(1, 2)][der], scale) <= TOL
+            assert rel(eng.step_block(s, 2, der), o["L2"][(2, 1)][der], scale) <= TOL
+        assert rel(eng.step_block(s, 3), o["L2"][(1, 3)][0], scale) <= TOL and rel(eng.step_block(s, 4), o["L2"][(3, 1)][0], scale) <= TOL
+    assert rel(Lvv, nz) <= TOL, rel(Lvv, nz)
+    assert rel(Lvec, Lv, np.abs(nz).max()) <= TOL
+    Lvv2 = np.zeros(eng.nnzbig)
+    eng.direct_assemble(Lvv=Lvv2)
+    assert np.array_equal(Lvv, Lvv2)          # deterministic
+    eng.close()
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 3), (3, 6), (6, 9)])
+def test_directxua_time_shard(mb, lo, hi):
+    """a handle that owns steps [lo,hi) produces exactly its block columns of the reference's Lvv / rows of Lv"""
+    OX, OU, nstep, dt, N = 2, 0, 9, 0.05, 6
+    model = udof_chain(mb, N)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU = model.getndof("X"), model.getndof("U")
+    st = states(mb, nX, nU, nstep)
+    P, big, outs, nz, Lv = oracle_all(mb, model, dis, OX, OU, nstep, dt, st)
+    W = 2 * nX + nU
+    c0, c1 = lo * W, hi * W
+    p0, p1 = big["colptr"][c0] - 1, big["colptr"][c1] - 1
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, lo, hi)
+    cp, rv = eng.big_pattern()
+    assert np.array_equal(cp - 1, big["colptr"][c0:c1 + 1] - 1 - p0) and np.array_equal(rv, big["rowval"][p0:p1])
+    for s in range(max(0, lo - 2), min(nstep, hi + 2)):
+        eng.set_state(s, st[s][0], st[s][1])
+    Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
+    eng.direct_assemble(Lvv=Lvv, Lv=Lvec)
+    assert rel(Lvv, nz[p0:p1], np.abs(nz).max()) <= TOL
+    assert rel(Lvec, Lv[c0:c1], np.abs(nz).max()) <= TOL
+    eng.close()

@@ -15,7 +15,7 @@ class _Gen:
     @classmethod
     def typekey(cls, **kw): return (cls.NAME,)
     @classmethod
-    def construct(cls, coords, **kw): return np.zeros((coords.shape[0], 0))
+    def construct(cls, coords, **kw): return np.zeros((coords[0].shape[0], 0))
 
 
 class Turbine(_Gen):      # test/SomeElements.jl:54-56
