@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py — EulerBeam3D residual+Jacobian element-assemblies/s (BASELINE.json metric) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nele E] [--ox 0|2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nele E] [--ox 0|1|2] [--workload sweepx|directxua]
   torchrun … bench.py --gpus N …      (one rank per GPU; RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* from the env)
 
-Workload (config.workload): BASELINE.json configs[2] — the inspect/PerformanceEulerBeam3D-style synthetic chain of 10M
+Default workload (config.workload): BASELINE.json configs[2] — the inspect/PerformanceEulerBeam3D-style synthetic chain of 10M
 EulerBeam3D elements per GPU, one SweepX `assemble!{:iter}` per step = element kernels + deterministic
-reduction into Lλ and the CSC nzval.  `value`: state resident in HBM.  `e2e`: through the C-ABI call
-mb_sweepx_assemble with pinned HOST buffers (H2D state, D2H Lλ + nzval inside the timed region).
-Inputs/outputs per step (≈1.3 GB geometry+maps read, ≈20 GB written/re-read) exceed the 126 MB L2: no L2 flush needed.
+reduction into Lλ and the CSC nzval.  `value`: state resident in HBM.  `e2e`: through the C-ABI call mb_sweepx_assemble with
+pinned HOST buffers (H2D state, D2H Lλ + nzval inside the timed region).
+N>1 (weak scaling): the chain has N·E elements, rank r owns elements [r·E,(r+1)·E); every step ends with the interface exchange
+(78 doubles per cut, NCCL send/recv to the right neighbour) — sharding.py.
+Inputs/outputs per step (≈1.8 GB read, ≈20 GB written/re-read per GPU) exceed the 126 MB L2: no L2 flush needed.
+
+`--workload directxua` (BASELINE.json configs[3] shape): DirectXUA{2,0,0} assemblebig! of a Udof beam chain, time steps sharded over
+the ranks (16 steps per GPU), halo L2[Λ,X] blocks of 2 steps exchanged with each neighbour over NCCL.
 
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, "port": Julia is not in this image) on the
 host cores, on a bounded sample of the same workload.
@@ -29,12 +34,10 @@ sys.path.insert(0, ROOT)
 METRIC = "EulerBeam3D residual+Jacobian element-assemblies/s"
 UNIT = "element-assemblies/s"
 
-# Executed FP64 work of the beam kernel per element, this formulation (forward-over-reverse, 12 directional lanes), counted
-# by ncu (profiles/): DFMA·2 + DMUL + DADD per element.  See DESIGN.md §roofline.
-FLOP_PER_ELEMENT = {0: None, 2: None}   # filled from profiles/flops.json when present
-# algorithmic HBM bytes per element-assembly of the element kernel: geometry 128 + dof idx 48 + X gather 96·ND
-# + element tangent 1152 + residual 96 (write)
+
 def alg_bytes_per_element(OX):
+    """algorithmic HBM bytes per element-assembly of the element kernel: geometry line 128 + dof indices 48 +
+    state gather 96·(OX+1) + element tangent 1152 + residual 96 (both written once)"""
     return 128 + 48 + 96 * (OX + 1) + 1152 + 96
 
 
@@ -44,8 +47,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--nele", type=float, default=1e7)
+    ap.add_argument("--workload", default="sweepx")
+    ap.add_argument("--nele", type=float, default=None)
     ap.add_argument("--ox", type=int, default=0)
+    ap.add_argument("--steps-per-gpu", type=int, default=16)
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -115,6 +120,16 @@ def cpu_port_rate(mb, OX, nsample, nthreads):
     return nsample / dt, dt
 
 
+def workload_config(args, OX, nele, world, note=None):
+    c = {"workload": "inspect/PerformanceEulerBeam3D-style synthetic chain, %d EulerBeam3D elements per GPU, SweepX{%d} assemble!{:iter} "
+                     "(residual + 12x12 tangent per element, scatter into Llambda and CSC nzval)" % (nele, OX),
+         "elements_per_gpu": int(nele), "OX": OX, "mission": "iter", "l2": "inputs/outputs larger than L2, no flush",
+         "sharding": "none" if world == 1 else "element ranges, %d ranks, interface rows exchanged over NCCL (78 doubles per cut)" % world}
+    if note:
+        c["note"] = note
+    return c
+
+
 def run_reference(args, rank, world):
     """reference arm: the reference algorithm's CPU port on the host cores (rank 0 only)."""
     if rank != 0:
@@ -126,83 +141,103 @@ def run_reference(args, rank, world):
     nsample = max(1000, int(args.cpu_sample) * max(1, cores // 2))
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_rate(mb, OX, 500, cores)
-    rates, times = [], []
+    times = []
     for _ in range(args.steps):
-        r, dt = cpu_port_rate(mb, OX, nsample, cores)
-        rates.append(r); times.append(dt)
+        _, dt = cpu_port_rate(mb, OX, nsample, cores)
+        times.append(dt)
     value = nsample * len(times) / sum(times)
+    N = int(args.nele or 1e7)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": workload_config(args, OX, nsample, note="bounded sample of the same chain/state; element loop spread over all host threads "
-                                      "(the reference's own loop src/Assemble.jl:479 is serial), serial scatter"),
+            "config": workload_config(args, OX, N, 1, note="bounded sample (%d elements per step) of the same chain/state; element loop spread over all host "
+                                      "threads (the reference's own loop src/Assemble.jl:479 is serial), serial scatter" % nsample),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d elements x %d steps" % (nsample, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, OX, nele, note=None):
-    c = {"workload": "inspect/PerformanceEulerBeam3D-style synthetic chain, %d EulerBeam3D elements per GPU, SweepX{%d} assemble!{:iter} "
-                     "(residual + 12x12 tangent per element, scatter into Llambda and CSC nzval)" % (nele, OX),
-         "elements_per_gpu": int(nele), "OX": OX, "mission": "iter", "l2": "inputs/outputs larger than L2, no flush"}
-    if note:
-        c["note"] = note
-    return c
+def load_flops(OX):
+    try:
+        with open(os.path.join(ROOT, "profiles", "flops.json")) as f:
+            return json.load(f).get("flop_per_element", {}).get(str(OX))
+    except Exception:
+        return None
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_sweepx(args, rank, world, local, dist):
     import muscade_b200 as mb
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     OX = args.ox
-    N = int(args.nele)
+    N = int(args.nele or 1e7)
     eng = mb.Engine(local)
     fp64_peak = eng.fp64_tflops()
-    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=OX > 0)
-    eng.add_eulerbeam3d(eleobj, idx, np.ones(12))
+    torch = None
+    if world > 1:
+        import torch
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eleobj, idx, ndof, dof0 = mb.sharding.chain_shard(N, rank, world, dynamic=OX > 0)
+    ityp = eng.add_eulerbeam3d(eleobj, idx, np.ones(12))
     del eleobj, idx
     nnz = eng.sweepx_prepare(ndof)
-    X = mb.synthetic.state(ndof, nder=OX + 1, seed=0x5EED + 7 * rank)
+    X = mb.synthetic.state(ndof, nder=OX + 1, offset=dof0)
     nm = mb.synthetic.newmark_coefficients(OX, 0.3)
-    # upload state once (resident in HBM for `value`)
     Lh = np.empty(ndof); nzh = np.empty(nnz)
-    eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh)
+    eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh)       # uploads the state once: resident in HBM for `value`
+    sendbuf = recvbuf = None
+    if world > 1:
+        a2f = eng.sweepx_asm_range(ityp, 0, 1)[1][0]; a2l = eng.sweepx_asm_range(ityp, N - 1, N)[1][0]
+        snz, sv, rnz, rvv = mb.sharding.interface_indices(a2l, a2f, ndof, rank, world)
+        eng.iface_setup(snz, sv, rnz, rvv)
+        sendbuf = torch.zeros(max(1, len(snz) + len(sv)), dtype=torch.float64, device="cuda")
+        recvbuf = torch.zeros(max(1, len(rnz) + len(rvv)), dtype=torch.float64, device="cuda")
+
+    def step_dev():
+        eng.sweepx_assemble_dev(OX, "iter", nm)
+        if world > 1:
+            eng.iface_pack(sendbuf.data_ptr())
+            mb.sharding.exchange_neighbours(dist, sendbuf, recvbuf, rank, world)
+            eng.iface_unpack_add(recvbuf.data_ptr())
 
     def barrier():
         eng.sync()
         if dist is not None:
-            dist.barrier()
+            torch.cuda.synchronize(); dist.barrier()
 
-    # ---- device-resident timing: W warm-up, K timed steps, CUDA events on the engine's stream via mb_sweepx_time_dev
     for _ in range(args.warmup):
-        eng.sweepx_assemble_dev(OX, "iter", nm)
+        step_dev()
     barrier()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
-    el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=args.steps)      # events bracket every launch set; returns averages
-    eng.sync()
-    wall = time.perf_counter() - t0
-    launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    step_ms = el_ms + ga_ms
-    if dist is not None:
-        import torch
+    if world == 1:
+        el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=args.steps)   # CUDA events on the engine's stream around every launch set
+        step_ms = el_ms + ga_ms
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step_dev()
+        ev1.record()
+        torch.cuda.synchronize()
+        step_ms = ev0.elapsed_time(ev1) / args.steps
+        el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=2)
         tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         step_ms = float(tt.item())
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
     value = world * N / (step_ms * 1e-3)
 
-    # ---- end to end through the C ABI with pinned host buffers
     e2e = None
     if not args.no_e2e:
         for a in X + [Lh, nzh]:
@@ -216,54 +251,148 @@ def main():
             eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh)
             ts.append(time.perf_counter() - t1)
         e2e_ms = 1e3 * float(np.mean(ts))
-        if dist is not None:
-            import torch
+        if world > 1:
             tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
         e2e = {"value": world * N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(8 * ndof * (OX + 1)), "d2h_bytes_per_step": int(8 * (ndof + nnz)),
-               "note": "mb_sweepx_assemble: pinned host state in, Llambda and nzval out; PCIe-bound (D2H of the CSC values)"}
+               "note": "mb_sweepx_assemble: pinned host state in, Llambda and nzval out (per rank); PCIe-bound (D2H of the CSC values)"}
         for a in X + [Lh, nzh]:
             eng.unpin(a)
 
     if rank == 0:
-        flops = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "flops.json")) as f:
-                flops = json.load(f).get("flop_per_element", {}).get(str(OX))
-        except Exception:
-            pass
-        roof = {"bound": "fp64", "kernel": "beam_kernel<ND=%d>" % (OX + 1), "unit": "TFLOP/s", "peak": fp64_peak,
+        flops = load_flops(OX)
+        roof = {"bound": "fp64", "kernel": "beam_kernel_sd<ND=%d>" % (OX + 1), "unit": "TFLOP/s", "peak": fp64_peak,
                 "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
-                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "traffic": None}
+                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "traffic": None, "achieved": None, "frac": None}
         if flops:
-            roof["flop_per_element"] = flops
-            roof["achieved"] = N * flops / (el_ms * 1e-3) / 1e12
+            roof["flop_per_element"] = flops["flop"]; roof["traffic"] = flops.get("dram_bytes_per_element")
+            roof["achieved"] = N * flops["flop"] / (el_ms * 1e-3) / 1e12
             roof["frac"] = roof["achieved"] / fp64_peak
-        else:
-            roof["achieved"] = None; roof["frac"] = None
-        hbm_peak = None
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                hbm_peak = json.load(f)["hbm_gbs"]
-        except Exception:
-            hbm_peak = 6650.0
-        roof["hbm"] = {"alg_bytes_per_element": alg_bytes_per_element(OX), "achieved_gbs": N * alg_bytes_per_element(OX) / (el_ms * 1e-3) / 1e9,
-                       "peak_gbs": hbm_peak, "frac": N * alg_bytes_per_element(OX) / (el_ms * 1e-3) / 1e9 / hbm_peak}
+            roof["fp64_inst_per_element"] = flops.get("fp64_inst")
+            if flops.get("fp64_inst"):
+                # issue-slot view of the same pipe: DMUL/DADD occupy a DFMA slot but count one flop
+                roof["fp64_pipe_frac"] = N * flops["fp64_inst"] * 2 / (el_ms * 1e-3) / 1e12 / fp64_peak
+        hp, hsrc = hbm_peak()
+        ab = alg_bytes_per_element(OX)
+        roof["hbm"] = {"alg_bytes_per_element": ab, "achieved_gbs": N * ab / (el_ms * 1e-3) / 1e9, "peak_gbs": hp, "peak_source": hsrc,
+                       "frac": N * ab / (el_ms * 1e-3) / 1e9 / hp}
         cpu_rate, cpu_dt = cpu_port_rate(mb, OX, args.cpu_sample, 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args, OX, N), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "config": workload_config(args, OX, N, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                  "sample": "%d elements of the same chain, oracle literal restatement, 1 thread (%.1f s)" % (args.cpu_sample, cpu_dt)},
                 "breakdown_ms": {"element_kernels": el_ms, "segmented_reduction": ga_ms, "wall_timed_region_s": wall}}
         print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def run_directxua(args, rank, world, local, dist):
+    """DirectXUA{2,0,0} assemblebig! with the time steps sharded over the ranks (weak: steps_per_gpu each)."""
+    import muscade_b200 as mb
+    OX, OU = 2, 0
+    N = int(args.nele or 1e5)
+    S = args.steps_per_gpu
+    nstep = S * world
+    lo, hi = rank * S, (rank + 1) * S
+    torch = None
+    model = mb.Model()
+    nod = mb.addnode(model, np.arange(N + 1)[:, None] * np.array([.8, .6, 0.])[None, :])
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1., Ca2=169.6, Ca3=169.6, Cq2=235.2, Cq3=235.2)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], unod], axis=1), mat=mat, Udof=True)
+    st0 = mb.initialize(model)
+    nX, nU = model.getndof("X"), model.getndof("U")
+    eng = mb.directxua.prepare(OX, OU, model, st0.dis, nstep, 0.1, lo, hi, device=local)
+    if world > 1:
+        import torch
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    for s in range(max(0, lo - 2), min(nstep, hi + 2)):
+        eng.set_state(s, [mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.05 if d == 0 else 0.1) for d in range(3)], mb.synthetic.uniform_pm1(99 + s, nU))
+    plan = mb.sharding.directxua_halo_plan(nstep, lo, hi)
+
+    def view(steps):
+        p, n = eng.step_ptrs(steps[0])[0]
+        return torch.as_tensor(mb.sharding.CudaView(p, n * len(steps)), device="cuda")
+
+    bufs = {}
+    if world > 1:
+        for k in ("send_left", "send_right", "recv_left", "recv_right"):
+            if plan[k]:
+                bufs[k] = view(plan[k])
+
+    def step_dev():
+        eng.direct_assemble(eval_range=(lo, hi), build_big=False)
+        if world > 1:
+            ops = []
+            if "send_right" in bufs: ops.append(dist.P2POp(dist.isend, bufs["send_right"], rank + 1))
+            if "send_left" in bufs: ops.append(dist.P2POp(dist.isend, bufs["send_left"], rank - 1))
+            if "recv_left" in bufs: ops.append(dist.P2POp(dist.irecv, bufs["recv_left"], rank - 1))
+            if "recv_right" in bufs: ops.append(dist.P2POp(dist.irecv, bufs["recv_right"], rank + 1))
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        eng.direct_assemble(eval_range=(lo, lo), build_big=True)
+
+    def barrier():
+        eng.sync()
+        if dist is not None:
+            torch.cuda.synchronize(); dist.barrier()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    launches0 = eng.launch_count()
+    if world == 1:
+        a, b = eng.direct_time(reps=args.steps)
+        step_ms = a + b
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step_dev()
+        ev1.record(); torch.cuda.synchronize()
+        step_ms = ev0.elapsed_time(ev1) / args.steps
+        tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms = float(tt.item())
+        a, b = eng.direct_time(reps=1)
+    barrier()
+    launches = eng.launch_count() - launches0
+    if rank == 0:
+        line = {"metric": "EulerBeam3D residual+Jacobian element-step assemblies/s (DirectXUA{2,0,0} assemblebig!)", "value": world * N * S / (step_ms * 1e-3),
+                "unit": "element-step assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "DirectXUA{2,0,0} load identification, %d EulerBeam3D{Udof} elements x %d time steps per GPU, time-sharded; "
+                                       "Lvv columns of the owned steps built on the device" % (N, S),
+                           "elements": N, "steps_per_gpu": S, "nstep": nstep, "lvv_nnz_per_gpu": int(eng.nnzbig),
+                           "halo": "L2[Lambda,X] of 2 steps per neighbour over NCCL send/recv" if world > 1 else "none"},
+                "gpu_launches": int(launches), "breakdown_ms": {"elements_and_step_blocks": a, "lvv_build": b}}
+        print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload == "directxua":
+        run_directxua(args, rank, world, local, dist)
+    else:
+        run_sweepx(args, rank, world, local, dist)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

@@ -61,6 +61,8 @@ int32_t mb_set_host_elements(mb_handle* h, int32_t ieletyp, const double* Re, co
 int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out);
 int32_t mb_sweepx_get_pattern(mb_handle* h, int64_t* colptr /* ndofX+1 */, int64_t* rowval /* nnz */);
 int32_t mb_sweepx_get_asm(mb_handle* h, int32_t ieletyp, int64_t* asm1 /* nx × nele */, int64_t* asm2 /* nx² × nele */);
+/* same for the elements [e0,e1) (0-based) only — the interface elements of a shard */
+int32_t mb_sweepx_get_asm_range(mb_handle* h, int32_t ieletyp, int64_t e0, int64_t e1, int64_t* asm1, int64_t* asm2);
 
 /* assemble!{:step|:iter}(out::AssemblySweepX{OX},…) (src/Assemble.jl:470, src/SweepX.jl:45-96).
  *   mission : 0 = :step, 1 = :iter.   X0,X1,X2 : state.X[1..OX+1] (ndofX each; X1/X2 may be NULL when OX is lower).
@@ -104,6 +106,18 @@ int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int3
 int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1);
 /* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build */
 int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
+
+/* ---- sharding over the GPUs of one box (one handle per GPU / process; NCCL itself is driven by the host, torch.distributed or ncclComm) -- */
+/* Run this handle's kernels and copies on a caller-owned CUDA stream (e.g. the stream NCCL work is ordered against). */
+int32_t mb_set_stream(mb_handle* h, void* cuda_stream);
+/* SweepX element-range sharding: entries of the local Lλ / nzval that belong to nodes shared with a neighbouring shard.
+ *   send_nz / send_v : 1-based positions in nzval / Lλ packed into the send buffer (nz first, then v)
+ *   recv_nz / recv_v : 1-based positions the first n_recv_nz / next n_recv_v received values are ADDED to; a position 0 means
+ *                      "ghost coupling, keep in the receive buffer" (rows owned here, columns of the neighbour's interior node). */
+int32_t mb_iface_setup(mb_handle* h, int64_t n_send_nz, const int64_t* send_nz, int64_t n_send_v, const int64_t* send_v,
+                       int64_t n_recv_nz, const int64_t* recv_nz, int64_t n_recv_v, const int64_t* recv_v);
+int32_t mb_iface_pack_dev(mb_handle* h, double* sendbuf_dev);
+int32_t mb_iface_unpack_add_dev(mb_handle* h, const double* recvbuf_dev);
 
 /* Page-lock / unlock a host array the caller owns (Julia: the Vector behind out.Lλx.nzval), so that the copies inside
  * mb_sweepx_assemble run at PCIe speed. */

@@ -42,6 +42,7 @@ SYMBOLS = {
     "mb_sweepx_prepare": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_int64)]),
     "mb_sweepx_get_pattern": (C.c_int32, [H, i64p, i64p]),
     "mb_sweepx_get_asm": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_sweepx_get_asm_range": (C.c_int32, [H, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mb_sweepx_assemble": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, f64p,
                                         C.c_void_p, C.c_void_p, C.POINTER(ErrInfo)]),
     "mb_sweepx_assemble_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p]),
@@ -63,6 +64,10 @@ SYMBOLS = {
     "mb_direct_step_ptrs": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mb_direct_time_dev": (C.c_int32, [H, C.c_int32, f32p]),
+    "mb_set_stream": (C.c_int32, [H, C.c_void_p]),
+    "mb_iface_setup": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mb_iface_pack_dev": (C.c_int32, [H, C.c_void_p]),
+    "mb_iface_unpack_add_dev": (C.c_int32, [H, C.c_void_p]),
     "mb_host_register": (C.c_int32, [H, C.c_void_p, C.c_int64]),
     "mb_host_unregister": (C.c_int32, [H, C.c_void_p]),
 }

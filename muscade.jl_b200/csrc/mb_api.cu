@@ -44,7 +44,7 @@ int32_t mb_destroy(mb_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     cudaFree(h->nanflag);
     cudaFreeHost(h->nanflag_host);
-    cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return MB_OK;
 }
@@ -258,6 +258,19 @@ int32_t mb_sweepx_get_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
     return MB_OK;
 }
 
+int32_t mb_sweepx_get_asm_range(mb_handle* h, int32_t ieletyp, int64_t e0, int64_t e1, int64_t* asm1, int64_t* asm2) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size(), "bad element type / not prepared");
+    const Group& g = h->groups[ieletyp - 1];
+    ARG(e0 >= 0 && e1 >= e0 && e1 <= g.nele, "element range");
+    CK(cudaSetDevice(h->device));
+    const int64_t n1 = (e1 - e0) * g.nx, n2 = n1 * g.nx;
+    std::vector<int32_t> t((size_t)(n2 > n1 ? n2 : n1));
+    if (asm1 && n1) { CK(cudaMemcpy(t.data(), g.idxX + e0 * g.nx, (size_t)n1 * 4, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < n1; ++i) asm1[i] = (int64_t)t[(size_t)i] + 1; }
+    if (asm2 && n2) { CK(cudaMemcpy(t.data(), h->asm2 + g.pair_base + e0 * g.nx * g.nx, (size_t)n2 * 4, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < n2; ++i) asm2[i] = t[(size_t)i]; }
+    return MB_OK;
+}
+
 int32_t mb_sweepx_get_asm(mb_handle* h, int32_t ieletyp, int64_t* asm1, int64_t* asm2) {
     if (!h) return MB_ERR_ARG;
     ARG(h->prepared && ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size(), "bad element type / not prepared");
@@ -461,6 +474,63 @@ int32_t mb_measure_copy_gbs(mb_handle* h, double* gbs) {
     }
     *gbs = 2.0 * n * sizeof(double2) / (best * 1e-3) / 1e9;
     cudaFree(a); cudaFree(b); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return MB_OK;
+}
+
+int32_t mb_set_stream(mb_handle* h, void* cuda_stream) {
+    if (!h) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream; h->own_stream = false;
+    return MB_OK;
+}
+static __global__ void iface_pack_kernel(int64_t nnz_part, int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ nzval,
+                                         const double* __restrict__ Ll, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (i < nnz_part) ? nzval[idx[i]] : Ll[idx[i]];
+}
+static __global__ void iface_unpack_kernel(int64_t nnz_part, int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ in,
+                                           double* __restrict__ nzval, double* __restrict__ Ll) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // positions are distinct: plain read-modify-write, no atomics
+    if (i < n && idx[i] >= 0) { if (i < nnz_part) nzval[idx[i]] += in[i]; else Ll[idx[i]] += in[i]; }
+}
+int32_t mb_iface_setup(mb_handle* h, int64_t n_send_nz, const int64_t* send_nz, int64_t n_send_v, const int64_t* send_v,
+                       int64_t n_recv_nz, const int64_t* recv_nz, int64_t n_recv_v, const int64_t* recv_v) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared, "call mb_sweepx_prepare first");
+    CK(cudaSetDevice(h->device));
+    auto up = [&](int64_t n1, const int64_t* a, int64_t lim1, int64_t n2, const int64_t* b, int64_t lim2, int32_t** dst) -> int32_t {
+        std::vector<int32_t> t((size_t)(n1 + n2));
+        for (int64_t i = 0; i < n1; ++i) { if (a[i] < 0 || a[i] > lim1) { h->err = "interface index out of range"; return MB_ERR_ARG; } t[(size_t)i] = (int32_t)(a[i] - 1); }
+        for (int64_t i = 0; i < n2; ++i) { if (b[i] < 0 || b[i] > lim2) { h->err = "interface index out of range"; return MB_ERR_ARG; } t[(size_t)(n1 + i)] = (int32_t)(b[i] - 1); }
+        CK(dalloc(h, dst, n1 + n2));
+        if (n1 + n2) CK(cudaMemcpy(*dst, t.data(), t.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        return MB_OK;
+    };
+    int32_t rc = up(n_send_nz, send_nz, h->nnz, n_send_v, send_v, h->ndofX, &h->if_send);
+    if (rc) return rc;
+    rc = up(n_recv_nz, recv_nz, h->nnz, n_recv_v, recv_v, h->ndofX, &h->if_recv);
+    if (rc) return rc;
+    h->if_nsend_nz = n_send_nz; h->if_nsend_v = n_send_v; h->if_nrecv_nz = n_recv_nz; h->if_nrecv_v = n_recv_v;
+    return MB_OK;
+}
+int32_t mb_iface_pack_dev(mb_handle* h, double* sendbuf_dev) {
+    if (!h) return MB_ERR_ARG;
+    const int64_t n = h->if_nsend_nz + h->if_nsend_v;
+    if (n == 0) return MB_OK;
+    ARG(sendbuf_dev, "null buffer");
+    iface_pack_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(h->if_nsend_nz, n, h->if_send, h->nzval, h->Ll, sendbuf_dev);
+    h->launches++;
+    return MB_OK;
+}
+int32_t mb_iface_unpack_add_dev(mb_handle* h, const double* recvbuf_dev) {
+    if (!h) return MB_ERR_ARG;
+    const int64_t n = h->if_nrecv_nz + h->if_nrecv_v;
+    if (n == 0) return MB_OK;
+    ARG(recvbuf_dev, "null buffer");
+    iface_unpack_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(h->if_nrecv_nz, n, h->if_recv, recvbuf_dev, h->nzval, h->Ll);
+    h->launches++;
     return MB_OK;
 }
 

@@ -52,6 +52,9 @@ struct mb_handle {
     int64_t launches = 0;
     int beamW = 1;
     std::vector<void*> owned;
+    bool own_stream = true;
+    int32_t *if_send = nullptr, *if_recv = nullptr;   // interface index lists (0-based into [nzval | Lλ], −1 = ghost)
+    int64_t if_nsend_nz = 0, if_nsend_v = 0, if_nrecv_nz = 0, if_nrecv_v = 0;
     struct DirectData* direct = nullptr;      // DirectXUA state (mb_direct.cu)
 };
 

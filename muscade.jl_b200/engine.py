@@ -107,6 +107,12 @@ class Engine:
         check(self.h, self.L.mb_sweepx_get_asm(self.h, ityp, ptr(asm1), ptr(asm2)))
         return asm1, asm2
 
+    def sweepx_asm_range(self, ityp, e0, e1):
+        _, nele, nx = self.groups[ityp - 1]
+        asm1 = np.zeros((e1 - e0, nx), np.int64); asm2 = np.zeros((e1 - e0, nx * nx), np.int64)
+        check(self.h, self.L.mb_sweepx_get_asm_range(self.h, ityp, int(e0), int(e1), ptr(asm1), ptr(asm2)))
+        return asm1, asm2
+
     def sweepx_assemble(self, OX, mission, X, newmark, U0=None, t=0., Llambda=None, nzval=None, dbg=None):
         """assemble!{mission}: host state in, host Lλ / nzval out (pass preallocated arrays to avoid allocation)."""
         X = [_f64(x) for x in X]
@@ -153,6 +159,19 @@ class Engine:
         v = C.c_double()
         check(self.h, self.L.mb_measure_copy_gbs(self.h, C.byref(v)))
         return v.value
+
+    def set_stream(self, cuda_stream):
+        check(self.h, self.L.mb_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def iface_setup(self, send_nz, send_v, recv_nz, recv_v):
+        a = [_i64(x) for x in (send_nz, send_v, recv_nz, recv_v)]
+        check(self.h, self.L.mb_iface_setup(self.h, len(a[0]), ptr(a[0]), len(a[1]), ptr(a[1]), len(a[2]), ptr(a[2]), len(a[3]), ptr(a[3])))
+
+    def iface_pack(self, dev_ptr):
+        check(self.h, self.L.mb_iface_pack_dev(self.h, C.c_void_p(int(dev_ptr))))
+
+    def iface_unpack_add(self, dev_ptr):
+        check(self.h, self.L.mb_iface_unpack_add_dev(self.h, C.c_void_p(int(dev_ptr))))
 
     def pin(self, a):
         """page-lock a numpy array in place (cudaHostRegister)"""

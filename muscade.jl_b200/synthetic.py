@@ -14,10 +14,10 @@ def splitmix64(seed, counter):
     return z ^ (z >> np.uint64(31))
 
 
-def uniform_pm1(seed, n):
-    """U(−1,1) from splitmix64(seed, dof index)"""
+def uniform_pm1(seed, n, offset=0):
+    """U(−1,1) from splitmix64(seed, dof index); `offset` = first (0-based) dof index, so a shard can generate its own slice"""
     with np.errstate(over="ignore"):
-        u = splitmix64(seed, np.arange(n, dtype=np.uint64))
+        u = splitmix64(seed, np.arange(offset, offset + n, dtype=np.uint64))
     return (u >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
 
 
@@ -37,15 +37,15 @@ def chain(N, h=1.0, mat=None, dynamic=False):
     return eleobj, idx, 6 * (N + 1)
 
 
-def state(ndofX, h=1.0, seed=0x5EED, nder=1, zero=False):
+def state(ndofX, h=1.0, seed=0x5EED, nder=1, zero=False, offset=0):
     """State of SURVEY.md §8d: translations 0.05·h·u, rotations 0.1·u; x′ = 0.1·u′, x″ = 0.1·u″ (seeds +1, +2)."""
     X = []
     for d in range(nder):
         if zero:
             X.append(np.zeros(ndofX)); continue
-        u = uniform_pm1(seed + d, ndofX)
+        u = uniform_pm1(seed + d, ndofX, offset)
         if d == 0:
-            amp = np.where((np.arange(ndofX) % 6) < 3, 0.05 * h, 0.1)
+            amp = np.where(((np.arange(ndofX) + offset) % 6) < 3, 0.05 * h, 0.1)
             X.append(u * amp)
         else:
             X.append(0.1 * u)
