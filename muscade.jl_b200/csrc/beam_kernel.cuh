@@ -28,6 +28,18 @@ struct StateDev { const double *X0, *X1, *X2, *U0; };
 #define MB_BLOCK 128
 #endif
 
+// per-thread scratch in dynamic shared memory: slot k of thread t lives at base[k·blockDim + t] (conflict-free)
+struct SmemScratch {
+    static constexpr bool enabled = true;
+    double* base; int stride;
+    __device__ __forceinline__ void put(int k, double v) { base[k * stride] = v; }
+    __device__ __forceinline__ double get(int k) const { return base[k * stride]; }
+};
+#ifndef MB_STASH
+#define MB_STASH 0   // measured: parking r2/rd in shared memory made ptxas spill MORE (static 376→576 B, Newmark 3.1→5.3 KB); kept for experiments
+#endif
+constexpr int MB_STASH_SLOTS = 2 * 9 * 2;      // rₛ₂ and Rodrigues(Δvᵧ) as SD<1,0>
+
 MB_HD void load_geo(const double* __restrict__ p16, BeamGeo& geo) {
     const double2* p = reinterpret_cast<const double2*>(p16);
     double buf[16];
@@ -81,7 +93,13 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 3; ++i) { U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
     }
+#if MB_STASH
+    extern __shared__ double mb_smem[];
+    SmemScratch sc{mb_smem + threadIdx.x, (int)blockDim.x};
+    beam_residual_n<ND, N, SmemScratch>(geo, m, Xu, Xv, g.udof != 0, U, R, sc);
+#else
     beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
+#endif
 
     bool bad = false;
     const int cu = (lane < 3) ? lane : lane + 3, cv = cu + 3;          // tangent columns of this lane
@@ -207,7 +225,7 @@ template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
 #define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \
     template <> void launch_beam<ND_, STEP_>(const BeamLaunch& a) {                                                                   \
         const int64_t nt = a.g.nele * 6;                                                                                              \
-        beam_kernel_sd<ND_><<<(unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase); \
+        beam_kernel_sd<ND_><<<(unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, MB_STASH ? MB_STASH_SLOTS * MB_BLOCK * sizeof(double) : 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase); \
         if (STEP_)                                                                                                                    \
             beam_dr_kernel<ND_><<<(unsigned)((a.g.nele + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Rp, a.nanflag, a.nanbase); \
     }

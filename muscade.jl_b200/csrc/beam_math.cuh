@@ -118,6 +118,39 @@ template <int W> using NumDual = Num<Dual<W>, Dual<W>, Dual<W>>;
 using NumSD = Num<SD<true, false>, SD<false, true>, SD<true, true>>;
 template <class N> using NumJet = Num<Jet<typename N::TR>, Jet<typename N::TU>, Jet<typename N::TS>>;
 
+// ------------------------------------------------------------------------------------------------ scratch (explicit spill space)
+// The reverse sweep needs rₛ₂ and Rodrigues(Δvᵧ) only at its very end; parking them in per-thread scratch (shared memory on the
+// device) instead of registers keeps ptxas from spilling to local memory, whose stores all reach DRAM (ncu: 2 KB/element).
+template <class T> struct Comp;
+template <> struct Comp<double> { static constexpr int n = 1; static MB_HD double get(const double& x, int) { return x; } static MB_HD void set(double& x, int, double v) { x = v; } };
+template <int W> struct Comp<Dual<W>> {
+    static constexpr int n = W + 1;
+    static MB_HD double get(const Dual<W>& x, int i) { return i == 0 ? x.v : x.d[i - 1]; }
+    static MB_HD void set(Dual<W>& x, int i, double v) { if (i == 0) x.v = v; else x.d[i - 1] = v; }
+};
+template <bool A, bool B> struct Comp<SD<A, B>> {
+    static constexpr int n = 1 + (A ? 1 : 0) + (B ? 1 : 0);
+    static MB_HD double get(const SD<A, B>& x, int i) { return i == 0 ? x.v : ((A && i == 1) ? sd0(x) : sd1(x)); }
+    static MB_HD void set(SD<A, B>& x, int i, double v) { if (i == 0) x.v = v; else if (A && i == 1) set0(x, v); else set1(x, v); }
+};
+struct HostScratch {                       // host build / kernels that do not stash
+    static constexpr bool enabled = false;
+    MB_HD void put(int, double) {}
+    MB_HD double get(int) const { return 0.; }
+};
+template <class SC, class T> MB_HD void stash(SC& sc, int slot0, const Mat3<T>& m) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int c = 0; c < Comp<T>::n; ++c) sc.put(slot0 + k * Comp<T>::n + c, Comp<T>::get(m.a[k], c));
+}
+template <class SC, class T> MB_HD void unstash(const SC& sc, int slot0, Mat3<T>& m) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int c = 0; c < Comp<T>::n; ++c) Comp<T>::set(m.a[k], c, sc.get(slot0 + k * Comp<T>::n + c));
+}
+
 // ------------------------------------------------------------------------------------------------ rotations (adjoint)
 // v̄ += ∂Rodrigues(v)ᵀ·R̄          (v, aux in TR;  R̄, v̄ in TS)
 template <class TR, class TS> MB_FN void rodrigues_adj(const Vec3<TR>& v, const RodAux<TR>& aux, const Mat3<TS>& Rb, Vec3<TS>& vb) {
@@ -277,8 +310,8 @@ template <class N> MB_HD void beam_gp_reverse(const GpConst& c, double L, const 
     a.vlb[2] = a.vlb[2] + (yv * pb[1] + kv * kb1);
 }
 // Everything upstream of the Gauss loop: ε, uₗ/vₗ, vₛₘ, the corotated frame and the three Rodrigues maps → X̄[12]
-template <class N> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N>& f, const typename N::TS& epsb, const Vec3<typename N::TS>& vsmb,
-                                               BeamAcc<typename N::TS>& a, typename N::TS* Xb) {
+template <class N, class SC> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N>& f, const typename N::TS& epsb, const Vec3<typename N::TS>& vsmb,
+                                               BeamAcc<typename N::TS>& a, typename N::TS* Xb, const SC& sc) {
     using S = typename N::TS;
     const double L = g.L;
     S z = Make<S>::c(0.);
@@ -301,7 +334,9 @@ template <class N> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N
     // r = rd · r1 · rm
     Mat3<S> t = mul_nt(rb, g.rm);                  // r̄ rₘᵀ
     Mat3<S> rdb = mul_nt(t, f.r1);                 // (r̄ rₘᵀ) r₁ᵀ
-    Mat3<S> r1b = mul_tn(f.rd, t);                 // r_dᵀ (r̄ rₘᵀ)
+    Mat3<S> r1b;                                   // r_dᵀ (r̄ rₘᵀ)
+    if constexpr (SC::enabled) { Mat3<typename N::TR> rd_; unstash(sc, 9 * Comp<typename N::TR>::n, rd_); r1b = mul_tn(rd_, t); }
+    else r1b = mul_tn(f.rd, t);
     // rd = Rodrigues(Δv)
     rodrigues_adj(f.dv, f.ad, rdb, dvb);
     // Δv = ½ Rodrigues⁻¹(M), M = r2 r1ᵀ
@@ -310,7 +345,9 @@ template <class N> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N
     Vec3<typename N::TR> h{2.0 * f.dv[0], 2.0 * f.dv[1], 2.0 * f.dv[2]};
     rodrigues_inv_adj(h, f.im, hb, Mb);
     Mat3<S> r2b = mul(Mb, f.r1);                   // M̄ r₁
-    Mat3<S> r1b2 = mul_tn(Mb, f.r2);               // M̄ᵀ r₂
+    Mat3<S> r1b2;                                  // M̄ᵀ r₂
+    if constexpr (SC::enabled) { Mat3<typename N::TR> r2_; unstash(sc, 0, r2_); r1b2 = mul_tn(Mb, r2_); }
+    else r1b2 = mul_tn(Mb, f.r2);
     for (int i = 0; i < 9; ++i) r1b.a[i] = r1b.a[i] + r1b2.a[i];
     Vec3<S> v1b{z, z, z}, v2b{z, z, z};
     rodrigues_adj(f.v1, f.a1, r1b, v1b);
@@ -327,8 +364,8 @@ template <class N> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N
 // ND = 1 (static), 2 (first order), 3 (Newmark / DirectXUA second order).
 // Xu[ider][6] = translations of node 1,2 (TU), Xv[ider][6] = rotation vectors of node 1,2 (TR), U0[3] (TU) carry the lane's
 // seeds.  Returns R[12] in TS (element dof order t1..r3 of node 1, then node 2): value = residual, partials = ∂R/∂(lane's directions).
-template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
-                                                     bool udof, const typename N::TU* U0, typename N::TS* R) {
+template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+                                                     bool udof, const typename N::TU* U0, typename N::TS* R, SC& sc) {
     using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
     const double L = g.L;
     BeamFwd<N> f;
@@ -342,6 +379,7 @@ template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const Be
     if (ND == 1) {
         beam_forward<N>(g, Vec3<TU>{Xu[0][0], Xu[0][1], Xu[0][2]}, Vec3<TR>{Xv[0][0], Xv[0][1], Xv[0][2]},
                         Vec3<TU>{Xu[0][3], Xu[0][4], Xu[0][5]}, Vec3<TR>{Xv[0][3], Xv[0][4], Xv[0][5]}, f);
+        if constexpr (SC::enabled) { stash(sc, 0, f.r2); stash(sc, 9 * Comp<TR>::n, f.rd); }
         MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
         for (int gp = 0; gp < NGP; ++gp) {
             const GpConst c = gp_const(gp);
@@ -373,6 +411,7 @@ template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const Be
         f.ad.a = fj.ad.a.c0; f.ad.b = fj.ad.b.c0; f.ad.small = fj.ad.small;
         f.im.x = fj.im.x.c0; f.im.s = fj.im.s.c0; f.ir.x = fj.ir.x.c0; f.ir.s = fj.ir.s.c0;
         f.eps = fj.eps.c0; f.qn = fj.qn.c0;
+        if constexpr (SC::enabled) { stash(sc, 0, f.r2); stash(sc, 9 * Comp<TR>::n, f.rd); }
         // external loads at the Gauss points from (x, ẋ, ẍ) and rₛₘ (BeamElement.jl:28-58)
         MB_PRAGMA(unroll MB_GP_UNROLL_DYN)
         for (int gp = 0; gp < NGP; ++gp) {
@@ -405,7 +444,13 @@ template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const Be
     }
     // internal axial force (BeamElement.jl:59): Σ_gp dL·fᵢ = EA·L·ε
     S epsb = (m.EA * L) * f.eps;
-    beam_reverse_rot<N>(g, f, epsb, vsmb, acc, R);
+    beam_reverse_rot<N, SC>(g, f, epsb, vsmb, acc, R, sc);
+}
+
+template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+                                                     bool udof, const typename N::TU* U0, typename N::TS* R) {
+    HostScratch sc;
+    beam_residual_n<ND, N, HostScratch>(g, m, Xu, Xv, udof, U0, R, sc);
 }
 
 // dense Dual<W> front-end (element dof order X[ider][12]); used by the δr lane of the :step mission and by the host tests
