@@ -68,15 +68,18 @@ template <class A, class B> MB_HD auto mulv_t(const Mat3<A>& a, const Vec3<B>& b
 
 // ------------------------------------------------------------------------------------------------ rotations (forward)
 // Rodrigues(v) = I + sinc1(θ)·S + ½sinc1(θ/2)²·S²   (toolbox/Rotations.jl:131-135, spin² :114-122, norm3 :106-112)
-template <class T> struct RodAux { T a, b; bool small; };     // what the adjoint needs again
+template <class T> struct RodAux { T a, b, th; double Sth[4], Sh[4]; bool small; };     // what the adjoint needs again: coefficients, θ, sinc1 packs at θ and θ/2
 template <class T> MB_FN Mat3<T> rodrigues(const Vec3<T>& v, RodAux<T>& aux) {
     T t2 = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
     T a, b;
     T th = mb_sqrt(t2);
     aux.small = value(th) < 1e-14;
     if (aux.small) { a = Make<T>::c(1.0); b = Make<T>::c(0.5); }                 // θ := 0 without partials
-    else { a = sinc1k<0>(th); T c = sinc1k<0>(th * 0.5); b = sqr_ref(c) * 0.5; }
-    aux.a = a; aux.b = b;
+    else {
+        sinc_pack(value(th), aux.Sth); sinc_pack(0.5 * value(th), aux.Sh);
+        a = apply_fn(th, aux.Sth); T c = apply_fn(th * 0.5, aux.Sh); b = sqr_ref(c) * 0.5;
+    }
+    aux.a = a; aux.b = b; aux.th = th;
     T v00 = v[0] * v[0], v11 = v[1] * v[1], v22 = v[2] * v[2];
     T b01 = b * (v[0] * v[1]), b02 = b * (v[0] * v[2]), b12 = b * (v[1] * v[2]);
     T a0 = a * v[0], a1 = a * v[1], a2 = a * v[2];
@@ -87,22 +90,12 @@ template <class T> MB_FN Mat3<T> rodrigues(const Vec3<T>& v, RodAux<T>& aux) {
     r(2, 1) = b12 + a0; r(1, 2) = b12 - a0;
     return r;
 }
-// scac(x) = sinc1(acos x) with its series about 1 (Rotations.jl:61-68), K-th derivative in generic arithmetic
-template <class T> MB_HD T scac(const T& x) {
-    T dx = x - 1.0;
-    if (fabs(value(dx)) > 1e-3) return sinc1k<0>(mb_acos(x));
-    return 1.0 + dx * (1. / 3 + dx * (-2. / 90 + dx * (0.0052911879917544626 + dx * (-0.0016229317117234072 + dx * 0.0005625))));
-}
-template <class T> MB_HD T scac1(const T& x) {                                    // d scac / dx, same branches
-    T dx = x - 1.0;
-    if (fabs(value(dx)) > 1e-3) { T w = 1.0 - x * x; return -(sinc1k<1>(mb_acos(x)) / mb_sqrt(w)); }
-    return 1. / 3 + dx * (2 * (-2. / 90) + dx * (3 * 0.0052911879917544626 + dx * (4 * -0.0016229317117234072 + dx * (5 * 0.0005625))));
-}
 // Rodrigues⁻¹(m) = spin⁻¹(m)/scac((tr m − 1)/2)   (Rotations.jl:90,105)
-template <class T> struct RinvAux { T x, s; };
+template <class T> struct RinvAux { T x, s; double C[4]; };     // scac pack at value(x)
 template <class T> MB_FN Vec3<T> rodrigues_inv(const Mat3<T>& m, RinvAux<T>& aux) {
     T x = (((m(0, 0) + m(1, 1)) + m(2, 2)) - 1.0) * 0.5;
-    T s = scac(x);
+    scac_pack(value(x), aux.C);
+    T s = apply_fn(x, aux.C);
     aux.x = x; aux.s = s;
     T is = mb_rcp(s);
     Vec3<T> v;
@@ -167,10 +160,10 @@ template <class TR, class TS> MB_FN void rodrigues_adj(const Vec3<TR>& v, const 
     if (!aux.small) {
         TS ab = (v[0] * k0 + v[1] * k1) + v[2] * k2;                                           // ā = S:R̄
         TS bb = 0.5 * ((v[0] * g0 + v[1] * g1) + v[2] * g2);                                   // b̄ = S²:R̄ (Euler: homogeneous degree 2)
-        TR th = mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+        const TR& th = aux.th;
         TR hth = th * 0.5;
-        TR da = sinc1k<1>(th);
-        TR db = (sinc1k<0>(hth) * sinc1k<1>(hth)) * 0.5;
+        TR da = apply_fn(th, aux.Sth + 1);                                                       // sinc1′(θ)
+        TR db = (apply_fn(hth, aux.Sh) * apply_fn(hth, aux.Sh + 1)) * 0.5;                       // d/dθ ½sinc1(θ/2)²
         TS tb = (ab * da + bb * db) / th;                                                      // θ̄/θ
         vb[0] = vb[0] + tb * v[0]; vb[1] = vb[1] + tb * v[1]; vb[2] = vb[2] + tb * v[2];
     }
@@ -179,7 +172,7 @@ template <class TR, class TS> MB_FN void rodrigues_adj(const Vec3<TR>& v, const 
 template <class TR, class TS> MB_FN void rodrigues_inv_adj(const Vec3<TR>& v, const RinvAux<TR>& aux, const Vec3<TS>& vb, Mat3<TS>& Mb) {
     TR is = mb_rcp(aux.s);
     TS sb = -(((vb[0] * v[0] + vb[1] * v[1]) + vb[2] * v[2]) * is);
-    TS xb = (sb * scac1(aux.x)) * 0.5;
+    TS xb = (sb * apply_fn(aux.x, aux.C + 1)) * 0.5;
     TS w0 = (vb[0] * is) * 0.5, w1 = (vb[1] * is) * 0.5, w2 = (vb[2] * is) * 0.5;
     Mb(0, 0) = Mb(0, 0) + xb; Mb(1, 1) = Mb(1, 1) + xb; Mb(2, 2) = Mb(2, 2) + xb;
     Mb(2, 1) = Mb(2, 1) + w0; Mb(1, 2) = Mb(1, 2) - w0;
@@ -406,9 +399,11 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
             f.ul[i] = fj.ul[i].c0; f.vl[i] = fj.vl[i].c0; f.dp[i] = fj.dp[i].c0; f.q[i] = fj.q[i].c0;
         }
         for (int i = 0; i < 9; ++i) { f.r1.a[i] = fj.r1.a[i].c0; f.r2.a[i] = fj.r2.a[i].c0; f.rd.a[i] = fj.rd.a[i].c0; f.r.a[i] = fj.r.a[i].c0; }
-        f.a1.a = fj.a1.a.c0; f.a1.b = fj.a1.b.c0; f.a1.small = fj.a1.small;
-        f.a2.a = fj.a2.a.c0; f.a2.b = fj.a2.b.c0; f.a2.small = fj.a2.small;
-        f.ad.a = fj.ad.a.c0; f.ad.b = fj.ad.b.c0; f.ad.small = fj.ad.small;
+        f.a1.a = fj.a1.a.c0; f.a1.b = fj.a1.b.c0; f.a1.th = fj.a1.th.c0; f.a1.small = fj.a1.small;
+        f.a2.a = fj.a2.a.c0; f.a2.b = fj.a2.b.c0; f.a2.th = fj.a2.th.c0; f.a2.small = fj.a2.small;
+        f.ad.a = fj.ad.a.c0; f.ad.b = fj.ad.b.c0; f.ad.th = fj.ad.th.c0; f.ad.small = fj.ad.small;
+        for (int k = 0; k < 4; ++k) { f.a1.Sth[k] = fj.a1.Sth[k]; f.a1.Sh[k] = fj.a1.Sh[k]; f.a2.Sth[k] = fj.a2.Sth[k]; f.a2.Sh[k] = fj.a2.Sh[k];
+                                      f.ad.Sth[k] = fj.ad.Sth[k]; f.ad.Sh[k] = fj.ad.Sh[k]; f.im.C[k] = fj.im.C[k]; f.ir.C[k] = fj.ir.C[k]; }
         f.im.x = fj.im.x.c0; f.im.s = fj.im.s.c0; f.ir.x = fj.ir.x.c0; f.ir.s = fj.ir.s.c0;
         f.eps = fj.eps.c0; f.qn = fj.qn.c0;
         if constexpr (SC::enabled) { stash(sc, 0, f.r2); stash(sc, 9 * Comp<TR>::n, f.rd); }

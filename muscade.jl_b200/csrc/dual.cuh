@@ -177,6 +177,54 @@ template <int K, class S> MB_HD Jet<S> sinc1k(const Jet<S>& a) { return jet_comp
 
 template <class T> MB_HD T sqr(const T& a) { return a * a; }
 
+// ------------------------------------------------------------------------------------------------ derivative packs
+// sinc1 and its first three derivatives at a plain argument, with ONE sincos shared by all orders; each order keeps the
+// reference's own branch (closed form vs series, toolbox/Rotations.jl:13-40).  S[k] = sinc1⁽ᵏ⁾(x), k = 0..3.
+MB_HD void sinc_pack_sc(double x, double s, double c, double* S) {
+    const double PI = 3.141592653589793;
+    const double x2 = x * x, ix = 1.0 / x, ix2 = ix * ix;
+    const double y = x / PI;
+    if (fabs(y) < 0.001) { const double y2 = y * y; S[0] = fma(y2, fma(y2, (PI * PI) * (PI * PI) / 120, -(PI * PI) / 6), 1.0); }
+    else S[0] = s * ix;
+    S[1] = (fabs(x) > 1e-3) ? (c * ix - s * ix2) : x * (-1. / 3 + x2 / 30);
+    S[2] = (fabs(x) > 1e-1) ? (-s * ix - 2 * c * ix2 + 2 * s * (ix2 * ix))
+                            : (-1. / 3 + x2 * (1. / 10 + x2 * (-1. / 168 + x2 * (1. / 6480))));
+    S[3] = (fabs(x) > 0.4) ? (-c * ix + 3 * s * ix2 + 6 * c * (ix2 * ix) - 6 * s * (ix2 * ix2))
+                           : x * (1. / 5 + x2 * (-1. / 42 + x2 * (1. / 1080 + x2 * (-1. / 55440 + x2 * (1. / 4717440)))));
+}
+MB_HD void sinc_pack(double x, double* S) {
+    double s = 0., c = 1.;
+    if (fabs(x) > 1e-3) mb_sincos(x, &s, &c);       // below 1e-3 every order is on its series branch
+    if (x == 0.) { S[0] = 1.; S[1] = 0.; S[2] = -1. / 3; S[3] = 0.; return; }
+    sinc_pack_sc(x, s, c, S);
+}
+// scac = sinc1∘acos and its first three derivatives (toolbox/Rotations.jl:61-68) — what the reference obtains by chasing
+// @DiffRule1(acos), @DiffRule1(sinc1…) through nested duals. sin(acos x) = √(1−x²), cos(acos x) = x: no trigonometric call.
+MB_HD void scac_pack(double x, double* C) {
+    const double dx = x - 1.0;
+    if (fabs(dx) > 1e-3) {
+        const double w = 1.0 - x * x, sq = sqrt(w), q = 1.0 / sq, q2 = q * q, q3 = q2 * q;
+        const double phi = acos(x);
+        double G[4];
+        sinc_pack_sc(phi, sq, x, G);
+        const double p1 = -q, p2 = -x * q3, p3 = -q3 - 3 * (x * x) * (q3 * q2);
+        C[0] = G[0];
+        C[1] = G[1] * p1;
+        C[2] = G[2] * (p1 * p1) + G[1] * p2;
+        C[3] = G[3] * (p1 * p1 * p1) + 3 * G[2] * (p1 * p2) + G[1] * p3;
+    } else {
+        const double c1 = 1. / 3, c2 = -2. / 90, c3 = 0.0052911879917544626, c4 = -0.0016229317117234072, c5 = 0.0005625;
+        C[0] = 1.0 + dx * (c1 + dx * (c2 + dx * (c3 + dx * (c4 + dx * c5))));
+        C[1] = c1 + dx * (2 * c2 + dx * (3 * c3 + dx * (4 * c4 + dx * (5 * c5))));
+        C[2] = 2 * c2 + dx * (6 * c3 + dx * (12 * c4 + dx * (20 * c5)));
+        C[3] = 6 * c3 + dx * (24 * c4 + dx * (60 * c5));
+    }
+}
+// f(x) for a number x of any of our types, given F[k] = f⁽ᵏ⁾(value(x)) for k up to the nesting depth of x
+MB_HD double apply_fn(double, const double* F) { return F[0]; }
+template <int W> MB_HD Dual<W> apply_fn(const Dual<W>& x, const double* F) { Dual<W> r; r.v = F[0]; MB_FORW r.d[i] = F[1] * x.d[i]; return r; }
+template <class S> MB_HD Jet<S> apply_fn(const Jet<S>& x, const double* F) { return jet_compose(x, apply_fn(x.c0, F), apply_fn(x.c0, F + 1), apply_fn(x.c0, F + 2)); }
+
 // widen<To>(x): embed a number into a type with more partial slots (missing slots are zero)
 template <class To, class From> struct Widen;
 template <class T> struct Widen<T, T> { static MB_HD T w(const T& x) { return x; } };

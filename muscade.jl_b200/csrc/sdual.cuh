@@ -71,5 +71,6 @@ template <bool A, bool B> MB_HD SD<A, B> mb_sqrt(const SD<A, B>& a) { SD<A, B> r
 template <bool A, bool B> MB_HD SD<A, B> mb_acos(const SD<A, B>& a) { SD<A, B> r; r.v = acos(a.v); const double m = -1.0 / sqrt(1.0 - a.v * a.v); set0(r, m * sd0(a)); set1(r, m * sd1(a)); return r; }
 template <int K, bool A, bool B> MB_HD SD<A, B> sinc1k(const SD<A, B>& a) { SD<A, B> r; r.v = sinc1k<K>(a.v); const double m = sinc1k<K + 1>(a.v); set0(r, m * sd0(a)); set1(r, m * sd1(a)); return r; }
 template <bool A, bool B> MB_HD SD<A, B> sqr_ref(const SD<A, B>& a) { return a * a; }
+template <bool A, bool B> MB_HD SD<A, B> apply_fn(const SD<A, B>& x, const double* F) { SD<A, B> r; r.v = F[0]; set0(r, F[1] * sd0(x)); set1(r, F[1] * sd1(x)); return r; }
 
 }  // namespace mb
