@@ -63,10 +63,56 @@ MB_HD void load_geo(const double* __restrict__ p16, BeamGeo& geo) {
 //   slot 0: rotation dof l  (element dofs r1,r2,r3 of node 1 then node 2)      slot 1: translation dof l (t1,t2,t3 of node 1, node 2)
 // of δX (src/SweepX.jl:63,84,92): X₀+δX, X₁+a₁δX, X₂+b₁δX with δX_p = scale.X[p]·e_p, and writes the two columns of the element
 // tangent they produce (rows scaled: Lλ .* scale.X, SweepX.jl:55,65). Lane 0 also writes the residual.
+// lane seeds of δX (see beam_kernel_sd)
+template <int ND> __device__ __forceinline__ void load_lane_state(const BeamGroupDev& g, const StateDev& st, const NewmarkDev& nm, int64_t e, int lane,
+                                                                 NumSD::TU (*Xu)[6], NumSD::TR (*Xv)[6], NumSD::TU* U) {
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3, iv = iu + 3;            // element dof numbers of translation / rotation i
+        const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iv);
+        const double su = (i == lane) ? g.scaleX[iu] : 0., sv = (i == lane) ? g.scaleX[iv] : 0.;
+        Xu[0][i].v = st.X0[du]; Xu[0][i].d1 = su;
+        Xv[0][i].v = st.X0[dv]; Xv[0][i].d0 = sv;
+        Xu[1][i].v = (ND >= 2) ? st.X1[du] : 0.; Xu[1][i].d1 = nm.a1 * su;
+        Xv[1][i].v = (ND >= 2) ? st.X1[dv] : 0.; Xv[1][i].d0 = nm.a1 * sv;
+        Xu[2][i].v = (ND >= 3) ? st.X2[du] : 0.; Xu[2][i].d1 = nm.b1 * su;
+        Xv[2][i].v = (ND >= 3) ? st.X2[dv] : 0.; Xv[2][i].d0 = nm.b1 * sv;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
+}
+constexpr int MB_NCOT = (NGP * 3 + 3) * 3;      // x̄_gp (4×3) and v̄ₛₘ (3) as SD<1,1>: 45 doubles per lane
+// K2 phase A (ND ≥ 2): time-jet forward → cotangent workspace Wc[k][thread] (k-major: coalesced)
 template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_cot_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Wc, int64_t nthreads) {
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 6;
+    const int lane = (int)(t - e * 6);
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    TU Xu[3][6], U[3]; TR Xv[3][6];
+    load_lane_state<ND>(g, st, nm, e, lane, Xu, Xv, U);
+    Vec3<TS> xb[NGP], vsmb;
+    beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
+    // workspace tile of one warp: [45][32] doubles — every store instruction is one contiguous 256-byte line, the tile is 11.5 KB
+    double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; w[(k) * 32] = xb[gp][i].v; w[(k + 1) * 32] = xb[gp][i].d0; w[(k + 2) * 32] = xb[gp][i].d1; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; w[(k) * 32] = vsmb[i].v; w[(k + 1) * 32] = vsmb[i].d0; w[(k + 2) * 32] = vsmb[i].d1; }
+}
+
+template <int ND, bool SPLIT>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
 beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke, double* __restrict__ Re,
-               unsigned long long* nanflag, unsigned long long nanbase) {
+               unsigned long long* nanflag, unsigned long long nanbase, const double* __restrict__ Wc, int64_t nthreads) {
     using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t / 6;
@@ -76,30 +122,20 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     load_geo(g.geo + e * 16, geo);
     const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
     TU Xu[3][6], U[3]; TR Xv[3][6]; TS R[12];
-    {
-        const int32_t* ix = g.idxX + e * 12;
+    load_lane_state<ND>(g, st, nm, e, lane, Xu, Xv, U);
+    if (SPLIT) {
+        Vec3<TS> xb[NGP], vsmb;
+        const double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int iu = (i < 3) ? i : i + 3, iv = iu + 3;            // element dof numbers of translation / rotation i
-            const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iv);
-            const double su = (i == lane) ? g.scaleX[iu] : 0., sv = (i == lane) ? g.scaleX[iv] : 0.;
-            Xu[0][i].v = st.X0[du]; Xu[0][i].d1 = su;
-            Xv[0][i].v = st.X0[dv]; Xv[0][i].d0 = sv;
-            Xu[1][i].v = (ND >= 2) ? st.X1[du] : 0.; Xu[1][i].d1 = nm.a1 * su;
-            Xv[1][i].v = (ND >= 2) ? st.X1[dv] : 0.; Xv[1][i].d0 = nm.a1 * sv;
-            Xu[2][i].v = (ND >= 3) ? st.X2[du] : 0.; Xu[2][i].d1 = nm.b1 * su;
-            Xv[2][i].v = (ND >= 3) ? st.X2[dv] : 0.; Xv[2][i].d0 = nm.b1 * sv;
-        }
+        for (int gp = 0; gp < NGP; ++gp)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
+            for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; xb[gp][i].v = w[(k) * 32]; xb[gp][i].d0 = w[(k + 1) * 32]; xb[gp][i].d1 = w[(k + 2) * 32]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; vsmb[i].v = w[(k) * 32]; vsmb[i].d0 = w[(k + 1) * 32]; vsmb[i].d1 = w[(k + 2) * 32]; }
+        beam_residual_cot<N>(geo, m, Xu[0], Xv[0], xb, vsmb, R);
+    } else {
+        beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
     }
-#if MB_STASH
-    extern __shared__ double mb_smem[];
-    SmemScratch sc{mb_smem + threadIdx.x, (int)blockDim.x};
-    beam_residual_n<ND, N, SmemScratch>(geo, m, Xu, Xv, g.udof != 0, U, R, sc);
-#else
-    beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
-#endif
 
     bool bad = false;
     const int cu = (lane < 3) ? lane : lane + 3, cv = cu + 3;          // tangent columns of this lane
@@ -219,13 +255,18 @@ template <int ND> void launch_beam_direct(const BeamGroupDev& g, const DirectSta
 // host-side launcher, one translation unit per (ND,STEP) so that the instantiations compile in parallel
 struct BeamLaunch {
     BeamGroupDev g; StateDev st; NewmarkDev nm;
-    double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream;
+    double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream; double* Wc;
 };
 template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
 #define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \
     template <> void launch_beam<ND_, STEP_>(const BeamLaunch& a) {                                                                   \
         const int64_t nt = a.g.nele * 6;                                                                                              \
-        beam_kernel_sd<ND_><<<(unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, MB_STASH ? MB_STASH_SLOTS * MB_BLOCK * sizeof(double) : 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase); \
+        const unsigned nb = (unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK);                                                               \
+        if (ND_ >= 2 && a.Wc) {                                                                                                       \
+            beam_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Wc, nt);                         \
+            beam_kernel_sd<ND_, true><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase, a.Wc, nt);    \
+        } else                                                                                                                        \
+            beam_kernel_sd<ND_, false><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase, nullptr, nt); \
         if (STEP_)                                                                                                                    \
             beam_dr_kernel<ND_><<<(unsigned)((a.g.nele + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Rp, a.nanflag, a.nanbase); \
     }

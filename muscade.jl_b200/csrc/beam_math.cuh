@@ -442,6 +442,72 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
     beam_reverse_rot<N, SC>(g, f, epsb, vsmb, acc, R, sc);
 }
 
+// ------------------------------------------------------------------------------------------------ two-phase variant (ND ≥ 2)
+// The fused Newmark kernel is ~210 KB of straight-line code and runs out of the instruction cache; split in two, each half fits.
+// Phase A: time-jets forward only → external-load cotangents x̄_gp = dL·fₑ (BeamElement.jl:28-58,169) and v̄ₛₘ = Σ dL·mₑ (:56-57).
+template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+                                                         bool udof, const typename N::TU* U0, Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb) {
+    using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
+    using NJ = NumJet<N>;
+    using JR = typename NJ::TR; using JU = typename NJ::TU; using JS = typename NJ::TS;
+    const double L = g.L;
+    JU XuJ[6]; JR XvJ[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        XuJ[i].c0 = Xu[0][i]; XuJ[i].c1 = Xu[1][i]; XuJ[i].c2 = (ND >= 3) ? Xu[2][i] : Make<TU>::c(0.);
+        XvJ[i].c0 = Xv[0][i]; XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
+    }
+    BeamFwd<NJ> fj;
+    beam_forward<NJ>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JR>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]},
+                     Vec3<JR>{XvJ[3], XvJ[4], XvJ[5]}, fj);
+    Mat3<TR> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
+    MB_PRAGMA(unroll MB_GP_UNROLL_DYN)
+    for (int gp = 0; gp < NGP; ++gp) {
+        const GpConst c = gp_const(gp);
+        Vec3<JS> p = beam_gp_local(c, L, fj.ul, fj.vl);
+        Vec3<S> x1, x2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            x1[i] = ((fj.r(i, 0).c0 * p[0].c1 + fj.r(i, 0).c1 * p[0].c0) + (fj.r(i, 1).c0 * p[1].c1 + fj.r(i, 1).c1 * p[1].c0))
+                  + ((fj.r(i, 2).c0 * p[2].c1 + fj.r(i, 2).c1 * p[2].c0) + fj.cs[i].c1);
+            if (ND >= 3) {
+                x2[i] = (((fj.r(i, 0).c0 * p[0].c2 + fj.r(i, 0).c2 * p[0].c0) + 2.0 * (fj.r(i, 0).c1 * p[0].c1))
+                       + ((fj.r(i, 1).c0 * p[1].c2 + fj.r(i, 1).c2 * p[1].c0) + 2.0 * (fj.r(i, 1).c1 * p[1].c1)))
+                      + (((fj.r(i, 2).c0 * p[2].c2 + fj.r(i, 2).c2 * p[2].c0) + 2.0 * (fj.r(i, 2).c1 * p[2].c1)) + fj.cs[i].c2);
+            } else x2[i] = Make<S>::c(0.);
+        }
+        Vec3<S> fe = beam_fe(m, r0, x1, x2);
+        const double dL = c.w * L;
+        for (int i = 0; i < 3; ++i) { if (udof) fe[i] = fe[i] - U0[i]; xb[gp][i] = dL * fe[i]; }
+    }
+    vsmb = Vec3<S>{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(0.)};
+    if (ND >= 3) {
+        TR m21 = (fj.r(0, 2).c0 * fj.r(0, 1).c2 + fj.r(1, 2).c0 * fj.r(1, 1).c2) + fj.r(2, 2).c0 * fj.r(2, 1).c2;
+        TR m12 = (fj.r(0, 1).c0 * fj.r(0, 2).c2 + fj.r(1, 1).c0 * fj.r(1, 2).c2) + fj.r(2, 1).c0 * fj.r(2, 2).c2;
+        TR m1l = (m.iota1 * L) * ((m21 - m12) * 0.5);
+        for (int i = 0; i < 3; ++i) vsmb[i] = widen<S>(r0(i, 0) * m1l);
+    }
+}
+// Phase B: order-0 forward + reverse sweep with the cotangents of phase A
+template <class N> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0, const typename N::TR* Xv0,
+                                                const Vec3<typename N::TS>* xb, const Vec3<typename N::TS>& vsmb, typename N::TS* R) {
+    using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
+    const double L = g.L;
+    BeamFwd<N> f;
+    BeamAcc<S> acc;
+    {
+        S z = Make<S>::c(0.);
+        for (int i = 0; i < 9; ++i) acc.rb.a[i] = z;
+        for (int i = 0; i < 3; ++i) { acc.ulb[i] = z; acc.vlb[i] = z; acc.cb[i] = z; }
+    }
+    beam_forward<N>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
+    MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
+    for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N>(gp_const(gp), L, m, f, xb[gp], acc);
+    S epsb = (m.EA * L) * f.eps;
+    HostScratch sc;
+    beam_reverse_rot<N, HostScratch>(g, f, epsb, vsmb, acc, R, sc);
+}
+
 template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
                                                      bool udof, const typename N::TU* U0, typename N::TS* R) {
     HostScratch sc;

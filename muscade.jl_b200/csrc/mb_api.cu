@@ -32,6 +32,8 @@ int32_t mb_create(int32_t device, mb_handle** out) {
         cudaMallocHost((void**)&h->nanflag_host, sizeof(unsigned long long)) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
     const char* w = getenv("MB_BEAM_W");
     if (w) h->beamW = atoi(w);
+    const char* sd = getenv("MB_SPLIT_DYN");
+    if (sd) h->split_dyn = atoi(sd);
     *out = h;
     return MB_OK;
 }
@@ -304,9 +306,15 @@ int32_t mb_sweepx_get_asm(mb_handle* h, int32_t ieletyp, int64_t* asm1, int64_t*
 // ------------------------------------------------------------------------------------------------------------ assemble
 template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group& g, const BeamGroupDev& gd, const StateDev& sd, const NewmarkDev& nm,
                                                        unsigned long long nanbase) {
-    BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->beamW, h->stream};
+    double* Wc = nullptr;
+    if (ND >= 2 && h->split_dyn) {                 // two-phase Newmark kernel: 45 doubles per lane of workspace (lazily sized to the largest beam type)
+        const int64_t need = ((g.nele * 6 + 31) / 32) * 32 * MB_NCOT;
+        if (h->Wc_len < need) { if (h->Wc) dfree(h, h->Wc); h->Wc = nullptr; h->Wc_len = 0; if (dalloc(h, &h->Wc, need) == cudaSuccess) h->Wc_len = need; else cudaGetLastError(); }
+        Wc = h->Wc_len >= need ? h->Wc : nullptr;  // falls back to the fused kernel when the workspace does not fit
+    }
+    BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->beamW, h->stream, Wc};
     launch_beam<ND, STEP>(a);
-    h->launches += STEP ? 2 : 1;
+    h->launches += (STEP ? 2 : 1) + (Wc ? 1 : 0);
 }
 
 static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm, double tnow) {
