@@ -188,25 +188,35 @@ beam_dr_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 }
 
 // K3: DirectXUA first-order path (src/DirectXUA.jl:85-120, no_second_order elements). Seeds are revariate{1}((;X,U),(;X=scale.X,U=scale.U))
-// (src/Taylor.jl:158-166): one partial per X₀,X₁,…,X_OX dof and per U₀ dof. Lanes per element: 6 per X derivative order d — lane (d,l)
-// carries (rotation dof l of X_d, translation dof l of X_d) — plus 3 lanes for the U₀ dofs of Udof elements.
+// (src/Taylor.jl:158-166): one partial per X₀,X₁,…,X_OX dof and per U₀ dof.
 // Output dR[e][p][i] = ∂R_i/∂seed_p with p in the reference's flat order X₀(12) X₁(12) X₂(12) U₀(3); R[e][i] unscaled (DirectXUA.jl:105).
+// Three launches, each inside the instruction cache (the fused one-kernel form was 216 KB of SASS and instruction-fetch bound):
+//   cot  (ND ≥ 2)  lanes (d,e,l), d-major: time-jet forward seeded at derivative order d → cotangents x̄_gp, v̄ₛₘ with partials → Wc
+//   b0             lanes (e,l): order-0 forward + reverse sweep in SD arithmetic → R and ∂R/∂X₀
+//   lin            lanes (d≥1,e,l) and 2 U-lanes per Udof element: R is linear in the cotangents, so ∂R/∂X_d = J(X₀)ᵀ·∂c/∂X_d needs the forward
+//                  sweep in plain values only and the reverse sweep on the partials of c (∂c/∂U is known in closed form: −dL·scale.U).
 struct DirectStateDev { const double* X[3]; const double* U0; };
-template <int ND>
-__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
-beam_direct_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag, unsigned long long nanbase) {
-    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
-    const int LPE = 6 * ND + (g.udof ? 3 : 0);
-    const int NP = 12 * ND + (g.udof ? 3 : 0);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t e = t / LPE;
-    const int lane = (int)(t - e * LPE);
-    if (e >= g.nele) return;
-    const int d = lane / 6, l = lane - 6 * d;          // d == ND ⇒ U lane l (0..2)
-    BeamGeo geo;
-    load_geo(g.geo + e * 16, geo);
-    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
-    TU Xu[3][6], U[3]; TR Xv[3][6]; TS Rv[12];
+__device__ __forceinline__ void store_cot(double* __restrict__ Wc, int64_t t, const Vec3<NumSD::TS>* xb, const Vec3<NumSD::TS>& vsmb) {
+    double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; w[(k) * 32] = xb[gp][i].v; w[(k + 1) * 32] = xb[gp][i].d0; w[(k + 2) * 32] = xb[gp][i].d1; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; w[(k) * 32] = vsmb[i].v; w[(k + 1) * 32] = vsmb[i].d0; w[(k + 2) * 32] = vsmb[i].d1; }
+}
+__device__ __forceinline__ void load_cot(const double* __restrict__ Wc, int64_t t, Vec3<NumSD::TS>* xb, Vec3<NumSD::TS>& vsmb) {
+    const double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; xb[gp][i].v = w[(k) * 32]; xb[gp][i].d0 = w[(k + 1) * 32]; xb[gp][i].d1 = w[(k + 2) * 32]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; vsmb[i].v = w[(k) * 32]; vsmb[i].d0 = w[(k + 1) * 32]; vsmb[i].d1 = w[(k + 2) * 32]; }
+}
+// state of one lane: values of X₀..X_{ND-1}, U₀ and the lane's two seeds (rotation dof l, translation dof l) at derivative order d (d<0: no seed)
+template <int ND> __device__ __forceinline__ void load_direct_state(const BeamGroupDev& g, const DirectStateDev& st, int64_t e, int d, int l,
+                                               NumSD::TU (*Xu)[6], NumSD::TR (*Xv)[6], NumSD::TU* U) {
     const int32_t* ix = g.idxX + e * 12;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -219,37 +229,133 @@ beam_direct_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, d
         }
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { U[i].v = g.udof ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = (d == ND && i == l) ? g.scaleU[i] : 0.; }
-    beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, Rv);
+    for (int i = 0; i < 3; ++i) { U[i].v = g.udof ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
+}
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ Wc) {
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = g.nele * 6;
+    if (t >= per * ND) return;
+    const int d = (int)(t / per);
+    const int64_t r = t - d * per, e = r / 6;
+    const int l = (int)(r - e * 6);
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    TU Xu[3][6], U[3]; TR Xv[3][6];
+    load_direct_state<ND>(g, st, e, d, l, Xu, Xv, U);
+    Vec3<TS> xb[NGP], vsmb;
+    beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
+    store_cot(Wc, t, xb, vsmb);
+}
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_direct_b0_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag,
+                      unsigned long long nanbase, const double* __restrict__ Wc) {
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    const int NP = 12 * ND + (g.udof ? 3 : 0);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 6;
+    const int l = (int)(t - e * 6);
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    TU Xu[3][6], U[3]; TR Xv[3][6]; TS Rv[12];
+    load_direct_state<1>(g, st, e, 0, l, Xu, Xv, U);
+    if (ND >= 2) {
+        Vec3<TS> xb[NGP], vsmb;
+        load_cot(Wc, t, xb, vsmb);
+        beam_residual_cot<N>(geo, m, Xu[0], Xv[0], xb, vsmb, Rv);
+    } else {
+        beam_residual_n<1, N>(geo, m, Xu, Xv, g.udof != 0, U, Rv);
+    }
     bool bad = false;
     double* out = dR + e * (int64_t)(12 * NP);
-    if (d < ND) {
-        const int cu = 12 * d + ((l < 3) ? l : l + 3), cv = cu + 3;
+    const int cu = (l < 3) ? l : l + 3, cv = cu + 3;
 #pragma unroll
-        for (int i = 0; i < 12; i += 2) {
-            double2 a, b; a.x = Rv[i].d1; a.y = Rv[i + 1].d1; b.x = Rv[i].d0; b.y = Rv[i + 1].d0;
-            bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
-            *reinterpret_cast<double2*>(out + 12 * cu + i) = a;
-            *reinterpret_cast<double2*>(out + 12 * cv + i) = b;
-        }
-    } else {
-        const int cu = 12 * ND + l;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) { double v = Rv[i].d1; bad |= (v != v); out[12 * cu + i] = v; }
+    for (int i = 0; i < 12; i += 2) {
+        double2 a, b; a.x = Rv[i].d1; a.y = Rv[i + 1].d1; b.x = Rv[i].d0; b.y = Rv[i + 1].d0;
+        bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
+        *reinterpret_cast<double2*>(out + 12 * cu + i) = a;
+        *reinterpret_cast<double2*>(out + 12 * cv + i) = b;
     }
-    if (lane == 0) {
+    if (l == 0) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) { double v = Rv[i].v; bad |= (v != v); R[e * 12 + i] = v; }
     }
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
-template <int ND> void launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
-                                          unsigned long long nanbase, cudaStream_t s);
-#define MB_INSTANTIATE_BEAM_DIRECT(ND_)                                                                                              \
-    template <> void launch_beam_direct<ND_>(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R,                 \
-                                             unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s) {              \
-        const int64_t nt = g.nele * (6 * ND_ + (g.udof ? 3 : 0));                                                                    \
-        beam_direct_kernel<ND_><<<(unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase);    \
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_direct_lin_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, unsigned long long* nanflag, unsigned long long nanbase,
+                       const double* __restrict__ Wc) {
+    using NV = NumVal; using V = SD<false, false>; using S = NumSD::TS;
+    const int NP = 12 * ND + (g.udof ? 3 : 0);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = g.nele * 6, nx = per * (ND - 1);
+    int64_t e; int c0, c1;                       // columns of dR fed by slot 0 / slot 1 of this lane (c < 0: none)
+    Vec3<S> xb[NGP], vsmb;
+    BeamGeo geo;
+    if (t < nx) {                                // X_d lane, d ≥ 1: cotangent partials from phase A (its thread index is per + t)
+        const int d = 1 + (int)(t / per);
+        const int64_t r = t - (d - 1) * per;
+        e = r / 6;
+        const int l = (int)(r - e * 6);
+        c1 = 12 * d + ((l < 3) ? l : l + 3); c0 = c1 + 3;
+        load_geo(g.geo + e * 16, geo);
+        load_cot(Wc, per + t, xb, vsmb);
+    } else {                                     // U lane u: slot 0 ← U dof 2u, slot 1 ← U dof 2u+1;  x̄_gp = dL·(fₑ − U) (BeamElement.jl:169)
+        const int64_t tu = t - nx;
+        e = tu >> 1;
+        if (!g.udof || e >= g.nele) return;
+        const int u = (int)(tu & 1);
+        c0 = 12 * ND + 2 * u; c1 = (u == 0) ? 12 * ND + 1 : -1;
+        load_geo(g.geo + e * 16, geo);
+        const S z = Make<S>::c(0.);
+#pragma unroll
+        for (int gp = 0; gp < NGP; ++gp) {
+            const double dL = gp_const(gp).w * geo.L;
+            xb[gp] = Vec3<S>{z, z, z};
+            if (u == 0) { xb[gp][0].d0 = -dL * g.scaleU[0]; xb[gp][1].d1 = -dL * g.scaleU[1]; }
+            else xb[gp][2].d0 = -dL * g.scaleU[2];
+        }
+        vsmb = Vec3<S>{z, z, z};
+    }
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    V Xu0[6], Xv0[6]; S Rv[12];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3;
+        Xu0[i].v = st.X[0][__ldg(ix + iu)]; Xv0[i].v = st.X[0][__ldg(ix + iu + 3)];
+    }
+    beam_residual_cot<NV, S>(geo, m, Xu0, Xv0, xb, vsmb, Rv);
+    bool bad = false;
+    double* out = dR + e * (int64_t)(12 * NP);
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        double2 a, b; a.x = Rv[i].d1; a.y = Rv[i + 1].d1; b.x = Rv[i].d0; b.y = Rv[i + 1].d0;
+        bad |= (b.x != b.x) | (b.y != b.y);
+        *reinterpret_cast<double2*>(out + 12 * c0 + i) = b;
+        if (c1 >= 0) { bad |= (a.x != a.x) | (a.y != a.y); *reinterpret_cast<double2*>(out + 12 * c1 + i) = a; }
+    }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+// returns the number of kernels launched; Wc must hold ((6·ND·nele+31)/32)·32·MB_NCOT doubles when ND ≥ 2
+template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                                         unsigned long long nanbase, double* Wc, cudaStream_t s);
+#define MB_INSTANTIATE_BEAM_DIRECT(ND_)                                                                                                       \
+    template <> int launch_beam_direct<ND_>(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R,                           \
+                                            unsigned long long* nanflag, unsigned long long nanbase, double* Wc, cudaStream_t s) {            \
+        const int64_t per = g.nele * 6, nlin = per * (ND_ - 1) + (g.udof ? 2 * g.nele : 0);                                                  \
+        int n = 1;                                                                                                                            \
+        if (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<(unsigned)((per * ND_ + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, Wc); ++n; } \
+        beam_direct_b0_kernel<ND_><<<(unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase, Wc);      \
+        if (nlin) { beam_direct_lin_kernel<ND_><<<(unsigned)((nlin + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, nanflag, nanbase, Wc); ++n; } \
+        return n;                                                                                                                             \
     }
 
 // host-side launcher, one translation unit per (ND,STEP) so that the instantiations compile in parallel

@@ -109,6 +109,7 @@ template <class T> MB_FN Vec3<T> rodrigues_inv(const Mat3<T>& m, RinvAux<T>& aux
 template <class TR_, class TU_, class TS_> struct Num { using TR = TR_; using TU = TU_; using TS = TS_; };
 template <int W> using NumDual = Num<Dual<W>, Dual<W>, Dual<W>>;
 using NumSD = Num<SD<true, false>, SD<false, true>, SD<true, true>>;
+using NumVal = Num<SD<false, false>, SD<false, false>, SD<false, false>>;     // plain values behind the SD interface
 template <class N> using NumJet = Num<Jet<typename N::TR>, Jet<typename N::TU>, Jet<typename N::TS>>;
 
 // ------------------------------------------------------------------------------------------------ scratch (explicit spill space)
@@ -204,7 +205,7 @@ MB_HD GpConst gp_const(int gp) {
 #define MB_GP_UNROLL_STATIC 1
 #endif
 #ifndef MB_GP_UNROLL_DYN
-#define MB_GP_UNROLL_DYN 4
+#define MB_GP_UNROLL_DYN 1
 #endif
 #define MB_PRAGMA_(x) _Pragma(#x)
 #define MB_PRAGMA(x) MB_PRAGMA_(x)
@@ -279,15 +280,14 @@ template <class TR, class S> MB_HD Vec3<S> beam_fe(const BeamMat& m, const Mat3<
 // Adjoint accumulators of the quantities the Gauss loop feeds: r̄ₛₘ, ūₗ, v̄ₗ, c̄ₛₘ
 template <class S> struct BeamAcc { Mat3<S> rb; Vec3<S> ulb, vlb, cb; };
 // One Gauss point: internal moment cotangent κ̄ = dL·mᵢ (BeamElement.jl:62) computed on the fly, external force cotangent x̄ given.
-template <class N> MB_HD void beam_gp_reverse(const GpConst& c, double L, const BeamMat& m, const BeamFwd<N>& f, const Vec3<typename N::TS>& xb,
-                                              BeamAcc<typename N::TS>& a) {
-    using S = typename N::TS;
+template <class N, class S = typename N::TS> MB_HD void beam_gp_reverse(const GpConst& c, double L, const BeamMat& m, const BeamFwd<N>& f, const Vec3<S>& xb,
+                                                                        BeamAcc<S>& a) {
     const double dL = c.w * L, yv = c.yv * L, ka = 2.0 / L, ku = c.ku / (L * L), kv = 2.0 / L;
     // κ = (κₐvₗ₁, κᵤuₗ₂+κᵥvₗ₃, κᵤuₗ₃−κᵥvₗ₂)  (BeamElement.jl:184)
     auto kb0 = (m.GJ * dL) * (ka * f.vl[0]);
-    S kb1 = (m.EI3 * dL) * (ku * f.ul[1] + kv * f.vl[2]);
-    S kb2 = (m.EI2 * dL) * (ku * f.ul[2] - kv * f.vl[1]);
-    Vec3<S> p = beam_gp_local(c, L, f.ul, f.vl);
+    auto kb1 = (m.EI3 * dL) * (ku * f.ul[1] + kv * f.vl[2]);
+    auto kb2 = (m.EI2 * dL) * (ku * f.ul[2] - kv * f.vl[1]);
+    auto p = beam_gp_local(c, L, f.ul, f.vl);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
@@ -303,9 +303,8 @@ template <class N> MB_HD void beam_gp_reverse(const GpConst& c, double L, const 
     a.vlb[2] = a.vlb[2] + (yv * pb[1] + kv * kb1);
 }
 // Everything upstream of the Gauss loop: ε, uₗ/vₗ, vₛₘ, the corotated frame and the three Rodrigues maps → X̄[12]
-template <class N, class SC> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N>& f, const typename N::TS& epsb, const Vec3<typename N::TS>& vsmb,
-                                               BeamAcc<typename N::TS>& a, typename N::TS* Xb, const SC& sc) {
-    using S = typename N::TS;
+template <class N, class SC, class S = typename N::TS> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N>& f, const S& epsb, const Vec3<S>& vsmb,
+                                                                                  BeamAcc<S>& a, S* Xb, const SC& sc) {
     const double L = g.L;
     S z = Make<S>::c(0.);
     Mat3<S>& rb = a.rb; Vec3<S>&ulb = a.ulb, &vlb = a.vlb, &cb = a.cb;
@@ -489,9 +488,10 @@ template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, cons
     }
 }
 // Phase B: order-0 forward + reverse sweep with the cotangents of phase A
-template <class N> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0, const typename N::TR* Xv0,
-                                                const Vec3<typename N::TS>* xb, const Vec3<typename N::TS>& vsmb, typename N::TS* R) {
-    using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
+// (S ≠ N::TS: forward in plain values, cotangents carrying partials — the linear lanes ∂R/∂X′, ∂R/∂X″, ∂R/∂U of DirectXUA)
+template <class N, class S = typename N::TS> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0, const typename N::TR* Xv0,
+                                                                          const Vec3<S>* xb, const Vec3<S>& vsmb, S* R) {
+    using TR = typename N::TR; using TU = typename N::TU;
     const double L = g.L;
     BeamFwd<N> f;
     BeamAcc<S> acc;
@@ -502,10 +502,10 @@ template <class N> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat&
     }
     beam_forward<N>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
     MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
-    for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N>(gp_const(gp), L, m, f, xb[gp], acc);
-    S epsb = (m.EA * L) * f.eps;
+    for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N, S>(gp_const(gp), L, m, f, xb[gp], acc);
+    S epsb = widen<S>((m.EA * L) * f.eps);
     HostScratch sc;
-    beam_reverse_rot<N, HostScratch>(g, f, epsb, vsmb, acc, R, sc);
+    beam_reverse_rot<N, HostScratch, S>(g, f, epsb, vsmb, acc, R, sc);
 }
 
 template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],

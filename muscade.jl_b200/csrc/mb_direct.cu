@@ -7,12 +7,13 @@
 // finite-difference stencils (src/FiniteDifferences.jl) reach its columns.  Lvv is never assembled by scattered adds:
 // one warp per Lvv column walks the blocks of that column and writes each value as the fixed-order weighted sum
 // Σ_der w·Δt^(−der)·block_der[ilv] — deterministic, no atomics, no nnz-sized index map (the map is implicit in the block layout).
+#include <algorithm>
 #include "mb_internal.h"
 #include <cub/cub.cuh>
 
 namespace mb {
-template <int ND> void launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
-                                          unsigned long long nanbase, cudaStream_t s);
+template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                                         unsigned long long nanbase, double* Wc, cudaStream_t s);
 }
 
 namespace {
@@ -208,6 +209,66 @@ __global__ void big_fill_kernel(BigDev B, int64_t ncol, const int64_t* __restric
         off += p1 - p0;
     }
 }
+// Values of the owned Lvv columns, the hot form: a CTA works inside ONE block column (tcol,class), so the list of blocks of that
+// block column — source array, finite-difference weights w_α·Δt^(-α) (DirectXUA.jl:347-349), class-pair pattern — is decoded once into
+// shared memory; then each warp streams pattern columns: per block ≤ 3 coalesced loads and one coalesced store of the column slice.
+constexpr int MB_BIG_MAXB = 48;          // ≥ 3 classes × 5 step offsets × (room for A-class blocks)
+constexpr int MB_BIG_CPC = 128;          // pattern columns per CTA
+struct BlkDesc { const double* a; const int32_t* pc; double wd[3]; int64_t nnzp; int nder; };
+__global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t* __restrict__ colptr, double* __restrict__ nzval) {
+    __shared__ BlkDesc sd[MB_BIG_MAXB];
+    const int bc = blockIdx.y, cb = bc % 3;
+    const int64_t tcol = B.lo + bc / 3;
+    const int64_t ncls = (cb == 2) ? B.nU : B.nX;
+    const int64_t lc0 = (int64_t)blockIdx.x * MB_BIG_CPC;
+    if (lc0 >= ncls) return;
+    const int32_t q0 = B.bcolptr[bc];
+    const int nb = B.bcolptr[bc + 1] - q0;
+    if ((int)threadIdx.x < nb) {
+        const int32_t br = B.browval[q0 + threadIdx.x];
+        const int ca = br % 3; const int64_t trow = br / 3;
+        const int p = pat_of(ca, cb);
+        BlkDesc d; d.a = nullptr; d.pc = B.pc[p]; d.nnzp = B.pnnz[p]; d.nder = 0; d.wd[0] = d.wd[1] = d.wd[2] = 0.;
+        const double* arr = nullptr; int64_t stride = 0, s = 0, t = 0;
+        if (ca == 0 && cb != 0) { s = trow; t = tcol; if (cb == 1) { arr = B.LX; stride = B.sLX; d.nder = B.OX + 1; } else { arr = B.LU; stride = B.sLU; d.nder = 1; } }
+        else if (cb == 0 && ca != 0) { s = tcol; t = trow; if (ca == 1) { arr = B.XL; stride = B.sLX; d.nder = B.OX + 1; } else { arr = B.UL; stride = B.sUL; d.nder = 1; } }
+        double sc = 1.;
+        for (int der = 0; der < d.nder; ++der) { double w = 0.; const bool on = fd_weight(der, B.nstep, s, t - s, w); d.wd[der] = on ? w * sc : 0.; sc /= B.dt; }
+        if (arr) d.a = arr + (s - B.elo) * stride;
+        sd[threadIdx.x] = d;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t cbase = (tcol - B.lo) * B.W + (cb == 0 ? 0 : (cb == 1 ? B.nX : 2 * B.nX));
+    const int64_t lc1 = (lc0 + MB_BIG_CPC < ncls) ? lc0 + MB_BIG_CPC : ncls;
+    for (int64_t lc = lc0 + warp; lc < lc1; lc += 8) {
+        int64_t off = colptr[cbase + lc];
+        for (int j = 0; j < nb; ++j) {
+            const int32_t p0 = sd[j].pc[lc], p1 = sd[j].pc[lc + 1];
+            const double* a = sd[j].a;
+            const int nder = sd[j].nder; const int64_t nnzp = sd[j].nnzp;
+            const double w0 = sd[j].wd[0], w1 = sd[j].wd[1], w2 = sd[j].wd[2];
+            for (int32_t k = p0 + lane; k < p1; k += 32) {
+                double v = 0.;                                     // same order of additions as the one-warp-per-column reference form
+                if (a) {
+                    if (w0 != 0.) v += a[k] * w0;
+                    if (nder > 1 && w1 != 0.) v += a[nnzp + k] * w1;
+                    if (nder > 2 && w2 != 0.) v += a[2 * nnzp + k] * w2;
+                }
+                nzval[off + (k - p0)] = v;
+            }
+            off += p1 - p0;
+        }
+    }
+}
+static void launch_big_values(const BigDev& B, int64_t ncol, const int64_t* colptr, double* nzval, int maxb, cudaStream_t st) {
+    const int64_t nbc = 3 * (B.hi - B.lo), ncls = B.nX > B.nU ? B.nX : B.nU;
+    if (maxb <= MB_BIG_MAXB && nbc <= 65535) {
+        dim3 grid((unsigned)((ncls + MB_BIG_CPC - 1) / MB_BIG_CPC), (unsigned)nbc);
+        big_values_kernel<<<grid, 256, 0, st>>>(B, colptr, nzval);
+    } else
+        big_fill_kernel<false><<<nblk(ncol * 32, 256), 256, 0, st>>>(B, ncol, colptr, nullptr, nzval);
+}
 __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
@@ -229,7 +290,7 @@ struct DirectData {
     double *X = nullptr, *U = nullptr;                  // stored states [step][3][nX], [step][nU]
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
     int32_t *bcolptr = nullptr, *browval = nullptr;
-    int64_t ncol = 0, nnzbig = 0;
+    int64_t ncol = 0, nnzbig = 0; int maxb = 0;         // maxb: most blocks in one block column
     int64_t *colptr = nullptr, *rowval = nullptr;
     double *nzval = nullptr, *Lv = nullptr;
 };
@@ -359,6 +420,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     // block pattern of the owned block columns and the Lvv structure
     const int64_t nbc = 3 * (step_hi - step_lo);
     const int32_t nblocks = bcolptr[nbc];
+    D->maxb = 0; for (int64_t b = 0; b < nbc; ++b) D->maxb = std::max<int>(D->maxb, bcolptr[b + 1] - bcolptr[b]);
     CK(dalloc(h, &D->bcolptr, nbc + 1)); CK(dalloc(h, &D->browval, nblocks));
     CK(cudaMemcpyAsync(D->bcolptr, bcolptr, (nbc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(D->browval, browval, (size_t)nblocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -437,10 +499,15 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
             for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
             const unsigned long long nanbase = (((unsigned long long)s) << 44) | (((unsigned long long)ig) << 40);
             double* dR = D->dR + D->G.drbase[ig]; double* R = D->R + D->G.rbase[ig];
-            if (nd == 1) launch_beam_direct<1>(gd, sd, dR, R, h->nanflag, nanbase, st);
-            else if (nd == 2) launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, st);
-            else launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, st);
-            h->launches++;
+            double* Wc = nullptr;
+            if (nd >= 2) {                         // cotangent workspace of the two-phase evaluation, shared with SweepX and sized lazily
+                const int64_t need = ((g.nele * 6 * nd + 31) / 32) * 32 * MB_NCOT;
+                if (h->Wc_len < need) { if (h->Wc) dfree(h, h->Wc); h->Wc = nullptr; h->Wc_len = 0; CK(dalloc(h, &h->Wc, need)); h->Wc_len = need; }
+                Wc = h->Wc;
+            }
+            if (nd == 1) h->launches += launch_beam_direct<1>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
+            else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
+            else h->launches += launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
         }
         const PairPat& XX = D->pat[P_XX];
         if (XX.nnz) { gather_xx_kernel<<<nblk(XX.nnz, 256), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz); h->launches++; }
@@ -466,7 +533,7 @@ int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32
     if (rc) return rc;
     if (build_big) {
         BigDev B = make_bigdev(D);
-        big_fill_kernel<false><<<nblk(D->ncol * 32, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, nullptr, D->nzval);
+        launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
         h->launches += 2;
         if (Lvv_nzval) CK(cudaMemcpyAsync(Lvv_nzval, D->nzval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -527,7 +594,7 @@ int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms) {
         direct_eval_steps(h, D->lo, D->hi);
         CK(cudaEventRecord(e1, h->stream));
         BigDev B = make_bigdev(D);
-        big_fill_kernel<false><<<nblk(D->ncol * 32, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, nullptr, D->nzval);
+        launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
         h->launches += 2;
         CK(cudaEventRecord(e2, h->stream));
