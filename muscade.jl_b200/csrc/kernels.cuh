@@ -11,14 +11,37 @@ namespace mb {
 
 // nzval[k] = Σ_{s ∈ [cstart[k],cstart[k+1])} Ke[src[s]]  — contributions added in the reference's element order
 // (src/Assemble.jl:472,479 → add_∂! :572-588), one thread per non-zero, no atomics.
+// Four consecutive non-zeros per thread: their contributor lists are one contiguous range of src, so the index and value loads of up to
+// four contributors are issued together (the one-non-zero-per-thread form was latency-bound on the cstart → src → Ke chain at 44 % of DRAM).
 static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src,
                                  const double* __restrict__ Ke, double* __restrict__ nzval) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nnz) return;
-    const uint32_t s0 = cstart[k], s1 = cstart[k + 1];
-    double acc = 0.;
-    for (uint32_t s = s0; s < s1; ++s) acc += __ldg(Ke + src[s]);
-    nzval[k] = acc;
+    const int64_t k0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (k0 >= nnz) return;
+    if (k0 + 4 <= nnz) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(cstart + k0));
+        const uint32_t c4 = __ldg(cstart + k0 + 4);
+        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+        for (uint32_t s = c.x; s < c4; s += 4) {
+            uint32_t i[4]; double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) i[j] = (s + j < c4) ? __ldg(src + s + j) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (s + j < c4) ? __ldg(Ke + i[j]) : 0.;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t sj = s + j;
+                if (sj < c4) { if (sj < c.y) a0 += v[j]; else if (sj < c.z) a1 += v[j]; else if (sj < c.w) a2 += v[j]; else a3 += v[j]; }
+            }
+        }
+        double2* out = reinterpret_cast<double2*>(nzval + k0);
+        out[0] = make_double2(a0, a1); out[1] = make_double2(a2, a3);
+    } else {
+        for (int64_t k = k0; k < nnz; ++k) {
+            double acc = 0.;
+            for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) acc += __ldg(Ke + src[s]);
+            nzval[k] = acc;
+        }
+    }
 }
 // Lλ[d] = Σ (Re[q] − Rp[q])  (add_value! then add_∂!{1,:minus}, src/SweepX.jl:56-57)
 static __global__ void gather_vec_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc,

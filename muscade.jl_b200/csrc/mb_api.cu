@@ -349,7 +349,7 @@ static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkD
     return MB_OK;
 }
 static void launch_gather(mb_handle* h, bool step) {
-    if (h->nnz > 0) { gather_nz_kernel<<<nblk(h->nnz, 256), 256, 0, h->stream>>>(h->nnz, h->cstart, h->src, h->Ke, h->nzval); h->launches++; }
+    if (h->nnz > 0) { gather_nz_kernel<<<nblk((h->nnz + 3) / 4, 256), 256, 0, h->stream>>>(h->nnz, h->cstart, h->src, h->Ke, h->nzval); h->launches++; }
     gather_vec_kernel<<<nblk(h->ndofX, 256), 256, 0, h->stream>>>(h->ndofX, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll);
     h->launches++;
 }
