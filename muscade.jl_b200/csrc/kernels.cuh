@@ -44,9 +44,9 @@ static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict_
     }
 }
 // Lλ[d] = Σ (Re[q] − Rp[q])  (add_value! then add_∂!{1,:minus}, src/SweepX.jl:56-57)
-static __global__ void gather_vec_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc,
+static __global__ void gather_vec_kernel(int64_t d0, int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc,
                                   const double* __restrict__ Re, const double* __restrict__ Rp, double* __restrict__ out) {
-    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t d = d0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
     const uint32_t s0 = vstart[d], s1 = vstart[d + 1];
     double acc = 0.;
@@ -56,6 +56,31 @@ static __global__ void gather_vec_kernel(int64_t ndof, const uint32_t* __restric
         if (Rp) acc -= Rp[q];
     }
     out[d] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------- completion prefixes (host-buffer pipeline)
+// last[k] = 1 + largest contributor index of segment k, ignoring contributors inside [skip0[r],skip1[r]) (host-evaluated element types, whose
+// contributions are uploaded before the device kernels start); 0 when nothing else contributes.
+struct SkipRanges { int n; uint32_t lo[8], hi[8]; };
+static __global__ void seg_last_kernel(int64_t nseg, const uint32_t* __restrict__ start, const uint32_t* __restrict__ src, SkipRanges sk, uint32_t* __restrict__ last) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nseg) return;
+    uint32_t m = 0;
+    for (uint32_t s = start[k]; s < start[k + 1]; ++s) {
+        const uint32_t id = src[s];
+        bool skip = false;
+        for (int r = 0; r < sk.n; ++r) skip |= (id >= sk.lo[r] && id < sk.hi[r]);
+        if (!skip && id + 1 > m) m = id + 1;
+    }
+    last[k] = m;
+}
+// cnt[j] = number of leading segments whose running maximum of `last` is ≤ bound[j]  (pm is non-decreasing)
+static __global__ void prefix_count_kernel(int64_t nseg, const uint32_t* __restrict__ pm, int nb, const int64_t* __restrict__ bound, int64_t* __restrict__ cnt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    int64_t lo = 0, hi = nseg;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)pm[mid] <= bound[j]) lo = mid + 1; else hi = mid; }
+    cnt[j] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------- pattern construction

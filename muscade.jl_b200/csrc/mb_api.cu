@@ -1,6 +1,7 @@
 // C ABI of the B200 assembly engine (include/muscade_b200.h). Owns all device memory; no PyTorch, no CPU fallback.
 #include "mb_internal.h"
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,10 @@ int32_t mb_create(int32_t device, mb_handle** out) {
     if (w) h->beamW = atoi(w);
     const char* sd = getenv("MB_SPLIT_DYN");
     if (sd) h->split_dyn = atoi(sd);
+    const char* pc = getenv("MB_E2E_CHUNKS");            // host-buffer pipeline: number of element chunks (<2: one shot) and size threshold
+    if (pc) h->pipe_chunks = std::min(64, atoi(pc));
+    const char* pm = getenv("MB_E2E_MIN_NNZ");
+    if (pm) h->pipe_min_nnz = atoll(pm);
     *out = h;
     return MB_OK;
 }
@@ -47,6 +52,8 @@ int32_t mb_destroy(mb_handle* h) {
     cudaFree(h->nanflag);
     cudaFreeHost(h->nanflag_host);
     if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t ev : h->pipe_ev) cudaEventDestroy(ev);
     delete h;
     return MB_OK;
 }
@@ -305,53 +312,122 @@ int32_t mb_sweepx_get_asm(mb_handle* h, int32_t ieletyp, int64_t* asm1, int64_t*
 
 // ------------------------------------------------------------------------------------------------------------ assemble
 template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group& g, const BeamGroupDev& gd, const StateDev& sd, const NewmarkDev& nm,
-                                                       unsigned long long nanbase) {
+                                                       unsigned long long nanbase, int64_t e0) {
     double* Wc = nullptr;
-    if (ND >= 2 && h->split_dyn) {                 // two-phase Newmark kernel: 45 doubles per lane of workspace (lazily sized to the largest beam type)
-        const int64_t need = ((g.nele * 6 + 31) / 32) * 32 * MB_NCOT;
+    if (ND >= 2 && h->split_dyn) {                 // two-phase Newmark kernel: 45 doubles per lane of workspace (lazily sized to the largest launch)
+        const int64_t need = ((gd.nele * 6 + 31) / 32) * 32 * MB_NCOT;
         if (h->Wc_len < need) { if (h->Wc) dfree(h, h->Wc); h->Wc = nullptr; h->Wc_len = 0; if (dalloc(h, &h->Wc, need) == cudaSuccess) h->Wc_len = need; else cudaGetLastError(); }
         Wc = h->Wc_len >= need ? h->Wc : nullptr;  // falls back to the fused kernel when the workspace does not fit
     }
-    BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->beamW, h->stream, Wc};
+    BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base + e0 * 144, h->Re + g.vec_base + e0 * 12, h->Rp + g.vec_base + e0 * 12, h->nanflag, nanbase + (unsigned long long)e0,
+                 h->beamW, h->stream, Wc};
     launch_beam<ND, STEP>(a);
     h->launches += (STEP ? 2 : 1) + (Wc ? 1 : 0);
 }
 
-static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm, double tnow) {
+// elements [e0,e1) of group ig (bar / soil groups are always launched whole)
+static int32_t launch_group_range(mb_handle* h, size_t ig, int64_t e0, int64_t e1, int OX, int mission, const NewmarkDev& nm, double tnow) {
     const bool step = (mission == 0) && OX > 0;
     StateDev sd{h->X0, h->X1, h->X2, h->ndofU > 0 ? h->U0 : nullptr};
-    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
-        const Group& g = h->groups[ig];
-        if (g.nele == 0) continue;
-        const unsigned long long nanbase = ((unsigned long long)ig) << 40;
-        if (g.kind == G_BEAM) {
-            BeamGroupDev gd;
-            gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
-            for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
-            for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
-            if (OX == 0) launch_beam_w<1, false>(h, g, gd, sd, nm, nanbase);
-            else if (OX == 1) { if (step) launch_beam_w<2, true>(h, g, gd, sd, nm, nanbase); else launch_beam_w<2, false>(h, g, gd, sd, nm, nanbase); }
-            else { if (step) launch_beam_w<3, true>(h, g, gd, sd, nm, nanbase); else launch_beam_w<3, false>(h, g, gd, sd, nm, nanbase); }
-        }
-        else if (g.kind == G_BAR) {
-            BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
-            for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
-            launch_bar(OX + 1, step, gd, sd, nm, tnow, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
-            h->launches++;
-        } else if (g.kind == G_SOIL) {
-            SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
-            for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
-            launch_soil(OX + 1, step, gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
-            h->launches++;
-        }
-        // G_HOST: contributions were uploaded by mb_set_host_elements
+    const Group& g = h->groups[ig];
+    if (g.nele == 0 || e1 <= e0) return MB_OK;
+    const unsigned long long nanbase = ((unsigned long long)ig) << 40;
+    if (g.kind == G_BEAM) {
+        BeamGroupDev gd;
+        gd.nele = e1 - e0; gd.geo = g.geo + e0 * 16; gd.mats = g.mats; gd.mat_id = g.mat_id ? g.mat_id + e0 : nullptr;
+        gd.idxX = g.idxX + e0 * 12; gd.idxU = g.idxU ? g.idxU + e0 * 3 : nullptr; gd.udof = g.udof;
+        for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
+        for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+        if (OX == 0) launch_beam_w<1, false>(h, g, gd, sd, nm, nanbase, e0);
+        else if (OX == 1) { if (step) launch_beam_w<2, true>(h, g, gd, sd, nm, nanbase, e0); else launch_beam_w<2, false>(h, g, gd, sd, nm, nanbase, e0); }
+        else { if (step) launch_beam_w<3, true>(h, g, gd, sd, nm, nanbase, e0); else launch_beam_w<3, false>(h, g, gd, sd, nm, nanbase, e0); }
     }
+    else if (g.kind == G_BAR) {
+        BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+        for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
+        launch_bar(OX + 1, step, gd, sd, nm, tnow, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
+        h->launches++;
+    } else if (g.kind == G_SOIL) {
+        SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
+        for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
+        launch_soil(OX + 1, step, gd, sd, nm, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
+        h->launches++;
+    }
+    // G_HOST: contributions were uploaded by mb_set_host_elements
     return MB_OK;
 }
-static void launch_gather(mb_handle* h, bool step) {
-    if (h->nnz > 0) { gather_nz_kernel<<<nblk((h->nnz + 3) / 4, 256), 256, 0, h->stream>>>(h->nnz, h->cstart, h->src, h->Ke, h->nzval); h->launches++; }
-    gather_vec_kernel<<<nblk(h->ndofX, 256), 256, 0, h->stream>>>(h->ndofX, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll);
-    h->launches++;
+static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkDev& nm, double tnow) {
+    for (size_t ig = 0; ig < h->groups.size(); ++ig) { int32_t rc = launch_group_range(h, ig, 0, h->groups[ig].nele, OX, mission, nm, tnow); if (rc) return rc; }
+    return MB_OK;
+}
+// segmented reductions of non-zeros [k0,k1) (k0 a multiple of 4) and dofs [d0,d1)
+static void launch_gather_range(mb_handle* h, bool step, int64_t k0, int64_t k1, int64_t d0, int64_t d1) {
+    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, h->stream>>>(k1 - k0, h->cstart + k0, h->src, h->Ke, h->nzval + k0); h->launches++; }
+    if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, 256), 256, 0, h->stream>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
+}
+static void launch_gather(mb_handle* h, bool step) { launch_gather_range(h, step, 0, h->nnz, 0, h->ndofX); }
+
+// ---- host-buffer pipeline: chunk plan + completion prefixes (built once, at the first large mb_sweepx_assemble)
+static int32_t build_pipeline(mb_handle* h) {
+    h->pipe_state = -1;
+    cudaStream_t st = h->stream;
+    int64_t work = 0;
+    for (const Group& g : h->groups) if (g.kind != G_HOST) work += g.nele * g.nx * g.nx;
+    if (work == 0 || h->nnz == 0 || h->pipe_chunks < 2) return MB_OK;
+    const int C = h->pipe_chunks;
+    std::vector<int64_t> pair_end((size_t)C, 0), vec_end((size_t)C, 0);
+    h->pipe_items.clear();
+    int64_t done = 0; int chunk = 0;
+    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+        const Group& g = h->groups[ig];
+        if (g.kind == G_HOST || g.nele == 0) continue;
+        const int64_t per = (int64_t)g.nx * g.nx;
+        int64_t e = 0;
+        while (e < g.nele) {
+            int64_t e1 = g.nele;
+            if (g.kind == G_BEAM) {                  // fill the current chunk up to its share of the work
+                const int64_t target = (work * (chunk + 1) + C - 1) / C;
+                const int64_t room = (target - done + per - 1) / per;
+                e1 = std::min(g.nele, e + std::max<int64_t>(room, 1));
+            }
+            h->pipe_items.push_back({(int)ig, e, e1, chunk});
+            done += (e1 - e) * per;
+            for (int j = chunk; j < C; ++j) { pair_end[(size_t)j] = g.pair_base + e1 * per; vec_end[(size_t)j] = g.vec_base + e1 * g.nx; }
+            e = e1;
+            while (chunk < C - 1 && done >= (work * (chunk + 1) + C - 1) / C) ++chunk;
+        }
+    }
+    // completion prefixes on the device
+    SkipRanges skp{0, {0}, {0}}, skv{0, {0}, {0}};
+    for (const Group& g : h->groups)
+        if (g.kind == G_HOST && g.nele > 0) {
+            if (skp.n == 8) return MB_OK;            // too many host-evaluated types: keep the one-shot path
+            skp.lo[skp.n] = (uint32_t)g.pair_base; skp.hi[skp.n] = (uint32_t)(g.pair_base + g.nele * g.nx * g.nx); ++skp.n;
+            skv.lo[skv.n] = (uint32_t)g.vec_base; skv.hi[skv.n] = (uint32_t)(g.vec_base + g.nele * g.nx); ++skv.n;
+        }
+    uint32_t* last = nullptr; int64_t *bound = nullptr, *cnt = nullptr;
+    CK(dalloc(h, &last, std::max(h->nnz, h->ndofX))); CK(dalloc(h, &bound, C)); CK(dalloc(h, &cnt, C));
+    h->pipe_nz_end.assign((size_t)C, 0); h->pipe_vec_end.assign((size_t)C, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t nseg = pass == 0 ? h->nnz : h->ndofX;
+        seg_last_kernel<<<nblk(nseg, 256), 256, 0, st>>>(nseg, pass == 0 ? h->cstart : h->vstart, pass == 0 ? h->src : h->vsrc, pass == 0 ? skp : skv, last);
+        void* tmp = nullptr; size_t tmpsz = 0;
+        CK(cub::DeviceScan::InclusiveScan(nullptr, tmpsz, last, last, cub::Max(), nseg, st));
+        CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+        CK(cub::DeviceScan::InclusiveScan(tmp, tmpsz, last, last, cub::Max(), nseg, st));
+        CK(cudaMemcpyAsync(bound, pass == 0 ? pair_end.data() : vec_end.data(), (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        prefix_count_kernel<<<1, 64, 0, st>>>(nseg, last, C, bound, cnt);
+        CK(cudaMemcpyAsync(pass == 0 ? h->pipe_nz_end.data() : h->pipe_vec_end.data(), cnt, (size_t)C * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+        h->launches += 3;
+    }
+    dfree(h, last); dfree(h, bound); dfree(h, cnt);
+    for (int j = 0; j < C - 1; ++j) h->pipe_nz_end[(size_t)j] &= ~(int64_t)3;     // ranges of the 4-per-thread reduction start at multiples of 4
+    h->pipe_nz_end[(size_t)C - 1] = h->nnz; h->pipe_vec_end[(size_t)C - 1] = h->ndofX;
+    if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    while ((int)h->pipe_ev.size() < C) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); h->pipe_ev.push_back(ev); }
+    h->pipe_state = 1;
+    return MB_OK;
 }
 
 extern "C" {
@@ -396,6 +472,33 @@ int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const doub
     if (OX >= 1) CK(cudaMemcpyAsync(h->X1, X1, nb, cudaMemcpyHostToDevice, h->stream));
     if (OX >= 2) CK(cudaMemcpyAsync(h->X2, X2, nb, cudaMemcpyHostToDevice, h->stream));
     if (U0 && h->ndofU > 0) CK(cudaMemcpyAsync(h->U0, U0, (size_t)h->ndofU * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->pipe_state == 0 && nzval && h->nnz >= h->pipe_min_nnz) { int32_t rc = build_pipeline(h); if (rc) return rc; }
+    if (h->pipe_state == 1 && nzval) {
+        // chunked: evaluate element range j, reduce the non-zeros / dofs it completes, ship them while range j+1 computes
+        ARG(OX >= 0 && OX <= 2 && (mission == 0 || mission == 1) && newmark, "bad OX / mission / newmark");
+        NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
+        const bool step = mission == 0 && OX > 0;
+        CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
+        const int C = h->pipe_chunks;
+        size_t it = 0; int64_t k0 = 0, d0 = 0;
+        for (int j = 0; j < C; ++j) {
+            for (; it < h->pipe_items.size() && h->pipe_items[it].chunk == j; ++it) {
+                const mb_handle::PipeItem& w = h->pipe_items[it];
+                int32_t rc = launch_group_range(h, (size_t)w.ig, w.e0, w.e1, OX, mission, nm, t);
+                if (rc) return rc;
+            }
+            const int64_t k1 = h->pipe_nz_end[(size_t)j], d1 = h->pipe_vec_end[(size_t)j];
+            launch_gather_range(h, step, k0, k1, d0, d1);
+            CK(cudaEventRecord(h->pipe_ev[(size_t)j], h->stream));
+            CK(cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[(size_t)j], 0));
+            if (k1 > k0) CK(cudaMemcpyAsync(nzval + k0, h->nzval + k0, (size_t)(k1 - k0) * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (Llambda && d1 > d0) CK(cudaMemcpyAsync(Llambda + d0, h->Ll + d0, (size_t)(d1 - d0) * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+            k0 = k1; d0 = d1;
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->copy_stream));
+        return mb_sync(h, where);
+    }
     int32_t rc = mb_sweepx_assemble_dev(h, OX, mission, t, newmark);
     if (rc) return rc;
     if (Llambda) CK(cudaMemcpyAsync(Llambda, h->Ll, nb, cudaMemcpyDeviceToHost, h->stream));

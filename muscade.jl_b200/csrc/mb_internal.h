@@ -57,6 +57,15 @@ struct mb_handle {
     int32_t *if_send = nullptr, *if_recv = nullptr;   // interface index lists (0-based into [nzval | Lλ], −1 = ghost)
     int64_t if_nsend_nz = 0, if_nsend_v = 0, if_nrecv_nz = 0, if_nrecv_v = 0;
     struct DirectData* direct = nullptr;      // DirectXUA state (mb_direct.cu)
+    // host-buffer path (mb_sweepx_assemble): element ranges are evaluated chunk by chunk and every prefix of nzval / Lλ whose contributors
+    // are all done is reduced and copied to the host while the next chunk computes
+    struct PipeItem { int ig; int64_t e0, e1; int chunk; };
+    std::vector<PipeItem> pipe_items;
+    std::vector<int64_t> pipe_nz_end, pipe_vec_end;      // per chunk: non-zeros / dofs complete after it
+    int pipe_state = 0;                                  // 0 not built, 1 ready, -1 not applicable
+    int pipe_chunks = 8; int64_t pipe_min_nnz = 1 << 22;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;
 };
 
 #define CK(call)                                                                                         \

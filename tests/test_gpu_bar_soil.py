@@ -28,8 +28,11 @@ def mixed_model(mb, N=40):
     return model
 
 
+@pytest.mark.parametrize("pipe", [False, True])
 @pytest.mark.parametrize("OX,mission", [(0, "iter"), (1, "step"), (2, "iter"), (2, "step")])
-def test_mixed_beam_bar_soil(mb, OX, mission):
+def test_mixed_beam_bar_soil(mb, OX, mission, pipe, monkeypatch):
+    if pipe:       # force the chunked host-buffer pipeline of mb_sweepx_assemble (normally only for ≥ 4M non-zeros)
+        monkeypatch.setenv("MB_E2E_MIN_NNZ", "0"); monkeypatch.setenv("MB_E2E_CHUNKS", "4")
     model = mixed_model(mb)
     mb.setscale(model, scale=dict(X=dict(t1=3., t2=3., t3=3., r1=1., r2=1., r3=1.)))
     state = mb.initialize(model)

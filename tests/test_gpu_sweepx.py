@@ -87,3 +87,33 @@ def test_nan_reported_with_location(mb, engine_factory):
     with pytest.raises(mb.MuscadeB200Error) as ei:
         eng.sweepx_assemble(0, "iter", X, mb.synthetic.newmark_coefficients(0, 0.))
     assert ei.value.dbg["ieletyp"] == 1 and ei.value.dbg["iele"] == 40
+
+
+@pytest.mark.parametrize("OX,mission", [(0, "iter"), (2, "step")])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_pipelined_host_path_is_bit_identical(mb, engine_factory, monkeypatch, OX, mission, shuffle):
+    """mb_sweepx_assemble with host buffers evaluates element chunks and ships completed prefixes of nzval / Lλ while the next chunk
+    computes (large models only; forced here).  Same kernels, same summation order ⇒ bit-identical to the one-shot path, also when the
+    element order is random (no prefix completes early) and when the chunk count does not divide the element count."""
+    N = 1013
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=OX > 0)
+    if shuffle:
+        perm = np.random.default_rng(3).permutation(N)
+        eleobj, idx = eleobj[perm], idx[perm]
+    X = mb.synthetic.state(ndof, nder=OX + 1)
+    nm = mb.synthetic.newmark_coefficients(OX, 0.3)
+    ref = engine_factory()
+    ref.add_eulerbeam3d(eleobj, idx, np.ones(12)); ref.sweepx_prepare(ndof)
+    L0, nz0 = ref.sweepx_assemble(OX, mission, X, nm)
+    monkeypatch.setenv("MB_E2E_MIN_NNZ", "0"); monkeypatch.setenv("MB_E2E_CHUNKS", "7")
+    eng = engine_factory()
+    eng.add_eulerbeam3d(eleobj, idx, np.ones(12)); eng.sweepx_prepare(ndof)
+    for _ in range(2):
+        L1, nz1 = eng.sweepx_assemble(OX, mission, X, nm)
+        assert np.array_equal(L0, L1) and np.array_equal(nz0, nz1)
+    # NaN location is still the first offending element in element order
+    Xbad = [x.copy() for x in X]
+    Xbad[0][idx[700, 3] - 1] = np.nan
+    with pytest.raises(mb.MuscadeB200Error) as ei:
+        eng.sweepx_assemble(OX, mission, Xbad, nm)
+    assert ei.value.dbg["iele"] == min(i for i in range(N) if (idx[i] == idx[700, 3]).any()) + 1
