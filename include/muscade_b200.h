@@ -108,6 +108,19 @@ int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nL
 int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
 
 /* ---- sharding over the GPUs of one box (one handle per GPU / process; NCCL itself is driven by the host, torch.distributed or ncclComm) -- */
+/* Device-resident state: the Newton update runs where the state lives, so X only crosses PCIe when the caller asks.
+ *   mb_sweepx_set_state / get_state : state.X[1..OX+1] (and state.U[1]) host↔device; pointers may be host or device memory.
+ *   mb_sweepx_set_dof_scale         : dis.scaleX per model dof (Xdofgr = allXdofs, src/SweepX.jl:196); default all ones.
+ *   mb_sweepx_newmark_decrement     : Newmarkβdecrement!{OX}(state,Δx,Xdofgr,c,firstiter,…) (src/SweepX.jl:98-132) with getdof!/decrement!
+ *                                     (src/Assemble.jl:206-233), same operation order (no FMA contraction) ⇒ bit-identical to the reference
+ *                                     arithmetic. dx: the solver's Δx (ndofX, host or device). Optional outputs Σ Δx² and Σ Lλ² of the last
+ *                                     assembled gradient (the convergence test of src/SweepX.jl:209,214), reduced on the device.
+ * After mb_sweepx_set_state, mb_sweepx_assemble may be called with X0 = NULL: it then assembles at the device-resident state. */
+int32_t mb_sweepx_set_state(mb_handle* h, int32_t OX, const double* X0, const double* X1, const double* X2, const double* U0);
+int32_t mb_sweepx_get_state(mb_handle* h, int32_t OX, double* X0, double* X1, double* X2);
+int32_t mb_sweepx_set_dof_scale(mb_handle* h, const double* scaleX);
+int32_t mb_sweepx_newmark_decrement(mb_handle* h, int32_t OX, int32_t firstiter, const double* dx, const double* newmark, double* dx2, double* Ll2);
+
 /* Run this handle's kernels and copies on a caller-owned CUDA stream (e.g. the stream NCCL work is ordered against). */
 int32_t mb_set_stream(mb_handle* h, void* cuda_stream);
 /* SweepX element-range sharding: entries of the local Lλ / nzval that belong to nodes shared with a neighbouring shard.

@@ -46,6 +46,10 @@ SYMBOLS = {
     "mb_sweepx_assemble": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, f64p,
                                         C.c_void_p, C.c_void_p, C.POINTER(ErrInfo)]),
     "mb_sweepx_assemble_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p]),
+    "mb_sweepx_set_state": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_sweepx_get_state": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_sweepx_set_dof_scale": (C.c_int32, [H, C.c_void_p]),
+    "mb_sweepx_newmark_decrement": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mb_sync": (C.c_int32, [H, C.POINTER(ErrInfo)]),
     "mb_get_device_ptrs": (C.c_int32, [H, C.POINTER(DevPtrs)]),
     "mb_set_ndofU": (C.c_int32, [H, C.c_int64]),

@@ -152,6 +152,32 @@ static __global__ void widen_plus1_kernel(int64_t n, const int32_t* __restrict__
     if (i < n) out[i] = (int64_t)in[i] + add;
 }
 
+// ---------------------------------------------------------------------------------------------- state update
+// Newmarkβdecrement!{OX} over all X dofs (src/SweepX.jl:98-132): x′,x″ ← getdof! (divide by scale), a = a₂x′+a₃x″, b = b₂x′+b₃x″ on the first
+// iteration, Δx′ = a₁Δx(+a), Δx″ = b₁Δx(+b), then decrement! X_d −= Δ·scale.  Explicit _rn intrinsics: no FMA contraction, i.e. the
+// reference's (Julia broadcast) rounding sequence.
+template <int OX>
+static __global__ void newmark_decrement_kernel(int64_t n, const double* __restrict__ dx, const double* __restrict__ scale, double* __restrict__ X0,
+                                                double* __restrict__ X1, double* __restrict__ X2, NewmarkDev c, int firstiter) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = dx[i], s = scale ? scale[i] : 1.0;
+    if (OX >= 1) {
+        double d1 = __dmul_rn(c.a1, d), d2 = (OX >= 2) ? __dmul_rn(c.b1, d) : 0.;
+        if (firstiter) {
+            const double xp = __ddiv_rn(X1[i], s), xpp = (OX >= 2) ? __ddiv_rn(X2[i], s) : 0.;
+            if (OX >= 2) {
+                d1 = __dadd_rn(d1, __dadd_rn(__dmul_rn(c.a2, xp), __dmul_rn(c.a3, xpp)));
+                d2 = __dadd_rn(d2, __dadd_rn(__dmul_rn(c.b2, xp), __dmul_rn(c.b3, xpp)));
+            } else d1 = __dadd_rn(d1, __dmul_rn(c.a2, xp));
+        }
+        X1[i] = __dsub_rn(X1[i], __dmul_rn(d1, s));
+        if (OX >= 2) X2[i] = __dsub_rn(X2[i], __dmul_rn(d2, s));
+    }
+    X0[i] = __dsub_rn(X0[i], __dmul_rn(d, s));
+}
+struct Square { __host__ __device__ double operator()(double x) const { return x * x; } };
+
 // ---------------------------------------------------------------------------------------------- measurement
 // FP64 FMA peak: 8 independent chains per thread, no memory traffic.
 static __global__ void fp64_peak_kernel(double* out, int iters) {

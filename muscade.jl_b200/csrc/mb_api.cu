@@ -50,6 +50,7 @@ int32_t mb_destroy(mb_handle* h) {
     mb_direct_release(h);
     for (void* p : h->owned) cudaFree(p);
     cudaFree(h->nanflag);
+    if (h->redtmp) cudaFree(h->redtmp);
     cudaFreeHost(h->nanflag_host);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -465,12 +466,14 @@ int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const doub
                            const double* U0, double t, const double* newmark, double* Llambda, double* nzval, mb_errinfo* where) {
     if (!h) return MB_ERR_ARG;
     ARG(h->prepared, "call mb_sweepx_prepare first");
-    ARG(X0 && (OX < 1 || X1) && (OX < 2 || X2), "state vectors missing for this OX");
+    ARG(!X0 || ((OX < 1 || X1) && (OX < 2 || X2)), "state vectors missing for this OX");
     CK(cudaSetDevice(h->device));
     const size_t nb = (size_t)h->ndofX * sizeof(double);
-    CK(cudaMemcpyAsync(h->X0, X0, nb, cudaMemcpyHostToDevice, h->stream));
-    if (OX >= 1) CK(cudaMemcpyAsync(h->X1, X1, nb, cudaMemcpyHostToDevice, h->stream));
-    if (OX >= 2) CK(cudaMemcpyAsync(h->X2, X2, nb, cudaMemcpyHostToDevice, h->stream));
+    if (X0) {                                      // X0 == NULL: assemble at the device-resident state (mb_sweepx_set_state / _newmark_decrement)
+        CK(cudaMemcpyAsync(h->X0, X0, nb, cudaMemcpyHostToDevice, h->stream));
+        if (OX >= 1) CK(cudaMemcpyAsync(h->X1, X1, nb, cudaMemcpyHostToDevice, h->stream));
+        if (OX >= 2) CK(cudaMemcpyAsync(h->X2, X2, nb, cudaMemcpyHostToDevice, h->stream));
+    }
     if (U0 && h->ndofU > 0) CK(cudaMemcpyAsync(h->U0, U0, (size_t)h->ndofU * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (h->pipe_state == 0 && nzval && h->nnz >= h->pipe_min_nnz) { int32_t rc = build_pipeline(h); if (rc) return rc; }
     if (h->pipe_state == 1 && nzval) {
@@ -504,6 +507,78 @@ int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const doub
     if (Llambda) CK(cudaMemcpyAsync(Llambda, h->Ll, nb, cudaMemcpyDeviceToHost, h->stream));
     if (nzval && h->nnz > 0) CK(cudaMemcpyAsync(nzval, h->nzval, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     return mb_sync(h, where);
+}
+
+int32_t mb_sweepx_set_state(mb_handle* h, int32_t OX, const double* X0, const double* X1, const double* X2, const double* U0) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && OX >= 0 && OX <= 2, "not prepared / bad OX");
+    ARG(X0 && (OX < 1 || X1) && (OX < 2 || X2), "state vectors missing for this OX");
+    CK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)h->ndofX * sizeof(double);
+    const double* src[3] = {X0, X1, X2}; double* dst[3] = {h->X0, h->X1, h->X2};
+    for (int d = 0; d <= OX; ++d) CK(cudaMemcpyAsync(dst[d], src[d], nb, cudaMemcpyDefault, h->stream));
+    if (U0 && h->ndofU > 0) CK(cudaMemcpyAsync(h->U0, U0, (size_t)h->ndofU * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
+int32_t mb_sweepx_get_state(mb_handle* h, int32_t OX, double* X0, double* X1, double* X2) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && OX >= 0 && OX <= 2, "not prepared / bad OX");
+    CK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)h->ndofX * sizeof(double);
+    double* dst[3] = {X0, X1, X2}; const double* src[3] = {h->X0, h->X1, h->X2};
+    for (int d = 0; d <= OX; ++d) if (dst[d]) CK(cudaMemcpyAsync(dst[d], src[d], nb, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
+int32_t mb_sweepx_set_dof_scale(mb_handle* h, const double* scaleX) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && scaleX, "not prepared / null");
+    CK(cudaSetDevice(h->device));
+    if (!h->dofscale) CK(dalloc(h, &h->dofscale, h->ndofX));
+    CK(cudaMemcpyAsync(h->dofscale, scaleX, (size_t)h->ndofX * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
+int32_t mb_sweepx_newmark_decrement(mb_handle* h, int32_t OX, int32_t firstiter, const double* dx, const double* newmark, double* dx2, double* Ll2) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && OX >= 0 && OX <= 2 && dx && (OX == 0 || newmark), "not prepared / bad OX / null");
+    CK(cudaSetDevice(h->device));
+    const int64_t n = h->ndofX;
+    cudaPointerAttributes at;
+    const bool on_dev = cudaPointerGetAttributes(&at, dx) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const double* d = dx;
+    if (!on_dev) {
+        if (!h->dxbuf) CK(dalloc(h, &h->dxbuf, n));
+        CK(cudaMemcpyAsync(h->dxbuf, dx, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        d = h->dxbuf;
+    }
+    NewmarkDev c{0, 0, 0, 0, 0, 0, 0};
+    if (newmark) c = NewmarkDev{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
+    if (dx2 || Ll2) {                              // Σ Δx², Σ Lλ² (src/SweepX.jl:209) before the state moves
+        if (!h->red) CK(dalloc(h, &h->red, 2));
+        for (int k = 0; k < 2; ++k) {
+            if (!(k == 0 ? dx2 : Ll2)) continue;
+            cub::TransformInputIterator<double, Square, const double*> it(k == 0 ? d : h->Ll, Square{});
+            size_t need = 0;
+            CK(cub::DeviceReduce::Sum(nullptr, need, it, h->red + k, n, h->stream));
+            if (need > h->redtmp_sz) { if (h->redtmp) cudaFree(h->redtmp); CK(cudaMalloc(&h->redtmp, need)); h->redtmp_sz = need; }
+            CK(cub::DeviceReduce::Sum(h->redtmp, need, it, h->red + k, n, h->stream));
+            h->launches += 1;
+        }
+    }
+    if (OX == 0) newmark_decrement_kernel<0><<<nblk(n, 256), 256, 0, h->stream>>>(n, d, h->dofscale, h->X0, h->X1, h->X2, c, firstiter);
+    else if (OX == 1) newmark_decrement_kernel<1><<<nblk(n, 256), 256, 0, h->stream>>>(n, d, h->dofscale, h->X0, h->X1, h->X2, c, firstiter);
+    else newmark_decrement_kernel<2><<<nblk(n, 256), 256, 0, h->stream>>>(n, d, h->dofscale, h->X0, h->X1, h->X2, c, firstiter);
+    h->launches++;
+    double r[2] = {0., 0.};
+    if (dx2 || Ll2) CK(cudaMemcpyAsync(r, h->red, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (dx2) *dx2 = r[0];
+    if (Ll2) *Ll2 = r[1];
+    CK(cudaGetLastError());
+    return MB_OK;
 }
 
 int32_t mb_get_device_ptrs(mb_handle* h, mb_dev_ptrs* out) {

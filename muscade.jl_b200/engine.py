@@ -130,6 +130,47 @@ class Engine:
         check(self.h, rc, dbg)
         return Llambda, nzval
 
+    # ---- device-resident state
+    def set_state(self, X, U0=None):
+        """state.X[1..OX+1] (and state.U[1]) → device"""
+        X = [_f64(x) for x in X]
+        OX = len(X) - 1
+        check(self.h, self.L.mb_sweepx_set_state(self.h, OX, ptr(X[0]), ptr(X[1]) if OX >= 1 else None, ptr(X[2]) if OX >= 2 else None, ptr(_f64(U0))))
+
+    def get_state(self, OX):
+        X = [np.empty(self.ndofX) for _ in range(OX + 1)]
+        check(self.h, self.L.mb_sweepx_get_state(self.h, OX, ptr(X[0]), ptr(X[1]) if OX >= 1 else None, ptr(X[2]) if OX >= 2 else None))
+        return X
+
+    def set_dof_scale(self, scaleX):
+        s = _f64(scaleX)
+        assert s.shape == (self.ndofX,)
+        check(self.h, self.L.mb_sweepx_set_dof_scale(self.h, ptr(s)))
+
+    def newmark_decrement(self, OX, firstiter, dx, newmark, norms=True):
+        """Newmarkβdecrement!{OX} on the device-resident state (SweepX.jl:98-132); returns (Σ Δx², Σ Lλ²) when norms."""
+        dx = _f64(dx)
+        assert dx.shape == (self.ndofX,)
+        a, b = C.c_double(0.), C.c_double(0.)
+        check(self.h, self.L.mb_sweepx_newmark_decrement(self.h, OX, int(bool(firstiter)), ptr(dx), ptr(_f64(newmark)),
+                                                         C.byref(a) if norms else None, C.byref(b) if norms else None))
+        return a.value, b.value
+
+    def sweepx_assemble_resident(self, OX, mission, newmark, U0=None, t=0., Llambda=None, nzval=None, dbg=None):
+        """assemble!{mission} at the device-resident state; host Lλ / nzval out (chunk-pipelined copy for large models)."""
+        if Llambda is None:
+            Llambda = np.empty(self.ndofX)
+        if nzval is None:
+            nzval = np.empty(self.nnz)
+        where = ErrInfo()
+        rc = self.L.mb_sweepx_assemble(self.h, OX, {"step": 0, "iter": 1}[mission], None, None, None, ptr(_f64(U0)), float(t), _f64(newmark),
+                                       ptr(Llambda), ptr(nzval), C.byref(where))
+        if rc == _lib.MB_ERR_NAN:
+            d = dict(dbg or {}); d.update(ieletyp=where.ieletyp, iele=where.iele)
+            raise MuscadeB200Error("residual(...) returned NaN in R, FB or derivatives", d)
+        check(self.h, rc, dbg)
+        return Llambda, nzval
+
     def sweepx_assemble_dev(self, OX, mission, newmark, t=0.):
         check(self.h, self.L.mb_sweepx_assemble_dev(self.h, OX, {"step": 0, "iter": 1}[mission], float(t), _f64(newmark)))
 

@@ -159,8 +159,10 @@ def newmark_decrement(OX, state, Δx, Xdofgr, c, firstiter, buf):
         decrement(state, 1, Δx, Xdofgr); decrement(state, 2, Δxp, Xdofgr)
 
 
-def solve(OX, initialstate, time, β=0.25, γ=0.5, maxiter=50, maxΔx=1e-5, maxLλ=np.inf, verbose=False, device=0, dbg=None):
-    """solve(SweepX{OX};initialstate,time,β,γ,maxiter,maxΔx,maxLλ)  (SweepX.jl:179-226) → list of states, one per time step."""
+def solve(OX, initialstate, time, β=0.25, γ=0.5, maxiter=50, maxΔx=1e-5, maxLλ=np.inf, verbose=False, device=0, dbg=None, device_state=False):
+    """solve(SweepX{OX};initialstate,time,β,γ,maxiter,maxΔx,maxLλ)  (SweepX.jl:179-226) → list of states, one per time step.
+    device_state=True keeps state.X on the GPU between iterations: Newmarkβdecrement! runs there (mb_sweepx_newmark_decrement) and X is
+    downloaded only for saved states (and for host-evaluated element types)."""
     model, dis = initialstate.model, initialstate.dis
     out, asm, Xdofgr = prepare(OX, model, dis, device)
     n = Xdofgr.getndof()
@@ -169,6 +171,10 @@ def solve(OX, initialstate, time, β=0.25, γ=0.5, maxiter=50, maxΔx=1e-5, maxL
     state = initialstate.copy().with_orders(1, OX + 1, 1)
     states = []
     citer = 0
+    eng = out.engine
+    if device_state:
+        eng.set_dof_scale(Xdofgr.scaleX)
+        eng.set_state(state.X[: OX + 1])
     try:
         for step, t in enumerate(time, 1):
             oldt = state.time
@@ -180,15 +186,28 @@ def solve(OX, initialstate, time, β=0.25, γ=0.5, maxiter=50, maxΔx=1e-5, maxL
             for iiter in range(1, maxiter + 1):
                 citer += 1
                 firstiter = iiter == 1
-                assemble("step" if firstiter else "iter", out, asm, dis, model, state, Δt, dict(dbg or {}, solver="SweepX", step=step, iiter=iiter))
+                mission, dbgi = "step" if firstiter else "iter", dict(dbg or {}, solver="SweepX", step=step, iiter=iiter)
+                if device_state:
+                    if out.host_types:
+                        state.X[: OX + 1] = eng.get_state(OX)
+                        _host_elements(out, state, mission, state.time)
+                    U0 = state.U[0] if len(state.U) and state.U[0].size else None
+                    eng.sweepx_assemble_resident(OX, mission, out.c, U0=U0, t=state.time, Llambda=out.Lλ, nzval=out.Lλx.data, dbg=dbgi)
+                else:
+                    assemble(mission, out, asm, dis, model, state, Δt, dbgi)
                 try:
                     lu = spla.splu(out.Lλx.tocsc())
                 except RuntimeError:
                     muscadeerror("matrix factorization failed at step=%i, iiter=%i" % (step, iiter))
                 Δx = lu.solve(out.Lλ)
-                Δx2, Lλ2 = float(Δx @ Δx), float(out.Lλ @ out.Lλ)
-                newmark_decrement(OX, state, Δx, Xdofgr, out.c, firstiter, buf)
+                if device_state:
+                    Δx2, Lλ2 = eng.newmark_decrement(OX, firstiter, Δx, out.c)
+                else:
+                    Δx2, Lλ2 = float(Δx @ Δx), float(out.Lλ @ out.Lλ)
+                    newmark_decrement(OX, state, Δx, Xdofgr, out.c, firstiter, buf)
                 if Δx2 <= cΔx2 and Lλ2 <= cLλ2:
+                    if device_state:
+                        state.X[: OX + 1] = eng.get_state(OX)
                     if verbose:
                         print("    step %3d converged in %3d iterations. |Δx|=%7.1e |Lλ|=%7.1e" % (step, iiter, Δx2 ** .5, Lλ2 ** .5))
                     states.append(State(state.time, state.Λ, [x.copy() for x in state.X], state.U, state.A, state.SP, model, dis))

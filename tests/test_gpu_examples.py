@@ -72,6 +72,10 @@ def test_static_beam_analysis(mb):
     for k in range(4):
         # converged states: same Newton loop, same (SuperLU) factorisation, assemblies equal to 1e-12 ⇒ states equal to solver round-off
         assert np.abs(states[k].X[0] - ref[k]).max() <= 1e-8 * max(1., np.abs(ref[k]).max()), k
+    # state kept on the GPU between iterations (device-side Newmarkβdecrement!): identical arithmetic ⇒ identical converged states
+    dev = mb.sweepx.solve(0, state0, times, maxΔx=1e-9, device_state=True)
+    for k in range(4):
+        assert np.array_equal(dev[k].X[0], states[k].X[0]), k
 
 
 def test_static_assembly_with_boundary_elements_parity(mb):
@@ -100,3 +104,55 @@ def test_static_assembly_with_boundary_elements_parity(mb):
     assert np.abs(out.Lλ - L).max() <= 1e-12 * np.abs(nz).max()
     assert np.abs(out.Lλx.data - nz).max() <= 1e-12 * np.abs(nz).max()
     out.engine.close()
+
+
+def test_dynamic_cantilever_newmark(mb):
+    """SweepX{2} (Newmark-β, src/SweepX.jl:179-226) on a cantilever released under its own weight: :step then :iter assemblies,
+    Newmarkβdecrement!, 6 time steps — GPU engine vs the same loop on the oracle's assembly; host-resident vs device-resident state."""
+    nel = 6
+    model = mb.Model("Cantilever")
+    coord = np.stack([np.linspace(0., 3., nel + 1), np.zeros(nel + 1), np.zeros(nel + 1)], axis=1)
+    nod = mb.addnode(model, coord)
+    mat = mb.BeamCrossSection(EA=1e5, EI2=50., EI3=40., GJ=30., mu=2., iota1=.05, w=4., Ca2=.5, Ca3=.5, Cq2=.3, Cq3=.3)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:]], axis=1), mat=mat, orient2=(0., 1., 0.))
+    for f in ["t1", "t2", "t3", "r1", "r2", "r3"]:
+        mb.addelement(model, mb.Hold, [nod[0]], field=f)
+    state0 = mb.initialize(model, time=0.)       # as test/TestSweepX2.jl:12 (the default −∞ gives Δt = ∞ on the first step)
+    times = 0.02 * np.arange(1, 7)
+    host = mb.sweepx.solve(2, state0, times, maxΔx=1e-9)
+    dev = mb.sweepx.solve(2, state0, times, maxΔx=1e-9, device_state=True)
+    assert len(host) == len(dev) == 6
+    for a, b in zip(host, dev):
+        for d in range(3):
+            assert np.array_equal(a.X[d], b.X[d])
+    assert abs(host[-1].X[0]).max() > 1e-4          # it moved
+    # oracle-driven loop
+    dis = state0.dis
+    ndof = model.getndof("X")
+    odis = [dict(X=d.X, U=np.zeros((d.X.shape[0], 0), np.int64), A=np.zeros((d.X.shape[0], 0), np.int64)) for d in dis.dis]
+    asm1, asm2, colptr, rowval = OP.prepare_sweepx(odis, ndof, 0, 0)
+    X = [np.zeros(ndof) for _ in range(3)]
+    told = 0.
+    for istep, t in enumerate(times):
+        nm = OE.newmark_coefficients(2, t - told); told = t
+        a1, a2, a3, b1, b2, b3 = nm[:6]
+        for it in range(50):
+            mission = "step" if it == 0 else "iter"
+            L = np.zeros(ndof); nz = np.zeros(len(rowval))
+            OE.sweepx_assemble_beams(model.ele[0].eleobj, dis.dis[0].X, asm1[0].T, asm2[0].T, 2, mission, X, np.ones(12), nm, L, nz)
+            for k in range(1, 7):        # Hold: R = (−λ, −x), constant K, no dependence on x′, x″ ⇒ no predictor term
+                ix = dis.dis[k].X[0] - 1; q = asm2[k][:, 0] - 1
+                L[ix[0]] += -X[0][ix[1]]; L[ix[1]] += -X[0][ix[0]]
+                nz[q[1]] += -1.; nz[q[2]] += -1.
+            dx = spla.splu(sp.csc_matrix((nz, rowval - 1, colptr - 1), shape=(ndof, ndof))).solve(L)
+            if it == 0:
+                a = a2 * X[1] + a3 * X[2]; b = b2 * X[1] + b3 * X[2]
+                dxp = a1 * dx + a; dxpp = b1 * dx + b
+            else:
+                dxp = a1 * dx; dxpp = b1 * dx
+            X[0] = X[0] - dx; X[1] = X[1] - dxp; X[2] = X[2] - dxpp
+            if dx @ dx <= 1e-18:
+                break
+        for d in range(3):
+            ref = X[d]
+            assert np.abs(host[istep].X[d] - ref).max() <= 1e-7 * max(1., np.abs(ref).max()), (istep, d)

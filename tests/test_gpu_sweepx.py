@@ -117,3 +117,37 @@ def test_pipelined_host_path_is_bit_identical(mb, engine_factory, monkeypatch, O
     with pytest.raises(mb.MuscadeB200Error) as ei:
         eng.sweepx_assemble(OX, mission, Xbad, nm)
     assert ei.value.dbg["iele"] == min(i for i in range(N) if (idx[i] == idx[700, 3]).any()) + 1
+
+
+@pytest.mark.parametrize("OX", [0, 1, 2])
+def test_device_newmark_decrement_is_bit_identical(mb, engine_factory, OX):
+    """mb_sweepx_newmark_decrement ≡ Newmarkβdecrement!{OX} (SweepX.jl:98-132) with getdof!/decrement! (Assemble.jl:206-233):
+    same rounding sequence as the host restatement (no FMA contraction) ⇒ bit-identical states, first and later iterations."""
+    N = 300
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=True)
+    eng = engine_factory()
+    eng.add_eulerbeam3d(eleobj, idx, np.ones(12)); eng.sweepx_prepare(ndof)
+    rng = np.random.default_rng(11)
+    scale = rng.uniform(0.1, 10., ndof)
+    X = [rng.standard_normal(ndof) for _ in range(OX + 1)]
+    nm = mb.synthetic.newmark_coefficients(OX, 0.37)
+    eng.set_dof_scale(scale); eng.set_state(X)
+
+    class S:                       # the slice of State / DofGroup the host restatement touches
+        pass
+    st = S(); st.X = [x.copy() for x in X]; st.Λ = []; st.U = []; st.A = np.zeros(0)
+    gr = S(); gr.iX = gr.jX = np.arange(1, ndof + 1); gr.scaleX = scale
+    gr.iΛ = gr.iU = gr.iA = gr.jΛ = gr.jU = gr.jA = np.zeros(0, np.int64)
+    buf = (np.zeros(ndof), np.zeros(ndof))
+    for it in range(3):
+        dx = rng.standard_normal(ndof) * 1e-2
+        mb.sweepx.newmark_decrement(OX, st, dx, gr, nm, it == 0, buf)
+        dx2, _ = eng.newmark_decrement(OX, it == 0, dx, nm)
+        got = eng.get_state(OX)
+        for d in range(OX + 1):
+            assert np.array_equal(got[d], st.X[d]), (it, d, np.abs(got[d] - st.X[d]).max())
+        assert abs(dx2 - dx @ dx) <= 1e-13 * (dx @ dx)
+    # assembling at the resident state == assembling at the same state passed from the host
+    L0, nz0 = eng.sweepx_assemble_resident(OX, "iter", nm)
+    L1, nz1 = eng.sweepx_assemble(OX, "iter", st.X, nm)
+    assert np.array_equal(L0, L1) and np.array_equal(nz0, nz1)
