@@ -209,26 +209,39 @@ __global__ void big_fill_kernel(BigDev B, int64_t ncol, const int64_t* __restric
         off += p1 - p0;
     }
 }
-// Values of the owned Lvv columns, the hot form: a CTA works inside ONE block column (tcol,class), so the list of blocks of that
-// block column — source array, finite-difference weights w_α·Δt^(-α) (DirectXUA.jl:347-349), class-pair pattern — is decoded once into
-// shared memory; then each warp streams pattern columns: per block ≤ 3 coalesced loads and one coalesced store of the column slice.
+// Values of the owned Lvv columns, the hot form: a CTA works inside ONE block column (tcol,class) on a chunk of pattern columns, so the
+// list of blocks of that block column — source array, finite-difference weights w_α·Δt^(-α) (DirectXUA.jl:347-349), class-pair pattern —
+// is decoded once into shared memory.  Inside a block the source entries of consecutive pattern columns are contiguous (CSC), so the
+// threads run over them flat: coalesced loads of ≤ 3 derivative arrays, destination = column base + offset of the block inside the
+// column + position in the slice.  For a fixed column class only two class-pair patterns occur (rows Λ/X, rows U), so the offset of block
+// j inside a column is nA_j·sizeA(col) + nB_j·sizeB(col).
 constexpr int MB_BIG_MAXB = 48;          // ≥ 3 classes × 5 step offsets × (room for A-class blocks)
 constexpr int MB_BIG_CPC = 128;          // pattern columns per CTA
-struct BlkDesc { const double* a; const int32_t* pc; double wd[3]; int64_t nnzp; int nder; };
+constexpr int MB_BIG_CAP = 6144;         // pattern entries of one kind per CTA chunk held in the column-of-entry table
+struct BlkDesc { const double* a; const int32_t* pc; double wd[3]; int64_t nnzp; int nder, kind, nA, nB; };
 __global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t* __restrict__ colptr, double* __restrict__ nzval) {
     __shared__ BlkDesc sd[MB_BIG_MAXB];
-    const int bc = blockIdx.y, cb = bc % 3;
+    __shared__ int64_t colbase[MB_BIG_CPC];
+    __shared__ int32_t pst[2][MB_BIG_CPC + 1];           // pattern colptr of the chunk, kinds A (rows Λ/X) and B (rows U)
+    __shared__ uint8_t colof[2][MB_BIG_CAP];
+    // block column fastest: CTAs running together read the same chunk of the per-step source arrays for all their time offsets (L2 reuse)
+    const int nbc = 3 * (int)(B.hi - B.lo);
+    const int bc = (int)(blockIdx.x % (unsigned)nbc), cb = bc % 3;
     const int64_t tcol = B.lo + bc / 3;
     const int64_t ncls = (cb == 2) ? B.nU : B.nX;
-    const int64_t lc0 = (int64_t)blockIdx.x * MB_BIG_CPC;
+    const int64_t lc0 = (int64_t)(blockIdx.x / (unsigned)nbc) * MB_BIG_CPC;
     if (lc0 >= ncls) return;
+    const int nc = (int)((lc0 + MB_BIG_CPC < ncls) ? MB_BIG_CPC : ncls - lc0);
     const int32_t q0 = B.bcolptr[bc];
     const int nb = B.bcolptr[bc + 1] - q0;
+    const int pA = pat_of(0, cb), pB = pat_of(2, cb);
     if ((int)threadIdx.x < nb) {
         const int32_t br = B.browval[q0 + threadIdx.x];
         const int ca = br % 3; const int64_t trow = br / 3;
         const int p = pat_of(ca, cb);
-        BlkDesc d; d.a = nullptr; d.pc = B.pc[p]; d.nnzp = B.pnnz[p]; d.nder = 0; d.wd[0] = d.wd[1] = d.wd[2] = 0.;
+        BlkDesc d; d.a = nullptr; d.pc = B.pc[p]; d.nnzp = B.pnnz[p]; d.nder = 0; d.wd[0] = d.wd[1] = d.wd[2] = 0.; d.kind = (p == pA) ? 0 : 1;
+        d.nA = 0; d.nB = 0;
+        for (int j = 0; j < (int)threadIdx.x; ++j) { if (pat_of(B.browval[q0 + j] % 3, cb) == pA) ++d.nA; else ++d.nB; }
         const double* arr = nullptr; int64_t stride = 0, s = 0, t = 0;
         if (ca == 0 && cb != 0) { s = trow; t = tcol; if (cb == 1) { arr = B.LX; stride = B.sLX; d.nder = B.OX + 1; } else { arr = B.LU; stride = B.sLU; d.nder = 1; } }
         else if (cb == 0 && ca != 0) { s = tcol; t = trow; if (ca == 1) { arr = B.XL; stride = B.sLX; d.nder = B.OX + 1; } else { arr = B.UL; stride = B.sUL; d.nder = 1; } }
@@ -237,36 +250,67 @@ __global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t
         if (arr) d.a = arr + (s - B.elo) * stride;
         sd[threadIdx.x] = d;
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t cbase = (tcol - B.lo) * B.W + (cb == 0 ? 0 : (cb == 1 ? B.nX : 2 * B.nX));
-    const int64_t lc1 = (lc0 + MB_BIG_CPC < ncls) ? lc0 + MB_BIG_CPC : ncls;
-    for (int64_t lc = lc0 + warp; lc < lc1; lc += 8) {
-        int64_t off = colptr[cbase + lc];
+    for (int c = threadIdx.x; c <= nc; c += blockDim.x) {
+        pst[0][c] = B.pc[pA][lc0 + c]; pst[1][c] = B.pc[pB][lc0 + c];
+        if (c < nc) colbase[c] = colptr[cbase + lc0 + c];
+    }
+    __syncthreads();
+    const int nEA = pst[0][nc] - pst[0][0], nEB = pst[1][nc] - pst[1][0];
+    if (nEA <= MB_BIG_CAP && nEB <= MB_BIG_CAP) {
+        for (int c = threadIdx.x; c < nc; c += blockDim.x)
+#pragma unroll
+            for (int kd = 0; kd < 2; ++kd)
+                for (int32_t k = pst[kd][c]; k < pst[kd][c + 1]; ++k) colof[kd][k - pst[kd][0]] = (uint8_t)c;
+        __syncthreads();
         for (int j = 0; j < nb; ++j) {
-            const int32_t p0 = sd[j].pc[lc], p1 = sd[j].pc[lc + 1];
+            const int kd = sd[j].kind;
             const double* a = sd[j].a;
-            const int nder = sd[j].nder; const int64_t nnzp = sd[j].nnzp;
+            const int nder = sd[j].nder, nA = sd[j].nA, nBk = sd[j].nB; const int64_t nnzp = sd[j].nnzp;
             const double w0 = sd[j].wd[0], w1 = sd[j].wd[1], w2 = sd[j].wd[2];
-            for (int32_t k = p0 + lane; k < p1; k += 32) {
-                double v = 0.;                                     // same order of additions as the one-warp-per-column reference form
+            const int32_t k0 = pst[kd][0], k1 = pst[kd][nc];
+            for (int32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+                const int c = colof[kd][k - k0];
+                const int64_t dst = colbase[c] + (int64_t)nA * (pst[0][c + 1] - pst[0][c]) + (int64_t)nBk * (pst[1][c + 1] - pst[1][c]) + (k - pst[kd][c]);
+                double v = 0.;                                     // same order of additions as the reference (DirectXUA.jl:342-352)
                 if (a) {
                     if (w0 != 0.) v += a[k] * w0;
                     if (nder > 1 && w1 != 0.) v += a[nnzp + k] * w1;
                     if (nder > 2 && w2 != 0.) v += a[2 * nnzp + k] * w2;
                 }
-                nzval[off + (k - p0)] = v;
+                nzval[dst] = v;
             }
-            off += p1 - p0;
+        }
+    } else {                                                       // very dense pattern columns: one warp per column
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int c = warp; c < nc; c += 8) {
+            int64_t off = colbase[c];
+            for (int j = 0; j < nb; ++j) {
+                const int kd = sd[j].kind;
+                const int32_t p0 = pst[kd][c], p1 = pst[kd][c + 1];
+                const double* a = sd[j].a;
+                const int nder = sd[j].nder; const int64_t nnzp = sd[j].nnzp;
+                const double w0 = sd[j].wd[0], w1 = sd[j].wd[1], w2 = sd[j].wd[2];
+                for (int32_t k = p0 + lane; k < p1; k += 32) {
+                    double v = 0.;
+                    if (a) {
+                        if (w0 != 0.) v += a[k] * w0;
+                        if (nder > 1 && w1 != 0.) v += a[nnzp + k] * w1;
+                        if (nder > 2 && w2 != 0.) v += a[2 * nnzp + k] * w2;
+                    }
+                    nzval[off + (k - p0)] = v;
+                }
+                off += p1 - p0;
+            }
         }
     }
 }
 static void launch_big_values(const BigDev& B, int64_t ncol, const int64_t* colptr, double* nzval, int maxb, cudaStream_t st) {
     const int64_t nbc = 3 * (B.hi - B.lo), ncls = B.nX > B.nU ? B.nX : B.nU;
-    if (maxb <= MB_BIG_MAXB && nbc <= 65535) {
-        dim3 grid((unsigned)((ncls + MB_BIG_CPC - 1) / MB_BIG_CPC), (unsigned)nbc);
-        big_values_kernel<<<grid, 256, 0, st>>>(B, colptr, nzval);
-    } else
+    const int64_t nchunk = (ncls + MB_BIG_CPC - 1) / MB_BIG_CPC;
+    if (maxb <= MB_BIG_MAXB && nchunk * nbc < (int64_t)INT32_MAX)
+        big_values_kernel<<<(unsigned)(nchunk * nbc), 256, 0, st>>>(B, colptr, nzval);
+    else
         big_fill_kernel<false><<<nblk(ncol * 32, 256), 256, 0, st>>>(B, ncol, colptr, nullptr, nzval);
 }
 __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) {
