@@ -96,6 +96,8 @@ int32_t mb_direct_class_pattern(mb_handle* h, int32_t which, int64_t* nnz, int64
 int32_t mb_direct_get_asm(mb_handle* h, int32_t ieletyp, int32_t which, int64_t* out);
 /* state[iexp][step] → device (X0..X_OX of ndofX, U0 of ndofU); step must be stored on this handle */
 int32_t mb_direct_set_state(mb_handle* h, int64_t step, const double* X0, const double* X1, const double* X2, const double* U0);
+/* state[step].time = t0 + step·dt (default t0 = 0); only Bar3D's weight ramp reads the time (toolbox/BarElement.jl:144) */
+int32_t mb_direct_set_time0(mb_handle* h, double t0);
 /* assemblebig!{:matrices}: evaluates the steps [eval_lo,eval_hi) (eval_lo<0: all stored steps, i.e. owned + halo recomputed locally),
  * then, if build_big, forms the owned columns of Lvv (nzval) and rows of Lv; host outputs may be NULL (results stay on the device). */
 int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32_t build_big, double* Lvv_nzval, double* Lv, mb_errinfo* where);

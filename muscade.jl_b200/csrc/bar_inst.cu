@@ -18,4 +18,21 @@ void launch_soil(int ND, bool step, const SoilGroupDev& g, const StateDev& st, c
     else { if (step) L_(3, true); else L_(3, false); }
 #undef L_
 }
+int launch_bar_direct(int ND, const BarGroupDev& g, const DirectStateDev& st, double t, double* dR, double* R, unsigned long long* nanflag,
+                      unsigned long long nanbase, cudaStream_t s) {
+    const int64_t nt = g.nele * (ND + (g.udof ? 1 : 0));
+    const unsigned nb = (unsigned)((nt + 127) / 128);
+    if (ND == 1) bar_direct_kernel<1><<<nb, 128, 0, s>>>(g, st, t, dR, R, nanflag, nanbase);
+    else if (ND == 2) bar_direct_kernel<2><<<nb, 128, 0, s>>>(g, st, t, dR, R, nanflag, nanbase);
+    else bar_direct_kernel<3><<<nb, 128, 0, s>>>(g, st, t, dR, R, nanflag, nanbase);
+    return 1;
+}
+int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                       unsigned long long nanbase, cudaStream_t s) {
+    const unsigned nb = (unsigned)((g.nele + 255) / 256);
+    if (ND == 1) soil_direct_kernel<1><<<nb, 256, 0, s>>>(g, st, dR, R, nanflag, nanbase);
+    else if (ND == 2) soil_direct_kernel<2><<<nb, 256, 0, s>>>(g, st, dR, R, nanflag, nanbase);
+    else soil_direct_kernel<3><<<nb, 256, 0, s>>>(g, st, dR, R, nanflag, nanbase);
+    return 1;
+}
 }  // namespace mb

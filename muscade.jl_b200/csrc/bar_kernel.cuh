@@ -16,6 +16,7 @@ struct BarGroupDev {
     const int32_t* idxU;      // [nele][3] or nullptr
     double scaleX[6];
     int udof;
+    double scaleU[3];
 };
 
 // residual(o::Bar3D,…) for one element. X[ider][6] carry the seeds; the Gauss point motion x = c + tg·ζ is linear in the nodal motion,
@@ -131,6 +132,70 @@ __global__ void soil_kernel(SoilGroupDev g, StateDev st, NewmarkDev nm, double* 
         if (STEP) Rp[e * 3 + i] = contact ? s * Cc[i] * (nm.a2 * xp[i] + nm.a3 * xpp[i]) : 0.;
     }
     if (bad && contact) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+
+// ---------------------------------------------------------------------------------------------- DirectXUA first-order path (DirectXUA.jl:85-120)
+// dR[e][p][i] = ∂R_i/∂seed_p, p over X₀(nx) X′(nx) X″(nx) U₀(nu) with seeds scale.X / scale.U; R[e][i] unscaled.
+// Bar3D: lane d < ND carries the six partials of X_d, lane ND (Udof types) the three of U₀ — dense Dual<6>, one thread per (element, lane).
+template <int ND>
+__global__ void __launch_bounds__(128)
+bar_direct_kernel(BarGroupDev g, DirectStateDev st, double t, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag, unsigned long long nanbase) {
+    const int LPE = ND + (g.udof ? 1 : 0), NP = 6 * ND + (g.udof ? 3 : 0);
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = q / LPE;
+    const int lane = (int)(q - e * LPE);
+    if (e >= g.nele) return;
+    using S = Dual<6>;
+    double geo8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) geo8[k] = g.geo[e * 8 + k];
+    const BarMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    S X[3][6], U[3], Rv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int32_t d = g.idxX[e * 6 + i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { X[k][i] = Make<S>::c((k < ND) ? st.X[k][d] : 0.); if (k == lane) X[k][i].d[i] = g.scaleX[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { U[i] = Make<S>::c(g.udof ? st.U0[g.idxU[e * 3 + i]] : 0.); if (lane == ND) U[i].d[i] = g.scaleU[i]; }
+    bar_residual<ND, S>(geo8, m, X, g.udof != 0, U, t, Rv);
+    bool bad = false;
+    double* out = dR + e * (int64_t)(6 * NP) + (int64_t)(6 * lane) * 6;
+    const int ncol = (lane < ND) ? 6 : 3;
+    for (int j = 0; j < ncol; ++j)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const double v = Rv[i].d[j]; bad |= (v != v); out[6 * j + i] = v; }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const double v = Rv[i].v; bad |= (v != v); R[e * 6 + i] = v; }
+    }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+// SoilContact: R = K·(x − z₀e₃) + C·x′ below z₀, else 0 with no partials (SoilContact.jl:10-20) — closed form
+template <int ND>
+__global__ void soil_direct_kernel(SoilGroupDev g, DirectStateDev st, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag,
+                                   unsigned long long nanbase) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    const double z0 = g.par[e * 5], Kh = g.par[e * 5 + 1], Kv = g.par[e * 5 + 2], Ch = g.par[e * 5 + 3], Cv = g.par[e * 5 + 4];
+    double x[3], xp[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int32_t d = g.idxX[e * 3 + i]; x[i] = st.X[0][d]; xp[i] = (ND >= 2) ? st.X[1][d] : 0.; }
+    const bool contact = x[2] < z0;
+    const double K[3] = {Kh, Kh, Kv}, Cc[3] = {Ch, Ch, Cv};
+    bool bad = false;
+    double* out = dR + e * (int64_t)(3 * 3 * ND);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double r = contact ? (K[i] * (i == 2 ? x[2] - z0 : x[i]) + Cc[i] * xp[i]) : 0.;
+        R[e * 3 + i] = r; bad |= (r != r);
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) out[(3 * d + j) * 3 + i] = (contact && i == j && d < 2) ? (d == 0 ? K[i] : Cc[i]) * g.scaleX[j] : 0.;
+    }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
 }  // namespace mb

@@ -346,6 +346,7 @@ static int32_t launch_group_range(mb_handle* h, size_t ig, int64_t e0, int64_t e
     else if (g.kind == G_BAR) {
         BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
         for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
+        for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
         launch_bar(OX + 1, step, gd, sd, nm, tnow, h->Ke + g.pair_base, h->Re + g.vec_base, h->Rp + g.vec_base, h->nanflag, nanbase, h->stream);
         h->launches++;
     } else if (g.kind == G_SOIL) {
@@ -765,6 +766,7 @@ int32_t mb_add_bar3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t u
     if (rc) return rc;
     if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU); if (rc) return rc; }
     for (int i = 0; i < 6; ++i) g.scaleX[i] = scaleX[i];
+    if (udof) for (int i = 0; i < 3; ++i) g.scaleU[i] = scaleU[i];
     h->groups.push_back(g);
     if (ieletyp_out) *ieletyp_out = (int32_t)h->groups.size();
     return MB_OK;

@@ -14,6 +14,10 @@
 namespace mb {
 template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
                                          unsigned long long nanbase, double* Wc, cudaStream_t s);
+int launch_bar_direct(int ND, const BarGroupDev& g, const DirectStateDev& st, double t, double* dR, double* R, unsigned long long* nanflag,
+                      unsigned long long nanbase, cudaStream_t s);
+int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                       unsigned long long nanbase, cudaStream_t s);
 }
 
 namespace {
@@ -28,7 +32,7 @@ struct PairPat {                  // one class-pair pattern of prepare(AssemblyD
 };
 
 constexpr int MAXG = 8;
-struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; };
+struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; };
 
 // ---------------------------------------------------------------------------------------------------------------- pattern build
 __global__ void pair_keys_kernel(int64_t nele, int ni, const int32_t* __restrict__ idxR, int nj, const int32_t* __restrict__ idxC, uint64_t nrows,
@@ -82,9 +86,10 @@ __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
         const uint32_t id = src[s];
         const int g = find_group(G.pbase[P_XX], G.n, id);
         const uint32_t loc = id - G.pbase[P_XX][g];
-        const int64_t e = loc / 144; const int r = (int)(loc - e * 144); const int jj = r / 12, i = r - 12 * jj;
-        const double* d = dR + G.drbase[g] + e * (int64_t)(12 * G.np[g]);
-        for (int der = 0; der < nd; ++der) { a[der] += d[(12 * der + jj) * 12 + i]; b[der] += d[(12 * der + i) * 12 + jj]; }
+        const int nx = G.nx[g], n2 = nx * nx;
+        const int64_t e = loc / n2; const int r = (int)(loc - e * n2); const int jj = r / nx, i = r - nx * jj;
+        const double* d = dR + G.drbase[g] + e * (int64_t)(nx * G.np[g]);
+        for (int der = 0; der < nd; ++der) { a[der] += d[(nx * der + jj) * nx + i]; b[der] += d[(nx * der + i) * nx + jj]; }
     }
     for (int der = 0; der < nd; ++der) { LX[der * nnz + k] = a[der]; XL[der * nnz + k] = b[der]; }
 }
@@ -99,11 +104,12 @@ __global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
         const uint32_t id = src[s];
         const int g = find_group(G.pbase[pat], G.n, id);
         const uint32_t loc = id - G.pbase[pat][g];
-        const int64_t e = loc / 36; const int r = (int)(loc - e * 36);
+        const int nx = G.nx[g], n2 = 3 * nx;
+        const int64_t e = loc / n2; const int r = (int)(loc - e * n2);
         int ix, ju;
-        if (!transposed) { ju = r / 12; ix = r - 12 * ju; }      // rows X (12), cols U (3): r = ix + 12·ju
-        else { ix = r / 3; ju = r - 3 * ix; }                     // rows U (3), cols X (12): r = ju + 3·ix
-        a += dR[G.drbase[g] + e * (int64_t)(12 * G.np[g]) + (12 * nd + ju) * 12 + ix];
+        if (!transposed) { ju = r / nx; ix = r - nx * ju; }      // rows X (nx), cols U (3): r = ix + nx·ju
+        else { ix = r / 3; ju = r - 3 * ix; }                     // rows U (3), cols X (nx): r = ju + 3·ix
+        a += dR[G.drbase[g] + e * (int64_t)(nx * G.np[g]) + (nx * nd + ju) * nx + ix];
     }
     out[k] = a;
 }
@@ -326,7 +332,7 @@ __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) 
 struct DirectData {
     int OX = 0, OU = 0;
     int64_t nX = 0, nU = 0, nstep = 0, lo = 0, hi = 0, elo = 0, ehi = 0;
-    double dt = 1.;
+    double dt = 1., t0 = 0.;                            // state[step].time = t0 + step·dt (read by Bar3D's weight ramp, BarElement.jl:144)
     PairPat pat[4];
     uint32_t *vstart = nullptr, *vsrc = nullptr;
     DirGroups G;
@@ -408,7 +414,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     ARG(OX >= 0 && OX <= 2 && OU >= 0 && OU <= 2 && ndofX >= 1 && ndofU >= 0 && nstep >= 1 && step_lo >= 0 && step_hi > step_lo && step_hi <= nstep, "bad argument");
     ARG(bcolptr && browval, "block pattern missing");
     ARG((int)h->groups.size() <= MAXG, "too many element types");
-    for (const Group& g : h->groups) ARG(g.kind == G_BEAM, "DirectXUA on the device supports EulerBeam3D element types in this version");
+    for (const Group& g : h->groups) ARG(g.kind == G_BEAM || g.kind == G_BAR || g.kind == G_SOIL, "DirectXUA on the device: EulerBeam3D, Bar3D, SoilContact element types");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     DirectData* D = new DirectData();
@@ -427,9 +433,9 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     for (size_t ig = 0; ig < h->groups.size(); ++ig) {
         const Group& g = h->groups[ig];
         for (int p = 0; p < 4; ++p) D->G.pbase[p][ig] = (uint32_t)D->pat[p].gbase[ig];
-        D->G.np[ig] = 12 * (OX + 1) + (g.udof ? 3 : 0); D->G.udof[ig] = g.udof;
+        D->G.nx[ig] = g.nx; D->G.np[ig] = g.nx * (OX + 1) + (g.udof ? 3 : 0); D->G.udof[ig] = g.udof;
         D->G.drbase[ig] = ndr; D->G.rbase[ig] = nvec;
-        ndr += g.nele * 12 * D->G.np[ig]; nvec += g.nele * 12;
+        ndr += g.nele * g.nx * D->G.np[ig]; nvec += g.nele * g.nx;
     }
     for (int p = 0; p < 4; ++p) D->G.pbase[p][h->groups.size()] = (uint32_t)D->pat[p].gbase[h->groups.size()];
     CK(dalloc(h, &D->vstart, ndofX + 1)); CK(dalloc(h, &D->vsrc, nvec));
@@ -440,7 +446,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
         for (size_t ig = 0; ig < h->groups.size(); ++ig) {
             const Group& g = h->groups[ig];
             if (g.nele == 0) continue;
-            vec_keys_kernel<<<nblk(g.nele * 12, 256), 256, 0, st>>>(g.nele * 12, g.idxX, keys, vals, (uint32_t)D->G.rbase[ig]);
+            vec_keys_kernel<<<nblk(g.nele * g.nx, 256), 256, 0, st>>>(g.nele * g.nx, g.idxX, keys, vals, (uint32_t)D->G.rbase[ig]);
             h->launches++;
         }
         int end_bit = 1; while (end_bit < 32 && ((uint64_t)ndofX >> end_bit)) ++end_bit;
@@ -537,12 +543,25 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         for (size_t ig = 0; ig < h->groups.size(); ++ig) {
             const Group& g = h->groups[ig];
             if (g.nele == 0) continue;
+            const unsigned long long nanbase = (((unsigned long long)s) << 44) | (((unsigned long long)ig) << 40);
+            double* dR = D->dR + D->G.drbase[ig]; double* R = D->R + D->G.rbase[ig];
+            if (g.kind == G_BAR) {
+                BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+                for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
+                for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+                h->launches += launch_bar_direct(nd, gd, sd, D->t0 + (double)s * D->dt, dR, R, h->nanflag, nanbase, st);
+                continue;
+            }
+            if (g.kind == G_SOIL) {
+                SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
+                for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
+                h->launches += launch_soil_direct(nd, gd, sd, dR, R, h->nanflag, nanbase, st);
+                continue;
+            }
             BeamGroupDev gd;
             gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
             for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
             for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
-            const unsigned long long nanbase = (((unsigned long long)s) << 44) | (((unsigned long long)ig) << 40);
-            double* dR = D->dR + D->G.drbase[ig]; double* R = D->R + D->G.rbase[ig];
             double* Wc = nullptr;
             if (nd >= 2) {                         // cotangent workspace of the two-phase evaluation, shared with SweepX and sized lazily
                 const int64_t need = ((g.nele * 6 * nd + 31) / 32) * 32 * MB_NCOT;
@@ -562,6 +581,12 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         gather_l1_kernel<<<nblk(D->nX, 256), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX);
         h->launches++;
     }
+    return MB_OK;
+}
+
+int32_t mb_direct_set_time0(mb_handle* h, double t0) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    h->direct->t0 = t0;
     return MB_OK;
 }
 

@@ -78,10 +78,15 @@ class DirectEngine(Engine):
 
     def direct_asm(self, ityp, which):
         nele = self.groups[ityp - 1][1]
-        ni = 3 if which in (2, 3) else 12; nj = 3 if which in (1, 3) else 12
+        nx, nu = self.groups[ityp - 1][2], 3
+        ni = nu if which in (2, 3) else nx; nj = nu if which in (1, 3) else nx
         out = np.zeros((nele, ni * nj), np.int64)
         check(self.h, self.L.mb_direct_get_asm(self.h, ityp, which, ptr(out)))
         return out
+
+    def set_time0(self, t0):
+        """state[step].time = t0 + step·dt"""
+        check(self.h, self.L.mb_direct_set_time0(self.h, float(t0)))
 
     def set_state(self, step, X, U0=None):
         X = [_f64(x) for x in X]
@@ -121,14 +126,20 @@ class DirectEngine(Engine):
         return float(ms[0]), float(ms[1])
 
 
-def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0):
+def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
     """prepare(AssemblyDirect{OX,OU,0},model,dis) + preparebig(0,[nstep],out) for the owned steps [lo,hi)"""
     hi = nstep if hi is None else hi
     eng = DirectEngine(device)
     for et, ed in zip(model.ele, dis.dis):
-        if et.ElType.kind != "eulerbeam3d":
-            muscadeerror("DirectXUA on the device supports EulerBeam3D element types in this version: %s" % (et.key,))
         udof = ed.U.shape[1] > 0
-        eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+        if et.ElType.kind == "eulerbeam3d":
+            eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+        elif et.ElType.kind == "bar3d":
+            eng.add_bar3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+        elif et.ElType.kind == "soilcontact":
+            eng.add_soilcontact(et.eleobj, ed.X, ed.scaleX)
+        else:
+            muscadeerror("DirectXUA on the device supports EulerBeam3D, Bar3D and SoilContact element types in this version: %s" % (et.key,))
     eng.direct_prepare(OX, OU, model.getndof("X"), model.getndof("U"), nstep, lo, hi, dt)
+    eng.set_time0(t0)
     return eng

@@ -283,7 +283,7 @@ def sweepx_addin_generic(residual_fn, nx, idx, asm1, asm2, OX, mission, X, scale
 
 
 # ------------------------------------------------------------------------------------------------ DirectXUA
-def direct_assemble_step_beams(elems, idxX, idxU, OX, OU, X, U, scaleX, scaleU, P, ityp):
+def direct_assemble_step_beams(elems, idxX, idxU, OX, OU, X, U, scaleX, scaleU, P, ityp, out=None):
     """assemble!{:matrices}(out::AssemblyDirect{OX,OU,0},…) for one state (one time step), EulerBeam3D type `ityp` (0-based) of the
     model whose prepare_direct() result is P (src/DirectXUA.jl:85-120, src/Assemble.jl:470-487).
     Returns dict with L1[1] (Λ) and L2[(1,2)],L2[(2,1)] (lists over X derivative), L2[(1,3)],L2[(3,1)] (lists over U derivative)."""
@@ -293,8 +293,9 @@ def direct_assemble_step_beams(elems, idxX, idxU, OX, OU, X, U, scaleX, scaleU, 
     asm = P["asm"]
     T = lambda a: np.ascontiguousarray(a.T, dtype=np.int64)
     nnz = {ab: len(P["pat"][ab][3]) for ab in P["pat"]}
-    out = dict(L1={1: np.zeros(P["ndof"][0])}, L2={(1, 2): np.zeros((nd, nnz[(1, 2)])), (2, 1): np.zeros((nd, nnz[(2, 1)])),
-                                                  (1, 3): np.zeros((ndu, nnz[(1, 3)])), (3, 1): np.zeros((ndu, nnz[(3, 1)]))})
+    if out is None:
+        out = dict(L1={1: np.zeros(P["ndof"][0])}, L2={(1, 2): np.zeros((nd, nnz[(1, 2)])), (2, 1): np.zeros((nd, nnz[(2, 1)])),
+                                                      (1, 3): np.zeros((ndu, nnz[(1, 3)])), (3, 1): np.zeros((ndu, nnz[(3, 1)]))})
     X = [np.ascontiguousarray(x, float) for x in X]; U = [np.ascontiguousarray(u, float) for u in U]
     aLU = T(asm[arrnum(1, 3)][ityp]) if udof else None; aUL = T(asm[arrnum(3, 1)][ityp]) if udof else None
     rc = lib().orc_direct_addin_beams(
@@ -307,4 +308,53 @@ def direct_assemble_step_beams(elems, idxX, idxU, OX, OU, X, U, scaleX, scaleU, 
         _ptr(out["L2"][(1, 3)]), nnz[(1, 3)], _ptr(out["L2"][(3, 1)]), nnz[(3, 1)])
     if rc:
         raise FloatingPointError("NaN or bad arguments (%d)" % rc)
+    return out
+
+
+def direct_out_zeros(P, OX, OU):
+    """empty out.L1 / out.L2 of prepare(AssemblyDirect{OX,OU,0}) for the blocks the first-order path fills (DirectXUA.jl:85-120)"""
+    nd, ndu = OX + 1, OU + 1
+    nnz = {ab: len(P["pat"][ab][3]) for ab in P["pat"]}
+    return dict(L1={1: np.zeros(P["ndof"][0])}, L2={(1, 2): np.zeros((nd, nnz[(1, 2)])), (2, 1): np.zeros((nd, nnz[(2, 1)])),
+                                                   (1, 3): np.zeros((ndu, nnz[(1, 3)])), (3, 1): np.zeros((ndu, nnz[(3, 1)]))})
+
+
+def direct_addin_generic(residual_fn, nx, nu, idxX, idxU, OX, OU, X, U, scaleX, scaleU, P, ityp, out):
+    """addin!{:matrices}(out::AssemblyDirect{OX,OU,0},…) first-order path (src/DirectXUA.jl:85-120) for any element type given
+    `residual_fn(iele, Xval (nd,nx), Xseed (nd,nx,np), Uval (nu,), Useed (nu,np))` → (R, dR (nx,np)); seeds = revariate{1}((;X,U),scale)
+    (Taylor.jl:158-166).  Adds into `out` (direct_out_zeros); python loop over elements — small cases only."""
+    from .pattern import arrnum
+    nd = OX + 1
+    np_ = nx * nd + nu
+    asm = P["asm"]
+    aL = asm[arrnum(1)][ityp]; aLX = asm[arrnum(1, 2)][ityp]; aXL = asm[arrnum(2, 1)][ityp]          # (n, nele), 1-based, 0 = absent
+    aLU = asm[arrnum(1, 3)][ityp] if nu else None; aUL = asm[arrnum(3, 1)][ityp] if nu else None
+    for e in range(idxX.shape[0]):
+        xv = np.stack([X[d][idxX[e] - 1] for d in range(nd)])
+        seed = np.zeros((nd, nx, np_))
+        for d in range(nd):
+            for i in range(nx):
+                seed[d, i, nx * d + i] = scaleX[i]
+        uv = U[0][idxU[e] - 1] if nu else np.zeros(0)
+        useed = np.zeros((nu, np_))
+        for i in range(nu):
+            useed[i, nx * nd + i] = scaleU[i]
+        R, dR = residual_fn(e, xv, seed, uv, useed)
+        for i in range(nx):
+            if aL[i, e]: out["L1"][1][aL[i, e] - 1] += R[i]
+        for d in range(nd):
+            for i in range(nx):
+                for j in range(nx):
+                    v = dR[i, nx * d + j]
+                    k = aLX[i + nx * j, e]
+                    if k: out["L2"][(1, 2)][d, k - 1] += v
+                    k = aXL[j + nx * i, e]
+                    if k: out["L2"][(2, 1)][d, k - 1] += v
+        for i in range(nx):
+            for j in range(nu):
+                v = dR[i, nx * nd + j]
+                k = aLU[i + nx * j, e]
+                if k: out["L2"][(1, 3)][0, k - 1] += v
+                k = aUL[j + nu * i, e]
+                if k: out["L2"][(3, 1)][0, k - 1] += v
     return out

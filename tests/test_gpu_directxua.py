@@ -102,3 +102,61 @@ def test_directxua_time_shard(mb, lo, hi):
     assert rel(Lvv, nz[p0:p1], np.abs(nz).max()) <= TOL
     assert rel(Lvec, Lv[c0:c1], np.abs(nz).max()) <= TOL
     eng.close()
+
+
+@pytest.mark.parametrize("OX", [2, 0])
+def test_directxua_beam_bar_soil(mb, OX):
+    """BASELINE.json configs[4] in small: EulerBeam3D{Udof} + Bar3D{Udof} + SoilContact on shared nodes through the DirectXUA first-order path
+    (DirectXUA.jl:85-120); every element type on the device; Bar3D reads state.time (weight ramp, BarElement.jl:144)."""
+    OU, nstep, dt, N, t0 = 0, 7, 0.1, 10, -7.4
+    rng = np.random.default_rng(5)
+    model = mb.Model()
+    coord = np.cumsum(np.concatenate([[[0., 0., -0.3]], rng.uniform(0.5, 1.0, (N, 3)) * [1, .3, .02]]), axis=0)
+    nod = mb.addnode(model, coord)
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    mesh = np.stack([nod[:-1], nod[1:], unod], axis=1)
+    bmat = mb.BeamCrossSection(EA=1e3, EI2=30., EI3=20., GJ=40., mu=2., iota1=.3, w=5., Ca2=3., Ca3=3., Cq2=2., Cq3=2., Cl1=.5)
+    mb.addelement(model, mb.EulerBeam3D, mesh[: N // 2], mat=bmat, orient2=(0., 0.2, 1.), Udof=True)
+    rmat = mb.AxisymmetricBarCrossSection(EA=500., mu=1.5, w=3., Cat=.2, Clt=.3, Cqt=.4, Can=2., Cln=.6, Cqn=1.2)
+    mb.addelement(model, mb.Bar3D, mesh[N // 2:], mat=rmat, Udof=True)
+    mb.addelement(model, mb.SoilContact, nod[: N // 2, None], z0=0.0, Kh=30., Kv=200., Ch=3., Cv=7.)
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)))
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    st = states(mb, nX, nU, nstep)
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+    bars, soil = model.ele[1].eleobj, model.ele[2].eleobj
+    outs = []
+    for s, (X, U) in enumerate(st):
+        o = OE.direct_out_zeros(P, OX, OU)
+        OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, OX, OU, X[: OX + 1], [U], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0, out=o)
+        OE.direct_addin_generic(lambda e, xv, sd, uv, usd: OE.bar_residual(bars[e], xv, sd, uv, usd, t=t0 + s * dt)[:2], 6, 3, dis.dis[1].X, dis.dis[1].U,
+                                OX, OU, X[: OX + 1], [U], dis.dis[1].scaleX, dis.dis[1].scaleU, P, 1, o)
+        OE.direct_addin_generic(lambda e, xv, sd, uv, usd: OE.soil_residual(soil[e], xv, sd)[:2], 3, 0, dis.dis[2].X, None,
+                                OX, OU, X[: OX + 1], [U], dis.dis[2].scaleX, None, P, 2, o)
+        outs.append(o)
+    nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, t0=t0)
+    cp, rv = eng.big_pattern()
+    assert np.array_equal(cp, big["colptr"]) and np.array_equal(rv, big["rowval"])
+    for ityp in (1, 2, 3):
+        assert np.array_equal(eng.direct_asm(ityp, 0).T, P["asm"][OP.arrnum(1, 2)][ityp - 1])
+    for s, (X, U) in enumerate(st):
+        eng.set_state(s, X[: OX + 1], U)
+    Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
+    eng.direct_assemble(Lvv=Lvv, Lv=Lvec)
+    for s in (0, 4):
+        o = outs[s]
+        scale = np.abs(o["L2"][(1, 2)]).max()
+        assert rel(eng.step_block(s, 0), o["L1"][1], scale) <= TOL
+        for der in range(OX + 1):
+            assert rel(eng.step_block(s, 1, der), o["L2"][(1, 2)][der], scale) <= TOL
+            assert rel(eng.step_block(s, 2, der), o["L2"][(2, 1)][der], scale) <= TOL
+        assert rel(eng.step_block(s, 3), o["L2"][(1, 3)][0], scale) <= TOL and rel(eng.step_block(s, 4), o["L2"][(3, 1)][0], scale) <= TOL
+    assert rel(Lvv, nz) <= TOL, rel(Lvv, nz)
+    assert rel(Lvec, Lv, np.abs(nz).max()) <= TOL
+    z = np.array([st[s][0][0][dis.dis[2].X[:, 2] - 1] for s in range(nstep)])
+    assert (z < 0).any() and (z >= 0).any()          # both SoilContact branches
+    eng.close()
