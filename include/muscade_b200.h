@@ -104,6 +104,20 @@ int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32
 int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr /* ncol+1 */, int64_t* rowval /* nnz, global rows */);
 /* out.L1/out.L2 of one stored step: which = 0 L1[Λ][1], 1 L2[Λ,X][1,der+1], 2 L2[X,Λ][der+1,1], 3 L2[Λ,U][1,1], 4 L2[U,Λ][1,1] */
 int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int32_t der, double* out);
+/* Newton update of the all-steps problem on the device.
+ *   mb_direct_sparser     : sparser!(cLvv,Lvv,rtol) (src/SparseTools.jl:172-199, called at src/DirectXUA.jl:486): compacts the owned columns of
+ *                           Lvv to the entries with |v| ≥ rtol·max|Lvv| (the structural zeros of the X-X, U-U blocks go), order preserved.
+ *   mb_direct_get_sparse  : the compacted CSC (1-based colptr / global rowval) — 40 % fewer bytes over PCIe than the full nzval.
+ *   mb_direct_set_lambda / get_state / set_dof_scale : state[step].Λ, reading states back, dofgr scales (Λ, X, U; default ones).
+ *   mb_direct_decrement   : decrementbig!(state,Δ²,Lvdis,dofgr,Δv,nder,Δt,nstep) (src/DirectXUA.jl:357-383) for the steps stored on this handle.
+ *                           dv = Δv rows of steps [s0,s1) in Lv's layout (per step Λ(nX) X(nX) U(nU)), host or device; the range must reach
+ *                           two steps beyond the stored ones (stencils of finitediff). delta2[3] = maxₜ ΣΔβ² over the OWNED steps (Λ,X,U). */
+int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
+int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
+int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda);
+int32_t mb_direct_get_state(mb_handle* h, int64_t step, double* X0, double* X1, double* X2, double* U0, double* Lambda);
+int32_t mb_direct_set_dof_scale(mb_handle* h, const double* scaleL, const double* scaleX, const double* scaleU);
+int32_t mb_direct_decrement(mb_handle* h, int64_t s0, int64_t s1, const double* dv, double* delta2);
 /* device pointers of the per-step blocks a neighbouring time-shard needs (halo exchange over NCCL): L2[Λ,X][1,:], L2[Λ,U][1,1], L1[Λ] */
 int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1);
 /* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build */

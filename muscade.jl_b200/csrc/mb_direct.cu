@@ -327,6 +327,61 @@ __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) 
     Lv[c] = (cls == 0) ? B.L1L[(step - B.elo) * B.nX + lc] : 0.;     // addin!(Lvasm,Lv,L1[Λ][1],Λblk)  (DirectXUA.jl:332-341)
 }
 
+// ---------------------------------------------------------------------------------------------------------------- sparser! / decrementbig!
+// sparser!(T,S,rtol) (src/SparseTools.jl:172-199): keep |nzval| ≥ rtol·max|S|, order preserved, colptr shifted by the drops before it
+struct AbsF { __host__ __device__ double operator()(double x) const { return fabs(x); } };
+struct KeepF { const double* v; double atol; __host__ __device__ int64_t operator()(int64_t i) const { return fabs(v[i]) >= atol ? 1 : 0; } };
+__global__ void sparser_scatter_kernel(int64_t nnz, const double* __restrict__ v, const int64_t* __restrict__ rv, const int64_t* __restrict__ pos, double atol,
+                                       double* __restrict__ v2, int64_t* __restrict__ rv2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    if (fabs(v[i]) >= atol) { const int64_t q = pos[i]; v2[q] = v[i]; rv2[q] = rv[i]; }
+}
+__global__ void sparser_colptr_kernel(int64_t ncol, int64_t nnz, const int64_t* __restrict__ colptr, const int64_t* __restrict__ pos, int64_t nkeep,
+                                      int64_t* __restrict__ colptr2) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncol) return;
+    const int64_t p = colptr[c];
+    colptr2[c] = (p < nnz) ? pos[p] : nkeep;
+}
+// decrementbig! (src/DirectXUA.jl:357-383): state[step].β[βder] −= ((Δβ·w)·Δt^(1−βder))·scale for every stencil point (Δs,w) of
+// finitediff(βder−1,nstep,step), Δβ = Δv block of step+Δs, class β — same sequence of roundings (no FMA contraction).
+struct DecDev {
+    int64_t nX, nU, W, nstep, elo, ehi, s0, s1; int OX; double dtp[3];
+    const double* dv; double *Lam, *X, *U; const double *scL, *scX, *scU;
+};
+__global__ void decrementbig_kernel(DecDev D) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (D.ehi - D.elo) * D.W) return;
+    const int64_t k = q / D.W, r = q - k * D.W, step = D.elo + k;
+    int cls; int64_t i;
+    if (r < D.nX) { cls = 0; i = r; } else if (r < 2 * D.nX) { cls = 1; i = r - D.nX; } else { cls = 2; i = r - 2 * D.nX; }
+    const int nder = (cls == 1) ? D.OX + 1 : 1;
+    const double sc = (cls == 0) ? (D.scL ? D.scL[i] : 1.) : (cls == 1 ? (D.scX ? D.scX[i] : 1.) : (D.scU ? D.scU[i] : 1.));
+    for (int der = 0; der < nder; ++der) {
+        double* x = (cls == 0) ? D.Lam + k * D.nX + i : (cls == 1 ? D.X + (k * 3 + der) * D.nX + i : D.U + k * D.nU + i);
+        double v = *x;
+        for (int64_t ds = -2; ds <= 2; ++ds) {                       // stencil points come in ascending Δs (FiniteDifferences.jl:8-31)
+            double w;
+            if (!fd_weight(der, D.nstep, step, ds, w)) continue;
+            const double d = D.dv[(step + ds - D.s0) * D.W + r];
+            v = __dsub_rn(v, __dmul_rn(__dmul_rn(__dmul_rn(d, w), D.dtp[der]), sc));
+        }
+        *x = v;
+    }
+}
+// Σ Δβ² per (step, class) of the owned steps; the maximum over steps is Δ²[β] (DirectXUA.jl:369-371)
+__global__ void __launch_bounds__(256) block_sumsq_kernel(int64_t nX, int64_t nU, int64_t W, const double* __restrict__ dv, double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int64_t b = blockIdx.x; const int cls = (int)(b % 3); const int64_t k = b / 3;
+    const int64_t n = (cls == 2) ? nU : nX, off = k * W + (cls == 0 ? 0 : (cls == 1 ? nX : 2 * nX));
+    double a = 0.;
+    for (int64_t i = threadIdx.x; i < n; i += 256) { const double d = dv[off + i]; a += d * d; }
+    sh[threadIdx.x] = a; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) out[b] = sh[0];
+}
+
 }  // namespace
 
 struct DirectData {
@@ -337,7 +392,9 @@ struct DirectData {
     uint32_t *vstart = nullptr, *vsrc = nullptr;
     DirGroups G;
     double *dR = nullptr, *R = nullptr;                 // element outputs of one step
-    double *X = nullptr, *U = nullptr;                  // stored states [step][3][nX], [step][nU]
+    double *X = nullptr, *U = nullptr, *Lam = nullptr;  // stored states [step][3][nX], [step][nU], [step][nX] (Λ enters decrementbig! only)
+    double *scL = nullptr, *scX = nullptr, *scU = nullptr, *dvbuf = nullptr; int64_t dvlen = 0;
+    int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;   // sparser! result
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
     int32_t *bcolptr = nullptr, *browval = nullptr;
     int64_t ncol = 0, nnzbig = 0; int maxb = 0;         // maxb: most blocks in one block column
@@ -463,6 +520,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     const int64_t ns = D->ehi - D->elo;
     CK(dalloc(h, &D->dR, ndr)); CK(dalloc(h, &D->R, nvec));
     CK(dalloc(h, &D->X, ns * 3 * ndofX)); CK(dalloc(h, &D->U, ns * (ndofU > 0 ? ndofU : 1)));
+    CK(dalloc(h, &D->Lam, ns * ndofX)); CK(cudaMemsetAsync(D->Lam, 0, (size_t)(ns * ndofX) * sizeof(double), st));
     CK(cudaMemsetAsync(D->X, 0, (size_t)(ns * 3 * ndofX) * sizeof(double), st));
     CK(cudaMemsetAsync(D->U, 0, (size_t)(ns * (ndofU > 0 ? ndofU : 1)) * sizeof(double), st));
     CK(dalloc(h, &D->LX, ns * (OX + 1) * D->pat[P_XX].nnz)); CK(dalloc(h, &D->XL, ns * (OX + 1) * D->pat[P_XX].nnz));
@@ -622,6 +680,129 @@ int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
     CK(cudaSetDevice(h->device));
     if (colptr) { CK(cudaMemcpy(colptr, D->colptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
     if (rowval) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1; }
+    return MB_OK;
+}
+// ---- Newton update of the all-steps problem on the device
+int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi && Lambda, "step not stored on this handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(D->Lam + (step - D->elo) * D->nX, Lambda, (size_t)D->nX * 8, cudaMemcpyDefault, h->stream));
+    return MB_OK;
+}
+int32_t mb_direct_get_state(mb_handle* h, int64_t step, double* X0, double* X1, double* X2, double* U0, double* Lambda) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi, "step not stored on this handle");
+    CK(cudaSetDevice(h->device));
+    const int64_t k = step - D->elo;
+    double* dst[3] = {X0, X1, X2};
+    for (int d = 0; d <= D->OX; ++d) if (dst[d]) CK(cudaMemcpyAsync(dst[d], D->X + (k * 3 + d) * D->nX, (size_t)D->nX * 8, cudaMemcpyDefault, h->stream));
+    if (U0 && D->nU) CK(cudaMemcpyAsync(U0, D->U + k * D->nU, (size_t)D->nU * 8, cudaMemcpyDefault, h->stream));
+    if (Lambda) CK(cudaMemcpyAsync(Lambda, D->Lam + k * D->nX, (size_t)D->nX * 8, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
+int32_t mb_direct_set_dof_scale(mb_handle* h, const double* scaleL, const double* scaleX, const double* scaleU) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    CK(cudaSetDevice(h->device));
+    const double* src[3] = {scaleL, scaleX, scaleU}; double** dst[3] = {&D->scL, &D->scX, &D->scU}; const int64_t n[3] = {D->nX, D->nX, D->nU};
+    for (int c = 0; c < 3; ++c) {
+        if (!src[c] || n[c] == 0) continue;
+        if (!*dst[c]) CK(dalloc(h, dst[c], n[c]));
+        CK(cudaMemcpyAsync(*dst[c], src[c], (size_t)n[c] * 8, cudaMemcpyDefault, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
+int32_t mb_direct_decrement(mb_handle* h, int64_t s0, int64_t s1, const double* dv, double* delta2) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(dv && s0 >= 0 && s1 <= D->nstep && s0 < s1, "bad step range");
+    ARG(D->OU == 0, "device decrementbig! stores ∂0(U) only (OU = 0)");
+    const int64_t need0 = D->elo - 2 < 0 ? 0 : D->elo - 2, need1 = D->ehi + 2 > D->nstep ? D->nstep : D->ehi + 2;
+    ARG(s0 <= need0 && s1 >= need1, "Δv must cover the stored steps and two steps on either side (finite-difference stencils)");
+    CK(cudaSetDevice(h->device));
+    const int64_t W = 2 * D->nX + D->nU, n = (s1 - s0) * W;
+    cudaPointerAttributes at;
+    const bool on_dev = cudaPointerGetAttributes(&at, dv) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const double* d = dv;
+    if (!on_dev) {
+        if (D->dvlen < n) { if (D->dvbuf) dfree(h, D->dvbuf); D->dvbuf = nullptr; D->dvlen = 0; CK(dalloc(h, &D->dvbuf, n)); D->dvlen = n; }
+        CK(cudaMemcpyAsync(D->dvbuf, dv, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        d = D->dvbuf;
+    }
+    DecDev Q;
+    Q.nX = D->nX; Q.nU = D->nU; Q.W = W; Q.nstep = D->nstep; Q.elo = D->elo; Q.ehi = D->ehi; Q.s0 = s0; Q.s1 = s1; Q.OX = D->OX;
+    Q.dtp[0] = 1.; Q.dtp[1] = 1. / D->dt; Q.dtp[2] = (1. / D->dt) * (1. / D->dt);          // Δt^(1−βder), Julia's power_by_squaring of inv(Δt)
+    Q.dv = d; Q.Lam = D->Lam; Q.X = D->X; Q.U = D->U; Q.scL = D->scL; Q.scX = D->scX; Q.scU = D->scU;
+    decrementbig_kernel<<<nblk((D->ehi - D->elo) * W, 256), 256, 0, h->stream>>>(Q);
+    h->launches++;
+    if (delta2) {
+        const int64_t nown = D->hi - D->lo;
+        double* sums = nullptr; CK(dalloc(h, &sums, 3 * nown));
+        block_sumsq_kernel<<<(unsigned)(3 * nown), 256, 0, h->stream>>>(D->nX, D->nU, W, d + (D->lo - s0) * W, sums);
+        h->launches++;
+        std::vector<double> hs((size_t)(3 * nown));
+        CK(cudaMemcpyAsync(hs.data(), sums, hs.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        dfree(h, sums);
+        delta2[0] = delta2[1] = delta2[2] = 0.;
+        for (int64_t k = 0; k < nown; ++k) for (int c = 0; c < 3; ++c) delta2[c] = std::max(delta2[c], hs[(size_t)(3 * k + c)]);
+    } else CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(D->nzval && D->nnzbig > 0, "assemble first");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t nnz = D->nnzbig;
+    if (!D->ccolptr) { CK(dalloc(h, &D->ccolptr, D->ncol + 1)); CK(dalloc(h, &D->crowval, nnz)); CK(dalloc(h, &D->cnzval, nnz)); }
+    double* dmax = nullptr; int64_t* pos = nullptr;
+    CK(dalloc(h, &dmax, 1)); CK(dalloc(h, &pos, nnz));
+    void* tmp = nullptr; size_t t1 = 0, t2 = 0;
+    cub::TransformInputIterator<double, AbsF, const double*> absit(D->nzval, AbsF{});
+    CK(cub::DeviceReduce::Max(nullptr, t1, absit, dmax, nnz, st));
+    cub::CountingInputIterator<int64_t> ids(0);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, cub::TransformInputIterator<int64_t, KeepF, cub::CountingInputIterator<int64_t>>(ids, KeepF{D->nzval, 0.}), pos, nnz, st));
+    CK(cudaMalloc(&tmp, std::max(t1, t2) + 1));
+    size_t tsz = std::max(t1, t2) + 1;
+    CK(cub::DeviceReduce::Max(tmp, tsz, absit, dmax, nnz, st));
+    double hmax = 0.;
+    CK(cudaMemcpyAsync(&hmax, dmax, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double atol = rtol * hmax;
+    tsz = std::max(t1, t2) + 1;
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tsz, cub::TransformInputIterator<int64_t, KeepF, cub::CountingInputIterator<int64_t>>(ids, KeepF{D->nzval, atol}), pos, nnz, st));
+    int64_t lastpos = 0; double lastv = 0.;
+    CK(cudaMemcpyAsync(&lastpos, pos + (nnz - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lastv, D->nzval + (nnz - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t nkeep = lastpos + (fabs(lastv) >= atol ? 1 : 0);
+    sparser_scatter_kernel<<<nblk(nnz, 256), 256, 0, st>>>(nnz, D->nzval, D->rowval, pos, atol, D->cnzval, D->crowval);
+    sparser_colptr_kernel<<<nblk(D->ncol + 1, 256), 256, 0, st>>>(D->ncol, nnz, D->colptr, pos, nkeep, D->ccolptr);
+    h->launches += 4;
+    CK(cudaStreamSynchronize(st));
+    cudaFree(tmp); dfree(h, dmax); dfree(h, pos);
+    D->cnnz = nkeep;
+    if (nnz_out) *nnz_out = nkeep;
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(D->cnnz >= 0, "call mb_direct_sparser first");
+    CK(cudaSetDevice(h->device));
+    if (colptr) { CK(cudaMemcpy(colptr, D->ccolptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
+    if (rowval && D->cnnz) { CK(cudaMemcpy(rowval, D->crowval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->cnnz; ++i) rowval[i] += 1; }
+    if (nzval && D->cnnz) CK(cudaMemcpy(nzval, D->cnzval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost));
     return MB_OK;
 }
 // out.L1 / out.L2 blocks of one stored step: which = 0 L1[Λ] (nX), 1 L2[Λ,X][1,der] , 2 L2[X,Λ][der,1], 3 L2[Λ,U][1,1], 4 L2[U,Λ][1,1]

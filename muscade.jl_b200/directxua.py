@@ -92,6 +92,42 @@ class DirectEngine(Engine):
         X = [_f64(x) for x in X]
         check(self.h, self.L.mb_direct_set_state(self.h, int(step), ptr(X[0]), ptr(X[1]) if len(X) > 1 else None, ptr(X[2]) if len(X) > 2 else None, ptr(_f64(U0))))
 
+    # ---- Newton update on the device
+    def set_lambda(self, step, Lam):
+        check(self.h, self.L.mb_direct_set_lambda(self.h, int(step), ptr(_f64(Lam))))
+
+    def get_state(self, step):
+        """→ (X[0..OX], U0, Λ) of a stored step"""
+        X = [np.empty(self.ndofX) for _ in range(self.OX + 1)]
+        U = np.empty(self.ndofU); Lam = np.empty(self.ndofX)
+        check(self.h, self.L.mb_direct_get_state(self.h, int(step), ptr(X[0]), ptr(X[1]) if self.OX >= 1 else None, ptr(X[2]) if self.OX >= 2 else None,
+                                                 ptr(U) if self.ndofU else None, ptr(Lam)))
+        return X, U, Lam
+
+    def set_dof_scale(self, scaleL=None, scaleX=None, scaleU=None):
+        check(self.h, self.L.mb_direct_set_dof_scale(self.h, ptr(_f64(scaleL)), ptr(_f64(scaleX)), ptr(_f64(scaleU))))
+
+    def decrement(self, dv, s0=0, s1=None):
+        """decrementbig! (DirectXUA.jl:357-383) on the stored steps; dv = Δv rows of steps [s0,s1) → Δ² (Λ,X,U), max over the owned steps"""
+        s1 = self.nstep if s1 is None else s1
+        dv = _f64(dv)
+        assert dv.shape == ((s1 - s0) * (2 * self.ndofX + self.ndofU),)
+        d2 = np.zeros(3)
+        check(self.h, self.L.mb_direct_decrement(self.h, int(s0), int(s1), ptr(dv), ptr(d2)))
+        return d2
+
+    def sparser(self, rtol=1e-9):
+        """sparser!(cLvv,Lvv,rtol) (SparseTools.jl:196-199) on the device → number of entries kept"""
+        n = C.c_int64()
+        check(self.h, self.L.mb_direct_sparser(self.h, float(rtol), C.byref(n)))
+        self.cnnz = n.value
+        return self.cnnz
+
+    def sparse(self):
+        colptr = np.zeros(self.ncol + 1, np.int64); rowval = np.zeros(self.cnnz, np.int64); nzval = np.zeros(self.cnnz)
+        check(self.h, self.L.mb_direct_get_sparse(self.h, ptr(colptr), ptr(rowval), ptr(nzval)))
+        return colptr, rowval, nzval
+
     def direct_assemble(self, eval_range=None, build_big=True, Lvv=None, Lv=None):
         where = ErrInfo()
         lo, hi = (-1, -1) if eval_range is None else eval_range

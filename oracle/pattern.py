@@ -327,3 +327,33 @@ def assemblebig(IA, nstep, dt, P, big, bigasm, pgr, outs):
                             for (dbs, wb) in finitediff(bd - 1, nstep, istep):
                                 addin_block(bigasm, nz, val, 3 * (istep + das - 1) + a, 3 * (istep + dbs - 1) + b, wa * wb * s)
     return nz, Lv
+
+
+# ------------------------------------------------------------------------------------------------ sparser! / decrementbig!
+def sparser(colptr, rowval, nzval, rtol=1e-9):
+    """sparser!(T,S,rtol)  src/SparseTools.jl:172-199 ; 1-based colptr/rowval in and out"""
+    atol = rtol * np.abs(nzval).max()
+    keep = np.abs(nzval) >= atol
+    ndrop_before = np.concatenate([[0], np.cumsum(~keep)])
+    return colptr - ndrop_before[colptr - 1], rowval[keep], nzval[keep]
+
+
+def decrementbig(states, dv, OX, OU, dt, nstep, nX, nU, scaleL, scaleX, scaleU):
+    """decrementbig!(state,Δ²,Lvdis,dofgr,Δv,nder,Δt,nstep)  src/DirectXUA.jl:357-383, one experiment, IA=0.
+    states[istep] = dict(L=[Λ], X=[X0..], U=[U0..]) mutated in place; dv in the block order of Lv (per step Λ, X, U). Returns Δ²[3]."""
+    W = 2 * nX + nU
+    off = {1: 0, 2: nX, 3: 2 * nX}; n = {1: nX, 2: nX, 3: nU}
+    key = {1: "L", 2: "X", 3: "U"}; sc = {1: scaleL, 2: scaleX, 3: scaleU}; nder = {1: 1, 2: OX + 1, 3: OU + 1}
+    d2 = np.zeros(3)
+    inv = 1.0 / dt
+    dtp = [1.0, inv, inv * inv]                      # Δt^(1−βder)
+    for istep in range(1, nstep + 1):
+        for b in (1, 2, 3):
+            for bder in range(1, nder[b] + 1):
+                for (ds, w) in finitediff(bder - 1, nstep, istep):
+                    blk = (istep + ds - 1) * W + off[b]
+                    db = dv[blk: blk + n[b]]
+                    states[istep - 1][key[b]][bder - 1] -= ((db * w) * dtp[bder - 1]) * sc[b]
+                    if bder == 1:
+                        d2[b - 1] = max(d2[b - 1], float((db * db).sum()))
+    return d2

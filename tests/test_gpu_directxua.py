@@ -160,3 +160,48 @@ def test_directxua_beam_bar_soil(mb, OX):
     z = np.array([st[s][0][0][dis.dis[2].X[:, 2] - 1] for s in range(nstep)])
     assert (z < 0).any() and (z >= 0).any()          # both SoilContact branches
     eng.close()
+
+
+def test_directxua_sparser_and_decrementbig(mb):
+    """sparser!(cLvv,Lvv,rtol) (SparseTools.jl:172-199) and decrementbig! (DirectXUA.jl:357-383) on the device against their restatements:
+    compacted structure bit-exact, values copied; states after the update to 1e-14 (Δt^(1−βder) is an un-pinned Julia `^`), Δ² to 1e-13."""
+    OX, OU, nstep, dt, N = 2, 0, 8, 0.1, 6
+    model = udof_chain(mb, N, np.random.default_rng(2))
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)), Λscale=1e3)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU = model.getndof("X"), model.getndof("U")
+    st = states(mb, nX, nU, nstep)
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt)
+    for s, (X, U) in enumerate(st):
+        eng.set_state(s, X, U)
+    Lvv = np.zeros(eng.nnzbig)
+    eng.direct_assemble(Lvv=Lvv)
+    cp, rv = eng.big_pattern()
+    for rtol in (1e-20, 1e-3):
+        nkeep = eng.sparser(rtol)
+        c2, r2, v2 = eng.sparse()
+        oc, orow, ov = OP.sparser(cp, rv, Lvv, rtol)
+        assert nkeep == len(ov) and np.array_equal(c2, oc) and np.array_equal(r2, orow) and np.array_equal(v2, ov)
+    assert eng.sparser(1e-20) < 0.75 * eng.nnzbig              # the structurally-zero X-X / U-U blocks are gone
+    # decrementbig!
+    rng = np.random.default_rng(8)
+    W = 2 * nX + nU
+    dv = rng.standard_normal(nstep * W) * 1e-2
+    Lam = [rng.standard_normal(nX) for _ in range(nstep)]
+    sL, sX, sU = dis.scaleΛ, dis.scaleX, dis.scaleU
+    assert len(set(sL)) > 1 and len(set(sX)) > 1
+    eng.set_dof_scale(sL, sX, sU)
+    for s in range(nstep):
+        eng.set_lambda(s, Lam[s])
+    ost = [dict(L=[Lam[s].copy()], X=[x.copy() for x in st[s][0]], U=[st[s][1].copy()]) for s in range(nstep)]
+    d2ref = OP.decrementbig(ost, dv, OX, OU, dt, nstep, nX, nU, sL, sX, sU)
+    d2 = eng.decrement(dv)
+    assert np.abs(d2 - d2ref).max() <= 1e-13 * d2ref.max()
+    for s in range(nstep):
+        X, U, L = eng.get_state(s)
+        assert np.abs(L - ost[s]["L"][0]).max() <= 1e-14 * np.abs(ost[s]["L"][0]).max()
+        assert np.abs(U - ost[s]["U"][0]).max() <= 1e-14 * np.abs(ost[s]["U"][0]).max()
+        for d in range(3):
+            ref = ost[s]["X"][d]
+            assert np.abs(X[d] - ref).max() <= 1e-14 * max(np.abs(ref).max(), np.abs(dv).max() / dt ** d), (s, d)
+    eng.close()

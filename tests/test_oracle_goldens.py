@@ -284,3 +284,18 @@ def test_soil_contact_branches():
     X[0, 2] = 0.5
     R, dR, c = OE.soil_residual(p, X, seed)
     assert c == 0 and np.all(R == 0) and np.all(dR == 0)
+
+
+# ------------------------------------------------------------------------------------------------ test/TestSparseTools.jl:58-76
+def test_sparser_golden():
+    import scipy.sparse as sp
+    i = np.array([3, 7, 2, 3, 6, 2, 7, 9, 2, 6, 4, 5, 9, 3, 9, 1, 7, 8, 10, 4, 9, 7])
+    j = np.array([2, 2, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 7, 8, 8, 9, 9, 9, 9, 10, 10, 11])
+    v = np.array([0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0])
+    s = sp.csc_matrix((v + 10., (i - 1, j - 1)), shape=(10, 11))        # +10: keep the explicit zeros of Julia's sparse(i,j,v) stored
+    s.sort_indices()
+    nz = s.data - 10.
+    colptr, rowval, nzval = OP.sparser(s.indptr.astype(np.int64) + 1, s.indices.astype(np.int64) + 1, nz, rtol=0.6)   # keep ⇔ v > 0.5 for v ∈ {0,1}
+    assert colptr.tolist() == [1, 1, 2, 3, 5, 5, 5, 6, 6, 7, 8, 8]
+    assert rowval.tolist() == [7, 6, 2, 7, 4, 1, 9]
+    assert np.array_equal(nzval, np.ones(7))
