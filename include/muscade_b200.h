@@ -112,6 +112,10 @@ int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int3
  *   mb_direct_decrement   : decrementbig!(state,Δ²,Lvdis,dofgr,Δv,nder,Δt,nstep) (src/DirectXUA.jl:357-383) for the steps stored on this handle.
  *                           dv = Δv rows of steps [s0,s1) in Lv's layout (per step Λ(nX) X(nX) U(nU)), host or device; the range must reach
  *                           two steps beyond the stored ones (stencils of finitediff). delta2[3] = maxₜ ΣΔβ² over the OWNED steps (Λ,X,U). */
+/* Host-evaluated single-dof costs of one stored step (SingleDofCost on X or U dofs, src/BasicElements.jl:198-208, evaluated by the host
+ * because `cost` is a user closure): dense per-dof gradient (→ L1[X][1], L1[U][1]) and second derivative (→ diagonal of L2[X,X][1,1],
+ * L2[U,U][1,1]) vectors, already multiplied by scale / scale²; NULL = zeros. Merged into Lv / Lvv by mb_direct_assemble. */
+int32_t mb_direct_set_host_cost(mb_handle* h, int64_t step, const double* gX, const double* hX, const double* gU, const double* hU);
 int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
 int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
 int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda);

@@ -147,6 +147,7 @@ struct BigDev {
     int64_t pnnz[4];
     const double *LX, *XL, *LU, *UL, *L1L;        // stored per-step blocks
     int64_t sLX, sLU, sUL;         // strides per stored step
+    const double* hostc;           // host-evaluated single-dof costs per stored step: gX(nX) hX(nX) gU(nU) hU(nU), or nullptr
 };
 __device__ __forceinline__ int pat_of(int ca, int cb) { return (ca == 2 ? 2 : 0) + (cb == 2 ? 1 : 0); }   // class 2 = U
 // finitediff(order,n,s) (src/FiniteDifferences.jl:2-31): weight of offset ds at 0-based step s, or 0 with found=false
@@ -324,7 +325,25 @@ __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) 
     if (c >= ncol) return;
     int64_t step, lc; int cls;
     decode_col(B, c, step, cls, lc);
-    Lv[c] = (cls == 0) ? B.L1L[(step - B.elo) * B.nX + lc] : 0.;     // addin!(Lvasm,Lv,L1[Λ][1],Λblk)  (DirectXUA.jl:332-341)
+    double v = 0.;
+    if (cls == 0) v = B.L1L[(step - B.elo) * B.nX + lc];               // addin!(Lvasm,Lv,L1[Λ][1],Λblk)  (DirectXUA.jl:332-341)
+    else if (B.hostc) v = B.hostc[(step - B.elo) * 2 * (B.nX + B.nU) + (cls == 1 ? 0 : 2 * B.nX) + lc];   // L1[X][1], L1[U][1] of cost elements
+    Lv[c] = v;
+}
+// L2[X,X][1,1] / L2[U,U][1,1] of host-evaluated single-dof costs: one diagonal entry per dof, added to the (step,step) block
+__global__ void big_diag_kernel(BigDev B, int64_t ncol, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, double* __restrict__ nzval,
+                                unsigned long long* missing) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    int64_t step, lc; int cls;
+    decode_col(B, c, step, cls, lc);
+    if (cls == 0) return;
+    const double hd = B.hostc[(step - B.elo) * 2 * (B.nX + B.nU) + (cls == 1 ? B.nX : 2 * B.nX + B.nU) + lc];
+    if (hd == 0.) return;
+    const int64_t row = step * B.W + (cls == 1 ? B.nX : 2 * B.nX) + lc;
+    int64_t lo = colptr[c], hi = colptr[c + 1];
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < row) lo = mid + 1; else hi = mid; }
+    if (lo < colptr[c + 1] && rowval[lo] == row) nzval[lo] += hd; else atomicAdd(missing, 1ULL);
 }
 
 // ---------------------------------------------------------------------------------------------------------------- sparser! / decrementbig!
@@ -395,6 +414,7 @@ struct DirectData {
     double *X = nullptr, *U = nullptr, *Lam = nullptr;  // stored states [step][3][nX], [step][nU], [step][nX] (Λ enters decrementbig! only)
     double *scL = nullptr, *scX = nullptr, *scU = nullptr, *dvbuf = nullptr; int64_t dvlen = 0;
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;   // sparser! result
+    double* hostc = nullptr; unsigned long long* missing = nullptr;
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
     int32_t *bcolptr = nullptr, *browval = nullptr;
     int64_t ncol = 0, nnzbig = 0; int maxb = 0;         // maxb: most blocks in one block column
@@ -457,6 +477,7 @@ static BigDev make_bigdev(const DirectData* D) {
     for (int p = 0; p < 4; ++p) { B.pc[p] = D->pat[p].colptr0; B.pr[p] = D->pat[p].rowval0; B.pnnz[p] = D->pat[p].nnz; }
     B.LX = D->LX; B.XL = D->XL; B.LU = D->LU; B.UL = D->UL; B.L1L = D->L1L;
     B.sLX = (int64_t)(D->OX + 1) * D->pat[P_XX].nnz; B.sLU = D->pat[P_XU].nnz; B.sUL = D->pat[P_UX].nnz;
+    B.hostc = D->hostc;
     return B;
 }
 
@@ -662,12 +683,18 @@ int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32
         BigDev B = make_bigdev(D);
         launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
+        if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing); h->launches++; }
         h->launches += 2;
         if (Lvv_nzval) CK(cudaMemcpyAsync(Lvv_nzval, D->nzval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost, h->stream));
         if (Lv) CK(cudaMemcpyAsync(Lv, D->Lv, (size_t)D->ncol * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaGetLastError());
     rc = mb_sync(h, where);
+    if (rc == MB_OK && build_big && D->hostc) {
+        unsigned long long miss = 0;
+        CK(cudaMemcpy(&miss, D->missing, 8, cudaMemcpyDeviceToHost));
+        if (miss) { CK(cudaMemset(D->missing, 0, 8)); h->err = "a host-evaluated cost sits on a dof whose diagonal is not in the Lvv pattern (no device element touches it)"; return MB_ERR_ARG; }
+    }
     if (rc == MB_ERR_NAN && where) {     // nanbase packs (step, ieletyp, iele)
         const unsigned long long f = *h->nanflag_host;
         where->ieletyp = (int32_t)((f >> 40) & 0xF) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = (int64_t)(f >> 44) + 1;
@@ -680,6 +707,28 @@ int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
     CK(cudaSetDevice(h->device));
     if (colptr) { CK(cudaMemcpy(colptr, D->colptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
     if (rowval) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1; }
+    return MB_OK;
+}
+// host-evaluated single-dof costs of one stored step (SingleDofCost on X or U dofs, src/BasicElements.jl:198-208): gradient → L1[X][1] / L1[U][1],
+// second derivative → the diagonal of L2[X,X][1,1] / L2[U,U][1,1]; dense per-dof vectors, already multiplied by the dof scales; NULL = zeros
+int32_t mb_direct_set_host_cost(mb_handle* h, int64_t step, const double* gX, const double* hX, const double* gU, const double* hU) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi, "step not stored on this handle");
+    CK(cudaSetDevice(h->device));
+    const int64_t per = 2 * (D->nX + D->nU), ns = D->ehi - D->elo;
+    if (!D->hostc) {
+        CK(dalloc(h, &D->hostc, ns * per)); CK(cudaMemsetAsync(D->hostc, 0, (size_t)(ns * per) * 8, h->stream));
+        CK(dalloc(h, &D->missing, 1)); CK(cudaMemsetAsync(D->missing, 0, 8, h->stream));
+    }
+    double* base = D->hostc + (step - D->elo) * per;
+    const double* src[4] = {gX, hX, gU, hU}; const int64_t off[4] = {0, D->nX, 2 * D->nX, 2 * D->nX + D->nU}; const int64_t n[4] = {D->nX, D->nX, D->nU, D->nU};
+    for (int k = 0; k < 4; ++k) {
+        if (n[k] == 0) continue;
+        if (src[k]) CK(cudaMemcpyAsync(base + off[k], src[k], (size_t)n[k] * 8, cudaMemcpyDefault, h->stream));
+        else CK(cudaMemsetAsync(base + off[k], 0, (size_t)n[k] * 8, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
     return MB_OK;
 }
 // ---- Newton update of the all-steps problem on the device
@@ -846,6 +895,7 @@ int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms) {
         BigDev B = make_bigdev(D);
         launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
+        if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing); h->launches++; }
         h->launches += 2;
         CK(cudaEventRecord(e2, h->stream));
         CK(cudaEventSynchronize(e2));

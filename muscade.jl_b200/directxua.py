@@ -116,6 +116,9 @@ class DirectEngine(Engine):
         check(self.h, self.L.mb_direct_decrement(self.h, int(s0), int(s1), ptr(dv), ptr(d2)))
         return d2
 
+    def set_host_cost(self, step, gX=None, hX=None, gU=None, hU=None):
+        check(self.h, self.L.mb_direct_set_host_cost(self.h, int(step), ptr(_f64(gX)), ptr(_f64(hX)), ptr(_f64(gU)), ptr(_f64(hU))))
+
     def sparser(self, rtol=1e-9):
         """sparser!(cLvv,Lvv,rtol) (SparseTools.jl:196-199) on the device → number of entries kept"""
         n = C.c_int64()
@@ -166,6 +169,7 @@ def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
     """prepare(AssemblyDirect{OX,OU,0},model,dis) + preparebig(0,[nstep],out) for the owned steps [lo,hi)"""
     hi = nstep if hi is None else hi
     eng = DirectEngine(device)
+    eng.host_costs = []
     for et, ed in zip(model.ele, dis.dis):
         udof = ed.U.shape[1] > 0
         if et.ElType.kind == "eulerbeam3d":
@@ -174,8 +178,75 @@ def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
             eng.add_bar3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
         elif et.ElType.kind == "soilcontact":
             eng.add_soilcontact(et.eleobj, ed.X, ed.scaleX)
+        elif et.ElType.kind == "hostcost":
+            eng.host_costs.append((et, ed))          # evaluated by the host, merged by the device (set_host_cost)
         else:
-            muscadeerror("DirectXUA on the device supports EulerBeam3D, Bar3D and SoilContact element types in this version: %s" % (et.key,))
+            muscadeerror("DirectXUA on the device supports EulerBeam3D, Bar3D, SoilContact and SingleDofCost element types in this version: %s" % (et.key,))
     eng.direct_prepare(OX, OU, model.getndof("X"), model.getndof("U"), nstep, lo, hi, dt)
     eng.set_time0(t0)
     return eng
+
+
+def host_costs(eng, step, X0, U0, t):
+    """lagrangian of the host-evaluated SingleDofCost types at one step → (gX,hX,gU,hU), scaled (∂/∂(dof/scale)), and Σ cost"""
+    nX, nU = eng.ndofX, eng.ndofU
+    g = dict(X=np.zeros(nX), U=np.zeros(nU)); h = dict(X=np.zeros(nX), U=np.zeros(nU))
+    total = 0.
+    for et, ed in eng.host_costs:
+        clas = et.extra["clas"]
+        idx = (ed.X if clas == "X" else ed.U)[:, 0] - 1
+        sc = (ed.scaleX if clas == "X" else ed.scaleU)[0]
+        c, c1, c2 = et.ElType.cost_derivs(et.extra, (X0 if clas == "X" else U0)[idx], t)
+        np.add.at(g[clas], idx, c1 * sc); np.add.at(h[clas], idx, c2 * sc * sc)
+        total += float(c.sum())
+    return g["X"], h["X"], g["U"], h["U"], total
+
+
+def solve(OX, OU, initialstate, time, maxiter=50, maxΔλ=1e-5, maxΔx=1e-5, maxΔu=1e-5, verbose=False, device=0, sparser_rtol=1e-20):
+    """solve(DirectXUA{OX,OU,0};initialstate=[s],time=[t0:Δt:t1],…) (src/DirectXUA.jl:440-508), one experiment: Newton iterations on the
+    all-steps KKT system.  Element evaluation, Lvv/Lv assembly, sparser! and decrementbig! run on the device; the factorisation (UMFPACK in
+    the reference) is SuperLU on the host.  Returns the list of converged states, one per time step."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from .model import State
+    model, dis = initialstate.model, initialstate.dis
+    time = np.asarray(time, float)
+    nstep = len(time)
+    dt = float(time[1] - time[0])
+    if OU != 0:
+        muscadeerror("device decrementbig! stores ∂0(U) only: OU must be 0")
+    eng = prepare(OX, OU, model, dis, nstep, dt, t0=float(time[0]), device=device)
+    try:
+        s0 = initialstate.with_orders(1, OX + 1, OU + 1)
+        for k in range(nstep):
+            eng.set_state(k, s0.X, s0.U[0])
+            eng.set_lambda(k, s0.Λ[0])
+        eng.set_dof_scale(dis.scaleΛ, dis.scaleX, dis.scaleU)
+        maxΔ2 = np.array([maxΔλ, maxΔx, maxΔu]) ** 2
+        Lv = np.zeros(eng.ncol)
+        for it in range(1, maxiter + 1):
+            if eng.host_costs:
+                for k in range(nstep):
+                    X, U, _ = eng.get_state(k)
+                    eng.set_host_cost(k, *host_costs(eng, k, X[0], U, time[k])[:4])
+            eng.direct_assemble(Lv=Lv)
+            eng.sparser(sparser_rtol)
+            colptr, rowval, nzval = eng.sparse()
+            try:
+                LU = spla.splu(sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(eng.ncol, eng.ncol)))
+            except RuntimeError:
+                muscadeerror("Lvv matrix factorization failed")
+            Δ2 = eng.decrement(LU.solve(Lv))
+            if verbose:
+                print("    iteration %3d  maxₜ|ΔΛ|=%7.1e |ΔX|=%7.1e |ΔU|=%7.1e" % ((it,) + tuple(np.sqrt(Δ2))))
+            if (Δ2 <= maxΔ2).all():
+                break
+            if it == maxiter:
+                muscadeerror("no convergence after %3d iterations." % it)
+        out = []
+        for k in range(nstep):
+            X, U, Lam = eng.get_state(k)
+            out.append(State(float(time[k]), [Lam], X, [U], s0.A, dict(γ=0., iter=it), model, dis))
+        return out
+    finally:
+        eng.close()

@@ -90,6 +90,8 @@ def prepare(OX, model, dis, device=0):
             eng.add_bar3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
         elif et.ElType.kind == "soilcontact":
             eng.add_soilcontact(et.eleobj, ed.X, ed.scaleX)
+        elif et.ElType.kind == "hostcost":
+            eng.add_host_elements(ed.X)      # costs have no Λ-dependence: zero residual in an X-analysis, but their dofs are in the pattern
         else:
             if ed.U.shape[1] or ed.A.shape[1]:
                 muscadeerror("host-evaluated element types with U- or A-dofs are not supported in SweepX yet: %s" % (et.key,))

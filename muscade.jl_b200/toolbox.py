@@ -212,3 +212,65 @@ class DofLoad(ElementType):
         n = X[0].shape[0]
         F = float(extra["value"](t, *extra["args"]))
         return np.full((n, 1), -F), np.zeros((n, 1, 1)), None, None
+
+
+class Taylor2:
+    """Second-order Taylor scalar (value, d/dx, d²/dx²), vectorised over elements: the part of ∂ℝ{2,1,∂ℝ{1,1}} (src/Adiff.jl) a single-dof
+    cost function needs.  Supports + − * / ** (real exponent) and unary minus; `Taylor2.apply(f, f′, f″)` lifts any other function."""
+    __array_priority__ = 100
+
+    def __init__(self, v, d1=0., d2=0.):
+        self.v, self.d1, self.d2 = np.asarray(v, float), d1, d2
+
+    @staticmethod
+    def lift(x):
+        return x if isinstance(x, Taylor2) else Taylor2(x)
+
+    def apply(self, f, f1, f2):
+        a, b, c = f(self.v), f1(self.v), f2(self.v)
+        return Taylor2(a, b * self.d1, c * self.d1 * self.d1 + b * self.d2)
+
+    def __add__(self, o): o = Taylor2.lift(o); return Taylor2(self.v + o.v, self.d1 + o.d1, self.d2 + o.d2)
+    __radd__ = __add__
+    def __neg__(self): return Taylor2(-self.v, -self.d1, -self.d2)
+    def __sub__(self, o): return self + (-Taylor2.lift(o))
+    def __rsub__(self, o): return Taylor2.lift(o) + (-self)
+    def __mul__(self, o):
+        o = Taylor2.lift(o)
+        return Taylor2(self.v * o.v, self.d1 * o.v + self.v * o.d1, self.d2 * o.v + 2. * self.d1 * o.d1 + self.v * o.d2)
+    __rmul__ = __mul__
+    def __truediv__(self, o):
+        o = Taylor2.lift(o)
+        return self * o.apply(lambda x: 1. / x, lambda x: -1. / (x * x), lambda x: 2. / (x * x * x))
+    def __rtruediv__(self, o): return Taylor2.lift(o) / self
+    def __pow__(self, p):
+        p = float(p)
+        return self.apply(lambda x: x ** p, lambda x: p * x ** (p - 1.), lambda x: p * (p - 1.) * x ** (p - 2.))
+
+
+class SingleDofCost(ElementType):
+    """SingleDofCost(nod;class,field,cost,costargs) (src/BasicElements.jl:198-208), derivative=0: lagrangian L = cost(dof,t,costargs...).
+    `clas` replaces the reserved word `class`.  The cost is a Python closure, so the host evaluates it (value, gradient and second
+    derivative through Taylor2) and the device merges the result (mb_direct_set_host_cost)."""
+    kind = "hostcost"
+
+    @classmethod
+    def doflist(cls, clas, field, **kw):
+        if clas not in ("X", "U"):
+            raise ValueError("'class' must be :X or :U")
+        return (1,), (clas,), (field,)
+
+    @classmethod
+    def typekey(cls, clas, field, cost, **kw):
+        return ("SingleDofCost", clas, field, id(cost))
+
+    @classmethod
+    def construct(cls, coords, clas, field, cost, costargs=()):
+        return np.zeros((coords[0].shape[0], 0)), dict(clas=clas, cost=cost, args=tuple(costargs))
+
+    @staticmethod
+    def cost_derivs(extra, x, t):
+        """x (nele,) → cost, ∂cost/∂x, ∂²cost/∂x² per element"""
+        c = Taylor2.lift(extra["cost"](Taylor2(x, 1., 0.), t, *extra["args"]))
+        bc = lambda a: np.broadcast_to(np.asarray(a, float), np.shape(x)).copy()
+        return bc(c.v), bc(c.d1), bc(c.d2)

@@ -156,3 +156,75 @@ def test_dynamic_cantilever_newmark(mb):
         for d in range(3):
             ref = X[d]
             assert np.abs(host[istep].X[d] - ref).max() <= 1e-7 * max(1., np.abs(ref).max()), (istep, d)
+
+
+def test_directxua_load_identification(mb):
+    """solve(DirectXUA{2,0,0}) (src/DirectXUA.jl:440-508) on a free-flying chain of EulerBeam3D{Udof}: unknown distributed loads U are identified
+    from 'measured' positions (SingleDofCost on every X dof, quadratic regularisation on every U dof).  Device: element evaluation, Lvv/Lv,
+    sparser!, decrementbig!; host: the cost closures (through Taylor2) and SuperLU.  Checked against the same Newton loop driven entirely by
+    the oracle (its assembly, assemblebig, sparser, decrementbig) with the cost derivatives written in closed form."""
+    N, OX, OU, nstep, dt = 4, 2, 0, 8, 0.05
+    σx, σu = 0.05, 2.0
+    model = mb.Model("LoadId")
+    nod = mb.addnode(model, np.arange(N + 1)[:, None] * np.array([.8, .6, 0.])[None, :])
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    mat = mb.BeamCrossSection(EA=50., EI2=3., EI3=2.5, GJ=4., mu=1., iota1=.2, w=.3, Ca2=.5, Ca3=.4, Cq2=.2, Cq3=.2)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], unod], axis=1), mat=mat, Udof=True)
+    fields = ["t1", "t2", "t3", "r1", "r2", "r3"]
+    amp = {f: 0.02 * (1 + i) * np.cos(np.arange(N + 1) + i) for i, f in enumerate(fields)}      # 'measurement' amplitudes per node
+    for f in fields:
+        mb.addelement(model, mb.SingleDofCost, nod[:, None], clas="X", field=f, cost=lambda x, t, a=amp[f]: 0.5 * ((x - a * np.sin(3. * t)) / σx) ** 2)
+    for f in ["t1", "t2", "t3"]:
+        mb.addelement(model, mb.SingleDofCost, unod[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / σu) ** 2)
+    mb.setscale(model, scale=dict(X=dict(t1=.5, t2=.5, t3=.5), U=dict(t1=2., t2=2., t3=2.)), Λscale=10.)
+    st0 = mb.initialize(model, time=0.)
+    dis = st0.dis
+    time = dt * np.arange(nstep)
+    # maxΔλ=∞: with no_second_order elements the reference leaves Λᵀ∂R/∂X out of L1[X] (DirectXUA.jl:85-120), so its 'ΔΛ' is the multiplier
+    # itself and never goes to zero (the reference's own tests pass maxΔλ=.5, test/TestScale.jl:33)
+    sol = mb.directxua.solve(OX, OU, st0, time, maxΔλ=np.inf, maxΔx=1e-8, maxΔu=1e-8)
+    assert len(sol) == nstep and max(np.abs(s.U[0]).max() for s in sol) > 1e-3        # some load was identified
+
+    # ---- the same loop on the oracle
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+
+    def diagpos(ab, n):
+        cp, rv = P["pat"][ab][2], P["pat"][ab][3]
+        pos = np.zeros(n, np.int64)
+        for j in range(1, n + 1):
+            q = np.nonzero(rv[cp[j - 1] - 1: cp[j] - 1] == j)[0]
+            pos[j - 1] = cp[j - 1] - 1 + q[0]
+        return pos
+    dX, dU = diagpos((2, 2), nX), diagpos((3, 3), nU)
+    mX = np.zeros(nX)                                       # amplitude per model dof
+    for i, f in enumerate(fields):
+        mX[dis.dis[1 + i].X[:, 0] - 1] = amp[f]
+    sX, sU, sL = dis.scaleX, dis.scaleU, dis.scaleΛ
+    ost = [dict(L=[np.zeros(nX)], X=[np.zeros(nX) for _ in range(3)], U=[np.zeros(nU)]) for _ in range(nstep)]
+    for it in range(50):
+        outs = []
+        for k in range(nstep):
+            o = OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, OX, OU, ost[k]["X"], ost[k]["U"], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0)
+            x, u = ost[k]["X"][0], ost[k]["U"][0]
+            o["L1"][2] = ((x - mX * np.sin(3. * time[k])) / σx ** 2 * sX)[None, :]
+            o["L1"][3] = (u / σu ** 2 * sU)[None, :]
+            hxx = np.zeros(len(P["pat"][(2, 2)][3])); hxx[dX] = sX ** 2 / σx ** 2
+            huu = np.zeros(len(P["pat"][(3, 3)][3])); huu[dU] = sU ** 2 / σu ** 2
+            o["L2"][(2, 2)] = {(1, 1): hxx}; o["L2"][(3, 3)] = {(1, 1): huu}
+            outs.append(o)
+        nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+        c2, r2, v2 = OP.sparser(big["colptr"], big["rowval"], nz, 1e-20)
+        dv = spla.splu(sp.csc_matrix((v2, r2 - 1, c2 - 1), shape=(big["m"], big["n"]))).solve(Lv)
+        d2 = OP.decrementbig(ost, dv, OX, OU, dt, nstep, nX, nU, sL, sX, sU)
+        if (d2[1:] <= 1e-16).all():
+            break
+    assert it < 40
+    for k in range(nstep):
+        for d in range(3):
+            ref = ost[k]["X"][d]
+            assert np.abs(sol[k].X[d] - ref).max() <= 1e-6 * max(1e-2, np.abs(ref).max()), (k, d)
+        assert np.abs(sol[k].U[0] - ost[k]["U"][0]).max() <= 1e-6 * max(1e-2, np.abs(ost[k]["U"][0]).max())
+    assert sol[0].SP["iter"] == it + 1                     # same number of Newton iterations
