@@ -159,6 +159,69 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 // :step mission only (src/SweepX.jl:46-57,69-78): the extra seed direction δr carries the Newmark predictor
 //   vx′ = x′ + a₁δX + a·δr,  vx″ = x″ + b₁δX + b·δr,  a = a₂x′+a₃x″,  b = b₂x′+b₃x″ ;   Rp = ∂(Lλ)/∂r is subtracted from the rhs.
 // One thread per element, dense one-direction dual.
+// δr moves x′ and x″ only, and R is linear in the external-load cotangents: ∂R/∂r = J(X₀)ᵀ·∂c/∂r.  So: (A) time-jets with ONE dense direction
+// (every number type carries slot 0) → ∂c/∂r, 15 doubles per element in Wd[k][e]; (B) order-0 forward in plain values and the reverse sweep
+// on ∂c/∂r.  Two launches: fused they are 155 KB of SASS, beyond the instruction cache.
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_dr_cot_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Wd) {
+    using N1 = Num<SD<true, false>, SD<true, false>, SD<true, false>>;
+    using S = SD<true, false>;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    S Xu[3][6], Xv[3][6], U[3];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3, iv = iu + 3;
+        const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iv);
+        const double u0 = st.X0[du], u1 = (ND >= 2) ? st.X1[du] : 0., u2 = (ND >= 3) ? st.X2[du] : 0.;
+        const double v0 = st.X0[dv], v1 = (ND >= 2) ? st.X1[dv] : 0., v2 = (ND >= 3) ? st.X2[dv] : 0.;
+        Xu[0][i].v = u0; Xu[0][i].d0 = 0.; Xu[1][i].v = u1; Xu[1][i].d0 = nm.a2 * u1 + nm.a3 * u2; Xu[2][i].v = u2; Xu[2][i].d0 = nm.b2 * u1 + nm.b3 * u2;
+        Xv[0][i].v = v0; Xv[0][i].d0 = 0.; Xv[1][i].v = v1; Xv[1][i].d0 = nm.a2 * v1 + nm.a3 * v2; Xv[2][i].v = v2; Xv[2][i].d0 = nm.b2 * v1 + nm.b3 * v2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d0 = 0.; }
+    Vec3<S> xb[NGP], vsmb;
+    beam_dyn_cotangents<(ND >= 2 ? ND : 2), N1>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
+    double* w = Wd + e;
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w[(gp * 3 + i) * g.nele] = xb[gp][i].d0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[(NGP * 3 + i) * g.nele] = vsmb[i].d0;
+}
+static __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_dr_lin_kernel(BeamGroupDev g, StateDev st, const double* __restrict__ Wd, double* __restrict__ Rp, unsigned long long* nanflag, unsigned long long nanbase) {
+    using S = SD<true, false>; using V = SD<false, false>;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    V Xu0[6], Xv0[6]; S R[12];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const int iu = (i < 3) ? i : i + 3; Xu0[i].v = st.X0[__ldg(ix + iu)]; Xv0[i].v = st.X0[__ldg(ix + iu + 3)]; }
+    Vec3<S> xb[NGP], vsmb;
+    const double* w = Wd + e;
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { xb[gp][i].v = 0.; xb[gp][i].d0 = w[(gp * 3 + i) * g.nele]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { vsmb[i].v = 0.; vsmb[i].d0 = w[(NGP * 3 + i) * g.nele]; }
+    beam_residual_cot<NumVal, S>(geo, m, Xu0, Xv0, xb, vsmb, R);
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { double v = R[i].d0 * g.scaleX[i]; bad |= (v != v); Rp[e * 12 + i] = v; }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+// fused form (used when the workspace could not be allocated)
 template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
 beam_dr_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Rp, unsigned long long* nanflag, unsigned long long nanbase) {
@@ -373,8 +436,14 @@ template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
             beam_kernel_sd<ND_, true><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase, a.Wc, nt);    \
         } else                                                                                                                        \
             beam_kernel_sd<ND_, false><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase, nullptr, nt); \
-        if (STEP_)                                                                                                                    \
-            beam_dr_kernel<ND_><<<(unsigned)((a.g.nele + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Rp, a.nanflag, a.nanbase); \
+        if (STEP_) {                                                                                                                  \
+            const unsigned ne = (unsigned)((a.g.nele + MB_BLOCK - 1) / MB_BLOCK);                                                     \
+            if (ND_ >= 2 && a.Wc) {       /* the cotangent workspace is free again once phase B has run (same stream) */               \
+                beam_dr_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<ne, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Wc);                       \
+                beam_dr_lin_kernel<<<ne, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Wc, a.Rp, a.nanflag, a.nanbase);                       \
+            } else                                                                                                                    \
+                beam_dr_kernel<ND_><<<ne, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Rp, a.nanflag, a.nanbase);                      \
+        }                                                                                                                             \
     }
 
 }  // namespace mb

@@ -323,7 +323,7 @@ template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group
     BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base + e0 * 144, h->Re + g.vec_base + e0 * 12, h->Rp + g.vec_base + e0 * 12, h->nanflag, nanbase + (unsigned long long)e0,
                  h->beamW, h->stream, Wc};
     launch_beam<ND, STEP>(a);
-    h->launches += (STEP ? 2 : 1) + (Wc ? 1 : 0);
+    h->launches += 1 + (Wc ? 1 : 0) + (STEP ? (Wc ? 2 : 1) : 0);
 }
 
 // elements [e0,e1) of group ig (bar / soil groups are always launched whole)
