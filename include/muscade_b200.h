@@ -141,6 +141,12 @@ int32_t mb_sweepx_get_state(mb_handle* h, int32_t OX, double* X0, double* X1, do
 int32_t mb_sweepx_set_dof_scale(mb_handle* h, const double* scaleX);
 int32_t mb_sweepx_newmark_decrement(mb_handle* h, int32_t OX, int32_t firstiter, const double* dx, const double* newmark, double* dx2, double* Ll2);
 
+/* getresult(state,req,els) (src/Output.jl:131-181) for one EulerBeam3D element type, all elements at once, values only: the ☼/♢ requestables of
+ * residual (toolbox/BeamElement.jl:151-174) and resultants (:28-64). out: nele × 77 doubles,
+ *   [0] ε   [1..9] rₛₘ (column-major)   [10..12] ♢κ   then for igp = 1..4 at 13+16(igp−1):  x(3) κgp(3) fᵢ mᵢ(3) fₑ(3) mₑ(3).
+ * X0 = NULL reads the device-resident state (mb_sweepx_set_state); out may be host or device memory. */
+int32_t mb_beam_results(mb_handle* h, int32_t ieletyp, int32_t OX, const double* X0, const double* X1, const double* X2, double* out);
+
 /* Run this handle's kernels and copies on a caller-owned CUDA stream (e.g. the stream NCCL work is ordered against). */
 int32_t mb_set_stream(mb_handle* h, void* cuda_stream);
 /* SweepX element-range sharding: entries of the local Lλ / nzval that belong to nodes shared with a neighbouring shard.

@@ -46,6 +46,7 @@ SYMBOLS = {
     "mb_sweepx_assemble": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, f64p,
                                         C.c_void_p, C.c_void_p, C.POINTER(ErrInfo)]),
     "mb_sweepx_assemble_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p]),
+    "mb_beam_results": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_sweepx_set_state": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_sweepx_get_state": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_sweepx_set_dof_scale": (C.c_int32, [H, C.c_void_p]),

@@ -250,6 +250,29 @@ beam_dr_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
+// getresult: batched extraction of the element requestables, one thread per element (values only; HBM-bound: 616 B out per element)
+template <int ND>
+__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+beam_results_kernel(BeamGroupDev g, StateDev st, double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    double Xu[3][6], Xv[3][6], r[MB_NRES];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3;
+        const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iu + 3);
+        Xu[0][i] = st.X0[du]; Xu[1][i] = (ND >= 2) ? st.X1[du] : 0.; Xu[2][i] = (ND >= 3) ? st.X2[du] : 0.;
+        Xv[0][i] = st.X0[dv]; Xv[1][i] = (ND >= 2) ? st.X1[dv] : 0.; Xv[2][i] = (ND >= 3) ? st.X2[dv] : 0.;
+    }
+    beam_results<ND>(geo, m, Xu, Xv, r);
+    for (int k = 0; k < MB_NRES; ++k) out[e * MB_NRES + k] = r[k];
+}
+void launch_beam_results(int ND, const BeamGroupDev& g, const StateDev& st, double* out, cudaStream_t s);
+
 // K3: DirectXUA first-order path (src/DirectXUA.jl:85-120, no_second_order elements). Seeds are revariate{1}((;X,U),(;X=scale.X,U=scale.U))
 // (src/Taylor.jl:158-166): one partial per X₀,X₁,…,X_OX dof and per U₀ dof.
 // Output dR[e][p][i] = ∂R_i/∂seed_p with p in the reference's flat order X₀(12) X₁(12) X₂(12) U₀(3); R[e][i] unscaled (DirectXUA.jl:105).

@@ -487,6 +487,56 @@ template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, cons
         for (int i = 0; i < 3; ++i) vsmb[i] = widen<S>(r0(i, 0) * m1l);
     }
 }
+// getresult (src/Output.jl:131-181) for EulerBeam3D, values only: the ☼/♢ requestables of residual (BeamElement.jl:151-174) and resultants (:28-64).
+// out[77]: ε, rₛₘ (column-major 9), ♢κ (3), then per Gauss point x(3), κgp(3), fᵢ, mᵢ(3), fₑ(3) (before the −U of :169), mₑ(3).
+constexpr int MB_NRES = 13 + 16 * NGP;
+template <int ND> MB_HD void beam_results(const BeamGeo& g, const BeamMat& m, const double (*Xu)[6], const double (*Xv)[6], double* out) {
+    using V = SD<false, false>; using NJ = NumJet<NumVal>; using J = Jet<V>;
+    const double L = g.L;
+    J XuJ[6], XvJ[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        XuJ[i].c0.v = Xu[0][i]; XuJ[i].c1.v = (ND >= 2) ? Xu[1][i] : 0.; XuJ[i].c2.v = (ND >= 3) ? Xu[2][i] : 0.;
+        XvJ[i].c0.v = Xv[0][i]; XvJ[i].c1.v = (ND >= 2) ? Xv[1][i] : 0.; XvJ[i].c2.v = (ND >= 3) ? Xv[2][i] : 0.;
+    }
+    BeamFwd<NJ> fj;
+    beam_forward<NJ>(g, Vec3<J>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<J>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<J>{XuJ[3], XuJ[4], XuJ[5]}, Vec3<J>{XvJ[3], XvJ[4], XvJ[5]}, fj);
+    Mat3<V> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
+    out[0] = fj.eps.c0.v;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out[1 + i + 3 * j] = r0(i, j).v;
+    out[10] = fj.vl[0].c0.v * (2 / L); out[11] = fj.vl[2].c0.v * (2 / L); out[12] = -fj.vl[1].c0.v * (2 / L);
+    // roll inertia moment (Rotations.jl:177-182 → BeamElement.jl:55-57)
+    V m1l = Make<V>::c(0.);
+    if (ND >= 3) {
+        V m21 = (fj.r(0, 2).c0 * fj.r(0, 1).c2 + fj.r(1, 2).c0 * fj.r(1, 1).c2) + fj.r(2, 2).c0 * fj.r(2, 1).c2;
+        V m12 = (fj.r(0, 1).c0 * fj.r(0, 2).c2 + fj.r(1, 1).c0 * fj.r(1, 2).c2) + fj.r(2, 1).c0 * fj.r(2, 2).c2;
+        m1l = m.iota1 * ((m21 - m12) * 0.5);
+    }
+    for (int gp = 0; gp < NGP; ++gp) {
+        const GpConst c = gp_const(gp);
+        double* q = out + 13 + 16 * gp;
+        Vec3<J> p = beam_gp_local(c, L, fj.ul, fj.vl);
+        const double ka = 2.0 / L, ku = c.ku / (L * L), kv = 2.0 / L;
+        const double kap[3] = {ka * fj.vl[0].c0.v, ku * fj.ul[1].c0.v + kv * fj.vl[2].c0.v, ku * fj.ul[2].c0.v - kv * fj.vl[1].c0.v};
+        Vec3<V> x1, x2;
+        for (int i = 0; i < 3; ++i) {
+            V x0 = ((fj.r(i, 0).c0 * p[0].c0 + fj.r(i, 1).c0 * p[1].c0) + fj.r(i, 2).c0 * p[2].c0) + fj.cs[i].c0;
+            q[i] = x0.v;
+            x1[i] = ((fj.r(i, 0).c0 * p[0].c1 + fj.r(i, 0).c1 * p[0].c0) + (fj.r(i, 1).c0 * p[1].c1 + fj.r(i, 1).c1 * p[1].c0))
+                  + ((fj.r(i, 2).c0 * p[2].c1 + fj.r(i, 2).c1 * p[2].c0) + fj.cs[i].c1);
+            if (ND >= 3) {
+                x2[i] = (((fj.r(i, 0).c0 * p[0].c2 + fj.r(i, 0).c2 * p[0].c0) + 2.0 * (fj.r(i, 0).c1 * p[0].c1))
+                       + ((fj.r(i, 1).c0 * p[1].c2 + fj.r(i, 1).c2 * p[1].c0) + 2.0 * (fj.r(i, 1).c1 * p[1].c1)))
+                      + (((fj.r(i, 2).c0 * p[2].c2 + fj.r(i, 2).c2 * p[2].c0) + 2.0 * (fj.r(i, 2).c1 * p[2].c1)) + fj.cs[i].c2);
+            } else x2[i] = Make<V>::c(0.);
+            q[3 + i] = kap[i];
+        }
+        Vec3<V> fe = beam_fe(m, r0, x1, x2);
+        q[6] = m.EA * fj.eps.c0.v;
+        q[7] = m.GJ * kap[0]; q[8] = m.EI3 * kap[1]; q[9] = m.EI2 * kap[2];
+        for (int i = 0; i < 3; ++i) { q[10 + i] = fe[i].v; q[13 + i] = (r0(i, 0) * m1l).v; }
+    }
+}
 // Phase B: order-0 forward + reverse sweep with the cotangents of phase A
 // (S ≠ N::TS: forward in plain values, cotangents carrying partials — the linear lanes ∂R/∂X′, ∂R/∂X″, ∂R/∂U of DirectXUA)
 template <class N, class S = typename N::TS> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0, const typename N::TR* Xv0,

@@ -582,6 +582,37 @@ int32_t mb_sweepx_newmark_decrement(mb_handle* h, int32_t OX, int32_t firstiter,
     return MB_OK;
 }
 
+// getresult(state,req,els) for one EulerBeam3D element type (src/Output.jl:131-181): 77 values per element, layout in include/muscade_b200.h
+int32_t mb_beam_results(mb_handle* h, int32_t ieletyp, int32_t OX, const double* X0, const double* X1, const double* X2, double* out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && OX >= 0 && OX <= 2 && out && ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size(), "bad argument");
+    const Group& g = h->groups[(size_t)ieletyp - 1];
+    ARG(g.kind == G_BEAM, "element type is not EulerBeam3D");
+    ARG(!X0 || ((OX < 1 || X1) && (OX < 2 || X2)), "state vectors missing for this OX");
+    CK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)h->ndofX * sizeof(double);
+    if (X0) {
+        CK(cudaMemcpyAsync(h->X0, X0, nb, cudaMemcpyDefault, h->stream));
+        if (OX >= 1) CK(cudaMemcpyAsync(h->X1, X1, nb, cudaMemcpyDefault, h->stream));
+        if (OX >= 2) CK(cudaMemcpyAsync(h->X2, X2, nb, cudaMemcpyDefault, h->stream));
+    }
+    BeamGroupDev gd;
+    gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+    for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
+    for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+    StateDev sd{h->X0, h->X1, h->X2, nullptr};
+    double* dout = nullptr;
+    CK(dalloc(h, &dout, g.nele * MB_NRES));
+    launch_beam_results(OX + 1, gd, sd, dout, h->stream);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, dout, (size_t)(g.nele * MB_NRES) * sizeof(double), cudaMemcpyDefault, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    dfree(h, dout);
+    CK(e);
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+
 int32_t mb_get_device_ptrs(mb_handle* h, mb_dev_ptrs* out) {
     if (!h || !out) return MB_ERR_ARG;
     ARG(h->prepared, "not prepared");

@@ -171,6 +171,18 @@ class Engine:
         check(self.h, rc, dbg)
         return Llambda, nzval
 
+    def beam_results(self, ityp, OX, X=None):
+        """getresult for all elements of EulerBeam3D type `ityp` (Output.jl:131-181): dict of arrays eps (n), rsm (n,3,3), kappa (n,3) and per Gauss
+        point x, kappa_gp, mi, fe, me (n,4,3), fi (n,4)  [ε, rₛₘ, ♢κ, x, κgp, mᵢ, fₑ, mₑ, fᵢ of the reference].  X=None: device-resident state."""
+        nele = self.groups[ityp - 1][1]
+        raw = np.empty((nele, 77))
+        X = None if X is None else [_f64(x) for x in X]
+        check(self.h, self.L.mb_beam_results(self.h, int(ityp), int(OX), ptr(X[0]) if X else None, ptr(X[1]) if X and OX >= 1 else None,
+                                             ptr(X[2]) if X and OX >= 2 else None, ptr(raw)))
+        gp = raw[:, 13:].reshape(nele, 4, 16)
+        return {"raw": raw, "eps": raw[:, 0], "rsm": raw[:, 1:10].reshape(nele, 3, 3).transpose(0, 2, 1), "kappa": raw[:, 10:13], "x": gp[:, :, 0:3],
+                "kappa_gp": gp[:, :, 3:6], "fi": gp[:, :, 6], "mi": gp[:, :, 7:10], "fe": gp[:, :, 10:13], "me": gp[:, :, 13:16]}
+
     def sweepx_assemble_dev(self, OX, mission, newmark, t=0.):
         check(self.h, self.L.mb_sweepx_assemble_dev(self.h, OX, {"step": 0, "iter": 1}[mission], float(t), _f64(newmark)))
 

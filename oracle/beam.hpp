@@ -221,7 +221,9 @@ inline Resultants resultants(const BeamCrossSection& o, const DV eps[3], const V
 // ---------------------------------------------------------------- residual  BeamElement.jl:151-174
 // X[ider][12] as ∂ℝ{1,Np} (seeded by the caller = the solver's addin!), U0[3] likewise (zero partials when not seeded).
 // Output R[12] as ∂ℝ{1,Np}.
-template <int ND> inline void beam_residual(const EulerBeam3D& o, const DV (*X)[12], bool udof, const DV* U0, DV* R) {
+// `espy` (77 doubles, optional): the ☼/♢ requestables of the element (@espy, BeamElement.jl:151-174 and :28-64), values only:
+//   ε, rₛₘ (column-major 9), κ♢ (3), then per Gauss point x(3), κgp(3), fᵢ, mᵢ(3), fₑ(3) (before the −U of :169), mₑ(3)
+template <int ND> inline void beam_residual(const EulerBeam3D& o, const DV (*X)[12], bool udof, const DV* U0, DV* R, double* espy = nullptr) {
     using T = typename MotionT<ND>::type;
     // motion{P}(X)
     T X_[12];
@@ -260,6 +262,11 @@ template <int ND> inline void beam_residual(const EulerBeam3D& o, const DV (*X)[
     DV Rg[ngp][12];
     for (int g = 0; g < ngp; ++g) {
         Resultants r = resultants(o.mat, eps, gk[g], gx[g], rsm, vi);
+        if (espy) {
+            double* q = espy + 13 + 16 * g;
+            for (int i = 0; i < 3; ++i) { q[i] = VALUE(gx[g][0][i]); q[3 + i] = VALUE(gk[g][0][i]); q[7 + i] = VALUE(r.mi[i]); q[10 + i] = VALUE(r.fe[i]); q[13 + i] = VALUE(r.me[i]); }
+            q[6] = VALUE(r.fi);
+        }
         if (udof) for (int i = 0; i < 3; ++i) r.fe[i] = r.fe[i] - U0[i];
         for (int j = 0; j < 12; ++j) {
             DV t1 = r.fi * eps_dX[j];
@@ -270,6 +277,13 @@ template <int ND> inline void beam_residual(const EulerBeam3D& o, const DV (*X)[
         }
     }
     for (int j = 0; j < 12; ++j) R[j] = ((Rg[0][j] + Rg[1][j]) + Rg[2][j]) + Rg[3][j];
+    if (espy) {
+        espy[0] = VALUE(eps[0]);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) espy[1 + i + 3 * j] = VALUE(rsm[0](i, j));
+        DV k0[3], k1[3], k2[3];                         // ♢κ = motion⁻¹{P,ND}(SVector(vₗ₂[1],vₗ₂[3],−vₗ₂[2])).*(2/L)
+        motion_inv(kd.vl2[0], k0); motion_inv(kd.vl2[2], k1); motion_inv(kd.vl2[1], k2);
+        espy[10] = VALUE(k0[0]) * (2 / o.L); espy[11] = VALUE(k1[0]) * (2 / o.L); espy[12] = -VALUE(k2[0]) * (2 / o.L);
+    }
 }
 
 }  // namespace orc

@@ -358,3 +358,18 @@ def direct_addin_generic(residual_fn, nx, nu, idxX, idxU, OX, OU, X, U, scaleX, 
                 k = aUL[j + nu * i, e]
                 if k: out["L2"][(3, 1)][0, k - 1] += v
     return out
+
+
+def beam_results(elem, X, U=None):
+    """getresult for one EulerBeam3D (src/Output.jl:131-181): dict of the @espy requestables (BeamElement.jl:151-174, :28-64), values only.
+    X (nd,12)."""
+    X = np.ascontiguousarray(np.atleast_2d(X), float)
+    out = np.zeros(77)
+    f = lib().orc_beam_results
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    U = None if U is None else np.ascontiguousarray(U, float)
+    rc = f(_ptr(np.ascontiguousarray(elem, float)), X.shape[0], _ptr(X), int(U is not None), _ptr(U), _ptr(out))
+    if rc:
+        raise ValueError("orc_beam_results: %d" % rc)
+    return out

@@ -115,6 +115,18 @@ int orc_beam_residual(const double* elem69, int nd, int np, const double* Xval, 
     return nan ? 2 : 0;
 }
 
+// getresult(state,req,els) for EulerBeam3D (src/Output.jl:131-181 → the @espy requestables): 77 values per element, see beam_residual
+int orc_beam_results(const double* elem69, int nd, const double* Xval, int udof, const double* Uval, double* espy77) {
+    if (nd < 1 || nd > 3) return -1;
+    DVctx::np = 0;
+    EulerBeam3D o; unpack_beam(elem69, o);
+    DV X[3][12], U[3], Rv[12];
+    for (int d = 0; d < nd; ++d) for (int i = 0; i < 12; ++i) X[d][i].x = Xval[d * 12 + i];
+    for (int i = 0; i < 3; ++i) U[i].x = (udof && Uval) ? Uval[i] : 0.;
+    beam_dispatch(nd, [&](auto ND) { beam_residual<decltype(ND)::value>(o, X, udof != 0, U, Rv, espy77); });
+    return 0;
+}
+
 double orc_sinc1k(int k, double x) {
     switch (k) { case 0: return sinc1k<0>(x); case 1: return sinc1k<1>(x); case 2: return sinc1k<2>(x); case 3: return sinc1k<3>(x); case 4: return sinc1k<4>(x); }
     return NAN;

@@ -70,3 +70,20 @@ extern "C" int mbh_beam_iter_sd(const double* geo16, const double* mat16, int nd
     else run_sd<3>(g, m, Xval, scale, a1, b1, udof, Uval, R, K);
     return 0;
 }
+
+// getresult values (beam_results, the body of beam_results_kernel): X element dof order t1..r3 of node 1 then node 2, as the reference
+extern "C" int mbh_beam_results(const double* geo16, const double* mat16, int nd, const double* Xval, double* out77) {
+    BeamGeo g; BeamMat m;
+    for (int i = 0; i < 3; ++i) g.cm[i] = geo16[i];
+    for (int i = 0; i < 9; ++i) g.rm.a[i] = geo16[3 + i];
+    for (int i = 0; i < 3; ++i) g.tgm[i] = geo16[12 + i];
+    g.L = geo16[15];
+    std::memcpy(&m, mat16, sizeof m);
+    static const int rot[6] = {3, 4, 5, 9, 10, 11}, tra[6] = {0, 1, 2, 6, 7, 8};
+    double Xu[3][6], Xv[3][6];
+    for (int d = 0; d < 3; ++d) for (int i = 0; i < 6; ++i) { Xu[d][i] = d < nd ? Xval[d * 12 + tra[i]] : 0.; Xv[d][i] = d < nd ? Xval[d * 12 + rot[i]] : 0.; }
+    if (nd == 1) beam_results<1>(g, m, Xu, Xv, out77);
+    else if (nd == 2) beam_results<2>(g, m, Xu, Xv, out77);
+    else beam_results<3>(g, m, Xu, Xv, out77);
+    return 0;
+}

@@ -151,3 +151,24 @@ def test_device_newmark_decrement_is_bit_identical(mb, engine_factory, OX):
     L0, nz0 = eng.sweepx_assemble_resident(OX, "iter", nm)
     L1, nz1 = eng.sweepx_assemble(OX, "iter", st.X, nm)
     assert np.array_equal(L0, L1) and np.array_equal(nz0, nz1)
+
+
+@pytest.mark.parametrize("OX", [0, 2])
+def test_beam_requestables_batched(mb, engine_factory, OX):
+    """getresult(state,req,els) for all EulerBeam3D elements at once (src/Output.jl:131-181; requestables of toolbox/BeamElement.jl:28-64,
+    151-174) vs the oracle's per-element capture; from host state and from the device-resident state."""
+    N = 257
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=True)
+    X = mb.synthetic.state(ndof, nder=OX + 1)
+    eng = engine_factory()
+    ityp = eng.add_eulerbeam3d(eleobj, idx, np.ones(12)); eng.sweepx_prepare(ndof)
+    res = eng.beam_results(ityp, OX, X)
+    ref = np.stack([OE.beam_results(eleobj[e], np.stack([X[d][idx[e] - 1] for d in range(OX + 1)])) for e in range(N)])
+    assert res["raw"].shape == ref.shape == (N, 77)
+    for lo, hi in [(0, 1), (1, 10), (10, 13)] + [(13 + 16 * g + a, 13 + 16 * g + b) for g in range(4) for a, b in [(0, 3), (3, 6), (6, 7), (7, 10), (10, 13), (13, 16)]]:
+        scale = max(np.abs(ref[:, lo:hi]).max(), 1e-3)
+        assert np.abs(res["raw"][:, lo:hi] - ref[:, lo:hi]).max() <= 1e-12 * max(scale, 1.), (lo, hi)
+    assert np.array_equal(res["fi"][:, 2], res["raw"][:, 13 + 32 + 6]) and res["rsm"].shape == (N, 3, 3)
+    eng.set_state(X)
+    res2 = eng.beam_results(ityp, OX)
+    assert np.array_equal(res2["raw"], res["raw"])

@@ -84,3 +84,20 @@ def test_reference_pow_quirk_is_reproduced(H):
     R1 = np.zeros(12); d = np.zeros((12, 1))
     H.mbh_beam_residual(geo16(e), np.ascontiguousarray(e[53:69]), 3, 1, 0, X, np.zeros((3, 12, 0)), 0, np.zeros(3), np.zeros((3, 0)), R1, d)
     assert rel(R1, R0) <= 1e-12
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+@pytest.mark.parametrize("amp", [0.0, 1.0, 3.0])
+def test_requestables_vs_oracle(H, nd, amp):
+    """getresult values (ε, rₛₘ, ♢κ and per Gauss point x, κgp, fᵢ, mᵢ, fₑ, mₑ): product math vs the oracle's espy capture"""
+    H.mbh_beam_results.argtypes = [f64p, f64p, C.c_int, f64p, f64p]
+    rng = np.random.default_rng(21 + nd)
+    e = OE.beam_ctor([0, 0, 0], [.8, .6, 0.1], OE.beam_cross_section(**MAT), orient2=(0, 1, .2))
+    X = np.zeros((nd, 12)); X[0] = rng.uniform(-1, 1, 12) * 0.3 * amp
+    for d in range(1, nd):
+        X[d] = rng.uniform(-1, 1, 12) * 0.1 * (amp > 0)
+    ref = OE.beam_results(e, X)
+    out = np.zeros(77)
+    assert H.mbh_beam_results(geo16(e), np.ascontiguousarray(e[53:69]), nd, np.ascontiguousarray(X), out) == 0
+    scale = max(np.abs(ref).max(), 1.)
+    assert np.abs(out - ref).max() <= 1e-12 * scale, np.abs(out - ref).argmax()

@@ -299,3 +299,17 @@ def test_sparser_golden():
     assert colptr.tolist() == [1, 1, 2, 3, 5, 5, 5, 6, 6, 7, 8, 8]
     assert rowval.tolist() == [7, 6, 2, 7, 4, 1, 9]
     assert np.array_equal(nzval, np.ones(7))
+
+
+# ------------------------------------------------------------------------------------------------ test/TestBeamElementStrainGauge.jl:30-56
+def test_beam_requestables_goldens():
+    """♢κ and the axial strain of the beam as read by StrainGaugeOnEulerBeam3D (eleres.κ, eleres.εₐₓ; atol = 1e-12 as in the reference)"""
+    b = OE.beam_ctor([0, 0, 0], [4, 0, 0], OE.beam_cross_section(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1.0))
+    for X, kap in [([0, 0, 0, 0, .1, 0, 0, 0, 0, 0, -.1, 0], [0, 0, 1 / 20]),
+                   ([0, 0, 0, 0, 0, .1, 0, 0, 0, 0, 0, -.1], [0, -1 / 20, 0]),
+                   ([0, 0, 0, 0, 0, 0, 0, 0, 0, 1., 0, 0], [.25, 0, 0])]:
+        r = OE.beam_results(b, np.array([X], float))
+        assert abs(r[0]) <= 1e-12                                   # εₐₓ
+        assert np.abs(r[10:13] - np.array(kap)).max() <= 1e-12       # ♢κ
+        # Gauss-point curvature κgp[1] (torsion rate) is uniform along the element and equals ♢κ[1]
+        assert np.abs(r[13 + 16 * np.arange(4) + 3] - kap[0]).max() <= 1e-12
