@@ -132,7 +132,7 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
             for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; xb[gp][i].v = w[(k) * 32]; xb[gp][i].d0 = w[(k + 1) * 32]; xb[gp][i].d1 = w[(k + 2) * 32]; }
 #pragma unroll
         for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; vsmb[i].v = w[(k) * 32]; vsmb[i].d0 = w[(k + 1) * 32]; vsmb[i].d1 = w[(k + 2) * 32]; }
-        beam_residual_cot<N>(geo, m, Xu[0], Xv[0], xb, vsmb, R);
+        beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, R);      // v̄ₛₘ ≠ 0 only with accelerations
     } else {
         beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
     }
@@ -354,7 +354,7 @@ beam_direct_b0_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR
     if (ND >= 2) {
         Vec3<TS> xb[NGP], vsmb;
         load_cot(Wc, t, xb, vsmb);
-        beam_residual_cot<N>(geo, m, Xu[0], Xv[0], xb, vsmb, Rv);
+        beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, Rv);
     } else {
         beam_residual_n<1, N>(geo, m, Xu, Xv, g.udof != 0, U, Rv);
     }
@@ -418,7 +418,7 @@ beam_direct_lin_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ d
         const int iu = (i < 3) ? i : i + 3;
         Xu0[i].v = st.X[0][__ldg(ix + iu)]; Xv0[i].v = st.X[0][__ldg(ix + iu + 3)];
     }
-    beam_residual_cot<NV, S>(geo, m, Xu0, Xv0, xb, vsmb, Rv);
+    beam_residual_cot<NV, S, (ND >= 3)>(geo, m, Xu0, Xv0, xb, vsmb, Rv);
     bool bad = false;
     double* out = dR + e * (int64_t)(12 * NP);
 #pragma unroll

@@ -221,8 +221,9 @@ template <class N> struct BeamFwd {
     Vec3<TS> ul, q; TS eps, qn;               // q = uₗ₂ + (L/2,0,0), qn = |q|
 };
 // corotated{:direct} + ε  (BeamElement.jl:181,192-208).  u1,u2: translations (TU); v1,v2: rotation vectors (TR)
-template <class N> MB_HD void beam_forward(const BeamGeo& g, const Vec3<typename N::TU>& u1, const Vec3<typename N::TR>& v1,
-                                           const Vec3<typename N::TU>& u2, const Vec3<typename N::TR>& v2, BeamFwd<N>& f) {
+// VSM = false skips vₛₘ = Rodrigues⁻¹(rₛₘ): it only feeds the roll-inertia cotangent v̄ₛₘ, which is zero without accelerations.
+template <class N, bool VSM = true> MB_HD void beam_forward(const BeamGeo& g, const Vec3<typename N::TU>& u1, const Vec3<typename N::TR>& v1,
+                                                            const Vec3<typename N::TU>& u2, const Vec3<typename N::TR>& v2, BeamFwd<N>& f) {
     using TR = typename N::TR; using TU = typename N::TU;
     f.v1 = v1; f.v2 = v2;
     f.r1 = rodrigues(f.v1, f.a1);
@@ -233,7 +234,7 @@ template <class N> MB_HD void beam_forward(const BeamGeo& g, const Vec3<typename
     for (int i = 0; i < 3; ++i) f.dv[i] = 0.5 * h[i];
     f.rd = rodrigues(f.dv, f.ad);
     f.r = mul(mul(f.rd, f.r1), g.rm);
-    f.vsm = rodrigues_inv(f.r, f.ir);
+    if constexpr (VSM) f.vsm = rodrigues_inv(f.r, f.ir);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         TU cs = 0.5 * (u1[i] + u2[i]);
@@ -279,14 +280,20 @@ template <class TR, class S> MB_HD Vec3<S> beam_fe(const BeamMat& m, const Mat3<
 // ------------------------------------------------------------------------------------------------ reverse sweep
 // Adjoint accumulators of the quantities the Gauss loop feeds: r̄ₛₘ, ūₗ, v̄ₗ, c̄ₛₘ
 template <class S> struct BeamAcc { Mat3<S> rb; Vec3<S> ulb, vlb, cb; };
-// One Gauss point: internal moment cotangent κ̄ = dL·mᵢ (BeamElement.jl:62) computed on the fly, external force cotangent x̄ given.
-template <class N, class S = typename N::TS> MB_HD void beam_gp_reverse(const GpConst& c, double L, const BeamMat& m, const BeamFwd<N>& f, const Vec3<S>& xb,
-                                                                        BeamAcc<S>& a) {
-    const double dL = c.w * L, yv = c.yv * L, ka = 2.0 / L, ku = c.ku / (L * L), kv = 2.0 / L;
-    // κ = (κₐvₗ₁, κᵤuₗ₂+κᵥvₗ₃, κᵤuₗ₃−κᵥvₗ₂)  (BeamElement.jl:184)
-    auto kb0 = (m.GJ * dL) * (ka * f.vl[0]);
-    auto kb1 = (m.EI3 * dL) * (ku * f.ul[1] + kv * f.vl[2]);
-    auto kb2 = (m.EI2 * dL) * (ku * f.ul[2] - kv * f.vl[1]);
+// Internal moments mᵢ = (GJκ₁, EI₃κ₂, EI₂κ₃) (BeamElement.jl:62) with κ = (κₐvₗ₁, κᵤuₗ₂+κᵥvₗ₃, κᵤuₗ₃−κᵥvₗ₂) (:184), κₐ = κᵥ = 2/L, κᵤ = −24ζ/L²: the
+// Gauss sum Σ dL·κ̄·∂κ is a quadratic form in the abscissae and is taken in closed form — Σw = 1, Σwζ = 0, Σwζ² = 1/12 (4-point rule,
+// exact to degree 7) — which gives the textbook coefficients 48EI/L³ on uₗ and 4EI/L, 4GJ/L on vₗ.
+template <class N, class S = typename N::TS> MB_HD void beam_internal_reverse(double L, const BeamMat& m, const BeamFwd<N>& f, BeamAcc<S>& a) {
+    const double c48 = 48.0 / (L * L * L), c4 = 4.0 / L;
+    a.ulb[1] = a.ulb[1] + (m.EI3 * c48) * f.ul[1];
+    a.ulb[2] = a.ulb[2] + (m.EI2 * c48) * f.ul[2];
+    a.vlb[0] = a.vlb[0] + (m.GJ * c4) * f.vl[0];
+    a.vlb[1] = a.vlb[1] + (m.EI2 * c4) * f.vl[1];
+    a.vlb[2] = a.vlb[2] + (m.EI3 * c4) * f.vl[2];
+}
+// One Gauss point, external loads: x̄ = dL·fₑ given; x = rₛₘ p + cₛₘ, p = (yₐuₗ₁+Lζ, yᵤuₗ₂+yᵥvₗ₃, yᵤuₗ₃−yᵥvₗ₂)  (BeamElement.jl:183-187)
+template <class N, class S = typename N::TS> MB_HD void beam_gp_reverse(const GpConst& c, double L, const BeamFwd<N>& f, const Vec3<S>& xb, BeamAcc<S>& a) {
+    const double yv = c.yv * L;
     auto p = beam_gp_local(c, L, f.ul, f.vl);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
@@ -296,15 +303,25 @@ template <class N, class S = typename N::TS> MB_HD void beam_gp_reverse(const Gp
 #pragma unroll
     for (int i = 0; i < 3; ++i) a.cb[i] = a.cb[i] + xb[i];
     a.ulb[0] = a.ulb[0] + c.ya * pb[0];
-    a.ulb[1] = a.ulb[1] + (c.yu * pb[1] + ku * kb1);
-    a.ulb[2] = a.ulb[2] + (c.yu * pb[2] + ku * kb2);
-    a.vlb[0] = a.vlb[0] + ka * kb0;
-    a.vlb[1] = a.vlb[1] - (yv * pb[2] + kv * kb2);
-    a.vlb[2] = a.vlb[2] + (yv * pb[1] + kv * kb1);
+    a.ulb[1] = a.ulb[1] + c.yu * pb[1];
+    a.ulb[2] = a.ulb[2] + c.yu * pb[2];
+    a.vlb[1] = a.vlb[1] - yv * pb[2];
+    a.vlb[2] = a.vlb[2] + yv * pb[1];
+}
+// The same summed over the Gauss points when fₑ does not depend on the point (statics: weight and −U): Σ dL·p = (0, −L²vₗ₃/6, L²vₗ₂/6)
+// (Σw·yₐ = Σw·yᵤ = Σwζ = 0, Σw·yᵥ = Σwζ² − ¼ = −1/6), Σ dL = L.
+template <class N, class S = typename N::TS> MB_HD void beam_uniform_reverse(double L, const BeamFwd<N>& f, const Vec3<S>& fe, BeamAcc<S>& a) {
+    const double k6 = L * L / 6.0;
+    auto P1 = -k6 * f.vl[2]; auto P2 = k6 * f.vl[1];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a.rb(i, 1) = a.rb(i, 1) + fe[i] * P1; a.rb(i, 2) = a.rb(i, 2) + fe[i] * P2; a.cb[i] = a.cb[i] + L * fe[i]; }
+    Vec3<S> gl = mulv_t(f.r, fe);
+    a.vlb[1] = a.vlb[1] + k6 * gl[2];
+    a.vlb[2] = a.vlb[2] - k6 * gl[1];
 }
 // Everything upstream of the Gauss loop: ε, uₗ/vₗ, vₛₘ, the corotated frame and the three Rodrigues maps → X̄[12]
-template <class N, class SC, class S = typename N::TS> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N>& f, const S& epsb, const Vec3<S>& vsmb,
-                                                                                  BeamAcc<S>& a, S* Xb, const SC& sc) {
+template <class N, class SC, class S = typename N::TS, bool VSM = true> MB_HD void beam_reverse_rot(const BeamGeo& g, const BeamFwd<N>& f, const S& epsb, const Vec3<S>& vsmb,
+                                                                                                   BeamAcc<S>& a, S* Xb, const SC& sc) {
     const double L = g.L;
     S z = Make<S>::c(0.);
     Mat3<S>& rb = a.rb; Vec3<S>&ulb = a.ulb, &vlb = a.vlb, &cb = a.cb;
@@ -322,7 +339,7 @@ template <class N, class SC, class S = typename N::TS> MB_HD void beam_reverse_r
 #pragma unroll
         for (int i = 0; i < 3; ++i) rb(i, j) = rb(i, j) + (f.dp[i] * ulb[j] + f.dv[i] * vlb[j]);
     // vₛₘ = Rodrigues⁻¹(r)
-    rodrigues_inv_adj(f.vsm, f.ir, vsmb, rb);
+    if constexpr (VSM) rodrigues_inv_adj(f.vsm, f.ir, vsmb, rb);
     // r = rd · r1 · rm
     Mat3<S> t = mul_nt(rb, g.rm);                  // r̄ rₘᵀ
     Mat3<S> rdb = mul_nt(t, f.r1);                 // (r̄ rₘᵀ) r₁ᵀ
@@ -369,17 +386,16 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
     }
     Vec3<S> vsmb{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(0.)};
     if (ND == 1) {
-        beam_forward<N>(g, Vec3<TU>{Xu[0][0], Xu[0][1], Xu[0][2]}, Vec3<TR>{Xv[0][0], Xv[0][1], Xv[0][2]},
-                        Vec3<TU>{Xu[0][3], Xu[0][4], Xu[0][5]}, Vec3<TR>{Xv[0][3], Xv[0][4], Xv[0][5]}, f);
+        beam_forward<N, false>(g, Vec3<TU>{Xu[0][0], Xu[0][1], Xu[0][2]}, Vec3<TR>{Xv[0][0], Xv[0][1], Xv[0][2]},
+                               Vec3<TU>{Xu[0][3], Xu[0][4], Xu[0][5]}, Vec3<TR>{Xv[0][3], Xv[0][4], Xv[0][5]}, f);
         if constexpr (SC::enabled) { stash(sc, 0, f.r2); stash(sc, 9 * Comp<TR>::n, f.rd); }
-        MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
-        for (int gp = 0; gp < NGP; ++gp) {
-            const GpConst c = gp_const(gp);
-            const double dL = c.w * L;
-            Vec3<S> xb{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(m.w * dL)};      // weight (BeamElement.jl:37); − U (:169)
-            if (udof) for (int i = 0; i < 3; ++i) xb[i] = xb[i] - dL * U0[i];
-            beam_gp_reverse<N>(c, L, m, f, xb, acc);
-        }
+        Vec3<S> fe{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(m.w)};               // weight (BeamElement.jl:37); − U (:169)
+        if (udof) for (int i = 0; i < 3; ++i) fe[i] = fe[i] - U0[i];
+        beam_uniform_reverse<N>(L, f, fe, acc);
+        beam_internal_reverse<N>(L, m, f, acc);
+        S epsb = (m.EA * L) * f.eps;                                                // internal axial force (:59): Σ_gp dL·fᵢ = EA·L·ε
+        beam_reverse_rot<N, SC, S, false>(g, f, epsb, vsmb, acc, R, sc);
+        return;
     } else {
         using NJ = NumJet<N>;
         using JR = typename NJ::TR; using JU = typename NJ::TU; using JS = typename NJ::TS;
@@ -426,8 +442,9 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
             const double dL = c.w * L;
             Vec3<S> xb;
             for (int i = 0; i < 3; ++i) { if (udof) fe[i] = fe[i] - U0[i]; xb[i] = dL * fe[i]; }
-            beam_gp_reverse<N>(c, L, m, f, xb, acc);
+            beam_gp_reverse<N>(c, L, f, xb, acc);
         }
+        beam_internal_reverse<N>(L, m, f, acc);
         // roll inertia: mₑ = rₛₘ[:,1]·ι₁·vᵢ₂[1], vᵢ₂ = spin⁻¹(ṙᵀṙ + rᵀr̈)  (Rotations.jl:177-182; the symmetric ṙᵀṙ drops out of spin⁻¹)
         if (ND >= 3) {
             TR m21 = (fj.r(0, 2).c0 * fj.r(0, 1).c2 + fj.r(1, 2).c0 * fj.r(1, 1).c2) + fj.r(2, 2).c0 * fj.r(2, 1).c2;   // (rᵀr̈)[3,2]
@@ -457,8 +474,8 @@ template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, cons
         XvJ[i].c0 = Xv[0][i]; XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
     }
     BeamFwd<NJ> fj;
-    beam_forward<NJ>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JR>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]},
-                     Vec3<JR>{XvJ[3], XvJ[4], XvJ[5]}, fj);
+    beam_forward<NJ, false>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JR>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]},
+                            Vec3<JR>{XvJ[3], XvJ[4], XvJ[5]}, fj);
     Mat3<TR> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
     MB_PRAGMA(unroll MB_GP_UNROLL_DYN)
     for (int gp = 0; gp < NGP; ++gp) {
@@ -500,7 +517,7 @@ template <int ND> MB_HD void beam_results(const BeamGeo& g, const BeamMat& m, co
         XvJ[i].c0.v = Xv[0][i]; XvJ[i].c1.v = (ND >= 2) ? Xv[1][i] : 0.; XvJ[i].c2.v = (ND >= 3) ? Xv[2][i] : 0.;
     }
     BeamFwd<NJ> fj;
-    beam_forward<NJ>(g, Vec3<J>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<J>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<J>{XuJ[3], XuJ[4], XuJ[5]}, Vec3<J>{XvJ[3], XvJ[4], XvJ[5]}, fj);
+    beam_forward<NJ, false>(g, Vec3<J>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<J>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<J>{XuJ[3], XuJ[4], XuJ[5]}, Vec3<J>{XvJ[3], XvJ[4], XvJ[5]}, fj);
     Mat3<V> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
     out[0] = fj.eps.c0.v;
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out[1 + i + 3 * j] = r0(i, j).v;
@@ -539,8 +556,8 @@ template <int ND> MB_HD void beam_results(const BeamGeo& g, const BeamMat& m, co
 }
 // Phase B: order-0 forward + reverse sweep with the cotangents of phase A
 // (S ≠ N::TS: forward in plain values, cotangents carrying partials — the linear lanes ∂R/∂X′, ∂R/∂X″, ∂R/∂U of DirectXUA)
-template <class N, class S = typename N::TS> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0, const typename N::TR* Xv0,
-                                                                          const Vec3<S>* xb, const Vec3<S>& vsmb, S* R) {
+template <class N, class S = typename N::TS, bool VSM = true> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0,
+                                                                                           const typename N::TR* Xv0, const Vec3<S>* xb, const Vec3<S>& vsmb, S* R) {
     using TR = typename N::TR; using TU = typename N::TU;
     const double L = g.L;
     BeamFwd<N> f;
@@ -550,12 +567,13 @@ template <class N, class S = typename N::TS> MB_HD void beam_residual_cot(const 
         for (int i = 0; i < 9; ++i) acc.rb.a[i] = z;
         for (int i = 0; i < 3; ++i) { acc.ulb[i] = z; acc.vlb[i] = z; acc.cb[i] = z; }
     }
-    beam_forward<N>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
+    beam_forward<N, VSM>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
     MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
-    for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N, S>(gp_const(gp), L, m, f, xb[gp], acc);
+    for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N, S>(gp_const(gp), L, f, xb[gp], acc);
+    beam_internal_reverse<N, S>(L, m, f, acc);
     S epsb = widen<S>((m.EA * L) * f.eps);
     HostScratch sc;
-    beam_reverse_rot<N, HostScratch, S>(g, f, epsb, vsmb, acc, R, sc);
+    beam_reverse_rot<N, HostScratch, S, VSM>(g, f, epsb, vsmb, acc, R, sc);
 }
 
 template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
