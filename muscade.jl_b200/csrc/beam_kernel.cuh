@@ -277,7 +277,8 @@ void launch_beam_results(int ND, const BeamGroupDev& g, const StateDev& st, doub
 // (src/Taylor.jl:158-166): one partial per X₀,X₁,…,X_OX dof and per U₀ dof.
 // Output dR[e][p][i] = ∂R_i/∂seed_p with p in the reference's flat order X₀(12) X₁(12) X₂(12) U₀(3); R[e][i] unscaled (DirectXUA.jl:105).
 // Three launches, each inside the instruction cache (the fused one-kernel form was 216 KB of SASS and instruction-fetch bound):
-//   cot  (ND ≥ 2)  lanes (d,e,l), d-major: time-jet forward seeded at derivative order d → cotangents x̄_gp, v̄ₛₘ with partials → Wc
+//   cot  (ND ≥ 2)  lanes (d,e,l), d ∈ {0,1}, d-major: time-jet forward seeded at X₀ or X′ → cotangents x̄_gp, v̄ₛₘ with partials → Wc; the
+//                  partials with respect to X″ are the order-0 partials of the X₀ lane (beam_dyn_cotangents<…,DD>) and are written by it
 //   b0             lanes (e,l): order-0 forward + reverse sweep in SD arithmetic → R and ∂R/∂X₀
 //   lin            lanes (d≥1,e,l) and 2 U-lanes per Udof element: R is linear in the cotangents, so ∂R/∂X_d = J(X₀)ᵀ·∂c/∂X_d needs the forward
 //                  sweep in plain values only and the reverse sweep on the partials of c (∂c/∂U is known in closed form: −dL·scale.U).
@@ -321,9 +322,10 @@ template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
 beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ Wc) {
     using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    constexpr int NDJ = (ND >= 3) ? 2 : ND;            // derivative orders that need their own time-jet lanes: X₀ and X′ (X″ comes with X₀)
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = g.nele * 6;
-    if (t >= per * ND) return;
+    if (t >= per * NDJ) return;
     const int d = (int)(t / per);
     const int64_t r = t - d * per, e = r / 6;
     const int l = (int)(r - e * 6);
@@ -333,7 +335,12 @@ beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ W
     TU Xu[3][6], U[3]; TR Xv[3][6];
     load_direct_state<ND>(g, st, e, d, l, Xu, Xv, U);
     Vec3<TS> xb[NGP], vsmb;
-    beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
+    if constexpr (ND >= 3) {                           // one copy of the jet code for both lane kinds (two would leave the instruction cache)
+        Vec3<TS> xb2[NGP], vsmb2;
+        beam_dyn_cotangents<ND, N, true>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, xb2, &vsmb2);
+        if (d == 0) store_cot(Wc, 2 * per + t, xb2, vsmb2);        // the tile the X″ lane (2,e,l) of the linear kernel reads
+    } else
+        beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
     store_cot(Wc, t, xb, vsmb);
 }
 template <int ND>
@@ -438,7 +445,7 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
                                             unsigned long long* nanflag, unsigned long long nanbase, double* Wc, cudaStream_t s) {            \
         const int64_t per = g.nele * 6, nlin = per * (ND_ - 1) + (g.udof ? 2 * g.nele : 0);                                                  \
         int n = 1;                                                                                                                            \
-        if (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<(unsigned)((per * ND_ + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, Wc); ++n; } \
+        if (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<(unsigned)((per * (ND_ >= 3 ? 2 : ND_) + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, Wc); ++n; } \
         beam_direct_b0_kernel<ND_><<<(unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase, Wc);      \
         if (nlin) { beam_direct_lin_kernel<ND_><<<(unsigned)((nlin + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, nanflag, nanbase, Wc); ++n; } \
         return n;                                                                                                                             \

@@ -461,8 +461,13 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
 // ------------------------------------------------------------------------------------------------ two-phase variant (ND ≥ 2)
 // The fused Newmark kernel is ~210 KB of straight-line code and runs out of the instruction cache; split in two, each half fits.
 // Phase A: time-jets forward only → external-load cotangents x̄_gp = dL·fₑ (BeamElement.jl:28-58,169) and v̄ₛₘ = Σ dL·mₑ (:56-57).
-template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
-                                                         bool udof, const typename N::TU* U0, Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb) {
+// DD (SD number types, ND = 3): also the partials of the cotangents with respect to the ACCELERATIONS of the lane's two dofs, xb2/vsmb2 (value
+// parts unused).  Along q(t) = X₀+X′t+X″t²/2, ∂/∂X″ⱼ f(q(t)) = (t²/2)·(∂ⱼf)(q(t)), whose second time derivative at 0 is ∂ⱼf(X₀): ∂ẍ/∂X″ⱼ = ∂x/∂X₀ⱼ,
+// ∂r̈/∂X″ⱼ = ∂r/∂X₀ⱼ, ∂ẋ/∂X″ⱼ = 0 — all of it already in the order-0 partials of this lane, so DirectXUA needs no time-jet lanes seeded at X″.
+// (Exact also under the reference's x^0 rule, whose missing term depends on X₀ and X′ only.)
+template <int ND, class N, bool DD = false> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+                                                         bool udof, const typename N::TU* U0, Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb,
+                                                         Vec3<typename N::TS>* xb2 = nullptr, Vec3<typename N::TS>* vsmb2 = nullptr) {
     using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
     using NJ = NumJet<N>;
     using JR = typename NJ::TR; using JU = typename NJ::TU; using JS = typename NJ::TS;
@@ -495,6 +500,21 @@ template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, cons
         Vec3<S> fe = beam_fe(m, r0, x1, x2);
         const double dL = c.w * L;
         for (int i = 0; i < 3; ++i) { if (udof) fe[i] = fe[i] - U0[i]; xb[gp][i] = dL * fe[i]; }
+        if constexpr (DD) {
+            // fₑ is linear in ẍ: ∂fₑ/∂X″ = μ·∂x + r₀·(Cₐ∘(r₀ᵀ∂x)) with ∂x = ∂x/∂X₀ (BeamElement.jl:37-45), r₀ taken as plain values
+            using V = SD<false, false>;
+            Vec3<S> dx;
+            for (int i = 0; i < 3; ++i) {
+                dx[i] = ((fj.r(i, 0).c0 * p[0].c0 + fj.r(i, 1).c0 * p[1].c0) + fj.r(i, 2).c0 * p[2].c0) + fj.cs[i].c0;
+                dx[i].v = 0.;
+            }
+            Mat3<V> rv; for (int i = 0; i < 9; ++i) rv.a[i].v = r0.a[i].v;
+            Vec3<S> dl = mulv_t(rv, dx);
+            const double Ca[3] = {m.Ca1, m.Ca2, m.Ca3};
+            for (int i = 0; i < 3; ++i) dl[i] = Ca[i] * dl[i];
+            Vec3<S> dg = mulv(rv, dl);
+            for (int i = 0; i < 3; ++i) xb2[gp][i] = dL * (m.mu * dx[i] + dg[i]);
+        }
     }
     vsmb = Vec3<S>{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(0.)};
     if (ND >= 3) {
@@ -502,6 +522,14 @@ template <int ND, class N> MB_HD void beam_dyn_cotangents(const BeamGeo& g, cons
         TR m12 = (fj.r(0, 1).c0 * fj.r(0, 2).c2 + fj.r(1, 1).c0 * fj.r(1, 2).c2) + fj.r(2, 1).c0 * fj.r(2, 2).c2;
         TR m1l = (m.iota1 * L) * ((m21 - m12) * 0.5);
         for (int i = 0; i < 3; ++i) vsmb[i] = widen<S>(r0(i, 0) * m1l);
+        if constexpr (DD) {
+            using V = SD<false, false>;
+            auto val = [](const TR& x) { V r; r.v = x.v; return r; };
+            TR a21 = (val(fj.r(0, 2).c0) * fj.r(0, 1).c0 + val(fj.r(1, 2).c0) * fj.r(1, 1).c0) + val(fj.r(2, 2).c0) * fj.r(2, 1).c0;
+            TR a12 = (val(fj.r(0, 1).c0) * fj.r(0, 2).c0 + val(fj.r(1, 1).c0) * fj.r(1, 2).c0) + val(fj.r(2, 1).c0) * fj.r(2, 2).c0;
+            TR d1l = (m.iota1 * L) * ((a21 - a12) * 0.5);
+            for (int i = 0; i < 3; ++i) { (*vsmb2)[i] = widen<S>(val(r0(i, 0)) * d1l); (*vsmb2)[i].v = 0.; }
+        }
     }
 }
 // getresult (src/Output.jl:131-181) for EulerBeam3D, values only: the ☼/♢ requestables of residual (BeamElement.jl:151-174) and resultants (:28-64).
