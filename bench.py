@@ -137,7 +137,10 @@ def run_reference(args, rank, world):
     import muscade_b200 as mb
     from oracle import elements as OE
     OX = args.ox
-    cores = OE.max_threads()
+    # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1 for N>1, which must not shrink the reference arm (the other ranks idle)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if OE.max_threads() == 1 and os.environ.get("OMP_NUM_THREADS", "") not in ("", "1"):
+        cores = 1                                   # built without OpenMP
     nsample = max(1000, int(args.cpu_sample) * max(1, cores // 2))
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_rate(mb, OX, 500, cores)
