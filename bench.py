@@ -270,7 +270,9 @@ def run_sweepx(args, rank, world, local, dist):
                 "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
                 "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "traffic": None, "achieved": None, "frac": None}
         if flops:
-            roof["flop_per_element"] = flops["flop"]; roof["traffic"] = flops.get("dram_bytes_per_element")
+            roof["flop_per_element"] = flops["flop"]
+            if flops.get("dram_bytes_per_element"):      # measured DRAM bytes of one launch of the element kernel(s) (ncu --set full, profiles/)
+                roof["traffic"] = int(N * flops["dram_bytes_per_element"]); roof["traffic_unit"] = "bytes per launch (dram read+write, ncu)"
             roof["achieved"] = N * flops["flop"] / (el_ms * 1e-3) / 1e12
             roof["frac"] = roof["achieved"] / fp64_peak
             roof["fp64_inst_per_element"] = flops.get("fp64_inst")
