@@ -83,6 +83,26 @@ template <int ND> __device__ __forceinline__ void load_lane_state(const BeamGrou
     for (int i = 0; i < 3; ++i) { U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
 }
 constexpr int MB_NCOT = (NGP * 3 + 3) * 3;      // x̄_gp (4×3) and v̄ₛₘ (3) as SD<1,1>: 45 doubles per lane
+// workspace tile of one warp: [45][32] doubles — every store instruction is one contiguous 256-byte line, the tile is 11.5 KB; streaming
+// accesses (written once, read once) so that L2 keeps the spill lines of the resident threads
+__device__ __forceinline__ void store_cot(double* __restrict__ Wc, int64_t t, const Vec3<NumSD::TS>* xb, const Vec3<NumSD::TS>& vsmb) {
+    double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; __stcs(w + (k) * 32, xb[gp][i].v); __stcs(w + (k + 1) * 32, xb[gp][i].d0); __stcs(w + (k + 2) * 32, xb[gp][i].d1); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; __stcs(w + (k) * 32, vsmb[i].v); __stcs(w + (k + 1) * 32, vsmb[i].d0); __stcs(w + (k + 2) * 32, vsmb[i].d1); }
+}
+__device__ __forceinline__ void load_cot(const double* __restrict__ Wc, int64_t t, Vec3<NumSD::TS>* xb, Vec3<NumSD::TS>& vsmb) {
+    const double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; xb[gp][i].v = __ldcs(w + (k) * 32); xb[gp][i].d0 = __ldcs(w + (k + 1) * 32); xb[gp][i].d1 = __ldcs(w + (k + 2) * 32); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; vsmb[i].v = __ldcs(w + (k) * 32); vsmb[i].d0 = __ldcs(w + (k + 1) * 32); vsmb[i].d1 = __ldcs(w + (k + 2) * 32); }
+}
 // K2 phase A (ND ≥ 2): time-jet forward → cotangent workspace Wc[k][thread] (k-major: coalesced)
 template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
@@ -99,14 +119,7 @@ beam_cot_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__
     load_lane_state<ND>(g, st, nm, e, lane, Xu, Xv, U);
     Vec3<TS> xb[NGP], vsmb;
     beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
-    // workspace tile of one warp: [45][32] doubles — every store instruction is one contiguous 256-byte line, the tile is 11.5 KB
-    double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
-#pragma unroll
-    for (int gp = 0; gp < NGP; ++gp)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; w[(k) * 32] = xb[gp][i].v; w[(k + 1) * 32] = xb[gp][i].d0; w[(k + 2) * 32] = xb[gp][i].d1; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; w[(k) * 32] = vsmb[i].v; w[(k + 1) * 32] = vsmb[i].d0; w[(k + 2) * 32] = vsmb[i].d1; }
+    store_cot(Wc, t, xb, vsmb);
 }
 
 template <int ND, bool SPLIT>
@@ -125,13 +138,7 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     load_lane_state<ND>(g, st, nm, e, lane, Xu, Xv, U);
     if (SPLIT) {
         Vec3<TS> xb[NGP], vsmb;
-        const double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
-#pragma unroll
-        for (int gp = 0; gp < NGP; ++gp)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; xb[gp][i].v = w[(k) * 32]; xb[gp][i].d0 = w[(k + 1) * 32]; xb[gp][i].d1 = w[(k + 2) * 32]; }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; vsmb[i].v = w[(k) * 32]; vsmb[i].d0 = w[(k + 1) * 32]; vsmb[i].d1 = w[(k + 2) * 32]; }
+        load_cot(Wc, t, xb, vsmb);
         beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, R);      // v̄ₛₘ ≠ 0 only with accelerations
     } else {
         beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
@@ -146,8 +153,8 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
         a.x = R[i].d1 * g.scaleX[i]; a.y = R[i + 1].d1 * g.scaleX[i + 1];
         b.x = R[i].d0 * g.scaleX[i]; b.y = R[i + 1].d0 * g.scaleX[i + 1];
         bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
-        *reinterpret_cast<double2*>(ke + 12 * cu + i) = a;
-        *reinterpret_cast<double2*>(ke + 12 * cv + i) = b;
+        __stcs(reinterpret_cast<double2*>(ke + 12 * cu + i), a);       // streaming: written once, read once by K6 — keep L2 for the spill lines
+        __stcs(reinterpret_cast<double2*>(ke + 12 * cv + i), b);
     }
     if (lane == 0) {
 #pragma unroll
@@ -283,24 +290,6 @@ void launch_beam_results(int ND, const BeamGroupDev& g, const StateDev& st, doub
 //   lin            lanes (d≥1,e,l) and 2 U-lanes per Udof element: R is linear in the cotangents, so ∂R/∂X_d = J(X₀)ᵀ·∂c/∂X_d needs the forward
 //                  sweep in plain values only and the reverse sweep on the partials of c (∂c/∂U is known in closed form: −dL·scale.U).
 struct DirectStateDev { const double* X[3]; const double* U0; };
-__device__ __forceinline__ void store_cot(double* __restrict__ Wc, int64_t t, const Vec3<NumSD::TS>* xb, const Vec3<NumSD::TS>& vsmb) {
-    double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
-#pragma unroll
-    for (int gp = 0; gp < NGP; ++gp)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; w[(k) * 32] = xb[gp][i].v; w[(k + 1) * 32] = xb[gp][i].d0; w[(k + 2) * 32] = xb[gp][i].d1; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; w[(k) * 32] = vsmb[i].v; w[(k + 1) * 32] = vsmb[i].d0; w[(k + 2) * 32] = vsmb[i].d1; }
-}
-__device__ __forceinline__ void load_cot(const double* __restrict__ Wc, int64_t t, Vec3<NumSD::TS>* xb, Vec3<NumSD::TS>& vsmb) {
-    const double* w = Wc + (t >> 5) * (int64_t)(MB_NCOT * 32) + (t & 31);
-#pragma unroll
-    for (int gp = 0; gp < NGP; ++gp)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { const int k = (gp * 3 + i) * 3; xb[gp][i].v = w[(k) * 32]; xb[gp][i].d0 = w[(k + 1) * 32]; xb[gp][i].d1 = w[(k + 2) * 32]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { const int k = (NGP * 3 + i) * 3; vsmb[i].v = w[(k) * 32]; vsmb[i].d0 = w[(k + 1) * 32]; vsmb[i].d1 = w[(k + 2) * 32]; }
-}
 // state of one lane: values of X₀..X_{ND-1}, U₀ and the lane's two seeds (rotation dof l, translation dof l) at derivative order d (d<0: no seed)
 template <int ND> __device__ __forceinline__ void load_direct_state(const BeamGroupDev& g, const DirectStateDev& st, int64_t e, int d, int l,
                                                NumSD::TU (*Xu)[6], NumSD::TR (*Xv)[6], NumSD::TU* U) {
