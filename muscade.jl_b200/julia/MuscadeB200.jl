@@ -130,4 +130,39 @@ function host_contributions!(out::AssemblySweepXB200{OX}, dis, model, state, mis
     end
 end
 
+# ---- device-resident Newton update (SURVEY §8f-1): state.X stays in HBM between iterations -----------------------------------------------
+"""
+    upload_state!(out,state) / download_state!(state,out)
+    Newmarkβdecrement!(out::AssemblySweepXB200{OX},Δx,firstiter) -> (Σ Δx², Σ Lλ²)
+
+Device versions of `Newmarkβdecrement!{OX}` (src/SweepX.jl:98-132) with `getdof!`/`decrement!` (src/Assemble.jl:206-233) for
+`Xdofgr = allXdofs(model,dis)`; same rounding sequence as the reference.  With the state resident, `assemble!` passes `C_NULL` for `X0`.
+"""
+function upload_state!(out::AssemblySweepXB200{OX}, state, dis) where {OX}
+    X = state.X
+    check(out.h, ccall((:mb_sweepx_set_dof_scale, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}), out.h, dis.scaleX))
+    GC.@preserve X check(out.h, ccall((:mb_sweepx_set_state, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
+        out.h, OX, X[1], OX ≥ 1 ? pointer(X[2]) : C_NULL, OX ≥ 2 ? pointer(X[3]) : C_NULL, C_NULL))
+end
+function download_state!(state, out::AssemblySweepXB200{OX}) where {OX}
+    X = state.X
+    GC.@preserve X check(out.h, ccall((:mb_sweepx_get_state, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
+        out.h, OX, X[1], OX ≥ 1 ? pointer(X[2]) : C_NULL, OX ≥ 2 ? pointer(X[3]) : C_NULL))
+end
+function Newmarkβdecrement!(out::AssemblySweepXB200{OX}, Δx::Vector{𝕣}, firstiter::Bool) where {OX}
+    c = out.c;  newmark = 𝕣[c.a₁, c.a₂, c.a₃, c.b₁, c.b₂, c.b₃, c.Δt]
+    Δx², Lλ² = Ref(0.), Ref(0.)
+    check(out.h, ccall((:mb_sweepx_newmark_decrement, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{𝕣}, Ptr{𝕣}, Ref{𝕣}, Ref{𝕣}),
+        out.h, OX, firstiter, Δx, newmark, Δx², Lλ²))
+    return Δx²[], Lλ²[]
+end
+
+# ---- getresult for all EulerBeam3D elements of a type (src/Output.jl:131-181): 77×nele matrix, layout in include/muscade_b200.h ---------------
+function beam_results(out::AssemblySweepXB200{OX}, ieletyp::Integer, nele::Integer) where {OX}
+    res = Matrix{𝕣}(undef, 77, nele)
+    check(out.h, ccall((:mb_beam_results, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
+        out.h, ieletyp, OX, C_NULL, C_NULL, C_NULL, res))          # C_NULL: at the device-resident state
+    return res          # res[1,:] ε, res[2:10,:] rₛₘ, res[11:13,:] κ, then per Gauss point x, κgp, fᵢ, mᵢ, fₑ, mₑ
+end
+
 end # module
