@@ -78,8 +78,12 @@ def test_static_beam_analysis(mb):
         assert np.array_equal(dev[k].X[0], states[k].X[0]), k
 
 
-def test_static_assembly_with_boundary_elements_parity(mb):
-    """one assemble!{:iter} of the full 8-type model at a non-trivial state: Lλ, nzval, pattern vs the oracle"""
+@pytest.mark.parametrize("pipe", [False, True])
+def test_static_assembly_with_boundary_elements_parity(mb, pipe, monkeypatch):
+    """one assemble!{:iter} of the full 8-type model at a non-trivial state: Lλ, nzval, pattern vs the oracle (pipe: the chunked host-buffer
+    path forced on this small model — the host-evaluated Hold/DofLoad types must not hold back the completion prefixes)"""
+    if pipe:
+        monkeypatch.setenv("MB_E2E_MIN_NNZ", "0"); monkeypatch.setenv("MB_E2E_CHUNKS", "3")
     model, nod, coord = build(mb)
     state = mb.initialize(model)
     dis = state.dis
