@@ -98,6 +98,10 @@ int32_t mb_direct_get_asm(mb_handle* h, int32_t ieletyp, int32_t which, int64_t*
 int32_t mb_direct_set_state(mb_handle* h, int64_t step, const double* X0, const double* X1, const double* X2, const double* U0);
 /* state[step].time = t0 + step·dt (default t0 = 0); only Bar3D's weight ramp reads the time (toolbox/BarElement.jl:144) */
 int32_t mb_direct_set_time0(mb_handle* h, double t0);
+/* model.scaleΛ (setscale!(model;Λscale), src/ModelDescription.jl:287-299): scale.Λ = scale.X·Λscale (src/Assemble.jl:55). Read by the element types
+ * that take DirectXUA's second-order path — SoilContact, which does not declare no_second_order (src/DirectXUA.jl:152-171): L1[Λ] = R·scale.Λ,
+ * L1[X][der] = Λᵀ∂R/∂X_der, L2[Λ,X] scaled by scale.Λ·scale.X. state[step].Λ comes from mb_direct_set_lambda. Default 1. */
+int32_t mb_direct_set_lambda_scale(mb_handle* h, double lambda_scale);
 /* assemblebig!{:matrices}: evaluates the steps [eval_lo,eval_hi) (eval_lo<0: all stored steps, i.e. owned + halo recomputed locally),
  * then, if build_big, forms the owned columns of Lvv (nzval) and rows of Lv; host outputs may be NULL (results stay on the device). */
 int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32_t build_big, double* Lvv_nzval, double* Lv, mb_errinfo* where);

@@ -27,12 +27,12 @@ int launch_bar_direct(int ND, const BarGroupDev& g, const DirectStateDev& st, do
     else bar_direct_kernel<3><<<nb, 128, 0, s>>>(g, st, t, dR, R, nanflag, nanbase);
     return 1;
 }
-int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
-                       unsigned long long nanbase, cudaStream_t s) {
+int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, const double* Lam, double lamscale, double* dR, double* R, double* GX,
+                       unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s) {
     const unsigned nb = (unsigned)((g.nele + 255) / 256);
-    if (ND == 1) soil_direct_kernel<1><<<nb, 256, 0, s>>>(g, st, dR, R, nanflag, nanbase);
-    else if (ND == 2) soil_direct_kernel<2><<<nb, 256, 0, s>>>(g, st, dR, R, nanflag, nanbase);
-    else soil_direct_kernel<3><<<nb, 256, 0, s>>>(g, st, dR, R, nanflag, nanbase);
+    if (ND == 1) soil_direct_kernel<1><<<nb, 256, 0, s>>>(g, st, Lam, lamscale, dR, R, GX, nanflag, nanbase);
+    else if (ND == 2) soil_direct_kernel<2><<<nb, 256, 0, s>>>(g, st, Lam, lamscale, dR, R, GX, nanflag, nanbase);
+    else soil_direct_kernel<3><<<nb, 256, 0, s>>>(g, st, Lam, lamscale, dR, R, GX, nanflag, nanbase);
     return 1;
 }
 }  // namespace mb

@@ -172,30 +172,39 @@ bar_direct_kernel(BarGroupDev g, DirectStateDev st, double t, double* __restrict
     }
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
-// SoilContact: R = K·(x − z₀e₃) + C·x′ below z₀, else 0 with no partials (SoilContact.jl:10-20) — closed form
+// SoilContact declares no `no_second_order`, so in DirectXUA it takes the second-order path (DirectXUA.jl:152-171): L = Λ∘R with
+// revariate{2}((;Λ,X,U),(;Λ=scale.Λ,X=scale.X,…)), scale.Λ = scale.X·Λscale (Assemble.jl:55).  R = K·(x − z₀e₃) + C·x′ below z₀, else 0 with no
+// partials (SoilContact.jl:10-20), so in closed form:  ∂L/∂Λᵢ = Rᵢ·sΛᵢ → L1[Λ];  ∂L/∂X₀ᵢ = ΛᵢKᵢ·sXᵢ, ∂L/∂X′ᵢ = ΛᵢCᵢ·sXᵢ → L1[X][1], L1[X][2];
+// ∂²L/∂Λᵢ∂X₀ᵢ = Kᵢ·sΛᵢ·sXᵢ, ∂²L/∂Λᵢ∂X′ᵢ = Cᵢ·sΛᵢ·sXᵢ → L2[Λ,X] and, transposed, L2[X,Λ];  L2[X,X] = L2[Λ,Λ] = 0 (R is linear).
+// GX[(e·3+i)·ND+d] receives the L1[X][d+1] contribution of element dof i.
 template <int ND>
-__global__ void soil_direct_kernel(SoilGroupDev g, DirectStateDev st, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag,
-                                   unsigned long long nanbase) {
+__global__ void soil_direct_kernel(SoilGroupDev g, DirectStateDev st, const double* __restrict__ Lam, double lamscale, double* __restrict__ dR,
+                                   double* __restrict__ R, double* __restrict__ GX, unsigned long long* nanflag, unsigned long long nanbase) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= g.nele) return;
     const double z0 = g.par[e * 5], Kh = g.par[e * 5 + 1], Kv = g.par[e * 5 + 2], Ch = g.par[e * 5 + 3], Cv = g.par[e * 5 + 4];
-    double x[3], xp[3];
+    double x[3], xp[3], lam[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { const int32_t d = g.idxX[e * 3 + i]; x[i] = st.X[0][d]; xp[i] = (ND >= 2) ? st.X[1][d] : 0.; }
+    for (int i = 0; i < 3; ++i) { const int32_t d = g.idxX[e * 3 + i]; x[i] = st.X[0][d]; xp[i] = (ND >= 2) ? st.X[1][d] : 0.; lam[i] = Lam[d]; }
     const bool contact = x[2] < z0;
     const double K[3] = {Kh, Kh, Kv}, Cc[3] = {Ch, Ch, Cv};
     bool bad = false;
     double* out = dR + e * (int64_t)(3 * 3 * ND);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
+        const double sL = g.scaleX[i] * lamscale;
         const double r = contact ? (K[i] * (i == 2 ? x[2] - z0 : x[i]) + Cc[i] * xp[i]) : 0.;
-        R[e * 3 + i] = r; bad |= (r != r);
+        R[e * 3 + i] = r * sL; bad |= (r != r);
 #pragma unroll
-        for (int d = 0; d < ND; ++d)
+        for (int d = 0; d < ND; ++d) {
+            const double coef = (contact && d < 2) ? (d == 0 ? K[i] : Cc[i]) : 0.;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) out[(3 * d + j) * 3 + i] = (contact && i == j && d < 2) ? (d == 0 ? K[i] : Cc[i]) * g.scaleX[j] : 0.;
+            for (int j = 0; j < 3; ++j) out[(3 * d + j) * 3 + i] = (i == j) ? coef * sL * g.scaleX[j] : 0.;
+            const double gx = lam[i] * coef * g.scaleX[i];
+            GX[(e * 3 + i) * ND + d] = gx; bad |= (gx != gx);
+        }
     }
-    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+    if (bad && contact) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
 }  // namespace mb

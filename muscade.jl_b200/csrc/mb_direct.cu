@@ -16,8 +16,8 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
                                          unsigned long long nanbase, double* Wc, cudaStream_t s);
 int launch_bar_direct(int ND, const BarGroupDev& g, const DirectStateDev& st, double t, double* dR, double* R, unsigned long long* nanflag,
                       unsigned long long nanbase, cudaStream_t s);
-int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
-                       unsigned long long nanbase, cudaStream_t s);
+int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, const double* Lam, double lamscale, double* dR, double* R, double* GX,
+                       unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s);
 }
 
 namespace {
@@ -32,7 +32,7 @@ struct PairPat {                  // one class-pair pattern of prepare(AssemblyD
 };
 
 constexpr int MAXG = 8;
-struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; };
+struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; int64_t gxbase[MAXG]; };
 
 // ---------------------------------------------------------------------------------------------------------------- pattern build
 __global__ void pair_keys_kernel(int64_t nele, int ni, const int32_t* __restrict__ idxR, int nj, const int32_t* __restrict__ idxC, uint64_t nrows,
@@ -121,6 +121,18 @@ __global__ void gather_l1_kernel(int64_t ndof, const uint32_t* __restrict__ vsta
     for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) acc += R[vsrc[s]];
     out[d] = acc;
 }
+// L1[X][der] of one step from the second-order element types (∂L/∂X_der = Λᵀ∂R/∂X_der): GX[q·nd+der], q = contributor entry (element dof)
+__global__ void gather_l1x_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ GX, int nd,
+                                  double* __restrict__ out) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    double acc[3] = {0., 0., 0.};
+    for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) {
+        const double* q = GX + (int64_t)vsrc[s] * nd;
+        for (int der = 0; der < nd; ++der) acc[der] += q[der];
+    }
+    for (int der = 0; der < nd; ++der) out[der * ndof + d] = acc[der];
+}
 __global__ void vec_keys_kernel(int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -148,6 +160,8 @@ struct BigDev {
     const double *LX, *XL, *LU, *UL, *L1L;        // stored per-step blocks
     int64_t sLX, sLU, sUL;         // strides per stored step
     const double* hostc;           // host-evaluated single-dof costs per stored step: gX(nX) hX(nX) gU(nU) hU(nU), or nullptr
+    const double* L1X;             // L1[X][der] per stored step [step][der][nX] from second-order element types, or nullptr
+    int64_t ehi;
 };
 __device__ __forceinline__ int pat_of(int ca, int cb) { return (ca == 2 ? 2 : 0) + (cb == 2 ? 1 : 0); }   // class 2 = U
 // finitediff(order,n,s) (src/FiniteDifferences.jl:2-31): weight of offset ds at 0-based step s, or 0 with found=false
@@ -327,7 +341,23 @@ __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) 
     decode_col(B, c, step, cls, lc);
     double v = 0.;
     if (cls == 0) v = B.L1L[(step - B.elo) * B.nX + lc];               // addin!(Lvasm,Lv,L1[Λ][1],Λblk)  (DirectXUA.jl:332-341)
-    else if (B.hostc) v = B.hostc[(step - B.elo) * 2 * (B.nX + B.nU) + (cls == 1 ? 0 : 2 * B.nX) + lc];   // L1[X][1], L1[U][1] of cost elements
+    else {
+        if (B.hostc) v = B.hostc[(step - B.elo) * 2 * (B.nX + B.nU) + (cls == 1 ? 0 : 2 * B.nX) + lc];   // L1[X][1], L1[U][1] of cost elements
+        if (cls == 1 && B.L1X) {
+            // Lv[X block of step] += Σ_s Σ_der w·Δt^(−der)·L1[X][der](state s), w = finitediff(der,nstep,s) at offset step−s (DirectXUA.jl:332-341)
+            double acc = 0.;
+            for (int64_t s = step - 2; s <= step + 2; ++s) {
+                if (s < B.elo || s >= B.ehi) continue;
+                double sc = 1.;
+                for (int der = 0; der <= B.OX; ++der) {
+                    double w;
+                    if (fd_weight(der, B.nstep, s, step - s, w)) acc += B.L1X[((s - B.elo) * (B.OX + 1) + der) * B.nX + lc] * (w * sc);
+                    sc /= B.dt;
+                }
+            }
+            v = (B.hostc ? v : 0.) + acc;
+        }
+    }
     Lv[c] = v;
 }
 // L2[X,X][1,1] / L2[U,U][1,1] of host-evaluated single-dof costs: one diagonal entry per dof, added to the (step,step) block
@@ -415,6 +445,7 @@ struct DirectData {
     double *scL = nullptr, *scX = nullptr, *scU = nullptr, *dvbuf = nullptr; int64_t dvlen = 0;
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;   // sparser! result
     double* hostc = nullptr; unsigned long long* missing = nullptr;
+    double *GX = nullptr, *L1X = nullptr; uint32_t *vstart2 = nullptr, *vsrc2 = nullptr; int64_t ngx = 0; double lamscale = 1.;   // second-order types
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
     int32_t *bcolptr = nullptr, *browval = nullptr;
     int64_t ncol = 0, nnzbig = 0; int maxb = 0;         // maxb: most blocks in one block column
@@ -477,7 +508,7 @@ static BigDev make_bigdev(const DirectData* D) {
     for (int p = 0; p < 4; ++p) { B.pc[p] = D->pat[p].colptr0; B.pr[p] = D->pat[p].rowval0; B.pnnz[p] = D->pat[p].nnz; }
     B.LX = D->LX; B.XL = D->XL; B.LU = D->LU; B.UL = D->UL; B.L1L = D->L1L;
     B.sLX = (int64_t)(D->OX + 1) * D->pat[P_XX].nnz; B.sLU = D->pat[P_XU].nnz; B.sUL = D->pat[P_UX].nnz;
-    B.hostc = D->hostc;
+    B.hostc = D->hostc; B.L1X = D->L1X; B.ehi = D->ehi;
     return B;
 }
 
@@ -536,6 +567,36 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
         h->launches++;
         CK(cudaStreamSynchronize(st)); cudaFree(tmp);
         dfree(h, keys); dfree(h, keys2); dfree(h, vals);
+    }
+    // second-order element types (SoilContact): contributor lists of their element dofs for L1[X][der]
+    {
+        int64_t nq = 0;
+        for (size_t ig = 0; ig < h->groups.size(); ++ig) { D->G.gxbase[ig] = nq; if (h->groups[ig].kind == G_SOIL) nq += h->groups[ig].nele * h->groups[ig].nx; }
+        D->ngx = nq;
+        if (nq > 0) {
+            CK(dalloc(h, &D->vstart2, ndofX + 1)); CK(dalloc(h, &D->vsrc2, nq)); CK(dalloc(h, &D->GX, nq * (OX + 1)));
+            CK(cudaMemsetAsync(D->vstart2, 0, (ndofX + 1) * sizeof(uint32_t), st));
+            uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
+            CK(dalloc(h, &keys, nq)); CK(dalloc(h, &keys2, nq)); CK(dalloc(h, &vals, nq));
+            for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+                const Group& g = h->groups[ig];
+                if (g.kind != G_SOIL || g.nele == 0) continue;
+                vec_keys_kernel<<<nblk(g.nele * g.nx, 256), 256, 0, st>>>(g.nele * g.nx, g.idxX, keys, vals, (uint32_t)D->G.gxbase[ig]);
+                h->launches++;
+            }
+            int end_bit = 1; while (end_bit < 32 && ((uint64_t)ndofX >> end_bit)) ++end_bit;
+            void* tmp = nullptr; size_t tmpsz = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, D->vsrc2, nq, 0, end_bit, st));
+            CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+            CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, D->vsrc2, nq, 0, end_bit, st));
+            vstart2_kernel<<<nblk(nq, 256), 256, 0, st>>>(nq, keys2, ndofX, D->vstart2);
+            h->launches++;
+            CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+            dfree(h, keys); dfree(h, keys2); dfree(h, vals);
+            const int64_t nsx = D->ehi - D->elo;
+            CK(dalloc(h, &D->L1X, nsx * (OX + 1) * ndofX));
+            CK(cudaMemsetAsync(D->L1X, 0, (size_t)(nsx * (OX + 1) * ndofX) * sizeof(double), st));
+        }
     }
     // buffers
     const int64_t ns = D->ehi - D->elo;
@@ -634,7 +695,7 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
             if (g.kind == G_SOIL) {
                 SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
                 for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
-                h->launches += launch_soil_direct(nd, gd, sd, dR, R, h->nanflag, nanbase, st);
+                h->launches += launch_soil_direct(nd, gd, sd, D->Lam + k * D->nX, D->lamscale, dR, R, D->GX + D->G.gxbase[ig] * nd, h->nanflag, nanbase, st);
                 continue;
             }
             BeamGroupDev gd;
@@ -659,10 +720,16 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         if (UX.nnz) { gather_xu_kernel<<<nblk(UX.nnz, 256), 256, 0, st>>>(UX.nnz, UX.cstart, UX.src, D->G, nd, 1, D->dR, D->UL + k * UX.nnz); h->launches++; }
         gather_l1_kernel<<<nblk(D->nX, 256), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX);
         h->launches++;
+        if (D->ngx) { gather_l1x_kernel<<<nblk(D->nX, 256), 256, 0, st>>>(D->nX, D->vstart2, D->vsrc2, D->GX, nd, D->L1X + k * nd * D->nX); h->launches++; }
     }
     return MB_OK;
 }
 
+int32_t mb_direct_set_lambda_scale(mb_handle* h, double lambda_scale) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    h->direct->lamscale = lambda_scale;
+    return MB_OK;
+}
 int32_t mb_direct_set_time0(mb_handle* h, double t0) {
     if (!h || !h->direct) return MB_ERR_ARG;
     h->direct->t0 = t0;

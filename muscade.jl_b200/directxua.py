@@ -88,6 +88,9 @@ class DirectEngine(Engine):
         """state[step].time = t0 + step·dt"""
         check(self.h, self.L.mb_direct_set_time0(self.h, float(t0)))
 
+    def set_lambda_scale(self, Λscale):
+        check(self.h, self.L.mb_direct_set_lambda_scale(self.h, float(Λscale)))
+
     def set_state(self, step, X, U0=None):
         X = [_f64(x) for x in X]
         check(self.h, self.L.mb_direct_set_state(self.h, int(step), ptr(X[0]), ptr(X[1]) if len(X) > 1 else None, ptr(X[2]) if len(X) > 2 else None, ptr(_f64(U0))))
@@ -184,6 +187,7 @@ def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
             muscadeerror("DirectXUA on the device supports EulerBeam3D, Bar3D, SoilContact and SingleDofCost element types in this version: %s" % (et.key,))
     eng.direct_prepare(OX, OU, model.getndof("X"), model.getndof("U"), nstep, lo, hi, dt)
     eng.set_time0(t0)
+    eng.set_lambda_scale(model.scaleΛ)
     return eng
 
 

@@ -373,3 +373,41 @@ def beam_results(elem, X, U=None):
     if rc:
         raise ValueError("orc_beam_results: %d" % rc)
     return out
+
+
+def direct_addin_soil_second_order(soil, idxX, OX, X, Lam, scaleX, lam_scale, P, ityp, out):
+    """addin!{:matrices}(out::AssemblyDirect{OX,OU,0},…,no_second_order::Val{false},…) (src/DirectXUA.jl:152-171 → :121-150) for SoilContact, which does
+    not declare `no_second_order`: L = Λ∘R(X) (Assemble.jl:721-726) differentiated to second order over (Λ, X₀, X′, X″) seeded by
+    revariate{2} with scales (Λ=scale.Λ, X=scale.X), scale.Λ = scale.X·Λscale (Assemble.jl:55).  R (SoilContact.jl:10-20) is linear in (x,x′) inside
+    the contact branch and identically zero outside, so the partials are written out instead of carried by nested duals:
+        ∂L/∂Λᵢ = Rᵢ·sΛᵢ            ∂L/∂X₀ᵢ = Λᵢ·Kᵢ·sXᵢ       ∂L/∂X′ᵢ = Λᵢ·Cᵢ·sXᵢ      ∂L/∂X″ᵢ = 0
+        ∂²L/∂Λᵢ∂X₀ᵢ = Kᵢ·sΛᵢ·sXᵢ     ∂²L/∂Λᵢ∂X′ᵢ = Cᵢ·sΛᵢ·sXᵢ   all other second partials 0
+    scattered by DirectXUA_lagrangian_addition! into L1[Λ][1], L1[X][der], L2[Λ,X][1,der], L2[X,Λ][der,1] (the zero blocks add nothing).
+    `out` as direct_out_zeros, plus out["L1"][2] of shape (OX+1, nX) created on demand."""
+    from .pattern import arrnum
+    nd = OX + 1
+    nX = P["ndof"][0]
+    if 2 not in out["L1"]:
+        out["L1"][2] = np.zeros((nd, nX))
+    asm = P["asm"]
+    aL = asm[arrnum(1)][ityp]; aX = asm[arrnum(2)][ityp]; aLX = asm[arrnum(1, 2)][ityp]; aXL = asm[arrnum(2, 1)][ityp]
+    for e in range(idxX.shape[0]):
+        z0, Kh, Kv, Ch, Cv = soil[e]
+        ix = idxX[e] - 1
+        x = X[0][ix]; xp = X[1][ix] if OX >= 1 else np.zeros(3)
+        lam = Lam[ix]
+        contact = x[2] < z0
+        K = np.array([Kh, Kh, Kv]); C = np.array([Ch, Ch, Cv])
+        R = (K * (x - np.array([0., 0., z0])) + C * xp) if contact else np.zeros(3)
+        sX = scaleX; sL = scaleX * lam_scale
+        coef = [K if contact else np.zeros(3), C if contact else np.zeros(3), np.zeros(3)]
+        for i in range(3):
+            if aL[i, e]: out["L1"][1][aL[i, e] - 1] += R[i] * sL[i]
+            for d in range(nd):
+                if aX[i, e]: out["L1"][2][d, aX[i, e] - 1] += lam[i] * coef[d][i] * sX[i]
+                v = coef[d][i] * sL[i] * sX[i]
+                k = aLX[i + 3 * i, e]
+                if k: out["L2"][(1, 2)][d, k - 1] += v
+                k = aXL[i + 3 * i, e]
+                if k: out["L2"][(2, 1)][d, k - 1] += v
+    return out

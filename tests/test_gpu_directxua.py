@@ -120,10 +120,11 @@ def test_directxua_beam_bar_soil(mb, OX):
     rmat = mb.AxisymmetricBarCrossSection(EA=500., mu=1.5, w=3., Cat=.2, Clt=.3, Cqt=.4, Can=2., Cln=.6, Cqn=1.2)
     mb.addelement(model, mb.Bar3D, mesh[N // 2:], mat=rmat, Udof=True)
     mb.addelement(model, mb.SoilContact, nod[: N // 2, None], z0=0.0, Kh=30., Kv=200., Ch=3., Cv=7.)
-    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)))
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)), Λscale=7.)
     st0 = mb.initialize(model); dis = st0.dis
     nX, nU, nA = model.getndof(("X", "U", "A"))
     st = states(mb, nX, nU, nstep)
+    Lam = [mb.synthetic.uniform_pm1(500 + s, nX) for s in range(nstep)]          # SoilContact takes the second-order path: Λ enters L1[X]
     odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
     P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
     big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
@@ -134,8 +135,7 @@ def test_directxua_beam_bar_soil(mb, OX):
         OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, OX, OU, X[: OX + 1], [U], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0, out=o)
         OE.direct_addin_generic(lambda e, xv, sd, uv, usd: OE.bar_residual(bars[e], xv, sd, uv, usd, t=t0 + s * dt)[:2], 6, 3, dis.dis[1].X, dis.dis[1].U,
                                 OX, OU, X[: OX + 1], [U], dis.dis[1].scaleX, dis.dis[1].scaleU, P, 1, o)
-        OE.direct_addin_generic(lambda e, xv, sd, uv, usd: OE.soil_residual(soil[e], xv, sd)[:2], 3, 0, dis.dis[2].X, None,
-                                OX, OU, X[: OX + 1], [U], dis.dis[2].scaleX, None, P, 2, o)
+        OE.direct_addin_soil_second_order(soil, dis.dis[2].X, OX, X[: OX + 1], Lam[s], dis.dis[2].scaleX, model.scaleΛ, P, 2, o)
         outs.append(o)
     nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
     eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, t0=t0)
@@ -145,8 +145,11 @@ def test_directxua_beam_bar_soil(mb, OX):
         assert np.array_equal(eng.direct_asm(ityp, 0).T, P["asm"][OP.arrnum(1, 2)][ityp - 1])
     for s, (X, U) in enumerate(st):
         eng.set_state(s, X[: OX + 1], U)
+        eng.set_lambda(s, Lam[s])
     Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
     eng.direct_assemble(Lvv=Lvv, Lv=Lvec)
+    W = 2 * nX + nU
+    assert np.abs(Lvec.reshape(nstep, W)[:, nX: 2 * nX]).max() > 0            # L1[X] of the soil springs reached Lv
     for s in (0, 4):
         o = outs[s]
         scale = np.abs(o["L2"][(1, 2)]).max()
