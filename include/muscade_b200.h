@@ -120,6 +120,11 @@ int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int3
  * because `cost` is a user closure): dense per-dof gradient (→ L1[X][1], L1[U][1]) and second derivative (→ diagonal of L2[X,X][1,1],
  * L2[U,U][1,1]) vectors, already multiplied by scale / scale²; NULL = zeros. Merged into Lv / Lvv by mb_direct_assemble. */
 int32_t mb_direct_set_host_cost(mb_handle* h, int64_t step, const double* gX, const double* hX, const double* gU, const double* hU);
+/* Host-evaluated X-class element types (Hold, DofLoad, DofConstraint — user closures, added with mb_add_host_elements) in DirectXUA's second-order
+ * branch (src/DirectXUA.jl:152-171), for residuals linear in X (so L2[X,X] = 0), one stored step at a time:
+ *   R  [nele][nx]          Rᵢ·scale.Λᵢ → L1[Λ];     GX [nele][nx][nd]   Σₖ Λₖ·∂Rₖ/∂X_der,ᵢ·scale.Xᵢ → L1[X][der+1];
+ *   dR [nele][nd·nx][nx]   ∂Rᵢ/∂X_der,ⱼ·scale.Λᵢ·scale.Xⱼ at [(nx·der+j)][i] → L2[Λ,X][1,der+1] and, transposed, L2[X,Λ][der+1,1].  NULL = zeros. */
+int32_t mb_direct_set_host_elements(mb_handle* h, int64_t step, int32_t ieletyp, const double* R, const double* dR, const double* GX);
 int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
 int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
 int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda);

@@ -66,6 +66,7 @@ SYMBOLS = {
     "mb_direct_set_time0": (C.c_int32, [H, C.c_double]),
     "mb_direct_set_lambda_scale": (C.c_int32, [H, C.c_double]),
     "mb_direct_set_host_cost": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_direct_set_host_elements": (C.c_int32, [H, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_direct_sparser": (C.c_int32, [H, C.c_double, C.POINTER(C.c_int64)]),
     "mb_direct_get_sparse": (C.c_int32, [H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_direct_set_lambda": (C.c_int32, [H, C.c_int64, C.c_void_p]),

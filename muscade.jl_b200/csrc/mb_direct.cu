@@ -445,6 +445,7 @@ struct DirectData {
     double *scL = nullptr, *scX = nullptr, *scU = nullptr, *dvbuf = nullptr; int64_t dvlen = 0;
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;   // sparser! result
     double* hostc = nullptr; unsigned long long* missing = nullptr;
+    std::vector<double*> hoststore;                     // per host-evaluated type: [stored step][R(nele·nx) | dR(nele·nx·nx·nd) | GX(nele·nx·nd)] or nullptr
     double *GX = nullptr, *L1X = nullptr; uint32_t *vstart2 = nullptr, *vsrc2 = nullptr; int64_t ngx = 0; double lamscale = 1.;   // second-order types
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
     int32_t *bcolptr = nullptr, *browval = nullptr;
@@ -523,7 +524,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     ARG(OX >= 0 && OX <= 2 && OU >= 0 && OU <= 2 && ndofX >= 1 && ndofU >= 0 && nstep >= 1 && step_lo >= 0 && step_hi > step_lo && step_hi <= nstep, "bad argument");
     ARG(bcolptr && browval, "block pattern missing");
     ARG((int)h->groups.size() <= MAXG, "too many element types");
-    for (const Group& g : h->groups) ARG(g.kind == G_BEAM || g.kind == G_BAR || g.kind == G_SOIL, "DirectXUA on the device: EulerBeam3D, Bar3D, SoilContact element types");
+    for (const Group& g : h->groups) ARG(g.kind == G_BEAM || g.kind == G_BAR || g.kind == G_SOIL || (g.kind == G_HOST && g.nu == 0), "DirectXUA on the device: EulerBeam3D, Bar3D, SoilContact and host-evaluated X-class element types");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     DirectData* D = new DirectData();
@@ -571,7 +572,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     // second-order element types (SoilContact): contributor lists of their element dofs for L1[X][der]
     {
         int64_t nq = 0;
-        for (size_t ig = 0; ig < h->groups.size(); ++ig) { D->G.gxbase[ig] = nq; if (h->groups[ig].kind == G_SOIL) nq += h->groups[ig].nele * h->groups[ig].nx; }
+        for (size_t ig = 0; ig < h->groups.size(); ++ig) { D->G.gxbase[ig] = nq; if (h->groups[ig].kind == G_SOIL || h->groups[ig].kind == G_HOST) nq += h->groups[ig].nele * h->groups[ig].nx; }
         D->ngx = nq;
         if (nq > 0) {
             CK(dalloc(h, &D->vstart2, ndofX + 1)); CK(dalloc(h, &D->vsrc2, nq)); CK(dalloc(h, &D->GX, nq * (OX + 1)));
@@ -580,7 +581,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
             CK(dalloc(h, &keys, nq)); CK(dalloc(h, &keys2, nq)); CK(dalloc(h, &vals, nq));
             for (size_t ig = 0; ig < h->groups.size(); ++ig) {
                 const Group& g = h->groups[ig];
-                if (g.kind != G_SOIL || g.nele == 0) continue;
+                if ((g.kind != G_SOIL && g.kind != G_HOST) || g.nele == 0) continue;
                 vec_keys_kernel<<<nblk(g.nele * g.nx, 256), 256, 0, st>>>(g.nele * g.nx, g.idxX, keys, vals, (uint32_t)D->G.gxbase[ig]);
                 h->launches++;
             }
@@ -692,6 +693,19 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
                 h->launches += launch_bar_direct(nd, gd, sd, D->t0 + (double)s * D->dt, dR, R, h->nanflag, nanbase, st);
                 continue;
             }
+            if (g.kind == G_HOST) {                // contributions uploaded by mb_direct_set_host_elements (zeros until then)
+                const int64_t nR = g.nele * g.nx, ndR = nR * g.nx * nd, nG = nR * nd, per = nR + ndR + nG;
+                const double* src = (ig < D->hoststore.size() && D->hoststore[ig]) ? D->hoststore[ig] + k * per : nullptr;
+                if (src) {
+                    CK(cudaMemcpyAsync(R, src, (size_t)nR * 8, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(dR, src + nR, (size_t)ndR * 8, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(D->GX + D->G.gxbase[ig] * nd, src + nR + ndR, (size_t)nG * 8, cudaMemcpyDeviceToDevice, st));
+                } else {
+                    CK(cudaMemsetAsync(R, 0, (size_t)nR * 8, st)); CK(cudaMemsetAsync(dR, 0, (size_t)ndR * 8, st));
+                    CK(cudaMemsetAsync(D->GX + D->G.gxbase[ig] * nd, 0, (size_t)nG * 8, st));
+                }
+                continue;
+            }
             if (g.kind == G_SOIL) {
                 SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
                 for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
@@ -774,6 +788,33 @@ int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
     CK(cudaSetDevice(h->device));
     if (colptr) { CK(cudaMemcpy(colptr, D->colptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
     if (rowval) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1; }
+    return MB_OK;
+}
+// Host-evaluated X-class element types (Hold, DofLoad, DofConstraint: user closures, default no_second_order = Val(false)) in the second-order
+// branch of DirectXUA (src/DirectXUA.jl:152-171), for residuals that are LINEAR in X (L2[X,X] = Λ·∂²R/∂X² = 0). Per stored step and element:
+//   R  [nele][nx]            Rᵢ·scale.Λᵢ                          → L1[Λ]
+//   dR [nele][nd·nx][nx]     ∂Rᵢ/∂X_der,ⱼ·scale.Λᵢ·scale.Xⱼ  (entry [(nx·der+j)][i]) → L2[Λ,X][1,der+1] and, transposed, L2[X,Λ][der+1,1]
+//   GX [nele][nx][nd]        Σₖ Λₖ·∂Rₖ/∂X_der,ᵢ·scale.Xᵢ        → L1[X][der+1]
+int32_t mb_direct_set_host_elements(mb_handle* h, int64_t step, int32_t ieletyp, const double* R, const double* dR, const double* GX) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi, "step not stored on this handle");
+    ARG(ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size() && h->groups[ieletyp - 1].kind == G_HOST, "not a host-evaluated element type");
+    CK(cudaSetDevice(h->device));
+    const size_t ig = (size_t)ieletyp - 1;
+    const Group& g = h->groups[ig];
+    const int nd = D->OX + 1;
+    const int64_t nR = g.nele * g.nx, ndR = nR * g.nx * nd, nG = nR * nd, per = nR + ndR + nG, ns = D->ehi - D->elo;
+    if (D->hoststore.size() < h->groups.size()) D->hoststore.resize(h->groups.size(), nullptr);
+    if (!D->hoststore[ig]) { CK(dalloc(h, &D->hoststore[ig], ns * per)); CK(cudaMemsetAsync(D->hoststore[ig], 0, (size_t)(ns * per) * 8, h->stream)); }
+    double* dst = D->hoststore[ig] + (step - D->elo) * per;
+    const double* src[3] = {R, dR, GX}; const int64_t n[3] = {nR, ndR, nG}; const int64_t off[3] = {0, nR, nR + ndR};
+    for (int q = 0; q < 3; ++q) {
+        if (n[q] == 0) continue;
+        if (src[q]) CK(cudaMemcpyAsync(dst + off[q], src[q], (size_t)n[q] * 8, cudaMemcpyDefault, h->stream));
+        else CK(cudaMemsetAsync(dst + off[q], 0, (size_t)n[q] * 8, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
     return MB_OK;
 }
 // host-evaluated single-dof costs of one stored step (SingleDofCost on X or U dofs, src/BasicElements.jl:198-208): gradient → L1[X][1] / L1[U][1],

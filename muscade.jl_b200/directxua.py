@@ -119,6 +119,9 @@ class DirectEngine(Engine):
         check(self.h, self.L.mb_direct_decrement(self.h, int(s0), int(s1), ptr(dv), ptr(d2)))
         return d2
 
+    def direct_set_host_elements(self, step, ityp, R, dR, GX):
+        check(self.h, self.L.mb_direct_set_host_elements(self.h, int(step), int(ityp), ptr(_f64(R)), ptr(_f64(dR)), ptr(_f64(GX))))
+
     def set_host_cost(self, step, gX=None, hX=None, gU=None, hU=None):
         check(self.h, self.L.mb_direct_set_host_cost(self.h, int(step), ptr(_f64(gX)), ptr(_f64(hX)), ptr(_f64(gU)), ptr(_f64(hU))))
 
@@ -173,6 +176,7 @@ def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
     hi = nstep if hi is None else hi
     eng = DirectEngine(device)
     eng.host_costs = []
+    eng.host_types = []
     for et, ed in zip(model.ele, dis.dis):
         udof = ed.U.shape[1] > 0
         if et.ElType.kind == "eulerbeam3d":
@@ -183,6 +187,9 @@ def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
             eng.add_soilcontact(et.eleobj, ed.X, ed.scaleX)
         elif et.ElType.kind == "hostcost":
             eng.host_costs.append((et, ed))          # evaluated by the host, merged by the device (set_host_cost)
+        elif et.ElType.kind == "host" and ed.U.shape[1] == 0 and ed.A.shape[1] == 0:
+            ityp = eng.add_host_elements(ed.X)       # Hold, DofLoad, …: second-order branch, evaluated by the host (set_host_elements)
+            eng.host_types.append((ityp, et, ed))
         else:
             muscadeerror("DirectXUA on the device supports EulerBeam3D, Bar3D, SoilContact and SingleDofCost element types in this version: %s" % (et.key,))
     eng.direct_prepare(OX, OU, model.getndof("X"), model.getndof("U"), nstep, lo, hi, dt)
@@ -204,6 +211,25 @@ def host_costs(eng, step, X0, U0, t):
         np.add.at(g[clas], idx, c1 * sc); np.add.at(h[clas], idx, c2 * sc * sc)
         total += float(c.sum())
     return g["X"], h["X"], g["U"], h["U"], total
+
+
+def host_elements(eng, step, X, Lam, t, Λscale):
+    """second-order branch (DirectXUA.jl:152-171) of the host-evaluated X-class types whose residual is linear in X (Hold, DofLoad):
+    L = Λ∘R ⇒ L1[Λ] = R·sΛ, L1[X][der] = (∂R/∂X_der)ᵀΛ·sX, L2[Λ,X][1,der] = ∂R/∂X_der·sΛ·sX (and its transpose in L2[X,Λ])"""
+    nd = eng.OX + 1
+    for ityp, et, ed in eng.host_types:
+        Xe = [X[d][ed.X - 1] for d in range(nd)]
+        R, K0, K1, K2 = et.ElType.residual(et.extra if et.extra is not None else et.eleobj, Xe, t)
+        nele, nx = R.shape
+        sX = ed.scaleX; sL = ed.scaleX * Λscale
+        lam = Lam[ed.X - 1]
+        dR = np.zeros((nele, nd * nx, nx)); GX = np.zeros((nele, nx, nd))
+        for der, K in enumerate([K0, K1, K2][:nd]):
+            if K is None:
+                continue
+            dR[:, nx * der: nx * (der + 1), :] = (K * sL[None, :, None] * sX[None, None, :]).transpose(0, 2, 1)      # [e][(nx·der+j)][i]
+            GX[:, :, der] = np.einsum("ek,eki->ei", lam, K) * sX[None, :]
+        eng.direct_set_host_elements(step, ityp, R * sL[None, :], dR, GX)
 
 
 def solve(OX, OU, initialstate, time, maxiter=50, maxΔλ=1e-5, maxΔx=1e-5, maxΔu=1e-5, verbose=False, device=0, sparser_rtol=1e-20):
@@ -229,10 +255,13 @@ def solve(OX, OU, initialstate, time, maxiter=50, maxΔλ=1e-5, maxΔx=1e-5, max
         maxΔ2 = np.array([maxΔλ, maxΔx, maxΔu]) ** 2
         Lv = np.zeros(eng.ncol)
         for it in range(1, maxiter + 1):
-            if eng.host_costs:
+            if eng.host_costs or eng.host_types:
                 for k in range(nstep):
-                    X, U, _ = eng.get_state(k)
-                    eng.set_host_cost(k, *host_costs(eng, k, X[0], U, time[k])[:4])
+                    X, U, Lam = eng.get_state(k)
+                    if eng.host_costs:
+                        eng.set_host_cost(k, *host_costs(eng, k, X[0], U, time[k])[:4])
+                    if eng.host_types:
+                        host_elements(eng, k, X, Lam, time[k], model.scaleΛ)
             eng.direct_assemble(Lv=Lv)
             eng.sparser(sparser_rtol)
             colptr, rowval, nzval = eng.sparse()

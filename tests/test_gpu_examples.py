@@ -232,3 +232,89 @@ def test_directxua_load_identification(mb):
             assert np.abs(sol[k].X[d] - ref).max() <= 1e-6 * max(1e-2, np.abs(ref).max()), (k, d)
         assert np.abs(sol[k].U[0] - ost[k]["U"][0]).max() <= 1e-6 * max(1e-2, np.abs(ost[k]["U"][0]).max())
     assert sol[0].SP["iter"] == it + 1                     # same number of Newton iterations
+
+
+def test_directxua_cantilever_with_holds(mb):
+    """solve(DirectXUA{2,0,0}) on a cantilever: EulerBeam3D{Udof} + six Hold at the root (host-evaluated, second-order branch of DirectXUA.jl:152-171:
+    L = Λ∘R ⇒ L1[Λ], L1[X] = (∂R/∂X)ᵀΛ, L2[Λ,X], L2[X,Λ]) + SingleDofCost measurements on the free nodes and on U.  Against the oracle loop."""
+    N, OX, OU, nstep, dt = 3, 2, 0, 7, 0.05
+    σx, σu = 0.05, 2.0
+    model = mb.Model("CantileverId")
+    nod = mb.addnode(model, np.arange(N + 1)[:, None] * np.array([1., 0., 0.])[None, :])
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    mat = mb.BeamCrossSection(EA=200., EI2=6., EI3=5., GJ=4., mu=1., iota1=.2, w=.5, Ca2=.5, Ca3=.4, Cq2=.2, Cq3=.2)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], unod], axis=1), mat=mat, Udof=True)
+    fields = ["t1", "t2", "t3", "r1", "r2", "r3"]
+    for f in fields:
+        mb.addelement(model, mb.Hold, [nod[0]], field=f)
+    amp = {f: 0.03 * (1 + i) * np.arange(1, N + 1) / N for i, f in enumerate(fields[:3])}
+    for f in fields[:3]:
+        mb.addelement(model, mb.SingleDofCost, nod[1:, None], clas="X", field=f, cost=lambda x, t, a=amp[f]: 0.5 * ((x - a * np.sin(4. * t)) / σx) ** 2)
+    for f in ["t1", "t2", "t3"]:
+        mb.addelement(model, mb.SingleDofCost, unod[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / σu) ** 2)
+    mb.setscale(model, scale=dict(X=dict(t1=.5, t2=.5, t3=.5), U=dict(t1=2., t2=2., t3=2.)), Λscale=3.)
+    st0 = mb.initialize(model, time=0.)
+    dis = st0.dis
+    time = dt * np.arange(nstep)
+    sol = mb.directxua.solve(OX, OU, st0, time, maxΔλ=np.inf, maxΔx=1e-8, maxΔu=1e-8)
+    # the root stays where the Holds put it; the tip moves
+    root = dis.dis[0].X[0, :6] - 1
+    assert max(np.abs(s.X[0][root]).max() for s in sol) <= 1e-9 and max(np.abs(s.X[0]).max() for s in sol) > 1e-3
+
+    # ---- oracle loop
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+
+    def diagpos(ab, n):
+        cp, rv = P["pat"][ab][2], P["pat"][ab][3]
+        pos = -np.ones(n, np.int64)
+        for j in range(1, n + 1):
+            q = np.nonzero(rv[cp[j - 1] - 1: cp[j] - 1] == j)[0]
+            if len(q): pos[j - 1] = cp[j - 1] - 1 + q[0]
+        return pos
+    dX, dU = diagpos((2, 2), nX), diagpos((3, 3), nU)
+    mX = np.zeros(nX); hasm = np.zeros(nX, bool)
+    for i, f in enumerate(fields[:3]):
+        ix = dis.dis[7 + i].X[:, 0] - 1
+        mX[ix] = amp[f]; hasm[ix] = True
+    sX, sU, sL = dis.scaleX, dis.scaleU, dis.scaleΛ
+    A = P["asm"]
+    ost = [dict(L=[np.zeros(nX)], X=[np.zeros(nX) for _ in range(3)], U=[np.zeros(nU)]) for _ in range(nstep)]
+    for it in range(60):
+        outs = []
+        for k in range(nstep):
+            o = OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, OX, OU, ost[k]["X"], ost[k]["U"], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0)
+            x, u, lam = ost[k]["X"][0], ost[k]["U"][0], ost[k]["L"][0]
+            o["L1"][2] = np.zeros((OX + 1, nX))
+            o["L1"][2][0] += np.where(hasm, (x - mX * np.sin(4. * time[k])) / σx ** 2 * sX, 0.)
+            o["L1"][3] = (u / σu ** 2 * sU)[None, :]
+            hxx = np.zeros(len(P["pat"][(2, 2)][3])); hxx[dX[hasm]] = (sX ** 2 / σx ** 2)[hasm]
+            huu = np.zeros(len(P["pat"][(3, 3)][3])); huu[dU] = sU ** 2 / σu ** 2
+            o["L2"][(2, 2)] = {(1, 1): hxx}; o["L2"][(3, 3)] = {(1, 1): huu}
+            for t in range(1, 7):                                   # Hold types: dofs (x, λc), R = (−λc, −x), ∂R/∂X = [[0,−1],[−1,0]]
+                ix = dis.dis[t].X[0] - 1
+                K = np.array([[0., -1.], [-1., 0.]])
+                R = K @ x[ix]
+                sl, sx = sL[ix], sX[ix]
+                aL, aXv, aLX, aXL = A[OP.arrnum(1)][t][:, 0], A[OP.arrnum(2)][t][:, 0], A[OP.arrnum(1, 2)][t][:, 0], A[OP.arrnum(2, 1)][t][:, 0]
+                for i in range(2):
+                    o["L1"][1][aL[i] - 1] += R[i] * sl[i]
+                    o["L1"][2][0, aXv[i] - 1] += (K[:, i] @ lam[ix]) * sx[i]
+                    for j in range(2):
+                        o["L2"][(1, 2)][0, aLX[i + 2 * j] - 1] += K[i, j] * sl[i] * sx[j]
+                        o["L2"][(2, 1)][0, aXL[j + 2 * i] - 1] += K[i, j] * sl[i] * sx[j]
+            outs.append(o)
+        nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+        c2, r2, v2 = OP.sparser(big["colptr"], big["rowval"], nz, 1e-20)
+        dv = spla.splu(sp.csc_matrix((v2, r2 - 1, c2 - 1), shape=(big["m"], big["n"]))).solve(Lv)
+        d2 = OP.decrementbig(ost, dv, OX, OU, dt, nstep, nX, nU, sL, sX, sU)
+        if (d2[1:] <= 1e-16).all():
+            break
+    assert it < 50 and sol[0].SP["iter"] == it + 1
+    for k in range(nstep):
+        for d in range(3):
+            ref = ost[k]["X"][d]
+            assert np.abs(sol[k].X[d] - ref).max() <= 1e-6 * max(1e-2, np.abs(ref).max()), (k, d)
+        assert np.abs(sol[k].U[0] - ost[k]["U"][0]).max() <= 1e-6 * max(1e-2, np.abs(ost[k]["U"][0]).max())
