@@ -221,8 +221,10 @@ def run_sweepx(args, rank, world, local, dist):
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     if world == 1:
-        el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=args.steps)   # CUDA events on the engine's stream around every launch set
-        step_ms = el_ms + ga_ms
+        # K whole steps exactly as a solver issues them (mb_sweepx_assemble_dev), CUDA events on the engine's stream; then the same launch sets
+        # with an event between element kernels and reduction for the per-kernel breakdown / roofline
+        step_ms = eng.time_step_dev(OX, "iter", nm, reps=args.steps)
+        el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=max(3, min(args.steps, 5)))
     else:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -266,9 +268,9 @@ def run_sweepx(args, rank, world, local, dist):
 
     if rank == 0:
         flops = load_flops(OX)
-        roof = {"bound": "fp64", "kernel": "beam_kernel_sd<ND=%d>" % (OX + 1), "unit": "TFLOP/s", "peak": fp64_peak,
+        roof = {"bound": "fp64", "kernel": "beam_static_sym_kernel" if OX == 0 else "beam_cot_kernel<%d> + beam_kernel_sd<%d,split>" % (OX + 1, OX + 1), "unit": "TFLOP/s", "peak": fp64_peak,
                 "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
-                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "traffic": None, "achieved": None, "frac": None}
+                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "kernel_ms_source": "CUDA events around the kernel's launches on the engine's stream", "traffic": None, "achieved": None, "frac": None}
         if flops:
             roof["flop_per_element"] = flops["flop"]
             if flops.get("dram_bytes_per_element"):      # measured DRAM bytes of one launch of the element kernel(s) (ncu --set full, profiles/)
@@ -290,7 +292,9 @@ def run_sweepx(args, rank, world, local, dist):
                 "roofline": roof,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                  "sample": "%d elements of the same chain, oracle literal restatement, 1 thread (%.1f s)" % (args.cpu_sample, cpu_dt)},
-                "breakdown_ms": {"element_kernels": el_ms, "segmented_reduction": ga_ms, "wall_timed_region_s": wall}}
+                "breakdown_ms": {"element_kernels": el_ms, "segmented_reduction": ga_ms, "serial_sum": el_ms + ga_ms, "wall_timed_region_s": wall,
+                                 "note": "value is from K whole steps between two events; element_kernels / segmented_reduction are the same launches "
+                                         "with an event in between (second pass)"}}
         print(json.dumps(line), flush=True)
     eng.close()
 

@@ -55,6 +55,7 @@ SYMBOLS = {
     "mb_get_device_ptrs": (C.c_int32, [H, C.POINTER(DevPtrs)]),
     "mb_set_ndofU": (C.c_int32, [H, C.c_int64]),
     "mb_sweepx_time_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p, C.c_int32, f32p]),
+    "mb_sweepx_time_step_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p, C.c_int32, f32p]),
     "mb_measure_fp64_tflops": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_measure_copy_gbs": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_launch_count": (C.c_int64, [H]),

@@ -163,6 +163,41 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
+// K1, statics (ND = 1): symmetric-tangent kernel (beam_static_sym, beam_math.cuh).  Thread t ↔ (element t/6, lane t%6); lane l sweeps the ROTATION
+// dof l only (everything in SD<1,0>), writes that column of Ke, the transposed copies into the translation columns and six closed-form
+// translation×translation entries.  Lane 0 also writes the residual.  −40 % FP64 work in the reverse sweep compared with beam_kernel_sd<1,false>.
+template <int MINB>          // resident CTAs per SM the register allocation aims at (template also so that only the ND = 1 translation unit compiles it)
+__global__ void __launch_bounds__(MB_BLOCK, MINB)
+beam_static_sym_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase) {
+    using V = SD<false, false>; using S = SD<true, false>;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 6;
+    const int lane = (int)(t - e * 6);
+    if (e >= g.nele) return;
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    V Xu[6], U[3]; S Xv[6], R[12];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3, iv = iu + 3;
+        Xu[i].v = st.X0[__ldg(ix + iu)];
+        Xv[i].v = st.X0[__ldg(ix + iv)]; Xv[i].d0 = (i == lane) ? g.scaleX[iv] : 0.;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.;
+    double Gc[3];
+    beam_static_sym(geo, m, Xu, Xv, g.udof != 0, U, lane % 3, R, Gc);
+    double* ke = Ke + e * 144;
+    bool bad = beam_static_sym_store(lane, R, Gc, g.scaleX, [&](int k, double v) { __stcs(ke + k, v); });
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { double v = R[i].v * g.scaleX[i]; bad |= (v != v); Re[e * 12 + i] = v; }
+    }
+    if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+
 // :step mission only (src/SweepX.jl:46-57,69-78): the extra seed direction δr carries the Newmark predictor
 //   vx′ = x′ + a₁δX + a·δr,  vx″ = x″ + b₁δX + b·δr,  a = a₂x′+a₃x″,  b = b₂x′+b₃x″ ;   Rp = ∂(Lλ)/∂r is subtracted from the rhs.
 // One thread per element, dense one-direction dual.
@@ -444,13 +479,24 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
 struct BeamLaunch {
     BeamGroupDev g; StateDev st; NewmarkDev nm;
     double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream; double* Wc;
+    int static_sym = 2;     // statics: symmetric-tangent kernel at 2/3/4 CTAs per SM (0: the two-direction SD kernel, kept for A/B measurements)
 };
 template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
+template <int ND> struct StaticSymLaunch { static void go(const BeamLaunch&, unsigned) {} };
+template <> struct StaticSymLaunch<1> {
+    static void go(const BeamLaunch& a, unsigned nb) {
+        if (a.static_sym == 3) beam_static_sym_kernel<3><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        else if (a.static_sym == 4) beam_static_sym_kernel<4><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        else beam_static_sym_kernel<2><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+    }
+};
 #define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \
     template <> void launch_beam<ND_, STEP_>(const BeamLaunch& a) {                                                                   \
         const int64_t nt = a.g.nele * 6;                                                                                              \
         const unsigned nb = (unsigned)((nt + MB_BLOCK - 1) / MB_BLOCK);                                                               \
-        if (ND_ >= 2 && a.Wc) {                                                                                                       \
+        if (ND_ == 1 && a.static_sym)                                                                                                 \
+            StaticSymLaunch<ND_>::go(a, nb);                                                                                          \
+        else if (ND_ >= 2 && a.Wc) {                                                                                                  \
             beam_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Wc, nt);                         \
             beam_kernel_sd<ND_, true><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.nm, a.Ke, a.Re, a.nanflag, a.nanbase, a.Wc, nt);    \
         } else                                                                                                                        \

@@ -610,6 +610,78 @@ template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const Be
     beam_residual_n<ND, N, HostScratch>(g, m, Xu, Xv, udof, U0, R, sc);
 }
 
+// ------------------------------------------------------------------------------------------------ statics: symmetric tangent
+// In statics the residual is the gradient of a potential (strain energy − weight·x + U·x: fₑ does not depend on X, BeamElement.jl:37,169),
+// so the tangent ∂R/∂X₀ is symmetric and only the six ROTATION directions need a forward-over-reverse sweep:
+//   columns of the rotation dofs      from the sweep seeded at rotation dof l (all in SD<1,0>: one direction instead of two),
+//   rows of the rotation dofs         by symmetry (the translation rows of those columns, transposed),
+//   translation × translation block   in closed form: translations enter only through d′ = (u₂−u₁)/2 + tgₘ/2 and only through
+//       d̄′ = rₛₘ·ūₗ,  ūₗ = 2EA(2/L − 1/|q|)·q + diag(0, 48EI₃/L³, 48EI₂/L³)·uₗ,  q = rₛₘᵀd′  (ε = 2|q|/L − 1, beam_reverse_rot / beam_internal_reverse)
+//       ⇒ G = ∂d̄′/∂d′ = rₛₘ·[2EA(2/L − 1/|q|)·I + 2EA·qqᵀ/|q|³ + diag(0,48EI₃/L³,48EI₂/L³)]·rₛₘᵀ and ∂R_{uₐ}/∂u_b = ±G/4.
+// c ∈ {0,1,2}: the column of G this lane returns in Gc[3].
+using NumRot = Num<SD<true, false>, SD<false, false>, SD<true, false>>;
+MB_HD void beam_static_sym(const BeamGeo& g, const BeamMat& m, const SD<false, false>* Xu0, const SD<true, false>* Xv0, bool udof,
+                           const SD<false, false>* U0, int c, SD<true, false>* R, double* Gc) {
+    using N = NumRot; using TR = N::TR; using TU = N::TU; using S = N::TS;
+    const double L = g.L;
+    BeamFwd<N> f;
+    BeamAcc<S> acc;
+    {
+        S z = Make<S>::c(0.);
+        for (int i = 0; i < 9; ++i) acc.rb.a[i] = z;
+        for (int i = 0; i < 3; ++i) { acc.ulb[i] = z; acc.vlb[i] = z; acc.cb[i] = z; }
+    }
+    Vec3<S> vsmb{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(0.)};
+    beam_forward<N, false>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]},
+                           Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
+    {
+        const double iq = 1.0 / f.qn.v, k = (2.0 * m.EA) * (2.0 / L - iq), h = (2.0 * m.EA) * (iq * iq * iq);
+        const double c48 = 48.0 / (L * L * L);
+        const double D[3] = {0., m.EI3 * c48, m.EI2 * c48};
+        double w[3], Aw[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) w[j] = (c == 0) ? f.r(0, j).v : ((c == 1) ? f.r(1, j).v : f.r(2, j).v);     // rₛₘᵀe_c
+        const double qw = (f.q[0].v * w[0] + f.q[1].v * w[1]) + f.q[2].v * w[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Aw[j] = (k + D[j]) * w[j] + (h * qw) * f.q[j].v;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Gc[i] = (f.r(i, 0).v * Aw[0] + f.r(i, 1).v * Aw[1]) + f.r(i, 2).v * Aw[2];
+    }
+    Vec3<S> fe{Make<S>::c(0.), Make<S>::c(0.), Make<S>::c(m.w)};
+    if (udof) for (int i = 0; i < 3; ++i) fe[i] = fe[i] - U0[i];
+    beam_uniform_reverse<N>(L, f, fe, acc);
+    beam_internal_reverse<N>(L, m, f, acc);
+    S epsb = (m.EA * L) * f.eps;
+    HostScratch sc;
+    beam_reverse_rot<N, HostScratch, S, false>(g, f, epsb, vsmb, acc, R, sc);
+}
+
+// Where lane l (rotation dof l; element dof cv = l+3 or l+6) of beam_static_sym puts its share of the scaled element tangent
+// Ke[i + 12j] = scale_i·∂R_i/∂X_j·scale_j (src/SweepX.jl:55,63): the rotation column cv, the same six translation-row entries transposed into
+// row cv of the translation columns, and the translation rows of translation column cu = cv − 3 (±G/4).  R must have been seeded with scale_cv.
+// put(k, value) stores entry k of the element's 144; returns true if any value is NaN.
+template <class Put> MB_HD bool beam_static_sym_store(int l, const SD<true, false>* R, const double* Gc, const double* scaleX, Put put) {
+    const int cu = (l < 3) ? l : l + 3, cv = cu + 3;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const double a = R[i].d0 * scaleX[i];
+        bad |= (a != a);
+        put(12 * cv + i, a);
+        if (i < 3 || (i >= 6 && i < 9)) put(12 * i + cv, a);
+    }
+    const double sc = 0.25 * scaleX[cu];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double v = Gc[a] * sc;
+        bad |= (v != v);
+        const double v1 = (l < 3) ? v : -v;               // rows of node 1: + when the column belongs to node 1
+        put(12 * cu + a, v1 * scaleX[a]);
+        put(12 * cu + 6 + a, -v1 * scaleX[6 + a]);
+    }
+    return bad;
+}
+
 // dense Dual<W> front-end (element dof order X[ider][12]); used by the δr lane of the :step mission and by the host tests
 template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMat& m, const Dual<W> (*X)[12], bool udof, const Dual<W>* U0, Dual<W>* R) {
     Dual<W> Xu[3][6], Xv[3][6];

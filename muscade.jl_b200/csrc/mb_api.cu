@@ -35,10 +35,14 @@ int32_t mb_create(int32_t device, mb_handle** out) {
     if (w) h->beamW = atoi(w);
     const char* sd = getenv("MB_SPLIT_DYN");
     if (sd) h->split_dyn = atoi(sd);
+    const char* ss = getenv("MB_STATIC_SYM");            // 0: statics through the two-direction SD kernel (A/B measurements)
+    if (ss) h->static_sym = atoi(ss);
     const char* pc = getenv("MB_E2E_CHUNKS");            // host-buffer pipeline: number of element chunks (<2: one shot) and size threshold
     if (pc) h->pipe_chunks = std::min(64, atoi(pc));
     const char* pm = getenv("MB_E2E_MIN_NNZ");
     if (pm) h->pipe_min_nnz = atoll(pm);
+    const char* ov = getenv("MB_DEV_OVERLAP");           // 1: reduction of element chunk j overlapped with the element kernels of chunk j+1 (no gain measured)
+    if (ov) h->dev_overlap = atoi(ov);
     *out = h;
     return MB_OK;
 }
@@ -55,6 +59,8 @@ int32_t mb_destroy(mb_handle* h) {
     if (h->own_stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t ev : h->pipe_ev) cudaEventDestroy(ev);
+    if (h->gather_done) cudaEventDestroy(h->gather_done);
+    if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
     delete h;
     return MB_OK;
 }
@@ -322,6 +328,7 @@ template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group
     }
     BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base + e0 * 144, h->Re + g.vec_base + e0 * 12, h->Rp + g.vec_base + e0 * 12, h->nanflag, nanbase + (unsigned long long)e0,
                  h->beamW, h->stream, Wc};
+    a.static_sym = h->static_sym;
     launch_beam<ND, STEP>(a);
     h->launches += 1 + (Wc ? 1 : 0) + (STEP ? (Wc ? 2 : 1) : 0);
 }
@@ -363,9 +370,10 @@ static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkD
     return MB_OK;
 }
 // segmented reductions of non-zeros [k0,k1) (k0 a multiple of 4) and dofs [d0,d1)
-static void launch_gather_range(mb_handle* h, bool step, int64_t k0, int64_t k1, int64_t d0, int64_t d1) {
-    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, h->stream>>>(k1 - k0, h->cstart + k0, h->src, h->Ke, h->nzval + k0); h->launches++; }
-    if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, 256), 256, 0, h->stream>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
+static void launch_gather_range(mb_handle* h, bool step, int64_t k0, int64_t k1, int64_t d0, int64_t d1, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
+    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->Ke, h->nzval + k0); h->launches++; }
+    if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, 256), 256, 0, st>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
 }
 static void launch_gather(mb_handle* h, bool step) { launch_gather_range(h, step, 0, h->nnz, 0, h->ndofX); }
 
@@ -441,10 +449,59 @@ int32_t mb_sweepx_assemble_dev(mb_handle* h, int32_t OX, int32_t mission, double
     CK(cudaSetDevice(h->device));
     NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
     CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
+    if (h->dev_overlap && h->pipe_state == 0 && h->nnz >= h->pipe_min_nnz) { int32_t rc = build_pipeline(h); if (rc) return rc; }
+    if (h->dev_overlap && h->pipe_state == 1) {
+        // chunk j's non-zeros are reduced on the high-priority stream while the element kernels of chunk j+1 run; results are visible to
+        // h->stream when the call returns (event wait), so callers keep ordering against h->stream only
+        if (!h->gather_stream) {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, hi));
+            CK(cudaEventCreateWithFlags(&h->gather_done, cudaEventDisableTiming));
+        }
+        const bool step = mission == 0 && OX > 0;
+        const int C = h->pipe_chunks;
+        size_t it = 0; int64_t k0 = 0, d0 = 0;
+        for (int j = 0; j < C; ++j) {
+            for (; it < h->pipe_items.size() && h->pipe_items[it].chunk == j; ++it) {
+                const mb_handle::PipeItem& w = h->pipe_items[it];
+                int32_t rc = launch_group_range(h, (size_t)w.ig, w.e0, w.e1, OX, mission, nm, t);
+                if (rc) return rc;
+            }
+            const int64_t k1 = h->pipe_nz_end[(size_t)j], d1 = h->pipe_vec_end[(size_t)j];
+            if (k1 > k0 || d1 > d0) {
+                CK(cudaEventRecord(h->pipe_ev[(size_t)j], h->stream));
+                CK(cudaStreamWaitEvent(h->gather_stream, h->pipe_ev[(size_t)j], 0));
+                launch_gather_range(h, step, k0, k1, d0, d1, h->gather_stream);
+            }
+            k0 = k1; d0 = d1;
+        }
+        CK(cudaEventRecord(h->gather_done, h->gather_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->gather_done, 0));
+        CK(cudaGetLastError());
+        return MB_OK;
+    }
     int32_t rc = launch_elements(h, OX, mission, nm, t);
     if (rc) return rc;
     launch_gather(h, mission == 0 && OX > 0);
     CK(cudaGetLastError());
+    return MB_OK;
+}
+
+// whole device-resident steps (mb_sweepx_assemble_dev as configured, overlapped or not), CUDA events on the engine's stream
+int32_t mb_sweepx_time_step_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark, int32_t reps, float* ms) {
+    if (!h) return MB_ERR_ARG;
+    ARG(h->prepared && reps >= 1 && ms && newmark, "bad argument");
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps; ++r) { int32_t rc = mb_sweepx_assemble_dev(h, OX, mission, t, newmark); if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; } }
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float a; CK(cudaEventElapsedTime(&a, e0, e1));
+    *ms = a / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return MB_OK;
 }
 

@@ -203,6 +203,12 @@ class Engine:
         check(self.h, self.L.mb_sweepx_time_dev(self.h, OX, {"step": 0, "iter": 1}[mission], 0., _f64(newmark), reps, ms))
         return float(ms[0]), float(ms[1])
 
+    def time_step_dev(self, OX, mission, newmark, reps=3):
+        """average ms of `reps` whole device-resident steps (sweepx_assemble_dev as configured)"""
+        ms = np.zeros(1, np.float32)
+        check(self.h, self.L.mb_sweepx_time_step_dev(self.h, OX, {"step": 0, "iter": 1}[mission], 0., _f64(newmark), reps, ms))
+        return float(ms[0])
+
     def fp64_tflops(self):
         v = C.c_double()
         check(self.h, self.L.mb_measure_fp64_tflops(self.h, C.byref(v)))

@@ -71,6 +71,29 @@ extern "C" int mbh_beam_iter_sd(const double* geo16, const double* mat16, int nd
     return 0;
 }
 
+// statics, symmetric-tangent path exactly as beam_static_sym_kernel's lanes run it. K[i][p] scaled on rows AND columns (Ke of the kernel, transposed to row-major).
+extern "C" int mbh_beam_static_sym(const double* geo16, const double* mat16, const double* Xval, const double* scale, int udof, const double* Uval,
+                                   double* R, double* K) {
+    BeamGeo g; BeamMat m;
+    for (int i = 0; i < 3; ++i) g.cm[i] = geo16[i];
+    for (int i = 0; i < 9; ++i) g.rm.a[i] = geo16[3 + i];
+    for (int i = 0; i < 3; ++i) g.tgm[i] = geo16[12 + i];
+    g.L = geo16[15];
+    std::memcpy(&m, mat16, sizeof m);
+    static const int rot[6] = {3, 4, 5, 9, 10, 11}, tra[6] = {0, 1, 2, 6, 7, 8};
+    int bad = 0;
+    for (int l = 0; l < 6; ++l) {
+        SD<false, false> Xu[6], U[3]; SD<true, false> Xv[6], Rv[12];
+        for (int i = 0; i < 6; ++i) { Xu[i].v = Xval[tra[i]]; Xv[i].v = Xval[rot[i]]; Xv[i].d0 = (i == l) ? scale[rot[i]] : 0.; }
+        for (int i = 0; i < 3; ++i) U[i].v = udof ? Uval[i] : 0.;
+        double Gc[3];
+        beam_static_sym(g, m, Xu, Xv, udof != 0, U, l % 3, Rv, Gc);
+        bad |= beam_static_sym_store(l, Rv, Gc, scale, [&](int k, double v) { K[(k % 12) * 12 + k / 12] = v; });
+        for (int i = 0; i < 12; ++i) R[i] = Rv[i].v * scale[i];
+    }
+    return bad;
+}
+
 // getresult values (beam_results, the body of beam_results_kernel): X element dof order t1..r3 of node 1 then node 2, as the reference
 extern "C" int mbh_beam_results(const double* geo16, const double* mat16, int nd, const double* Xval, double* out77) {
     BeamGeo g; BeamMat m;
