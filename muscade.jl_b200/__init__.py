@@ -8,5 +8,5 @@ from . import _lib, toolbox, synthetic, model, sweepx, directxua, sharding  # no
 from ._lib import MuscadeB200Error, build  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .model import Model, addnode, addelement, setscale, initialize, Disassembler, State, getdof  # noqa: F401
-from .toolbox import (BeamCrossSection, EulerBeam3D, AxisymmetricBarCrossSection, Bar3D, SoilContact, Hold, DofLoad,
+from .toolbox import (BeamCrossSection, EulerBeam3D, AxisymmetricBarCrossSection, Bar3D, SoilContact, Hold, DofLoad, DofConstraint,
                       ElementType, SingleDofCost, Taylor2)  # noqa: F401

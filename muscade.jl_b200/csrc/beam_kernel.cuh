@@ -3,6 +3,7 @@
 #include "beam_math.cuh"
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 
 namespace mb {
 
@@ -40,6 +41,16 @@ struct SmemScratch {
 #endif
 constexpr int MB_STASH_SLOTS = 2 * 9 * 2;      // rₛ₂ and Rodrigues(Δvᵧ) as SD<1,0>
 
+// two consecutive doubles: one 16-byte streaming store when the destination allows it.  Element types with an odd number of entries stored before
+// the beams (SoilContact: 9 per element, host-evaluated DofLoad: 1) leave the beams' rows 8-byte aligned only; `al` is uniform over the launch.
+__device__ __forceinline__ void store_pair_cs(double* p, double x, double y, bool al) {
+    if (al) __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));
+    else { __stcs(p, x); __stcs(p + 1, y); }
+}
+__device__ __forceinline__ void store_pair(double* p, double x, double y, bool al) {
+    if (al) *reinterpret_cast<double2*>(p) = make_double2(x, y);
+    else { p[0] = x; p[1] = y; }
+}
 MB_HD void load_geo(const double* __restrict__ p16, BeamGeo& geo) {
     const double2* p = reinterpret_cast<const double2*>(p16);
     double buf[16];
@@ -147,14 +158,15 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     bool bad = false;
     const int cu = (lane < 3) ? lane : lane + 3, cv = cu + 3;          // tangent columns of this lane
     double* ke = Ke + e * 144;
+    const bool al = (reinterpret_cast<uintptr_t>(ke) & 15) == 0;
 #pragma unroll
     for (int i = 0; i < 12; i += 2) {
         double2 a, b;
         a.x = R[i].d1 * g.scaleX[i]; a.y = R[i + 1].d1 * g.scaleX[i + 1];
         b.x = R[i].d0 * g.scaleX[i]; b.y = R[i + 1].d0 * g.scaleX[i + 1];
         bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
-        __stcs(reinterpret_cast<double2*>(ke + 12 * cu + i), a);       // streaming: written once, read once by K6 — keep L2 for the spill lines
-        __stcs(reinterpret_cast<double2*>(ke + 12 * cv + i), b);
+        store_pair_cs(ke + 12 * cu + i, a.x, a.y, al);                 // streaming: written once, read once by K6 — keep L2 for the spill lines
+        store_pair_cs(ke + 12 * cv + i, b.x, b.y, al);
     }
     if (lane == 0) {
 #pragma unroll
@@ -165,7 +177,13 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 
 // K1, statics (ND = 1): symmetric-tangent kernel (beam_static_sym, beam_math.cuh).  Thread t ↔ (element t/6, lane t%6); lane l sweeps the ROTATION
 // dof l only (everything in SD<1,0>), writes that column of Ke, the transposed copies into the translation columns and six closed-form
-// translation×translation entries.  Lane 0 also writes the residual.  −40 % FP64 work in the reverse sweep compared with beam_kernel_sd<1,false>.
+// translation×translation entries.  Lane 0 also writes the residual.  −13 % FP64 instructions (16 348 → 14 274 per element) and a third of the
+// spill traffic compared with beam_kernel_sd<1,false>; 19.8 → 17.3 ms at 10 M elements with the paired 16-byte stores.
+// Measured and dropped (B200, 10 M elements): 3 / 4 CTAs per SM (168 / 128 registers: 19.6 / 23.8 ms, the spills cost more than the extra warps
+// hide); a persistent CTA working on 21-element tiles with cp.async input staging and a shared-memory transpose for coalesced stores (21.8 ms:
+// with two warps per scheduler every __syncthreads idles the FP64 pipe); a persistent, barrier-free variant with a private cp.async prefetch of the
+// next element's dof indices / state / geometry (21.4 ms: long_scoreboard 1.49 → 1.00 per issue as intended, but no_instruction 0.37 → 1.12 —
+// the 76 KB loop body thrashes the 32 KB instruction cache when every warp of the SM loops over it instead of streaming through it once).
 template <int MINB>          // resident CTAs per SM the register allocation aims at (template also so that only the ND = 1 translation unit compiles it)
 __global__ void __launch_bounds__(MB_BLOCK, MINB)
 beam_static_sym_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase) {
@@ -190,7 +208,9 @@ beam_static_sym_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, dou
     double Gc[3];
     beam_static_sym(geo, m, Xu, Xv, g.udof != 0, U, lane % 3, R, Gc);
     double* ke = Ke + e * 144;
-    bool bad = beam_static_sym_store(lane, R, Gc, g.scaleX, [&](int k, double v) { __stcs(ke + k, v); });
+    const bool al = (reinterpret_cast<uintptr_t>(ke) & 15) == 0;
+    bool bad = beam_static_sym_store(lane, R, Gc, g.scaleX, [&](int k, double v) { __stcs(ke + k, v); },
+                                     [&](int k, double v0, double v1) { store_pair_cs(ke + k, v0, v1, al); });
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 12; ++i) { double v = R[i].v * g.scaleX[i]; bad |= (v != v); Re[e * 12 + i] = v; }
@@ -391,13 +411,14 @@ beam_direct_b0_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR
     }
     bool bad = false;
     double* out = dR + e * (int64_t)(12 * NP);
+    const bool al = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const int cu = (l < 3) ? l : l + 3, cv = cu + 3;
 #pragma unroll
     for (int i = 0; i < 12; i += 2) {
         double2 a, b; a.x = Rv[i].d1; a.y = Rv[i + 1].d1; b.x = Rv[i].d0; b.y = Rv[i + 1].d0;
         bad |= (a.x != a.x) | (a.y != a.y) | (b.x != b.x) | (b.y != b.y);
-        *reinterpret_cast<double2*>(out + 12 * cu + i) = a;
-        *reinterpret_cast<double2*>(out + 12 * cv + i) = b;
+        store_pair(out + 12 * cu + i, a.x, a.y, al);
+        store_pair(out + 12 * cv + i, b.x, b.y, al);
     }
     if (l == 0) {
 #pragma unroll
@@ -452,12 +473,13 @@ beam_direct_lin_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ d
     beam_residual_cot<NV, S, (ND >= 3)>(geo, m, Xu0, Xv0, xb, vsmb, Rv);
     bool bad = false;
     double* out = dR + e * (int64_t)(12 * NP);
+    const bool al = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 #pragma unroll
     for (int i = 0; i < 12; i += 2) {
         double2 a, b; a.x = Rv[i].d1; a.y = Rv[i + 1].d1; b.x = Rv[i].d0; b.y = Rv[i + 1].d0;
         bad |= (b.x != b.x) | (b.y != b.y);
-        *reinterpret_cast<double2*>(out + 12 * c0 + i) = b;
-        if (c1 >= 0) { bad |= (a.x != a.x) | (a.y != a.y); *reinterpret_cast<double2*>(out + 12 * c1 + i) = a; }
+        store_pair(out + 12 * c0 + i, b.x, b.y, al);
+        if (c1 >= 0) { bad |= (a.x != a.x) | (a.y != a.y); store_pair(out + 12 * c1 + i, a.x, a.y, al); }
     }
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
@@ -479,15 +501,14 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
 struct BeamLaunch {
     BeamGroupDev g; StateDev st; NewmarkDev nm;
     double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream; double* Wc;
-    int static_sym = 2;     // statics: symmetric-tangent kernel at 2/3/4 CTAs per SM (0: the two-direction SD kernel, kept for A/B measurements)
+    int static_sym = 1;     // statics: 1 = symmetric-tangent kernel, 0 = two-direction SD kernel (kept for A/B measurements)
+    int nsm = 148;
 };
 template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
 template <int ND> struct StaticSymLaunch { static void go(const BeamLaunch&, unsigned) {} };
 template <> struct StaticSymLaunch<1> {
     static void go(const BeamLaunch& a, unsigned nb) {
-        if (a.static_sym == 3) beam_static_sym_kernel<3><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
-        else if (a.static_sym == 4) beam_static_sym_kernel<4><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
-        else beam_static_sym_kernel<2><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        beam_static_sym_kernel<2><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
     }
 };
 #define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \

@@ -659,26 +659,28 @@ MB_HD void beam_static_sym(const BeamGeo& g, const BeamMat& m, const SD<false, f
 // Where lane l (rotation dof l; element dof cv = l+3 or l+6) of beam_static_sym puts its share of the scaled element tangent
 // Ke[i + 12j] = scale_i·∂R_i/∂X_j·scale_j (src/SweepX.jl:55,63): the rotation column cv, the same six translation-row entries transposed into
 // row cv of the translation columns, and the translation rows of translation column cu = cv − 3 (±G/4).  R must have been seeded with scale_cv.
-// put(k, value) stores entry k of the element's 144; returns true if any value is NaN.
-template <class Put> MB_HD bool beam_static_sym_store(int l, const SD<true, false>* R, const double* Gc, const double* scaleX, Put put) {
+// put(k, value) stores entry k of the element's 144, put2(k, v0, v1) entries k (even) and k+1; returns true if any value is NaN.
+template <class Put, class Put2> MB_HD bool beam_static_sym_store(int l, const SD<true, false>* R, const double* Gc, const double* scaleX, Put put, Put2 put2) {
     const int cu = (l < 3) ? l : l + 3, cv = cu + 3;
     bool bad = false;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        const double a = R[i].d0 * scaleX[i];
-        bad |= (a != a);
-        put(12 * cv + i, a);
+    for (int i = 0; i < 12; i += 2) {
+        const double a = R[i].d0 * scaleX[i], b = R[i + 1].d0 * scaleX[i + 1];
+        bad |= (a != a) | (b != b);
+        put2(12 * cv + i, a, b);                              // even offsets: 16-byte stores
         if (i < 3 || (i >= 6 && i < 9)) put(12 * i + cv, a);
+        if (i + 1 < 3 || (i + 1 >= 6 && i + 1 < 9)) put(12 * (i + 1) + cv, b);
     }
     const double sc = 0.25 * scaleX[cu];
+    double v1[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const double v = Gc[a] * sc;
         bad |= (v != v);
-        const double v1 = (l < 3) ? v : -v;               // rows of node 1: + when the column belongs to node 1
-        put(12 * cu + a, v1 * scaleX[a]);
-        put(12 * cu + 6 + a, -v1 * scaleX[6 + a]);
+        v1[a] = (l < 3) ? v : -v;                             // rows of node 1: + when the column belongs to node 1
     }
+    put2(12 * cu, v1[0] * scaleX[0], v1[1] * scaleX[1]); put(12 * cu + 2, v1[2] * scaleX[2]);
+    put2(12 * cu + 6, -v1[0] * scaleX[6], -v1[1] * scaleX[7]); put(12 * cu + 8, -v1[2] * scaleX[8]);
     return bad;
 }
 

@@ -31,6 +31,7 @@ int32_t mb_create(int32_t device, mb_handle** out) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
     if (cudaMalloc((void**)&h->nanflag, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost((void**)&h->nanflag_host, sizeof(unsigned long long)) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
+    { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->nsm = prop.multiProcessorCount; }
     const char* w = getenv("MB_BEAM_W");
     if (w) h->beamW = atoi(w);
     const char* sd = getenv("MB_SPLIT_DYN");
@@ -328,7 +329,7 @@ template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group
     }
     BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base + e0 * 144, h->Re + g.vec_base + e0 * 12, h->Rp + g.vec_base + e0 * 12, h->nanflag, nanbase + (unsigned long long)e0,
                  h->beamW, h->stream, Wc};
-    a.static_sym = h->static_sym;
+    a.static_sym = h->static_sym; a.nsm = h->nsm;
     launch_beam<ND, STEP>(a);
     h->launches += 1 + (Wc ? 1 : 0) + (STEP ? (Wc ? 2 : 1) : 0);
 }

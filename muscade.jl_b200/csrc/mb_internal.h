@@ -53,7 +53,7 @@ struct mb_handle {
     int64_t launches = 0;
     int beamW = 1;
     std::vector<void*> owned;
-    double* Wc = nullptr; int64_t Wc_len = 0; int split_dyn = 1; int static_sym = 2;   // cotangent workspace of the two-phase Newmark kernel
+    double* Wc = nullptr; int64_t Wc_len = 0; int split_dyn = 1; int static_sym = 1; int nsm = 148;   // cotangent workspace of the two-phase Newmark kernel
     bool own_stream = true;
     int32_t *if_send = nullptr, *if_recv = nullptr;   // interface index lists (0-based into [nzval | Lλ], −1 = ghost)
     int64_t if_nsend_nz = 0, if_nsend_v = 0, if_nrecv_nz = 0, if_nrecv_v = 0;

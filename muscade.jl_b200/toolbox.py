@@ -192,6 +192,50 @@ class Hold(ElementType):
         return R, K, None, None
 
 
+class DofConstraint(ElementType):
+    """DofConstraint(nod;xinod,xfield,λinod,λclass=:X,λfield,gap,gargs,mode)  (src/BasicElements.jl:406-438), λclass = :X only.
+    residual (:425-438):  R = (−∂g/∂x·λ, −g) [equal],  (−∂g/∂x·λ, −(g·λ−γ)) [positive, γ = 0],  (0, −λ) [off].
+    The reference differentiates `gap` with its own dual numbers; here `gap(x,t,*gargs)` returns (g, ∂g/∂x) or (g, ∂g/∂x, ∂²g/∂x²) for
+    x of shape (nele,Nx) — arrays (nele,), (nele,Nx), (nele,Nx,Nx); evaluated on the host like Hold and DofLoad.  mode: "equal" | "positive" |
+    "off" or a callable t → one of them."""
+
+    @classmethod
+    def doflist(cls, xinod=(), xfield=(), λinod=1, λclass="X", λfield=None, **kw):
+        if λclass != "X":
+            raise ValueError("DofConstraint: only λclass = :X is on this path")
+        return tuple(xinod) + (λinod,), ("X",) * (len(xinod) + 1), tuple(xfield) + (λfield,)
+
+    @classmethod
+    def typekey(cls, xinod=(), xfield=(), λinod=1, λclass="X", λfield=None, gap=None, gargs=(), mode="equal", **kw):
+        return ("DofConstraint", λclass, len(xinod), tuple(xinod), tuple(xfield), λinod, λfield, id(gap), id(mode) if callable(mode) else mode)
+
+    @classmethod
+    def construct(cls, coords, xinod=(), xfield=(), λinod=1, λclass="X", λfield=None, gap=None, gargs=(), mode="equal"):
+        return np.zeros((coords[0].shape[0], 0)), dict(gap=gap, gargs=gargs, mode=mode, Nx=len(xinod))
+
+    @staticmethod
+    def residual(extra, X, t):
+        Nx = extra["Nx"]
+        x, lam = X[0][:, :Nx], X[0][:, Nx]
+        n = x.shape[0]
+        m = extra["mode"](t) if callable(extra["mode"]) else extra["mode"]
+        res = extra["gap"](x, t, *extra["gargs"])
+        g, dg = np.broadcast_to(np.asarray(res[0], float), (n,)), np.broadcast_to(np.asarray(res[1], float), (n, Nx))
+        d2g = np.broadcast_to(np.asarray(res[2], float), (n, Nx, Nx)) if len(res) > 2 else np.zeros((n, Nx, Nx))
+        R = np.zeros((n, Nx + 1)); K = np.zeros((n, Nx + 1, Nx + 1))
+        if m == "equal":
+            R[:, :Nx] = -dg * lam[:, None]; R[:, Nx] = -g
+            K[:, :Nx, :Nx] = -d2g * lam[:, None, None]; K[:, :Nx, Nx] = -dg; K[:, Nx, :Nx] = -dg
+        elif m == "positive":                                  # S(λ,g,γ) = g·λ − γ, γ = 0 (SP.γ is a solver parameter of other solvers)
+            R[:, :Nx] = -dg * lam[:, None]; R[:, Nx] = -g * lam
+            K[:, :Nx, :Nx] = -d2g * lam[:, None, None]; K[:, :Nx, Nx] = -dg; K[:, Nx, :Nx] = -dg * lam[:, None]; K[:, Nx, Nx] = -g
+        elif m == "off":
+            R[:, Nx] = -lam; K[:, Nx, Nx] = -1.
+        else:
+            raise ValueError("DofConstraint: mode must be equal, positive or off")
+        return R, K, None, None
+
+
 class DofLoad(ElementType):
     """DofLoad(nod;field,value)  (src/BasicElements.jl:275-284): R = (−value(t)); plain Float64 residual ⇒ no tangent."""
 

@@ -88,7 +88,8 @@ extern "C" int mbh_beam_static_sym(const double* geo16, const double* mat16, con
         for (int i = 0; i < 3; ++i) U[i].v = udof ? Uval[i] : 0.;
         double Gc[3];
         beam_static_sym(g, m, Xu, Xv, udof != 0, U, l % 3, Rv, Gc);
-        bad |= beam_static_sym_store(l, Rv, Gc, scale, [&](int k, double v) { K[(k % 12) * 12 + k / 12] = v; });
+        bad |= beam_static_sym_store(l, Rv, Gc, scale, [&](int k, double v) { K[(k % 12) * 12 + k / 12] = v; },
+                                     [&](int k, double v0, double v1) { K[(k % 12) * 12 + k / 12] = v0; K[((k + 1) % 12) * 12 + (k + 1) / 12] = v1; });
         for (int i = 0; i < 12; ++i) R[i] = Rv[i].v * scale[i];
     }
     return bad;
