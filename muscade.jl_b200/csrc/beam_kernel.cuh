@@ -28,6 +28,9 @@ struct StateDev { const double *X0, *X1, *X2, *U0; };
 #ifndef MB_BLOCK
 #define MB_BLOCK 128
 #endif
+#ifndef MB_SYM_MINB
+#define MB_SYM_MINB 2     // resident CTAs per SM of the static symmetric-tangent kernel (2 × 128 threads × 255 registers)
+#endif
 
 // per-thread scratch in dynamic shared memory: slot k of thread t lives at base[k·blockDim + t] (conflict-free)
 struct SmemScratch {
@@ -508,7 +511,7 @@ template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
 template <int ND> struct StaticSymLaunch { static void go(const BeamLaunch&, unsigned) {} };
 template <> struct StaticSymLaunch<1> {
     static void go(const BeamLaunch& a, unsigned nb) {
-        beam_static_sym_kernel<2><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        beam_static_sym_kernel<MB_SYM_MINB><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
     }
 };
 #define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \

@@ -31,7 +31,7 @@ struct PairPat {                  // one class-pair pattern of prepare(AssemblyD
     std::vector<int64_t> gbase;   // per group: first pair id
 };
 
-constexpr int MAXG = 8;
+constexpr int MAXG = 32;    // element types of one model on the DirectXUA path (the SCR riser of configs[4] has 11)
 struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; int64_t gxbase[MAXG]; };
 
 // ---------------------------------------------------------------------------------------------------------------- pattern build

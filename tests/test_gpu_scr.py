@@ -39,8 +39,14 @@ def vert_target(t): return np.exp(min(t, 0.)) * 303.1 + zmotion(t)              
 def ramp(t): return (min(t, -5.) + 10.) / 5.                                     # :119-121
 
 
-def build(mb):
+def build(mb, udof=False):
+    """udof: EulerBeam3D{Udof=true} with one U-node per element (unknown distributed loads, the XUA set-up of configs[4])"""
     acc = np.concatenate([[0.], np.cumsum(SEGLEN)])
+
+    def mesh(n1, n2):
+        n1, n2 = np.atleast_1d(n1), np.atleast_1d(n2)
+        cols = [n1, n2] + ([mb.addnode(model, np.zeros((len(n1), 0)))] if udof else [])
+        return np.stack(cols, axis=1)
     model = mb.Model("CatenaryRiser")
     mats = [mb.BeamCrossSection(**X1), mb.BeamCrossSection(**X2), mb.BeamCrossSection(**X1)]
     node_lists = []
@@ -49,12 +55,12 @@ def build(mb):
         c = np.stack([acc[seg] + np.arange(nn) / (nn - 1) * SEGLEN[seg], np.zeros(nn), -300. + np.zeros(nn)], axis=1)
         if seg == 0:
             nod = mb.addnode(model, c)
-            mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:]], axis=1), mat=mats[0], orient2=(0., 1., 0.))
+            mb.addelement(model, mb.EulerBeam3D, mesh(nod[:-1], nod[1:]), mat=mats[0], orient2=(0., 1., 0.), Udof=udof)
             last = nod[-1]
         else:
             nod = mb.addnode(model, c[1:])
-            mb.addelement(model, mb.EulerBeam3D, [last, nod[0]], mat=mats[seg], orient2=(0., 1., 0.))
-            mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:]], axis=1), mat=mats[seg], orient2=(0., 1., 0.))
+            mb.addelement(model, mb.EulerBeam3D, mesh(last, nod[0]), mat=mats[seg], orient2=(0., 1., 0.), Udof=udof)
+            mb.addelement(model, mb.EulerBeam3D, mesh(nod[:-1], nod[1:]), mat=mats[seg], orient2=(0., 1., 0.), Udof=udof)
             last = nod[-1]
         node_lists.append(nod)
     first = node_lists[0][0]
@@ -193,6 +199,97 @@ def test_scr_riser_assembly_parity(mb, OX, mission):
     assert np.abs(out.Lλx.data - nz).max() <= 1e-12 * np.abs(nz).max()
     assert np.abs(out.Lλ - L).max() <= 1e-12 * max(np.abs(nz).max(), np.abs(L).max())
     out.engine.close()
+
+
+def oracle_scr_direct_step(model, dis, weights, P, OX, OU, X, U, Lam, t, σu):
+    """assemble!{:matrices}(out::AssemblyDirect{OX,OU,0},…) of the whole SCR model at one step: beams through the first-order path
+    (DirectXUA.jl:85-120), SoilContact / Hold / DofConstraint / DofLoad through the second-order path (:152-171, L = Λ∘R), SingleDofCost on U
+    (lagrangian = cost, BasicElements.jl:198-208).  Boundary elements restated by hand as in OracleSCR."""
+    nX, nU = P["ndof"][0], P["ndof"][2]
+    A = P["asm"]
+    sL, sX, sU = dis.scaleΛ, dis.scaleX, dis.scaleU
+    o = OE.direct_out_zeros(P, OX, OU)
+    o["L1"][2] = np.zeros((OX + 1, nX)); o["L1"][3] = np.zeros((OU + 1, nU))
+    huu = np.zeros(len(P["pat"][(3, 3)][3]))
+    cpU, rvU = P["pat"][(3, 3)][2], P["pat"][(3, 3)][3]
+    iload = 0
+    for k, (et, d) in enumerate(zip(model.ele, dis.dis)):
+        kind = et.ElType.__name__
+        if kind == "EulerBeam3D":
+            OE.direct_assemble_step_beams(et.eleobj, d.X, d.U, OX, OU, X[: OX + 1], [U], d.scaleX, d.scaleU, P, k, out=o)
+        elif kind == "SoilContact":
+            OE.direct_addin_soil_second_order(et.eleobj, d.X, OX, X[: OX + 1], Lam, d.scaleX, model.scaleΛ, P, k, o)
+        elif kind in ("Hold", "DofConstraint", "DofLoad"):
+            aL, aXv, aLX, aXL = A[OP.arrnum(1)][k], A[OP.arrnum(2)][k], A[OP.arrnum(1, 2)][k], A[OP.arrnum(2, 1)][k]
+            if kind == "DofLoad":
+                F = weights[iload](t); iload += 1
+            for e in range(d.X.shape[0]):
+                ix = d.X[e] - 1
+                if kind == "DofLoad":                       # R = −value(t): only L1[Λ] (and zeros elsewhere)
+                    o["L1"][1][aL[0, e] - 1] += -F * sL[ix[0]]
+                    continue
+                target = 0. if kind == "Hold" else (horiz_target(t) if et.field[0] == "t1" else vert_target(t))
+                K = np.array([[0., -1.], [-1., 0.]])         # dofs (x, λc): R = (−λc, −(x − target))
+                R = np.array([-X[0][ix[1]], -(X[0][ix[0]] - target)])
+                for i in range(2):
+                    o["L1"][1][aL[i, e] - 1] += R[i] * sL[ix[i]]
+                    o["L1"][2][0, aXv[i, e] - 1] += (K[:, i] @ Lam[ix]) * sX[ix[i]]
+                    for j in range(2):
+                        o["L2"][(1, 2)][0, aLX[i + 2 * j, e] - 1] += K[i, j] * sL[ix[i]] * sX[ix[j]]
+                        o["L2"][(2, 1)][0, aXL[j + 2 * i, e] - 1] += K[i, j] * sL[ix[i]] * sX[ix[j]]
+        elif kind == "SingleDofCost":                        # ½(u/σu)² on a U dof
+            for e in range(d.U.shape[0]):
+                j = d.U[e, 0]
+                o["L1"][3][0, j - 1] += U[j - 1] / σu ** 2 * sU[j - 1]
+                q = cpU[j - 1] - 1 + np.nonzero(rvU[cpU[j - 1] - 1: cpU[j] - 1] == j)[0][0]
+                huu[q] += sU[j - 1] ** 2 / σu ** 2
+        else:
+            raise AssertionError(kind)
+    o["L2"][(3, 3)] = {(1, 1): huu}
+    return o
+
+
+@pytest.mark.gpu
+def test_scr_directxua_assembly_parity(mb):
+    """BASELINE.json configs[4] at test size: assemblebig!{:matrices} (DirectXUA.jl:316-356) of the SCR riser — 100 EulerBeam3D{Udof} in 5 types /
+    2 cross-sections, 61 SoilContact, 4 Hold, 2 DofConstraint with moving gaps, 101 DofLoad, quadratic SingleDofCost on every U dof — over 7 steps
+    at random (Λ, X, X′, X″, U): Lvv structure bit-exact, Lvv values and Lv ≤ 1e-12 against the oracle."""
+    OX, OU, nstep, dt, t0, σu = 2, 0, 7, 0.3, -6.3, 50.
+    model, node_lists, weights = build(mb, udof=True)
+    unodes = np.concatenate([et.nodID[:, 2] for et in model.ele if et.ElType.__name__ == "EulerBeam3D"])
+    for f in ("t1", "t2", "t3"):
+        mb.addelement(model, mb.SingleDofCost, unodes[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / σu) ** 2)
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=30., t2=30., t3=30.)), Λscale=1e3)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    assert nX == 612 and nU == 300
+    time = t0 + dt * np.arange(nstep)                         # crosses t = −5: the weight ramp saturates (DynamicBeamAnalysis.jl:119-121)
+    st = [([mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.2 if d == 0 else 0.3) for d in range(3)], 20. * mb.synthetic.uniform_pm1(99 + s, nU)) for s in range(nstep)]
+    Lam = [mb.synthetic.uniform_pm1(500 + s, nX) for s in range(nstep)]
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+    outs = [oracle_scr_direct_step(model, dis, weights, P, OX, OU, st[s][0], st[s][1], Lam[s], time[s], σu) for s in range(nstep)]
+    nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, t0=t0)
+    try:
+        cp, rv = eng.big_pattern()
+        assert np.array_equal(cp, big["colptr"]) and np.array_equal(rv, big["rowval"])
+        for s, (X, U) in enumerate(st):
+            eng.set_state(s, X, U)
+            eng.set_lambda(s, Lam[s])
+            eng.set_host_cost(s, *mb.directxua.host_costs(eng, s, X[0], U, time[s])[:4])
+            mb.directxua.host_elements(eng, s, X, Lam[s], time[s], model.scaleΛ)
+        Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
+        eng.direct_assemble(Lvv=Lvv, Lv=Lvec)
+        scale = np.abs(nz).max()
+        assert np.abs(Lvv - nz).max() <= 1e-12 * scale
+        assert np.abs(Lvec - Lv).max() <= 1e-12 * max(scale, np.abs(Lv).max())
+        W = 2 * nX + nU
+        assert np.abs(Lvec.reshape(nstep, W)[:, nX: 2 * nX]).max() > 0 and np.abs(Lvec.reshape(nstep, W)[:, 2 * nX:]).max() > 0
+    finally:
+        eng.close()
 
 
 def test_scr_oracle_loop_converges_on_cpu():
