@@ -131,6 +131,14 @@ int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda);
 int32_t mb_direct_get_state(mb_handle* h, int64_t step, double* X0, double* X1, double* X2, double* U0, double* Lambda);
 int32_t mb_direct_set_dof_scale(mb_handle* h, const double* scaleL, const double* scaleX, const double* scaleU);
 int32_t mb_direct_decrement(mb_handle* h, int64_t s0, int64_t s1, const double* dv, double* delta2);
+/* Sliding window over the time steps (BASELINE.json configs[3]: 2000 steps do not fit as one materialised Lvv).  Away from the first and last step
+ * finitediff (src/FiniteDifferences.jl:8-31) is the central stencil everywhere, so makepattern's block pattern (src/DirectXUA.jl:245-307) and the CSC
+ * structure of the owned columns (SparseTools.prepare, src/SparseTools.jl:32-94) of a window [lo,hi) with 3 ≤ lo, hi ≤ nstep−3 repeat for every such window
+ * up to a shift of the global row numbers.  mb_direct_rebase moves the handle to [new_lo, new_lo+hi−lo) without rebuilding anything: row_shift (added to
+ * the rowval the handle was built with; mb_direct_big_pattern / mb_direct_get_sparse export shifted rows) is returned, states and per-step blocks of steps
+ * stored before and after the move are kept, so a window advancing by its own length evaluates only its new steps
+ * (mb_direct_set_state + mb_direct_assemble(eval_lo = old stored end, eval_hi = new stored end)).  mb_direct_set_state also accepts device pointers. */
+int32_t mb_direct_rebase(mb_handle* h, int64_t new_lo, int64_t* row_shift_out);
 /* device pointers of the per-step blocks a neighbouring time-shard needs (halo exchange over NCCL): L2[Λ,X][1,:], L2[Λ,U][1,1], L1[Λ] */
 int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1);
 /* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build */

@@ -362,7 +362,7 @@ __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) 
 }
 // L2[X,X][1,1] / L2[U,U][1,1] of host-evaluated single-dof costs: one diagonal entry per dof, added to the (step,step) block
 __global__ void big_diag_kernel(BigDev B, int64_t ncol, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, double* __restrict__ nzval,
-                                unsigned long long* missing) {
+                                unsigned long long* missing, int64_t rowshift) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncol) return;
     int64_t step, lc; int cls;
@@ -370,7 +370,7 @@ __global__ void big_diag_kernel(BigDev B, int64_t ncol, const int64_t* __restric
     if (cls == 0) return;
     const double hd = B.hostc[(step - B.elo) * 2 * (B.nX + B.nU) + (cls == 1 ? B.nX : 2 * B.nX + B.nU) + lc];
     if (hd == 0.) return;
-    const int64_t row = step * B.W + (cls == 1 ? B.nX : 2 * B.nX) + lc;
+    const int64_t row = step * B.W + (cls == 1 ? B.nX : 2 * B.nX) + lc - rowshift;
     int64_t lo = colptr[c], hi = colptr[c + 1];
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < row) lo = mid + 1; else hi = mid; }
     if (lo < colptr[c + 1] && rowval[lo] == row) nzval[lo] += hd; else atomicAdd(missing, 1ULL);
@@ -450,7 +450,8 @@ struct DirectData {
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
     int32_t *bcolptr = nullptr, *browval = nullptr;
     int64_t ncol = 0, nnzbig = 0; int maxb = 0;         // maxb: most blocks in one block column
-    int64_t *colptr = nullptr, *rowval = nullptr;
+    int64_t *colptr = nullptr, *rowval = nullptr;       // rowval: global rows of the window the structure was BUILT for; + rowshift after mb_direct_rebase
+    int64_t rowshift = 0;
     double *nzval = nullptr, *Lv = nullptr;
 };
 
@@ -667,8 +668,8 @@ int32_t mb_direct_set_state(mb_handle* h, int64_t step, const double* X0, const 
     CK(cudaSetDevice(h->device));
     double* x = D->X + (step - D->elo) * 3 * D->nX;
     const double* src[3] = {X0, X1, X2};
-    for (int d = 0; d <= D->OX; ++d) { ARG(src[d], "state derivative missing"); CK(cudaMemcpyAsync(x + d * D->nX, src[d], (size_t)D->nX * 8, cudaMemcpyHostToDevice, h->stream)); }
-    if (U0 && D->nU) CK(cudaMemcpyAsync(D->U + (step - D->elo) * D->nU, U0, (size_t)D->nU * 8, cudaMemcpyHostToDevice, h->stream));
+    for (int d = 0; d <= D->OX; ++d) { ARG(src[d], "state derivative missing"); CK(cudaMemcpyAsync(x + d * D->nX, src[d], (size_t)D->nX * 8, cudaMemcpyDefault, h->stream)); }
+    if (U0 && D->nU) CK(cudaMemcpyAsync(D->U + (step - D->elo) * D->nU, U0, (size_t)D->nU * 8, cudaMemcpyDefault, h->stream));
     return MB_OK;
 }
 
@@ -764,7 +765,7 @@ int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32
         BigDev B = make_bigdev(D);
         launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
-        if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing); h->launches++; }
+        if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing, D->rowshift); h->launches++; }
         h->launches += 2;
         if (Lvv_nzval) CK(cudaMemcpyAsync(Lvv_nzval, D->nzval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost, h->stream));
         if (Lv) CK(cudaMemcpyAsync(Lv, D->Lv, (size_t)D->ncol * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -787,7 +788,7 @@ int32_t mb_direct_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
     DirectData* D = h->direct;
     CK(cudaSetDevice(h->device));
     if (colptr) { CK(cudaMemcpy(colptr, D->colptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
-    if (rowval) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1; }
+    if (rowval) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1 + D->rowshift; }
     return MB_OK;
 }
 // Host-evaluated X-class element types (Hold, DofLoad, DofConstraint: user closures, default no_second_order = Val(false)) in the second-order
@@ -958,7 +959,7 @@ int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, dou
     ARG(D->cnnz >= 0, "call mb_direct_sparser first");
     CK(cudaSetDevice(h->device));
     if (colptr) { CK(cudaMemcpy(colptr, D->ccolptr, (size_t)(D->ncol + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ncol; ++i) colptr[i] += 1; }
-    if (rowval && D->cnnz) { CK(cudaMemcpy(rowval, D->crowval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->cnnz; ++i) rowval[i] += 1; }
+    if (rowval && D->cnnz) { CK(cudaMemcpy(rowval, D->crowval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->cnnz; ++i) rowval[i] += 1 + D->rowshift; }
     if (nzval && D->cnnz) CK(cudaMemcpy(nzval, D->cnzval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost));
     return MB_OK;
 }
@@ -979,6 +980,55 @@ int32_t mb_direct_get_step_block(mb_handle* h, int64_t step, int32_t which, int3
     return MB_OK;
 }
 // device pointers and sizes of the per-step blocks, for the halo exchange between time-shards (NCCL send/recv of whole steps)
+// Slide the owned window of an INTERIOR handle to [new_lo, new_lo + (hi−lo)).  Away from the first and the last time step every finite-difference
+// stencil is the central one (src/FiniteDifferences.jl:8-31), so the block pattern of makepattern (src/DirectXUA.jl:245-307) and the CSC structure of the
+// owned columns repeat from window to window up to a shift of the global row numbers by (new_lo−lo)·(2·ndofX+ndofU): nothing is rebuilt, the shift is
+// applied when the structure is exported.  States and per-step blocks of the steps stored both before and after the move keep their values (a
+// window that advances by its own length keeps the four steps around its old right edge: only the new steps need set_state + evaluation).
+static __global__ void shift_i32_kernel(int64_t n, int32_t* __restrict__ a, int32_t d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += d;
+}
+int32_t mb_direct_rebase(mb_handle* h, int64_t new_lo, int64_t* row_shift_out) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    const int64_t len = D->hi - D->lo, delta = new_lo - D->lo, ns = D->ehi - D->elo;
+    ARG(D->lo >= 3 && D->hi <= D->nstep - 3, "only a handle whose stored steps exclude the first and the last time step can be moved");
+    ARG(new_lo >= 3 && new_lo + len <= D->nstep - 3, "the new window must stay clear of the first and the last time step (their stencils differ)");
+    if (row_shift_out) *row_shift_out = D->rowshift + delta * (2 * D->nX + D->nU);
+    if (delta == 0) return MB_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int nd = D->OX + 1;
+    const int64_t nbc = 3 * len;
+    int32_t nblocks = 0;
+    CK(cudaMemcpyAsync(&nblocks, D->bcolptr + nbc, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    shift_i32_kernel<<<nblk(nblocks, 256), 256, 0, st>>>(nblocks, D->browval, (int32_t)(3 * delta));
+    h->launches++;
+    // per-step arrays: slot of step s moves from s−elo to s−(elo+delta)
+    struct Arr { double* p; int64_t stride; };
+    std::vector<Arr> arrs = {{D->X, 3 * D->nX}, {D->U, D->nU}, {D->Lam, D->nX}, {D->LX, nd * D->pat[P_XX].nnz}, {D->XL, nd * D->pat[P_XX].nnz},
+                             {D->LU, D->pat[P_XU].nnz}, {D->UL, D->pat[P_UX].nnz}, {D->L1L, D->nX}, {D->L1X, nd * D->nX},
+                             {D->hostc, 2 * (D->nX + D->nU)}};
+    for (size_t ig = 0; ig < D->hoststore.size(); ++ig) {
+        if (!D->hoststore[ig]) continue;
+        const Group& g = h->groups[ig];
+        const int64_t nR = g.nele * g.nx;
+        arrs.push_back({D->hoststore[ig], nR + nR * g.nx * nd + nR * nd});
+    }
+    const int64_t k0 = delta > 0 ? delta : 0, k1 = delta > 0 ? ns : ns + delta;      // old slots that stay stored
+    for (const Arr& a : arrs) {
+        if (!a.p || a.stride == 0) continue;
+        if (delta > 0) for (int64_t k = k0; k < k1; ++k) CK(cudaMemcpyAsync(a.p + (k - delta) * a.stride, a.p + k * a.stride, (size_t)a.stride * 8, cudaMemcpyDeviceToDevice, st));
+        else for (int64_t k = k1 - 1; k >= k0; --k) CK(cudaMemcpyAsync(a.p + (k - delta) * a.stride, a.p + k * a.stride, (size_t)a.stride * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    D->lo += delta; D->hi += delta; D->elo += delta; D->ehi += delta;
+    D->rowshift += delta * (2 * D->nX + D->nU);
+    D->cnnz = -1;
+    CK(cudaGetLastError());
+    return MB_OK;
+}
 int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1) {
     if (!h || !h->direct) return MB_ERR_ARG;
     DirectData* D = h->direct;
@@ -1003,7 +1053,7 @@ int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms) {
         BigDev B = make_bigdev(D);
         launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
-        if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing); h->launches++; }
+        if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing, D->rowshift); h->launches++; }
         h->launches += 2;
         CK(cudaEventRecord(e2, h->stream));
         CK(cudaEventSynchronize(e2));

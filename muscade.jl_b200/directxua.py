@@ -119,6 +119,22 @@ class DirectEngine(Engine):
         check(self.h, self.L.mb_direct_decrement(self.h, int(s0), int(s1), ptr(dv), ptr(d2)))
         return d2
 
+    def rebase(self, new_lo):
+        """slide an interior window (3 ≤ lo, hi ≤ nstep−3) to [new_lo, new_lo+hi−lo): same Lvv structure, rows shifted → row shift relative to prepare"""
+        sh = C.c_int64()
+        check(self.h, self.L.mb_direct_rebase(self.h, int(new_lo), C.byref(sh)))
+        d = int(new_lo) - self.lo
+        self.lo += d; self.hi += d
+        return sh.value
+
+    def stored_range(self):
+        return max(0, self.lo - 2), min(self.nstep, self.hi + 2)
+
+    def set_state_dev(self, step, X_ptrs, U_ptr=None):
+        """set_state from device memory (raw device addresses, e.g. torch .data_ptr())"""
+        p = [C.c_void_p(int(a)) for a in X_ptrs] + [None] * (3 - len(X_ptrs))
+        check(self.h, self.L.mb_direct_set_state(self.h, int(step), p[0], p[1], p[2], C.c_void_p(int(U_ptr)) if U_ptr else None))
+
     def direct_set_host_elements(self, step, ityp, R, dR, GX):
         check(self.h, self.L.mb_direct_set_host_elements(self.h, int(step), int(ityp), ptr(_f64(R)), ptr(_f64(dR)), ptr(_f64(GX))))
 

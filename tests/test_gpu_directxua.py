@@ -104,6 +104,56 @@ def test_directxua_time_shard(mb, lo, hi):
     eng.close()
 
 
+def test_directxua_sliding_window(mb):
+    """mb_direct_rebase (BASELINE.json configs[3]: 2000 steps streamed through one window): a handle built for an interior window, moved forward by
+    its own length twice and then backward by an overlapping amount, yields the reference's Lvv columns / Lv rows of each window — structure
+    bit-exact (rows shifted), values ≤ 1e-12 — while evaluating only the steps that were not stored before the move."""
+    OX, OU, nstep, dt, N, L = 2, 0, 26, 0.07, 5, 5
+    model = udof_chain(mb, N, np.random.default_rng(3))
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)))
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU = model.getndof("X"), model.getndof("U")
+    st = states(mb, nX, nU, nstep)
+    P, big, outs, nz, Lv = oracle_all(mb, model, dis, OX, OU, nstep, dt, st)
+    W = 2 * nX + nU
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, 4, 4 + L)
+    stored = set()
+
+    def check(lo):
+        c0, c1 = lo * W, (lo + L) * W
+        p0, p1 = big["colptr"][c0] - 1, big["colptr"][c1] - 1
+        cp, rv = eng.big_pattern()
+        assert np.array_equal(cp - 1, big["colptr"][c0:c1 + 1] - 1 - p0) and np.array_equal(rv, big["rowval"][p0:p1])
+        new = [s for s in range(lo - 2, lo + L + 2) if s not in stored]
+        for s in new:
+            eng.set_state(s, st[s][0], st[s][1])
+        runs = []                                              # contiguous runs of new steps
+        for s in new:
+            if runs and runs[-1][1] == s: runs[-1][1] = s + 1
+            else: runs.append([s, s + 1])
+        for a, b in runs:
+            eng.direct_assemble(eval_range=(a, b), build_big=False)
+        Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
+        eng.direct_assemble(eval_range=(lo, lo), build_big=True, Lvv=Lvv, Lv=Lvec)
+        assert rel(Lvv, nz[p0:p1], np.abs(nz).max()) <= TOL
+        assert rel(Lvec, Lv[c0:c1], np.abs(nz).max()) <= TOL
+        stored.clear(); stored.update(range(lo - 2, lo + L + 2))
+        return len(new)
+
+    assert check(4) == L + 4
+    assert eng.rebase(4 + L) == L * W and check(4 + L) == L        # forward by the window length: only the L new steps are evaluated
+    assert eng.rebase(4 + 2 * L) == 2 * L * W and check(4 + 2 * L) == L
+    assert eng.rebase(11) == 7 * W and check(11) == 3                # backward, overlapping
+    assert eng.rebase(nstep - 3 - L) == (nstep - 3 - L - 4) * W and check(nstep - 3 - L) == 7      # up to the last movable position; two stored steps kept
+    with pytest.raises(Exception):
+        eng.rebase(nstep - 2 - L)                                    # would reach the last step, whose stencil is one-sided
+    eng.close()
+    edge = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, 0, L)
+    with pytest.raises(Exception):
+        edge.rebase(L)                                               # a window that contains step 0 cannot be moved
+    edge.close()
+
+
 @pytest.mark.parametrize("OX", [2, 0])
 def test_directxua_beam_bar_soil(mb, OX):
     """BASELINE.json configs[4] in small: EulerBeam3D{Udof} + Bar3D{Udof} + SoilContact on shared nodes through the DirectXUA first-order path
