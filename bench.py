@@ -12,8 +12,11 @@ N>1 (weak scaling): the chain has N·E elements, rank r owns elements [r·E,(r+1
 (78 doubles per cut, NCCL send/recv to the right neighbour) — sharding.py.
 Inputs/outputs per step (≈1.8 GB read, ≈20 GB written/re-read per GPU) exceed the 126 MB L2: no L2 flush needed.
 
-`--workload directxua` (BASELINE.json configs[3] shape): DirectXUA{2,0,0} assemblebig! of a Udof beam chain, time steps sharded over
-the ranks (16 steps per GPU), halo L2[Λ,X] blocks of 2 steps exchanged with each neighbour over NCCL.
+`--workload directxua` (BASELINE.json configs[3]): DirectXUA{2,0,0} assemblebig! of a 100k-element Udof beam chain over 2000 time steps, the
+steps sharded over the ranks (strong scaling).  The materialised FP64 Lvv of 2000 steps (2.9e11 non-zeros) does not fit on 8 x 180 GB, so every rank
+streams its steps through a window of 10 steps (1.4e9 non-zeros: 11.5 GB of values + 11.5 GB of row indices, handed to the solver window by window): mb_direct_rebase slides the
+window without rebuilding the structure and only the new steps are evaluated.  `--workload directxua_weak`: 16 steps per GPU, one window, halo
+L2[Λ,X] blocks of 2 steps exchanged with each neighbour over NCCL.
 
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, "port": Julia is not in this image) on the
 host cores, on a bounded sample of the same workload.
@@ -50,7 +53,9 @@ def parse():
     ap.add_argument("--workload", default="sweepx")
     ap.add_argument("--nele", type=float, default=None)
     ap.add_argument("--ox", type=int, default=0)
-    ap.add_argument("--steps-per-gpu", type=int, default=16)
+    ap.add_argument("--steps-per-gpu", type=int, default=16)      # directxua_weak
+    ap.add_argument("--nstep", type=int, default=2000)            # directxua: time steps of the whole problem (BASELINE.json configs[3])
+    ap.add_argument("--window", type=int, default=10)             # directxua: time steps per Lvv window
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -136,6 +141,19 @@ def run_reference(args, rank, world):
         return
     import muscade_b200 as mb
     from oracle import elements as OE
+    if args.workload.startswith("directxua"):
+        nsamp = max(50, args.cpu_sample // 4)
+        cpu_port_rate_direct(mb, 50)
+        times = [cpu_port_rate_direct(mb, nsamp)[1] for _ in range(args.steps)]
+        value = nsamp * len(times) / sum(times)
+        unit = "element-step assemblies/s"
+        print(json.dumps({"impl": "reference", "metric": "EulerBeam3D residual+Jacobian element-step assemblies/s (DirectXUA{2,0,0} assemblebig!)", "value": value,
+                          "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "DirectXUA{2,0,0}, bounded sample: one time step of %d EulerBeam3D{Udof} elements per step, oracle port, 1 thread" % nsamp},
+                          "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": "port", "sample": "%d element-steps x %d" % (nsamp, args.steps)},
+                          "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
     OX = args.ox
     # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1 for N>1, which must not shrink the reference arm (the other ranks idle)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -299,7 +317,190 @@ def run_sweepx(args, rank, world, local, dist):
     eng.close()
 
 
+def directxua_model(mb, N):
+    model = mb.Model()
+    nod = mb.addnode(model, np.arange(N + 1)[:, None] * np.array([.8, .6, 0.])[None, :])
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1., Ca2=169.6, Ca3=169.6, Cq2=235.2, Cq3=235.2)
+    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], unod], axis=1), mat=mat, Udof=True)
+    return model
+
+
+def cpu_port_rate_direct(mb, nsample):
+    """oracle (literal reference algorithm, DirectXUA.jl:85-120 with Np = 39 partials) on one time step of `nsample` elements, 1 thread"""
+    from oracle import elements as OE, pattern as OP
+    model = directxua_model(mb, nsample)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    P = OP.prepare_direct([dict(X=d.X, U=d.U, A=d.A) for d in dis.dis], nX, nU, nA, 2, 0, 0)
+    X = [mb.synthetic.uniform_pm1(10 + d, nX) * (0.05 if d == 0 else 0.1) for d in range(3)]; U = mb.synthetic.uniform_pm1(99, nU)
+    t = time.perf_counter()
+    OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, 2, 0, X, [U], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0)
+    dt = time.perf_counter() - t
+    return nsample / dt, dt
+
+
 def run_directxua(args, rank, world, local, dist):
+    """BASELINE.json configs[3]: DirectXUA{2,0,0} assemblebig! of N Udof beams over `nstep` time steps; rank r owns steps [r·nstep/world,(r+1)·nstep/world)
+    (strong scaling) and streams them through a sliding window of `window` steps.  One bench step = one pass over all time steps."""
+    import torch
+    import muscade_b200 as mb
+    OX, OU = 2, 0
+    N = int(args.nele or 1e5)
+    nstep = args.nstep
+    assert nstep % world == 0 and nstep // world >= 6
+    L, H = rank * nstep // world, (rank + 1) * nstep // world
+    Wn = max(w for w in range(1, min(args.window, H - L) + 1) if (H - L) % w == 0)
+    torch.cuda.set_device(local)
+    stream = torch.cuda.current_stream().cuda_stream
+    model = directxua_model(mb, N)
+    st0 = mb.initialize(model)
+    nX, nU = model.getndof("X"), model.getndof("U")
+    dtm = 0.1
+    windows = [(a, a + Wn) for a in range(L, H, Wn)]
+    interior = [w for w in windows if w[0] >= 3 and w[1] <= nstep - 3]
+    engines = {}
+
+    def make(lo, hi):
+        e = mb.directxua.prepare(OX, OU, model, st0.dis, nstep, dtm, lo, hi, device=local)
+        e.set_stream(stream)
+        return e
+    for w in windows:
+        if w not in interior:
+            engines[w] = make(*w)                      # contains the first or the last step: one-sided stencils, its own structure
+    e_int = make(*interior[0]) if interior else None
+    # synthetic states: a bank of B states resident in HBM, step s reads bank[s % B]; a pinned host copy feeds the e2e pass
+    B = 32
+    hostX = [[mb.synthetic.uniform_pm1(10 + 3 * b + d, nX) * (0.05 if d == 0 else 0.1) for d in range(3)] for b in range(B)]
+    hostU = [mb.synthetic.uniform_pm1(99 + b, nU) for b in range(B)]
+    devX = [[torch.from_numpy(x).cuda() for x in xs] for xs in hostX]
+    devU = [torch.from_numpy(u).cuda() for u in hostU]
+    nset = [0]
+
+    def set_dev(e, s):
+        e.set_state_dev(s, [x.data_ptr() for x in devX[s % B]], devU[s % B].data_ptr()); nset[0] += 1
+
+    def set_host(e, s):
+        e.set_state(s, hostX[s % B], hostU[s % B]); nset[0] += 1
+
+    def one_pass(setter, Lv_host=None):
+        """every window of this rank once: new states in, new steps evaluated, owned Lvv columns and Lv rows built"""
+        kept = (0, 0)
+        for w in windows:
+            if w in engines:
+                e = engines[w]; kept_w = (0, 0)
+            else:
+                e = e_int
+                if (e.lo, e.hi) != w:
+                    old = e.stored_range()
+                    e.rebase(w[0])
+                    new = e.stored_range()
+                    kept_w = (max(old[0], new[0]), min(old[1], new[1])) if e_int_valid[0] else (0, 0)
+                else:
+                    kept_w = (0, 0)
+                e_int_valid[0] = True
+            a, b = e.stored_range()
+            todo = [s for s in range(a, b) if not (kept_w[0] <= s < kept_w[1])]
+            for s in todo:
+                setter(e, s)
+            if todo:
+                e.direct_assemble(eval_range=(todo[0], todo[-1] + 1), build_big=False)      # the new steps are one contiguous run
+            e.direct_assemble(eval_range=(w[0], w[0]), build_big=True, Lv=Lv_host)
+
+    e_int_valid = [False]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        e_int_valid[0] = False
+        one_pass(set_dev)
+    barrier()
+    all_eng = list(engines.values()) + ([e_int] if e_int else [])
+    launches0 = sum(e.launch_count() for e in all_eng)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        e_int_valid[0] = False                         # every pass starts from scratch: nothing kept from the previous pass
+        one_pass(set_dev)
+    ev1.record(); torch.cuda.synchronize()
+    step_ms = ev0.elapsed_time(ev1) / args.steps
+    if dist is not None:
+        tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms = float(tt.item())
+    barrier()
+    launches = sum(e.launch_count() for e in all_eng) - launches0
+    clocks = sampler.stop() if sampler else None
+    # kernel breakdown on one window (CUDA events inside the engine)
+    et = e_int or all_eng[0]
+    a_ms, b_ms = et.direct_time(reps=2)
+    el_ms = et.last_element_ms
+    # e2e: the same pass through the C ABI with HOST buffers — states from pinned host memory, Lv rows back to the host; Lvv stays in HBM for the
+    # device solver (mb_get_device_ptrs), as it would in production: 29 GB per window over PCIe would only measure the bus
+    e2e = None
+    if not args.no_e2e:
+        Lvh = np.empty(et.ncol)
+        for arrs in hostX:
+            for x in arrs: et.pin(x)
+        for u in hostU: et.pin(u)
+        et.pin(Lvh)
+        e_int_valid[0] = False; one_pass(set_host, Lvh)
+        barrier()
+        n0 = nset[0]
+        t1 = time.perf_counter()
+        e_int_valid[0] = False; one_pass(set_host, Lvh)
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t1)
+        nset_pass = nset[0] - n0
+        if dist is not None:
+            tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item())
+        e2e = {"value": N * nstep / (e2e_ms * 1e-3), "unit": "element-step assemblies/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(nset_pass * 8 * (3 * nX + nU)), "d2h_bytes_per_step": int(len(windows) * 8 * et.ncol),
+               "note": "per rank: mb_direct_set_state from pinned host memory for every newly stored step, mb_direct_assemble with a host Lv; "
+                       "Lvv stays in HBM (device-pointer hand-off to the solver)"}
+    if rank == 0:
+        flops = load_flops("directxua")
+        nown = et.hi - et.lo
+        roof = {"bound": "fp64", "kernel": "beam_direct_cot_kernel<3> + beam_direct_b0_kernel<3> + beam_direct_lin_kernel<3>", "unit": "TFLOP/s",
+                "peak": et.fp64_tflops(), "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
+                "kernel_ms": el_ms, "kernel_ms_source": "CUDA events around the element kernels of one window (%d steps, 3 launches each) on the engine's stream" % nown,
+                "kernel_share_of_step": el_ms / (a_ms + b_ms), "traffic": None, "achieved": None, "frac": None}
+        if flops:
+            roof["flop_per_element"] = flops["flop"]; roof["fp64_inst_per_element"] = flops.get("fp64_inst")
+            roof["achieved"] = N * nown * flops["flop"] / (el_ms * 1e-3) / 1e12
+            roof["frac"] = roof["achieved"] / roof["peak"]
+            if flops.get("fp64_inst"):
+                roof["fp64_pipe_frac"] = N * nown * flops["fp64_inst"] * 2 / (el_ms * 1e-3) / 1e12 / roof["peak"]
+            if flops.get("dram_bytes_per_element"):
+                roof["traffic"] = int(N * flops["dram_bytes_per_element"]); roof["traffic_unit"] = "bytes per time step (dram read+write of the three launches, ncu)"
+        nsamp = max(50, args.cpu_sample // 4)
+        cpu_rate, cpu_dt = cpu_port_rate_direct(mb, nsamp)
+        line = {"metric": "EulerBeam3D residual+Jacobian element-step assemblies/s (DirectXUA{2,0,0} assemblebig!)", "value": N * nstep / (step_ms * 1e-3),
+                "unit": "element-step assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "DirectXUA{2,0,0} load identification, %d EulerBeam3D{Udof} elements x %d time steps (BASELINE.json configs[3]), time steps "
+                                       "sharded over %d GPU(s), each rank streaming its %d steps through a sliding window of %d steps (Lvv columns of the window "
+                                       "built on the device)" % (N, nstep, world, H - L, Wn),
+                           "elements": N, "nstep": nstep, "steps_per_gpu": H - L, "window": Wn, "lvv_nnz_per_window": int(et.nnzbig),
+                           "states": "bank of %d synthetic states resident in HBM, step s reads bank[s mod %d]" % (B, B),
+                           "l2": "per-step blocks and Lvv columns far larger than L2, no flush",
+                           "halo": "the 2+2 halo steps at a rank's edges are evaluated locally (no data-path collective)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+                "cpu_baseline": {"value": cpu_rate, "unit": "element-step assemblies/s", "cores": 1, "kind": "port",
+                                 "sample": "one time step of %d elements, oracle literal restatement (39 partials), 1 thread (%.1f s)" % (nsamp, cpu_dt)},
+                "breakdown_ms": {"window_elements_and_step_blocks": a_ms, "window_lvv_build": b_ms, "window_element_kernels": el_ms, "windows_per_rank": len(windows)}}
+        print(json.dumps(line), flush=True)
+    for e in all_eng:
+        e.close()
+
+
+def run_directxua_weak(args, rank, world, local, dist):
     """DirectXUA{2,0,0} assemblebig! with the time steps sharded over the ranks (weak: steps_per_gpu each)."""
     import muscade_b200 as mb
     OX, OU = 2, 0
@@ -397,6 +598,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.workload == "directxua":
         run_directxua(args, rank, world, local, dist)
+    elif args.workload == "directxua_weak":
+        run_directxua_weak(args, rank, world, local, dist)
     else:
         run_sweepx(args, rank, world, local, dist)
     if dist is not None:

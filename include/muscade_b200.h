@@ -141,7 +141,7 @@ int32_t mb_direct_decrement(mb_handle* h, int64_t s0, int64_t s1, const double* 
 int32_t mb_direct_rebase(mb_handle* h, int64_t new_lo, int64_t* row_shift_out);
 /* device pointers of the per-step blocks a neighbouring time-shard needs (halo exchange over NCCL): L2[Λ,X][1,:], L2[Λ,U][1,1], L1[Λ] */
 int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nLX, double** LU, int64_t* nLU, double** L1L, int64_t* nL1);
-/* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build */
+/* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build, ms[2] the element kernels alone (float ms[3]) */
 int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
 
 /* ---- sharding over the GPUs of one box (one handle per GPU / process; NCCL itself is driven by the host, torch.distributed or ncclComm) -- */

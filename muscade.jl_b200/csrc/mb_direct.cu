@@ -452,6 +452,7 @@ struct DirectData {
     int64_t ncol = 0, nnzbig = 0; int maxb = 0;         // maxb: most blocks in one block column
     int64_t *colptr = nullptr, *rowval = nullptr;       // rowval: global rows of the window the structure was BUILT for; + rowshift after mb_direct_rebase
     int64_t rowshift = 0;
+    bool elements_only = false;                         // timing aid: direct_eval_steps launches the element kernels without the per-step reductions
     double *nzval = nullptr, *Lv = nullptr;
 };
 
@@ -727,6 +728,7 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
             else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
             else h->launches += launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
         }
+        if (D->elements_only) continue;
         const PairPat& XX = D->pat[P_XX];
         if (XX.nnz) { gather_xx_kernel<<<nblk(XX.nnz, 256), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz); h->launches++; }
         const PairPat& XU = D->pat[P_XU];
@@ -1060,6 +1062,14 @@ int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms) {
         float x, y; CK(cudaEventElapsedTime(&x, e0, e1)); CK(cudaEventElapsedTime(&y, e1, e2)); a += x; b += y;
     }
     ms[0] = a / reps; ms[1] = b / reps;
+    // ms[2]: the element kernels of the owned steps alone (they write the one-step scratch dR/R only: the stored blocks stay valid)
+    D->elements_only = true;
+    CK(cudaEventRecord(e0, h->stream));
+    direct_eval_steps(h, D->lo, D->hi);
+    CK(cudaEventRecord(e1, h->stream));
+    D->elements_only = false;
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms[2], e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return MB_OK;
 }
