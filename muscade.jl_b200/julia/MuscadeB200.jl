@@ -165,4 +165,12 @@ function beam_results(out::AssemblySweepXB200{OX}, ieletyp::Integer, nele::Integ
     return res          # res[1,:] ε, res[2:10,:] rₛₘ, res[11:13,:] κ, then per Gauss point x, κgp, fᵢ, mᵢ, fₑ, mₑ
 end
 
+# Sliding window over the time steps of a DirectXUA problem too long to materialise (BASELINE configs[3]): `h` was prepared for an interior window
+# [lo,hi) (3 ≤ lo, hi ≤ nstep-3, 0-based); returns the shift to add to the rowval the handle was built with.
+function direct_rebase!(h::Ptr{Cvoid}, new_lo::Integer)
+    shift = Ref{Int64}(0)
+    check(h, ccall((:mb_direct_rebase, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}), h, new_lo, shift))
+    return shift[]
+end
+
 end # module
