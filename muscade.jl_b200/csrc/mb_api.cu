@@ -221,6 +221,11 @@ int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
     }
     h->nnz = nnz;
     CK(dalloc(h, &h->nzval, nnz));
+    {   // pair descriptors for the reduction, padded to whole threads (4 non-zeros)
+        const int64_t npp = 2 * ((nnz + 3) / 4);
+        CK(dalloc(h, &h->pdesc, std::max<int64_t>(2 * npp, 4)));
+        if (npp > 0) { pair_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(nnz, npp, h->cstart, h->src, h->pdesc); h->launches++; }
+    }
 
     // ---- vector map: contributors of every dof in element order (asmvec!, src/Assemble.jl:340-357)
     if (nvec > 0) {
@@ -373,7 +378,7 @@ static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkD
 // segmented reductions of non-zeros [k0,k1) (k0 a multiple of 4) and dofs [d0,d1)
 static void launch_gather_range(mb_handle* h, bool step, int64_t k0, int64_t k1, int64_t d0, int64_t d1, cudaStream_t st = nullptr) {
     if (!st) st = h->stream;
-    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->Ke, h->nzval + k0); h->launches++; }
+    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->pdesc + k0, h->Ke, h->nzval + k0); h->launches++; }
     if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, 256), 256, 0, st>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
 }
 static void launch_gather(mb_handle* h, bool step) { launch_gather_range(h, step, 0, h->nnz, 0, h->ndofX); }
