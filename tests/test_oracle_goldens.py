@@ -244,6 +244,31 @@ def test_directxua_prepare_and_big_pattern():
     assert bigasm["nzval"][150].tolist() == [595, 596, 615, 616, 635, 636, 655, 656, 681, 682, 707, 708]         # :135
 
 
+def test_big_pattern_repeats_over_interior_windows():
+    """The property mb_direct_rebase rests on, checked on the restatement of makepattern / SparseTools.prepare (src/DirectXUA.jl:245-307,
+    src/SparseTools.jl:32-94): away from the first and the last step the finite-difference stencils are central (src/FiniteDifferences.jl:8-31), so the
+    Lvv columns of the steps [lo,lo+L), 3 ≤ lo, lo+L ≤ nstep−3 (0-based) have the same structure for every lo, up to a shift of the row numbers by W per step."""
+    dis = _dis_directxua()
+    nX, nU, nstep, L = 2, 4, 14, 3
+    P = OP.prepare_direct(dis, nX, nU, 6, OX=2, OU=0, IA=0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+    W = 2 * nX + nU
+    assert big["n"] == nstep * W
+    cp, rv = big["colptr"], big["rowval"]
+
+    def window(lo):
+        c0, c1 = lo * W, (lo + L) * W
+        p0, p1 = cp[c0] - 1, cp[c1] - 1
+        return cp[c0:c1 + 1] - cp[c0], rv[p0:p1] - lo * W
+    ref = window(3)
+    for lo in range(4, nstep - 3 - L + 1):
+        w = window(lo)
+        assert np.array_equal(w[0], ref[0]) and np.array_equal(w[1], ref[1]), lo
+    for lo in (0, 2, nstep - 2 - L, nstep - L):            # windows that reach the one-sided stencils at either end differ
+        w = window(lo)
+        assert not (np.array_equal(w[0], ref[0]) and np.array_equal(w[1], ref[1])), lo
+
+
 # ------------------------------------------------------------------------------------------------ test/TestBarElement.jl
 def test_bar_element_goldens():
     EAb, L0, mub = 10., 2., 1.
