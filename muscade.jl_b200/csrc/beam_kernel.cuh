@@ -188,7 +188,10 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 // next element's dof indices / state / geometry (21.4 ms: long_scoreboard 1.49 → 1.00 per issue as intended, but no_instruction 0.37 → 1.12 —
 // the 76 KB loop body thrashes the 32 KB instruction cache when every warp of the SM loops over it instead of streaming through it once);
 // CTA shapes 64×4 / 256×1 / 96×2 / 96×3 / 288×1 (6.90 / 7.39 / 7.57 / 7.72 / 8.24 ms against 6.92 ms at 4 M elements); pulling the inputs of the element
-// one grid wave ahead into L2 (prefetch.global.L2 of geometry / index lines at entry, of the far state entries at exit: 6.96 ms, no gain).
+// one grid wave ahead into L2 (prefetch.global.L2 of geometry / index lines at entry, of the far state entries at exit: 6.96 ms, no gain);
+// persistent CTAs again, this time with ONE __syncthreads per tile: as a plain loop +3.7 %, with a two-stage cp.async prefetch of the next tiles' dof indices,
+// geometry and gathered state (one shared-memory copy per element) +10 % — long_scoreboard 0.98 → 0.77 per issue as intended, but no_instruction 0.37 → 1.10 again:
+// the back edge over the 76 KB body, not warp drift, is what the instruction fetch does not cope with.
 template <int MINB>          // resident CTAs per SM the register allocation aims at (template also so that only the ND = 1 translation unit compiles it)
 __global__ void __launch_bounds__(MB_BLOCK, MINB)
 beam_static_sym_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase) {
