@@ -125,6 +125,10 @@ int32_t mb_direct_set_host_cost(mb_handle* h, int64_t step, const double* gX, co
  *   R  [nele][nx]          Rᵢ·scale.Λᵢ → L1[Λ];     GX [nele][nx][nd]   Σₖ Λₖ·∂Rₖ/∂X_der,ᵢ·scale.Xᵢ → L1[X][der+1];
  *   dR [nele][nd·nx][nx]   ∂Rᵢ/∂X_der,ⱼ·scale.Λᵢ·scale.Xⱼ at [(nx·der+j)][i] → L2[Λ,X][1,der+1] and, transposed, L2[X,Λ][der+1,1].  NULL = zeros. */
 int32_t mb_direct_set_host_elements(mb_handle* h, int64_t step, int32_t ieletyp, const double* R, const double* dR, const double* GX);
+/* The X-X part of the same branch for host-evaluated types that are NOT linear in X (DofConstraint in `positive` mode, curved gaps; src/DirectXUA.jl:121-150):
+ * L2[X,X][1,1](i,j) += Σₖ Λₖ·∂²Rₖ/∂Xᵢ∂Xⱼ·scale.Xᵢ·scale.Xⱼ as triplets (1-based model X dofs), one per (i,j) — the caller sums its elements in element order.
+ * Replaces what was set for this step; n = 0 clears. Merged into the (step,step) X-X block of Lvv by mb_direct_assemble. */
+int32_t mb_direct_set_host_xx(mb_handle* h, int64_t step, int64_t n, const int64_t* i, const int64_t* j, const double* v);
 int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
 int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
 int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda);

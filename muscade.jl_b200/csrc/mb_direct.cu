@@ -8,6 +8,7 @@
 // one warp per Lvv column walks the blocks of that column and writes each value as the fixed-order weighted sum
 // Σ_der w·Δt^(−der)·block_der[ilv] — deterministic, no atomics, no nnz-sized index map (the map is implicit in the block layout).
 #include <algorithm>
+#include <map>
 #include "mb_internal.h"
 #include <cub/cub.cuh>
 
@@ -376,6 +377,18 @@ __global__ void big_diag_kernel(BigDev B, int64_t ncol, const int64_t* __restric
     if (lo < colptr[c + 1] && rowval[lo] == row) nzval[lo] += hd; else atomicAdd(missing, 1ULL);
 }
 
+// L2[X,X][1,1] entries of host-evaluated element types (mb_direct_set_host_xx): unique (i,j) per step, added to the (step,step) X-X block
+__global__ void big_xx_kernel(BigDev B, int64_t n, const int32_t* __restrict__ ii, const int32_t* __restrict__ jj, const double* __restrict__ v, int64_t step,
+                              const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, double* __restrict__ nzval, unsigned long long* missing, int64_t rowshift) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int64_t c = (step - B.lo) * B.W + B.nX + jj[q];
+    const int64_t row = step * B.W + B.nX + ii[q] - rowshift;
+    int64_t lo = colptr[c], hi = colptr[c + 1];
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < row) lo = mid + 1; else hi = mid; }
+    if (lo < colptr[c + 1] && rowval[lo] == row) nzval[lo] += v[q]; else atomicAdd(missing, 1ULL);
+}
+
 // ---------------------------------------------------------------------------------------------------------------- sparser! / decrementbig!
 // sparser!(T,S,rtol) (src/SparseTools.jl:172-199): keep |nzval| ≥ rtol·max|S|, order preserved, colptr shifted by the drops before it
 struct AbsF { __host__ __device__ double operator()(double x) const { return fabs(x); } };
@@ -445,6 +458,8 @@ struct DirectData {
     double *scL = nullptr, *scX = nullptr, *scU = nullptr, *dvbuf = nullptr; int64_t dvlen = 0;
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;   // sparser! result
     double* hostc = nullptr; unsigned long long* missing = nullptr;
+    struct HostXX { int64_t n = 0; int32_t *i = nullptr, *j = nullptr; double* v = nullptr; };
+    std::map<int64_t, HostXX> hostxx;                   // per (absolute) step: pre-summed L2[X,X][1,1] entries of host-evaluated types that are not linear in X
     std::vector<double*> hoststore;                     // per host-evaluated type: [stored step][R(nele·nx) | dR(nele·nx·nx·nd) | GX(nele·nx·nd)] or nullptr
     double *GX = nullptr, *L1X = nullptr; uint32_t *vstart2 = nullptr, *vsrc2 = nullptr; int64_t ngx = 0; double lamscale = 1.;   // second-order types
     double *LX = nullptr, *XL = nullptr, *LU = nullptr, *UL = nullptr, *L1L = nullptr;
@@ -768,16 +783,22 @@ int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32
         launch_big_values(B, D->ncol, D->colptr, D->nzval, D->maxb, h->stream);
         big_vec_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->Lv);
         if (D->hostc) { big_diag_kernel<<<nblk(D->ncol, 256), 256, 0, h->stream>>>(B, D->ncol, D->colptr, D->rowval, D->nzval, D->missing, D->rowshift); h->launches++; }
+        for (const auto& kv : D->hostxx) {
+            if (kv.first < D->lo || kv.first >= D->hi || kv.second.n == 0) continue;       // halo steps: their columns belong to a neighbour
+            big_xx_kernel<<<nblk(kv.second.n, 256), 256, 0, h->stream>>>(B, kv.second.n, kv.second.i, kv.second.j, kv.second.v, kv.first, D->colptr, D->rowval, D->nzval,
+                                                                          D->missing, D->rowshift);
+            h->launches++;
+        }
         h->launches += 2;
         if (Lvv_nzval) CK(cudaMemcpyAsync(Lvv_nzval, D->nzval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost, h->stream));
         if (Lv) CK(cudaMemcpyAsync(Lv, D->Lv, (size_t)D->ncol * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaGetLastError());
     rc = mb_sync(h, where);
-    if (rc == MB_OK && build_big && D->hostc) {
+    if (rc == MB_OK && build_big && D->missing) {
         unsigned long long miss = 0;
         CK(cudaMemcpy(&miss, D->missing, 8, cudaMemcpyDeviceToHost));
-        if (miss) { CK(cudaMemset(D->missing, 0, 8)); h->err = "a host-evaluated cost sits on a dof whose diagonal is not in the Lvv pattern (no device element touches it)"; return MB_ERR_ARG; }
+        if (miss) { CK(cudaMemset(D->missing, 0, 8)); h->err = "a host-evaluated cost or X-X entry is not in the Lvv pattern (no element added with mb_add_* couples these dofs)"; return MB_ERR_ARG; }
     }
     if (rc == MB_ERR_NAN && where) {     // nanbase packs (step, ieletyp, iele)
         const unsigned long long f = *h->nanflag_host;
@@ -820,6 +841,31 @@ int32_t mb_direct_set_host_elements(mb_handle* h, int64_t step, int32_t ieletyp,
     CK(cudaStreamSynchronize(h->stream));
     return MB_OK;
 }
+// Host-evaluated element types whose residual is NOT linear in X (DofConstraint in `positive` mode, curved gaps): the X-X part of the second-order branch
+// (src/DirectXUA.jl:121-150), L2[X,X][1,1](i,j) += Σₖ Λₖ·∂²Rₖ/∂Xᵢ∂Xⱼ·scale.Xᵢ·scale.Xⱼ, as triplets with 1-based model X dofs — ONE triplet per (i,j), the caller
+// sums the contributions of its elements in element order.  Replaces what was set for this step; n = 0 clears it.
+int32_t mb_direct_set_host_xx(mb_handle* h, int64_t step, int64_t n, const int64_t* i, const int64_t* j, const double* v) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(step >= D->elo && step < D->ehi && n >= 0 && (n == 0 || (i && j && v)), "step not stored on this handle / bad triplets");
+    CK(cudaSetDevice(h->device));
+    DirectData::HostXX& x = D->hostxx[step];
+    if (x.i) { dfree(h, x.i); dfree(h, x.j); dfree(h, x.v); x = DirectData::HostXX(); }
+    if (n == 0) { D->hostxx.erase(step); return MB_OK; }
+    std::vector<int32_t> ii((size_t)n), jj((size_t)n);
+    for (int64_t q = 0; q < n; ++q) {
+        ARG(i[q] >= 1 && i[q] <= D->nX && j[q] >= 1 && j[q] <= D->nX, "X dof out of range");
+        ii[(size_t)q] = (int32_t)(i[q] - 1); jj[(size_t)q] = (int32_t)(j[q] - 1);
+    }
+    CK(dalloc(h, &x.i, n)); CK(dalloc(h, &x.j, n)); CK(dalloc(h, &x.v, n));
+    CK(cudaMemcpyAsync(x.i, ii.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(x.j, jj.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(x.v, v, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    x.n = n;
+    if (!D->missing) { CK(dalloc(h, &D->missing, 1)); CK(cudaMemsetAsync(D->missing, 0, 8, h->stream)); }
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
 // host-evaluated single-dof costs of one stored step (SingleDofCost on X or U dofs, src/BasicElements.jl:198-208): gradient → L1[X][1] / L1[U][1],
 // second derivative → the diagonal of L2[X,X][1,1] / L2[U,U][1,1]; dense per-dof vectors, already multiplied by the dof scales; NULL = zeros
 int32_t mb_direct_set_host_cost(mb_handle* h, int64_t step, const double* gX, const double* hX, const double* gU, const double* hU) {
@@ -830,7 +876,7 @@ int32_t mb_direct_set_host_cost(mb_handle* h, int64_t step, const double* gX, co
     const int64_t per = 2 * (D->nX + D->nU), ns = D->ehi - D->elo;
     if (!D->hostc) {
         CK(dalloc(h, &D->hostc, ns * per)); CK(cudaMemsetAsync(D->hostc, 0, (size_t)(ns * per) * 8, h->stream));
-        CK(dalloc(h, &D->missing, 1)); CK(cudaMemsetAsync(D->missing, 0, 8, h->stream));
+        if (!D->missing) { CK(dalloc(h, &D->missing, 1)); CK(cudaMemsetAsync(D->missing, 0, 8, h->stream)); }
     }
     double* base = D->hostc + (step - D->elo) * per;
     const double* src[4] = {gX, hX, gU, hU}; const int64_t off[4] = {0, D->nX, 2 * D->nX, 2 * D->nX + D->nU}; const int64_t n[4] = {D->nX, D->nX, D->nU, D->nU};
@@ -1026,6 +1072,9 @@ int32_t mb_direct_rebase(mb_handle* h, int64_t new_lo, int64_t* row_shift_out) {
         else for (int64_t k = k1 - 1; k >= k0; --k) CK(cudaMemcpyAsync(a.p + (k - delta) * a.stride, a.p + k * a.stride, (size_t)a.stride * 8, cudaMemcpyDeviceToDevice, st));
     }
     D->lo += delta; D->hi += delta; D->elo += delta; D->ehi += delta;
+    for (auto it = D->hostxx.begin(); it != D->hostxx.end();) {
+        if (it->first < D->elo || it->first >= D->ehi) { dfree(h, it->second.i); dfree(h, it->second.j); dfree(h, it->second.v); it = D->hostxx.erase(it); } else ++it;
+    }
     D->rowshift += delta * (2 * D->nX + D->nU);
     D->cnnz = -1;
     CK(cudaGetLastError());

@@ -138,6 +138,11 @@ class DirectEngine(Engine):
     def direct_set_host_elements(self, step, ityp, R, dR, GX):
         check(self.h, self.L.mb_direct_set_host_elements(self.h, int(step), int(ityp), ptr(_f64(R)), ptr(_f64(dR)), ptr(_f64(GX))))
 
+    def set_host_xx(self, step, i, j, v):
+        """L2[X,X][1,1] entries (1-based X dofs, one per (i,j), already scaled) of host-evaluated types that are not linear in X; empty lists clear"""
+        i = np.ascontiguousarray(i, np.int64); j = np.ascontiguousarray(j, np.int64); v = _f64(np.asarray(v, float))
+        check(self.h, self.L.mb_direct_set_host_xx(self.h, int(step), len(i), ptr(i), ptr(j), ptr(v)))
+
     def set_host_cost(self, step, gX=None, hX=None, gU=None, hU=None):
         check(self.h, self.L.mb_direct_set_host_cost(self.h, int(step), ptr(_f64(gX)), ptr(_f64(hX)), ptr(_f64(gU)), ptr(_f64(hU))))
 
@@ -231,12 +236,22 @@ def host_costs(eng, step, X0, U0, t):
 
 
 def host_elements(eng, step, X, Lam, t, Λscale):
-    """second-order branch (DirectXUA.jl:152-171) of the host-evaluated X-class types whose residual is linear in X (Hold, DofLoad):
+    """second-order branch (DirectXUA.jl:152-171) of the host-evaluated X-class types (Hold, DofLoad, DofConstraint{:X}; L2[X,X] through `hessian` where R is not linear in X):
     L = Λ∘R ⇒ L1[Λ] = R·sΛ, L1[X][der] = (∂R/∂X_der)ᵀΛ·sX, L2[Λ,X][1,der] = ∂R/∂X_der·sΛ·sX (and its transpose in L2[X,Λ])"""
     nd = eng.OX + 1
+    xx = {}                                     # (i,j) → Σ over elements, in element order (types whose residual is not linear in X)
     for ityp, et, ed in eng.host_types:
         Xe = [X[d][ed.X - 1] for d in range(nd)]
         R, K0, K1, K2 = et.ElType.residual(et.extra if et.extra is not None else et.eleobj, Xe, t)
+        hess = getattr(et.ElType, "hessian", None)
+        H = hess(et.extra if et.extra is not None else et.eleobj, Xe, Lam[ed.X - 1], t) if hess else None
+        if H is not None:                       # L2[X,X][1,1] += Λ·∂²R/∂X²·sX·sX  (DirectXUA.jl:121-150)
+            H = H * ed.scaleX[None, :, None] * ed.scaleX[None, None, :]
+            for e in range(H.shape[0]):
+                for a in range(H.shape[1]):
+                    for b in range(H.shape[2]):
+                        key = (int(ed.X[e, a]), int(ed.X[e, b]))
+                        xx[key] = xx.get(key, 0.) + H[e, a, b]
         nele, nx = R.shape
         sX = ed.scaleX; sL = ed.scaleX * Λscale
         lam = Lam[ed.X - 1]
@@ -247,6 +262,10 @@ def host_elements(eng, step, X, Lam, t, Λscale):
             dR[:, nx * der: nx * (der + 1), :] = (K * sL[None, :, None] * sX[None, None, :]).transpose(0, 2, 1)      # [e][(nx·der+j)][i]
             GX[:, :, der] = np.einsum("ek,eki->ei", lam, K) * sX[None, :]
         eng.direct_set_host_elements(step, ityp, R * sL[None, :], dR, GX)
+    if xx or getattr(eng, "_had_xx", False):
+        keys = list(xx.keys())
+        eng.set_host_xx(step, [k[0] for k in keys], [k[1] for k in keys], [xx[k] for k in keys])
+        eng._had_xx = True
 
 
 def solve(OX, OU, initialstate, time, maxiter=50, maxΔλ=1e-5, maxΔx=1e-5, maxΔu=1e-5, verbose=False, device=0, sparser_rtol=1e-20):

@@ -235,6 +235,32 @@ class DofConstraint(ElementType):
             raise ValueError("DofConstraint: mode must be equal, positive or off")
         return R, K, None, None
 
+    @staticmethod
+    def hessian(extra, X, lam_e, t):
+        """H[e,i,j] = Σₖ Λₖ·∂²Rₖ/∂Xᵢ∂Xⱼ for the second-order branch of DirectXUA (L = Λ∘R, src/DirectXUA.jl:152-171; src/Assemble.jl:721-726), element dofs
+        (x₁…x_Nx, λ), lam_e (nele,Nx+1) = Λ at the element dofs.  Exact for gaps up to second degree (∂³g/∂x³ is not asked from the closure); None when R is
+        linear in (x,λ)."""
+        Nx = extra["Nx"]
+        x, lam = X[0][:, :Nx], X[0][:, Nx]
+        n = x.shape[0]
+        m = extra["mode"](t) if callable(extra["mode"]) else extra["mode"]
+        res = extra["gap"](x, t, *extra["gargs"])
+        curved = len(res) > 2 and np.any(np.asarray(res[2]) != 0)
+        if m == "off" or (m == "equal" and not curved):
+            return None
+        dg = np.broadcast_to(np.asarray(res[1], float), (n, Nx))
+        d2g = np.broadcast_to(np.asarray(res[2], float), (n, Nx, Nx)) if len(res) > 2 else np.zeros((n, Nx, Nx))
+        H = np.zeros((n, Nx + 1, Nx + 1))
+        Lx, Ll = lam_e[:, :Nx], lam_e[:, Nx]
+        cross = -np.einsum("ei,eij->ej", Lx, d2g)                        # Σᵢ Λᵢ·∂²(−∂g/∂xᵢ·λ)/∂xⱼ∂λ
+        if m == "equal":                                                   # R = (−∂g/∂x·λ, −g)
+            H[:, :Nx, :Nx] = -d2g * Ll[:, None, None]
+        else:                                                              # positive: R = (−∂g/∂x·λ, −g·λ)
+            H[:, :Nx, :Nx] = -d2g * (Ll * lam)[:, None, None]
+            cross = cross - dg * Ll[:, None]
+        H[:, :Nx, Nx] = cross; H[:, Nx, :Nx] = cross
+        return H
+
 
 class DofLoad(ElementType):
     """DofLoad(nod;field,value)  (src/BasicElements.jl:275-284): R = (−value(t)); plain Float64 residual ⇒ no tangent."""

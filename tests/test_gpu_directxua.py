@@ -154,6 +154,81 @@ def test_directxua_sliding_window(mb):
     edge.close()
 
 
+def test_directxua_curved_constraints(mb):
+    """Host-evaluated element types that are NOT linear in X on DirectXUA's second-order branch (L = Λ∘R, src/DirectXUA.jl:152-171, src/Assemble.jl:721-726):
+    DofConstraint{:X} (src/BasicElements.jl:425-438) in `positive` mode and in `equal` mode with a quadratic gap (plus one switched `off`) on a Udof beam chain.
+    Besides L1[Λ], L1[X], L2[Λ,X], L2[X,Λ] they feed L2[X,X] = Λ·∂²R/∂X² (mb_direct_set_host_xx).  Lvv and Lv against the oracle, constraints restated by hand."""
+    OX, OU, nstep, dt, N, t0 = 2, 0, 7, 0.1, 4, 0.3
+    model = udof_chain(mb, N, np.random.default_rng(7))
+    nod = np.arange(1, N + 2)
+    cons = [("positive", 2, "t2", (0.4, 0.3, 0.1, -0.05)), ("equal", 3, "t3", (0.5, -0.2, 0.0, 0.02)), ("off", 1, "t1", (0.0, 1.0, 0.0, 0.0))]
+
+    def gapfun(c):
+        a, b, c0, ct = c
+        return lambda x, t: (a * x[:, 0] ** 2 + b * x[:, 0] + c0 + ct * t, (2 * a * x + b), np.full((x.shape[0], 1, 1), 2 * a))
+    for mode, inod, field, c in cons:
+        mb.addelement(model, mb.DofConstraint, [nod[inod]], xinod=(1,), xfield=(field,), λinod=1, λclass="X", λfield="λ" + field, gap=gapfun(c), mode=mode)
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2., λt2=3., λt3=.5), U=dict(t1=5., t2=5., t3=5.)), Λscale=4.)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    st = states(mb, nX, nU, nstep)
+    Lam = [mb.synthetic.uniform_pm1(700 + s, nX) for s in range(nstep)]
+    time = t0 + dt * np.arange(nstep)
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+    A = P["asm"]; sL, sX = dis.scaleΛ, dis.scaleX
+    nnzXX = len(P["pat"][(2, 2)][3])
+    outs = []
+    for s, (X, U) in enumerate(st):
+        o = OE.direct_out_zeros(P, OX, OU)
+        OE.direct_assemble_step_beams(model.ele[0].eleobj, dis.dis[0].X, dis.dis[0].U, OX, OU, X[: OX + 1], [U], dis.dis[0].scaleX, dis.dis[0].scaleU, P, 0, out=o)
+        o["L1"][2] = np.zeros((OX + 1, nX)); hxx = np.zeros(nnzXX)
+        for k, (mode, inod, field, (a, b, c0, ct)) in enumerate(cons, start=1):
+            ix = dis.dis[k].X[0] - 1
+            x, lam = X[0][ix[0]], X[0][ix[1]]
+            g, dg, d2g = a * x * x + b * x + c0 + ct * time[s], 2 * a * x + b, 2 * a
+            L1, L2 = Lam[s][ix]
+            if mode == "positive":
+                R = np.array([-dg * lam, -g * lam]); K = np.array([[-d2g * lam, -dg], [-dg * lam, -g]])
+                H = np.array([[L2 * (-d2g * lam), L1 * (-d2g) + L2 * (-dg)], [L1 * (-d2g) + L2 * (-dg), 0.]])
+            elif mode == "equal":
+                R = np.array([-dg * lam, -g]); K = np.array([[-d2g * lam, -dg], [-dg, 0.]])
+                H = np.array([[L2 * (-d2g), L1 * (-d2g)], [L1 * (-d2g), 0.]])
+            else:
+                R = np.array([0., -lam]); K = np.array([[0., 0.], [0., -1.]]); H = np.zeros((2, 2))
+            aL, aXv, aLX, aXL, aXX = (A[OP.arrnum(1)][k][:, 0], A[OP.arrnum(2)][k][:, 0], A[OP.arrnum(1, 2)][k][:, 0], A[OP.arrnum(2, 1)][k][:, 0],
+                                      A[OP.arrnum(2, 2)][k][:, 0])
+            for i in range(2):
+                o["L1"][1][aL[i] - 1] += R[i] * sL[ix[i]]
+                o["L1"][2][0, aXv[i] - 1] += (K[:, i] @ Lam[s][ix]) * sX[ix[i]]
+                for j in range(2):
+                    o["L2"][(1, 2)][0, aLX[i + 2 * j] - 1] += K[i, j] * sL[ix[i]] * sX[ix[j]]
+                    o["L2"][(2, 1)][0, aXL[j + 2 * i] - 1] += K[i, j] * sL[ix[i]] * sX[ix[j]]
+                    hxx[aXX[i + 2 * j] - 1] += H[i, j] * sX[ix[i]] * sX[ix[j]]
+        o["L2"][(2, 2)] = {(1, 1): hxx}
+        outs.append(o)
+    nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+    assert max(np.abs(o["L2"][(2, 2)][(1, 1)]).max() for o in outs) > 1e-3
+
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, t0=t0)
+    try:
+        cp, rv = eng.big_pattern()
+        assert np.array_equal(cp, big["colptr"]) and np.array_equal(rv, big["rowval"])
+        for s, (X, U) in enumerate(st):
+            eng.set_state(s, X, U); eng.set_lambda(s, Lam[s])
+            mb.directxua.host_elements(eng, s, X, Lam[s], time[s], model.scaleΛ)
+        Lvv = np.zeros(eng.nnzbig); Lvec = np.zeros(eng.ncol)
+        eng.direct_assemble(Lvv=Lvv, Lv=Lvec)
+        assert rel(Lvv, nz) <= TOL, rel(Lvv, nz)
+        assert rel(Lvec, Lv, np.abs(nz).max()) <= TOL
+        Lvv2 = np.zeros(eng.nnzbig)
+        eng.direct_assemble(Lvv=Lvv2)
+        assert np.array_equal(Lvv, Lvv2)          # the X-X entries are added once per assembly, not accumulated
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("OX", [2, 0])
 def test_directxua_beam_bar_soil(mb, OX):
     """BASELINE.json configs[4] in small: EulerBeam3D{Udof} + Bar3D{Udof} + SoilContact on shared nodes through the DirectXUA first-order path
