@@ -70,68 +70,112 @@ template <int ND, class S> MB_HD void bar_residual(const double* geo8, const Bar
     for (int i = 0; i < 3; ++i) { S q = k * d0[i]; R[i] = R[i] - q; R[3 + i] = R[3 + i] + q; }
 }
 
+// One thread per element, dense Dual<6|7>.  A thread's 36 tangent entries are contiguous in Ke, so stored directly every warp store instruction would touch
+// 32 different sectors (stride 288 bytes); the warp stages its 32 × 36 (+ 32 × 6 residual) values in shared memory and writes them out as contiguous 256-byte
+// rows instead (2.43 → see profiles/r1_bar_soil_hbm.jsonl at 10 M elements).
+constexpr int BAR_TS = 37;      // tile row stride in doubles (36 + 1: lanes hit different banks)
 template <int ND, bool STEP>
 __global__ void __launch_bounds__(128)
 bar_kernel(BarGroupDev g, StateDev st, NewmarkDev nm, double t, double* __restrict__ Ke, double* __restrict__ Re, double* __restrict__ Rp,
            unsigned long long* nanflag, unsigned long long nanbase) {
     constexpr int W = 6 + (STEP ? 1 : 0);
+    __shared__ double tileK[4][32 * BAR_TS];
+    __shared__ double tileR[4][32 * 6];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.nele) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e0 = e - lane;
+    if (e0 >= g.nele) return;                                  // whole warp beyond the end
+    const bool active = e < g.nele;
     using S = Dual<W>;
-    double geo8[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) geo8[k] = g.geo[e * 8 + k];
-    const BarMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
-    S X[3][6], U[3], R[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int32_t d = g.idxX[e * 6 + i];
-        const double x0 = st.X0[d], x1 = (ND >= 2) ? st.X1[d] : 0., x2 = (ND >= 3) ? st.X2[d] : 0.;
-        X[0][i] = Make<S>::c(x0); X[1][i] = Make<S>::c(x1); X[2][i] = Make<S>::c(x2);
-        X[0][i].d[i] = g.scaleX[i]; X[1][i].d[i] = nm.a1 * g.scaleX[i]; X[2][i].d[i] = nm.b1 * g.scaleX[i];
-        if (STEP) { X[1][i].d[W - 1] = nm.a2 * x1 + nm.a3 * x2; X[2][i].d[W - 1] = nm.b2 * x1 + nm.b3 * x2; }
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) U[i] = Make<S>::c((g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.);
-    bar_residual<ND, S>(geo8, m, X, g.udof != 0, U, t, R);
     bool bad = false;
+    double rp[6] = {0., 0., 0., 0., 0., 0.};                   // :step only: −∂R/∂r, staged after the residual
+    if (active) {
+        double geo8[8];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const double s = g.scaleX[i];
-        double v = R[i].v * s; bad |= (v != v); Re[e * 6 + i] = v;
+        for (int k = 0; k < 8; ++k) geo8[k] = g.geo[e * 8 + k];
+        const BarMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+        S X[3][6], U[3], R[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { double k = R[i].d[j] * s; bad |= (k != k); Ke[e * 36 + i + 6 * j] = k; }
-        if (STEP) { double p = R[i].d[W - 1] * s; bad |= (p != p); Rp[e * 6 + i] = p; }
+        for (int i = 0; i < 6; ++i) {
+            const int32_t d = g.idxX[e * 6 + i];
+            const double x0 = st.X0[d], x1 = (ND >= 2) ? st.X1[d] : 0., x2 = (ND >= 3) ? st.X2[d] : 0.;
+            X[0][i] = Make<S>::c(x0); X[1][i] = Make<S>::c(x1); X[2][i] = Make<S>::c(x2);
+            X[0][i].d[i] = g.scaleX[i]; X[1][i].d[i] = nm.a1 * g.scaleX[i]; X[2][i].d[i] = nm.b1 * g.scaleX[i];
+            if (STEP) { X[1][i].d[W - 1] = nm.a2 * x1 + nm.a3 * x2; X[2][i].d[W - 1] = nm.b2 * x1 + nm.b3 * x2; }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) U[i] = Make<S>::c((g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.);
+        bar_residual<ND, S>(geo8, m, X, g.udof != 0, U, t, R);
+        double* tk = tileK[warp] + lane * BAR_TS;
+        double* tr = tileR[warp] + lane * 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double s = g.scaleX[i];
+            double v = R[i].v * s; bad |= (v != v); tr[i] = v;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { double k = R[i].d[j] * s; bad |= (k != k); tk[i + 6 * j] = k; }
+            if (STEP) { double p = R[i].d[W - 1] * s; bad |= (p != p); rp[i] = p; }
+        }
+    }
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, g.nele - e0);
+    {
+        double* dst = Ke + e0 * 36; const double* src = tileK[warp];
+        for (int q = lane; q < cnt * 36; q += 32) { const int el = q / 36; dst[q] = src[el * BAR_TS + (q - el * 36)]; }
+        for (int q = lane; q < cnt * 6; q += 32) Re[e0 * 6 + q] = tileR[warp][q];
+    }
+    if (STEP) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tileR[warp][lane * 6 + i] = rp[i];
+        __syncwarp();
+        for (int q = lane; q < cnt * 6; q += 32) Rp[e0 * 6 + q] = tileR[warp][q];
     }
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
 struct SoilGroupDev { int64_t nele; const double* par; const int32_t* idxX; double scaleX[3]; };   // par [nele][5] z₀ Kh Kv Ch Cv
 template <int ND, bool STEP>
-__global__ void soil_kernel(SoilGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke, double* __restrict__ Re, double* __restrict__ Rp,
-                            unsigned long long* nanflag, unsigned long long nanbase) {
+__global__ void __launch_bounds__(128)
+soil_kernel(SoilGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke, double* __restrict__ Re, double* __restrict__ Rp,
+            unsigned long long* nanflag, unsigned long long nanbase) {
+    // outputs staged per warp and written as contiguous rows, as in bar_kernel
+    __shared__ double tileK[4][32 * 9];
+    __shared__ double tileR[4][32 * 3 * 2];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.nele) return;
-    const double z0 = g.par[e * 5], Kh = g.par[e * 5 + 1], Kv = g.par[e * 5 + 2], Ch = g.par[e * 5 + 3], Cv = g.par[e * 5 + 4];
-    double x[3], xp[3], xpp[3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e0 = e - lane;
+    if (e0 >= g.nele) return;
+    bool flag = false;
+    if (e < g.nele) {
+        const double z0 = g.par[e * 5], Kh = g.par[e * 5 + 1], Kv = g.par[e * 5 + 2], Ch = g.par[e * 5 + 3], Cv = g.par[e * 5 + 4];
+        double x[3], xp[3], xpp[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int32_t d = g.idxX[e * 3 + i];
-        x[i] = st.X0[d]; xp[i] = (ND >= 2) ? st.X1[d] : 0.; xpp[i] = (ND >= 3) ? st.X2[d] : 0.;
+        for (int i = 0; i < 3; ++i) {
+            const int32_t d = g.idxX[e * 3 + i];
+            x[i] = st.X0[d]; xp[i] = (ND >= 2) ? st.X1[d] : 0.; xpp[i] = (ND >= 3) ? st.X2[d] : 0.;
+        }
+        const bool contact = x[2] < z0;                                // if z < o.z₀  (SoilContact.jl:14); else R = SVector(0,0,0) and no partials
+        const double K[3] = {Kh, Kh, Kv}, Cc[3] = {Ch, Ch, Cv};
+        bool bad = (x[0] != x[0]) | (x[1] != x[1]) | (x[2] != x[2]);
+        double* tk = tileK[warp] + lane * 9; double* tr = tileR[warp] + lane * 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double s = g.scaleX[i];
+            const double r = contact ? (K[i] * (i == 2 ? x[2] - z0 : x[i]) + Cc[i] * xp[i]) : 0.;
+            tr[i] = r * s; bad |= (r != r);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) tk[i + 3 * j] = (contact && i == j) ? s * (K[i] + nm.a1 * Cc[i]) * s : 0.;
+            if (STEP) tr[32 * 3 + i] = contact ? s * Cc[i] * (nm.a2 * xp[i] + nm.a3 * xpp[i]) : 0.;
+        }
+        flag = bad && contact;
     }
-    const bool contact = x[2] < z0;                                // if z < o.z₀  (SoilContact.jl:14); else R = SVector(0,0,0) and no partials
-    const double K[3] = {Kh, Kh, Kv}, Cc[3] = {Ch, Ch, Cv};
-    bool bad = (x[0] != x[0]) | (x[1] != x[1]) | (x[2] != x[2]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double s = g.scaleX[i];
-        const double r = contact ? (K[i] * (i == 2 ? x[2] - z0 : x[i]) + Cc[i] * xp[i]) : 0.;
-        Re[e * 3 + i] = r * s; bad |= (r != r);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Ke[e * 9 + i + 3 * j] = (contact && i == j) ? s * (K[i] + nm.a1 * Cc[i]) * s : 0.;
-        if (STEP) Rp[e * 3 + i] = contact ? s * Cc[i] * (nm.a2 * xp[i] + nm.a3 * xpp[i]) : 0.;
-    }
-    if (bad && contact) atomicMin(nanflag, nanbase + (unsigned long long)e);
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, g.nele - e0);
+    for (int q = lane; q < cnt * 9; q += 32) Ke[e0 * 9 + q] = tileK[warp][q];
+    for (int q = lane; q < cnt * 3; q += 32) Re[e0 * 3 + q] = tileR[warp][q];
+    if (STEP) for (int q = lane; q < cnt * 3; q += 32) Rp[e0 * 3 + q] = tileR[warp][32 * 3 + q];
+    if (flag) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
 // ---------------------------------------------------------------------------------------------- DirectXUA first-order path (DirectXUA.jl:85-120)
