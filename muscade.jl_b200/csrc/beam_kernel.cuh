@@ -191,7 +191,9 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 // one grid wave ahead into L2 (prefetch.global.L2 of geometry / index lines at entry, of the far state entries at exit: 6.96 ms, no gain);
 // persistent CTAs again, this time with ONE __syncthreads per tile: as a plain loop +3.7 %, with a two-stage cp.async prefetch of the next tiles' dof indices,
 // geometry and gathered state (one shared-memory copy per element) +10 % — long_scoreboard 0.98 → 0.77 per issue as intended, but no_instruction 0.37 → 1.10 again:
-// the back edge over the 76 KB body, not warp drift, is what the instruction fetch does not cope with.
+// the back edge over the 76 KB body, not warp drift, is what the instruction fetch does not cope with;
+// streaming CTAs of 21 whole elements that stage Ke/Re in shared memory and write contiguous rows after ONE barrier (what pays for the one-thread-per-element
+// bar and soil kernels): 7.65 ms against 6.93 ms — the lanes' 16-byte column stores already merge in L2 and the barrier costs more than the LSU saves.
 template <int MINB>          // resident CTAs per SM the register allocation aims at (template also so that only the ND = 1 translation unit compiles it)
 __global__ void __launch_bounds__(MB_BLOCK, MINB)
 beam_static_sym_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase) {
