@@ -299,6 +299,12 @@ def run_sweepx(args, rank, world, local, dist):
             if flops.get("fp64_inst"):
                 # issue-slot view of the same pipe: DMUL/DADD occupy a DFMA slot but count one flop
                 roof["fp64_pipe_frac"] = N * flops["fp64_inst"] * 2 / (el_ms * 1e-3) / 1e12 / fp64_peak
+        # SURVEY.md §8d's provisional algorithmic count (structure-exploiting evaluation of the same mathematics, before any kernel existed): the
+        # forward-over-reverse kernels need a fifth of it, so `achieved`/`frac` above use the EXECUTED flops; this block only places the kernel against the
+        # ceiling the survey derived from its own figure (FP64 peak / F_alg elements/s; its 60 % target was 2.2e8 el/s)
+        f_alg = {0: 1.0e5, 1: 1.5e5, 2: 1.5e5}[OX]
+        roof["survey_f_alg"] = {"flop_per_element": f_alg, "ceiling_elements_per_s": fp64_peak * 1e12 / f_alg,
+                                "kernel_elements_per_s": N / (el_ms * 1e-3), "kernel_over_ceiling": N / (el_ms * 1e-3) / (fp64_peak * 1e12 / f_alg)}
         hp, hsrc = hbm_peak()
         ab = alg_bytes_per_element(OX)
         roof["hbm"] = {"alg_bytes_per_element": ab, "achieved_gbs": N * ab / (el_ms * 1e-3) / 1e9, "peak_gbs": hp, "peak_source": hsrc,
