@@ -173,4 +173,11 @@ function direct_rebase!(h::Ptr{Cvoid}, new_lo::Integer)
     return shift[]
 end
 
+# L2[X,X][1,1] entries of host-evaluated element types whose residual is not linear in X (second-order branch of DirectXUA, src/DirectXUA.jl:121-150):
+# i, j 1-based model X dofs (one triplet per entry, summed over the elements in element order by the caller), v already scaled by scale.X[i]*scale.X[j].
+function direct_set_host_xx!(h::Ptr{Cvoid}, step::Integer, i::Vector{Int64}, j::Vector{Int64}, v::Vector{Float64})
+    GC.@preserve i j v check(h, ccall((:mb_direct_set_host_xx, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                                      h, step, length(i), i, j, v))
+end
+
 end # module
