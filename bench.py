@@ -354,17 +354,13 @@ def run_directxua(args, rank, world, local, dist):
     OX, OU = 2, 0
     N = int(args.nele or 1e5)
     nstep = args.nstep
-    assert nstep % world == 0 and nstep // world >= 6
-    L, H = rank * nstep // world, (rank + 1) * nstep // world
-    Wn = max(w for w in range(1, min(args.window, H - L) + 1) if (H - L) % w == 0)
+    L, H, Wn, windows, interior = mb.sharding.directxua_windows(nstep, rank, world, args.window)
     torch.cuda.set_device(local)
     stream = torch.cuda.current_stream().cuda_stream
     model = directxua_model(mb, N)
     st0 = mb.initialize(model)
     nX, nU = model.getndof("X"), model.getndof("U")
     dtm = 0.1
-    windows = [(a, a + Wn) for a in range(L, H, Wn)]
-    interior = [w for w in windows if w[0] >= 3 and w[1] <= nstep - 3]
     engines = {}
 
     def make(lo, hi):

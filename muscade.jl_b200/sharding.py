@@ -72,6 +72,21 @@ def directxua_halo_plan(nstep, lo, hi):
                 recv_right=[s for s in (hi, hi + 1) if s < nstep])
 
 
+def directxua_windows(nstep, rank, world, window):
+    """Time-shard of rank `rank` and its sliding windows (BASELINE configs[3] streamed through mb_direct_rebase): the rank owns the steps
+    [L,H) = [rank·nstep/world,(rank+1)·nstep/world) and walks them in windows of Wn steps, Wn the largest divisor of H−L not above `window`.
+    Returns (L, H, Wn, windows, interior): `windows` = [(lo,hi)…] in order; `interior` = those with 3 ≤ lo and hi ≤ nstep−3, whose Lvv structure repeats up to a
+    row shift (central finite-difference stencils only, src/FiniteDifferences.jl:8-31) — one handle serves them all; the others contain the first or the last
+    step and need a handle of their own."""
+    if nstep % world != 0 or nstep // world < 6:
+        raise ValueError("the number of time steps must be a multiple of the number of ranks, at least 6 steps each")
+    L, H = rank * nstep // world, (rank + 1) * nstep // world
+    Wn = max(w for w in range(1, min(window, H - L) + 1) if (H - L) % w == 0)
+    windows = [(a, a + Wn) for a in range(L, H, Wn)]
+    interior = [w for w in windows if w[0] >= 3 and w[1] <= nstep - 3]
+    return L, H, Wn, windows, interior
+
+
 class CudaView:
     """expose a raw device pointer to torch through __cuda_array_interface__ (zero-copy view for NCCL send/recv)"""
 

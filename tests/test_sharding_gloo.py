@@ -84,3 +84,27 @@ def test_directxua_halo_plan(mb):
     # the block pattern of a shard only references stored steps
     bc, br = mb.directxua.block_pattern(2, 0, nstep, 4, 8)
     assert br.min() // 3 >= 2 and br.max() // 3 <= 9 and len(bc) == 3 * 4 + 1
+
+
+def test_directxua_window_plan(mb):
+    """the sliding-window plan of the configs[3] bench: the ranks' windows tile the time axis exactly once; only the windows holding the first / last step
+    fall outside the set that one moved handle can serve"""
+    for nstep, window in [(2000, 10), (2000, 25), (96, 7), (48, 16)]:
+        for world in (1, 2, 4, 8):
+            if nstep % world or nstep // world < 6:
+                with pytest.raises(ValueError):
+                    mb.sharding.directxua_windows(nstep, 0, world, window)
+                continue
+            seen = []
+            for rank in range(world):
+                L, H, Wn, windows, interior = mb.sharding.directxua_windows(nstep, rank, world, window)
+                assert (H - L) % Wn == 0 and Wn <= window and windows[0][0] == L and windows[-1][1] == H
+                assert all(hi - lo == Wn for lo, hi in windows) and all(a[1] == b[0] for a, b in zip(windows, windows[1:]))
+                for w in windows:
+                    if w in interior:
+                        assert w[0] - 2 >= 1 and w[1] + 2 <= nstep - 1        # its stored steps exclude step 0 and step nstep-1
+                    else:
+                        assert w[0] < 3 or w[1] > nstep - 3
+                assert len(windows) - len(interior) <= (rank == 0) + (rank == world - 1)
+                seen += [s for lo, hi in windows for s in range(lo, hi)]
+            assert seen == list(range(nstep))
