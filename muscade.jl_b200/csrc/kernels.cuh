@@ -17,12 +17,15 @@ namespace mb {
 // b0 = NONE marks an irregular pair, which walks cstart/src as before.  Index traffic 4 B per non-zero instead of 9.3 (cstart 4 + src 4·144/108).
 // A thread owns two pairs (four non-zeros): one 16-byte descriptor load, then up to eight independent value loads.
 constexpr uint32_t MB_NONE = 0xFFFFFFFFu;
+// Pairs that are not "entry and entry+1 of the same elements" but whose two non-zeros have at most two contributors each (three dofs per node: the pair
+// straddles two node blocks; a spring on a beam node) are SPLIT pairs: (NONE, q) points to xdesc[q] = (a0,a1,c0,c1), contributors of 2p and of 2p+1 (NONE =
+// absent) — one more dependent load, still no walk through cstart/src.  Everything else is (NONE, NONE).
 static __global__ void pair_desc_kernel(int64_t nnz, int64_t npairs_padded, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src,
-                                        uint32_t* __restrict__ pdesc) {
+                                        uint32_t* __restrict__ pdesc, uint32_t* __restrict__ split) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs_padded) return;
     const int64_t k = 2 * p;
-    uint32_t b0 = MB_NONE, b1 = MB_NONE;
+    uint32_t b0 = MB_NONE, b1 = MB_NONE, sp = 0;
     if (k + 1 < nnz) {
         const uint32_t c0 = cstart[k], c1 = cstart[k + 1], c2 = cstart[k + 2];
         const uint32_t n0 = c1 - c0, n1 = c2 - c1;
@@ -33,16 +36,40 @@ static __global__ void pair_desc_kernel(int64_t nnz, int64_t npairs_padded, cons
                 else { const uint32_t s1 = src[c0 + 1], t1 = src[c1 + 1]; if (t1 == s1 + 1) { b0 = s0; b1 = s1; } }
             }
         }
+        if (b0 == MB_NONE && n0 >= 1 && n0 <= 2 && n1 >= 1 && n1 <= 2) sp = 1;
     }
     pdesc[2 * p] = b0; pdesc[2 * p + 1] = b1;
+    split[p] = sp;
+}
+static __global__ void split_desc_kernel(int64_t npairs_padded, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, const uint32_t* __restrict__ split,
+                                         const uint32_t* __restrict__ pos, uint32_t* __restrict__ pdesc, uint4* __restrict__ xdesc) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs_padded || !split[p]) return;
+    const int64_t k = 2 * p;
+    const uint32_t c0 = cstart[k], c1 = cstart[k + 1], c2 = cstart[k + 2];
+    uint4 x;
+    x.x = src[c0]; x.y = (c1 - c0 == 2) ? src[c0 + 1] : MB_NONE;
+    x.z = src[c1]; x.w = (c2 - c1 == 2) ? src[c1 + 1] : MB_NONE;
+    xdesc[pos[p]] = x;
+    pdesc[2 * p + 1] = pos[p];
 }
 __device__ __forceinline__ double gather_one(const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, const double* __restrict__ Ke, int64_t k) {
     double acc = 0.;
     for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) acc += __ldg(Ke + src[s]);
     return acc;
 }
+__device__ __forceinline__ void gather_pair(const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, const uint4* __restrict__ xdesc, uint32_t q,
+                                            const double* __restrict__ Ke, int64_t k, double& a, double& b) {
+    if (q != MB_NONE) {
+        const uint4 x = __ldg(xdesc + q);
+        const double va = __ldg(Ke + x.x), vb = __ldg(Ke + x.z);
+        const double wa = __ldg(Ke + (x.y != MB_NONE ? x.y : 0u)), wb = __ldg(Ke + (x.w != MB_NONE ? x.w : 0u));
+        a = 0. + va; if (x.y != MB_NONE) a += wa;
+        b = 0. + vb; if (x.w != MB_NONE) b += wb;
+    } else { a = gather_one(cstart, src, Ke, k); b = gather_one(cstart, src, Ke, k + 1); }
+}
 static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, const uint32_t* __restrict__ pdesc,
-                                 const double* __restrict__ Ke, double* __restrict__ nzval) {
+                                 const uint4* __restrict__ xdesc, const double* __restrict__ Ke, double* __restrict__ nzval) {
     const int64_t k0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (k0 >= nnz) return;
     if (k0 + 4 <= nnz) {
@@ -54,9 +81,9 @@ static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict_
         const double v10 = __ldg(Ke + i1), v11 = __ldg(Ke + i1 + 1), w10 = __ldg(Ke + j1), w11 = __ldg(Ke + j1 + 1);
         double a0, a1, a2, a3;
         if (r0) { a0 = 0. + v00; a1 = 0. + v01; if (t0) { a0 += w00; a1 += w01; } }
-        else { a0 = gather_one(cstart, src, Ke, k0); a1 = gather_one(cstart, src, Ke, k0 + 1); }
+        else gather_pair(cstart, src, xdesc, d.y, Ke, k0, a0, a1);
         if (r1) { a2 = 0. + v10; a3 = 0. + v11; if (t1) { a2 += w10; a3 += w11; } }
-        else { a2 = gather_one(cstart, src, Ke, k0 + 2); a3 = gather_one(cstart, src, Ke, k0 + 3); }
+        else gather_pair(cstart, src, xdesc, d.w, Ke, k0 + 2, a2, a3);
         double2* out = reinterpret_cast<double2*>(nzval + k0);
         out[0] = make_double2(a0, a1); out[1] = make_double2(a2, a3);
     } else {

@@ -224,7 +224,25 @@ int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
     {   // pair descriptors for the reduction, padded to whole threads (4 non-zeros)
         const int64_t npp = 2 * ((nnz + 3) / 4);
         CK(dalloc(h, &h->pdesc, std::max<int64_t>(2 * npp, 4)));
-        if (npp > 0) { pair_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(nnz, npp, h->cstart, h->src, h->pdesc); h->launches++; }
+        if (npp > 0) {
+            uint32_t *split = nullptr, *pos = nullptr;
+            CK(dalloc(h, &split, npp)); CK(dalloc(h, &pos, npp));
+            pair_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(nnz, npp, h->cstart, h->src, h->pdesc, split);
+            void* tmp = nullptr; size_t tmpsz = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpsz, split, pos, npp, st));
+            CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+            CK(cub::DeviceScan::ExclusiveSum(tmp, tmpsz, split, pos, npp, st));
+            uint32_t lastpos = 0, lastflag = 0;
+            CK(cudaMemcpyAsync(&lastpos, pos + (npp - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&lastflag, split + (npp - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+            const int64_t nsplit = (int64_t)lastpos + lastflag;
+            CK(dalloc(h, &h->xdesc, std::max<int64_t>(nsplit, 1)));
+            if (nsplit > 0) split_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(npp, h->cstart, h->src, split, pos, h->pdesc, h->xdesc);
+            h->launches += 2;
+            CK(cudaStreamSynchronize(st));
+            dfree(h, split); dfree(h, pos);
+        }
     }
 
     // ---- vector map: contributors of every dof in element order (asmvec!, src/Assemble.jl:340-357)
@@ -378,7 +396,7 @@ static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkD
 // segmented reductions of non-zeros [k0,k1) (k0 a multiple of 4) and dofs [d0,d1)
 static void launch_gather_range(mb_handle* h, bool step, int64_t k0, int64_t k1, int64_t d0, int64_t d1, cudaStream_t st = nullptr) {
     if (!st) st = h->stream;
-    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->pdesc + k0, h->Ke, h->nzval + k0); h->launches++; }
+    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->pdesc + k0, h->xdesc, h->Ke, h->nzval + k0); h->launches++; }
     if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, 256), 256, 0, st>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
 }
 static void launch_gather(mb_handle* h, bool step) { launch_gather_range(h, step, 0, h->nnz, 0, h->ndofX); }

@@ -48,6 +48,7 @@ struct mb_handle {
     int32_t *asm2 = nullptr, *colptr0 = nullptr, *rowval0 = nullptr;
     uint32_t *cstart = nullptr, *src = nullptr, *vstart = nullptr, *vsrc = nullptr;
     uint32_t* pdesc = nullptr;      // pair descriptors of the non-zero reduction (kernels.cuh), 2 words per pair of non-zeros
+    uint4* xdesc = nullptr;         // split pairs: contributors of the two non-zeros of an irregular pair (≤ 2 each)
     double *dofscale = nullptr, *dxbuf = nullptr, *red = nullptr; void* redtmp = nullptr; size_t redtmp_sz = 0;   // device-resident Newton update
     unsigned long long* nanflag = nullptr;
     unsigned long long* nanflag_host = nullptr;   // pinned
