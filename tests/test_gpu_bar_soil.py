@@ -29,11 +29,12 @@ def mixed_model(mb, N=40):
 
 
 @pytest.mark.parametrize("pipe", [False, True])
-@pytest.mark.parametrize("OX,mission", [(0, "iter"), (1, "step"), (2, "iter"), (2, "step")])
-def test_mixed_beam_bar_soil(mb, OX, mission, pipe, monkeypatch):
+@pytest.mark.parametrize("OX,mission,N", [(0, "iter", 40), (1, "step", 40), (2, "iter", 40), (2, "step", 40), (0, "iter", 730), (2, "step", 730)])
+def test_mixed_beam_bar_soil(mb, OX, mission, N, pipe, monkeypatch):
+    """N = 730: 365 bars / 365 soil springs = several CTAs of full warps plus a partial one (the warp-staged stores of bar_kernel / soil_kernel)"""
     if pipe:       # force the chunked host-buffer pipeline of mb_sweepx_assemble (normally only for ≥ 4M non-zeros)
         monkeypatch.setenv("MB_E2E_MIN_NNZ", "0"); monkeypatch.setenv("MB_E2E_CHUNKS", "4")
-    model = mixed_model(mb)
+    model = mixed_model(mb, N)
     mb.setscale(model, scale=dict(X=dict(t1=3., t2=3., t3=3., r1=1., r2=1., r3=1.)))
     state = mb.initialize(model)
     dis = state.dis
