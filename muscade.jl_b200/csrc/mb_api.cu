@@ -221,29 +221,7 @@ int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
     }
     h->nnz = nnz;
     CK(dalloc(h, &h->nzval, nnz));
-    {   // pair descriptors for the reduction, padded to whole threads (4 non-zeros)
-        const int64_t npp = 2 * ((nnz + 3) / 4);
-        CK(dalloc(h, &h->pdesc, std::max<int64_t>(2 * npp, 4)));
-        if (npp > 0) {
-            uint32_t *split = nullptr, *pos = nullptr;
-            CK(dalloc(h, &split, npp)); CK(dalloc(h, &pos, npp));
-            pair_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(nnz, npp, h->cstart, h->src, h->pdesc, split);
-            void* tmp = nullptr; size_t tmpsz = 0;
-            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpsz, split, pos, npp, st));
-            CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
-            CK(cub::DeviceScan::ExclusiveSum(tmp, tmpsz, split, pos, npp, st));
-            uint32_t lastpos = 0, lastflag = 0;
-            CK(cudaMemcpyAsync(&lastpos, pos + (npp - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&lastflag, split + (npp - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st)); cudaFree(tmp);
-            const int64_t nsplit = (int64_t)lastpos + lastflag;
-            CK(dalloc(h, &h->xdesc, std::max<int64_t>(nsplit, 1)));
-            if (nsplit > 0) split_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(npp, h->cstart, h->src, split, pos, h->pdesc, h->xdesc);
-            h->launches += 2;
-            CK(cudaStreamSynchronize(st));
-            dfree(h, split); dfree(h, pos);
-        }
-    }
+    { int32_t rcpd = build_pair_descriptors(h, nnz, h->cstart, h->src, &h->pdesc, &h->xdesc); if (rcpd) return rcpd; }
 
     // ---- vector map: contributors of every dof in element order (asmvec!, src/Assemble.jl:340-357)
     if (nvec > 0) {

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "bar_kernel.cuh"
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -116,3 +117,29 @@ static inline int32_t upload_index(mb_handle* h, const int64_t* src, int64_t n, 
     return MB_OK;
 }
 
+// pair / split descriptors of a contributor-list structure (kernels.cuh), padded to whole threads of four non-zeros
+static inline int32_t build_pair_descriptors(mb_handle* h, int64_t nnz, const uint32_t* cstart, const uint32_t* src, uint32_t** pdesc, uint4** xdesc) {
+    cudaStream_t st = h->stream;
+    const int64_t npp = 2 * ((nnz + 3) / 4);
+    CK(dalloc(h, pdesc, npp > 0 ? 2 * npp : 4));
+    *xdesc = nullptr;
+    if (npp == 0) return MB_OK;
+    uint32_t *split = nullptr, *pos = nullptr;
+    CK(dalloc(h, &split, npp)); CK(dalloc(h, &pos, npp));
+    mb::pair_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(nnz, npp, cstart, src, *pdesc, split);
+    void* tmp = nullptr; size_t tmpsz = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpsz, split, pos, npp, st));
+    CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tmpsz, split, pos, npp, st));
+    uint32_t lastpos = 0, lastflag = 0;
+    CK(cudaMemcpyAsync(&lastpos, pos + (npp - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lastflag, split + (npp - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+    const int64_t nsplit = (int64_t)lastpos + lastflag;
+    CK(dalloc(h, xdesc, nsplit > 0 ? nsplit : 1));
+    if (nsplit > 0) mb::split_desc_kernel<<<nblk(npp, 256), 256, 0, st>>>(npp, cstart, src, split, pos, *pdesc, *xdesc);
+    h->launches += 2;
+    CK(cudaStreamSynchronize(st));
+    dfree(h, split); dfree(h, pos);
+    return MB_OK;
+}
