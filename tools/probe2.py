@@ -11,5 +11,6 @@ for OX in oxs:
     for mission in (["iter"] if OX == 0 else ["iter", "step"]):
         nm = mb.synthetic.newmark_coefficients(OX, 0.3)
         eng.sweepx_assemble(OX, mission, X, nm)
+        eng.time_dev(OX, mission, nm, reps=1)
         el, ga = eng.time_dev(OX, mission, nm, reps=5)
         print(f"{os.environ.get('MB_LIB','default'):40s} OX={OX} {mission}: element {el:.3f} ms gather {ga:.3f} ms -> {N/el*1e3:.3e} el/s", flush=True)

@@ -15,6 +15,7 @@ for N in (8, 1000, 100000, 1000000, 10000000):
     for OX, mission in ((0, "iter"), (2, "iter"), (2, "step")):
         nm = mb.synthetic.newmark_coefficients(OX, 0.3)
         eng.sweepx_assemble(OX, mission, X, nm)
+        eng.time_dev(OX, mission, nm, reps=1)           # warm-up: the whole-model cotangent workspace is allocated at the first device-path launch
         el, ga = eng.time_dev(OX, mission, nm, reps=5 if N >= 1000000 else 20)
         print("| %d | %d | %s | %.3f | %.3f | %.3e |" % (N, OX, mission, el, ga, N / (el + ga) * 1e3), flush=True)
     eng.close()
