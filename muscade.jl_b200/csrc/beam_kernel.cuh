@@ -323,25 +323,38 @@ beam_dr_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
 }
 
 // getresult: batched extraction of the element requestables, one thread per element (values only; HBM-bound: 616 B out per element)
+// one thread per element; the 77 results of a thread are contiguous in `out`, so each warp stages its 32 × 77 values in shared memory and writes contiguous
+// rows (as bar_kernel / soil_kernel do) — CTAs of two warps: 2 × 32 × 77 doubles = 39 KB
+constexpr int MB_RES_BLOCK = 64;
 template <int ND>
-__global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
+__global__ void __launch_bounds__(MB_RES_BLOCK)
 beam_results_kernel(BeamGroupDev g, StateDev st, double* __restrict__ out) {
+    __shared__ double tile[MB_RES_BLOCK / 32][32 * MB_NRES];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.nele) return;
-    BeamGeo geo;
-    load_geo(g.geo + e * 16, geo);
-    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
-    double Xu[3][6], Xv[3][6], r[MB_NRES];
-    const int32_t* ix = g.idxX + e * 12;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e0 = e - lane;
+    if (e0 >= g.nele) return;
+    if (e < g.nele) {
+        BeamGeo geo;
+        load_geo(g.geo + e * 16, geo);
+        const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+        double Xu[3][6], Xv[3][6], r[MB_NRES];
+        const int32_t* ix = g.idxX + e * 12;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int iu = (i < 3) ? i : i + 3;
-        const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iu + 3);
-        Xu[0][i] = st.X0[du]; Xu[1][i] = (ND >= 2) ? st.X1[du] : 0.; Xu[2][i] = (ND >= 3) ? st.X2[du] : 0.;
-        Xv[0][i] = st.X0[dv]; Xv[1][i] = (ND >= 2) ? st.X1[dv] : 0.; Xv[2][i] = (ND >= 3) ? st.X2[dv] : 0.;
+        for (int i = 0; i < 6; ++i) {
+            const int iu = (i < 3) ? i : i + 3;
+            const int32_t du = __ldg(ix + iu), dv = __ldg(ix + iu + 3);
+            Xu[0][i] = st.X0[du]; Xu[1][i] = (ND >= 2) ? st.X1[du] : 0.; Xu[2][i] = (ND >= 3) ? st.X2[du] : 0.;
+            Xv[0][i] = st.X0[dv]; Xv[1][i] = (ND >= 2) ? st.X1[dv] : 0.; Xv[2][i] = (ND >= 3) ? st.X2[dv] : 0.;
+        }
+        beam_results<ND>(geo, m, Xu, Xv, r);
+        double* tw = tile[warp] + lane * MB_NRES;
+#pragma unroll
+        for (int k = 0; k < MB_NRES; ++k) tw[k] = r[k];
     }
-    beam_results<ND>(geo, m, Xu, Xv, r);
-    for (int k = 0; k < MB_NRES; ++k) out[e * MB_NRES + k] = r[k];
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, g.nele - e0);
+    for (int q = lane; q < cnt * MB_NRES; q += 32) out[e0 * MB_NRES + q] = tile[warp][q];
 }
 void launch_beam_results(int ND, const BeamGroupDev& g, const StateDev& st, double* out, cudaStream_t s);
 
