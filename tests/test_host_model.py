@@ -100,3 +100,30 @@ def test_shared_dofs_and_multiple_types(mb):
     dis = mb.Disassembler(model)
     assert dis.dis[1].X.tolist() == [[1, 55]] and dis.dis[6].X.tolist() == [[6, 60]] and dis.dis[7].X.tolist() == [[50]]
     assert dis.fieldX[54:] == ["λt1", "λt2", "λt3", "λr1", "λr2", "λr3"]
+
+
+def test_dofconstraint_hessian_matches_finite_differences():
+    """host-evaluated DofConstraint{:X} on DirectXUA's second-order branch (L = Λ∘R, src/DirectXUA.jl:152-171): the Λ-contracted second derivative handed to
+    mb_direct_set_host_xx equals the derivative of (∂R/∂X)ᵀΛ, for every mode and a quadratic two-dof gap"""
+    import muscade_b200 as mb
+    A = np.array([[0.4, 0.1], [0.1, -0.3]]); bvec = np.array([0.3, -0.2])
+
+    def gap(x, t):
+        g = 0.5 * np.einsum("ei,ij,ej->e", x, A, x) + x @ bvec + 0.1 - 0.05 * t
+        return g, x @ A + bvec, np.broadcast_to(A, (x.shape[0], 2, 2))
+    X = [np.array([[0.3, -0.4, 0.7], [0.1, 0.2, -0.6]])]; Lam = np.array([[0.2, -0.5, 0.9], [-0.3, 0.4, 0.1]])
+    for mode in ("equal", "positive", "off"):
+        ex = dict(gap=gap, gargs=(), mode=mode, Nx=2)
+        H = mb.DofConstraint.hessian(ex, X, Lam, 0.2)
+        h = 1e-6
+        Hfd = np.zeros((2, 3, 3))
+        for j in range(3):
+            Xp = [X[0].copy()]; Xp[0][:, j] += h; Xm = [X[0].copy()]; Xm[0][:, j] -= h
+            Kp = mb.DofConstraint.residual(ex, Xp, 0.2)[1]; Km = mb.DofConstraint.residual(ex, Xm, 0.2)[1]
+            Hfd[:, :, j] = (np.einsum("eki,ek->ei", Kp, Lam) - np.einsum("eki,ek->ei", Km, Lam)) / (2 * h)
+        if H is None:
+            assert np.abs(Hfd).max() < 1e-9 and mode == "off"
+        else:
+            assert np.abs(H - Hfd).max() < 1e-8 and np.abs(H - H.transpose(0, 2, 1)).max() == 0.
+    lin = dict(gap=lambda x, t: (x[:, 0] - t, np.ones_like(x)), gargs=(), mode="equal", Nx=1)
+    assert mb.DofConstraint.hessian(lin, [np.array([[0.3, 0.7]])], np.array([[0.2, -0.5]]), 0.) is None      # affine gap, equal mode: R linear in (x,λ)
