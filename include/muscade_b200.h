@@ -148,7 +148,7 @@ int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nL
 /* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build, ms[2] the element kernels alone (float ms[3]) */
 int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
 
-/* ---- sharding over the GPUs of one box (one handle per GPU / process; NCCL itself is driven by the host, torch.distributed or ncclComm) -- */
+/* ---- sharding over the GPUs of one box (one handle per GPU / process) ------------------------------------------------------------------------- */
 /* Device-resident state: the Newton update runs where the state lives, so X only crosses PCIe when the caller asks.
  *   mb_sweepx_set_state / get_state : state.X[1..OX+1] (and state.U[1]) host↔device; pointers may be host or device memory.
  *   mb_sweepx_set_dof_scale         : dis.scaleX per model dof (Xdofgr = allXdofs, src/SweepX.jl:196); default all ones.
@@ -178,6 +178,33 @@ int32_t mb_iface_setup(mb_handle* h, int64_t n_send_nz, const int64_t* send_nz, 
                        int64_t n_recv_nz, const int64_t* recv_nz, int64_t n_recv_v, const int64_t* recv_v);
 int32_t mb_iface_pack_dev(mb_handle* h, double* sendbuf_dev);
 int32_t mb_iface_unpack_add_dev(mb_handle* h, const double* recvbuf_dev);
+
+/* The interface exchange itself, inside the shim (NCCL on the handle's stream; see "multi-GPU" below): pack → send to rank+1 / receive from rank−1 →
+ * unpack-add.  Replaces nothing in the reference (its assemble! is single-process, src/Assemble.jl:470-487); it is what makes the sharded nzval / Lλ
+ * equal the unsharded ones on the owned rows.  mb_iface_buffers: the device buffers it uses (the first n_recv_nz received values whose position is 0
+ * are the ghost couplings); mb_iface_get_recvbuf copies the receive buffer to the host. */
+int32_t mb_iface_exchange(mb_handle* h);
+int32_t mb_iface_buffers(mb_handle* h, double** sendbuf_dev, int64_t* nsend, double** recvbuf_dev, int64_t* nrecv);
+int32_t mb_iface_get_recvbuf(mb_handle* h, double* out);
+
+/* ---- multi-GPU: one handle per GPU / process, NCCL inside the shim (north_star: Julia → thin shim, no PyTorch) -------------------------------------
+ * mb_comm_unique_id  : ncclGetUniqueId — one process creates the 128-byte id and hands it to the others by its own means (file, socket, MPI).
+ * mb_comm_init       : ncclCommInitRank on the handle's device; rank r of `world` consecutive shards (element ranges or time-step ranges).
+ * mb_comm_allreduce  : small HOST vectors in place (op 0 sum, 1 max, 2 min), blocking — timings, norms of the convergence test (src/SweepX.jl:209,
+ *                      src/DirectXUA.jl:493-500), and the A-class sums Σ_step L1[A], L2[A,A] of time shards (src/DirectXUA.jl:321-326).
+ * mb_comm_allreduce_dev : the same on device memory, asynchronous on the handle's stream.
+ * mb_direct_halo_exchange : time shards (mb_direct_prepare with step_lo/step_hi): the per-step blocks L2[Λ,X] (and L1[X] of second-order element types) of the
+ *                      two steps at each end of the owned range go to the neighbours, the halo steps' blocks come in (src/FiniteDifferences.jl:2-4 reach ±2).
+ * libnccl.so.2 is opened with dlopen at the first call: MB_ERR_NCCL if it is absent or an NCCL call fails (mb_last_error has the text). */
+int32_t mb_comm_unique_id(uint8_t* id128);
+int32_t mb_comm_init(mb_handle* h, const uint8_t* id128, int32_t rank, int32_t world);
+int32_t mb_comm_share(mb_handle* h, mb_handle* owner);     /* a second handle on the same GPU borrows the owner's communicator (owner must outlive it) */
+int32_t mb_comm_destroy(mb_handle* h);
+int32_t mb_comm_info(const mb_handle* h, int32_t* rank, int32_t* world, int32_t* nccl_version);
+int32_t mb_comm_allreduce(mb_handle* h, double* buf, int64_t n, int32_t op);
+int32_t mb_comm_allreduce_dev(mb_handle* h, double* dev, int64_t n, int32_t op);
+int32_t mb_comm_barrier(mb_handle* h);
+int32_t mb_direct_halo_exchange(mb_handle* h);
 
 /* Page-lock / unlock a host array the caller owns (Julia: the Vector behind out.Lλx.nzval), so that the copies inside
  * mb_sweepx_assemble run at PCIe speed. */

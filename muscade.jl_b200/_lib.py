@@ -86,6 +86,18 @@ SYMBOLS = {
     "mb_iface_setup": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "mb_iface_pack_dev": (C.c_int32, [H, C.c_void_p]),
     "mb_iface_unpack_add_dev": (C.c_int32, [H, C.c_void_p]),
+    "mb_iface_exchange": (C.c_int32, [H]),
+    "mb_iface_buffers": (C.c_int32, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "mb_iface_get_recvbuf": (C.c_int32, [H, C.c_void_p]),
+    "mb_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "mb_comm_init": (C.c_int32, [H, C.c_void_p, C.c_int32, C.c_int32]),
+    "mb_comm_share": (C.c_int32, [H, H]),
+    "mb_comm_destroy": (C.c_int32, [H]),
+    "mb_comm_info": (C.c_int32, [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mb_comm_allreduce": (C.c_int32, [H, C.c_void_p, C.c_int64, C.c_int32]),
+    "mb_comm_allreduce_dev": (C.c_int32, [H, C.c_void_p, C.c_int64, C.c_int32]),
+    "mb_comm_barrier": (C.c_int32, [H]),
+    "mb_direct_halo_exchange": (C.c_int32, [H]),
     "mb_host_register": (C.c_int32, [H, C.c_void_p, C.c_int64]),
     "mb_host_unregister": (C.c_int32, [H, C.c_void_p]),
 }

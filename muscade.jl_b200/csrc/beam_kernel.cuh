@@ -228,6 +228,115 @@ beam_static_sym_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, dou
     if (bad) atomicMin(nanflag, nanbase + (unsigned long long)e);
 }
 
+// K1, statics, active/passive formulation (beam_static_ap, beam_math.cuh).  Same lane ↔ rotation-dof mapping and same stores as beam_static_sym_kernel.
+// SHARE: warps are cut into groups of 6 lanes = whole elements (30 working lanes, lanes 30/31 idle), and the sinc1 packs of the three Rodrigues maps —
+// pure value computations that every lane of the element would otherwise repeat (sincos, reciprocals: a third of the primal FP64 work and most of its
+// integer/branch instructions) — are evaluated once per element: lane l%6 == 0 takes (θ), lane 1 takes (θ/2) of whatever Rodrigues map the element is at,
+// and the 4+4 doubles go round by warp shuffles.
+#ifndef MB_AP_MINB
+#define MB_AP_MINB 2
+#endif
+struct PacksShuffle {
+    int sub;                 // lane within the element group (0..5); lanes 0-2: active node 1, lanes 3-5: active node 2
+    int base;                // first warp lane of the group
+    mutable RodPacks other;  // packs of the passive node, fetched together with the active ones
+    __device__ __forceinline__ void operator()(int which, double th, RodPacks& pk) const {
+        if (which == 1) { pk = other; return; }
+        // which == 0: lanes 0,1 hold θ = |v₁| and take its packs at θ, θ/2; lanes 3,4 the same for |v₂|.  which == 2: |Δv′| is the same in all six lanes.
+        const bool work = (which == 0) ? (sub != 2 && sub != 5) : (sub < 2);
+        const bool half = (sub == 1) || (sub == 4);
+        double S[4];
+        if (work) sinc_pack(half ? 0.5 * th : th, S); else { S[0] = S[1] = S[2] = S[3] = 0.; }
+        const int own = (which == 0 && sub >= 3) ? base + 3 : base, oth = (sub >= 3) ? base : base + 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            pk.Sth[k] = __shfl_sync(0xffffffffu, S[k], own);
+            pk.Sh[k] = __shfl_sync(0xffffffffu, S[k], own + 1);
+            if (which == 0) { other.Sth[k] = __shfl_sync(0xffffffffu, S[k], oth); other.Sh[k] = __shfl_sync(0xffffffffu, S[k], oth + 1); }
+        }
+    }
+};
+// Stores of one lane (rotation dof l of the element, tangent column cv) as the sweep produces them: column cv of the scaled element tangent
+// Ke[i + 12j] = scale_i·∂R_i/∂X_j·scale_j (the seed carries scale_cv), the six translation rows of that column transposed into row cv of the translation
+// columns (symmetric tangent), the translation rows of translation column cu = cv − 3 (±G/4), and, from lane 0, the residual.  Same values and
+// positions as beam_static_sym_store; rows of the active / passive node are addressed, not selected.
+struct ApStore {
+    double* ke; double* re; const double* sc; int lane; bool live, al, bad;
+    __device__ __forceinline__ void put(int k, double v) { bad |= (v != v); if (live) __stcs(ke + k, v); }
+    __device__ __forceinline__ void put2(int k, double v0, double v1) { bad |= (v0 != v0) | (v1 != v1); if (live) store_pair_cs(ke + k, v0, v1, al); }
+    __device__ __forceinline__ void tt(const double* Gc) {
+        const bool n1 = lane < 3;
+        const int cu = n1 ? lane : lane + 3;
+        const double s4 = (n1 ? 0.25 : -0.25) * sc[cu];
+        const double v0 = Gc[0] * s4, v1 = Gc[1] * s4, v2 = Gc[2] * s4;
+        put2(12 * cu, v0 * sc[0], v1 * sc[1]); put(12 * cu + 2, v2 * sc[2]);
+        put2(12 * cu + 6, -v0 * sc[6], -v1 * sc[7]); put(12 * cu + 8, -v2 * sc[8]);
+    }
+    __device__ __forceinline__ void trans(const SD<true, false>* Ru1, const SD<true, false>* Ru2) {
+        const int cv = ((lane < 3) ? lane : lane + 3) + 3;
+        double a[3], b[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { a[i] = Ru1[i].d0 * sc[i]; b[i] = Ru2[i].d0 * sc[6 + i]; }
+        put2(12 * cv, a[0], a[1]); put(12 * cv + 2, a[2]);
+        put2(12 * cv + 6, b[0], b[1]); put(12 * cv + 8, b[2]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { put(12 * i + cv, a[i]); put(12 * (6 + i) + cv, b[i]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { const double x = Ru1[i].v * sc[i], y = Ru2[i].v * sc[6 + i]; bad |= (x != x) | (y != y); if (live) { re[i] = x; re[6 + i] = y; } }
+        }
+    }
+    __device__ __forceinline__ void rot(const SD<true, false>* Rva, const SD<true, false>* Rvp) {
+        const bool n1 = lane < 3;
+        const int cv = (n1 ? lane : lane + 3) + 3, ra0 = n1 ? 3 : 9, rp0 = 12 - ra0;
+        put(12 * cv + ra0, Rva[0].d0 * sc[ra0]); put2(12 * cv + ra0 + 1, Rva[1].d0 * sc[ra0 + 1], Rva[2].d0 * sc[ra0 + 2]);
+        put(12 * cv + rp0, Rvp[0].d0 * sc[rp0]); put2(12 * cv + rp0 + 1, Rvp[1].d0 * sc[rp0 + 1], Rvp[2].d0 * sc[rp0 + 2]);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { const double x = Rva[i].v * sc[3 + i], y = Rvp[i].v * sc[9 + i]; bad |= (x != x) | (y != y); if (live) { re[3 + i] = x; re[9 + i] = y; } }
+        }
+    }
+};
+template <int MINB, bool SHARE>
+__global__ void __launch_bounds__(MB_BLOCK, MINB)
+beam_static_ap_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase) {
+    using V = SD<false, false>; using S = SD<true, false>;
+    int64_t e; int lane; bool live = true;
+    int sub = 0, base = 0;
+    if (SHARE) {
+        const int wl = threadIdx.x & 31;
+        const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        sub = wl % 6; base = wl - sub;
+        e = warp * 5 + wl / 6; lane = sub;
+        if (wl >= 30) { e = warp * 5 + 4; live = false; base = 24; }          // idle lanes shadow the last element of the warp (no stores)
+        if (e >= g.nele) { e = g.nele - 1; live = false; }
+    } else {
+        const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        e = t / 6; lane = (int)(t - e * 6);
+        if (e >= g.nele) return;
+    }
+    BeamGeo geo;
+    load_geo(g.geo + e * 16, geo);
+    const BeamMat m = g.mats[g.mat_id ? g.mat_id[e] : 0];
+    double xu[6], xv[6]; V U[3];
+    const int32_t* ix = g.idxX + e * 12;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3;
+        xu[i] = st.X0[__ldg(ix + iu)];
+        xv[i] = st.X0[__ldg(ix + iu + 3)];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.;
+    const int cv = ((lane < 3) ? lane : lane + 3) + 3;
+    double* ke = Ke + e * 144;
+    ApStore out;
+    out.ke = ke; out.re = Re + e * 12; out.sc = g.scaleX; out.lane = lane; out.live = live; out.al = (reinterpret_cast<uintptr_t>(ke) & 15) == 0; out.bad = false;
+    if (SHARE) { PacksShuffle ps; ps.sub = sub; ps.base = base; beam_static_ap_lane(geo, m, xu, xv, g.scaleX[cv], lane, g.udof != 0, U, ps, out); }
+    else beam_static_ap_lane(geo, m, xu, xv, g.scaleX[cv], lane, g.udof != 0, U, PacksLocal(), out);
+    if (out.bad && live) atomicMin(nanflag, nanbase + (unsigned long long)e);
+}
+
 // :step mission only (src/SweepX.jl:46-57,69-78): the extra seed direction δr carries the Newmark predictor
 //   vx′ = x′ + a₁δX + a·δr,  vx″ = x″ + b₁δX + b·δr,  a = a₂x′+a₃x″,  b = b₂x′+b₃x″ ;   Rp = ∂(Lλ)/∂r is subtracted from the rhs.
 // One thread per element, dense one-direction dual.
@@ -524,14 +633,23 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
 struct BeamLaunch {
     BeamGroupDev g; StateDev st; NewmarkDev nm;
     double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream; double* Wc;
-    int static_sym = 1;     // statics: 1 = symmetric-tangent kernel, 0 = two-direction SD kernel (kept for A/B measurements)
+    int static_sym = 3;     // statics: 3 = active/passive sweep with shuffle-shared packs (default), 2 = the same with local packs, 1 = symmetric-tangent kernel, 0 = two-direction SD kernel (A/B measurements)
     int nsm = 148;
 };
 template <int ND, bool STEP> void launch_beam(const BeamLaunch& a);
 template <int ND> struct StaticSymLaunch { static void go(const BeamLaunch&, unsigned) {} };
 template <> struct StaticSymLaunch<1> {
     static void go(const BeamLaunch& a, unsigned nb) {
-        beam_static_sym_kernel<MB_SYM_MINB><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        if (a.static_sym == 3 || a.static_sym == 13 || a.static_sym == 14) {             // active/passive sweep, packs shared by shuffles: 5 whole elements per warp
+            const int64_t nw = (a.g.nele + 4) / 5;
+            const unsigned nbw = (unsigned)((nw * 32 + MB_BLOCK - 1) / MB_BLOCK);
+            if (a.static_sym == 13) beam_static_ap_kernel<3, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+            else if (a.static_sym == 14) beam_static_ap_kernel<4, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+            else beam_static_ap_kernel<MB_AP_MINB, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        } else if (a.static_sym == 2)
+            beam_static_ap_kernel<MB_AP_MINB, false><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+        else
+            beam_static_sym_kernel<MB_SYM_MINB><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
     }
 };
 #define MB_INSTANTIATE_BEAM(ND_, STEP_)                                                                                               \

@@ -684,6 +684,202 @@ template <class Put, class Put2> MB_HD bool beam_static_sym_store(int l, const S
     return bad;
 }
 
+// ------------------------------------------------------------------------------------------------ statics: active / passive node
+// Lane l of beam_static_sym seeds ONE rotation dof, which belongs to one of the two nodes — the lane's ACTIVE node a; the rotation vector of the
+// other, PASSIVE node p carries no partial, yet the SD<1,0> sweep above drags a (zero) partial through everything that depends on it.  The corotated
+// frame is symmetric in the two nodes: with N = rₐ·rₚᵀ, Δv′ = ½Rodrigues⁻¹(N),
+//     rₛₘ = Rodrigues(Δvᵧ)·rₛ₁·rₘ = Rodrigues(Δv′)·rₚ·rₘ                     (BeamElement.jl:195-199; rₛ₂ = Rodrigues(Δvᵧ)²·rₛ₁, Rodrigues(−v) = Rodrigues(v)ᵀ)
+//     Δvᵧ = σ·Δv′, σ = +1 if a is node 2, −1 if a is node 1               (Rodrigues⁻¹(Mᵀ) = −Rodrigues⁻¹(M))
+//     vₗ  = rₛₘᵀ·Δvᵧ = σ·(rₚ·rₘ)ᵀ·Δv′                                     (a rotation leaves its own axis alone)
+// so all six lanes run the same code with their own (a,p) and everything that depends on the passive node only — Rodrigues(vₚ), B = rₚ·rₘ — is plain
+// values (SD<0,0>): products with them cost one direction less, and the passive adjoints need the tangent of the cotangent only.
+// Xv_a: rotation vector of the active node with the lane's seed, Xv_p: of the passive node, sigma as above.  Returns the residual rows of
+// u₁, u₂ (Ru1, Ru2), of the active node's rotation (Rva) and of the passive node's (Rvp): value = R, d0 = the lane's tangent column.
+// Special-function packs: PK = nullptr evaluates them here; otherwise PK[0..7] = sinc packs at θₐ, θₐ/2 and PK[8..15] at θₚ, θₚ/2 come from the caller
+// (one lane of the element evaluates each of them and they are exchanged by warp shuffles, see beam_static_ap_kernel).
+struct RodPacks { double Sth[4], Sh[4]; };
+// I + a·S + b·S² from the rotation vector and the two coefficients (the tail of rodrigues)
+template <class T> MB_HD Mat3<T> rod_matrix(const Vec3<T>& v, const T& a, const T& b) {
+    T v00 = v[0] * v[0], v11 = v[1] * v[1], v22 = v[2] * v[2];
+    T b01 = b * (v[0] * v[1]), b02 = b * (v[0] * v[2]), b12 = b * (v[1] * v[2]);
+    T a0 = a * v[0], a1 = a * v[1], a2 = a * v[2];
+    Mat3<T> r;
+    r(0, 0) = 1.0 - b * (v11 + v22); r(1, 1) = 1.0 - b * (v00 + v22); r(2, 2) = 1.0 - b * (v00 + v11);
+    r(1, 0) = b01 + a2; r(0, 1) = b01 - a2;
+    r(2, 0) = b02 - a1; r(0, 2) = b02 + a1;
+    r(2, 1) = b12 + a0; r(1, 2) = b12 - a0;
+    return r;
+}
+// Rematerialisation fence: the value is unchanged, but the compiler may no longer assume so — what is recomputed from it is not merged with the first
+// evaluation and kept in registers from the forward sweep to the end of the reverse sweep (the kernel is bound by its register live set, not by flops).
+MB_HD void opaque(double& x) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(x));
+#else
+    (void)x;
+#endif
+}
+template <bool A, bool B> MB_HD void opaque(SD<A, B>& x) { opaque(x.v); if constexpr (A) opaque(x.d0); if constexpr (B) opaque(x.d1); }
+#ifndef MB_AP_REMAT
+#define MB_AP_REMAT 1
+#endif
+template <class T> MB_FN Mat3<T> rodrigues_pk(const Vec3<T>& v, RodAux<T>& aux, const T& th, bool small, const RodPacks& pk) {
+    T a, b;
+    aux.small = small;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { aux.Sth[k] = pk.Sth[k]; aux.Sh[k] = pk.Sh[k]; }
+    if (small) { a = Make<T>::c(1.0); b = Make<T>::c(0.5); }
+    else { a = apply_fn(th, aux.Sth); T c = apply_fn(th * 0.5, aux.Sh); b = sqr_ref(c) * 0.5; }
+    aux.a = a; aux.b = b; aux.th = th;
+    return rod_matrix(v, a, b);
+}
+template <class T> MB_HD T norm_of(const Vec3<T>& v) { return mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); }
+MB_HD void rod_packs(double th, RodPacks& pk) { sinc_pack(th, pk.Sth); sinc_pack(0.5 * th, pk.Sh); }
+
+// EX: how the packs of the three Rodrigues maps are obtained — a functor  ex(which, θ, pk)  with which = 0 (active), 1 (passive), 2 (Δv′)
+struct PacksLocal { MB_HD void operator()(int, double th, RodPacks& pk) const { rod_packs(th, pk); } };
+// OUT: where results go as soon as they exist (holding them to the end of the sweep costs registers the kernel does not have):
+//   out.tt(Gc)          column c of G (closed-form translation × translation block), after the forward sweep
+//   out.trans(Ru1,Ru2)  residual rows of u₁, u₂ (value = R, d0 = the lane's tangent column), early in the reverse sweep
+//   out.rot(Rva,Rvp)    rows of the active / passive node's rotation, at the end
+template <class EX, class OUT>
+MB_HD void beam_static_ap(const BeamGeo& g, const BeamMat& m, const SD<false, false>* Xu0, const SD<true, false>* Xv_a, const SD<false, false>* Xv_p,
+                          double sigma, bool udof, const SD<false, false>* U0, int c, const EX& ex, OUT& out) {
+    using S = SD<true, false>; using V = SD<false, false>;
+    const double L = g.L;
+    // ---- forward
+    Vec3<S> va{Xv_a[0], Xv_a[1], Xv_a[2]}; Vec3<V> vp{Xv_p[0], Xv_p[1], Xv_p[2]};
+    RodAux<S> aa; RodAux<V> ap; RodAux<S> ad; RinvAux<S> ai;
+    RodPacks pk;
+    S tha = norm_of(va); V thp = norm_of(vp);
+    ex(0, tha.v, pk);
+    Mat3<S> ra = rodrigues_pk(va, aa, tha, tha.v < 1e-14, pk);
+    ex(1, thp.v, pk);
+    Mat3<V> rp = rodrigues_pk(vp, ap, thp, thp.v < 1e-14, pk);
+    Mat3<S> Nm = mul_nt(ra, rp);
+    Vec3<S> h = rodrigues_inv(Nm, ai);
+    Vec3<S> dvp{0.5 * h[0], 0.5 * h[1], 0.5 * h[2]};
+    S thd = norm_of(dvp);
+    ex(2, thd.v, pk);
+    Mat3<S> rd = rodrigues_pk(dvp, ad, thd, thd.v < 1e-14, pk);
+    Mat3<V> gm; for (int i = 0; i < 9; ++i) gm.a[i].v = g.rm.a[i];
+    Mat3<V> B = mul(rp, gm);
+    Mat3<S> r = mul(rd, B);
+    Vec3<S> dv{sigma * dvp[0], sigma * dvp[1], sigma * dvp[2]};
+    Vec3<V> dp, cs;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        V c2 = 0.5 * (Xu0[i] + Xu0[3 + i]);
+        dp[i] = (Xu0[3 + i] + g.tgm[i] * 0.5) - c2;
+        cs[i] = c2 + g.cm[i];
+    }
+    Vec3<S> q = mulv_t(r, dp);
+    Vec3<S> ul = q; ul[0] = ul[0] - L * 0.5;
+    Vec3<S> vl = mulv_t(r, dv);
+    S qn = mb_sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
+    S eps = qn * (2.0 / L) - 1.0;
+    // ---- translation × translation block, closed form (see beam_static_sym)
+    {
+        const double iq = 1.0 / qn.v, k = (2.0 * m.EA) * (2.0 / L - iq), hh = (2.0 * m.EA) * (iq * iq * iq);
+        const double c48 = 48.0 / (L * L * L);
+        const double D[3] = {0., m.EI3 * c48, m.EI2 * c48};
+        double w[3], Aw[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) w[j] = (c == 0) ? r(0, j).v : ((c == 1) ? r(1, j).v : r(2, j).v);
+        const double qw = (q[0].v * w[0] + q[1].v * w[1]) + q[2].v * w[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Aw[j] = (k + D[j]) * w[j] + (hh * qw) * q[j].v;
+#pragma unroll
+        double Gc[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Gc[i] = (r(i, 0).v * Aw[0] + r(i, 1).v * Aw[1]) + r(i, 2).v * Aw[2];
+        out.tt(Gc);
+    }
+    // ---- reverse: Gauss sums in closed form (beam_uniform_reverse, beam_internal_reverse), then the frame
+    Mat3<S> rb; Vec3<S> ulb, vlb, cb;
+    {
+        V fe[3]; fe[0].v = 0.; fe[1].v = 0.; fe[2].v = m.w;
+        if (udof) for (int i = 0; i < 3; ++i) fe[i] = fe[i] - U0[i];
+        const double k6 = L * L / 6.0;
+        S P1 = -k6 * vl[2], P2 = k6 * vl[1];
+        S zero = Make<S>::c(0.);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { rb(i, 0) = zero; rb(i, 1) = fe[i] * P1; rb(i, 2) = fe[i] * P2; cb[i] = widen<S>(L * fe[i]); }
+        Vec3<V> fev{fe[0], fe[1], fe[2]};
+        Vec3<S> gl = mulv_t(r, fev);
+        const double c48 = 48.0 / (L * L * L), c4 = 4.0 / L;
+        S k = (((m.EA * L) * eps) * (2.0 / L)) / qn;
+        ulb[0] = k * q[0];
+        ulb[1] = (m.EI3 * c48) * ul[1] + k * q[1];
+        ulb[2] = (m.EI2 * c48) * ul[2] + k * q[2];
+        vlb[0] = (m.GJ * c4) * vl[0];
+        vlb[1] = (m.EI2 * c4) * vl[1] + k6 * gl[2];
+        vlb[2] = (m.EI3 * c4) * vl[2] - k6 * gl[1];
+    }
+    Vec3<S> dvb = mulv(r, vlb);
+    {
+        Vec3<S> dpb = mulv(r, ulb);
+        S Ru1[3], Ru2[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { S hcs = 0.5 * (cb[i] - dpb[i]); Ru1[i] = hcs; Ru2[i] = hcs + dpb[i]; }      // d′ = (u₂ + tgₘ/2) − ½(u₁+u₂) ; cₛₘ = ½(u₁+u₂) + cₘ
+        out.trans(Ru1, Ru2);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rb(i, j) = rb(i, j) + (dp[i] * ulb[j] + dv[i] * vlb[j]);
+    // r = rd·B, B = rₚ·rₘ
+    Mat3<S> rdb = mul_nt(rb, B);
+    Mat3<S> Bb = mul_tn(rd, rb);
+    Mat3<S> rpb = mul_nt(Bb, gm);
+    // rd = Rodrigues(Δv′), Δvᵧ = σΔv′
+    Vec3<S> dvpb{sigma * dvb[0], sigma * dvb[1], sigma * dvb[2]};
+    rodrigues_adj(dvp, ad, rdb, dvpb);
+    // Δv′ = ½Rodrigues⁻¹(N), N = rₐ·rₚᵀ
+    Mat3<S> Nb; { S z = Make<S>::c(0.); for (int i = 0; i < 9; ++i) Nb.a[i] = z; }
+    Vec3<S> hb{0.5 * dvpb[0], 0.5 * dvpb[1], 0.5 * dvpb[2]};
+    rodrigues_inv_adj(h, ai, hb, Nb);
+#if MB_AP_REMAT
+    {   // rₐ, rₚ again from (v, a, b) rather than held in registers since the forward sweep
+        S a2 = aa.a, b2 = aa.b; opaque(a2); opaque(b2);
+        ra = rod_matrix(va, a2, b2);
+        V a3 = ap.a, b3 = ap.b; opaque(a3); opaque(b3);
+        rp = rod_matrix(vp, a3, b3);
+    }
+#endif
+    Mat3<S> rab = mul(Nb, rp);
+    Mat3<S> rpb2 = mul_tn(Nb, ra);
+    for (int i = 0; i < 9; ++i) rpb.a[i] = rpb.a[i] + rpb2.a[i];
+    S z = Make<S>::c(0.);
+    Vec3<S> vab{z, z, z}, vpb{z, z, z};
+    rodrigues_adj(va, aa, rab, vab);
+    rodrigues_adj(vp, ap, rpb, vpb);
+    out.rot(vab.a, vpb.a);
+}
+// collects the outputs in element dof order, as beam_static_sym returns them (host tests; feeds beam_static_sym_store)
+struct ApCollect {
+    bool n1; SD<true, false>* R; double* G;
+    MB_HD void tt(const double* Gc) { for (int i = 0; i < 3; ++i) G[i] = Gc[i]; }
+    MB_HD void trans(const SD<true, false>* Ru1, const SD<true, false>* Ru2) { for (int i = 0; i < 3; ++i) { R[i] = Ru1[i]; R[6 + i] = Ru2[i]; } }
+    MB_HD void rot(const SD<true, false>* Rva, const SD<true, false>* Rvp) { for (int i = 0; i < 3; ++i) { R[(n1 ? 3 : 9) + i] = Rva[i]; R[(n1 ? 9 : 3) + i] = Rvp[i]; } }
+};
+
+// Lane l (rotation dof l of the element: node 1 for l < 3, node 2 otherwise) of the active/passive sweep: xu = (u₁,u₂), xv = (v₁,v₂) plain values,
+// seed = scale.X of the lane's dof.  Results go to `out` (see beam_static_ap).
+template <class EX, class OUT>
+MB_HD void beam_static_ap_lane(const BeamGeo& g, const BeamMat& m, const double* xu, const double* xv, double seed, int l, bool udof,
+                               const SD<false, false>* U0, const EX& ex, OUT& out) {
+    using S = SD<true, false>; using V = SD<false, false>;
+    const bool n1 = l < 3;
+    const int c = n1 ? l : l - 3;
+    V Xu0[6]; S va[3]; V vp[3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Xu0[i].v = xu[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { va[i].v = n1 ? xv[i] : xv[3 + i]; va[i].d0 = (i == c) ? seed : 0.; vp[i].v = n1 ? xv[3 + i] : xv[i]; }
+    beam_static_ap(g, m, Xu0, va, vp, n1 ? -1.0 : 1.0, udof, U0, c, ex, out);
+}
+
 // dense Dual<W> front-end (element dof order X[ider][12]); used by the δr lane of the :step mission and by the host tests
 template <int ND, int W> MB_HD void beam_residual(const BeamGeo& g, const BeamMat& m, const Dual<W> (*X)[12], bool udof, const Dual<W>* U0, Dual<W>* R) {
     Dual<W> Xu[3][6], Xv[3][6];

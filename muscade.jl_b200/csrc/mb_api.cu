@@ -52,6 +52,7 @@ int32_t mb_destroy(mb_handle* h) {
     if (!h) return MB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    mb_comm_destroy(h);
     mb_direct_release(h);
     for (void* p : h->owned) cudaFree(p);
     cudaFree(h->nanflag);
@@ -106,9 +107,9 @@ int32_t mb_add_eulerbeam3d(mb_handle* h, int64_t nele, const double* eleobj, int
         CK(dalloc(h, &g.mat_id, nele));
         CK(cudaMemcpy(g.mat_id, mat_id.data(), mat_id.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
-    int32_t rc = upload_index(h, idxX, nele * 12, 0, &g.idxX);
+    int32_t rc = upload_index(h, idxX, nele * 12, 0, &g.idxX, &g.maxX);
     if (rc) return rc;
-    if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU); if (rc) return rc; }
+    if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU, &g.maxU); if (rc) return rc; }
     for (int i = 0; i < 12; ++i) g.scaleX[i] = scaleX[i];
     if (udof) for (int i = 0; i < 3; ++i) g.scaleU[i] = scaleU[i];
     h->groups.push_back(g);
@@ -123,7 +124,7 @@ int32_t mb_add_host_elements(mb_handle* h, int64_t nele, int32_t nx, const int64
     CK(cudaSetDevice(h->device));
     Group g;
     g.kind = G_HOST; g.nele = nele; g.nx = nx;
-    int32_t rc = upload_index(h, idxX, nele * nx, 0, &g.idxX);
+    int32_t rc = upload_index(h, idxX, nele * nx, 0, &g.idxX, &g.maxX);
     if (rc) return rc;
     h->groups.push_back(g);
     if (ieletyp_out) *ieletyp_out = (int32_t)h->groups.size();
@@ -159,6 +160,7 @@ int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
     if (!h) return MB_ERR_ARG;
     ARG(!h->prepared, "already prepared");
     ARG(ndofX >= 1 && ndofX < INT32_MAX, "ndofX out of range");
+    { int32_t rc = check_group_dofs(h, ndofX, h->ndofU > 0 ? h->ndofU : INT64_MAX); if (rc) return rc; }     // ndofU may be left unset for SweepX (U is read through idxU only when given)
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     h->ndofX = ndofX;
@@ -209,6 +211,9 @@ int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
         CK(cudaMemcpyAsync(&last, inz + (npair - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st)); cudaFree(tmp);
         nnz = last;
+        // asm2 / colptr0 / rowval0 / the pair descriptors index non-zeros with 32 bits (signed in asm2): an EulerBeam3D chain has 108 non-zeros per element,
+        // so the npair < 2^32 guard above (29.8 M beams) is not enough — 19.9 M elements already pass 2^31 non-zeros
+        if (nnz > (int64_t)INT32_MAX) { h->err = "more than 2^31-1 non-zeros on one device: shard the element range (mb_iface_*)"; dfree(h, keys); dfree(h, keys2); dfree(h, vals); dfree(h, inz); return MB_ERR_TOOBIG; }
         CK(dalloc(h, &h->rowval0, nnz)); CK(dalloc(h, &h->cstart, nnz + 1));
         finish_pattern_kernel<<<nblk(npair, 256), 256, 0, st>>>(npair, keys2, h->src, inz, (uint64_t)ndofX, h->asm2, h->rowval0, h->cstart);
         colptr_kernel<<<nblk(nnz, 256), 256, 0, st>>>(nnz, keys2, h->cstart, (uint64_t)ndofX, h->colptr0);
@@ -785,6 +790,10 @@ int32_t mb_iface_setup(mb_handle* h, int64_t n_send_nz, const int64_t* send_nz, 
         if (n1 + n2) CK(cudaMemcpy(*dst, t.data(), t.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         return MB_OK;
     };
+    for (int64_t i = 0; i < n_send_nz; ++i) ARG(send_nz[i] >= 1, "send positions are 1-based (0 = ghost is for receive lists only)");
+    for (int64_t i = 0; i < n_send_v; ++i) ARG(send_v[i] >= 1, "send positions are 1-based (0 = ghost is for receive lists only)");
+    if (h->if_sendbuf) { dfree(h, h->if_sendbuf); h->if_sendbuf = nullptr; }
+    if (h->if_recvbuf) { dfree(h, h->if_recvbuf); h->if_recvbuf = nullptr; }
     int32_t rc = up(n_send_nz, send_nz, h->nnz, n_send_v, send_v, h->ndofX, &h->if_send);
     if (rc) return rc;
     rc = up(n_recv_nz, recv_nz, h->nnz, n_recv_v, recv_v, h->ndofX, &h->if_recv);
@@ -794,19 +803,25 @@ int32_t mb_iface_setup(mb_handle* h, int64_t n_send_nz, const int64_t* send_nz, 
 }
 int32_t mb_iface_pack_dev(mb_handle* h, double* sendbuf_dev) {
     if (!h) return MB_ERR_ARG;
+    ARG(h->prepared, "call mb_sweepx_prepare first");
     const int64_t n = h->if_nsend_nz + h->if_nsend_v;
     if (n == 0) return MB_OK;
     ARG(sendbuf_dev, "null buffer");
+    CK(cudaSetDevice(h->device));
     iface_pack_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(h->if_nsend_nz, n, h->if_send, h->nzval, h->Ll, sendbuf_dev);
+    CK(cudaGetLastError());
     h->launches++;
     return MB_OK;
 }
 int32_t mb_iface_unpack_add_dev(mb_handle* h, const double* recvbuf_dev) {
     if (!h) return MB_ERR_ARG;
+    ARG(h->prepared, "call mb_sweepx_prepare first");
     const int64_t n = h->if_nrecv_nz + h->if_nrecv_v;
     if (n == 0) return MB_OK;
     ARG(recvbuf_dev, "null buffer");
+    CK(cudaSetDevice(h->device));
     iface_unpack_kernel<<<nblk(n, 128), 128, 0, h->stream>>>(h->if_nrecv_nz, n, h->if_recv, recvbuf_dev, h->nzval, h->Ll);
+    CK(cudaGetLastError());
     h->launches++;
     return MB_OK;
 }
@@ -852,9 +867,9 @@ int32_t mb_add_bar3d(mb_handle* h, int64_t nele, const double* eleobj, int32_t u
     CK(dalloc(h, &g.barmats, (int64_t)mats.size()));
     CK(cudaMemcpy(g.barmats, mats.data(), mats.size() * sizeof(BarMat), cudaMemcpyHostToDevice));
     if (mats.size() > 1) { CK(dalloc(h, &g.mat_id, nele)); CK(cudaMemcpy(g.mat_id, mat_id.data(), mat_id.size() * sizeof(int32_t), cudaMemcpyHostToDevice)); }
-    int32_t rc = upload_index(h, idxX, nele * 6, 0, &g.idxX);
+    int32_t rc = upload_index(h, idxX, nele * 6, 0, &g.idxX, &g.maxX);
     if (rc) return rc;
-    if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU); if (rc) return rc; }
+    if (udof) { rc = upload_index(h, idxU, nele * 3, 0, &g.idxU, &g.maxU); if (rc) return rc; }
     for (int i = 0; i < 6; ++i) g.scaleX[i] = scaleX[i];
     if (udof) for (int i = 0; i < 3; ++i) g.scaleU[i] = scaleU[i];
     h->groups.push_back(g);
@@ -870,7 +885,7 @@ int32_t mb_add_soilcontact(mb_handle* h, int64_t nele, const double* eleobj, con
     g.kind = G_SOIL; g.nele = nele; g.nx = 3;
     CK(dalloc(h, &g.geo, nele * 5));
     CK(cudaMemcpy(g.geo, eleobj, (size_t)nele * 5 * sizeof(double), cudaMemcpyHostToDevice));
-    int32_t rc = upload_index(h, idxX, nele * 3, 0, &g.idxX);
+    int32_t rc = upload_index(h, idxX, nele * 3, 0, &g.idxX, &g.maxX);
     if (rc) return rc;
     for (int i = 0; i < 3; ++i) g.scaleX[i] = scaleX[i];
     h->groups.push_back(g);

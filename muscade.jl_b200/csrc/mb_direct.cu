@@ -448,6 +448,13 @@ __global__ void __launch_bounds__(256) block_sumsq_kernel(int64_t nX, int64_t nU
 
 }  // namespace
 
+// location of the first NaN, packed so that atomicMin keeps the FIRST one in (step, element type, element) order: step above bit 46, six bits of
+// element-type index (MAXG = 32 types), 40 bits of element index — one encode / decode pair for every kernel of this file
+static inline unsigned long long nan_pack(int64_t step, int ig) { return (((unsigned long long)step) << 46) | (((unsigned long long)ig) << 40); }
+static inline void nan_unpack(unsigned long long f, mb_errinfo* where) {
+    where->ieletyp = (int32_t)((f >> 40) & 0x3F) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = (int64_t)(f >> 46) + 1;
+}
+static_assert(MAXG <= 64, "nan_pack gives the element-type index six bits");
 struct DirectData {
     int OX = 0, OU = 0;
     int64_t nX = 0, nU = 0, nstep = 0, lo = 0, hi = 0, elo = 0, ehi = 0;
@@ -512,6 +519,7 @@ static int32_t build_pattern(mb_handle* h, PairPat& P, bool rowU, bool colU, int
     CK(cudaMemcpyAsync(&last, inz + (npair - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st)); cudaFree(tmp);
     P.nnz = last;
+    if (P.nnz > (int64_t)INT32_MAX) { h->err = "more than 2^31-1 non-zeros in a class-pair pattern on one device"; dfree(h, keys); dfree(h, keys2); dfree(h, vals); dfree(h, inz); return MB_ERR_TOOBIG; }
     CK(dalloc(h, &P.rowval0, P.nnz)); CK(dalloc(h, &P.cstart, P.nnz + 1));
     finish_pat_kernel<<<nblk(npair, 256), 256, 0, st>>>(npair, keys2, P.src, inz, (uint64_t)nrows, P.asmK, P.rowval0, P.cstart);
     colptr_pat_kernel<<<nblk(P.nnz, 256), 256, 0, st>>>(P.nnz, keys2, P.cstart, (uint64_t)nrows, ncols, P.colptr0);
@@ -550,6 +558,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     h->direct = D;
     D->OX = OX; D->OU = OU; D->nX = ndofX; D->nU = ndofU; D->nstep = nstep; D->lo = step_lo; D->hi = step_hi; D->dt = dt;
     D->elo = step_lo - 2 < 0 ? 0 : step_lo - 2; D->ehi = step_hi + 2 > nstep ? nstep : step_hi + 2;
+    { int32_t rcd = check_group_dofs(h, ndofX, ndofU); if (rcd) { delete D; h->direct = nullptr; return rcd; } }
     h->ndofX = ndofX; h->ndofU = ndofU;
     int32_t rc;
     if ((rc = build_pattern(h, D->pat[P_XX], false, false, ndofX, ndofX))) return rc;
@@ -703,7 +712,7 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         for (size_t ig = 0; ig < h->groups.size(); ++ig) {
             const Group& g = h->groups[ig];
             if (g.nele == 0) continue;
-            const unsigned long long nanbase = (((unsigned long long)s) << 44) | (((unsigned long long)ig) << 40);
+            const unsigned long long nanbase = nan_pack(s, (int)ig);
             double* dR = D->dR + D->G.drbase[ig]; double* R = D->R + D->G.rbase[ig];
             if (g.kind == G_BAR) {
                 BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
@@ -804,7 +813,7 @@ int32_t mb_direct_assemble(mb_handle* h, int64_t eval_lo, int64_t eval_hi, int32
     }
     if (rc == MB_ERR_NAN && where) {     // nanbase packs (step, ieletyp, iele)
         const unsigned long long f = *h->nanflag_host;
-        where->ieletyp = (int32_t)((f >> 40) & 0xF) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = (int64_t)(f >> 44) + 1;
+        nan_unpack(f, where);
     }
     return rc;
 }
@@ -1091,6 +1100,36 @@ int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nL
     if (LU) *LU = D->LU + k * D->pat[P_XU].nnz; if (nLU) *nLU = D->pat[P_XU].nnz;
     if (L1L) *L1L = D->L1L + k * D->nX; if (nL1) *nL1 = D->nX;
     return MB_OK;
+}
+// Time shards over NCCL: rank r owns the steps [lo,hi) and stores [lo−2,hi+2)∩[0,nstep).  After its own steps are evaluated
+// (mb_direct_assemble(eval_lo = lo, eval_hi = hi, build_big = 0)) the per-step blocks its neighbours' stencils reach go out and the halo blocks come in:
+// L2[Λ,X][1,:] (the only per-step block read at a foreign step by the columns of an owned step, src/DirectXUA.jl:342-352 with src/FiniteDifferences.jl:2-4)
+// and, when second-order element types are present, L1[X][:] .  Ranks are consecutive time shards of equal length: rank−1 owns the steps before lo.
+// Asynchronous on the handle's stream; follow with mb_direct_assemble(eval_lo = eval_hi, build_big = 1).
+int32_t mb_direct_halo_exchange(mb_handle* h) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(h->comm, "call mb_comm_init first");
+    CK(cudaSetDevice(h->device));
+    const int64_t nd = D->OX + 1, nLX = nd * D->pat[P_XX].nnz, nL1X = D->L1X ? nd * D->nX : 0;
+    const int64_t nl = D->lo - D->elo, nr = D->ehi - D->hi;              // halo steps stored on the left / right (0, 1 or 2)
+    const int64_t own = D->hi - D->lo;
+    ARG(own >= 2, "a time shard needs at least two steps");
+    std::vector<MbXfer> s, r;
+    auto at = [&](double* base, int64_t per, int64_t step) { return base + (step - D->elo) * per; };
+    if (D->lo > 0) {                                                      // left neighbour: my first two steps out, its last nl steps in
+        ARG(h->rank > 0, "steps before this shard but no rank to the left");
+        s.push_back({at(D->LX, nLX, D->lo), 2 * nLX, h->rank - 1});
+        r.push_back({at(D->LX, nLX, D->elo), nl * nLX, h->rank - 1});
+        if (nL1X) { s.push_back({at(D->L1X, nL1X, D->lo), 2 * nL1X, h->rank - 1}); r.push_back({at(D->L1X, nL1X, D->elo), nl * nL1X, h->rank - 1}); }
+    }
+    if (D->hi < D->nstep) {                                               // right neighbour: my last two steps out, its first nr steps in
+        ARG(h->rank + 1 < h->world, "steps after this shard but no rank to the right");
+        s.push_back({at(D->LX, nLX, D->hi - 2), 2 * nLX, h->rank + 1});
+        r.push_back({at(D->LX, nLX, D->hi), nr * nLX, h->rank + 1});
+        if (nL1X) { s.push_back({at(D->L1X, nL1X, D->hi - 2), 2 * nL1X, h->rank + 1}); r.push_back({at(D->L1X, nL1X, D->hi), nr * nL1X, h->rank + 1}); }
+    }
+    return mb_comm_sendrecv(h, s, r);
 }
 int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms) {
     if (!h || !h->direct || !ms) return MB_ERR_ARG;

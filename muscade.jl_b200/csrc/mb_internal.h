@@ -15,6 +15,8 @@ using namespace mb;
 
 struct mb_handle;
 void mb_direct_release(mb_handle* h);   // mb_direct.cu
+struct MbXfer { double* p; int64_t n; int peer; };
+int32_t mb_comm_sendrecv(mb_handle* h, const std::vector<MbXfer>& sends, const std::vector<MbXfer>& recvs);   // mb_comm.cu: one NCCL group on h->stream
 
 enum GroupKind { G_BEAM = 1, G_BAR = 2, G_SOIL = 3, G_HOST = 4 };
 
@@ -31,6 +33,7 @@ struct Group {
     double scaleX[12] = {0}, scaleU[3] = {0};
     int64_t pair_base = 0;       // offset of this group's nx²·nele tangent entries in Ke_all
     int64_t vec_base = 0;        // offset of this group's nx·nele residual entries in Re_all
+    int64_t maxX = 0, maxU = 0;  // largest 1-based dof numbers of the group (checked against ndofX / ndofU at prepare)
 };
 
 struct mb_handle {
@@ -56,10 +59,12 @@ struct mb_handle {
     int64_t launches = 0;
     int beamW = 1;
     std::vector<void*> owned;
-    double* Wc = nullptr; int64_t Wc_len = 0; int split_dyn = 1; int static_sym = 1; int nsm = 148;   // cotangent workspace of the two-phase Newmark kernel
+    double* Wc = nullptr; int64_t Wc_len = 0; int split_dyn = 1; int static_sym = 3; int nsm = 148;   // cotangent workspace of the two-phase Newmark kernel
     bool own_stream = true;
     int32_t *if_send = nullptr, *if_recv = nullptr;   // interface index lists (0-based into [nzval | Lλ], −1 = ghost)
     int64_t if_nsend_nz = 0, if_nsend_v = 0, if_nrecv_nz = 0, if_nrecv_v = 0;
+    double *if_sendbuf = nullptr, *if_recvbuf = nullptr;   // device buffers of mb_iface_exchange
+    void* comm = nullptr; bool comm_owned = true; int rank = 0, world = 1; double* comm_scratch = nullptr;   // NCCL communicator of this handle (mb_comm.cu)
     struct DirectData* direct = nullptr;      // DirectXUA state (mb_direct.cu)
     // host-buffer path (mb_sweepx_assemble): element ranges are evaluated chunk by chunk and every prefix of nzval / Lλ whose contributors
     // are all done is reduced and copied to the host while the next chunk computes
@@ -103,15 +108,28 @@ static inline void dfree(mb_handle* h, void* p) {
     cudaFree(p);
 }
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+// every group's dof numbers against the model sizes given to prepare (an index beyond them would scatter outside colptr / the state vectors)
+static inline int32_t check_group_dofs(mb_handle* h, int64_t ndofX, int64_t ndofU) {
+    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+        const Group& g = h->groups[ig];
+        if (g.maxX > ndofX) { h->err = "element type " + std::to_string(ig + 1) + ": X-dof index " + std::to_string(g.maxX) + " exceeds ndofX = " + std::to_string(ndofX); return MB_ERR_ARG; }
+        if (g.maxU > ndofU) { h->err = "element type " + std::to_string(ig + 1) + ": U-dof index " + std::to_string(g.maxU) + " exceeds ndofU = " + std::to_string(ndofU); return MB_ERR_ARG; }
+    }
+    return MB_OK;
+}
 
 // Int64 1-based [nele][n] (reference memory order) → int32 0-based on the device
-static inline int32_t upload_index(mb_handle* h, const int64_t* src, int64_t n, int64_t limit, int32_t** dst) {
+// maxout: largest 1-based index seen (the model sizes are not known yet when groups are added: prepare checks it against ndofX / ndofU)
+static inline int32_t upload_index(mb_handle* h, const int64_t* src, int64_t n, int64_t limit, int32_t** dst, int64_t* maxout = nullptr) {
     std::vector<int32_t> tmp((size_t)n);
+    int64_t mx = 0;
     for (int64_t i = 0; i < n; ++i) {
         const int64_t v = src[i];
         if (v < 1 || (limit > 0 && v > limit) || v > INT32_MAX) { h->err = "dof index out of range (expects 1-based Int64)"; return MB_ERR_ARG; }
         tmp[(size_t)i] = (int32_t)(v - 1);
+        if (v > mx) mx = v;
     }
+    if (maxout) *maxout = mx;
     CK(dalloc(h, dst, n));
     CK(cudaMemcpy(*dst, tmp.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
     return MB_OK;

@@ -186,6 +186,11 @@ class DirectEngine(Engine):
         check(self.h, self.L.mb_direct_step_ptrs(self.h, int(step), C.byref(p[0]), C.byref(n[0]), C.byref(p[1]), C.byref(n[1]), C.byref(p[2]), C.byref(n[2])))
         return [(p[i].value, n[i].value) for i in range(3)]
 
+    def halo_exchange(self):
+        """time shards: the per-step blocks of the two steps at each end of the owned range go to the neighbours, the halo steps' blocks come in
+        (NCCL inside the shim, asynchronous on the handle's stream)"""
+        check(self.h, self.L.mb_direct_halo_exchange(self.h))
+
     def direct_time(self, reps=3):
         ms = np.zeros(3, np.float32)
         check(self.h, self.L.mb_direct_time_dev(self.h, reps, ms))
@@ -229,7 +234,7 @@ def host_costs(eng, step, X0, U0, t):
         clas = et.extra["clas"]
         idx = (ed.X if clas == "X" else ed.U)[:, 0] - 1
         sc = (ed.scaleX if clas == "X" else ed.scaleU)[0]
-        c, c1, c2 = et.ElType.cost_derivs(et.extra, (X0 if clas == "X" else U0)[idx], t)
+        c, c1, c2 = et.cost_derivs((X0 if clas == "X" else U0)[idx], t)
         np.add.at(g[clas], idx, c1 * sc); np.add.at(h[clas], idx, c2 * sc * sc)
         total += float(c.sum())
     return g["X"], h["X"], g["U"], h["U"], total
@@ -242,9 +247,8 @@ def host_elements(eng, step, X, Lam, t, Λscale):
     xx = {}                                     # (i,j) → Σ over elements, in element order (types whose residual is not linear in X)
     for ityp, et, ed in eng.host_types:
         Xe = [X[d][ed.X - 1] for d in range(nd)]
-        R, K0, K1, K2 = et.ElType.residual(et.extra if et.extra is not None else et.eleobj, Xe, t)
-        hess = getattr(et.ElType, "hessian", None)
-        H = hess(et.extra if et.extra is not None else et.eleobj, Xe, Lam[ed.X - 1], t) if hess else None
+        R, K0, K1, K2 = et.residual(Xe, t)
+        H = et.hessian(Xe, Lam[ed.X - 1], t)
         if H is not None:                       # L2[X,X][1,1] += Λ·∂²R/∂X²·sX·sX  (DirectXUA.jl:121-150)
             H = H * ed.scaleX[None, :, None] * ed.scaleX[None, None, :]
             for e in range(H.shape[0]):

@@ -232,6 +232,54 @@ class Engine:
     def iface_unpack_add(self, dev_ptr):
         check(self.h, self.L.mb_iface_unpack_add_dev(self.h, C.c_void_p(int(dev_ptr))))
 
+    def iface_exchange(self):
+        """pack → NCCL send to rank+1 / receive from rank−1 → unpack-add, inside the shim, asynchronous on the handle's stream"""
+        check(self.h, self.L.mb_iface_exchange(self.h))
+
+    def iface_buffers(self):
+        """(send pointer, n_send, receive pointer, n_recv) of the device buffers mb_iface_exchange uses"""
+        ps, pr, ns, nr = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self.h, self.L.mb_iface_buffers(self.h, C.byref(ps), C.byref(ns), C.byref(pr), C.byref(nr)))
+        return ps.value, ns.value, pr.value, nr.value
+
+    def iface_recvbuf(self):
+        n = self.iface_buffers()[3]
+        out = np.zeros(n)
+        check(self.h, self.L.mb_iface_get_recvbuf(self.h, ptr(out)))
+        return out
+
+    # ---- NCCL inside the shim ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (one process creates it, the host hands it to the others)"""
+        buf = np.zeros(128, np.uint8)
+        rc = _lib.lib().mb_comm_unique_id(ptr(buf))
+        if rc != _lib.MB_OK:
+            raise MuscadeB200Error("muscade_b200 [%d]: ncclGetUniqueId failed (libnccl.so.2 missing?)" % rc)
+        return buf
+
+    def comm_init(self, uid, rank, world):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.size == 128
+        check(self.h, self.L.mb_comm_init(self.h, ptr(uid), int(rank), int(world)))
+
+    def comm_init_from(self, owner):
+        """borrow the NCCL communicator of another Engine on the same GPU (which must outlive this one)"""
+        check(self.h, self.L.mb_comm_share(self.h, owner.h))
+
+    def comm_info(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.h, self.L.mb_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def comm_allreduce(self, values, op="sum"):
+        a = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).copy()
+        check(self.h, self.L.mb_comm_allreduce(self.h, ptr(a), a.size, {"sum": 0, "max": 1, "min": 2}[op]))
+        return a
+
+    def comm_barrier(self):
+        check(self.h, self.L.mb_comm_barrier(self.h))
+
     def pin(self, a):
         """page-lock a numpy array in place (cudaHostRegister)"""
         check(self.h, self.L.mb_host_register(self.h, ptr(a), a.nbytes))

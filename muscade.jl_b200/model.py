@@ -43,6 +43,43 @@ class EleTyp:
     def idof(self, clas):
         return [j for j, c in enumerate(self.clas) if c == clas]
 
+    # ---- host-evaluated element types (user closures) -----------------------------------------------------------------------------------------
+    # The reference stores args / costargs / gargs in every element object (src/BasicElements.jl:198-208,275-284,406-438), so two addelement! calls
+    # with the same closure and different arguments land in ONE element type whose elements differ.  `runs` keeps the keyword data of each call with
+    # the element range it covers; the evaluators below call the element type once per run and stitch the results in element order.
+    def _runs(self):
+        runs = getattr(self, "runs", None)
+        return runs if runs else [(0, self.nele, self.extra if self.extra is not None else self.eleobj)]
+
+    def residual(self, X, t):
+        """ElType.residual over all elements: X = [X₀,X′,…] of shape (nele,nx) each → (R, K0, K1, K2), K1/K2 None when no run has them"""
+        parts = [self.ElType.residual(ex, [x[a:b] for x in X], t) for a, b, ex in self._runs()]
+        if len(parts) == 1:
+            return parts[0]
+        out = []
+        for k in range(4):
+            cols = [p[k] for p in parts]
+            if all(c is None for c in cols):
+                out.append(None); continue
+            ref = next(c for c in cols if c is not None)
+            cols = [c if c is not None else np.zeros((b - a,) + ref.shape[1:]) for c, (a, b, _) in zip(cols, self._runs())]
+            out.append(np.concatenate(cols))
+        return tuple(out)
+
+    def hessian(self, X, lam_e, t):
+        fn = getattr(self.ElType, "hessian", None)
+        if fn is None:
+            return None
+        parts = [fn(ex, [x[a:b] for x in X], lam_e[a:b], t) for a, b, ex in self._runs()]
+        if all(p is None for p in parts):
+            return None
+        ref = next(p for p in parts if p is not None)
+        return np.concatenate([p if p is not None else np.zeros((b - a,) + ref.shape[1:]) for p, (a, b, _) in zip(parts, self._runs())])
+
+    def cost_derivs(self, x, t):
+        parts = [self.ElType.cost_derivs(ex, x[a:b], t) for a, b, ex in self._runs()]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+
 
 class Model:
     def __init__(self, ID="muscade_model"):
@@ -198,6 +235,10 @@ def addelement(model, ElType, nodID, **kwargs):
         et.eleobj, et.extra = eleobj, extra
     else:
         et.eleobj = np.concatenate([et.eleobj, eleobj])
+    if extra is not None:                                   # per-call keyword data (args, costargs, gargs …) with the elements it belongs to
+        if not hasattr(et, "runs"):
+            et.runs = []
+        et.runs.append((iele_sofar, iele_sofar + nele_new, extra))
     iele = iele_sofar + np.arange(1, nele_new + 1)
     return (ieletyp, int(iele[0])) if single else (ieletyp, iele)
 

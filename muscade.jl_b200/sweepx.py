@@ -113,7 +113,7 @@ def _host_elements(out, state, mission, t):
     step = mission == "step" and OX > 0
     for ityp, et, ed in out.host_types:
         X = [state.X[d][ed.X - 1] for d in range(OX + 1)]
-        R, K0, K1, K2 = et.ElType.residual(et.extra if et.extra is not None else et.eleobj, X, t)
+        R, K0, K1, K2 = et.residual(X, t)
         s = ed.scaleX
         K = K0.copy()
         if K1 is not None and OX >= 1: K = K + a1 * K1

@@ -95,6 +95,32 @@ extern "C" int mbh_beam_static_sym(const double* geo16, const double* mat16, con
     return bad;
 }
 
+// statics, active/passive formulation exactly as beam_static_ap_kernel's lanes run it (packs evaluated locally; the kernel exchanges them by shuffles)
+extern "C" int mbh_beam_static_ap(const double* geo16, const double* mat16, const double* Xval, const double* scale, int udof, const double* Uval,
+                                  double* R, double* K) {
+    BeamGeo g; BeamMat m;
+    for (int i = 0; i < 3; ++i) g.cm[i] = geo16[i];
+    for (int i = 0; i < 9; ++i) g.rm.a[i] = geo16[3 + i];
+    for (int i = 0; i < 3; ++i) g.tgm[i] = geo16[12 + i];
+    g.L = geo16[15];
+    std::memcpy(&m, mat16, sizeof m);
+    static const int rot[6] = {3, 4, 5, 9, 10, 11}, tra[6] = {0, 1, 2, 6, 7, 8};
+    int bad = 0;
+    double xu[6], xv[6];
+    for (int i = 0; i < 6; ++i) { xu[i] = Xval[tra[i]]; xv[i] = Xval[rot[i]]; }
+    for (int l = 0; l < 6; ++l) {
+        SD<false, false> U[3]; SD<true, false> Rv[12];
+        for (int i = 0; i < 3; ++i) U[i].v = udof ? Uval[i] : 0.;
+        double Gc[3];
+        ApCollect col{l < 3, Rv, Gc};
+        beam_static_ap_lane(g, m, xu, xv, scale[rot[l]], l, udof != 0, U, PacksLocal(), col);
+        bad |= beam_static_sym_store(l, Rv, Gc, scale, [&](int k, double v) { K[(k % 12) * 12 + k / 12] = v; },
+                                     [&](int k, double v0, double v1) { K[(k % 12) * 12 + k / 12] = v0; K[((k + 1) % 12) * 12 + (k + 1) / 12] = v1; });
+        if (l == 0) for (int i = 0; i < 12; ++i) R[i] = Rv[i].v * scale[i];
+    }
+    return bad;
+}
+
 // getresult values (beam_results, the body of beam_results_kernel): X element dof order t1..r3 of node 1 then node 2, as the reference
 extern "C" int mbh_beam_results(const double* geo16, const double* mat16, int nd, const double* Xval, double* out77) {
     BeamGeo g; BeamMat m;

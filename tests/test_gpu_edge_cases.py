@@ -133,3 +133,18 @@ def test_directxua_nan_reports_step_and_element(mb):
         assert d["step"] == 5 and d["ieletyp"] == 1 and d["iele"] == min(e for e in range(N) if (dis.dis[0].X[e] == dis.dis[0].X[6, 2]).any()) + 1
     finally:
         eng.close()
+
+
+def test_dof_index_beyond_model_size_is_rejected(mb):
+    """prepare checks every group's dof numbers against ndofX / ndofU (they are not known when the groups are added): an index beyond the model would
+    scatter outside colptr and read outside the state vectors — MB_ERR_ARG instead"""
+    eleobj, idx, ndof = mb.synthetic.chain(5)
+    e = mb.Engine(0)
+    e.add_eulerbeam3d(eleobj, idx, np.ones(12))
+    with pytest.raises(mb.MuscadeB200Error, match="exceeds ndofX"):
+        e.sweepx_prepare(ndof - 1)
+    e.close()
+    e = mb.Engine(0)
+    e.add_eulerbeam3d(eleobj, idx, np.ones(12))
+    assert e.sweepx_prepare(ndof) == 108 * 5 + 36
+    e.close()

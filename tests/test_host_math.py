@@ -94,6 +94,25 @@ def test_static_symmetric_tangent_vs_oracle(H, amp, udof):
     assert np.abs(K0 - K0.T).max() <= 1e-12 * np.abs(K0).max()          # the property the kernel relies on, checked on the ORACLE's tangent
 
 
+@pytest.mark.parametrize("amp", [0.0, 1.0, 3.0, 8.0])
+@pytest.mark.parametrize("udof", [0, 1])
+def test_static_active_passive_vs_oracle(H, amp, udof):
+    """statics kernel, active/passive formulation (beam_static_ap): each lane's seeded rotation dof belongs to its ACTIVE node; the corotated frame is
+    rebuilt from N = r_a r_p^T so that everything depending on the passive node only is plain values. Same checks as the symmetric kernel."""
+    H.mbh_beam_static_ap.argtypes = [f64p, f64p, f64p, f64p, C.c_int, f64p, f64p, f64p]
+    rng = np.random.default_rng(77 + int(amp))
+    e = OE.beam_ctor([0, 0, 0], [.8, .6, 0.1], OE.beam_cross_section(**MAT), orient2=(0, 1, .2))
+    scale = np.array([10., 20, 5, 1, 2, 3, 7, 10, 4, .5, 1, 2])
+    X = np.zeros((1, 12)); X[0] = rng.uniform(-1, 1, 12) * 0.3 * amp
+    U = rng.uniform(-1, 1, 3) * udof
+    Xs = np.zeros((1, 12, 12)); Xs[0, np.arange(12), np.arange(12)] = scale
+    R0, dR0, rc = OE.beam_residual(e, X, Xs, U, np.zeros((3, 12)))
+    K0 = dR0 * scale[:, None]
+    R1 = np.zeros(12); K1 = np.zeros((12, 12))
+    assert H.mbh_beam_static_ap(geo16(e), np.ascontiguousarray(e[53:69]), np.ascontiguousarray(X[0]), scale, udof, U, R1, K1) == 0
+    assert rel(R1, R0 * scale) <= 1e-12 and rel(K1, K0) <= 1e-12
+
+
 def test_reference_pow_quirk_is_reproduced(H):
     """src/Adiff.jl:230 (x^0 → zero) drops 2·ċ² from d²/dt² of sinc1(θ/2)² in Rodrigues for 3-deep duals (SweepX{2}, DirectXUA OX=2).
     The oracle has it by construction; the product reproduces it (sqr_ref). A mathematically 'correct' square differs at 1e-6."""

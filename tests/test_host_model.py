@@ -127,3 +127,23 @@ def test_dofconstraint_hessian_matches_finite_differences():
             assert np.abs(H - Hfd).max() < 1e-8 and np.abs(H - H.transpose(0, 2, 1)).max() == 0.
     lin = dict(gap=lambda x, t: (x[:, 0] - t, np.ones_like(x)), gargs=(), mode="equal", Nx=1)
     assert mb.DofConstraint.hessian(lin, [np.array([[0.3, 0.7]])], np.array([[0.2, -0.5]]), 0.) is None      # affine gap, equal mode: R linear in (x,λ)
+
+
+def test_host_element_arguments_are_kept_per_element():
+    """the reference stores args / costargs / gargs in every element object (src/BasicElements.jl:198-208,275-284): two addelement! calls with the same
+    closure and different arguments make ONE element type whose elements differ — the later arguments must not be dropped"""
+    import muscade_b200 as mb
+    model = mb.Model()
+    nod = mb.addnode(model, np.array([[0., 0, 0], [1., 0, 0], [2., 0, 0]]))
+    cost = lambda x, t, k: 0.5 * k * x * x
+    t1, _ = mb.addelement(model, mb.SingleDofCost, [nod[0]], clas="X", field="t1", cost=cost, costargs=(1.,))
+    t2, _ = mb.addelement(model, mb.SingleDofCost, [nod[1]], clas="X", field="t1", cost=cost, costargs=(5.,))
+    assert t1 == t2 and model.ele[t1 - 1].nele == 2
+    c, c1, c2 = model.ele[t1 - 1].cost_derivs(np.array([2., 2.]), 0.)
+    assert c.tolist() == [2., 10.] and c1.tolist() == [2., 10.] and c2.tolist() == [1., 5.]
+    load = lambda t, a: a * t
+    l1, _ = mb.addelement(model, mb.DofLoad, [nod[0]], field="t2", value=load, args=(1.,))
+    l2, _ = mb.addelement(model, mb.DofLoad, np.array([[nod[1]], [nod[2]]]), field="t2", value=load, args=(-3.,))
+    assert l1 == l2
+    R, K0, K1, K2 = model.ele[l1 - 1].residual([np.zeros((3, 1))], 2.)
+    assert R[:, 0].tolist() == [-2., 6., 6.] and K0.shape == (3, 1, 1) and K1 is None
