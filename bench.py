@@ -9,7 +9,10 @@ EulerBeam3D elements per GPU, one SweepX `assemble!{:iter}` per
 reduction into Lλ and the CSC nzval.  `value`: state resident in HBM.  `e2e`: through the C-ABI call mb_sweepx_assemble with
 pinned HOST buffers (H2D state, D2H Lλ + nzval inside the timed region).
 N>1 (weak scaling): the chain has N·E elements, rank r owns elements [r·E,(r+1)·E); every step ends with the interface exchange
-(78 doubles per cut, NCCL send/recv to the right neighbour) — sharding.py.
+(78 doubles per cut, NCCL send/recv to the right neighbour INSIDE the shim: mb_comm_init / mb_iface_exchange — torch.distributed (gloo) only hands the
+128-byte NCCL id round at start-up, nothing of it is on the timed path).
+Every default line also carries a `directxua` block: BASELINE.json configs[3] (1e5 elements x 2000 time steps, time-sharded, strong scaling) measured in the
+same run, so that the driver's 1→8 scaling record holds the DirectXUA curve too (--no-directxua skips it).
 Inputs/outputs per step (≈1.8 GB read, ≈20 GB written/re-read per GPU) exceed the 126 MB L2: no L2 flush needed.
 
 `--workload directxua` (BASELINE.json configs[3]): DirectXUA{2,0,0} assemblebig! of a 100k-element Udof beam chain over 2000 time steps, the
@@ -58,6 +61,8 @@ def parse():
     ap.add_argument("--window", type=int, default=10)             # directxua: time steps per Lvv window
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-directxua", action="store_true")        # skip the configs[3] block of the default line
+    ap.add_argument("--dx-passes", type=int, default=2)           # timed passes of the configs[3] block (after 1 warm-up pass)
     return ap.parse_args()
 
 
@@ -107,7 +112,8 @@ class ClockSampler:
 
 
 def cpu_port_rate(mb, OX, nsample, nthreads):
-    """oracle (literal restatement of the reference algorithm) on `nsample` elements of the same chain/state."""
+    """oracle (literal restatement of the reference algorithm; the -O3 build with static-size duals, bit-identical to the checker build) on `nsample`
+    elements of the same chain/state."""
     from oracle import elements as OE, pattern as OP
     eleobj, idx, ndof = mb.synthetic.chain(nsample, dynamic=OX > 0)
     X = mb.synthetic.state(ndof, nder=OX + 1)
@@ -117,10 +123,7 @@ def cpu_port_rate(mb, OX, nsample, nthreads):
     L = np.zeros(ndof); nz = np.zeros(len(rv))
     a1t, a2t = np.ascontiguousarray(a1[0].T), np.ascontiguousarray(a2[0].T)
     t = time.perf_counter()
-    if nthreads == 1:
-        OE.sweepx_assemble_beams(eleobj, idx, a1t, a2t, OX, "iter", X, np.ones(12), nm, L, nz)
-    else:
-        OE.sweepx_assemble_beams_mt(eleobj, idx, a1t, a2t, OX, X, np.ones(12), nm, L, nz, nthreads)
+    OE.sweepx_assemble_beams_mt(eleobj, idx, a1t, a2t, OX, X, np.ones(12), nm, L, nz, nthreads, static_duals=True)
     dt = time.perf_counter() - t
     return nsample / dt, dt
 
@@ -159,7 +162,7 @@ def run_reference(args, rank, world):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if OE.max_threads() == 1 and os.environ.get("OMP_NUM_THREADS", "") not in ("", "1"):
         cores = 1                                   # built without OpenMP
-    nsample = max(1000, int(args.cpu_sample) * max(1, cores // 2))
+    nsample = max(1000, int(args.cpu_sample) * max(1, cores) * 2)
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_rate(mb, OX, 500, cores)
     times = []
@@ -173,7 +176,7 @@ def run_reference(args, rank, world):
             "data": "synthetic",
             "config": workload_config(args, OX, N, 1, note="bounded sample (%d elements per step) of the same chain/state; element loop spread over all host "
                                       "threads (the reference's own loop src/Assemble.jl:479 is serial), serial scatter" % nsample),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d elements x %d steps" % (nsample, args.steps)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d elements x %d steps, C++ port of the algorithm (not Muscade/Julia), -O3, static-size duals (12 partials)" % (nsample, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -194,16 +197,51 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_sweepx(args, rank, world, local, dist):
+def load_falg(key):
+    """frozen algorithmic flop counts (tools/opcount.cpp → profiles/falg.json, table in BASELINE.md §5)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "falg.json")) as f:
+            return json.load(f)[key]
+    except Exception:
+        return None
+
+
+class Comm:
+    """One NCCL communicator per process, owned by a tiny engine that lives for the whole run (the shim's mb_comm_*); the 128-byte id travels over the
+    gloo group torchrun's environment describes — start-up plumbing only."""
+
+    def __init__(self, mb, rank, world, local, dist):
+        self.rank, self.world, self.eng = rank, world, None
+        if world > 1:
+            import torch
+            self.eng = mb.Engine(local)
+            uid = torch.from_numpy(mb.Engine.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8))
+            dist.broadcast(uid, src=0)
+            self.eng.comm_init(uid.numpy(), rank, world)
+
+    def attach(self, eng):
+        if self.eng is not None:
+            eng.comm_init_from(self.eng)
+
+    def max(self, x):
+        return float(self.eng.comm_allreduce([x], "max")[0]) if self.eng is not None else float(x)
+
+    def barrier(self):
+        if self.eng is not None:
+            self.eng.comm_barrier()
+
+    def close(self):
+        if self.eng is not None:
+            self.eng.close(); self.eng = None
+
+
+def run_sweepx(args, rank, world, local, comm):
     import muscade_b200 as mb
     OX = args.ox
     N = int(args.nele or 1e7)
     eng = mb.Engine(local)
     fp64_peak = eng.fp64_tflops()
-    torch = None
-    if world > 1:
-        import torch
-        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    comm.attach(eng)
     eleobj, idx, ndof, dof0 = mb.sharding.chain_shard(N, rank, world, dynamic=OX > 0)
     ityp = eng.add_eulerbeam3d(eleobj, idx, np.ones(12))
     del eleobj, idx
@@ -212,115 +250,104 @@ def run_sweepx(args, rank, world, local, dist):
     nm = mb.synthetic.newmark_coefficients(OX, 0.3)
     Lh = np.empty(ndof); nzh = np.empty(nnz)
     eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh)       # uploads the state once: resident in HBM for `value`
-    sendbuf = recvbuf = None
     if world > 1:
         a2f = eng.sweepx_asm_range(ityp, 0, 1)[1][0]; a2l = eng.sweepx_asm_range(ityp, N - 1, N)[1][0]
         snz, sv, rnz, rvv = mb.sharding.interface_indices(a2l, a2f, ndof, rank, world)
         eng.iface_setup(snz, sv, rnz, rvv)
-        sendbuf = torch.zeros(max(1, len(snz) + len(sv)), dtype=torch.float64, device="cuda")
-        recvbuf = torch.zeros(max(1, len(rnz) + len(rvv)), dtype=torch.float64, device="cuda")
-
-    def step_dev():
-        eng.sweepx_assemble_dev(OX, "iter", nm)
-        if world > 1:
-            eng.iface_pack(sendbuf.data_ptr())
-            mb.sharding.exchange_neighbours(dist, sendbuf, recvbuf, rank, world)
-            eng.iface_unpack_add(recvbuf.data_ptr())
 
     def barrier():
-        eng.sync()
-        if dist is not None:
-            torch.cuda.synchronize(); dist.barrier()
+        eng.sync(); comm.barrier()
 
-    for _ in range(args.warmup):
-        step_dev()
+    # a step = mb_sweepx_assemble_dev (+ mb_iface_exchange on a shard), exactly as a solver issues it; mb_sweepx_time_step_dev runs `reps` of them
+    # between two CUDA events on the engine's stream
+    eng.time_step_dev(OX, "iter", nm, reps=max(1, args.warmup))
     barrier()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
-    if world == 1:
-        # K whole steps exactly as a solver issues them (mb_sweepx_assemble_dev), CUDA events on the engine's stream; then the same launch sets
-        # with an event between element kernels and reduction for the per-kernel breakdown / roofline
-        step_ms = eng.time_step_dev(OX, "iter", nm, reps=args.steps)
-        el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=max(3, min(args.steps, 5)))
-    else:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(args.steps):
-            step_dev()
-        ev1.record()
-        torch.cuda.synchronize()
-        step_ms = ev0.elapsed_time(ev1) / args.steps
-        el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=2)
-        tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        step_ms = float(tt.item())
+    step_ms = comm.max(eng.time_step_dev(OX, "iter", nm, reps=args.steps))
     barrier()
     wall = time.perf_counter() - t0
     launches = eng.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=max(3, min(args.steps, 5)))      # same launch sets with an event between element kernels and reduction
+    barrier()
     value = world * N / (step_ms * 1e-3)
 
     e2e = None
     if not args.no_e2e:
         for a in X + [Lh, nzh]:
             eng.pin(a)
-        for _ in range(2):
-            eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh)
-        barrier()
-        ts = []
-        for _ in range(max(3, min(args.steps, 5))):
-            t1 = time.perf_counter()
-            eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh)
-            ts.append(time.perf_counter() - t1)
-        e2e_ms = 1e3 * float(np.mean(ts))
-        if world > 1:
-            tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_ms = float(tt.item())
-        e2e = {"value": world * N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(8 * ndof * (OX + 1)), "d2h_bytes_per_step": int(8 * (ndof + nnz)),
-               "note": "mb_sweepx_assemble: pinned host state in, Llambda and nzval out (per rank); PCIe-bound (D2H of the CSC values)"}
+
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            barrier()
+            ts = []
+            for _ in range(reps):
+                t1 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t1)
+            return comm.max(1e3 * float(np.mean(ts)))
+        reps = max(3, min(args.steps, 5))
+        # (1) what a solver with a DEVICE sparse solver does (north_star: nzval handed over behind mb_get_device_ptrs): host state in, Lλ out, nzval stays in HBM
+        res_ms = timed(lambda: eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval_on_device=True), reps)
+        # (2) everything back to the host (a host sparse solver): + 8·nnz bytes of CSC values over PCIe, chunk-pipelined with the element kernels
+        all_ms = timed(lambda: eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh), reps)
+        e2e = {"value": world * N / (res_ms * 1e-3), "unit": UNIT, "ms_per_step": res_ms,
+               "h2d_bytes_per_step": int(8 * ndof * (OX + 1)), "d2h_bytes_per_step": int(8 * ndof),
+               "note": "mb_sweepx_assemble through the C ABI with pinned HOST buffers, per rank: state.X in, Llambda out; the CSC values stay in HBM for the device "
+                       "solver (mb_get_device_ptrs), as north_star specifies",
+               "host_csc": {"value": world * N / (all_ms * 1e-3), "unit": UNIT, "ms_per_step": all_ms, "h2d_bytes_per_step": int(8 * ndof * (OX + 1)),
+                            "d2h_bytes_per_step": int(8 * (ndof + nnz)),
+                            "note": "the same call with nzval copied to the host as well (host sparse solver): PCIe-bound on the D2H of the CSC values"}}
         for a in X + [Lh, nzh]:
             eng.unpin(a)
 
+    line = None
     if rank == 0:
         flops = load_flops(OX)
-        roof = {"bound": "fp64", "kernel": "beam_static_sym_kernel" if OX == 0 else "beam_cot_kernel<%d> + beam_kernel_sd<%d,split>" % (OX + 1, OX + 1), "unit": "TFLOP/s", "peak": fp64_peak,
+        falg = load_falg({0: "static", 1: "newmark_iter", 2: "newmark_iter"}[OX])
+        kern = "beam_static_ap_kernel" if OX == 0 else "beam_cot_kernel<%d> + beam_kernel_sd<%d,split>" % (OX + 1, OX + 1)
+        roof = {"bound": "fp64", "kernel": kern, "unit": "TFLOP/s", "peak": fp64_peak,
                 "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
-                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "kernel_ms_source": "CUDA events around the kernel's launches on the engine's stream", "traffic": None, "achieved": None, "frac": None}
+                "kernel_ms": el_ms, "kernel_share_of_step": el_ms / (el_ms + ga_ms), "kernel_ms_source": "CUDA events around the kernel's launches on the engine's stream",
+                "traffic": None, "achieved": None, "frac": None}
         if flops:
             roof["flop_per_element"] = flops["flop"]
             if flops.get("dram_bytes_per_element"):      # measured DRAM bytes of one launch of the element kernel(s) (ncu --set full, profiles/)
                 roof["traffic"] = int(N * flops["dram_bytes_per_element"]); roof["traffic_unit"] = "bytes per launch (dram read+write, ncu)"
             roof["achieved"] = N * flops["flop"] / (el_ms * 1e-3) / 1e12
             roof["frac"] = roof["achieved"] / fp64_peak
+            roof["frac_executed"] = roof["frac"]
+            roof["flop_source"] = "executed FP64 flops per element counted by ncu (profiles/flops.json): every lane of an element repeats the value sweep"
             roof["fp64_inst_per_element"] = flops.get("fp64_inst")
             if flops.get("fp64_inst"):
                 # issue-slot view of the same pipe: DMUL/DADD occupy a DFMA slot but count one flop
                 roof["fp64_pipe_frac"] = N * flops["fp64_inst"] * 2 / (el_ms * 1e-3) / 1e12 / fp64_peak
-        # SURVEY.md §8d's provisional algorithmic count (structure-exploiting evaluation of the same mathematics, before any kernel existed): the
-        # forward-over-reverse kernels need a fifth of it, so `achieved`/`frac` above use the EXECUTED flops; this block only places the kernel against the
-        # ceiling the survey derived from its own figure (FP64 peak / F_alg elements/s; its 60 % target was 2.2e8 el/s)
-        f_alg = {0: 1.0e5, 1: 1.5e5, 2: 1.5e5}[OX]
-        roof["survey_f_alg"] = {"flop_per_element": f_alg, "ceiling_elements_per_s": fp64_peak * 1e12 / f_alg,
-                                "kernel_elements_per_s": N / (el_ms * 1e-3), "kernel_over_ceiling": N / (el_ms * 1e-3) / (fp64_peak * 1e12 / f_alg)}
+        if falg:
+            # the frozen ALGORITHMIC count: forward-over-reverse mathematics per element with the value sweep counted once
+            fa = falg["algorithmic"]["flop"]
+            roof["alg_flop_per_element"] = fa
+            roof["achieved_alg"] = N * fa / (el_ms * 1e-3) / 1e12
+            roof["frac_alg"] = roof["achieved_alg"] / fp64_peak
+            roof["alg_flop_source"] = "tools/opcount.cpp on the product's math headers (profiles/falg.json); +-*/sqrt = 1, fma = 2, libm call = 40"
         hp, hsrc = hbm_peak()
         ab = alg_bytes_per_element(OX)
         roof["hbm"] = {"alg_bytes_per_element": ab, "achieved_gbs": N * ab / (el_ms * 1e-3) / 1e9, "peak_gbs": hp, "peak_source": hsrc,
                        "frac": N * ab / (el_ms * 1e-3) / 1e9 / hp}
-        cpu_rate, cpu_dt = cpu_port_rate(mb, OX, args.cpu_sample, 1)
+        cpu_n = args.cpu_sample * 5                       # ≈ 10 s of one host core with the static-dual build
+        cpu_rate, cpu_dt = cpu_port_rate(mb, OX, cpu_n, 1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, OX, N, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof,
                 "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                 "sample": "%d elements of the same chain, oracle literal restatement, 1 thread (%.1f s)" % (args.cpu_sample, cpu_dt)},
+                                 "sample": "%d elements of the same chain, C++ port of the reference algorithm (not Muscade/Julia: no Julia in the image), -O3 with "
+                                           "static-size duals, 1 thread as the reference's serial element loop (%.1f s)" % (cpu_n, cpu_dt)},
                 "breakdown_ms": {"element_kernels": el_ms, "segmented_reduction": ga_ms, "serial_sum": el_ms + ga_ms, "wall_timed_region_s": wall,
                                  "note": "value is from K whole steps between two events; element_kernels / segmented_reduction are the same launches "
                                          "with an event in between (second pass)"}}
-        print(json.dumps(line), flush=True)
     eng.close()
+    return line
 
 
 def directxua_model(mb, N):
@@ -346,13 +373,15 @@ def cpu_port_rate_direct(mb, nsample):
     return nsample / dt, dt
 
 
-def run_directxua(args, rank, world, local, dist):
+def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block=False):
     """BASELINE.json configs[3]: DirectXUA{2,0,0} assemblebig! of N Udof beams over `nstep` time steps; rank r owns steps [r·nstep/world,(r+1)·nstep/world)
     (strong scaling) and streams them through a sliding window of `window` steps.  One bench step = one pass over all time steps."""
     import torch
     import muscade_b200 as mb
     OX, OU = 2, 0
-    N = int(args.nele or 1e5)
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
+    N = int(1e5 if block or not args.nele else args.nele)
     nstep = args.nstep
     L, H, Wn, windows, interior = mb.sharding.directxua_windows(nstep, rank, world, args.window)
     torch.cuda.set_device(local)
@@ -413,10 +442,9 @@ def run_directxua(args, rank, world, local, dist):
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        comm.barrier()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         e_int_valid[0] = False
         one_pass(set_dev)
     barrier()
@@ -425,15 +453,11 @@ def run_directxua(args, rank, world, local, dist):
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e_int_valid[0] = False                         # every pass starts from scratch: nothing kept from the previous pass
         one_pass(set_dev)
     ev1.record(); torch.cuda.synchronize()
-    step_ms = ev0.elapsed_time(ev1) / args.steps
-    if dist is not None:
-        tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        step_ms = float(tt.item())
+    step_ms = comm.max(ev0.elapsed_time(ev1) / steps)
     barrier()
     launches = sum(e.launch_count() for e in all_eng) - launches0
     clocks = sampler.stop() if sampler else None
@@ -444,7 +468,7 @@ def run_directxua(args, rank, world, local, dist):
     # e2e: the same pass through the C ABI with HOST buffers — states from pinned host memory, Lv rows back to the host; Lvv stays in HBM for the
     # device solver (mb_get_device_ptrs), as it would in production: 29 GB per window over PCIe would only measure the bus
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not block:
         Lvh = np.empty(et.ncol)
         for arrs in hostX:
             for x in arrs: et.pin(x)
@@ -458,16 +482,15 @@ def run_directxua(args, rank, world, local, dist):
         torch.cuda.synchronize()
         e2e_ms = 1e3 * (time.perf_counter() - t1)
         nset_pass = nset[0] - n0
-        if dist is not None:
-            tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_ms = float(tt.item())
+        e2e_ms = comm.max(e2e_ms)
         e2e = {"value": N * nstep / (e2e_ms * 1e-3), "unit": "element-step assemblies/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(nset_pass * 8 * (3 * nX + nU)), "d2h_bytes_per_step": int(len(windows) * 8 * et.ncol),
                "note": "per rank: mb_direct_set_state from pinned host memory for every newly stored step, mb_direct_assemble with a host Lv; "
                        "Lvv stays in HBM (device-pointer hand-off to the solver)"}
+    line = None
     if rank == 0:
         flops = load_flops("directxua")
+        falg = load_falg("directxua_200_udof")
         nown = et.hi - et.lo
         roof = {"bound": "fp64", "kernel": "beam_direct_cot_kernel<3> + beam_direct_b0_kernel<3> + beam_direct_lin_kernel<3>", "unit": "TFLOP/s",
                 "peak": et.fp64_tflops(), "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
@@ -479,12 +502,17 @@ def run_directxua(args, rank, world, local, dist):
             roof["frac"] = roof["achieved"] / roof["peak"]
             if flops.get("fp64_inst"):
                 roof["fp64_pipe_frac"] = N * nown * flops["fp64_inst"] * 2 / (el_ms * 1e-3) / 1e12 / roof["peak"]
+            roof["frac_executed"] = roof["frac"]
             if flops.get("dram_bytes_per_element"):
                 roof["traffic"] = int(N * flops["dram_bytes_per_element"]); roof["traffic_unit"] = "bytes per time step (dram read+write of the three launches, ncu)"
+        if falg:
+            roof["alg_flop_per_element"] = falg["algorithmic"]["flop"]
+            roof["achieved_alg"] = N * nown * falg["algorithmic"]["flop"] / (el_ms * 1e-3) / 1e12
+            roof["frac_alg"] = roof["achieved_alg"] / roof["peak"]
         nsamp = max(50, args.cpu_sample // 4)
-        cpu_rate, cpu_dt = cpu_port_rate_direct(mb, nsamp)
+        cpu_rate, cpu_dt = (None, 0.) if block else cpu_port_rate_direct(mb, nsamp)
         line = {"metric": "EulerBeam3D residual+Jacobian element-step assemblies/s (DirectXUA{2,0,0} assemblebig!)", "value": N * nstep / (step_ms * 1e-3),
-                "unit": "element-step assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+                "unit": "element-step assemblies/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms, "ms_per_pass": step_ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "DirectXUA{2,0,0} load identification, %d EulerBeam3D{Udof} elements x %d time steps (BASELINE.json configs[3]), time steps "
                                        "sharded over %d GPU(s), each rank streaming its %d steps through a sliding window of %d steps (Lvv columns of the window "
@@ -497,82 +525,60 @@ def run_directxua(args, rank, world, local, dist):
                 "cpu_baseline": {"value": cpu_rate, "unit": "element-step assemblies/s", "cores": 1, "kind": "port",
                                  "sample": "one time step of %d elements, oracle literal restatement (39 partials), 1 thread (%.1f s)" % (nsamp, cpu_dt)},
                 "breakdown_ms": {"window_elements_and_step_blocks": a_ms, "window_lvv_build": b_ms, "window_element_kernels": el_ms, "windows_per_rank": len(windows)}}
-        print(json.dumps(line), flush=True)
+        if block:
+            for k in ("cpu_baseline", "e2e", "higher_is_better", "vs_baseline", "dtype", "data", "clocks"):
+                line.pop(k, None)
+            line["steps_per_gpu"] = H - L
     for e in all_eng:
         e.close()
+    del devX, devU
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_directxua_weak(args, rank, world, local, dist):
-    """DirectXUA{2,0,0} assemblebig! with the time steps sharded over the ranks (weak: steps_per_gpu each)."""
+def run_directxua_weak(args, rank, world, local, comm):
+    """DirectXUA{2,0,0} assemblebig! with the time steps sharded over the ranks (weak: steps_per_gpu each), one resident window per rank and the halo
+    blocks exchanged over NCCL inside the shim (mb_direct_halo_exchange) — the data-path collective of SURVEY.md §8e, kept as a bench of its own."""
     import muscade_b200 as mb
     OX, OU = 2, 0
     N = int(args.nele or 1e5)
     S = args.steps_per_gpu
     nstep = S * world
     lo, hi = rank * S, (rank + 1) * S
-    torch = None
-    model = mb.Model()
-    nod = mb.addnode(model, np.arange(N + 1)[:, None] * np.array([.8, .6, 0.])[None, :])
-    unod = mb.addnode(model, np.zeros((N, 0)))
-    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1., Ca2=169.6, Ca3=169.6, Cq2=235.2, Cq3=235.2)
-    mb.addelement(model, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], unod], axis=1), mat=mat, Udof=True)
+    model = directxua_model(mb, N)
     st0 = mb.initialize(model)
     nX, nU = model.getndof("X"), model.getndof("U")
     eng = mb.directxua.prepare(OX, OU, model, st0.dis, nstep, 0.1, lo, hi, device=local)
-    if world > 1:
-        import torch
-        eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    for s in range(max(0, lo - 2), min(nstep, hi + 2)):
+    comm.attach(eng)
+    for s in range(lo, hi):                                # own steps only: the halo blocks come from the neighbours
         eng.set_state(s, [mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.05 if d == 0 else 0.1) for d in range(3)], mb.synthetic.uniform_pm1(99 + s, nU))
-    plan = mb.sharding.directxua_halo_plan(nstep, lo, hi)
-
-    def view(steps):
-        p, n = eng.step_ptrs(steps[0])[0]
-        return torch.as_tensor(mb.sharding.CudaView(p, n * len(steps)), device="cuda")
-
-    bufs = {}
-    if world > 1:
-        for k in ("send_left", "send_right", "recv_left", "recv_right"):
-            if plan[k]:
-                bufs[k] = view(plan[k])
 
     def step_dev():
         eng.direct_assemble(eval_range=(lo, hi), build_big=False)
         if world > 1:
-            ops = []
-            if "send_right" in bufs: ops.append(dist.P2POp(dist.isend, bufs["send_right"], rank + 1))
-            if "send_left" in bufs: ops.append(dist.P2POp(dist.isend, bufs["send_left"], rank - 1))
-            if "recv_left" in bufs: ops.append(dist.P2POp(dist.irecv, bufs["recv_left"], rank - 1))
-            if "recv_right" in bufs: ops.append(dist.P2POp(dist.irecv, bufs["recv_right"], rank + 1))
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+            eng.halo_exchange()
         eng.direct_assemble(eval_range=(lo, lo), build_big=True)
 
     def barrier():
-        eng.sync()
-        if dist is not None:
-            torch.cuda.synchronize(); dist.barrier()
+        eng.sync(); comm.barrier()
 
     for _ in range(args.warmup):
         step_dev()
     barrier()
     launches0 = eng.launch_count()
+    t0 = time.perf_counter()
     if world == 1:
         a, b = eng.direct_time(reps=args.steps)
         step_ms = a + b
     else:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
         for _ in range(args.steps):
             step_dev()
-        ev1.record(); torch.cuda.synchronize()
-        step_ms = ev0.elapsed_time(ev1) / args.steps
-        tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        step_ms = float(tt.item())
+        eng.sync()
+        step_ms = comm.max(1e3 * (time.perf_counter() - t0) / args.steps)      # host clock around device-synchronised steps (the engine owns its stream)
         a, b = eng.direct_time(reps=1)
     barrier()
     launches = eng.launch_count() - launches0
+    line = None
     if rank == 0:
         line = {"metric": "EulerBeam3D residual+Jacobian element-step assemblies/s (DirectXUA{2,0,0} assemblebig!)", "value": world * N * S / (step_ms * 1e-3),
                 "unit": "element-step assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
@@ -580,10 +586,10 @@ def run_directxua_weak(args, rank, world, local, dist):
                 "config": {"workload": "DirectXUA{2,0,0} load identification, %d EulerBeam3D{Udof} elements x %d time steps per GPU, time-sharded; "
                                        "Lvv columns of the owned steps built on the device" % (N, S),
                            "elements": N, "steps_per_gpu": S, "nstep": nstep, "lvv_nnz_per_gpu": int(eng.nnzbig),
-                           "halo": "L2[Lambda,X] of 2 steps per neighbour over NCCL send/recv" if world > 1 else "none"},
+                           "halo": "L2[Lambda,X] of 2 steps per neighbour over NCCL send/recv inside the shim (mb_direct_halo_exchange)" if world > 1 else "none"},
                 "gpu_launches": int(launches), "breakdown_ms": {"elements_and_step_blocks": a, "lvv_build": b}}
-        print(json.dumps(line), flush=True)
     eng.close()
+    return line
 
 
 def main():
@@ -592,18 +598,32 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    import muscade_b200 as mb
     dist = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")              # start-up plumbing only (the NCCL id); the data path and the timing reductions are NCCL inside the shim
+    comm = Comm(mb, rank, world, local, dist)
     if args.workload == "directxua":
-        run_directxua(args, rank, world, local, dist)
+        line = run_directxua(args, rank, world, local, comm)
     elif args.workload == "directxua_weak":
-        run_directxua_weak(args, rank, world, local, dist)
+        line = run_directxua_weak(args, rank, world, local, comm)
     else:
-        run_sweepx(args, rank, world, local, dist)
+        line = run_sweepx(args, rank, world, local, comm)
+        if not args.no_directxua and args.nele is None and args.ox == 0:
+            # BASELINE.json configs[3] in the same run (strong scaling over the ranks): 1 warm-up + dx_passes timed passes over all 2000 time steps
+            dx = run_directxua(args, rank, world, local, comm, steps=args.dx_passes, warmup=1, block=True)
+            if line is not None:
+                line["directxua"] = dx
+    if rank == 0 and line is not None:
+        line["comm"] = {"backend": "NCCL inside libmuscade_b200.so (mb_comm_init, dlopen libnccl.so.2)" if world > 1 else "none", "ranks": world,
+                        "nccl_version": comm.eng.comm_info()[2] if comm.eng is not None else None,
+                        "torch_distributed_on_timed_path": False}
+        print(json.dumps(line), flush=True)
+    comm.barrier()
+    comm.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

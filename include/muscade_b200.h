@@ -215,6 +215,7 @@ int32_t mb_host_unregister(mb_handle* h, void* p);
 /* Times one launch set of the last assemble configuration with CUDA events on the handle's stream:
  *   ms[0] = element kernels, ms[1] = segmented reduction into nzval/Lλ. */
 int32_t mb_sweepx_time_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark, int32_t reps, float* ms);
+/* On a handle with a communicator and interface lists (element-range shard) every step is mb_sweepx_assemble_dev + mb_iface_exchange. */
 /* Times `reps` whole device-resident steps (mb_sweepx_assemble_dev exactly as a solver calls it: for large models the segmented reduction of
  * element chunk j overlaps the element kernels of chunk j+1 on a second, high-priority stream): *ms = average per step. */
 int32_t mb_sweepx_time_step_dev(mb_handle* h, int32_t OX, int32_t mission, double t, const double* newmark, int32_t reps, float* ms);

@@ -742,10 +742,11 @@ struct PacksLocal { MB_HD void operator()(int, double th, RodPacks& pk) const { 
 //   out.tt(Gc)          column c of G (closed-form translation × translation block), after the forward sweep
 //   out.trans(Ru1,Ru2)  residual rows of u₁, u₂ (value = R, d0 = the lane's tangent column), early in the reverse sweep
 //   out.rot(Rva,Rvp)    rows of the active / passive node's rotation, at the end
-template <class EX, class OUT>
-MB_HD void beam_static_ap(const BeamGeo& g, const BeamMat& m, const SD<false, false>* Xu0, const SD<true, false>* Xv_a, const SD<false, false>* Xv_p,
+// S = SD<1,0> (the kernel's lanes) or SD<0,0> (values only: what tools/opcount counts as the primal share of a lane)
+template <class S, class EX, class OUT>
+MB_HD void beam_static_ap(const BeamGeo& g, const BeamMat& m, const SD<false, false>* Xu0, const S* Xv_a, const SD<false, false>* Xv_p,
                           double sigma, bool udof, const SD<false, false>* U0, int c, const EX& ex, OUT& out) {
-    using S = SD<true, false>; using V = SD<false, false>;
+    using V = SD<false, false>;
     const double L = g.L;
     // ---- forward
     Vec3<S> va{Xv_a[0], Xv_a[1], Xv_a[2]}; Vec3<V> vp{Xv_p[0], Xv_p[1], Xv_p[2]};

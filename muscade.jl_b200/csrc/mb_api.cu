@@ -503,7 +503,12 @@ int32_t mb_sweepx_time_step_dev(mb_handle* h, int32_t OX, int32_t mission, doubl
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, h->stream));
-    for (int r = 0; r < reps; ++r) { int32_t rc = mb_sweepx_assemble_dev(h, OX, mission, t, newmark); if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; } }
+    const bool exch = h->comm && (h->if_nsend_nz + h->if_nsend_v + h->if_nrecv_nz + h->if_nrecv_v) > 0;      // element-range shard: a step ends with the interface exchange
+    for (int r = 0; r < reps; ++r) {
+        int32_t rc = mb_sweepx_assemble_dev(h, OX, mission, t, newmark);
+        if (!rc && exch) rc = mb_iface_exchange(h);
+        if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    }
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     float a; CK(cudaEventElapsedTime(&a, e0, e1));

@@ -113,12 +113,13 @@ class Engine:
         check(self.h, self.L.mb_sweepx_get_asm_range(self.h, ityp, int(e0), int(e1), ptr(asm1), ptr(asm2)))
         return asm1, asm2
 
-    def sweepx_assemble(self, OX, mission, X, newmark, U0=None, t=0., Llambda=None, nzval=None, dbg=None):
-        """assemble!{mission}: host state in, host Lλ / nzval out (pass preallocated arrays to avoid allocation)."""
+    def sweepx_assemble(self, OX, mission, X, newmark, U0=None, t=0., Llambda=None, nzval=None, dbg=None, nzval_on_device=False):
+        """assemble!{mission}: host state in, host Lλ / nzval out (pass preallocated arrays to avoid allocation).
+        nzval_on_device: the CSC values stay in HBM behind mb_get_device_ptrs (device solver hand-off); only Lλ comes back."""
         X = [_f64(x) for x in X]
         if Llambda is None:
             Llambda = np.empty(self.ndofX)
-        if nzval is None:
+        if nzval is None and not nzval_on_device:
             nzval = np.empty(self.nnz)
         where = ErrInfo()
         rc = self.L.mb_sweepx_assemble(self.h, OX, {"step": 0, "iter": 1}[mission], ptr(X[0]), ptr(X[1]) if OX >= 1 else None,

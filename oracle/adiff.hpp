@@ -24,8 +24,16 @@
 namespace orc {
 
 // ---------------------------------------------------------------- DV : ∂ℝ{1,Np,Float64}, Np runtime
+// ORC_NP_FIXED (build flag, oracle/Makefile → liboracle_np12.so): the number of partials is a compile-time constant, as it is in the reference
+// (∂ℝ{1,12,Float64} is an isbits struct of 13 doubles whose loops StaticArrays unrolls) — the build the CPU baseline is timed with.  The default build keeps
+// it a run-time value so that one library serves every seeding (12, 13, 39 … partials); both give bit-identical numbers (tests/test_oracle_goldens.py).
+#ifdef ORC_NP_FIXED
+constexpr int DV_MAX = ORC_NP_FIXED;
+struct DVctx { static constexpr int np = ORC_NP_FIXED; static bool set(int n) { return n <= ORC_NP_FIXED; } };     // fewer seeds: the spare partials stay zero
+#else
 constexpr int DV_MAX = 48;
-struct DVctx { static inline thread_local int np = 0; };
+struct DVctx { static inline thread_local int np = 0; static bool set(int n) { np = n; return n <= DV_MAX; } };
+#endif
 struct DV {
     double x;
     double dx[DV_MAX];

@@ -173,10 +173,30 @@ def sweepx_assemble_beams(elems, idx, asm1, asm2, OX, mission, X, scaleX, newmar
         raise FloatingPointError("residual(EulerBeam3D,...) returned NaN in R, FB or derivatives (iele=%d)" % rc)
 
 
-def sweepx_assemble_beams_mt(elems, idx, asm1, asm2, OX, X, scaleX, newmark, Llambda, nzval, nthreads):
-    """:iter assembly with the element loop spread over host threads (bench.py --impl reference)"""
+_LIB12 = None
+
+
+def lib_np12():
+    """liboracle_np12.so: the same sources built with static-size duals (12 partials, the SweepX :iter seeding) and -O3 — the CPU baseline build."""
+    global _LIB12
+    if _LIB12 is None:
+        so = os.path.join(_HERE, "liboracle_np12.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle_np12.so"])
+        L = C.CDLL(so)
+        L.orc_sweepx_assemble_beams.argtypes = lib().orc_sweepx_assemble_beams.argtypes
+        L.orc_sweepx_assemble_beams.restype = C.c_int
+        L.orc_sweepx_assemble_beams_mt.argtypes = lib().orc_sweepx_assemble_beams_mt.argtypes
+        L.orc_sweepx_assemble_beams_mt.restype = C.c_int
+        L.orc_max_threads.restype = C.c_int
+        _LIB12 = L
+    return _LIB12
+
+
+def sweepx_assemble_beams_mt(elems, idx, asm1, asm2, OX, X, scaleX, newmark, Llambda, nzval, nthreads, static_duals=False):
+    """:iter assembly with the element loop spread over host threads (bench.py --impl reference); static_duals: the -O3 build with 12 compile-time partials"""
     X = [np.ascontiguousarray(x, float) for x in X]
-    rc = lib().orc_sweepx_assemble_beams_mt(elems.shape[0], np.ascontiguousarray(elems), np.ascontiguousarray(idx, np.int64),
+    rc = (lib_np12() if static_duals else lib()).orc_sweepx_assemble_beams_mt(elems.shape[0], np.ascontiguousarray(elems), np.ascontiguousarray(idx, np.int64),
                                             np.ascontiguousarray(asm1, np.int64), np.ascontiguousarray(asm2, np.int64), OX, X[0],
                                             _ptr(X[1]) if OX >= 1 else None, _ptr(X[2]) if OX >= 2 else None,
                                             np.ascontiguousarray(scaleX, float), np.ascontiguousarray(newmark, float), Llambda, nzval, nthreads)

@@ -94,7 +94,7 @@ int orc_beam_ctor(const double* c1, const double* c2, const double* orient2, con
 int orc_beam_residual(const double* elem69, int nd, int np, const double* Xval, const double* Xseed, int udof,
                       const double* Uval, const double* Useed, double* R, double* dR) {
     if (np > DV_MAX || nd < 1 || nd > 3) return -1;
-    DVctx::np = np;
+    if (!DVctx::set(np)) return -1;
     EulerBeam3D o; unpack_beam(elem69, o);
     DV X[3][12], U[3], Rv[12];
     for (int d = 0; d < nd; ++d) for (int i = 0; i < 12; ++i) {
@@ -118,7 +118,7 @@ int orc_beam_residual(const double* elem69, int nd, int np, const double* Xval, 
 // getresult(state,req,els) for EulerBeam3D (src/Output.jl:131-181 → the @espy requestables): 77 values per element, see beam_residual
 int orc_beam_results(const double* elem69, int nd, const double* Xval, int udof, const double* Uval, double* espy77) {
     if (nd < 1 || nd > 3) return -1;
-    DVctx::np = 0;
+    if (!DVctx::set(0)) return -1;
     EulerBeam3D o; unpack_beam(elem69, o);
     DV X[3][12], U[3], Rv[12];
     for (int d = 0; d < nd; ++d) for (int i = 0; i < 12; ++i) X[d][i].x = Xval[d * 12 + i];
@@ -164,7 +164,7 @@ int orc_sweepx_assemble_beams(int64_t nele, const double* elems69, const int64_t
     const int Nx = 12;
     const bool step = (mission == 0) && OX > 0;
     const int np = step ? Nx + 1 : Nx;
-    DVctx::np = np;
+    if (!DVctx::set(np)) return -1;
     const double a1 = newmark[0], a2 = newmark[1], a3 = newmark[2], b1 = newmark[3], b2 = newmark[4], b3 = newmark[5];
     const int nd = OX + 1;
     for (int64_t e = 0; e < nele; ++e) {
@@ -220,7 +220,7 @@ int orc_beams_iter_elementwise(int64_t nele, const double* elems69, const int64_
 #pragma omp parallel for schedule(static) reduction(+ : bad)
 #endif
     for (int64_t e = 0; e < nele; ++e) {
-        DVctx::np = 12;
+        DVctx::set(12);
         EulerBeam3D o; unpack_beam(elems69 + 69 * e, o);
         const int64_t* ix = idx + 12 * e;
         DV X[3][12], U[3], R[12];
@@ -270,7 +270,7 @@ int orc_direct_addin_beams(int64_t nele, const double* elems69, const int64_t* i
     const int nd = OX + 1, ndu = OU + 1;
     const int np = 12 * nd + (udof ? 3 * ndu : 0);
     if (np > DV_MAX) return -1;
-    DVctx::np = np;
+    if (!DVctx::set(np)) return -1;
     const double* Xs[3] = {X0, X1, X2}; const double* Us[3] = {U0, U1, U2};
     for (int64_t e = 0; e < nele; ++e) {
         EulerBeam3D o; unpack_beam(elems69 + 69 * e, o);
