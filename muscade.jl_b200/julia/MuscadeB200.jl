@@ -10,7 +10,7 @@
 # pointed at `AssemblySweepXB200{OX}`.
 module MuscadeB200
 
-using Muscade, SparseArrays
+using Muscade, SparseArrays, LinearAlgebra, Printf
 using Muscade: Assembly, assemble!, zero!, Newmarkβcoefficients, allXdofs, getndof, getneletyp, muscadeerror, 𝕣, 𝕫
 
 const LIB = get(ENV, "MUSCADE_B200_LIB", "libmuscade_b200")
@@ -179,5 +179,244 @@ function direct_set_host_xx!(h::Ptr{Cvoid}, step::Integer, i::Vector{Int64}, j::
     GC.@preserve i j v check(h, ccall((:mb_direct_set_host_xx, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                                       h, step, length(i), i, j, v))
 end
+
+
+# =====================================================================================================================================================
+# DirectXUA on the device: AssemblyDirectB200{OX,OU,0} replaces what `solve(DirectXUA{OX,OU,0};…)` (src/DirectXUA.jl:438-513) does between its
+# `prepare` (:452) and its linear solve (:486-492): prepare(AssemblyDirect) + preparebig (:22-56, :245-315), assemblebig!{:matrices} (:316-356),
+# sparser! (src/SparseTools.jl:172-199) and decrementbig! (:357-383).  One handle owns the time steps [lo,hi) (0-based) of ONE experiment; with several
+# GPUs each process owns a contiguous range and the halo blocks travel over NCCL inside the shim (mb_direct_halo_exchange).
+# Mirrors muscade.jl_b200/directxua.py (`prepare`, `DirectEngine`, `solve`) call for call — that Python host is what the GPU tests execute.
+# =====================================================================================================================================================
+mutable struct AssemblyDirectB200{OX,OU,IA} <: Assembly
+    h        :: Ptr{Cvoid}
+    nstep    :: Int
+    lo       :: Int                               # owned steps lo:hi-1 (0-based, as the C ABI counts them)
+    hi       :: Int
+    ncol     :: Int                               # owned columns of Lvv = rows of Lv: (hi-lo)·(2nX+nU)
+    nnz      :: Int
+    Lv       :: Vector{𝕣}
+    hosttyp  :: Vector{Int}                       # X-class types evaluated by Muscade's own addin! on the host (Hold, DofLoad, DofConstraint{:X})
+    costtyp  :: Vector{Int}                       # SingleDofCost types (user closures) → mb_direct_set_host_cost
+end
+
+# finitediff(order,n,s) (src/FiniteDifferences.jl:8-31) is Muscade's own; only the block pattern of the OWNED columns is needed here:
+# makepattern(0,[nstep],out) (src/DirectXUA.jl:245-307) restricted to the block columns 3lo:3hi-1, as CSC over blocks, 0-based block numbers 3·step+class
+function owned_block_pattern(OX, OU, nstep, lo, hi)
+    nder = (1, OX + 1, OU + 1)
+    cols = Dict{Int,Set{Int}}()
+    for istep = max(1, lo - 1):min(nstep, hi + 2), α = 1:3, β = 1:3
+        α == 1 && β == 1 && continue                                                   # Lλλ is always zero (src/DirectXUA.jl:41)
+        for αder = 1:nder[α], βder = 1:nder[β]
+            for (Δαs, _) ∈ Muscade.finitediff(αder - 1, nstep, istep), (Δβs, _) ∈ Muscade.finitediff(βder - 1, nstep, istep)
+                sc = istep + Δβs - 1
+                lo ≤ sc < hi && push!(get!(cols, 3sc + β - 1, Set{Int}()), 3 * (istep + Δαs - 1) + α - 1)
+            end
+        end
+    end
+    bcolptr, browval = Int32[0], Int32[]
+    for bc = 3lo:3hi-1
+        append!(browval, sort!(collect(get(cols, bc, Set{Int}()))))
+        push!(bcolptr, length(browval))
+    end
+    return bcolptr, browval
+end
+
+"""
+    out,asm,dofgr = prepare(AssemblyDirectB200{OX,OU,0},model,dis;nstep,Δt,lo=0,hi=nstep,device=0,t₀=0.)
+
+Replaces `prepare(AssemblyDirect{OX,OU,IA},…)` + `preparebig` (src/DirectXUA.jl:452-455).  Class-pair patterns, element→nz maps and the CSC
+structure of the owned columns of `Lvv` are built on the device, bit-identical to `asmmat!` / `SparseTools.prepare` (fetch them with
+`mb_direct_class_pattern`, `mb_direct_get_asm`, `mb_direct_big_pattern` when the host needs them).
+"""
+function Muscade.prepare(::Type{AssemblyDirectB200{OX,OU,0}}, model, dis; nstep, Δt, lo=0, hi=nstep, device=0, t₀=0.) where {OX,OU}
+    href = Ref{Ptr{Cvoid}}()
+    check(C_NULL, ccall((:mb_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, href))
+    h = href[]
+    hosttyp, costtyp = Int[], Int[]
+    for ieletyp = 1:getneletyp(model)
+        eleobj, d, E = model.eleobj[ieletyp], dis.dis[ieletyp], eltype(model.eleobj[ieletyp])
+        nx   = length(d.scale.X)
+        idxX = [d.index[iele].X[i] for i = 1:nx, iele = 1:length(eleobj)]
+        udof = length(d.scale.U) > 0
+        idxU = udof ? [d.index[iele].U[i] for i = 1:length(d.scale.U), iele = 1:length(eleobj)] : Matrix{Int64}(undef, 0, 0)
+        ityp = Ref{Int32}()
+        if E <: Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection} || E <: Muscade.Toolbox.Bar3D{Muscade.Toolbox.AxisymmetricBarCrossSection}
+            f = E <: Muscade.Toolbox.EulerBeam3D ? :mb_add_eulerbeam3d : :mb_add_bar3d
+            GC.@preserve eleobj idxX idxU check(h, ccall((f, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+                h, length(eleobj), pointer(reinterpret(Float64, eleobj)), udof, idxX, udof ? pointer(idxU) : C_NULL,
+                collect(d.scale.X), udof ? collect(d.scale.U) : C_NULL, ityp))
+        elseif E <: Muscade.Toolbox.SoilContact
+            GC.@preserve eleobj idxX check(h, ccall((:mb_add_soilcontact, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{Int32}),
+                h, length(eleobj), pointer(reinterpret(Float64, eleobj)), idxX, collect(d.scale.X), ityp))
+        elseif E <: Muscade.SingleDofCost
+            push!(costtyp, ieletyp)                               # no device group: gradient / second derivative per dof, mb_direct_set_host_cost
+        elseif !udof && length(d.scale.A) == 0
+            check(h, ccall((:mb_add_host_elements, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{Int64}, Ref{Int32}), h, length(eleobj), nx, idxX, ityp))
+            push!(hosttyp, ieletyp)
+        else
+            muscadeerror((;ieletyp), "AssemblyDirectB200: element types with U or A dofs other than EulerBeam3D / Bar3D stay on the reference path")
+        end
+    end
+    nX, nU = getndof(model, :X), getndof(model, :U)
+    bcolptr, browval = owned_block_pattern(OX, OU, nstep, lo, hi)
+    ncol, nnz = Ref{Int64}(), Ref{Int64}()
+    check(h, ccall((:mb_direct_prepare, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Int64, Int64, Int64, Int64, Int64, 𝕣, Ptr{Int32}, Ptr{Int32}, Ref{Int64}, Ref{Int64}),
+        h, OX, OU, nX, nU, nstep, lo, hi, Δt, bcolptr, browval, ncol, nnz))
+    check(h, ccall((:mb_direct_set_time0, LIB), Int32, (Ptr{Cvoid}, 𝕣), h, t₀))
+    check(h, ccall((:mb_direct_set_lambda_scale, LIB), Int32, (Ptr{Cvoid}, 𝕣), h, model.scaleΛ))
+    check(h, ccall((:mb_direct_set_dof_scale, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), h, dis.scaleΛ, dis.scaleX, dis.scaleU))
+    out = AssemblyDirectB200{OX,OU,0}(h, nstep, lo, hi, ncol[], nnz[], zeros(𝕣, ncol[]), hosttyp, costtyp)
+    finalizer(o -> ccall((:mb_destroy, LIB), Int32, (Ptr{Cvoid},), o.h), out)
+    dofgr = (Muscade.allΛdofs(model, dis), allXdofs(model, dis), Muscade.allUdofs(model, dis), Muscade.allAdofs(model, dis))
+    return out, nothing, dofgr
+end
+
+"state[step] (one experiment) → device; the handle stores the steps lo-2:hi+1 its finite-difference stencils reach"
+function upload_states!(out::AssemblyDirectB200{OX,OU}, state::Vector) where {OX,OU}
+    for s = max(0, out.lo - 2):min(out.nstep, out.hi + 2)-1
+        st = state[s+1]; X = st.X
+        GC.@preserve X st begin
+            check(out.h, ccall((:mb_direct_set_state, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
+                out.h, s, X[1], OX ≥ 1 ? pointer(X[2]) : C_NULL, OX ≥ 2 ? pointer(X[3]) : C_NULL, isempty(st.U[1]) ? C_NULL : pointer(st.U[1])))
+            check(out.h, ccall((:mb_direct_set_lambda, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{𝕣}), out.h, s, st.Λ[1]))
+        end
+    end
+end
+
+"""
+    assemblebig!{:matrices}(out::AssemblyDirectB200,…)  — replaces src/DirectXUA.jl:316-356 for the owned steps
+
+Evaluates every owned step (and, single GPU, the halo steps) on the device, merges the host-evaluated types, forms the owned columns of `Lvv`
+(left in HBM: `mb_direct_sparser` / `mb_direct_get_sparse` hand the compacted CSC to the solver) and the owned rows of `Lv` (returned in `out.Lv`).
+`comm=true`: time shards over NCCL — own steps only, then `mb_direct_halo_exchange`.
+"""
+function assemblebig!(out::AssemblyDirectB200{OX,OU}, model, dis, state::Vector, dbg; comm=false) where {OX,OU}
+    host_direct_contributions!(out, model, dis, state, dbg)
+    where = Ref(ErrInfo(0, 0, 0, 0))
+    if comm
+        rc = ccall((:mb_direct_assemble, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{𝕣}, Ptr{𝕣}, Ref{ErrInfo}), out.h, out.lo, out.hi, 0, C_NULL, C_NULL, where)
+        rc == 0 && (rc = ccall((:mb_direct_halo_exchange, LIB), Int32, (Ptr{Cvoid},), out.h))
+        rc == 0 && (rc = ccall((:mb_direct_assemble, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{𝕣}, Ptr{𝕣}, Ref{ErrInfo}), out.h, out.lo, out.lo, 1, C_NULL, out.Lv, where))
+    else
+        rc = ccall((:mb_direct_assemble, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{𝕣}, Ptr{𝕣}, Ref{ErrInfo}), out.h, -1, -1, 1, C_NULL, out.Lv, where)
+    end
+    rc == 3 && muscadeerror((dbg..., ieletyp=where[].ieletyp, iele=where[].iele, istep=where[].step), "residual(...) returned NaN in R, FB or derivatives")
+    check(out.h, rc, dbg)
+    return
+end
+
+"cLvv = sparser!(Lvv,rtol) on the device (src/SparseTools.jl:172-199, called at src/DirectXUA.jl:486): the owned columns, global rows, compacted"
+function sparser(out::AssemblyDirectB200, rtol=1e-9)
+    n = Ref{Int64}()
+    check(out.h, ccall((:mb_direct_sparser, LIB), Int32, (Ptr{Cvoid}, 𝕣, Ref{Int64}), out.h, rtol, n))
+    colptr, rowval, nzval = Vector{Int64}(undef, out.ncol + 1), Vector{Int64}(undef, n[]), Vector{𝕣}(undef, n[])
+    check(out.h, ccall((:mb_direct_get_sparse, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{𝕣}), out.h, colptr, rowval, nzval))
+    return colptr, rowval, nzval          # rows are GLOBAL: with one handle, SparseMatrixCSC(ncol,ncol,colptr,rowval,nzval) is the reference's cLvv
+end
+
+"decrementbig!(state,Δ²,Lvdis,dofgr,Δv,nder,Δt,nstep) (src/DirectXUA.jl:357-383) on the device-resident states; Δv rows of steps s0:s1-1 in Lv's layout"
+function decrementbig!(out::AssemblyDirectB200, Δv::Vector{𝕣}, s0=0, s1=out.nstep)
+    Δ² = zeros(𝕣, 3)
+    check(out.h, ccall((:mb_direct_decrement, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{𝕣}, Ptr{𝕣}), out.h, s0, s1, Δv, Δ²))
+    return Δ²                             # maxₜ ΣΔΛ², ΣΔX², ΣΔU² over the owned steps: the convergence test of src/DirectXUA.jl:493-500
+end
+
+"states back to the host after convergence (src/DirectXUA.jl:505-511)"
+function download_states!(state::Vector, out::AssemblyDirectB200{OX,OU}) where {OX,OU}
+    for s = out.lo:out.hi-1
+        st = state[s+1]; X = st.X
+        GC.@preserve X st check(out.h, ccall((:mb_direct_get_state, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
+            out.h, s, X[1], OX ≥ 1 ? pointer(X[2]) : C_NULL, OX ≥ 2 ? pointer(X[3]) : C_NULL, isempty(st.U[1]) ? C_NULL : pointer(st.U[1]), st.Λ[1]))
+    end
+end
+
+# Host-evaluated types of the all-steps problem: Muscade's own second-order addin! (src/DirectXUA.jl:121-171) on a one-element AssemblyDirect, one
+# stored step at a time, handed over as dense per-element arrays (mb_direct_set_host_elements, mb_direct_set_host_xx) or per-dof vectors (SingleDofCost,
+# mb_direct_set_host_cost).  Mirrors directxua.host_elements / directxua.host_costs of the Python host.
+function host_direct_contributions!(out::AssemblyDirectB200{OX,OU}, model, dis, state::Vector, dbg) where {OX,OU}
+    (isempty(out.hosttyp) && isempty(out.costtyp)) && return
+    nX, nU, nd = getndof(model, :X), getndof(model, :U), OX + 1
+    for s = max(0, out.lo - 2):min(out.nstep, out.hi + 2)-1
+        st = state[s+1]
+        if !isempty(out.costtyp)
+            gX, hX, gU, hU = zeros(𝕣, nX), zeros(𝕣, nX), zeros(𝕣, nU), zeros(𝕣, nU)
+            for ieletyp ∈ out.costtyp, (iele, e) ∈ enumerate(model.eleobj[ieletyp])
+                d = dis.dis[ieletyp]; index = d.index[iele]
+                isX = length(index.X) == 1
+                x   = Muscade.variate{2,1}(Muscade.variate{1,1}(isX ? st.X[1][index.X[1]] : st.U[1][index.U[1]]))      # second-order dual of the one dof
+                c   = e.cost(x, st.time, e.costargs...)
+                sc  = isX ? d.scale.X[1] : d.scale.U[1]
+                g, hh = Muscade.∂{2,1}(c)[1], Muscade.∂{1,1}(Muscade.∂{2,1}(c)[1])[1]
+                if isX gX[index.X[1]] += Muscade.value{1}(g) * sc; hX[index.X[1]] += hh * sc^2
+                else   gU[index.U[1]] += Muscade.value{1}(g) * sc; hU[index.U[1]] += hh * sc^2 end
+            end
+            check(out.h, ccall((:mb_direct_set_host_cost, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), out.h, s, gX, hX, gU, hU))
+        end
+        for ieletyp ∈ out.hosttyp
+            eleobj, d = model.eleobj[ieletyp], dis.dis[ieletyp]
+            nele, nx  = length(eleobj), length(d.scale.X)
+            R, dR, GX = zeros(𝕣, nx, nele), zeros(𝕣, nx, nd * nx, nele), zeros(𝕣, nd, nx, nele)
+            tmp, tasm, _ = Muscade.prepare(Muscade.AssemblyDirect{OX,OU,0}, one_element_model(model, ieletyp), one_element_dis(dis, ieletyp))   # element-local out
+            ii, jj, vv = Int64[], Int64[], 𝕣[]
+            for iele = 1:nele
+                zero!(tmp)
+                index = d.index[iele]
+                Muscade.addin!{:matrices}(tmp, tasm, 1, d.scale, eleobj[iele], (st.Λ[1][index.X],), NTuple{nd}(x[index.X] for x ∈ st.X), (st.U[1][index.U],),
+                                          st.A[index.A], st.time, 0., st.SP, dbg)
+                R[:, iele] .= tmp.L1[1][1]
+                for der = 1:nd
+                    GX[der, :, iele] .= tmp.L1[2][der]
+                    dR[:, (der-1)*nx+1:der*nx, iele] .= Matrix(tmp.L2[1, 2][1, der])
+                end
+                H = Matrix(tmp.L2[2, 2][1, 1])
+                for a = 1:nx, b = 1:nx
+                    H[a, b] != 0 && (push!(ii, index.X[a]); push!(jj, index.X[b]); push!(vv, H[a, b]))
+                end
+            end
+            check(out.h, ccall((:mb_direct_set_host_elements, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), out.h, s, ieletyp, R, dR, GX))
+            isempty(ii) || direct_set_host_xx!(out.h, s, ii, jj, vv)
+        end
+    end
+end
+# one-element views of model / dis for the element-local AssemblyDirect above (a maintainer has these as two-line helpers over model.eleobj / dis.dis)
+one_element_model(model, ieletyp) = Muscade.submodel(model, ieletyp, 1)
+one_element_dis(dis, ieletyp)     = Muscade.subdis(dis, ieletyp, 1)
+
+"""
+    solve_direct_b200(OX,OU;initialstate,time,maxiter=50,maxΔλ=1e-5,maxΔx=1e-5,maxΔu=1e-5,device=0)
+
+The body of `solve(DirectXUA{OX,OU,0};…)` (src/DirectXUA.jl:438-513) with the assembly, `sparser!` and `decrementbig!` on the device.
+"""
+function solve_direct_b200(OX, OU; initialstate, time, maxiter=50, maxΔλ=1e-5, maxΔx=1e-5, maxΔu=1e-5, device=0, dbg=(;))
+    model, dis = initialstate.model, initialstate.dis
+    nstep, Δt  = length(time), step(time)
+    out, _, _  = Muscade.prepare(AssemblyDirectB200{OX,OU,0}, model, dis; nstep, Δt, device, t₀=first(time))
+    state      = [Muscade.State{1,OX+1,OU+1}(copy(initialstate, time=t)) for t ∈ time]
+    upload_states!(out, state)
+    for iter = 1:maxiter
+        assemblebig!(out, model, dis, state, (dbg..., iter=iter))
+        colptr, rowval, nzval = sparser(out, 1e-20)
+        Δv = try lu(SparseMatrixCSC(out.ncol, out.ncol, colptr, rowval, nzval)) \ out.Lv
+             catch; muscadeerror(@sprintf("Lvv matrix factorization failed at iter=%i", iter)) end
+        Δ² = decrementbig!(out, Δv)
+        all(Δ² .≤ (maxΔλ^2, maxΔx^2, maxΔu^2)) && break
+        iter == maxiter && muscadeerror(@sprintf("no convergence after %3d iterations.", iter))
+        isempty(out.hosttyp) && isempty(out.costtyp) || download_states!(state, out)       # the host-evaluated types read the updated states
+    end
+    download_states!(state, out)
+    return state
+end
+
+# ---- NCCL inside the shim: one handle per GPU / process ---------------------------------------------------------------------------------------------
+comm_unique_id() = (id = zeros(UInt8, 128); ccall((:mb_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id) == 0 || error("ncclGetUniqueId failed"); id)
+comm_init!(h::Ptr{Cvoid}, id::Vector{UInt8}, rank, world) = check(h, ccall((:mb_comm_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), h, id, rank, world))
+comm_share!(h::Ptr{Cvoid}, owner::Ptr{Cvoid})             = check(h, ccall((:mb_comm_share, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h, owner))
+comm_allreduce!(h::Ptr{Cvoid}, v::Vector{𝕣}, op=0)        = check(h, ccall((:mb_comm_allreduce, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Int64, Int32), h, v, length(v), op))
+"element-range shard of a large SweepX mesh: after `assemble!` with device-resident outputs, the interface rows go to / come from the neighbours"
+iface_exchange!(out::AssemblySweepXB200) = check(out.h, ccall((:mb_iface_exchange, LIB), Int32, (Ptr{Cvoid},), out.h))
 
 end # module
