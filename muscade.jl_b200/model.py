@@ -51,9 +51,14 @@ class EleTyp:
         runs = getattr(self, "runs", None)
         return runs if runs else [(0, self.nele, self.extra if self.extra is not None else self.eleobj)]
 
-    def residual(self, X, t):
-        """ElType.residual over all elements: X = [X₀,X′,…] of shape (nele,nx) each → (R, K0, K1, K2), K1/K2 None when no run has them"""
-        parts = [self.ElType.residual(ex, [x[a:b] for x in X], t) for a, b, ex in self._runs()]
+    def residual(self, X, t, U=None, A=None):
+        """ElType.residual over all elements: X = [X₀,X′,…] of shape (nele,nx) each → (R, K0, K1, K2), K1/K2 None when no run has them.
+        Element types that read U- or A-dofs (as plain values: an X-analysis does not differentiate with respect to them, src/SweepX.jl:45-96)
+        declare `takes_UA = True` and receive U (nele,nu), A (nele,na) as keyword arguments."""
+        if getattr(self.ElType, "takes_UA", False):
+            parts = [self.ElType.residual(ex, [x[a:b] for x in X], t, U=None if U is None else U[a:b], A=None if A is None else A[a:b]) for a, b, ex in self._runs()]
+        else:
+            parts = [self.ElType.residual(ex, [x[a:b] for x in X], t) for a, b, ex in self._runs()]
         if len(parts) == 1:
             return parts[0]
         out = []

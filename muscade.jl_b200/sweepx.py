@@ -93,8 +93,8 @@ def prepare(OX, model, dis, device=0):
         elif et.ElType.kind == "hostcost":
             eng.add_host_elements(ed.X)      # costs have no Λ-dependence: zero residual in an X-analysis, but their dofs are in the pattern
         else:
-            if ed.U.shape[1] or ed.A.shape[1]:
-                muscadeerror("host-evaluated element types with U- or A-dofs are not supported in SweepX yet: %s" % (et.key,))
+            if (ed.U.shape[1] or ed.A.shape[1]) and not getattr(et.ElType, "takes_UA", False):
+                muscadeerror("host-evaluated element types with U- or A-dofs must declare takes_UA (their residual then receives U and A as values): %s" % (et.key,))
             eng.add_host_elements(ed.X)
             host_types.append((k + 1, et, ed))
     nnz = eng.sweepx_prepare(ndof)
@@ -113,7 +113,9 @@ def _host_elements(out, state, mission, t):
     step = mission == "step" and OX > 0
     for ityp, et, ed in out.host_types:
         X = [state.X[d][ed.X - 1] for d in range(OX + 1)]
-        R, K0, K1, K2 = et.residual(X, t)
+        Ue = state.U[0][ed.U - 1] if ed.U.shape[1] and len(state.U) else None
+        Ae = state.A[ed.A - 1] if ed.A.shape[1] else None
+        R, K0, K1, K2 = et.residual(X, t, U=Ue, A=Ae)
         s = ed.scaleX
         K = K0.copy()
         if K1 is not None and OX >= 1: K = K + a1 * K1

@@ -315,3 +315,4 @@ int orc_max_threads() {
 }  // extern "C"
 
 #include "bar_api.inc"
+#include "kat_api.inc"

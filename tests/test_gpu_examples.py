@@ -65,9 +65,11 @@ def test_static_beam_analysis(mb):
     assert len(states) == 4
     for k in (1, 2, 3):
         tip = [coord[-1, i] + mb.getdof(states[k], f, nodID=[nod[-1]])[0] for i, f in enumerate(("t1", "t2", "t3"))]
-        # Muscade's 8-element answer sits between / next to the two literature solutions, which differ by ≤0.07 themselves
-        assert np.allclose(tip, LONGVA[k], atol=0.35), (k, tip)
-        assert np.allclose(tip, CRISFIELD[k], atol=0.35), (k, tip)
+        # Muscade's 8-element answer sits next to the two literature solutions (which differ by ≤ 0.07 themselves): measured deviations are
+        # ≤ 0.056 from Longva and ≤ 0.093 from Crisfield, the bounds below leave 10 % — a wrong sign convention of orient2 or a missing load
+        # component moves the tip by more than a unit
+        assert np.allclose(tip, LONGVA[k], atol=0.062), (k, tip)
+        assert np.allclose(tip, CRISFIELD[k], atol=0.102), (k, tip)
     ref = oracle_newton(model, state0.dis, times)
     for k in range(4):
         # converged states: same Newton loop, same (SuperLU) factorisation, assemblies equal to 1e-12 ⇒ states equal to solver round-off

@@ -147,3 +147,36 @@ def test_host_element_arguments_are_kept_per_element():
     assert l1 == l2
     R, K0, K1, K2 = model.ele[l1 - 1].residual([np.zeros((3, 1))], 2.)
     assert R[:, 0].tolist() == [-2., 6., 6.] and K0.shape == (3, 1, 1) and K1 is None
+
+
+def test_vectorised_constructors_equal_the_oracle_and_the_reference_golden():
+    """toolbox.eulerbeam3d_structs / bar3d_structs (the host side of mb_add_eulerbeam3d / mb_add_bar3d: 69 / 38 doubles per element, the reference's struct
+    layout) against the oracle's literal constructors — bit for bit over random elements — and against test/TestBeamElement.jl:15-31"""
+    import muscade_b200 as mb
+    from oracle import elements as OE
+    rng = np.random.default_rng(12)
+    n = 50
+    c1 = rng.uniform(-5, 5, (n, 3)); c2 = c1 + rng.uniform(0.3, 3., (n, 3)) * rng.choice([-1., 1.], (n, 3))
+    o2 = rng.uniform(-1, 1, (n, 3))
+    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=2.5, GJ=4., mu=1., iota1=1.3, w=.7, Ca2=1., Cq3=2.)
+    for e in range(n):
+        got = mb.toolbox.eulerbeam3d_structs(c1[e], c2[e], mat, orient2=o2[e])[0]
+        ref = OE.beam_ctor(c1[e], c2[e], np.asarray(mat, float), orient2=o2[e])
+        assert np.array_equal(got, ref), e
+    got = mb.toolbox.eulerbeam3d_structs(c1, c2, mat)                     # many at once = one at a time
+    assert np.array_equal(got, np.stack([OE.beam_ctor(c1[e], c2[e], np.asarray(mat, float)) for e in range(n)]))
+    bmat = mb.AxisymmetricBarCrossSection(EA=10., mu=1.5, w=.3, Cat=2., Clt=.2, Cqt=4., Can=1., Cln=.1, Cqn=3.)
+    gotb = mb.toolbox.bar3d_structs(c1, c2, bmat)
+    assert np.array_equal(gotb, np.stack([OE.bar_ctor(c1[e], c2[e], np.asarray(bmat, float)) for e in range(n)]))
+    # the reference's own constructor golden (test/TestBeamElement.jl:8-31), through the product's constructor
+    b = mb.toolbox.eulerbeam3d_structs([0, 0, 0], [4, 3, 0], mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1.))[0]
+    L = 5.
+    assert np.allclose(b[0:3], [2., 1.5, 0.]) and np.allclose(b[3:12].reshape(3, 3).T, [[.8, -.6, 0.], [.6, .8, 0.], [0., 0., 1.]])
+    assert np.allclose(b[12:16], [-0.4305681557970263, -0.16999052179242816, 0.16999052179242816, 0.4305681557970263]) and np.allclose(b[16:18], [-.5, .5])
+    assert np.allclose(b[18:21], [4., 3., 0.]) and np.allclose(b[21:24], [5., 0., 0.])
+    assert np.allclose(b[24:28], [-0.8611363115940526, -0.3399810435848563, 0.3399810435848563, 0.8611363115940526])
+    assert np.allclose(b[28:32], [-0.972414176921822, -0.49032285223640754, 0.49032285223640754, 0.972414176921822])
+    assert np.allclose(b[32:36], np.array([-0.0646110632135477, -0.221103222500738, -0.221103222500738, -0.0646110632135477]) * L)
+    assert np.allclose(b[36:40], 2. / L) and np.allclose(b[40:44], np.array([10.333635739128631, 4.079772523018276, -4.079772523018276, -10.333635739128631]) / L ** 2)
+    assert np.allclose(b[44:48], 2. / L) and b[48] == L
+    assert np.allclose(b[49:53], np.array([0.17392742256872692, 0.3260725774312731, 0.3260725774312731, 0.17392742256872692]) * L)

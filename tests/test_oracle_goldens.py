@@ -338,3 +338,69 @@ def test_beam_requestables_goldens():
         assert np.abs(r[10:13] - np.array(kap)).max() <= 1e-12       # ♢κ
         # Gauss-point curvature κgp[1] (torsion rate) is uniform along the element and equals ♢κ[1]
         assert np.abs(r[13 + 16 * np.arange(4) + 3] - kap[0]).max() <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+# adiff.hpp / Taylor restatements pinned DIRECTLY on the reference's unit-test expressions (not only through the beam matrices they produce)
+def _kat(name, n):
+    import ctypes as C
+    L = OE.lib()
+    fn = getattr(L, name)
+    fn.argtypes = [np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]
+    fn.restype = C.c_int
+    out = np.full(n, np.nan)
+    assert fn(out) == n
+    return out
+
+
+def test_adiff_operations_kat():
+    """test/TestAdiff.jl:40-52 and :107-121 — nested duals of different precedence: od = oa+oc, oj = od^2 === od*od, ok = oc*oa/oc, the `x^0 → zero` rule
+    (Adiff.jl:230) and norm(variate{1,3}(ox)) === sqrt(sum(oX.^2))"""
+    o = _kat("orc_kat_adiff", 22)
+    od, oj, odod, ok, z0, nrm = o[0:4], o[4:8], o[8:12], o[12:16], o[16:18], o[18:22]
+    assert od.tolist() == [4., 1., 1., 0.]                 # ∂ℝ{3,1,∂𝕣11}(∂𝕣11(4.0,[1.0]), [∂𝕣11(1.0,[0.0])])        TestAdiff.jl:110
+    assert oj.tolist() == odod.tolist() == [16., 8., 8., 2.]   # oj === od*od                                        TestAdiff.jl:113
+    assert ok.tolist() == [1., 1., 0., 0.]                 # ∂ℝ{3,1,∂𝕣11}(∂𝕣11(1.0,[1.0]), [∂𝕣11(0.0,[0.0])])        TestAdiff.jl:115
+    assert z0.tolist() == [0., 0.]                         # variate{1}(0.)^0 === ∂ℝ{1,1,𝕣}(0.,[0.])                  TestAdiff.jl:117
+    x = np.array([1., 2., 3.]); s = np.sqrt(14.)
+    assert nrm[0] == s and np.array_equal(nrm[1:], (2. * x) / 2. / s)                                                # TestAdiff.jl:121
+
+
+def test_taylor_motion_roundtrip_kat():
+    """test/TestTaylor.jl:5-66 — motion{P}(X) packs (x,x′,x″) into nested one-partial duals, motion⁻¹ unpacks value / velocity / acceleration
+    (zero for the orders the tuple does not hold), partials of the solver's seeding carried along"""
+    o = _kat("orc_kat_motion", 108).reshape(3, 3, 3, 4)              # [ND-1][component][ider][value + 3 partials]
+    for nd in (1, 2, 3):
+        for c in range(3):
+            for d in range(3):
+                exp = np.zeros(4)
+                if d < nd:
+                    exp[0] = 3 * d + c + 1; exp[1 + c] = 1.        # variate{1,3}(SVector(1,2,3)) etc.
+                assert np.array_equal(o[nd - 1, c, d], exp), (nd, c, d)
+
+
+def test_taylor_revariate_and_chainrule_kat():
+    """test/TestTaylor.jl:69-74 (revariate{2}) and :119-131 ("chainrule NamedTuple": q == q2) on the oracle's revariate2 / McLaurin"""
+    o = _kat("orc_kat_chainrule", 51)
+    assert o[:9].tolist() == [3., 1., 0., 1., 0., 0., 0., 0., 0.]   # ∂ℝ{2,2,∂ℝ{1,2}}(∂ℝ{1,2}(3,[1,0]), [∂ℝ{1,2}(1,[0,0]), ∂ℝ{1,2}(0,[0,0])])
+    q, q2 = o[9:30], o[30:51]
+    assert np.array_equal(q, q2)                                     # TestTaylor.jl:130
+    assert q2[0] == 1. + 4. + 6.25 + 9. + 4. and q2[1:5].tolist() == [2., 4., 5., 6.] and not q2[5:].any()
+
+
+def test_static_dual_build_is_bit_identical():
+    """liboracle_np12.so (the -O3 build with 12 compile-time partials that bench.py's CPU arm times) gives the very bits of the checker build"""
+    import muscade_b200 as mb
+    n = 300
+    for OX in (0, 2):
+        eleobj, idx, ndof = mb.synthetic.chain(n, dynamic=OX > 0)
+        X = mb.synthetic.state(ndof, nder=OX + 1); nm = mb.synthetic.newmark_coefficients(OX, 0.3)
+        dis = [dict(X=idx, U=np.zeros((n, 0), np.int64), A=np.zeros((n, 0), np.int64))]
+        a1, a2, cp, rv = OP.prepare_sweepx(dis, ndof, 0, 0)
+        a1t, a2t = np.ascontiguousarray(a1[0].T), np.ascontiguousarray(a2[0].T)
+        res = []
+        for fast in (False, True):
+            L = np.zeros(ndof); nz = np.zeros(len(rv))
+            OE.sweepx_assemble_beams_mt(eleobj, idx, a1t, a2t, OX, X, np.ones(12), nm, L, nz, 2, static_duals=fast)
+            res.append((L, nz))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
