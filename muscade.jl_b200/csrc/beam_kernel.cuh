@@ -132,7 +132,7 @@ beam_cot_kernel(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__
     TU Xu[3][6], U[3]; TR Xv[3][6];
     load_lane_state<ND>(g, st, nm, e, lane, Xu, Xv, U);
     Vec3<TS> xb[NGP], vsmb;
-    beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
+    beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, nullptr, nullptr, lane < 3);
     store_cot(Wc, t, xb, vsmb);
 }
 
@@ -153,7 +153,7 @@ beam_kernel_sd(BeamGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ 
     if (SPLIT) {
         Vec3<TS> xb[NGP], vsmb;
         load_cot(Wc, t, xb, vsmb);
-        beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, R);      // v̄ₛₘ ≠ 0 only with accelerations
+        beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, R, lane < 3);      // v̄ₛₘ ≠ 0 only with accelerations
     } else {
         beam_residual_n<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, R);
     }
@@ -513,10 +513,10 @@ beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ W
     Vec3<TS> xb[NGP], vsmb;
     if constexpr (ND >= 3) {                           // one copy of the jet code for both lane kinds (two would leave the instruction cache)
         Vec3<TS> xb2[NGP], vsmb2;
-        beam_dyn_cotangents<ND, N, true>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, xb2, &vsmb2);
+        beam_dyn_cotangents<ND, N, true>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, xb2, &vsmb2, l < 3);
         if (d == 0) store_cot(Wc, 2 * per + t, xb2, vsmb2);        // the tile the X″ lane (2,e,l) of the linear kernel reads
     } else
-        beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb);
+        beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, nullptr, nullptr, l < 3);
     store_cot(Wc, t, xb, vsmb);
 }
 template <int ND>
@@ -537,7 +537,7 @@ beam_direct_b0_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR
     if (ND >= 2) {
         Vec3<TS> xb[NGP], vsmb;
         load_cot(Wc, t, xb, vsmb);
-        beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, Rv);
+        beam_residual_cot<N, TS, (ND >= 3)>(geo, m, Xu[0], Xv[0], xb, vsmb, Rv, l < 3);
     } else {
         beam_residual_n<1, N>(geo, m, Xu, Xv, g.udof != 0, U, Rv);
     }

@@ -458,6 +458,174 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
     beam_reverse_rot<N, SC>(g, f, epsb, vsmb, acc, R, sc);
 }
 
+// ------------------------------------------------------------------------------------------------ active / passive formulation, any number type
+// (see "statics: active / passive node" below for the identities).  A lane whose seed directions all belong to ONE node — its ACTIVE node a — carries
+// the other node's rotation as plain numbers of type TP (no partial slots), so every product with them costs a direction less; the same holds one level
+// up for time-jets.  TA: number type of the active rotation (SD<1,0>, Jet<SD<1,0>>, or plain), TP: of the passive one, TU: of the translations.
+struct RodPacks { double Sth[4], Sh[4]; };
+// I + a·S + b·S² from the rotation vector and the two coefficients (the tail of rodrigues)
+template <class T> MB_HD Mat3<T> rod_matrix(const Vec3<T>& v, const T& a, const T& b) {
+    T v00 = v[0] * v[0], v11 = v[1] * v[1], v22 = v[2] * v[2];
+    T b01 = b * (v[0] * v[1]), b02 = b * (v[0] * v[2]), b12 = b * (v[1] * v[2]);
+    T a0 = a * v[0], a1 = a * v[1], a2 = a * v[2];
+    Mat3<T> r;
+    r(0, 0) = 1.0 - b * (v11 + v22); r(1, 1) = 1.0 - b * (v00 + v22); r(2, 2) = 1.0 - b * (v00 + v11);
+    r(1, 0) = b01 + a2; r(0, 1) = b01 - a2;
+    r(2, 0) = b02 - a1; r(0, 2) = b02 + a1;
+    r(2, 1) = b12 + a0; r(1, 2) = b12 - a0;
+    return r;
+}
+// Rematerialisation fence: the value is unchanged, but the compiler may no longer assume so — what is recomputed from it is not merged with the first
+// evaluation and kept in registers from the forward sweep to the end of the reverse sweep (the kernel is bound by its register live set, not by flops).
+MB_HD void opaque(double& x) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(x));
+#else
+    (void)x;
+#endif
+}
+template <bool A, bool B> MB_HD void opaque(SD<A, B>& x) { opaque(x.v); if constexpr (A) opaque(x.d0); if constexpr (B) opaque(x.d1); }
+#ifndef MB_AP_REMAT
+#define MB_AP_REMAT 1
+#endif
+template <class T> MB_FN Mat3<T> rodrigues_pk(const Vec3<T>& v, RodAux<T>& aux, const T& th, bool small, const RodPacks& pk) {
+    T a, b;
+    aux.small = small;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { aux.Sth[k] = pk.Sth[k]; aux.Sh[k] = pk.Sh[k]; }
+    if (small) { a = Make<T>::c(1.0); b = Make<T>::c(0.5); }
+    else { a = apply_fn(th, aux.Sth); T c = apply_fn(th * 0.5, aux.Sh); b = sqr_ref(c) * 0.5; }
+    aux.a = a; aux.b = b; aux.th = th;
+    return rod_matrix(v, a, b);
+}
+template <class T> MB_HD T norm_of(const Vec3<T>& v) { return mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); }
+MB_HD void rod_packs(double th, RodPacks& pk) { sinc_pack(th, pk.Sth); sinc_pack(0.5 * th, pk.Sh); }
+
+struct PacksLocal { MB_HD void operator()(int, double th, RodPacks& pk) const { rod_packs(th, pk); } };
+template <class TA, class TP, class TU> struct BeamFwdAP {
+    using TS = decltype(TA() * TU());
+    Vec3<TA> va, h, dvp, dv, vl, vsm;        // dvp = Δv′ = ½Rodrigues⁻¹(rₐrₚᵀ), dv = Δvᵧ = σΔv′, vl = rₛₘᵀΔvᵧ
+    Vec3<TP> vp;
+    RodAux<TA> aa, ad; RodAux<TP> ap; RinvAux<TA> ai, ir;
+    Mat3<TA> ra, rd, r; Mat3<TP> rp, B;      // B = rₚ·rₘ, r = rₛₘ = Rodrigues(Δv′)·B
+    Vec3<TU> dp, cs;
+    Vec3<TS> ul, q; TS eps, qn;
+};
+template <bool VSM, class TA, class TP, class TU, class EX>
+MB_HD void beam_forward_ap(const BeamGeo& g, const Vec3<TU>& u1, const Vec3<TU>& u2, const Vec3<TA>& va, const Vec3<TP>& vp, double sigma,
+                           BeamFwdAP<TA, TP, TU>& f, const EX& ex) {
+    f.va = va; f.vp = vp;
+    RodPacks pk;
+    TA tha = norm_of(va); TP thp = norm_of(vp);
+    ex(0, value(tha), pk);
+    f.ra = rodrigues_pk(f.va, f.aa, tha, value(tha) < 1e-14, pk);
+    ex(1, value(thp), pk);
+    f.rp = rodrigues_pk(f.vp, f.ap, thp, value(thp) < 1e-14, pk);
+    Mat3<TA> Nm = mul_nt(f.ra, f.rp);
+    f.h = rodrigues_inv(Nm, f.ai);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { f.dvp[i] = 0.5 * f.h[i]; f.dv[i] = sigma * f.dvp[i]; }
+    TA thd = norm_of(f.dvp);
+    ex(2, value(thd), pk);
+    f.rd = rodrigues_pk(f.dvp, f.ad, thd, value(thd) < 1e-14, pk);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f.B(i, j) = (f.rp(i, 0) * g.rm(0, j) + f.rp(i, 1) * g.rm(1, j)) + f.rp(i, 2) * g.rm(2, j);
+    f.r = mul(f.rd, f.B);
+    if constexpr (VSM) f.vsm = rodrigues_inv(f.r, f.ir);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        TU c2 = 0.5 * (u1[i] + u2[i]);
+        f.dp[i] = (u2[i] + g.tgm[i] * 0.5) - c2;
+        f.cs[i] = c2 + g.cm[i];
+    }
+    f.q = mulv_t(f.r, f.dp);
+    f.ul = f.q; f.ul[0] = f.ul[0] - g.L * 0.5;
+    f.vl = mulv_t(f.r, f.dv);
+    f.qn = mb_sqrt((f.q[0] * f.q[0] + f.q[1] * f.q[1]) + f.q[2] * f.q[2]);
+    f.eps = f.qn * (2.0 / g.L) - 1.0;
+}
+// Everything upstream of the Gauss loop, reverse: ε, uₗ/vₗ, vₛₘ, r = rd·B, Δv′, N = rₐrₚᵀ and the three Rodrigues maps → rows of u₁, u₂, vₐ, vₚ
+template <bool VSM, class TA, class TP, class TU, class S>
+MB_HD void beam_reverse_ap(const BeamGeo& g, const BeamFwdAP<TA, TP, TU>& f, const S& epsb, const Vec3<S>& vsmb, BeamAcc<S>& a, double sigma,
+                           S* Ru1, S* Ru2, S* Rva, S* Rvp) {
+    const double L = g.L;
+    Mat3<S>& rb = a.rb; Vec3<S>&ulb = a.ulb, &vlb = a.vlb, &cb = a.cb;
+    {
+        S k = (epsb * (2.0 / L)) / f.qn;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ulb[i] = ulb[i] + k * f.q[i];
+    }
+    Vec3<S> dvb = mulv(f.r, vlb);
+    {
+        Vec3<S> dpb = mulv(f.r, ulb);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { S hcs = 0.5 * (cb[i] - dpb[i]); Ru1[i] = hcs; Ru2[i] = hcs + dpb[i]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rb(i, j) = rb(i, j) + (f.dp[i] * ulb[j] + f.dv[i] * vlb[j]);
+    if constexpr (VSM) rodrigues_inv_adj(f.vsm, f.ir, vsmb, rb);
+    Mat3<S> rdb = mul_nt(rb, f.B);
+    Mat3<S> Bb = mul_tn(f.rd, rb);
+    Mat3<S> rpb;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rpb(i, j) = (Bb(i, 0) * g.rm(j, 0) + Bb(i, 1) * g.rm(j, 1)) + Bb(i, 2) * g.rm(j, 2);
+    Vec3<S> dvpb{sigma * dvb[0], sigma * dvb[1], sigma * dvb[2]};
+    rodrigues_adj(f.dvp, f.ad, rdb, dvpb);
+    Mat3<S> Nb; { S z = Make<S>::c(0.); for (int i = 0; i < 9; ++i) Nb.a[i] = z; }
+    Vec3<S> hb{0.5 * dvpb[0], 0.5 * dvpb[1], 0.5 * dvpb[2]};
+    rodrigues_inv_adj(f.h, f.ai, hb, Nb);
+    Mat3<S> rab = mul(Nb, f.rp);
+    Mat3<S> rpb2 = mul_tn(Nb, f.ra);
+    for (int i = 0; i < 9; ++i) rpb.a[i] = rpb.a[i] + rpb2.a[i];
+    S z = Make<S>::c(0.);
+    Vec3<S> vab{z, z, z}, vpb{z, z, z};
+    rodrigues_adj(f.va, f.aa, rab, vab);
+    rodrigues_adj(f.vp, f.ap, rpb, vpb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Rva[i] = vab[i]; Rvp[i] = vpb[i]; }
+}
+// Gauss-loop accumulators for the AP forward state (same arithmetic as beam_internal_reverse / beam_gp_reverse on BeamFwd)
+template <class F, class S> MB_HD void beam_internal_reverse_f(double L, const BeamMat& m, const F& f, BeamAcc<S>& a) {
+    const double c48 = 48.0 / (L * L * L), c4 = 4.0 / L;
+    a.ulb[1] = a.ulb[1] + (m.EI3 * c48) * f.ul[1];
+    a.ulb[2] = a.ulb[2] + (m.EI2 * c48) * f.ul[2];
+    a.vlb[0] = a.vlb[0] + (m.GJ * c4) * f.vl[0];
+    a.vlb[1] = a.vlb[1] + (m.EI2 * c4) * f.vl[1];
+    a.vlb[2] = a.vlb[2] + (m.EI3 * c4) * f.vl[2];
+}
+template <class F, class S> MB_HD void beam_gp_reverse_f(const GpConst& c, double L, const F& f, const Vec3<S>& xb, BeamAcc<S>& a) {
+    const double yv = c.yv * L;
+    auto p = beam_gp_local(c, L, f.ul, f.vl);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a.rb(i, j) = a.rb(i, j) + xb[i] * p[j];
+    Vec3<S> pb = mulv_t(f.r, xb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) a.cb[i] = a.cb[i] + xb[i];
+    a.ulb[0] = a.ulb[0] + c.ya * pb[0];
+    a.ulb[1] = a.ulb[1] + c.yu * pb[1];
+    a.ulb[2] = a.ulb[2] + c.yu * pb[2];
+    a.vlb[1] = a.vlb[1] - yv * pb[2];
+    a.vlb[2] = a.vlb[2] + yv * pb[1];
+}
+// strips the partial slots: the passive node's numbers
+MB_HD SD<false, false> strip(const SD<false, false>& x) { return x; }
+template <bool A, bool B> MB_HD SD<false, false> strip(const SD<A, B>& x) { SD<false, false> r; r.v = x.v; return r; }
+template <class T> MB_HD auto strip(const Jet<T>& x) -> Jet<decltype(strip(x.c0))> { Jet<decltype(strip(x.c0))> r; r.c0 = strip(x.c0); r.c1 = strip(x.c1); r.c2 = strip(x.c2); return r; }
+// MB_DYN_AP: the Newmark / DirectXUA lanes (NumSD: rotation dof l and translation dof l, both of node ⌊l/3⌋+1) run the active/passive formulation
+#ifndef MB_DYN_AP
+#define MB_DYN_AP 1
+#endif
+template <class N> struct ApOk { static constexpr bool value = false; };
+template <> struct ApOk<NumSD> { static constexpr bool value = MB_DYN_AP != 0; };
+
 // ------------------------------------------------------------------------------------------------ two-phase variant (ND ≥ 2)
 // The fused Newmark kernel is ~210 KB of straight-line code and runs out of the instruction cache; split in two, each half fits.
 // Phase A: time-jets forward only → external-load cotangents x̄_gp = dL·fₑ (BeamElement.jl:28-58,169) and v̄ₛₘ = Σ dL·mₑ (:56-57).
@@ -465,22 +633,13 @@ template <int ND, class N, class SC> MB_HD void beam_residual_n(const BeamGeo& g
 // parts unused).  Along q(t) = X₀+X′t+X″t²/2, ∂/∂X″ⱼ f(q(t)) = (t²/2)·(∂ⱼf)(q(t)), whose second time derivative at 0 is ∂ⱼf(X₀): ∂ẍ/∂X″ⱼ = ∂x/∂X₀ⱼ,
 // ∂r̈/∂X″ⱼ = ∂r/∂X₀ⱼ, ∂ẋ/∂X″ⱼ = 0 — all of it already in the order-0 partials of this lane, so DirectXUA needs no time-jet lanes seeded at X″.
 // (Exact also under the reference's x^0 rule, whose missing term depends on X₀ and X′ only.)
-template <int ND, class N, bool DD = false> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
-                                                         bool udof, const typename N::TU* U0, Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb,
-                                                         Vec3<typename N::TS>* xb2 = nullptr, Vec3<typename N::TS>* vsmb2 = nullptr) {
-    using TR = typename N::TR; using TU = typename N::TU; using S = typename N::TS;
-    using NJ = NumJet<N>;
-    using JR = typename NJ::TR; using JU = typename NJ::TU; using JS = typename NJ::TS;
+// the Gauss loop of phase A on a forward state F (BeamFwd<NumJet<N>> or BeamFwdAP of jets): fj.r, fj.ul, fj.vl, fj.cs
+template <int ND, class N, bool DD, class F> MB_HD void beam_dyn_cot_tail(const BeamGeo& g, const BeamMat& m, const F& fj, bool udof, const typename N::TU* U0,
+                                                                          Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb,
+                                                                          Vec3<typename N::TS>* xb2, Vec3<typename N::TS>* vsmb2) {
+    using TR = typename N::TR; using S = typename N::TS;
+    using JS = Jet<S>;
     const double L = g.L;
-    JU XuJ[6]; JR XvJ[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        XuJ[i].c0 = Xu[0][i]; XuJ[i].c1 = Xu[1][i]; XuJ[i].c2 = (ND >= 3) ? Xu[2][i] : Make<TU>::c(0.);
-        XvJ[i].c0 = Xv[0][i]; XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
-    }
-    BeamFwd<NJ> fj;
-    beam_forward<NJ, false>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JR>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]},
-                            Vec3<JR>{XvJ[3], XvJ[4], XvJ[5]}, fj);
     Mat3<TR> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
     MB_PRAGMA(unroll MB_GP_UNROLL_DYN)
     for (int gp = 0; gp < NGP; ++gp) {
@@ -530,6 +689,41 @@ template <int ND, class N, bool DD = false> MB_HD void beam_dyn_cotangents(const
             TR d1l = (m.iota1 * L) * ((a21 - a12) * 0.5);
             for (int i = 0; i < 3; ++i) { (*vsmb2)[i] = widen<S>(val(r0(i, 0)) * d1l); (*vsmb2)[i].v = 0.; }
         }
+    }
+}
+// n1: the lane's seeds belong to node 1 (lanes 0-2) or node 2 (lanes 3-5) — only read by the active/passive formulation (ApOk<N>)
+template <int ND, class N, bool DD = false> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+                                                         bool udof, const typename N::TU* U0, Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb,
+                                                         Vec3<typename N::TS>* xb2 = nullptr, Vec3<typename N::TS>* vsmb2 = nullptr, bool n1 = true) {
+    using TR = typename N::TR; using TU = typename N::TU;
+    using NJ = NumJet<N>;
+    using JR = typename NJ::TR; using JU = typename NJ::TU;
+    JU XuJ[6]; JR XvJ[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        XuJ[i].c0 = Xu[0][i]; XuJ[i].c1 = Xu[1][i]; XuJ[i].c2 = (ND >= 3) ? Xu[2][i] : Make<TU>::c(0.);
+        XvJ[i].c0 = Xv[0][i]; XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
+    }
+    // ND = 3 stays on the symmetric form: under the reference's x^0 rule (sqr_ref, dual.cuh) the SECOND time derivative of Rodrigues is not the derivative of a
+    // rotation, so Rodrigues(Δvᵧ)·rₛ₁ = Rodrigues(Δvᵧ)ᵀ·rₛ₂ — which the active/passive form rests on for the lanes of node 1 — holds for values and velocities
+    // only; the accelerations must be formed exactly as the reference forms them (BeamElement.jl:195-199)
+    if constexpr (ApOk<N>::value && ND < 3) {
+        using JP = decltype(strip(XvJ[0]));
+        Vec3<JR> va; Vec3<JP> vp;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const JP p1 = strip(XvJ[i]), p2 = strip(XvJ[3 + i]);
+            va[i].c0 = n1 ? XvJ[i].c0 : XvJ[3 + i].c0; va[i].c1 = n1 ? XvJ[i].c1 : XvJ[3 + i].c1; va[i].c2 = n1 ? XvJ[i].c2 : XvJ[3 + i].c2;
+            vp[i].c0 = n1 ? p2.c0 : p1.c0; vp[i].c1 = n1 ? p2.c1 : p1.c1; vp[i].c2 = n1 ? p2.c2 : p1.c2;
+        }
+        BeamFwdAP<JR, JP, JU> fj;
+        beam_forward_ap<false>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]}, va, vp, n1 ? -1.0 : 1.0, fj, PacksLocal());
+        beam_dyn_cot_tail<ND, N, DD>(g, m, fj, udof, U0, xb, vsmb, xb2, vsmb2);
+    } else {
+        BeamFwd<NJ> fj;
+        beam_forward<NJ, false>(g, Vec3<JU>{XuJ[0], XuJ[1], XuJ[2]}, Vec3<JR>{XvJ[0], XvJ[1], XvJ[2]}, Vec3<JU>{XuJ[3], XuJ[4], XuJ[5]},
+                                Vec3<JR>{XvJ[3], XvJ[4], XvJ[5]}, fj);
+        beam_dyn_cot_tail<ND, N, DD>(g, m, fj, udof, U0, xb, vsmb, xb2, vsmb2);
     }
 }
 // getresult (src/Output.jl:131-181) for EulerBeam3D, values only: the ☼/♢ requestables of residual (BeamElement.jl:151-174) and resultants (:28-64).
@@ -585,23 +779,52 @@ template <int ND> MB_HD void beam_results(const BeamGeo& g, const BeamMat& m, co
 // Phase B: order-0 forward + reverse sweep with the cotangents of phase A
 // (S ≠ N::TS: forward in plain values, cotangents carrying partials — the linear lanes ∂R/∂X′, ∂R/∂X″, ∂R/∂U of DirectXUA)
 template <class N, class S = typename N::TS, bool VSM = true> MB_HD void beam_residual_cot(const BeamGeo& g, const BeamMat& m, const typename N::TU* Xu0,
-                                                                                           const typename N::TR* Xv0, const Vec3<S>* xb, const Vec3<S>& vsmb, S* R) {
+                                                                                           const typename N::TR* Xv0, const Vec3<S>* xb, const Vec3<S>& vsmb, S* R,
+                                                                                           bool n1 = true) {
     using TR = typename N::TR; using TU = typename N::TU;
     const double L = g.L;
-    BeamFwd<N> f;
     BeamAcc<S> acc;
     {
         S z = Make<S>::c(0.);
         for (int i = 0; i < 9; ++i) acc.rb.a[i] = z;
         for (int i = 0; i < 3; ++i) { acc.ulb[i] = z; acc.vlb[i] = z; acc.cb[i] = z; }
     }
-    beam_forward<N, VSM>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
-    MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
-    for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N, S>(gp_const(gp), L, f, xb[gp], acc);
-    beam_internal_reverse<N, S>(L, m, f, acc);
-    S epsb = widen<S>((m.EA * L) * f.eps);
-    HostScratch sc;
-    beam_reverse_rot<N, HostScratch, S, VSM>(g, f, epsb, vsmb, acc, R, sc);
+    // measured on B200 (4 M elements): with accelerations (VSM: the v̄ₛₘ branch adds Rodrigues⁻¹(rₛₘ) to the live set) the active/passive phase B spills more than it
+    // saves (SweepX{2} 26.2 vs 25.3 ms), without it wins (SweepX{1} 16.3 vs 17.2 ms) — so only the first-order kernels use it
+    if constexpr (ApOk<N>::value && !VSM) {
+        using TP = decltype(strip(Xv0[0]));
+        Vec3<TR> va; Vec3<TP> vp;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const TP p1 = strip(Xv0[i]), p2 = strip(Xv0[3 + i]);
+            va[i] = n1 ? Xv0[i] : Xv0[3 + i];
+            vp[i] = n1 ? p2 : p1;
+        }
+        const double sigma = n1 ? -1.0 : 1.0;
+        BeamFwdAP<TR, TP, TU> f;
+        beam_forward_ap<VSM>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, va, vp, sigma, f, PacksLocal());
+        MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
+        for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse_f(gp_const(gp), L, f, xb[gp], acc);
+        beam_internal_reverse_f(L, m, f, acc);
+        S epsb = widen<S>((m.EA * L) * f.eps);
+        S Ru1[3], Ru2[3], Rva[3], Rvp[3];
+        beam_reverse_ap<VSM>(g, f, epsb, vsmb, acc, sigma, Ru1, Ru2, Rva, Rvp);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            R[i] = Ru1[i]; R[6 + i] = Ru2[i];
+            R[3 + i] = n1 ? Rva[i] : Rvp[i];
+            R[9 + i] = n1 ? Rvp[i] : Rva[i];
+        }
+    } else {
+        BeamFwd<N> f;
+        beam_forward<N, VSM>(g, Vec3<TU>{Xu0[0], Xu0[1], Xu0[2]}, Vec3<TR>{Xv0[0], Xv0[1], Xv0[2]}, Vec3<TU>{Xu0[3], Xu0[4], Xu0[5]}, Vec3<TR>{Xv0[3], Xv0[4], Xv0[5]}, f);
+        MB_PRAGMA(unroll MB_GP_UNROLL_STATIC)
+        for (int gp = 0; gp < NGP; ++gp) beam_gp_reverse<N, S>(gp_const(gp), L, f, xb[gp], acc);
+        beam_internal_reverse<N, S>(L, m, f, acc);
+        S epsb = widen<S>((m.EA * L) * f.eps);
+        HostScratch sc;
+        beam_reverse_rot<N, HostScratch, S, VSM>(g, f, epsb, vsmb, acc, R, sc);
+    }
 }
 
 template <int ND, class N> MB_HD void beam_residual_n(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
@@ -697,47 +920,7 @@ template <class Put, class Put2> MB_HD bool beam_static_sym_store(int l, const S
 // u₁, u₂ (Ru1, Ru2), of the active node's rotation (Rva) and of the passive node's (Rvp): value = R, d0 = the lane's tangent column.
 // Special-function packs: PK = nullptr evaluates them here; otherwise PK[0..7] = sinc packs at θₐ, θₐ/2 and PK[8..15] at θₚ, θₚ/2 come from the caller
 // (one lane of the element evaluates each of them and they are exchanged by warp shuffles, see beam_static_ap_kernel).
-struct RodPacks { double Sth[4], Sh[4]; };
-// I + a·S + b·S² from the rotation vector and the two coefficients (the tail of rodrigues)
-template <class T> MB_HD Mat3<T> rod_matrix(const Vec3<T>& v, const T& a, const T& b) {
-    T v00 = v[0] * v[0], v11 = v[1] * v[1], v22 = v[2] * v[2];
-    T b01 = b * (v[0] * v[1]), b02 = b * (v[0] * v[2]), b12 = b * (v[1] * v[2]);
-    T a0 = a * v[0], a1 = a * v[1], a2 = a * v[2];
-    Mat3<T> r;
-    r(0, 0) = 1.0 - b * (v11 + v22); r(1, 1) = 1.0 - b * (v00 + v22); r(2, 2) = 1.0 - b * (v00 + v11);
-    r(1, 0) = b01 + a2; r(0, 1) = b01 - a2;
-    r(2, 0) = b02 - a1; r(0, 2) = b02 + a1;
-    r(2, 1) = b12 + a0; r(1, 2) = b12 - a0;
-    return r;
-}
-// Rematerialisation fence: the value is unchanged, but the compiler may no longer assume so — what is recomputed from it is not merged with the first
-// evaluation and kept in registers from the forward sweep to the end of the reverse sweep (the kernel is bound by its register live set, not by flops).
-MB_HD void opaque(double& x) {
-#ifdef __CUDA_ARCH__
-    asm volatile("" : "+d"(x));
-#else
-    (void)x;
-#endif
-}
-template <bool A, bool B> MB_HD void opaque(SD<A, B>& x) { opaque(x.v); if constexpr (A) opaque(x.d0); if constexpr (B) opaque(x.d1); }
-#ifndef MB_AP_REMAT
-#define MB_AP_REMAT 1
-#endif
-template <class T> MB_FN Mat3<T> rodrigues_pk(const Vec3<T>& v, RodAux<T>& aux, const T& th, bool small, const RodPacks& pk) {
-    T a, b;
-    aux.small = small;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { aux.Sth[k] = pk.Sth[k]; aux.Sh[k] = pk.Sh[k]; }
-    if (small) { a = Make<T>::c(1.0); b = Make<T>::c(0.5); }
-    else { a = apply_fn(th, aux.Sth); T c = apply_fn(th * 0.5, aux.Sh); b = sqr_ref(c) * 0.5; }
-    aux.a = a; aux.b = b; aux.th = th;
-    return rod_matrix(v, a, b);
-}
-template <class T> MB_HD T norm_of(const Vec3<T>& v) { return mb_sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); }
-MB_HD void rod_packs(double th, RodPacks& pk) { sinc_pack(th, pk.Sth); sinc_pack(0.5 * th, pk.Sh); }
-
 // EX: how the packs of the three Rodrigues maps are obtained — a functor  ex(which, θ, pk)  with which = 0 (active), 1 (passive), 2 (Δv′)
-struct PacksLocal { MB_HD void operator()(int, double th, RodPacks& pk) const { rod_packs(th, pk); } };
 // OUT: where results go as soon as they exist (holding them to the end of the sweep costs registers the kernel does not have):
 //   out.tt(Gc)          column c of G (closed-form translation × translation block), after the forward sweep
 //   out.trans(Ru1,Ru2)  residual rows of u₁, u₂ (value = R, d0 = the lane's tangent column), early in the reverse sweep

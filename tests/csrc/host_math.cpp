@@ -137,3 +137,37 @@ extern "C" int mbh_beam_results(const double* geo16, const double* mat16, int nd
     else beam_results<3>(g, m, Xu, Xv, out77);
     return 0;
 }
+
+// Two-phase :iter path exactly as beam_cot_kernel + beam_kernel_sd<ND,split> run it (phase A: time-jets → cotangents, phase B: order-0 forward + reverse),
+// lane l = (rotation dof l, translation dof l); with MB_DYN_AP the lanes use the active/passive formulation. Returns R[12], K[12][12] like mbh_beam_iter_sd.
+template <int ND> static void run_split(const BeamGeo& g, const BeamMat& m, const double* Xval, const double* scale, double a1, double b1,
+                                        int udof, const double* Uval, double* R, double* K) {
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    static const int rot[6] = {3, 4, 5, 9, 10, 11}, tra[6] = {0, 1, 2, 6, 7, 8};
+    for (int l = 0; l < 6; ++l) {
+        TU Xu[3][6], U[3]; TR Xv[3][6]; TS Rv[12];
+        for (int d = 0; d < 3; ++d) for (int i = 0; i < 6; ++i) {
+            const double coef = d == 0 ? 1.0 : (d == 1 ? a1 : b1);
+            Xu[d][i].v = d < ND ? Xval[d * 12 + tra[i]] : 0.; Xu[d][i].d1 = (i == l) ? coef * scale[tra[i]] : 0.;
+            Xv[d][i].v = d < ND ? Xval[d * 12 + rot[i]] : 0.; Xv[d][i].d0 = (i == l) ? coef * scale[rot[i]] : 0.;
+        }
+        for (int i = 0; i < 3; ++i) { U[i].v = udof ? Uval[i] : 0.; U[i].d1 = 0.; }
+        Vec3<TS> xb[NGP], vsmb;
+        beam_dyn_cotangents<ND, N>(g, m, Xu, Xv, udof != 0, U, xb, vsmb, nullptr, nullptr, l < 3);
+        beam_residual_cot<N, TS, (ND >= 3)>(g, m, Xu[0], Xv[0], xb, vsmb, Rv, l < 3);
+        for (int i = 0; i < 12; ++i) { R[i] = Rv[i].v; K[i * 12 + rot[l]] = Rv[i].d0; K[i * 12 + tra[l]] = Rv[i].d1; }
+    }
+}
+extern "C" int mbh_beam_iter_split(const double* geo16, const double* mat16, int nd, const double* Xval, const double* scale, double a1, double b1,
+                                   int udof, const double* Uval, double* R, double* K) {
+    BeamGeo g; BeamMat m;
+    for (int i = 0; i < 3; ++i) g.cm[i] = geo16[i];
+    for (int i = 0; i < 9; ++i) g.rm.a[i] = geo16[3 + i];
+    for (int i = 0; i < 3; ++i) g.tgm[i] = geo16[12 + i];
+    g.L = geo16[15];
+    std::memcpy(&m, mat16, sizeof m);
+    if (nd == 2) run_split<2>(g, m, Xval, scale, a1, b1, udof, Uval, R, K);
+    else if (nd == 3) run_split<3>(g, m, Xval, scale, a1, b1, udof, Uval, R, K);
+    else return -1;
+    return 0;
+}

@@ -74,6 +74,29 @@ def test_sparse_dual_lanes_vs_oracle(H, nd, amp):
     assert rel(R1, R0) <= 1e-12 and rel(K1, dR0) <= 1e-12
 
 
+@pytest.mark.parametrize("nd", [2, 3])
+@pytest.mark.parametrize("amp", [0.0, 1.0, 3.0, 8.0])
+def test_two_phase_active_passive_lanes_vs_oracle(H, nd, amp):
+    """the Newmark / DirectXUA lanes as beam_cot_kernel + beam_kernel_sd<ND,split> run them: phase A (time-jets → cotangents) and phase B (order-0
+    forward + reverse), both in the active/passive formulation — the lane's rotation and translation dof belong to one node, the other node's rotation
+    is carried as plain numbers (and plain jets)"""
+    H.mbh_beam_iter_split.argtypes = [f64p, f64p, C.c_int, f64p, f64p, C.c_double, C.c_double, C.c_int, f64p, f64p, f64p]
+    rng = np.random.default_rng(50 + nd + int(amp))
+    e = OE.beam_ctor([0, 0, 0], [.8, .6, 0.1], OE.beam_cross_section(**MAT), orient2=(0, 1, .2))
+    scale = np.array([10., 10, 10, 1, 1, 1] * 2); a1, b1 = 3.3, 7.1
+    X = np.zeros((3, 12)); X[0] = rng.uniform(-1, 1, 12) * 0.3 * amp
+    for d in range(1, nd):
+        X[d] = rng.uniform(-1, 1, 12) * 0.1 * (amp > 0)
+    U = rng.uniform(-1, 1, 3)
+    Xs = np.zeros((nd, 12, 12))
+    for d in range(nd):
+        Xs[d, np.arange(12), np.arange(12)] = scale * [1, a1, b1][d]
+    R0, dR0, rc = OE.beam_residual(e, X[:nd], Xs, U, np.zeros((3, 12)))
+    R1 = np.zeros(12); K1 = np.zeros((12, 12))
+    assert H.mbh_beam_iter_split(geo16(e), np.ascontiguousarray(e[53:69]), nd, np.ascontiguousarray(X), scale, a1, b1, 1, U, R1, K1) == 0
+    assert rel(R1, R0) <= 1e-12 and rel(K1, dR0) <= 1e-12, (rel(R1, R0), rel(K1, dR0))
+
+
 @pytest.mark.parametrize("amp", [0.0, 1.0, 3.0, 8.0])
 @pytest.mark.parametrize("udof", [0, 1])
 def test_static_symmetric_tangent_vs_oracle(H, amp, udof):
