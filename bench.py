@@ -235,10 +235,12 @@ class Comm:
             self.eng.close(); self.eng = None
 
 
-def run_sweepx(args, rank, world, local, comm):
+def run_sweepx(args, rank, world, local, comm, OX=None, N=None, steps=None, block=False):
+    """block: a secondary workload carried inside the default line (no e2e / CPU legs): BASELINE.json configs[1] = SweepX{2} Newmark on 1e6 elements"""
     import muscade_b200 as mb
-    OX = args.ox
-    N = int(args.nele or 1e7)
+    OX = args.ox if OX is None else OX
+    N = int(args.nele or 1e7) if N is None else int(N)
+    steps = args.steps if steps is None else steps
     eng = mb.Engine(local)
     fp64_peak = eng.fp64_tflops()
     comm.attach(eng)
@@ -265,7 +267,7 @@ def run_sweepx(args, rank, world, local, comm):
     launches0 = eng.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
-    step_ms = comm.max(eng.time_step_dev(OX, "iter", nm, reps=args.steps))
+    step_ms = comm.max(eng.time_step_dev(OX, "iter", nm, reps=steps))
     barrier()
     wall = time.perf_counter() - t0
     launches = eng.launch_count() - launches0
@@ -275,7 +277,7 @@ def run_sweepx(args, rank, world, local, comm):
     value = world * N / (step_ms * 1e-3)
 
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not block:
         for a in X + [Lh, nzh]:
             eng.pin(a)
 
@@ -335,8 +337,8 @@ def run_sweepx(args, rank, world, local, comm):
         roof["hbm"] = {"alg_bytes_per_element": ab, "achieved_gbs": N * ab / (el_ms * 1e-3) / 1e9, "peak_gbs": hp, "peak_source": hsrc,
                        "frac": N * ab / (el_ms * 1e-3) / 1e9 / hp}
         cpu_n = args.cpu_sample * 5                       # ≈ 10 s of one host core with the static-dual build
-        cpu_rate, cpu_dt = cpu_port_rate(mb, OX, cpu_n, 1)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        cpu_rate, cpu_dt = (None, 0.) if block else cpu_port_rate(mb, OX, cpu_n, 1)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, OX, N, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof,
@@ -346,6 +348,9 @@ def run_sweepx(args, rank, world, local, comm):
                 "breakdown_ms": {"element_kernels": el_ms, "segmented_reduction": ga_ms, "serial_sum": el_ms + ga_ms, "wall_timed_region_s": wall,
                                  "note": "value is from K whole steps between two events; element_kernels / segmented_reduction are the same launches "
                                          "with an event in between (second pass)"}}
+        if block:
+            for k in ("cpu_baseline", "e2e", "higher_is_better", "vs_baseline", "dtype", "data", "clocks"):
+                line.pop(k, None)
     eng.close()
     return line
 
@@ -615,8 +620,11 @@ def main():
         if not args.no_directxua and args.nele is None and args.ox == 0:
             # BASELINE.json configs[3] in the same run (strong scaling over the ranks): 1 warm-up + dx_passes timed passes over all 2000 time steps
             dx = run_directxua(args, rank, world, local, comm, steps=args.dx_passes, warmup=1, block=True)
+            # BASELINE.json configs[1]: SweepX{2} Newmark-β assemble!{:iter} on 1e6 elements per GPU (the per-step assembly of a 1000-step run)
+            nw = run_sweepx(args, rank, world, local, comm, OX=2, N=1e6, steps=50, block=True)
             if line is not None:
                 line["directxua"] = dx
+                line["newmark"] = nw
     if rank == 0 and line is not None:
         line["comm"] = {"backend": "NCCL inside libmuscade_b200.so (mb_comm_init, dlopen libnccl.so.2)" if world > 1 else "none", "ranks": world,
                         "nccl_version": comm.eng.comm_info()[2] if comm.eng is not None else None,

@@ -183,7 +183,9 @@ soil_kernel(SoilGroupDev g, StateDev st, NewmarkDev nm, double* __restrict__ Ke,
 // Bar3D: lane d < ND carries the six partials of X_d, lane ND (Udof types) the three of U₀ — dense Dual<6>, one thread per (element, lane).
 template <int ND>
 __global__ void __launch_bounds__(128)
-bar_direct_kernel(BarGroupDev g, DirectStateDev st, double t, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag, unsigned long long nanbase) {
+bar_direct_kernel(BarGroupDev g, DirectStateDev st, double t, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag, unsigned long long nanbase,
+                  StepBatch sb) {
+    batch_state(st, sb); t += blockIdx.y * sb.dt; dR += (int64_t)blockIdx.y * sb.sdR; R += (int64_t)blockIdx.y * sb.sR; nanbase += blockIdx.y * sb.snan;
     const int LPE = ND + (g.udof ? 1 : 0), NP = 6 * ND + (g.udof ? 3 : 0);
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = q / LPE;
@@ -223,7 +225,9 @@ bar_direct_kernel(BarGroupDev g, DirectStateDev st, double t, double* __restrict
 // GX[(e·3+i)·ND+d] receives the L1[X][d+1] contribution of element dof i.
 template <int ND>
 __global__ void soil_direct_kernel(SoilGroupDev g, DirectStateDev st, const double* __restrict__ Lam, double lamscale, double* __restrict__ dR,
-                                   double* __restrict__ R, double* __restrict__ GX, unsigned long long* nanflag, unsigned long long nanbase) {
+                                   double* __restrict__ R, double* __restrict__ GX, unsigned long long* nanflag, unsigned long long nanbase, StepBatch sb) {
+    batch_state(st, sb); Lam += (int64_t)blockIdx.y * sb.sLam; dR += (int64_t)blockIdx.y * sb.sdR; R += (int64_t)blockIdx.y * sb.sR; GX += (int64_t)blockIdx.y * sb.sGX;
+    nanbase += blockIdx.y * sb.snan;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= g.nele) return;
     const double z0 = g.par[e * 5], Kh = g.par[e * 5 + 1], Kv = g.par[e * 5 + 2], Ch = g.par[e * 5 + 3], Cv = g.par[e * 5 + 4];

@@ -477,6 +477,17 @@ void launch_beam_results(int ND, const BeamGroupDev& g, const StateDev& st, doub
 //   lin            lanes (d≥1,e,l) and 2 U-lanes per Udof element: R is linear in the cotangents, so ∂R/∂X_d = J(X₀)ᵀ·∂c/∂X_d needs the forward
 //                  sweep in plain values only and the reverse sweep on the partials of c (∂c/∂U is known in closed form: −dL·scale.U).
 struct DirectStateDev { const double* X[3]; const double* U0; };
+// Step batching (models with few elements and many time steps, BASELINE.json configs[4]: the steps of DirectXUA are independent, src/DirectXUA.jl:328-331):
+// blockIdx.y = step within the batch; every per-step pointer advances by its stride.  One launch set then serves `nb` time steps instead of one.
+struct StepBatch {
+    int64_t sX = 0, sU = 0, sLam = 0, sdR = 0, sR = 0, sGX = 0, sWc = 0;     // strides in doubles per step
+    unsigned long long snan = 0;                                              // increment of the NaN location code per step
+    double dt = 0.;                                                           // state[step].time advances by Δt
+};
+__device__ __forceinline__ void batch_state(DirectStateDev& st, const StepBatch& sb) {
+    const int64_t b = blockIdx.y;
+    st.X[0] += b * sb.sX; st.X[1] += b * sb.sX; st.X[2] += b * sb.sX; if (st.U0) st.U0 += b * sb.sU;
+}
 // state of one lane: values of X₀..X_{ND-1}, U₀ and the lane's two seeds (rotation dof l, translation dof l) at derivative order d (d<0: no seed)
 template <int ND> __device__ __forceinline__ void load_direct_state(const BeamGroupDev& g, const DirectStateDev& st, int64_t e, int d, int l,
                                                NumSD::TU (*Xu)[6], NumSD::TR (*Xv)[6], NumSD::TU* U) {
@@ -496,8 +507,9 @@ template <int ND> __device__ __forceinline__ void load_direct_state(const BeamGr
 }
 template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
-beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ Wc) {
+beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ Wc, StepBatch sb) {
     using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    batch_state(st, sb); Wc += (int64_t)blockIdx.y * sb.sWc;
     constexpr int NDJ = (ND >= 3) ? 2 : ND;            // derivative orders that need their own time-jet lanes: X₀ and X′ (X″ comes with X₀)
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = g.nele * 6;
@@ -522,8 +534,9 @@ beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ W
 template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
 beam_direct_b0_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, double* __restrict__ R, unsigned long long* nanflag,
-                      unsigned long long nanbase, const double* __restrict__ Wc) {
+                      unsigned long long nanbase, const double* __restrict__ Wc, StepBatch sb) {
     using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
+    batch_state(st, sb); Wc += (int64_t)blockIdx.y * sb.sWc; dR += (int64_t)blockIdx.y * sb.sdR; R += (int64_t)blockIdx.y * sb.sR; nanbase += blockIdx.y * sb.snan;
     const int NP = 12 * ND + (g.udof ? 3 : 0);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t / 6;
@@ -561,8 +574,9 @@ beam_direct_b0_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR
 template <int ND>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
 beam_direct_lin_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ dR, unsigned long long* nanflag, unsigned long long nanbase,
-                       const double* __restrict__ Wc) {
+                       const double* __restrict__ Wc, StepBatch sb) {
     using NV = NumVal; using V = SD<false, false>; using S = NumSD::TS;
+    batch_state(st, sb); Wc += (int64_t)blockIdx.y * sb.sWc; dR += (int64_t)blockIdx.y * sb.sdR; nanbase += blockIdx.y * sb.snan;
     const int NP = 12 * ND + (g.udof ? 3 : 0);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = g.nele * 6, nx = per * (ND - 1);
@@ -617,15 +631,16 @@ beam_direct_lin_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ d
 }
 // returns the number of kernels launched; Wc must hold ((6·ND·nele+31)/32)·32·MB_NCOT doubles when ND ≥ 2
 template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
-                                         unsigned long long nanbase, double* Wc, cudaStream_t s);
+                                         unsigned long long nanbase, double* Wc, cudaStream_t s, const StepBatch& sb, int nb);
 #define MB_INSTANTIATE_BEAM_DIRECT(ND_)                                                                                                       \
     template <> int launch_beam_direct<ND_>(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R,                           \
-                                            unsigned long long* nanflag, unsigned long long nanbase, double* Wc, cudaStream_t s) {            \
+                                            unsigned long long* nanflag, unsigned long long nanbase, double* Wc, cudaStream_t s,              \
+                                            const StepBatch& sb, int nb) {                                                                    \
         const int64_t per = g.nele * 6, nlin = per * (ND_ - 1) + (g.udof ? 2 * g.nele : 0);                                                  \
         int n = 1;                                                                                                                            \
-        if (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<(unsigned)((per * (ND_ >= 3 ? 2 : ND_) + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, Wc); ++n; } \
-        beam_direct_b0_kernel<ND_><<<(unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase, Wc);      \
-        if (nlin) { beam_direct_lin_kernel<ND_><<<(unsigned)((nlin + MB_BLOCK - 1) / MB_BLOCK), MB_BLOCK, 0, s>>>(g, st, dR, nanflag, nanbase, Wc); ++n; } \
+        if (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<dim3((unsigned)((per * (ND_ >= 3 ? 2 : ND_) + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, Wc, sb); ++n; } \
+        beam_direct_b0_kernel<ND_><<<dim3((unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase, Wc, sb);      \
+        if (nlin) { beam_direct_lin_kernel<ND_><<<dim3((unsigned)((nlin + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, dR, nanflag, nanbase, Wc, sb); ++n; } \
         return n;                                                                                                                             \
     }
 

@@ -14,11 +14,11 @@
 
 namespace mb {
 template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
-                                         unsigned long long nanbase, double* Wc, cudaStream_t s);
+                                         unsigned long long nanbase, double* Wc, cudaStream_t s, const StepBatch& sb, int nb);
 int launch_bar_direct(int ND, const BarGroupDev& g, const DirectStateDev& st, double t, double* dR, double* R, unsigned long long* nanflag,
-                      unsigned long long nanbase, cudaStream_t s);
+                      unsigned long long nanbase, cudaStream_t s, const StepBatch& sb, int nb);
 int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, const double* Lam, double lamscale, double* dR, double* R, double* GX,
-                       unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s);
+                       unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s, const StepBatch& sb, int nb);
 }
 
 namespace {
@@ -81,9 +81,10 @@ __device__ __forceinline__ int find_group(const uint32_t* pbase, int n, uint32_t
 // Measured and dropped: one thread per pair of non-zeros with the pair / split descriptors of kernels.cuh instead of the cstart → src walk, all loads issued
 // before the sums: 0.30 ms per step of 10⁵ elements either way — the strided loads of the transposed block and the 2·nd stores bound it, not the index chain.
 __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd,
-                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL) {
+                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL, int64_t sdR) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
+    dR += (int64_t)blockIdx.y * sdR; LX += (int64_t)blockIdx.y * nd * nnz; XL += (int64_t)blockIdx.y * nd * nnz;      // step batching: one grid row per time step
     double a[3] = {0., 0., 0.}, b[3] = {0., 0., 0.};
     for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
         const uint32_t id = src[s];
@@ -98,9 +99,10 @@ __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
 }
 // XU-type (rows X dofs, cols U dofs): L2[Λ,U][1,1];  UX-type: L2[U,Λ][1,1].  Only ∂0(U) enters the toolbox elements.
 __global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd, int transposed,
-                                 const double* __restrict__ dR, double* __restrict__ out) {
+                                 const double* __restrict__ dR, double* __restrict__ out, int64_t sdR) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
+    dR += (int64_t)blockIdx.y * sdR; out += (int64_t)blockIdx.y * nnz;
     const int pat = transposed ? P_UX : P_XU;
     double a = 0.;
     for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
@@ -117,18 +119,20 @@ __global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
     out[k] = a;
 }
 __global__ void gather_l1_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ R,
-                                 double* __restrict__ out) {
+                                 double* __restrict__ out, int64_t sR) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
+    R += (int64_t)blockIdx.y * sR; out += (int64_t)blockIdx.y * ndof;
     double acc = 0.;
     for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) acc += R[vsrc[s]];
     out[d] = acc;
 }
 // L1[X][der] of one step from the second-order element types (∂L/∂X_der = Λᵀ∂R/∂X_der): GX[q·nd+der], q = contributor entry (element dof)
 __global__ void gather_l1x_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ GX, int nd,
-                                  double* __restrict__ out) {
+                                  double* __restrict__ out, int64_t sGX) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
+    GX += (int64_t)blockIdx.y * sGX; out += (int64_t)blockIdx.y * nd * ndof;
     double acc[3] = {0., 0., 0.};
     for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) {
         const double* q = GX + (int64_t)vsrc[s] * nd;
@@ -462,7 +466,8 @@ struct DirectData {
     PairPat pat[4];
     uint32_t *vstart = nullptr, *vsrc = nullptr;
     DirGroups G;
-    double *dR = nullptr, *R = nullptr;                 // element outputs of one step
+    double *dR = nullptr, *R = nullptr;                 // element outputs of one BATCH of steps: [step in batch][ndr] / [nvec]
+    int64_t ndr = 0, nvec = 0, batch = 1;               // batch: time steps evaluated by one launch set (step batching for small models)
     double *X = nullptr, *U = nullptr, *Lam = nullptr;  // stored states [step][3][nX], [step][nU], [step][nX] (Λ enters decrementbig! only)
     double *scL = nullptr, *scX = nullptr, *scU = nullptr, *dvbuf = nullptr; int64_t dvlen = 0;
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;   // sparser! result
@@ -629,7 +634,19 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     }
     // buffers
     const int64_t ns = D->ehi - D->elo;
-    CK(dalloc(h, &D->dR, ndr)); CK(dalloc(h, &D->R, nvec));
+    // step batching: one launch set per `batch` time steps when the model is small (launch-bound otherwise: configs[4] has 100 beams × 4000 steps).
+    // Aim at ≥ 65 536 element-steps per launch, within 1 GiB of extra element-output space; MB_DIRECT_BATCH overrides.
+    {
+        int64_t nel = 0; for (const Group& g : h->groups) nel += g.nele;
+        int64_t want = nel > 0 ? (65536 + nel - 1) / nel : 1;
+        const int64_t bytes_per_step = 8 * (ndr + nvec + D->ngx * (OX + 1)) + 8 * 6 * (OX + 1) * nel * MB_NCOT;
+        const int64_t cap = std::max<int64_t>(1, (int64_t(1) << 30) / std::max<int64_t>(1, bytes_per_step));
+        want = std::min<int64_t>(std::min<int64_t>(want, cap), std::min<int64_t>(ns, 65535));
+        if (const char* eb = getenv("MB_DIRECT_BATCH")) want = std::max<int64_t>(1, std::min<int64_t>(atoll(eb), std::min<int64_t>(ns, 65535)));
+        D->batch = std::max<int64_t>(1, want); D->ndr = (ndr + 1) & ~int64_t(1); D->nvec = (nvec + 1) & ~int64_t(1);
+    }
+    CK(dalloc(h, &D->dR, D->ndr * D->batch)); CK(dalloc(h, &D->R, D->nvec * D->batch));
+    if (D->ngx > 0 && D->batch > 1) { dfree(h, D->GX); CK(dalloc(h, &D->GX, ((D->ngx * (OX + 1) + 1) & ~int64_t(1)) * D->batch)); }
     CK(dalloc(h, &D->X, ns * 3 * ndofX)); CK(dalloc(h, &D->U, ns * (ndofU > 0 ? ndofU : 1)));
     CK(dalloc(h, &D->Lam, ns * ndofX)); CK(cudaMemsetAsync(D->Lam, 0, (size_t)(ns * ndofX) * sizeof(double), st));
     CK(cudaMemsetAsync(D->X, 0, (size_t)(ns * 3 * ndofX) * sizeof(double), st));
@@ -704,11 +721,17 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
     DirectData* D = h->direct;
     cudaStream_t st = h->stream;
     const int nd = D->OX + 1;
-    for (int64_t s = s0; s < s1; ++s) {
+    // Step batching: the steps are independent (src/DirectXUA.jl:328-331), so `nb` of them share one launch set (grid row = step): element outputs of the
+    // batch lie [step][…] in dR / R / GX / Wc, the per-step blocks are contiguous over the stored steps anyway.  nb = 1 for large models (D->batch).
+    const int64_t ndr = D->ndr, nvec = D->nvec, ngxd = (D->ngx * nd + 1) & ~int64_t(1);      // per-step strides, even: the kernels' 16-byte stores keep their alignment
+    for (int64_t s = s0; s < s1; s += D->batch) {
+        const int nb = (int)std::min<int64_t>(D->batch, s1 - s);
         const int64_t k = s - D->elo;
         DirectStateDev sd;
         for (int d = 0; d < 3; ++d) sd.X[d] = D->X + (k * 3 + d) * D->nX;
         sd.U0 = D->U + k * D->nU;
+        StepBatch sb;
+        sb.sX = 3 * D->nX; sb.sU = D->nU; sb.sLam = D->nX; sb.sdR = ndr; sb.sR = nvec; sb.sGX = ngxd; sb.snan = nan_pack(1, 0); sb.dt = D->dt;
         for (size_t ig = 0; ig < h->groups.size(); ++ig) {
             const Group& g = h->groups[ig];
             if (g.nele == 0) continue;
@@ -718,26 +741,27 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
                 BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
                 for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
                 for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
-                h->launches += launch_bar_direct(nd, gd, sd, D->t0 + (double)s * D->dt, dR, R, h->nanflag, nanbase, st);
+                h->launches += launch_bar_direct(nd, gd, sd, D->t0 + (double)s * D->dt, dR, R, h->nanflag, nanbase, st, sb, nb);
                 continue;
             }
-            if (g.kind == G_HOST) {                // contributions uploaded by mb_direct_set_host_elements (zeros until then)
+            if (g.kind == G_HOST) {                // contributions uploaded by mb_direct_set_host_elements (zeros until then): [stored step][R | dR | GX]
                 const int64_t nR = g.nele * g.nx, ndR = nR * g.nx * nd, nG = nR * nd, per = nR + ndR + nG;
                 const double* src = (ig < D->hoststore.size() && D->hoststore[ig]) ? D->hoststore[ig] + k * per : nullptr;
+                double* gx = D->GX + D->G.gxbase[ig] * nd;
                 if (src) {
-                    CK(cudaMemcpyAsync(R, src, (size_t)nR * 8, cudaMemcpyDeviceToDevice, st));
-                    CK(cudaMemcpyAsync(dR, src + nR, (size_t)ndR * 8, cudaMemcpyDeviceToDevice, st));
-                    CK(cudaMemcpyAsync(D->GX + D->G.gxbase[ig] * nd, src + nR + ndR, (size_t)nG * 8, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpy2DAsync(R, (size_t)nvec * 8, src, (size_t)per * 8, (size_t)nR * 8, nb, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpy2DAsync(dR, (size_t)ndr * 8, src + nR, (size_t)per * 8, (size_t)ndR * 8, nb, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpy2DAsync(gx, (size_t)ngxd * 8, src + nR + ndR, (size_t)per * 8, (size_t)nG * 8, nb, cudaMemcpyDeviceToDevice, st));
                 } else {
-                    CK(cudaMemsetAsync(R, 0, (size_t)nR * 8, st)); CK(cudaMemsetAsync(dR, 0, (size_t)ndR * 8, st));
-                    CK(cudaMemsetAsync(D->GX + D->G.gxbase[ig] * nd, 0, (size_t)nG * 8, st));
+                    CK(cudaMemset2DAsync(R, (size_t)nvec * 8, 0, (size_t)nR * 8, nb, st)); CK(cudaMemset2DAsync(dR, (size_t)ndr * 8, 0, (size_t)ndR * 8, nb, st));
+                    CK(cudaMemset2DAsync(gx, (size_t)ngxd * 8, 0, (size_t)nG * 8, nb, st));
                 }
                 continue;
             }
             if (g.kind == G_SOIL) {
                 SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
                 for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
-                h->launches += launch_soil_direct(nd, gd, sd, D->Lam + k * D->nX, D->lamscale, dR, R, D->GX + D->G.gxbase[ig] * nd, h->nanflag, nanbase, st);
+                h->launches += launch_soil_direct(nd, gd, sd, D->Lam + k * D->nX, D->lamscale, dR, R, D->GX + D->G.gxbase[ig] * nd, h->nanflag, nanbase, st, sb, nb);
                 continue;
             }
             BeamGroupDev gd;
@@ -746,24 +770,24 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
             for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
             double* Wc = nullptr;
             if (nd >= 2) {                         // cotangent workspace of the two-phase evaluation, shared with SweepX and sized lazily
-                const int64_t need = ((g.nele * 6 * nd + 31) / 32) * 32 * MB_NCOT;
+                const int64_t one = ((g.nele * 6 * nd + 31) / 32) * 32 * MB_NCOT, need = one * D->batch;
                 if (h->Wc_len < need) { if (h->Wc) dfree(h, h->Wc); h->Wc = nullptr; h->Wc_len = 0; CK(dalloc(h, &h->Wc, need)); h->Wc_len = need; }
-                Wc = h->Wc;
+                Wc = h->Wc; sb.sWc = one;
             }
-            if (nd == 1) h->launches += launch_beam_direct<1>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
-            else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
-            else h->launches += launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st);
+            if (nd == 1) h->launches += launch_beam_direct<1>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
+            else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
+            else h->launches += launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
         }
         if (D->elements_only) continue;
         const PairPat& XX = D->pat[P_XX];
-        if (XX.nnz) { gather_xx_kernel<<<nblk(XX.nnz, 256), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz); h->launches++; }
+        if (XX.nnz) { gather_xx_kernel<<<dim3(nblk(XX.nnz, 256), nb), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz, ndr); h->launches++; }
         const PairPat& XU = D->pat[P_XU];
-        if (XU.nnz) { gather_xu_kernel<<<nblk(XU.nnz, 256), 256, 0, st>>>(XU.nnz, XU.cstart, XU.src, D->G, nd, 0, D->dR, D->LU + k * XU.nnz); h->launches++; }
+        if (XU.nnz) { gather_xu_kernel<<<dim3(nblk(XU.nnz, 256), nb), 256, 0, st>>>(XU.nnz, XU.cstart, XU.src, D->G, nd, 0, D->dR, D->LU + k * XU.nnz, ndr); h->launches++; }
         const PairPat& UX = D->pat[P_UX];
-        if (UX.nnz) { gather_xu_kernel<<<nblk(UX.nnz, 256), 256, 0, st>>>(UX.nnz, UX.cstart, UX.src, D->G, nd, 1, D->dR, D->UL + k * UX.nnz); h->launches++; }
-        gather_l1_kernel<<<nblk(D->nX, 256), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX);
+        if (UX.nnz) { gather_xu_kernel<<<dim3(nblk(UX.nnz, 256), nb), 256, 0, st>>>(UX.nnz, UX.cstart, UX.src, D->G, nd, 1, D->dR, D->UL + k * UX.nnz, ndr); h->launches++; }
+        gather_l1_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX, nvec);
         h->launches++;
-        if (D->ngx) { gather_l1x_kernel<<<nblk(D->nX, 256), 256, 0, st>>>(D->nX, D->vstart2, D->vsrc2, D->GX, nd, D->L1X + k * nd * D->nX); h->launches++; }
+        if (D->ngx) { gather_l1x_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart2, D->vsrc2, D->GX, nd, D->L1X + k * nd * D->nX, ngxd); h->launches++; }
     }
     return MB_OK;
 }
