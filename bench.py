@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-directxua", action="store_true")        # skip the configs[3] block of the default line
     ap.add_argument("--dx-passes", type=int, default=2)           # timed passes of the configs[3] block (after 1 warm-up pass)
+    ap.add_argument("--scr-nstep", type=int, default=4000)        # scr: time steps of BASELINE.json configs[4]
     return ap.parse_args()
 
 
@@ -597,6 +598,100 @@ def run_directxua_weak(args, rank, world, local, comm):
     return line
 
 
+def run_scr(args, rank, world, local, comm, block=False):
+    """BASELINE.json configs[4]: DirectXUA{2,0,0} assemblebig! of the SCR riser (examples/DynamicBeamAnalysis.jl:62-135: 100 EulerBeam3D{Udof} + 61 SoilContact on
+    the device, Hold / DofConstraint / DofLoad / U-costs host-evaluated) over `--scr-nstep` time steps (4000), time-sharded over the ranks with locally evaluated
+    halos.  The whole series fits one handle per rank (≈ 5·10⁴ Lvv non-zeros per step); the steps share launch sets (step batching).  One bench step = one pass."""
+    import muscade_b200 as mb
+    OX, OU, nstep, dt, t0, su = 2, 0, args.scr_nstep, 0.1, 0., 50.
+    model, node_lists, weights = mb.examples.scr_riser(mb, udof=True)
+    unodes = np.concatenate([et.nodID[:, 2] for et in model.ele if et.ElType.__name__ == "EulerBeam3D"])
+    for f in ("t1", "t2", "t3"):
+        mb.addelement(model, mb.SingleDofCost, unodes[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / su) ** 2)
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=30., t2=30., t3=30.)), Λscale=1e3)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU = model.getndof("X"), model.getndof("U")
+    nel_dev = sum(et.nele for et in model.ele if et.ElType.kind in ("eulerbeam3d", "soilcontact", "bar3d"))
+    if nstep % world or nstep // world < 6:
+        raise ValueError("the number of time steps must be a multiple of the number of ranks, at least 6 each")
+    lo, hi = rank * nstep // world, (rank + 1) * nstep // world
+    import torch
+    torch.cuda.set_device(local)
+    eng = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, lo, hi, device=local, t0=t0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)          # CUDA events of the timed region are recorded on this stream
+    a, b = eng.stored_range()
+    B = 16                                            # bank of synthetic states (amplitudes of the parity test), step s reads bank[s mod B]
+    bankX = [[mb.synthetic.uniform_pm1(10 + 3 * k + d, nX) * (0.2 if d == 0 else 0.3) for d in range(3)] for k in range(B)]
+    bankU = [20. * mb.synthetic.uniform_pm1(99 + k, nU) for k in range(B)]
+    bankL = [mb.synthetic.uniform_pm1(500 + k, nX) for k in range(B)]
+
+    def upload():
+        for s in range(a, b):
+            eng.set_state(s, bankX[s % B], bankU[s % B])
+    upload()
+    for s in range(a, b):                             # Λ and the host-evaluated types: the host's share of an iteration, set once (not device work)
+        eng.set_lambda(s, bankL[s % B])
+    for s in range(a, min(b, a + B)):                 # host contributions of the first B steps, reused round-robin through the bank (same states ⇒ same values up to t)
+        eng.set_host_cost(s, *mb.directxua.host_costs(eng, s, bankX[s % B][0], bankU[s % B], t0 + s * dt)[:4])
+        mb.directxua.host_elements(eng, s, bankX[s % B], bankL[s % B], t0 + s * dt, model.scaleΛ)
+
+    def barrier():
+        eng.sync(); torch.cuda.synchronize(); comm.barrier()
+
+    steps = args.dx_passes if block else args.steps
+    warm = 1 if block else args.warmup
+    for _ in range(warm):
+        eng.direct_assemble()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local) if rank == 0 and not block else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        eng.direct_assemble()                         # every stored step (owned + the 2+2 halo steps) evaluated, owned Lvv columns / Lv rows built
+    ev1.record(); torch.cuda.synchronize()
+    step_ms = comm.max(ev0.elapsed_time(ev1) / steps)
+    a_ms, b_ms = eng.direct_time(reps=1)              # breakdown of the owned steps (CUDA events inside the engine)
+    barrier()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    el_ms = eng.last_element_ms
+    e2e = None
+    if not args.no_e2e and not block:
+        Lvh = np.empty(eng.ncol)
+        for arrs in bankX:
+            for x in arrs: eng.pin(x)
+        for u in bankU: eng.pin(u)
+        eng.pin(Lvh)
+
+        def one():
+            upload(); eng.direct_assemble(Lv=Lvh)
+        one(); barrier()
+        t1 = time.perf_counter(); one(); eng.sync()
+        e2e_ms = comm.max(1e3 * (time.perf_counter() - t1))
+        e2e = {"value": nel_dev * nstep / (e2e_ms * 1e-3), "unit": "element-step assemblies/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int((b - a) * 8 * (3 * nX + nU)), "d2h_bytes_per_step": int(8 * eng.ncol),
+               "note": "per rank: mb_direct_set_state for every stored step from pinned host memory, mb_direct_assemble with a host Lv; Lvv stays in HBM"}
+    line = None
+    if rank == 0:
+        nown = hi - lo
+        line = {"metric": "element-step assemblies/s (DirectXUA{2,0,0} assemblebig!, SCR riser: EulerBeam3D{Udof} + SoilContact)", "value": nel_dev * nstep / (step_ms * 1e-3),
+                "unit": "element-step assemblies/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": step_ms, "ms_per_pass": step_ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "DirectXUA{2,0,0} XU-optimisation set-up of the SCR riser (BASELINE.json configs[4]; IA = 0): %d device elements per step (100 EulerBeam3D{Udof} in "
+                                       "5 types + 61 SoilContact), 107 host-evaluated elements (Hold, DofConstraint, DofLoad) and 300 U-costs merged, x %d time steps, "
+                                       "%d per GPU, step batching" % (nel_dev, nstep, nown),
+                           "device_elements_per_step": nel_dev, "nstep": nstep, "steps_per_gpu": nown, "lvv_nnz_per_gpu": int(eng.nnzbig), "ndofX": nX, "ndofU": nU,
+                           "l2": "per-step blocks and Lvv (%.1f GB per GPU) larger than L2" % (16e-9 * eng.nnzbig)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "breakdown_ms": {"elements_and_step_blocks": a_ms, "lvv_build": b_ms, "element_kernels": el_ms}}
+        if block:
+            for k in ("e2e", "higher_is_better", "vs_baseline", "dtype", "data", "clocks"):
+                line.pop(k, None)
+    eng.close()
+    return line
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -615,6 +710,8 @@ def main():
         line = run_directxua(args, rank, world, local, comm)
     elif args.workload == "directxua_weak":
         line = run_directxua_weak(args, rank, world, local, comm)
+    elif args.workload == "scr":
+        line = run_scr(args, rank, world, local, comm)
     else:
         line = run_sweepx(args, rank, world, local, comm)
         if not args.no_directxua and args.nele is None and args.ox == 0:
@@ -622,9 +719,12 @@ def main():
             dx = run_directxua(args, rank, world, local, comm, steps=args.dx_passes, warmup=1, block=True)
             # BASELINE.json configs[1]: SweepX{2} Newmark-β assemble!{:iter} on 1e6 elements per GPU (the per-step assembly of a 1000-step run)
             nw = run_sweepx(args, rank, world, local, comm, OX=2, N=1e6, steps=50, block=True)
+            # BASELINE.json configs[4]: DirectXUA on the SCR riser, 4000 time steps (few elements, many steps: step batching)
+            sc = run_scr(args, rank, world, local, comm, block=True)
             if line is not None:
                 line["directxua"] = dx
                 line["newmark"] = nw
+                line["scr"] = sc
     if rank == 0 and line is not None:
         line["comm"] = {"backend": "NCCL inside libmuscade_b200.so (mb_comm_init, dlopen libnccl.so.2)" if world > 1 else "none", "ranks": world,
                         "nccl_version": comm.eng.comm_info()[2] if comm.eng is not None else None,
