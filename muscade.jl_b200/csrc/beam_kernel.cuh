@@ -260,10 +260,15 @@ struct PacksShuffle {
 // Ke[i + 12j] = scale_i·∂R_i/∂X_j·scale_j (the seed carries scale_cv), the six translation rows of that column transposed into row cv of the translation
 // columns (symmetric tangent), the translation rows of translation column cu = cv − 3 (±G/4), and, from lane 0, the residual.  Same values and
 // positions as beam_static_sym_store; rows of the active / passive node are addressed, not selected.
-struct ApStore {
+// FUSE: `ke` is the element's 144 slots of the warp's SHARED-MEMORY tile (plain stores, same positions); the warp's epilogue sums them into nzval (kernels.cuh,
+// "fused epilogue") and copies to Ke only what other warps contribute to.
+template <bool FUSE> struct ApStoreT {
     double* ke; double* re; const double* sc; int lane; bool live, al, bad;
-    __device__ __forceinline__ void put(int k, double v) { bad |= (v != v); if (live) __stcs(ke + k, v); }
-    __device__ __forceinline__ void put2(int k, double v0, double v1) { bad |= (v0 != v0) | (v1 != v1); if (live) store_pair_cs(ke + k, v0, v1, al); }
+    __device__ __forceinline__ void put(int k, double v) { bad |= (v != v); if (live) { if constexpr (FUSE) ke[k] = v; else __stcs(ke + k, v); } }
+    __device__ __forceinline__ void put2(int k, double v0, double v1) {
+        bad |= (v0 != v0) | (v1 != v1);
+        if (live) { if constexpr (FUSE) store_pair(ke + k, v0, v1, true); else store_pair_cs(ke + k, v0, v1, al); }
+    }
     __device__ __forceinline__ void tt(const double* Gc) {
         const bool n1 = lane < 3;
         const int cu = n1 ? lane : lane + 3;
@@ -297,15 +302,31 @@ struct ApStore {
         }
     }
 };
-template <int MINB, bool SHARE>
-__global__ void __launch_bounds__(MB_BLOCK, MINB)
-beam_static_ap_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase) {
-    using V = SD<false, false>; using S = SD<true, false>;
+// Fused epilogue (FUSE): a warp holds FIVE whole consecutive elements.  Their 720 tangent entries go to a shared-memory tile instead of Ke; after the sweep the warp walks
+// its range of non-zeros [wbase, wbase + wlen) with its PATTERN (kernels.cuh, "fused epilogue": per non-zero the one or two tile entries that make it up, built at prepare
+// from the segmented reduction's maps): such a non-zero is (0 + first) + second — the bit pattern of gather_one — and written to nzval, final; the entries of the other
+// non-zeros (interface nodes shared with another warp, another group or type) are copied to Ke for gather_list_kernel.  Header and pattern arrive by cp.async while the sweep
+// runs.  On a chain numbered along its axis 9/10 of the entries never reach HBM as Ke.
+constexpr int MB_EPW = 5;                 // elements per warp
+constexpr int MB_TILE = MB_EPW * 144;     // tile entries per warp (5.6 KB)
+constexpr int MB_FUSE_RANGE = 768;        // non-zeros a warp walks at most (a chain numbered along its axis needs 648); what lies beyond stays with the segmented reduction
+constexpr int MB_PAT_WORDS = MB_FUSE_RANGE + MB_TILE / 2;      // largest pattern, 32-bit words (multiple of 4); MB_FUSE_RANGE is a multiple of 256
+constexpr uint32_t MB_PAT_NOTMINE = (uint32_t)(MB_TILE * 8) * 0x10001u;      // pattern word of a non-zero that is not this warp's: both byte offsets at the zero slot
+struct FuseDev {
+    const int4* whdr; const uint32_t* cpat; double* nzval;      // per warp of the group (wbase, wlen | nun << 16, pattern offset / 4 words, 0); the patterns; the CSC values
+    int64_t warp0;                                              // first warp of this launch within the group
+};
+struct __align__(16) FuseSmem { double tile[MB_TILE + 2]; uint32_t pat[MB_PAT_WORDS]; int4 hdr; };      // tile[MB_TILE] = 0: the absent second contributor
+template <bool SHARE, bool FUSE>
+__device__ __forceinline__ void beam_static_ap_body(const BeamGroupDev& g, const StateDev& st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase, const FuseDev& fz) {
+    static_assert(!FUSE || SHARE, "the fused epilogue needs whole elements per warp");
+    using V = SD<false, false>;
+    __shared__ FuseSmem fsm[FUSE ? MB_BLOCK / 32 : 1];
     int64_t e; int lane; bool live = true;
     int sub = 0, base = 0;
+    const int wl = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (SHARE) {
-        const int wl = threadIdx.x & 31;
-        const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         sub = wl % 6; base = wl - sub;
         e = warp * 5 + wl / 6; lane = sub;
         if (wl >= 30) { e = warp * 5 + 4; live = false; base = 24; }          // idle lanes shadow the last element of the warp (no stores)
@@ -314,6 +335,18 @@ beam_static_ap_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, doub
         const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         e = t / 6; lane = (int)(t - e * 6);
         if (e >= g.nele) return;
+    }
+    if constexpr (FUSE) {
+        if (warp * 5 < g.nele) {
+            FuseSmem& F = fsm[threadIdx.x >> 5];
+            const int4 hd = __ldg(fz.whdr + fz.warp0 + warp);
+            if (wl == 0) { F.hdr = hd; F.tile[MB_TILE] = 0.; }
+            const int n4 = ((((hd.y & 0xFFFF) + 255) & ~255) + ((hd.y >> 16) + 1) / 2 + 3) / 4;
+            const uint32_t* gp = fz.cpat + (int64_t)hd.z * 4;
+            const unsigned sp = (unsigned)__cvta_generic_to_shared(F.pat);
+            for (int i = wl; i < n4; i += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sp + 16u * i), "l"(gp + 4 * i));
+            asm volatile("cp.async.commit_group;");
+        }
     }
     BeamGeo geo;
     load_geo(g.geo + e * 16, geo);
@@ -329,14 +362,58 @@ beam_static_ap_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, doub
 #pragma unroll
     for (int i = 0; i < 3; ++i) U[i].v = (g.udof && st.U0) ? st.U0[g.idxU[e * 3 + i]] : 0.;
     const int cv = ((lane < 3) ? lane : lane + 3) + 3;
-    double* ke = Ke + e * 144;
-    ApStore out;
+    double* ke = FUSE ? fsm[FUSE ? (threadIdx.x >> 5) : 0].tile + (e - warp * 5) * 144 : Ke + e * 144;
+    ApStoreT<FUSE> out;
     out.ke = ke; out.re = Re + e * 12; out.sc = g.scaleX; out.lane = lane; out.live = live; out.al = (reinterpret_cast<uintptr_t>(ke) & 15) == 0; out.bad = false;
     if (SHARE) { PacksShuffle ps; ps.sub = sub; ps.base = base; beam_static_ap_lane(geo, m, xu, xv, g.scaleX[cv], lane, g.udof != 0, U, ps, out); }
     else beam_static_ap_lane(geo, m, xu, xv, g.scaleX[cv], lane, g.udof != 0, U, PacksLocal(), out);
     if (out.bad && live) atomicMin(nanflag, nanbase + (unsigned long long)e);
+    if constexpr (FUSE) {
+        // everything the epilogue needs is re-derived here (volatile reads of the special registers: nothing of it stays live across the sweep)
+        unsigned bx, tx;
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tx));
+        const int el = (int)(tx & 31u);
+        const int64_t wk = ((int64_t)bx * MB_BLOCK + tx) >> 5;
+        if (wk * 5 >= g.nele) return;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        const FuseSmem& F = fsm[tx >> 5];
+        const int4 hd = F.hdr;
+        const int tlen = hd.y & 0xFFFF, nun = hd.y >> 16;
+        double* nz = fz.nzval + hd.x;
+        // branch-free, eight non-zeros per lane at a time: all pattern words, then all tile entries, then the sums — the loads of a chunk are in flight together
+        // (two warps per scheduler do not hide a dependent LDS → LDS → DADD → STG chain per non-zero).  An absent second contributor points at tile[MB_TILE] = 0:
+        // 0 + first is never −0, so adding +0 leaves its bits alone.
+        const char* tb = reinterpret_cast<const char*>(F.tile);
+        for (int s0 = 0; s0 < tlen; s0 += 256) {               // the pattern is padded to whole chunks with MB_PAT_NOTMINE: no bounds checks
+            uint32_t d[8]; double a[8], b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = F.pat[s0 + 32 * j + el];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = *reinterpret_cast<const double*>(tb + (d[j] & 0xFFFFu)); b[j] = *reinterpret_cast<const double*>(tb + (d[j] >> 16)); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const double acc = (0. + a[j]) + b[j]; if (d[j] != MB_PAT_NOTMINE) nz[s0 + 32 * j + el] = acc; }
+        }
+        const uint16_t* ul = reinterpret_cast<const uint16_t*>(F.pat + ((tlen + 255) & ~255));
+        double* kw = Ke + wk * (int64_t)MB_TILE;
+        for (int i0 = 0; i0 < nun; i0 += 128) {
+            int q[4]; double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int i = i0 + 32 * j + el; q[j] = (i < nun) ? (int)ul[i] : -1; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = F.tile[max(q[j], 0)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (q[j] >= 0) __stcs(kw + q[j], v[j]);
+        }
+    }
 }
 
+template <int MINB, bool SHARE, bool FUSE = false>
+__global__ void __launch_bounds__(MB_BLOCK, MINB)
+beam_static_ap_kernel(BeamGroupDev g, StateDev st, double* __restrict__ Ke, double* __restrict__ Re, unsigned long long* nanflag, unsigned long long nanbase, FuseDev fz) {
+    beam_static_ap_body<SHARE, FUSE>(g, st, Ke, Re, nanflag, nanbase, fz);
+}
 // :step mission only (src/SweepX.jl:46-57,69-78): the extra seed direction δr carries the Newmark predictor
 //   vx′ = x′ + a₁δX + a·δr,  vx″ = x″ + b₁δX + b·δr,  a = a₂x′+a₃x″,  b = b₂x′+b₃x″ ;   Rp = ∂(Lλ)/∂r is subtracted from the rhs.
 // One thread per element, dense one-direction dual.
@@ -648,6 +725,7 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
 struct BeamLaunch {
     BeamGroupDev g; StateDev st; NewmarkDev nm;
     double *Ke, *Re, *Rp; unsigned long long* nanflag; unsigned long long nanbase; int W; cudaStream_t stream; double* Wc;
+    FuseDev fz{nullptr, nullptr, nullptr, 0};      // fused epilogue of the static kernel (statics, static_sym = 3): whdr = nullptr → off
     int static_sym = 3;     // statics: 3 = active/passive sweep with shuffle-shared packs (default), 2 = the same with local packs, 1 = symmetric-tangent kernel, 0 = two-direction SD kernel (A/B measurements)
     int nsm = 148;
 };
@@ -658,11 +736,18 @@ template <> struct StaticSymLaunch<1> {
         if (a.static_sym == 3 || a.static_sym == 13 || a.static_sym == 14) {             // active/passive sweep, packs shared by shuffles: 5 whole elements per warp
             const int64_t nw = (a.g.nele + 4) / 5;
             const unsigned nbw = (unsigned)((nw * 32 + MB_BLOCK - 1) / MB_BLOCK);
-            if (a.static_sym == 13) beam_static_ap_kernel<3, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
-            else if (a.static_sym == 14) beam_static_ap_kernel<4, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
-            else beam_static_ap_kernel<MB_AP_MINB, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+            const FuseDev nofz{nullptr, nullptr, nullptr, 0};
+            if (a.static_sym == 13) beam_static_ap_kernel<3, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, nofz);
+            else if (a.static_sym == 14) beam_static_ap_kernel<4, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, nofz);
+            else if (a.fz.whdr) {
+                // 40 KB of tiles and patterns per CTA, two CTAs per SM (register-bound): ask for a shared-memory carve-out that holds both
+                static bool carved = false;
+                if (!carved) { cudaFuncSetAttribute(beam_static_ap_kernel<MB_AP_MINB, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 40); carved = true; }
+                beam_static_ap_kernel<MB_AP_MINB, true, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, a.fz);
+            }
+            else beam_static_ap_kernel<MB_AP_MINB, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, nofz);
         } else if (a.static_sym == 2)
-            beam_static_ap_kernel<MB_AP_MINB, false><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
+            beam_static_ap_kernel<MB_AP_MINB, false><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, FuseDev{nullptr, nullptr, nullptr, 0});
         else
             beam_static_sym_kernel<MB_SYM_MINB><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase);
     }

@@ -68,10 +68,22 @@ __device__ __forceinline__ void gather_pair(const uint32_t* __restrict__ cstart,
         b = 0. + vb; if (x.w != MB_NONE) b += wb;
     } else { a = gather_one(cstart, src, Ke, k); b = gather_one(cstart, src, Ke, k + 1); }
 }
+// wflag (or nullptr): one byte per non-zero, 1 = already final in nzval — written by the element kernel's fused epilogue (beam_static_ap_kernel<…,FUSE>),
+// whose warp held every contributor of that non-zero; such non-zeros are neither read nor written here.
 static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, const uint32_t* __restrict__ pdesc,
-                                 const uint4* __restrict__ xdesc, const double* __restrict__ Ke, double* __restrict__ nzval) {
+                                 const uint4* __restrict__ xdesc, const double* __restrict__ Ke, double* __restrict__ nzval, const uint8_t* __restrict__ wflag) {
     const int64_t k0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (k0 >= nnz) return;
+    uint32_t fl = 0;
+    if (wflag) {
+        if (k0 + 4 <= nnz) fl = __ldg(reinterpret_cast<const uint32_t*>(wflag + k0));
+        else for (int64_t k = k0; k < nnz; ++k) fl |= (uint32_t)wflag[k] << (8 * (k - k0));
+        if (fl == 0x01010101u) return;
+    }
+    if (fl != 0) {                                   // some of the four are final already: the others one by one
+        for (int64_t k = k0; k < nnz && k < k0 + 4; ++k) if (!((fl >> (8 * (k - k0))) & 1u)) nzval[k] = gather_one(cstart, src, Ke, k);
+        return;
+    }
     if (k0 + 4 <= nnz) {
         const uint4 d = __ldg(reinterpret_cast<const uint4*>(pdesc + k0));          // (b0,b1) of the pairs (k0,k0+1) and (k0+2,k0+3)
         const bool r0 = d.x != MB_NONE, r1 = d.z != MB_NONE, t0 = r0 && d.y != MB_NONE, t1 = r1 && d.w != MB_NONE;
@@ -90,6 +102,150 @@ static __global__ void gather_nz_kernel(int64_t nnz, const uint32_t* __restrict_
         for (int64_t k = k0; k < nnz; ++k) nzval[k] = gather_one(cstart, src, Ke, k);
     }
 }
+// ---------------------------------------------------------------------------------------------- fused epilogue: which non-zeros a warp can finish itself
+// The static element kernel gives a warp FIVE whole consecutive elements and keeps their 720 tangent entries in a shared-memory tile (beam_kernel.cuh).  A non-zero whose
+// contributors (one or two) all lie in one such tile is summed there, in element order, and written to nzval by the element kernel; the others go through Ke and
+// gather_list_kernel.  Built once at prepare, per beam group and per warp:
+//   header  (wbase, wlen | nun << 16, offset of its PATTERN in 16-byte units, 0)
+//   pattern wlen words, one per non-zero of the range [wbase, wbase + wlen): BYTE offsets (o0 | o1 << 16) of its contributors in the tile, o1 = 8·MB_TILE (a zero slot) = none, both there = not this warp's; padded to whole chunks of 256;
+//           then nun 16-bit tile entries that are NOT finished here (ascending) and are copied to Ke.
+// Patterns are relative to the tile and to wbase, so on a regular mesh they repeat: a warp whose pattern equals its predecessor's points to the same copy
+// (a chain numbered along its axis keeps three patterns in all, resident in L2).  The kernel pulls header and pattern into shared memory with cp.async at entry —
+// no register is held across the sweep for the epilogue, and no load of the epilogue waits on HBM.
+__device__ __forceinline__ bool fuse_owned(int64_t k, uint32_t q0, uint32_t q1, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src) {
+    const uint32_t c0 = cstart[k], c1 = cstart[k + 1];
+    if (c1 == c0 || c1 - c0 > 2) return false;
+    for (uint32_t c = c0; c < c1; ++c) { const uint32_t q = src[c]; if (q < q0 || q >= q1) return false; }
+    return true;
+}
+static __global__ void fuse_mark_kernel(int64_t npair_g, uint32_t pair_base, const int32_t* __restrict__ asm2, const uint32_t* __restrict__ cstart,
+                                        const uint32_t* __restrict__ src, int32_t* __restrict__ wbase) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npair_g) return;
+    const int64_t k = (int64_t)asm2[pair_base + q] - 1;
+    if (k < 0) return;
+    const int64_t w = q / MB_TILE;
+    const uint32_t q0 = pair_base + (uint32_t)(w * MB_TILE), q1 = (uint32_t)min((int64_t)q0 + MB_TILE, (int64_t)pair_base + npair_g);
+    if (fuse_owned(k, q0, q1, cstart, src)) atomicMin(&wbase[w], (int32_t)k);
+}
+static __global__ void fuse_dest_kernel(int64_t npair_g, uint32_t pair_base, const int32_t* __restrict__ asm2, const uint32_t* __restrict__ cstart,
+                                        const uint32_t* __restrict__ src, const int32_t* __restrict__ wbase, int32_t* __restrict__ wlen, uint32_t* __restrict__ ebits,
+                                        uint8_t* __restrict__ wflag) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npair_g) return;
+    const int64_t k = (int64_t)asm2[pair_base + q] - 1, w = q / MB_TILE;
+    const int i = (int)(q - w * MB_TILE);
+    bool done = (k < 0);                              // an entry that goes nowhere needs no store either
+    if (!done) {
+        const uint32_t q0 = pair_base + (uint32_t)(w * MB_TILE), q1 = (uint32_t)min((int64_t)q0 + MB_TILE, (int64_t)pair_base + npair_g);
+        const int64_t slot = k - wbase[w];
+        if (fuse_owned(k, q0, q1, cstart, src) && slot < MB_FUSE_RANGE) {       // the same decision for every contributor of k: they share the warp, hence wbase
+            done = true; wflag[k] = 1; atomicMax(&wlen[w], (int32_t)slot + 1);
+        }
+    }
+    if (done) atomicOr(&ebits[w * 23 + (i >> 5)], 1u << (i & 31));
+}
+// words of warp w's pattern (multiple of 4) and its count of unfinished entries
+static __global__ void fuse_size_kernel(int64_t nw, int64_t npair_g, const int32_t* __restrict__ wlen, const uint32_t* __restrict__ ebits, int32_t* __restrict__ wnun, int64_t* __restrict__ psz) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nw) return;
+    const int nq = (int)min((int64_t)MB_TILE, npair_g - w * MB_TILE);
+    int done = 0;
+    for (int j = 0; j < 23; ++j) done += __popc(ebits[w * 23 + j]);
+    const int nun = nq - done;
+    wnun[w] = nun;
+    psz[w] = ((((wlen[w] + 255) & ~255) + (nun + 1) / 2 + 3) / 4) * 4;
+}
+// one CUDA warp per element-kernel warp: writes its pattern at pat + poff[w]
+static __global__ void fuse_fill_kernel(int64_t nw, int64_t npair_g, uint32_t pair_base, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src,
+                                        const int32_t* __restrict__ wbase, const int32_t* __restrict__ wlen, const uint32_t* __restrict__ ebits,
+                                        const int64_t* __restrict__ poff, const int64_t* __restrict__ psz, uint32_t* __restrict__ pat) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31;
+    if (w >= nw) return;
+    uint32_t* P = pat + poff[w];
+    const int n = wlen[w];
+    const int64_t kb = wbase[w];
+    const uint32_t q0 = pair_base + (uint32_t)(w * MB_TILE), q1 = (uint32_t)min((int64_t)q0 + MB_TILE, (int64_t)pair_base + npair_g);
+    for (int sl = l; sl < n; sl += 32) {
+        const int64_t k = kb + sl;
+        uint32_t d = MB_PAT_NOTMINE;
+        if (fuse_owned(k, q0, q1, cstart, src)) {
+            const uint32_t c0 = cstart[k], c1 = cstart[k + 1];
+            d = 8u * ((src[c0] - q0) | ((c1 - c0 == 2 ? src[c0 + 1] - q0 : (uint32_t)MB_TILE) << 16));
+        }
+        P[sl] = d;
+    }
+    for (int64_t i = n + l; i < psz[w]; i += 32) P[i] = MB_PAT_NOTMINE;        // chunk padding (read by the kernel), list area and tail: defined, so that equal patterns compare equal
+    __syncwarp();
+    uint16_t* U = reinterpret_cast<uint16_t*>(P + ((n + 255) & ~255));
+    const int nq = (int)(q1 - q0);
+    int base = 0;
+    for (int j = 0; j < 23; ++j) {
+        const int i = j * 32 + l;
+        const bool un = i < nq && !((ebits[w * 23 + j] >> l) & 1u);
+        const unsigned m = __ballot_sync(0xffffffffu, un);
+        if (un) U[base + __popc(m & ((1u << l) - 1u))] = (uint16_t)i;
+        base += __popc(m);
+    }
+}
+// eq[w] = 0 where warp w's header sizes or pattern differ from warp w−1's (w is the head of a run), else 1; hd[w] = w or 0 for the max-scan that finds the run's head
+static __global__ void fuse_eq_kernel(int64_t nw, const int32_t* __restrict__ wlen, const int32_t* __restrict__ wnun, const int64_t* __restrict__ poff, const int64_t* __restrict__ psz,
+                                      const uint32_t* __restrict__ pat, int64_t* __restrict__ hd, int64_t* __restrict__ hsz) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31;
+    if (w >= nw) return;
+    bool same = w > 0 && wlen[w] == wlen[w - 1] && wnun[w] == wnun[w - 1] && psz[w] == psz[w - 1];
+    if (same) {
+        const uint32_t *A = pat + poff[w], *B = pat + poff[w - 1];
+        bool ok = true;
+        for (int64_t i = l; i < psz[w]; i += 32) ok &= (A[i] == B[i]);
+        same = __all_sync(0xffffffffu, ok);
+    }
+    if (l == 0) { hd[w] = same ? 0 : w; hsz[w] = same ? 0 : psz[w]; }
+}
+static __global__ void fuse_compact_kernel(int64_t nw, const int64_t* __restrict__ head, const int64_t* __restrict__ poff, const int64_t* __restrict__ psz, const int64_t* __restrict__ noff,
+                                           const uint32_t* __restrict__ pat, uint32_t* __restrict__ cpat, const int32_t* __restrict__ wbase, const int32_t* __restrict__ wlen,
+                                           const int32_t* __restrict__ wnun, int4* __restrict__ whdr) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31;
+    if (w >= nw) return;
+    const int64_t hw = head[w];
+    if (hw == w) for (int64_t i = l; i < psz[w]; i += 32) cpat[noff[w] + i] = pat[poff[w] + i];
+    if (l == 0) whdr[w] = make_int4(wbase[w], wlen[w] | (wnun[w] << 16), (int)(noff[hw] / 4), 0);
+}
+struct MaxI64 { __host__ __device__ int64_t operator()(int64_t a, int64_t b) const { return a > b ? a : b; } };
+
+// the non-zeros the element kernel did NOT finish, as a compact ascending list (built once at prepare) of (k, first, second contributor | NONE, ·): one thread per
+// non-zero, one 16-byte descriptor load, then the value loads side by side; first = NONE: more than two contributors, walk cstart / src
+static __global__ void list_desc_kernel(int64_t n, const int32_t* __restrict__ list, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, uint4* __restrict__ udesc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = list[i];
+    const uint32_t c0 = cstart[k], c1 = cstart[k + 1];
+    uint4 d = make_uint4((uint32_t)k, MB_NONE, MB_NONE, 0u);
+    if (c1 - c0 >= 1 && c1 - c0 <= 2) { d.y = src[c0]; if (c1 - c0 == 2) d.z = src[c0 + 1]; }
+    else if (c1 == c0) d.w = 1u;                     // no contributor: the value is 0
+    udesc[i] = d;
+}
+static __global__ void gather_list_kernel(int64_t n, const uint4* __restrict__ udesc, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src,
+                                          const double* __restrict__ Ke, double* __restrict__ nzval) {
+    const int64_t i0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);       // two listed non-zeros per thread: four value loads in flight
+    if (i0 >= n) return;
+    const bool two = i0 + 1 < n;
+    const uint4 d = __ldg(udesc + i0), e = two ? __ldg(udesc + i0 + 1) : d;
+    const bool fd = d.y != MB_NONE, fe = e.y != MB_NONE;
+    const double a0 = __ldcs(Ke + (fd ? d.y : 0u)), a1 = __ldcs(Ke + (fd ? (d.z != MB_NONE ? d.z : d.y) : 0u));
+    const double b0 = __ldcs(Ke + (fe ? e.y : 0u)), b1 = __ldcs(Ke + (fe ? (e.z != MB_NONE ? e.z : e.y) : 0u));
+    double x = 0. + a0; if (d.z != MB_NONE) x += a1;
+    double y = 0. + b0; if (e.z != MB_NONE) y += b1;
+    if (!fd) x = d.w ? 0. : gather_one(cstart, src, Ke, d.x);
+    if (!fe) y = e.w ? 0. : gather_one(cstart, src, Ke, e.x);
+    nzval[d.x] = x;
+    if (two) nzval[e.x] = y;
+}
+struct NotFlag { const uint8_t* f; __host__ __device__ bool operator()(int32_t k) const { return f[k] == 0; } };
+
 // Lλ[d] = Σ (Re[q] − Rp[q])  (add_value! then add_∂!{1,:minus}, src/SweepX.jl:56-57)
 static __global__ void gather_vec_kernel(int64_t d0, int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc,
                                   const double* __restrict__ Re, const double* __restrict__ Rp, double* __restrict__ out) {

@@ -28,7 +28,9 @@ int32_t mb_create(int32_t device, mb_handle** out) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return MB_ERR_CUDA;
     mb_handle* h = new mb_handle();
     h->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
+    int prlo = 0, prhi = 0;                              // the engine's stream at the greatest priority: the background reduction (MB_DEV_OVERLAP=2) runs below it
+    if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetStreamPriorityRange(&prlo, &prhi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prhi) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
     if (cudaMalloc((void**)&h->nanflag, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost((void**)&h->nanflag_host, sizeof(unsigned long long)) != cudaSuccess) { delete h; return MB_ERR_CUDA; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->nsm = prop.multiProcessorCount; }
@@ -36,14 +38,21 @@ int32_t mb_create(int32_t device, mb_handle** out) {
     if (w) h->beamW = atoi(w);
     const char* sd = getenv("MB_SPLIT_DYN");
     if (sd) h->split_dyn = atoi(sd);
+    const char* fu = getenv("MB_FUSE");                  // 1: static kernel with the fused epilogue (beam_kernel.cuh; bit-identical, half the DRAM traffic, 2 % slower: off by default)
+    if (fu) h->fuse = atoi(fu);
     const char* ss = getenv("MB_STATIC_SYM");            // 0: statics through the two-direction SD kernel (A/B measurements)
     if (ss) h->static_sym = atoi(ss);
     const char* pc = getenv("MB_E2E_CHUNKS");            // host-buffer pipeline: number of element chunks (<2: one shot) and size threshold
     if (pc) h->pipe_chunks = std::min(64, atoi(pc));
     const char* pm = getenv("MB_E2E_MIN_NNZ");
     if (pm) h->pipe_min_nnz = atoll(pm);
-    const char* ov = getenv("MB_DEV_OVERLAP");           // 1: reduction of element chunk j overlapped with the element kernels of chunk j+1 (no gain measured)
+    // 1 / 2: reduction of element chunk j on a second stream (above / below the engine's priority) while the element kernels of chunk j+1 run.  No gain measured, either way
+    // (10 M elements, 8-32 chunks: 18.2-18.8 ms against 18.2), also not with the static kernel held to 240 / 224 / 208 registers so that the reduction's CTAs fit BESIDE
+    // its two CTAs per SM (18.5 / 19.1 / 19.6 ms: the spills cost, the overlap does not pay) — profiles/r2_probe_overlap.txt
+    const char* ov = getenv("MB_DEV_OVERLAP");
     if (ov) h->dev_overlap = atoi(ov);
+    const char* gb = getenv("MB_GATHER_BLOCK");
+    if (gb) h->gather_block = atoi(gb);
     *out = h;
     return MB_OK;
 }
@@ -227,6 +236,67 @@ int32_t mb_sweepx_prepare(mb_handle* h, int64_t ndofX, int64_t* nnz_out) {
     h->nnz = nnz;
     CK(dalloc(h, &h->nzval, nnz));
     { int32_t rcpd = build_pair_descriptors(h, nnz, h->cstart, h->src, &h->pdesc, &h->xdesc); if (rcpd) return rcpd; }
+    // ---- fused epilogue of the static beam kernel: which element entries a warp of five whole elements finishes itself (kernels.cuh)
+    h->fuse_groups.assign(h->groups.size(), mb_handle::FuseGroup());
+    if (h->fuse && h->static_sym == 3 && nnz > 0) {
+        bool any = false;
+        for (const Group& g : h->groups) any |= (g.kind == G_BEAM && g.nele > 0);
+        if (any) {
+            CK(dalloc(h, &h->wflag, nnz + 4)); CK(cudaMemsetAsync(h->wflag, 0, (size_t)(nnz + 4), st));
+            for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+                const Group& g = h->groups[ig];
+                if (g.kind != G_BEAM || g.nele == 0) continue;
+                mb_handle::FuseGroup& F = h->fuse_groups[ig];
+                const int64_t nw = (g.nele + MB_EPW - 1) / MB_EPW, np = g.nele * 144;
+                int32_t *wbase = nullptr, *wlen = nullptr, *wnun = nullptr; uint32_t *ebits = nullptr, *pat = nullptr; int64_t *psz = nullptr, *poff = nullptr, *hd = nullptr, *hsz = nullptr, *noff = nullptr;
+                CK(dalloc(h, &wbase, nw)); CK(dalloc(h, &wlen, nw)); CK(dalloc(h, &wnun, nw)); CK(dalloc(h, &ebits, nw * 23));
+                CK(dalloc(h, &psz, nw)); CK(dalloc(h, &poff, nw)); CK(dalloc(h, &hd, nw)); CK(dalloc(h, &hsz, nw)); CK(dalloc(h, &noff, nw));
+                CK(cudaMemsetAsync(wbase, 0x7F, (size_t)nw * 4, st)); CK(cudaMemsetAsync(wlen, 0, (size_t)nw * 4, st));
+                CK(cudaMemsetAsync(ebits, 0, (size_t)nw * 23 * 4, st));
+                fuse_mark_kernel<<<nblk(np, 256), 256, 0, st>>>(np, (uint32_t)g.pair_base, h->asm2, h->cstart, h->src, wbase);
+                fuse_dest_kernel<<<nblk(np, 256), 256, 0, st>>>(np, (uint32_t)g.pair_base, h->asm2, h->cstart, h->src, wbase, wlen, ebits, h->wflag);
+                fuse_size_kernel<<<nblk(nw, 256), 256, 0, st>>>(nw, np, wlen, ebits, wnun, psz);
+                void* tmp = nullptr; size_t t1 = 0, t2 = 0;
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, t1, psz, poff, (int)nw, st));
+                CK(cub::DeviceScan::InclusiveScan(nullptr, t2, hd, hd, MaxI64(), (int)nw, st));
+                CK(cudaMalloc(&tmp, std::max(t1, t2) + 1));
+                CK(cub::DeviceScan::ExclusiveSum(tmp, t1, psz, poff, (int)nw, st));
+                int64_t last[2] = {0, 0};
+                CK(cudaMemcpyAsync(&last[0], poff + nw - 1, 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(&last[1], psz + nw - 1, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                CK(dalloc(h, &pat, last[0] + last[1]));
+                fuse_fill_kernel<<<nblk(nw * 32, 256), 256, 0, st>>>(nw, np, (uint32_t)g.pair_base, h->cstart, h->src, wbase, wlen, ebits, poff, psz, pat);
+                fuse_eq_kernel<<<nblk(nw * 32, 256), 256, 0, st>>>(nw, wlen, wnun, poff, psz, pat, hd, hsz);
+                CK(cub::DeviceScan::InclusiveScan(tmp, t2, hd, hd, MaxI64(), (int)nw, st));          // hd[w] = first warp of the run of equal patterns w belongs to
+                CK(cub::DeviceScan::ExclusiveSum(tmp, t1, hsz, noff, (int)nw, st));
+                CK(cudaMemcpyAsync(&last[0], noff + nw - 1, 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(&last[1], hsz + nw - 1, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if ((last[0] + last[1]) / 4 >= INT32_MAX) { cudaFree(tmp); h->err = "fused epilogue: pattern table too large"; return MB_ERR_TOOBIG; }
+                CK(dalloc(h, &F.cpat, last[0] + last[1])); CK(dalloc(h, &F.whdr, nw));
+                fuse_compact_kernel<<<nblk(nw * 32, 256), 256, 0, st>>>(nw, hd, poff, psz, noff, pat, F.cpat, wbase, wlen, wnun, F.whdr);
+                h->launches += 9;
+                CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+                cudaFree(tmp);
+                dfree(h, wbase); dfree(h, wlen); dfree(h, wnun); dfree(h, ebits); dfree(h, pat); dfree(h, psz); dfree(h, poff); dfree(h, hd); dfree(h, hsz); dfree(h, noff);
+            }
+            // compact ascending list of the non-zeros that still go through the segmented reduction
+            int64_t* dn = nullptr; CK(dalloc(h, &dn, 1));
+            cub::CountingInputIterator<int32_t> it0(0);
+            void* tmp = nullptr; size_t tmpsz = 0, tmpsz2 = 0;
+            CK(cub::DeviceSelect::If(nullptr, tmpsz, it0, (int32_t*)nullptr, dn, (int)nnz, NotFlag{h->wflag}, st));
+            CK(cub::DeviceSelect::If(nullptr, tmpsz2, it0, cub::DiscardOutputIterator<int32_t>(), dn, (int)nnz, NotFlag{h->wflag}, st));
+            tmpsz = std::max(tmpsz, tmpsz2);
+            CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+            CK(cub::DeviceSelect::If(tmp, tmpsz2, it0, cub::DiscardOutputIterator<int32_t>(), dn, (int)nnz, NotFlag{h->wflag}, st));      // count first: the list is a tenth of nnz on a chain
+            CK(cudaMemcpyAsync(&h->nulist, dn, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(dalloc(h, &h->ulist, std::max<int64_t>(h->nulist, 1)));
+            CK(cub::DeviceSelect::If(tmp, tmpsz, it0, h->ulist, dn, (int)nnz, NotFlag{h->wflag}, st));
+            CK(dalloc(h, &h->udesc, std::max<int64_t>(h->nulist, 1)));
+            if (h->nulist > 0) { list_desc_kernel<<<nblk(h->nulist, 256), 256, 0, st>>>(h->nulist, h->ulist, h->cstart, h->src, h->udesc); h->launches++; }
+            CK(cudaStreamSynchronize(st)); cudaFree(tmp); dfree(h, dn); dfree(h, h->ulist); h->ulist = nullptr;
+        }
+    }
 
     // ---- vector map: contributors of every dof in element order (asmvec!, src/Assemble.jl:340-357)
     if (nvec > 0) {
@@ -336,6 +406,11 @@ template <int ND, bool STEP> static void launch_beam_w(mb_handle* h, const Group
     BeamLaunch a{gd, sd, nm, h->Ke + g.pair_base + e0 * 144, h->Re + g.vec_base + e0 * 12, h->Rp + g.vec_base + e0 * 12, h->nanflag, nanbase + (unsigned long long)e0,
                  h->beamW, h->stream, Wc};
     a.static_sym = h->static_sym; a.nsm = h->nsm;
+    if (ND == 1 && h->wflag) {                     // statics: entries a warp can finish go straight to nzval (e0 is a multiple of MB_EPW: the chunk plan keeps it so)
+        const size_t ig = (size_t)(&g - h->groups.data());
+        const mb_handle::FuseGroup& F = h->fuse_groups[ig];
+        if (F.whdr && e0 % MB_EPW == 0) a.fz = FuseDev{F.whdr, F.cpat, h->nzval, e0 / MB_EPW};
+    }
     launch_beam<ND, STEP>(a);
     h->launches += 1 + (Wc ? 1 : 0) + (STEP ? (Wc ? 2 : 1) : 0);
 }
@@ -345,7 +420,9 @@ static int32_t launch_group_range(mb_handle* h, size_t ig, int64_t e0, int64_t e
     const bool step = (mission == 0) && OX > 0;
     StateDev sd{h->X0, h->X1, h->X2, h->ndofU > 0 ? h->U0 : nullptr};
     const Group& g = h->groups[ig];
+    h->fused_now = (OX == 0) && h->wflag != nullptr;        // the segmented reduction that follows skips what the static kernel finishes itself
     if (g.nele == 0 || e1 <= e0) return MB_OK;
+    if (h->fused_now && g.kind == G_BEAM && e0 % MB_EPW != 0) { h->err = "element range of a static launch does not start at a whole warp"; return MB_ERR_STATE; }
     const unsigned long long nanbase = ((unsigned long long)ig) << 40;
     if (g.kind == G_BEAM) {
         BeamGroupDev gd;
@@ -379,10 +456,18 @@ static int32_t launch_elements(mb_handle* h, int OX, int mission, const NewmarkD
 // segmented reductions of non-zeros [k0,k1) (k0 a multiple of 4) and dofs [d0,d1)
 static void launch_gather_range(mb_handle* h, bool step, int64_t k0, int64_t k1, int64_t d0, int64_t d1, cudaStream_t st = nullptr) {
     if (!st) st = h->stream;
-    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, 256), 256, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->pdesc + k0, h->xdesc, h->Ke, h->nzval + k0); h->launches++; }
-    if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, 256), 256, 0, st>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
+    const uint8_t* wf = (h->fused_now && h->wflag) ? h->wflag + k0 : nullptr;      // non-zeros the static element kernel has finished already
+    if (k1 > k0) { gather_nz_kernel<<<nblk((k1 - k0 + 3) / 4, h->gather_block), h->gather_block, 0, st>>>(k1 - k0, h->cstart + k0, h->src, h->pdesc + k0, h->xdesc, h->Ke, h->nzval + k0, wf); h->launches++; }
+    if (d1 > d0) { gather_vec_kernel<<<nblk(d1 - d0, h->gather_block), h->gather_block, 0, st>>>(d0, d1, h->vstart, h->vsrc, h->Re, step ? h->Rp : nullptr, h->Ll); h->launches++; }
 }
-static void launch_gather(mb_handle* h, bool step) { launch_gather_range(h, step, 0, h->nnz, 0, h->ndofX); }
+static void launch_gather(mb_handle* h, bool step) {
+    if (h->fused_now && h->udesc) {                  // statics with the fused epilogue: only the listed non-zeros are still to be summed
+        if (h->nulist > 0) { gather_list_kernel<<<nblk((h->nulist + 1) / 2, 256), 256, 0, h->stream>>>(h->nulist, h->udesc, h->cstart, h->src, h->Ke, h->nzval); h->launches++; }
+        launch_gather_range(h, step, 0, 0, 0, h->ndofX);
+        return;
+    }
+    launch_gather_range(h, step, 0, h->nnz, 0, h->ndofX);
+}
 
 // ---- host-buffer pipeline: chunk plan + completion prefixes (built once, at the first large mb_sweepx_assemble)
 static int32_t build_pipeline(mb_handle* h) {
@@ -406,6 +491,7 @@ static int32_t build_pipeline(mb_handle* h) {
                 const int64_t target = (work * (chunk + 1) + C - 1) / C;
                 const int64_t room = (target - done + per - 1) / per;
                 e1 = std::min(g.nele, e + std::max<int64_t>(room, 1));
+                if (e1 < g.nele) e1 = std::min(g.nele, e + std::max<int64_t>(MB_EPW, ((e1 - e) / MB_EPW) * MB_EPW));      // whole warps of the static kernel (fused epilogue)
             }
             h->pipe_items.push_back({(int)ig, e, e1, chunk});
             done += (e1 - e) * per;
@@ -463,7 +549,7 @@ int32_t mb_sweepx_assemble_dev(mb_handle* h, int32_t OX, int32_t mission, double
         if (!h->gather_stream) {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CK(cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, hi));
+            CK(cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, h->dev_overlap == 2 ? lo : hi));      // 2: below the element kernels — the reduction takes what they leave
             CK(cudaEventCreateWithFlags(&h->gather_done, cudaEventDisableTiming));
         }
         const bool step = mission == 0 && OX > 0;

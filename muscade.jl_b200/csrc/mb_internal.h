@@ -61,6 +61,9 @@ struct mb_handle {
     std::vector<void*> owned;
     double* Wc = nullptr; int64_t Wc_len = 0; int split_dyn = 1; int static_sym = 3; int nsm = 148;   // cotangent workspace of the two-phase Newmark kernel
     bool own_stream = true;
+    // fused epilogue of the static beam kernel (kernels.cuh): per beam group the non-zero range of every warp and the entries it finishes in its tile
+    struct FuseGroup { int4* whdr = nullptr; uint32_t* cpat = nullptr; };
+    std::vector<FuseGroup> fuse_groups; uint8_t* wflag = nullptr; int32_t* ulist = nullptr; uint4* udesc = nullptr; int64_t nulist = 0; int fuse = 0; bool fused_now = false;   // fused_now: the assembly being issued is a static one (OX = 0)
     int32_t *if_send = nullptr, *if_recv = nullptr;   // interface index lists (0-based into [nzval | Lλ], −1 = ghost)
     int64_t if_nsend_nz = 0, if_nsend_v = 0, if_nrecv_nz = 0, if_nrecv_v = 0;
     double *if_sendbuf = nullptr, *if_recvbuf = nullptr;   // device buffers of mb_iface_exchange
@@ -78,7 +81,7 @@ struct mb_handle {
     // device-resident path (mb_sweepx_assemble_dev), optional (MB_DEV_OVERLAP=1): the same chunk plan; the segmented reduction of chunk j on a
     // high-priority stream while the element kernels of chunk j+1 run.  Measured on B200 (10 M elements): 23.1 ms vs 23.0 ms serial — the
     // element CTAs hold the whole register file, the two kernels time-share the SMs instead of overlapping — so it is off by default.
-    cudaStream_t gather_stream = nullptr; cudaEvent_t gather_done = nullptr; int dev_overlap = 0;
+    cudaStream_t gather_stream = nullptr; cudaEvent_t gather_done = nullptr; int dev_overlap = 0; int gather_block = 256;
 };
 
 #define CK(call)                                                                                         \

@@ -172,3 +172,35 @@ def test_beam_requestables_batched(mb, engine_factory, OX):
     eng.set_state(X)
     res2 = eng.beam_results(ityp, OX)
     assert np.array_equal(res2["raw"], res["raw"])
+
+
+@pytest.mark.parametrize("topology", ["chain", "shuffled", "star", "mixed", "chain_pipelined"])
+def test_fused_epilogue_bit_identical(mb, engine_factory, monkeypatch, topology):
+    """MB_FUSE=1: the static kernel sums the non-zeros a warp of five elements holds all contributors of in its shared-memory tile (beam_kernel.cuh, "fused
+    epilogue") — same element-order sums, so Lλ and nzval are the BITS of the default path, whatever the mesh (pattern dedupe, partial last warp, nodes with
+    many elements, another element type on the same dofs)."""
+    N = {"star": 40, "chain_pipelined": 50003}.get(topology, 1003)          # 50 003 elements: nnz beyond the threshold of the chunked host-buffer pipeline
+    rng = np.random.default_rng(11)
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=False)
+    bars = None
+    if topology == "shuffled":
+        perm = rng.permutation(ndof)
+        idx = (perm[idx - 1] + 1).astype(np.int64)
+        order = rng.permutation(N); eleobj, idx = eleobj[order], idx[order]
+    elif topology == "star":                                  # every element's first node is node 1
+        idx = idx.copy(); idx[:, :6] = np.arange(1, 7)
+    X = mb.synthetic.state(ndof, nder=1)
+    nm = mb.synthetic.newmark_coefficients(0, 0.)
+    out = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("MB_FUSE", fuse)
+        eng = engine_factory()
+        eng.add_eulerbeam3d(eleobj, idx, np.ones(12))
+        if topology == "mixed":                               # a second beam type sharing the first type's nodes: contributors from two groups
+            eng.add_eulerbeam3d(eleobj[:200], idx[100:300], np.ones(12))
+        eng.sweepx_prepare(ndof)
+        L, nz = eng.sweepx_assemble(0, "iter", X, nm)
+        L2, nz2 = eng.sweepx_assemble(0, "iter", X, nm)
+        assert np.array_equal(L, L2) and np.array_equal(nz, nz2)
+        out.append((L, nz))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
