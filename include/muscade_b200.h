@@ -148,6 +148,45 @@ int32_t mb_direct_step_ptrs(mb_handle* h, int64_t step, double** LX, int64_t* nL
 /* CUDA-event timing of the owned steps: ms[0] element kernels + per-step reductions, ms[1] Lvv/Lv build, ms[2] the element kernels alone (float ms[3]) */
 int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
 
+/* ---- DirectXUA{OX,OU,IA}, GENERAL form: any dof classes (Λ,X,U,A), IA = 0 or 1, several experiments (csrc/mb_xua.cu) ------------------------------
+ * The reference's whole assembly for the all-steps optimisation problem, for element types the beam-specialised path above does not cover (A-dofs, U-costs,
+ * user Lagrangians): prepare(AssemblyDirect{OX,OU,IA}) (src/DirectXUA.jl:22-56: asmvec!/asmmat! for all class pairs), makepattern / preparebig (:245-315, with the
+ * A block row / column and `for iexp`), SparseTools.prepare (src/SparseTools.jl:32-94: Lvv, Lvvasm, Lvasm — bit-identical structures), assembleA! (:320-326),
+ * assemblebig!{:matrices} (:316-356), sparser! and decrementbig! (:357-383).  Classes are numbered 1 Λ, 2 X, 3 U, 4 A as `ind` (:14); experiments and steps 1-based.
+ * Element derivatives come in as PACKETS per element type and step: ∇L [nele][Np] and ∇²L [nele][Np][Np] (row-major) in the order of partials of
+ * DirectXUA_lagrangian_addition! (:121-150): Λ (nx), X₀…X_OX (nx each), U₀…U_OU (nu each), A (na, IA = 1 only), scaled as revariate(…,scale) scales them.  Which parts are
+ * filled follows the reference's addin! method for the element type: no_second_order types (:85-120) fill ∇L[Λ] = R and the Λ-row / Λ-column of ∇²L only.
+ * Acost types (acost = 1; only A dofs) are assembled by mb_xua_add_A from packets with Np = na (unscaled, :70-84) AND, like any type, by mb_xua_add_step from their
+ * general packets — src/Assemble.jl:477 (`assemble_!(…,eleobj::Acost,…) = nothing`) does not match the Vector{<:Acost} it is called with; test/TestDirectXUA.jl:107 pins it.
+ *   mb_xua_add_eletyp  : dof numbers [nele][n] per class, 1-based within the class (dis.dis[ieletyp].index[iele].X|U|A).
+ *   mb_xua_prepare     : flags = 1 Xwhite | 2 XUindep | 4 UAindep | 8 XAindep (:22).  nstep[nexp], dt[nexp] = length.(time), step.(time) (:443).
+ *   mb_xua_class_pattern / get_asm / big_pattern / big_asm : the structures, for checking against the reference (test/TestDirectXUA.jl:93-136).
+ *   mb_xua_zero; [mb_xua_set_packet… mb_xua_add_A]; for every step [mb_xua_set_packet… mb_xua_add_step] : one assemblebig!.
+ *   mb_xua_get_out     : out.L1[α][αder] (beta = 0) / out.L2[α,β][αder,βder].nzval of the last added step. */
+int32_t mb_xua_add_eletyp(mb_handle* h, int64_t nele, int32_t nx, int32_t nu, int32_t na, const int64_t* idxX, const int64_t* idxU, const int64_t* idxA,
+                          int32_t acost, int32_t* ieletyp_out);
+int32_t mb_xua_prepare(mb_handle* h, int32_t OX, int32_t OU, int32_t IA, int64_t ndofX, int64_t ndofU, int64_t ndofA, int32_t nexp, const int64_t* nstep,
+                       const double* dt, int32_t flags, int64_t* nbig_out, int64_t* nnzbig_out);
+int32_t mb_xua_class_pattern(mb_handle* h, int32_t alpha, int32_t beta, int64_t* nnz, int64_t* colptr, int64_t* rowval);
+int32_t mb_xua_get_asm(mb_handle* h, int32_t ieletyp, int32_t alpha, int32_t beta, int64_t* out);
+int32_t mb_xua_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval);
+int32_t mb_xua_big_asm(mb_handle* h, int64_t* nb, int64_t* nblock, int64_t* bcolptr, int64_t* browval, int64_t* boff, int64_t* basm, int64_t* pgr);
+int32_t mb_xua_zero(mb_handle* h);
+int32_t mb_xua_set_packet(mb_handle* h, int32_t ieletyp, const double* gradL, const double* hessL);
+int32_t mb_xua_add_A(mb_handle* h);
+int32_t mb_xua_add_step(mb_handle* h, int32_t iexp, int64_t istep);
+int32_t mb_xua_get_out(mb_handle* h, int32_t alpha, int32_t beta, int32_t ader, int32_t bder, double* out);
+int32_t mb_xua_out_shape(mb_handle* h, int32_t alpha, int32_t beta, int32_t* na, int32_t* nb);
+int32_t mb_xua_get_big(mb_handle* h, double* Lvv_nzval, double* Lv);
+int32_t mb_xua_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
+int32_t mb_xua_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
+/* state[iexp][istep]: Λ (nX), X (OX+1)·nX, U (OU+1)·nU contiguous by derivative, A (nA) shared by all states (:452); NULL leaves a part untouched.
+ * mb_xua_decrement: decrementbig! with dv = Δv in Lv's layout (host or device) → Δ² for Λ, X, U (max over steps of ΣΔβ²) and A. */
+int32_t mb_xua_set_state(mb_handle* h, int32_t iexp, int64_t istep, const double* Lambda, const double* X, const double* U, const double* A);
+int32_t mb_xua_get_state(mb_handle* h, int32_t iexp, int64_t istep, double* Lambda, double* X, double* U, double* A);
+int32_t mb_xua_set_dof_scale(mb_handle* h, const double* sL, const double* sX, const double* sU, const double* sA);
+int32_t mb_xua_decrement(mb_handle* h, const double* dv, double* delta2 /* 4 */);
+
 /* ---- sharding over the GPUs of one box (one handle per GPU / process) ------------------------------------------------------------------------- */
 /* Device-resident state: the Newton update runs where the state lives, so X only crosses PCIe when the caller asks.
  *   mb_sweepx_set_state / get_state : state.X[1..OX+1] (and state.U[1]) host↔device; pointers may be host or device memory.

@@ -82,6 +82,26 @@ SYMBOLS = {
     "mb_direct_step_ptrs": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mb_direct_time_dev": (C.c_int32, [H, C.c_int32, f32p]),
+    "mb_xua_add_eletyp": (C.c_int32, [H, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "mb_xua_prepare": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mb_xua_class_pattern": (C.c_int32, [H, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "mb_xua_get_asm": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mb_xua_big_pattern": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
+    "mb_xua_big_asm": (C.c_int32, [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_xua_zero": (C.c_int32, [H]),
+    "mb_xua_set_packet": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_xua_add_A": (C.c_int32, [H]),
+    "mb_xua_add_step": (C.c_int32, [H, C.c_int32, C.c_int64]),
+    "mb_xua_get_out": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mb_xua_out_shape": (C.c_int32, [H, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mb_xua_get_big": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
+    "mb_xua_sparser": (C.c_int32, [H, C.c_double, C.POINTER(C.c_int64)]),
+    "mb_xua_get_sparse": (C.c_int32, [H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_xua_set_state": (C.c_int32, [H, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_xua_get_state": (C.c_int32, [H, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_xua_set_dof_scale": (C.c_int32, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_xua_decrement": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
     "mb_set_stream": (C.c_int32, [H, C.c_void_p]),
     "mb_iface_setup": (C.c_int32, [H, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "mb_iface_pack_dev": (C.c_int32, [H, C.c_void_p]),

@@ -63,6 +63,7 @@ int32_t mb_destroy(mb_handle* h) {
     cudaStreamSynchronize(h->stream);
     mb_comm_destroy(h);
     mb_direct_release(h);
+    mb_xua_release(h);
     for (void* p : h->owned) cudaFree(p);
     cudaFree(h->nanflag);
     if (h->redtmp) cudaFree(h->redtmp);

@@ -11,6 +11,7 @@
 #include <map>
 #include "mb_internal.h"
 #include <cub/cub.cuh>
+#include "pattern_build.cuh"
 
 namespace mb {
 template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
@@ -25,51 +26,8 @@ namespace {
 
 enum { P_XX = 0, P_XU = 1, P_UX = 2, P_UU = 3 };
 
-struct PairPat {                  // one class-pair pattern of prepare(AssemblyDirect): asmmat! (src/Assemble.jl:373-448)
-    int64_t m = 0, n = 0, nnz = 0, npair = 0;
-    int32_t *colptr0 = nullptr, *rowval0 = nullptr, *asmK = nullptr;
-    uint32_t *cstart = nullptr, *src = nullptr;
-    std::vector<int64_t> gbase;   // per group: first pair id
-};
-
 constexpr int MAXG = 32;    // element types of one model on the DirectXUA path (the SCR riser of configs[4] has 11)
 struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; int64_t gxbase[MAXG]; };
-
-// ---------------------------------------------------------------------------------------------------------------- pattern build
-__global__ void pair_keys_kernel(int64_t nele, int ni, const int32_t* __restrict__ idxR, int nj, const int32_t* __restrict__ idxC, uint64_t nrows,
-                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n2 = (int64_t)ni * nj;
-    if (p >= nele * n2) return;
-    const int64_t e = p / n2;
-    const int r = (int)(p - e * n2);
-    const int j = r / ni, i = r - j * ni;                      // jeledof outer, ieledof inner (src/Assemble.jl:389)
-    keys[base + p] = (uint64_t)idxC[e * nj + j] * nrows + (uint64_t)idxR[e * ni + i];
-    vals[base + p] = base + (uint32_t)p;
-}
-__global__ void finish_pat_kernel(int64_t npair, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ inz,
-                                  uint64_t nrows, int32_t* __restrict__ asmK, int32_t* __restrict__ rowval0, uint32_t* __restrict__ cstart) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= npair) return;
-    const uint32_t k = inz[s];
-    asmK[vals[s]] = (int32_t)k;
-    const uint64_t key = keys[s];
-    if (s == 0 || key != keys[s - 1]) { rowval0[k - 1] = (int32_t)(key % nrows); cstart[k - 1] = (uint32_t)s; }
-    if (s == npair - 1) cstart[k] = (uint32_t)npair;
-}
-__global__ void colptr_pat_kernel(int64_t nnz, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ cstart, uint64_t nrows, int64_t ncols,
-                                  int32_t* __restrict__ colptr0) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nnz) return;
-    const int64_t col = (int64_t)(keys[cstart[k]] / nrows);
-    const int64_t prev = (k == 0) ? -1 : (int64_t)(keys[cstart[k - 1]] / nrows);
-    for (int64_t c = prev + 1; c <= col; ++c) colptr0[c] = (int32_t)k;
-    if (k == nnz - 1) for (int64_t c = col + 1; c <= ncols; ++c) colptr0[c] = (int32_t)nnz;
-}
-struct KeyFlagD {
-    const uint64_t* k;
-    __host__ __device__ uint32_t operator()(int64_t s) const { return (s == 0 || k[s] != k[s - 1]) ? 1u : 0u; }
-};
 
 // ---------------------------------------------------------------------------------------------------------------- per-step gathers
 __device__ __forceinline__ int find_group(const uint32_t* pbase, int n, uint32_t id) {
@@ -171,19 +129,6 @@ struct BigDev {
     int64_t ehi;
 };
 __device__ __forceinline__ int pat_of(int ca, int cb) { return (ca == 2 ? 2 : 0) + (cb == 2 ? 1 : 0); }   // class 2 = U
-// finitediff(order,n,s) (src/FiniteDifferences.jl:2-31): weight of offset ds at 0-based step s, or 0 with found=false
-__device__ __forceinline__ bool fd_weight(int order, int64_t n, int64_t s, int64_t ds, double& w) {
-    if (order == 0) { w = 1.; return ds == 0; }
-    const int pos = (s == 0) ? 0 : (s == n - 1 ? 1 : 2);
-    if (order == 1) {
-        if (pos == 0) { if (ds == 0) { w = -1.; return true; } if (ds == 1) { w = 1.; return true; } return false; }
-        if (pos == 1) { if (ds == -1) { w = -1.; return true; } if (ds == 0) { w = 1.; return true; } return false; }
-        if (ds == -1) { w = -.5; return true; } if (ds == 1) { w = .5; return true; } return false;
-    }
-    if (pos == 0) { if (ds == 0) { w = 1.; return true; } if (ds == 1) { w = -2.; return true; } if (ds == 2) { w = 1.; return true; } return false; }
-    if (pos == 1) { if (ds == -2) { w = 1.; return true; } if (ds == -1) { w = -2.; return true; } if (ds == 0) { w = 1.; return true; } return false; }
-    if (ds == -1) { w = 1.; return true; } if (ds == 0) { w = -2.; return true; } if (ds == 1) { w = 1.; return true; } return false;
-}
 __device__ __forceinline__ void decode_col(const BigDev& B, int64_t c, int64_t& step, int& cls, int64_t& lc) {
     step = B.lo + c / B.W; const int64_t r = c % B.W;
     if (r < B.nX) { cls = 0; lc = r; } else if (r < 2 * B.nX) { cls = 1; lc = r - B.nX; } else { cls = 2; lc = r - 2 * B.nX; }
@@ -397,21 +342,6 @@ __global__ void big_xx_kernel(BigDev B, int64_t n, const int32_t* __restrict__ i
 
 // ---------------------------------------------------------------------------------------------------------------- sparser! / decrementbig!
 // sparser!(T,S,rtol) (src/SparseTools.jl:172-199): keep |nzval| ≥ rtol·max|S|, order preserved, colptr shifted by the drops before it
-struct AbsF { __host__ __device__ double operator()(double x) const { return fabs(x); } };
-struct KeepF { const double* v; double atol; __host__ __device__ int64_t operator()(int64_t i) const { return fabs(v[i]) >= atol ? 1 : 0; } };
-__global__ void sparser_scatter_kernel(int64_t nnz, const double* __restrict__ v, const int64_t* __restrict__ rv, const int64_t* __restrict__ pos, double atol,
-                                       double* __restrict__ v2, int64_t* __restrict__ rv2) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz) return;
-    if (fabs(v[i]) >= atol) { const int64_t q = pos[i]; v2[q] = v[i]; rv2[q] = rv[i]; }
-}
-__global__ void sparser_colptr_kernel(int64_t ncol, int64_t nnz, const int64_t* __restrict__ colptr, const int64_t* __restrict__ pos, int64_t nkeep,
-                                      int64_t* __restrict__ colptr2) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > ncol) return;
-    const int64_t p = colptr[c];
-    colptr2[c] = (p < nnz) ? pos[p] : nkeep;
-}
 // decrementbig! (src/DirectXUA.jl:357-383): state[step].β[βder] −= ((Δβ·w)·Δt^(1−βder))·scale for every stencil point (Δs,w) of
 // finitediff(βder−1,nstep,step), Δβ = Δv block of step+Δs, class β — same sequence of roundings (no FMA contraction).
 struct DecDev {
@@ -486,52 +416,9 @@ struct DirectData {
 };
 
 static int32_t build_pattern(mb_handle* h, PairPat& P, bool rowU, bool colU, int64_t nrows, int64_t ncols) {
-    cudaStream_t st = h->stream;
-    P.m = nrows; P.n = ncols; P.gbase.clear();
-    int64_t npair = 0;
-    for (const Group& g : h->groups) { P.gbase.push_back(npair); npair += g.nele * (rowU ? g.nu : g.nx) * (colU ? g.nu : g.nx); }
-    P.gbase.push_back(npair);
-    P.npair = npair;
-    if (npair >= (int64_t)UINT32_MAX) { h->err = "more than 2^32 element-matrix entries on one device"; return MB_ERR_TOOBIG; }
-    CK(dalloc(h, &P.colptr0, ncols + 1));
-    CK(cudaMemsetAsync(P.colptr0, 0, (ncols + 1) * sizeof(int32_t), st));
-    if (npair == 0 || nrows == 0 || ncols == 0) { P.nnz = 0; CK(dalloc(h, &P.rowval0, 1)); CK(dalloc(h, &P.cstart, 1)); CK(dalloc(h, &P.src, 1)); CK(dalloc(h, &P.asmK, 1));
-        CK(cudaMemsetAsync(P.cstart, 0, sizeof(uint32_t), st)); return MB_OK; }
-    uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *inz = nullptr;
-    CK(dalloc(h, &keys, npair)); CK(dalloc(h, &keys2, npair)); CK(dalloc(h, &vals, npair)); CK(dalloc(h, &inz, npair));
-    CK(dalloc(h, &P.src, npair)); CK(dalloc(h, &P.asmK, npair));
-    for (size_t ig = 0; ig < h->groups.size(); ++ig) {
-        const Group& g = h->groups[ig];
-        const int ni = rowU ? g.nu : g.nx, nj = colU ? g.nu : g.nx;
-        const int64_t n = g.nele * ni * nj;
-        if (n == 0) continue;
-        pair_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(g.nele, ni, rowU ? g.idxU : g.idxX, nj, colU ? g.idxU : g.idxX, (uint64_t)nrows, keys, vals, (uint32_t)P.gbase[ig]);
-        h->launches++;
-    }
-    int end_bit = 1; while (end_bit < 64 && ((uint64_t)nrows * (uint64_t)ncols) >> end_bit) ++end_bit;
-    void* tmp = nullptr; size_t tmpsz = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, P.src, npair, 0, end_bit, st));
-    CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
-    CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, P.src, npair, 0, end_bit, st));
-    CK(cudaStreamSynchronize(st)); cudaFree(tmp);
-    cub::CountingInputIterator<int64_t> cnt(0);
-    cub::TransformInputIterator<uint32_t, KeyFlagD, cub::CountingInputIterator<int64_t>> flags(cnt, KeyFlagD{keys2});
-    tmp = nullptr; tmpsz = 0;
-    CK(cub::DeviceScan::InclusiveSum(nullptr, tmpsz, flags, inz, npair, st));
-    CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
-    CK(cub::DeviceScan::InclusiveSum(tmp, tmpsz, flags, inz, npair, st));
-    uint32_t last = 0;
-    CK(cudaMemcpyAsync(&last, inz + (npair - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st)); cudaFree(tmp);
-    P.nnz = last;
-    if (P.nnz > (int64_t)INT32_MAX) { h->err = "more than 2^31-1 non-zeros in a class-pair pattern on one device"; dfree(h, keys); dfree(h, keys2); dfree(h, vals); dfree(h, inz); return MB_ERR_TOOBIG; }
-    CK(dalloc(h, &P.rowval0, P.nnz)); CK(dalloc(h, &P.cstart, P.nnz + 1));
-    finish_pat_kernel<<<nblk(npair, 256), 256, 0, st>>>(npair, keys2, P.src, inz, (uint64_t)nrows, P.asmK, P.rowval0, P.cstart);
-    colptr_pat_kernel<<<nblk(P.nnz, 256), 256, 0, st>>>(P.nnz, keys2, P.cstart, (uint64_t)nrows, ncols, P.colptr0);
-    h->launches += 2;
-    CK(cudaStreamSynchronize(st));
-    dfree(h, keys); dfree(h, keys2); dfree(h, vals); dfree(h, inz);
-    return MB_OK;
+    std::vector<PatSide> rows, cols;
+    for (const Group& g : h->groups) { rows.push_back({g.nele, rowU ? g.nu : g.nx, rowU ? g.idxU : g.idxX}); cols.push_back({g.nele, colU ? g.nu : g.nx, colU ? g.idxU : g.idxX}); }
+    return build_pair_pattern(h, P, rows, cols, nrows, ncols);
 }
 
 static BigDev make_bigdev(const DirectData* D) {

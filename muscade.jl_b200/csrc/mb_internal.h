@@ -15,6 +15,7 @@ using namespace mb;
 
 struct mb_handle;
 void mb_direct_release(mb_handle* h);   // mb_direct.cu
+void mb_xua_release(mb_handle* h);      // mb_xua.cu
 struct MbXfer { double* p; int64_t n; int peer; };
 int32_t mb_comm_sendrecv(mb_handle* h, const std::vector<MbXfer>& sends, const std::vector<MbXfer>& recvs);   // mb_comm.cu: one NCCL group on h->stream
 
@@ -68,6 +69,7 @@ struct mb_handle {
     int64_t if_nsend_nz = 0, if_nsend_v = 0, if_nrecv_nz = 0, if_nrecv_v = 0;
     double *if_sendbuf = nullptr, *if_recvbuf = nullptr;   // device buffers of mb_iface_exchange
     void* comm = nullptr; bool comm_owned = true; int rank = 0, world = 1; double* comm_scratch = nullptr;   // NCCL communicator of this handle (mb_comm.cu)
+    struct XuaData* xua = nullptr;            // DirectXUA{OX,OU,IA}, general form (mb_xua.cu)
     struct DirectData* direct = nullptr;      // DirectXUA state (mb_direct.cu)
     // host-buffer path (mb_sweepx_assemble): element ranges are evaluated chunk by chunk and every prefix of nzval / Lλ whose contributors
     // are all done is reduced and copied to the host while the next chunk computes

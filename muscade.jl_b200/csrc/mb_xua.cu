@@ -1,0 +1,787 @@
+// DirectXUA{OX,OU,IA} on the device, GENERAL form: any element type with Λ/X/U/A dofs, IA = 0 or 1, several experiments.
+//
+//   prepare(AssemblyDirect{OX,OU,IA})        src/DirectXUA.jl:22-56     asmvec! / asmmat! maps and class-pair patterns (all 16 pairs; 9 distinct)
+//   DirectXUA_lagrangian_addition!           src/DirectXUA.jl:121-150   per element ∇L (Np) and ∇²L (Np×Np) → out.L1[α][αder], out.L2[α,β][αder,βder]
+//   assembleA! (Acost elements)              src/Assemble.jl:507-520, src/DirectXUA.jl:70-84
+//   makepattern / preparebig                 src/DirectXUA.jl:245-315   block pattern over (experiment, step, class) + the A block row / column
+//   SparseTools.prepare / addin!             src/SparseTools.jl:32-137  Lvv structure, Lvvasm, Lvasm
+//   assemblebig!{:matrices}                  src/DirectXUA.jl:316-356   finite-difference weighted addition of every step's out into Lvv / Lv
+//   sparser! / decrementbig!                 src/SparseTools.jl:172-199, src/DirectXUA.jl:357-383
+//
+// The element LAGRANGIAN DERIVATIVES come in as packets, one per element type and step: ∇L [nele][Np], ∇²L [nele][Np][Np] in the reference's order of partials
+// (Λ, X₀…X_OX, U₀…U_OU, A; Np = nx + nx(OX+1) + nu(OU+1) + na·IA), already scaled as revariate(…,scale) scales them.  Element types whose `lagrangian` /
+// `residual` is a user closure (El1, Spring, SingleUdof, SingleDofCost, Acost … of test/TestDirectXUA.jl) are differentiated by the host (the reference does
+// that with its dual numbers); device element types can write their packets where they are.  Everything after the packets — the hot loop of assemblebig! — runs
+// here: segmented reductions in the reference's accumulation order (element type, element), then thread-per-entry weighted adds in the reference's loop order
+// (α, β, αder, βder, iα, iβ): no atomics, results reproducible bit for bit.
+// The beam-specialised path of mb_direct.cu (IA = 0, device element kernels, block-implicit Lvv, time-step windows) stays the fast one for large models.
+#include <algorithm>
+#include <map>
+#include <cmath>
+#include "mb_internal.h"
+#include <cub/cub.cuh>
+#include "pattern_build.cuh"
+
+namespace {
+
+constexpr int XMAXT = 40;                       // element types of one model on this path
+enum { CX = 0, CU = 1, CA = 2 };
+inline int cgroup(int a) { return a <= 1 ? CX : a - 1; }      // class α = 0 Λ, 1 X, 2 U, 3 A → dof-index group (Λ shares the X dofs)
+
+struct XuaType {
+    int64_t nele = 0; int n[3] = {0, 0, 0}; int32_t* idx[3] = {nullptr, nullptr, nullptr}; int acost = 0;
+    int Np = 0; int base[4] = {0, 0, 0, 0};     // first partial of class α in the packet; derivative d of α starts at base[α] + d·n[cgroup(α)]
+    double *g = nullptr, *H = nullptr; bool has = false;
+};
+struct TabDev {                                  // per element type, for one (α,β) or α: by value into the gather kernels
+    int n; uint32_t pbase[XMAXT + 1]; int ni[XMAXT], nj[XMAXT], Np[XMAXT], bi[XMAXT], bj[XMAXT]; const double* p[XMAXT];
+};
+struct Combo2 { int i, j; double f; int64_t off; };      // L2[α,β][i,j]·f → Lvv.nzval[basm[off + l]]
+struct Combo1 { int i; double f; int64_t row0; };        // L1[β][i]·f → Lv[row0 + d]
+
+__device__ __forceinline__ int find_type(const uint32_t* pbase, int n, uint32_t id) {
+    int t = 0;
+    while (t + 1 < n && id >= pbase[t + 1]) ++t;
+    return t;
+}
+// out[(i·nbd + j)·nnz + k] = Σ_contributors H[e][bi + ni·i + ia][bj + nj·j + ib]   (grid.y = i·nbd + j)
+__global__ void xua_gather2_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, TabDev T, int nbd, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int i = blockIdx.y / nbd, j = blockIdx.y - i * nbd;
+    double acc = 0.;
+    for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
+        const uint32_t id = src[s];
+        const int t = find_type(T.pbase, T.n, id);
+        if (!T.p[t]) continue;
+        const uint32_t r = id - T.pbase[t];
+        const int n2 = T.ni[t] * T.nj[t];
+        const int64_t e = r / n2; const int q = (int)(r - e * n2);
+        const int ib = q / T.ni[t], ia = q - ib * T.ni[t];                      // entry ieledof + ni·(jeledof−1)  (src/Assemble.jl:389)
+        acc += T.p[t][(e * T.Np[t] + (T.bi[t] + T.ni[t] * i + ia)) * T.Np[t] + (T.bj[t] + T.nj[t] * j + ib)];
+    }
+    out[(int64_t)blockIdx.y * nnz + k] = acc;
+}
+// out[i·ndof + d] = Σ_contributors g[e][bi + ni·i + ia]   (grid.y = i)
+__global__ void xua_gather1_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, TabDev T, double* __restrict__ out) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    const int i = blockIdx.y;
+    double acc = 0.;
+    for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) {
+        const uint32_t id = vsrc[s];
+        const int t = find_type(T.pbase, T.n, id);
+        if (!T.p[t]) continue;
+        const uint32_t r = id - T.pbase[t];
+        const int64_t e = r / T.ni[t]; const int ia = (int)(r - e * T.ni[t]);
+        acc += T.p[t][e * T.Np[t] + (T.bi[t] + T.ni[t] * i + ia)];
+    }
+    out[(int64_t)i * ndof + d] = acc;
+}
+// addin!(asm,out,block,ibr,ibc,factor) (src/SparseTools.jl:101-122) for every (αder,βder,iα,iβ) of one class pair, in the reference's loop order, one thread per block entry
+__global__ void xua_addin2_kernel(int64_t nnz, const double* __restrict__ L2, int nbd, const Combo2* __restrict__ cb, int nc, const int64_t* __restrict__ basm, double* __restrict__ big) {
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nnz) return;
+    for (int c = 0; c < nc; ++c) {
+        const Combo2 q = cb[c];
+        double* dst = big + (basm[q.off + l] - 1);
+        *dst = __dadd_rn(*dst, __dmul_rn(L2[(int64_t)(q.i * nbd + q.j) * nnz + l], q.f));
+    }
+}
+__global__ void xua_addin1_kernel(int64_t ndof, const double* __restrict__ L1, const Combo1* __restrict__ cb, int nc, double* __restrict__ Lv) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    for (int c = 0; c < nc; ++c) {
+        const Combo1 q = cb[c];
+        double* dst = Lv + q.row0 + d;
+        *dst = __dadd_rn(*dst, __dmul_rn(L1[(int64_t)q.i * ndof + d], q.f));
+    }
+}
+// contributors of every dof of one class: key = dof, value = (type base + e·n + ieledof)
+__global__ void xua_vec_keys_kernel(int64_t n, const int32_t* __restrict__ idx, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t base) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[base + p] = (uint32_t)idx[p]; vals[base + p] = base + (uint32_t)p;
+}
+__global__ void xua_vstart_kernel(int64_t nvec, const uint32_t* __restrict__ keys, int64_t ndof, uint32_t* __restrict__ vstart) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nvec) return;
+    const uint32_t d = keys[s];
+    const int64_t prev = (s == 0) ? -1 : (int64_t)keys[s - 1];
+    for (int64_t c = prev + 1; c <= (int64_t)d; ++c) vstart[c] = (uint32_t)s;
+    if (s == nvec - 1) for (int64_t c = (int64_t)d + 1; c <= ndof; ++c) vstart[c] = (uint32_t)nvec;
+}
+__global__ void xua_asmvec_kernel(int64_t n, const int32_t* __restrict__ idx, int64_t* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) out[p] = (int64_t)idx[p] + 1;
+}
+__global__ void xua_widen_kernel(int64_t n, const int32_t* __restrict__ a, int64_t add, int64_t* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) out[p] = (int64_t)a[p] + add;
+}
+
+// ---- SparseTools.prepare on the device.  Blocks in CSC order of the block pattern; block b has class pair pat[b] (0..8), block row brow[b]; block column c
+// holds the blocks [bcolptr[c], bcolptr[c+1]).  pgr / pgc: first global row / column (0-based) of every block row / column.
+struct BigStruct {
+    int64_t nbc; const int32_t *bcolptr, *brow, *bpat; const int64_t *pg, *boff;      // pg: 0-based first global row (= column) of a block row, nbc+1 entries
+    const int32_t* pc[9]; const int32_t* pr[9];
+};
+__device__ __forceinline__ void big_decode_col(const BigStruct& B, int64_t c, int64_t& bc, int64_t& lc) {
+    int64_t lo = 0, hi = B.nbc;                      // largest bc with pg[bc] ≤ c
+    while (hi - lo > 1) { const int64_t m = (lo + hi) / 2; if (B.pg[m] <= c) lo = m; else hi = m; }
+    bc = lo; lc = c - B.pg[lo];
+}
+__global__ void xua_big_count_kernel(BigStruct B, int64_t ncol, int64_t* __restrict__ cnt) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    int64_t bc, lc; big_decode_col(B, c, bc, lc);
+    int64_t n = 0;
+    for (int32_t b = B.bcolptr[bc]; b < B.bcolptr[bc + 1]; ++b) { const int32_t* pc = B.pc[B.bpat[b]]; n += pc[lc + 1] - pc[lc]; }
+    cnt[c] = n;
+}
+__global__ void xua_big_fill_kernel(BigStruct B, int64_t ncol, const int64_t* __restrict__ colptr, int64_t* __restrict__ rowval, int64_t* __restrict__ basm) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    int64_t bc, lc; big_decode_col(B, c, bc, lc);
+    int64_t igv = colptr[c];
+    for (int32_t b = B.bcolptr[bc]; b < B.bcolptr[bc + 1]; ++b) {
+        const int p = B.bpat[b];
+        const int32_t* pc = B.pc[p]; const int32_t* pr = B.pr[p];
+        const int64_t r0 = B.pg[B.brow[b]];
+        for (int32_t ilv = pc[lc]; ilv < pc[lc + 1]; ++ilv) { rowval[igv] = r0 + pr[ilv]; basm[B.boff[b] + ilv] = igv + 1; ++igv; }
+    }
+}
+
+// ---- decrementbig! (src/DirectXUA.jl:357-383): one thread per (global step, class Λ/X/U, dof)
+struct XDec {
+    int nexp; int64_t cum[9]; int64_t ns[8]; double dtp[8][3];      // experiments: first global step, number of steps, Δt^(1−βder)
+    int64_t nX, nU, W; int OX, OU; int64_t nstot;
+    const double* dv; double *Lam, *X, *U; const double *scL, *scX, *scU;
+};
+__global__ void xua_decrement_kernel(XDec D) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= D.nstot * D.W) return;
+    const int64_t gs = q / D.W, r = q - gs * D.W;
+    int ie = 0; while (ie + 1 < D.nexp && gs >= D.cum[ie + 1]) ++ie;
+    const int64_t step = gs - D.cum[ie], n = D.ns[ie];
+    int cls; int64_t i;
+    if (r < D.nX) { cls = 0; i = r; } else if (r < 2 * D.nX) { cls = 1; i = r - D.nX; } else { cls = 2; i = r - 2 * D.nX; }
+    const int nder = (cls == 0) ? 1 : (cls == 1 ? D.OX + 1 : D.OU + 1);
+    const double sc = (cls == 0) ? (D.scL ? D.scL[i] : 1.) : (cls == 1 ? (D.scX ? D.scX[i] : 1.) : (D.scU ? D.scU[i] : 1.));
+    for (int der = 0; der < nder; ++der) {
+        double* x = (cls == 0) ? D.Lam + gs * D.nX + i : (cls == 1 ? D.X + (gs * 3 + der) * D.nX + i : D.U + (gs * 3 + der) * D.nU + i);
+        double v = *x;
+        for (int64_t ds = -2; ds <= 2; ++ds) {                       // stencil points in ascending Δs (src/FiniteDifferences.jl:8-31)
+            double w;
+            if (!fd_weight(der, n, step, ds, w)) continue;
+            const double d = D.dv[(gs + ds) * D.W + r];
+            v = __dsub_rn(v, __dmul_rn(__dmul_rn(__dmul_rn(d, w), D.dtp[ie][der]), sc));
+        }
+        *x = v;
+    }
+}
+__global__ void xua_decrementA_kernel(int64_t nA, const double* __restrict__ dv, const double* __restrict__ sc, double* __restrict__ A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nA) A[i] = __dsub_rn(A[i], __dmul_rn(dv[i], sc ? sc[i] : 1.));
+}
+// Σ Δβ² of one block per CUDA block: blocks 3·gs + class, then (optionally) the A block
+__global__ void __launch_bounds__(256) xua_sumsq_kernel(int64_t nX, int64_t nU, int64_t W, int64_t nblk3, int64_t nA, const double* __restrict__ dv, double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int64_t b = blockIdx.x;
+    int64_t n, off;
+    if (b < nblk3) { const int cls = (int)(b % 3); const int64_t k = b / 3; n = (cls == 2) ? nU : nX; off = k * W + (cls == 0 ? 0 : (cls == 1 ? nX : 2 * nX)); }
+    else { n = nA; off = (nblk3 / 3) * W; }
+    double a = 0.;
+    for (int64_t i = threadIdx.x; i < n; i += 256) { const double d = dv[off + i]; a += d * d; }
+    sh[threadIdx.x] = a; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) out[b] = sh[0];
+}
+
+}  // namespace
+
+struct XuaData {
+    int OX = 0, OU = 0, IA = 0, flags = 0;
+    int64_t ndof[3] = {0, 0, 0};                      // X, U, A
+    std::vector<XuaType> types;
+    int nexp = 0; std::vector<int64_t> nstep, cum; std::vector<double> dt;
+    int nder[4] = {1, 1, 1, 0}; int nL2[4][4][2];
+    bool prepared = false;
+    PairPat pat[3][3];
+    uint32_t *vstart[3] = {nullptr, nullptr, nullptr}, *vsrc[3] = {nullptr, nullptr, nullptr}; std::vector<int64_t> vbase[3];
+    double* L1[4] = {nullptr, nullptr, nullptr, nullptr};        // [α]: [nder α][ndof α]
+    double* L2[4][4];                                            // [α][β]: [nα][nβ][nnz(α,β)]
+    // all-steps system
+    int64_t nb = 0, nblock = 0, ngr = 0, nnzbig = 0;
+    std::vector<int32_t> bcolptr, brow, bpat, balpha, bbeta; std::vector<int64_t> pg, boff;
+    int32_t *d_bcolptr = nullptr, *d_brow = nullptr, *d_bpat = nullptr; int64_t *d_pg = nullptr, *d_boff = nullptr;
+    int64_t *colptr = nullptr, *rowval = nullptr, *basm = nullptr;      // 0-based colptr / rowval, 1-based basm (as Lvvasm)
+    double *nzval = nullptr, *Lv = nullptr;
+    Combo2* cb2 = nullptr; Combo1* cb1 = nullptr;
+    std::vector<int64_t> c2start, c1start;            // [(gs+1)·16 + 4α + β] → first combo (gs = −1: the A step), sentinel at the end; c1start: [(gs+1)·4 + β]
+    int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;
+    double *Lam = nullptr, *X = nullptr, *U = nullptr, *A = nullptr, *sc[4] = {nullptr, nullptr, nullptr, nullptr}, *dvbuf = nullptr;
+};
+
+void mb_xua_release(mb_handle* h) { delete h->xua; h->xua = nullptr; }
+
+static const int FDN[3][3] = {{1, 1, 1}, {2, 2, 2}, {3, 3, 3}};
+static const int FDS[3][3][3] = {{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, {{0, 1, 0}, {-1, 0, 0}, {-1, 1, 0}}, {{0, 1, 2}, {-2, -1, 0}, {-1, 0, 1}}};
+static const double FDW[3][3][3] = {{{1., 0, 0}, {1., 0, 0}, {1., 0, 0}}, {{-1., 1., 0}, {-1., 1., 0}, {-.5, .5, 0}}, {{1., -2., 1.}, {1., -2., 1.}, {1., -2., 1.}}};
+// finitediff(order,n,s) (src/FiniteDifferences.jl:8-31), s 1-based: number of stencil points, their Δs and weights
+static inline int fd_host(int order, int64_t n, int64_t s, const int** ds, const double** w) {
+    const int k = (order == 0) ? 0 : (s == 1 ? 0 : (s == n ? 1 : 2));
+    *ds = FDS[order][k]; *w = FDW[order][k];
+    return FDN[order][k];
+}
+
+extern "C" {
+
+int32_t mb_xua_add_eletyp(mb_handle* h, int64_t nele, int32_t nx, int32_t nu, int32_t na, const int64_t* idxX, const int64_t* idxU, const int64_t* idxA,
+                          int32_t acost, int32_t* ieletyp_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(nele >= 0 && nx >= 0 && nu >= 0 && na >= 0, "negative size");
+    ARG((nx == 0 || idxX) && (nu == 0 || idxU) && (na == 0 || idxA), "missing dof index array");
+    CK(cudaSetDevice(h->device));
+    if (!h->xua) h->xua = new XuaData();
+    XuaData* D = h->xua;
+    ARG(!D->prepared, "element types must be added before mb_xua_prepare");
+    ARG((int)D->types.size() < XMAXT, "too many element types");
+    XuaType T; T.nele = nele; T.n[0] = nx; T.n[1] = nu; T.n[2] = na; T.acost = acost ? 1 : 0;
+    const int64_t* src[3] = {idxX, idxU, idxA};
+    for (int c = 0; c < 3; ++c)
+        if (T.n[c] > 0 && nele > 0) { int32_t rc = upload_index(h, src[c], nele * T.n[c], 0, &T.idx[c]); if (rc) return rc; }
+    D->types.push_back(T);
+    if (ieletyp_out) *ieletyp_out = (int32_t)D->types.size();
+    return MB_OK;
+}
+
+int32_t mb_xua_prepare(mb_handle* h, int32_t OX, int32_t OU, int32_t IA, int64_t ndofX, int64_t ndofU, int64_t ndofA, int32_t nexp, const int64_t* nstep,
+                       const double* dt, int32_t flags, int64_t* nbig_out, int64_t* nnzbig_out) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(!D->prepared, "already prepared");
+    ARG(OX >= 0 && OX <= 2 && OU >= 0 && OU <= 2 && (IA == 0 || IA == 1), "OX, OU in 0..2, IA in 0..1");
+    ARG(nexp >= 1 && nexp <= 8 && nstep && dt, "1 to 8 experiments");
+    ARG(ndofX >= 0 && ndofU >= 0 && ndofA >= 0, "negative model size");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    D->OX = OX; D->OU = OU; D->IA = IA; D->flags = flags; D->nexp = nexp;
+    D->ndof[0] = ndofX; D->ndof[1] = ndofU; D->ndof[2] = ndofA;
+    D->nstep.assign(nstep, nstep + nexp); D->dt.assign(dt, dt + nexp);
+    D->cum.assign((size_t)nexp + 1, 0);
+    for (int e = 0; e < nexp; ++e) {
+        ARG(nstep[e] >= 1, "an experiment needs at least one step");
+        if ((OX > 0 || OU > 0) && nstep[e] < 6) { h->err = "Number of steps must be ≥6"; return MB_ERR_ARG; }      // src/FiniteDifferences.jl:9
+        D->cum[(size_t)e + 1] = D->cum[(size_t)e] + nstep[e];
+    }
+    const int nder[4] = {1, OX + 1, OU + 1, IA};
+    for (int a = 0; a < 4; ++a) D->nder[a] = nder[a];
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            int na = nder[a], nb = nder[b];
+            if (a == 0 && b == 0) { na = 0; nb = 0; }                                                   // Lλλ is always zero (src/DirectXUA.jl:41)
+            if ((flags & 1) && a == 1 && b == 1) { na = 1; nb = 1; }                                    // Xwhite
+            if ((flags & 2) && ((a == 1 && b == 2) || (a == 2 && b == 1))) { na = 0; nb = 0; }          // XUindep
+            if ((flags & 8) && ((a == 1 && b == 3) || (a == 3 && b == 1))) { na = 0; nb = 0; }          // XAindep
+            if ((flags & 4) && ((a == 2 && b == 3) || (a == 3 && b == 2))) { na = 0; nb = 0; }          // UAindep
+            if (na == 0 || nb == 0) { na = 0; nb = 0; }
+            D->nL2[a][b][0] = na; D->nL2[a][b][1] = nb;
+            D->L2[a][b] = nullptr;
+        }
+    // packets: order of partials Λ, X₀…, U₀…, A (src/DirectXUA.jl:127-135)
+    for (XuaType& T : D->types) {
+        int64_t mx[3] = {0, 0, 0};
+        (void)mx;
+        T.base[0] = 0; T.base[1] = T.n[0]; T.base[2] = T.base[1] + T.n[0] * (OX + 1); T.base[3] = T.base[2] + T.n[1] * (OU + 1);
+        T.Np = T.base[3] + T.n[2] * IA;
+    }
+    // dof numbers against the model sizes (an index beyond them would scatter outside the patterns)
+    for (size_t it = 0; it < D->types.size(); ++it)
+        for (int c = 0; c < 3; ++c) {
+            const XuaType& T = D->types[it];
+            const int64_t n = T.nele * T.n[c];
+            if (n == 0) continue;
+            int32_t* dmax = nullptr; CK(dalloc(h, &dmax, 1));
+            void* tmp = nullptr; size_t tsz = 0;
+            CK(cub::DeviceReduce::Max(nullptr, tsz, T.idx[c], dmax, n, st));
+            CK(cudaMalloc(&tmp, tsz ? tsz : 1));
+            CK(cub::DeviceReduce::Max(tmp, tsz, T.idx[c], dmax, n, st));
+            int32_t m = 0; CK(cudaMemcpyAsync(&m, dmax, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+            cudaFree(tmp); dfree(h, dmax);
+            if ((int64_t)m >= D->ndof[c]) { h->err = "element type " + std::to_string(it + 1) + ": dof index " + std::to_string(m + 1) + " exceeds the model's number of dofs of its class"; return MB_ERR_ARG; }
+        }
+    // ---- class-pair patterns (asmmat!) for the nine pairs of dof groups, and per-class contributor lists (asmvec!)
+    for (int ca = 0; ca < 3; ++ca)
+        for (int cb = 0; cb < 3; ++cb) {
+            std::vector<PatSide> rows, cols;
+            for (const XuaType& T : D->types) { rows.push_back({T.nele, T.n[ca], T.idx[ca]}); cols.push_back({T.nele, T.n[cb], T.idx[cb]}); }
+            int32_t rc = build_pair_pattern(h, D->pat[ca][cb], rows, cols, D->ndof[ca], D->ndof[cb]);
+            if (rc) return rc;
+        }
+    for (int c = 0; c < 3; ++c) {
+        int64_t nv = 0; D->vbase[c].clear();
+        for (const XuaType& T : D->types) { D->vbase[c].push_back(nv); nv += T.nele * T.n[c]; }
+        D->vbase[c].push_back(nv);
+        ARG(nv < (int64_t)UINT32_MAX, "more than 2^32 element dofs of one class");
+        CK(dalloc(h, &D->vstart[c], D->ndof[c] + 1)); CK(dalloc(h, &D->vsrc[c], nv));
+        CK(cudaMemsetAsync(D->vstart[c], 0, (size_t)(D->ndof[c] + 1) * 4, st));
+        if (nv == 0) continue;
+        uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
+        CK(dalloc(h, &keys, nv)); CK(dalloc(h, &keys2, nv)); CK(dalloc(h, &vals, nv));
+        for (size_t it = 0; it < D->types.size(); ++it) {
+            const XuaType& T = D->types[it];
+            const int64_t n = T.nele * T.n[c];
+            if (n) { xua_vec_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(n, T.idx[c], keys, vals, (uint32_t)D->vbase[c][it]); h->launches++; }
+        }
+        void* tmp = nullptr; size_t tsz = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tsz, keys, keys2, vals, D->vsrc[c], nv, 0, 32, st));
+        CK(cudaMalloc(&tmp, tsz ? tsz : 1));
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tsz, keys, keys2, vals, D->vsrc[c], nv, 0, 32, st));
+        xua_vstart_kernel<<<nblk(nv, 256), 256, 0, st>>>(nv, keys2, D->ndof[c], D->vstart[c]);
+        h->launches += 2;
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+        dfree(h, keys); dfree(h, keys2); dfree(h, vals);
+    }
+    // ---- out: L1[α][αder], L2[α,β][αder,βder] of one step
+    for (int a = 0; a < 4; ++a) { const int64_t n = (int64_t)std::max(nder[a], 1) * D->ndof[cgroup(a)]; CK(dalloc(h, &D->L1[a], n)); CK(cudaMemsetAsync(D->L1[a], 0, (size_t)std::max<int64_t>(n, 1) * 8, st)); }
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            const int64_t n = (int64_t)D->nL2[a][b][0] * D->nL2[a][b][1] * D->pat[cgroup(a)][cgroup(b)].nnz;
+            if (n > 0) { CK(dalloc(h, &D->L2[a][b], n)); CK(cudaMemsetAsync(D->L2[a][b], 0, (size_t)n * 8, st)); }
+        }
+    // ---- makepattern (src/DirectXUA.jl:245-307): the set of blocks, in CSC order; block numbers 0-based: 3·(global step) + class, then the A block
+    int64_t nstot = D->cum[(size_t)nexp];
+    const int64_t Ablk = 3 * nstot;
+    D->nb = 3 * nstot + (IA ? 1 : 0);
+    std::map<std::pair<int64_t, int64_t>, std::pair<int, int>> blocks;      // (column, row) → (α, β)
+    for (int e = 0; e < nexp; ++e)
+        for (int64_t s = 1; s <= nstep[e]; ++s)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    for (int ad = 0; ad < D->nL2[a][b][0]; ++ad)
+                        for (int bd = 0; bd < D->nL2[a][b][1]; ++bd) {
+                            const int *dsa, *dsb; const double *wa, *wb;
+                            const int na = fd_host(ad, nstep[e], s, &dsa, &wa), nb = fd_host(bd, nstep[e], s, &dsb, &wb);
+                            for (int p = 0; p < na; ++p)
+                                for (int q = 0; q < nb; ++q)
+                                    blocks.emplace(std::make_pair(3 * (D->cum[(size_t)e] + s + dsb[q] - 1) + b, 3 * (D->cum[(size_t)e] + s + dsa[p] - 1) + a), std::make_pair(a, b));
+                        }
+    if (IA) {
+        blocks.emplace(std::make_pair(Ablk, Ablk), std::make_pair(3, 3));
+        for (int64_t gs = 0; gs < nstot; ++gs)
+            for (int a = 0; a < 3; ++a)
+                if (D->nL2[3][a][0] > 0) {
+                    blocks.emplace(std::make_pair(3 * gs + a, Ablk), std::make_pair(3, a));
+                    blocks.emplace(std::make_pair(Ablk, 3 * gs + a), std::make_pair(a, 3));
+                }
+    }
+    D->nblock = (int64_t)blocks.size();
+    D->bcolptr.assign((size_t)D->nb + 1, 0); D->brow.clear(); D->bpat.clear(); D->balpha.clear(); D->bbeta.clear(); D->boff.assign(1, 0);
+    for (const auto& kv : blocks) {
+        D->bcolptr[(size_t)kv.first.first + 1]++;
+        D->brow.push_back((int32_t)kv.first.second);
+        D->balpha.push_back(kv.second.first); D->bbeta.push_back(kv.second.second);
+        const int p = 3 * cgroup(kv.second.first) + cgroup(kv.second.second);
+        D->bpat.push_back(p);
+        D->boff.push_back(D->boff.back() + D->pat[p / 3][p % 3].nnz);
+    }
+    for (int64_t c = 0; c < D->nb; ++c) D->bcolptr[(size_t)c + 1] += D->bcolptr[(size_t)c];
+    // every block row / column must hold a block (src/SparseTools.jl:52-61), sizes by class
+    D->pg.assign((size_t)D->nb + 1, 0);
+    {
+        std::vector<char> seenr((size_t)D->nb, 0);
+        for (int32_t r : D->brow) seenr[(size_t)r] = 1;
+        for (int64_t c = 0; c < D->nb; ++c)
+            if (D->bcolptr[(size_t)c + 1] == D->bcolptr[(size_t)c] || !seenr[(size_t)c]) { h->err = "invalid sparse-of-sparse pattern: block row or column " + std::to_string(c + 1) + " has only empty blocks"; return MB_ERR_ARG; }
+        for (int64_t c = 0; c < D->nb; ++c) {
+            const int cls = (c == Ablk && IA) ? 3 : (int)(c % 3);
+            D->pg[(size_t)c + 1] = D->pg[(size_t)c] + D->ndof[cgroup(cls)];
+        }
+    }
+    D->ngr = D->pg[(size_t)D->nb];
+    D->nnzbig = D->boff.back();
+    CK(dalloc(h, &D->d_bcolptr, D->nb + 1)); CK(dalloc(h, &D->d_brow, D->nblock)); CK(dalloc(h, &D->d_bpat, D->nblock)); CK(dalloc(h, &D->d_pg, D->nb + 1)); CK(dalloc(h, &D->d_boff, D->nblock + 1));
+    CK(cudaMemcpyAsync(D->d_bcolptr, D->bcolptr.data(), (size_t)(D->nb + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D->d_brow, D->brow.data(), (size_t)D->nblock * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D->d_bpat, D->bpat.data(), (size_t)D->nblock * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D->d_pg, D->pg.data(), (size_t)(D->nb + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(D->d_boff, D->boff.data(), (size_t)(D->nblock + 1) * 8, cudaMemcpyHostToDevice, st));
+    // ---- SparseTools.prepare: Lvv structure and Lvvasm
+    CK(dalloc(h, &D->colptr, D->ngr + 1)); CK(dalloc(h, &D->rowval, D->nnzbig)); CK(dalloc(h, &D->basm, D->nnzbig)); CK(dalloc(h, &D->nzval, D->nnzbig)); CK(dalloc(h, &D->Lv, D->ngr));
+    BigStruct B;
+    B.nbc = D->nb; B.bcolptr = D->d_bcolptr; B.brow = D->d_brow; B.bpat = D->d_bpat; B.pg = D->d_pg; B.boff = D->d_boff;
+    for (int p = 0; p < 9; ++p) { B.pc[p] = D->pat[p / 3][p % 3].colptr0; B.pr[p] = D->pat[p / 3][p % 3].rowval0; }
+    if (D->ngr > 0) {
+        int64_t* cnt = nullptr; CK(dalloc(h, &cnt, D->ngr + 1));
+        CK(cudaMemsetAsync(cnt, 0, (size_t)(D->ngr + 1) * 8, st));
+        xua_big_count_kernel<<<nblk(D->ngr, 256), 256, 0, st>>>(B, D->ngr, cnt);
+        void* tmp = nullptr; size_t tsz = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tsz, cnt, D->colptr, D->ngr + 1, st));
+        CK(cudaMalloc(&tmp, tsz ? tsz : 1));
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tsz, cnt, D->colptr, D->ngr + 1, st));
+        if (D->nnzbig > 0) xua_big_fill_kernel<<<nblk(D->ngr, 256), 256, 0, st>>>(B, D->ngr, D->colptr, D->rowval, D->basm);
+        h->launches += 3;
+        CK(cudaStreamSynchronize(st)); cudaFree(tmp); dfree(h, cnt);
+    }
+    // ---- the weighted additions of assemblebig! (src/DirectXUA.jl:332-352), tabulated per global step (entry 0: the A step of :321-326)
+    auto find_block = [&](int64_t ibr, int64_t ibc) -> int64_t {
+        for (int32_t b = D->bcolptr[(size_t)ibc]; b < D->bcolptr[(size_t)ibc + 1]; ++b) if (D->brow[(size_t)b] == ibr) return b;
+        return -1;
+    };
+    std::vector<Combo2> c2; std::vector<Combo1> c1;
+    D->c2start.assign((size_t)(nstot + 1) * 16 + 1, 0); D->c1start.assign((size_t)(nstot + 1) * 4 + 1, 0);
+    const int ncls = IA ? 4 : 3;
+    for (int a = 0; a < 4; ++a) {                 // the A step
+        D->c1start[(size_t)a] = (int64_t)c1.size();
+        if (IA && a == 3) c1.push_back({0, 1., D->pg[(size_t)Ablk]});
+        for (int b = 0; b < 4; ++b) {
+            D->c2start[(size_t)(4 * a + b)] = (int64_t)c2.size();
+            if (IA && a == 3 && b == 3) c2.push_back({0, 0, 1., D->boff[(size_t)find_block(Ablk, Ablk)]});
+        }
+    }
+    for (int e = 0; e < nexp; ++e)
+        for (int64_t s = 1; s <= nstep[e]; ++s) {
+            const int64_t gs = D->cum[(size_t)e] + s - 1;
+            for (int b = 0; b < 4; ++b) {
+                D->c1start[(size_t)((gs + 1) * 4 + b)] = (int64_t)c1.size();
+                if (b >= ncls) continue;
+                for (int bd = 0; bd < nder[b]; ++bd) {
+                    const double sc = std::pow(dt[e], -bd);                           // Δt^(1−βder)
+                    const int* ds; const double* w;
+                    const int n = fd_host(bd, nstep[e], s, &ds, &w);
+                    for (int q = 0; q < n; ++q) {
+                        const int64_t blk = (b == 3) ? Ablk : 3 * (gs + ds[q]) + b;
+                        c1.push_back({bd, w[q] * sc, D->pg[(size_t)blk]});
+                    }
+                }
+            }
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) {
+                    D->c2start[(size_t)((gs + 1) * 16 + 4 * a + b)] = (int64_t)c2.size();
+                    if (a >= ncls || b >= ncls) continue;
+                    for (int ad = 0; ad < D->nL2[a][b][0]; ++ad)
+                        for (int bd = 0; bd < D->nL2[a][b][1]; ++bd) {
+                            const double sc = std::pow(dt[e], -(ad + bd));            // Δt^(2−αder−βder)
+                            const int *dsa, *dsb; const double *wa, *wb;
+                            const int na = fd_host(ad, nstep[e], s, &dsa, &wa), nb = fd_host(bd, nstep[e], s, &dsb, &wb);
+                            for (int p = 0; p < na; ++p)
+                                for (int q = 0; q < nb; ++q) {
+                                    const int64_t ab = (a == 3) ? Ablk : 3 * (gs + dsa[p]) + a, bb = (b == 3) ? Ablk : 3 * (gs + dsb[q]) + b;
+                                    const int64_t blk = find_block(ab, bb);
+                                    if (blk < 0) { h->err = "BlockSparseAssembler pattern has no block [" + std::to_string(ab + 1) + "," + std::to_string(bb + 1) + "]"; return MB_ERR_STATE; }
+                                    c2.push_back({ad, bd, wa[p] * wb[q] * sc, D->boff[(size_t)blk]});
+                                }
+                        }
+                }
+        }
+    D->c2start.back() = (int64_t)c2.size(); D->c1start.back() = (int64_t)c1.size();
+    CK(dalloc(h, &D->cb2, (int64_t)c2.size())); CK(dalloc(h, &D->cb1, (int64_t)c1.size()));
+    if (!c2.empty()) CK(cudaMemcpy(D->cb2, c2.data(), c2.size() * sizeof(Combo2), cudaMemcpyHostToDevice));
+    if (!c1.empty()) CK(cudaMemcpy(D->cb1, c1.data(), c1.size() * sizeof(Combo1), cudaMemcpyHostToDevice));
+    // ---- states (decrementbig!)
+    CK(dalloc(h, &D->Lam, nstot * ndofX)); CK(dalloc(h, &D->X, nstot * 3 * ndofX)); CK(dalloc(h, &D->U, nstot * 3 * ndofU)); CK(dalloc(h, &D->A, ndofA));
+    CK(cudaMemsetAsync(D->Lam, 0, (size_t)std::max<int64_t>(nstot * ndofX, 1) * 8, st)); CK(cudaMemsetAsync(D->X, 0, (size_t)std::max<int64_t>(nstot * 3 * ndofX, 1) * 8, st));
+    CK(cudaMemsetAsync(D->U, 0, (size_t)std::max<int64_t>(nstot * 3 * ndofU, 1) * 8, st)); CK(cudaMemsetAsync(D->A, 0, (size_t)std::max<int64_t>(ndofA, 1) * 8, st));
+    CK(cudaMemsetAsync(D->nzval, 0, (size_t)std::max<int64_t>(D->nnzbig, 1) * 8, st)); CK(cudaMemsetAsync(D->Lv, 0, (size_t)std::max<int64_t>(D->ngr, 1) * 8, st));
+    CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    D->prepared = true;
+    if (nbig_out) *nbig_out = D->ngr;
+    if (nnzbig_out) *nnzbig_out = D->nnzbig;
+    return MB_OK;
+}
+
+#define XUA_READY()                                                                     \
+    if (!h || !h->xua) return MB_ERR_ARG;                                               \
+    XuaData* D = h->xua;                                                                \
+    ARG(D->prepared, "call mb_xua_prepare first");                                      \
+    CK(cudaSetDevice(h->device));                                                       \
+    cudaStream_t st = h->stream; (void)st;
+
+int32_t mb_xua_class_pattern(mb_handle* h, int32_t alpha, int32_t beta, int64_t* nnz, int64_t* colptr, int64_t* rowval) {
+    XUA_READY();
+    ARG(alpha >= 1 && alpha <= 4 && beta >= 1 && beta <= 4, "class numbers are 1..4 (Λ,X,U,A)");
+    const PairPat& P = D->pat[cgroup(alpha - 1)][cgroup(beta - 1)];
+    if (nnz) *nnz = P.nnz;
+    if (colptr) {
+        int64_t* tmp = nullptr; CK(dalloc(h, &tmp, P.n + 1));
+        xua_widen_kernel<<<nblk(P.n + 1, 256), 256, 0, st>>>(P.n + 1, P.colptr0, 1, tmp);
+        CK(cudaMemcpyAsync(colptr, tmp, (size_t)(P.n + 1) * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); dfree(h, tmp);
+    }
+    if (rowval && P.nnz) {
+        int64_t* tmp = nullptr; CK(dalloc(h, &tmp, P.nnz));
+        xua_widen_kernel<<<nblk(P.nnz, 256), 256, 0, st>>>(P.nnz, P.rowval0, 1, tmp);
+        CK(cudaMemcpyAsync(rowval, tmp, (size_t)P.nnz * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); dfree(h, tmp);
+    }
+    return MB_OK;
+}
+
+/* asm[arrnum(α),ieletyp] (beta = 0: n_α × nele) or asm[arrnum(α,β),ieletyp] (n_α·n_β × nele), column-major as the reference stores them, 1-based */
+int32_t mb_xua_get_asm(mb_handle* h, int32_t ieletyp, int32_t alpha, int32_t beta, int64_t* out) {
+    XUA_READY();
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && alpha >= 1 && alpha <= 4 && beta >= 0 && beta <= 4 && out, "bad argument");
+    const XuaType& T = D->types[(size_t)ieletyp - 1];
+    const int ca = cgroup(alpha - 1);
+    if (beta == 0) {
+        const int64_t n = T.nele * T.n[ca];
+        if (n == 0) return MB_OK;
+        int64_t* tmp = nullptr; CK(dalloc(h, &tmp, n));
+        xua_asmvec_kernel<<<nblk(n, 256), 256, 0, st>>>(n, T.idx[ca], tmp);
+        CK(cudaMemcpyAsync(out, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); dfree(h, tmp);
+        return MB_OK;
+    }
+    const int cb = cgroup(beta - 1);
+    const PairPat& P = D->pat[ca][cb];
+    const int64_t n = T.nele * T.n[ca] * T.n[cb];
+    if (n == 0) return MB_OK;
+    int64_t* tmp = nullptr; CK(dalloc(h, &tmp, n));
+    xua_widen_kernel<<<nblk(n, 256), 256, 0, st>>>(n, P.asmK + P.gbase[(size_t)ieletyp - 1], 0, tmp);
+    CK(cudaMemcpyAsync(out, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); dfree(h, tmp);
+    return MB_OK;
+}
+
+int32_t mb_xua_big_pattern(mb_handle* h, int64_t* colptr, int64_t* rowval) {
+    XUA_READY();
+    if (colptr) { CK(cudaMemcpy(colptr, D->colptr, (size_t)(D->ngr + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ngr; ++i) colptr[i] += 1; }
+    if (rowval && D->nnzbig) { CK(cudaMemcpy(rowval, D->rowval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->nnzbig; ++i) rowval[i] += 1; }
+    return MB_OK;
+}
+
+/* Lvvasm (bcolptr nb+1, browval nblock, 1-based; block b's Lvv positions are basm[boff[b] .. boff[b+1]), 1-based) and Lvasm = pgr (nb+1, 1-based) */
+int32_t mb_xua_big_asm(mb_handle* h, int64_t* nb, int64_t* nblock, int64_t* bcolptr, int64_t* browval, int64_t* boff, int64_t* basm, int64_t* pgr) {
+    XUA_READY();
+    if (nb) *nb = D->nb;
+    if (nblock) *nblock = D->nblock;
+    if (bcolptr) for (int64_t i = 0; i <= D->nb; ++i) bcolptr[i] = D->bcolptr[(size_t)i] + 1;
+    if (browval) for (int64_t i = 0; i < D->nblock; ++i) browval[i] = D->brow[(size_t)i] + 1;
+    if (boff) for (int64_t i = 0; i <= D->nblock; ++i) boff[i] = D->boff[(size_t)i];
+    if (basm && D->nnzbig) CK(cudaMemcpy(basm, D->basm, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost));
+    if (pgr) for (int64_t i = 0; i <= D->nb; ++i) pgr[i] = D->pg[(size_t)i] + 1;
+    return MB_OK;
+}
+
+int32_t mb_xua_zero(mb_handle* h) {
+    XUA_READY();
+    CK(cudaMemsetAsync(D->nzval, 0, (size_t)std::max<int64_t>(D->nnzbig, 1) * 8, st));
+    CK(cudaMemsetAsync(D->Lv, 0, (size_t)std::max<int64_t>(D->ngr, 1) * 8, st));
+    for (XuaType& T : D->types) T.has = false;
+    D->cnnz = -1;
+    return MB_OK;
+}
+
+/* ∇L [nele][Np], ∇²L [nele][Np][Np] of one element type for the step about to be added (host or device memory; NULL ∇²L = zeros) */
+int32_t mb_xua_set_packet(mb_handle* h, int32_t ieletyp, const double* gradL, const double* hessL) {
+    XUA_READY();
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size(), "no such element type");
+    XuaType& T = D->types[(size_t)ieletyp - 1];
+    const int64_t ng = T.nele * T.Np, nh = ng * T.Np;
+    if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(dalloc(h, &T.H, nh)); }
+    if (gradL && ng) CK(cudaMemcpyAsync(T.g, gradL, (size_t)ng * 8, cudaMemcpyDefault, st)); else CK(cudaMemsetAsync(T.g, 0, (size_t)std::max<int64_t>(ng, 1) * 8, st));
+    if (hessL && nh) CK(cudaMemcpyAsync(T.H, hessL, (size_t)nh * 8, cudaMemcpyDefault, st)); else CK(cudaMemsetAsync(T.H, 0, (size_t)std::max<int64_t>(nh, 1) * 8, st));
+    CK(cudaStreamSynchronize(st));             // the caller may reuse its buffers
+    T.has = true;
+    return MB_OK;
+}
+
+// assemble!(out) of the packets at hand (acost: assembleA!, only Acost types; else EVERY type — as the reference is written its Acost vectors also go through assemble!,
+// src/Assemble.jl:477 does not match them; pinned by test/TestDirectXUA.jl:107), then the weighted additions of entry `slot` of the tables
+static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_t slot) {
+    cudaStream_t st = h->stream;
+    const int ncls = 4;
+    for (int a = 0; a < ncls; ++a) {
+        const int ca = cgroup(a);
+        const int nd = D->nder[a];
+        if (nd == 0 || D->ndof[ca] == 0) continue;
+        TabDev T; T.n = (int)D->types.size();
+        for (int t = 0; t < T.n; ++t) {
+            const XuaType& Y = D->types[(size_t)t];
+            T.pbase[t] = (uint32_t)D->vbase[ca][(size_t)t]; T.ni[t] = Y.n[ca]; T.nj[t] = 0; T.Np[t] = Y.Np; T.bi[t] = Y.base[a]; T.bj[t] = 0;
+            T.p[t] = (Y.has && (!acost || Y.acost) && (a != 3 || D->IA)) ? Y.g : nullptr;
+        }
+        T.pbase[T.n] = (uint32_t)D->vbase[ca][(size_t)T.n];
+        xua_gather1_kernel<<<dim3(nblk(D->ndof[ca], 128), (unsigned)nd), 128, 0, st>>>(D->ndof[ca], D->vstart[ca], D->vsrc[ca], T, D->L1[a]);
+        h->launches++;
+        const int64_t c0 = D->c1start[(size_t)(slot * 4 + a)], c1 = D->c1start[(size_t)(slot * 4 + a + 1)];
+        if (c1 > c0) { xua_addin1_kernel<<<nblk(D->ndof[ca], 128), 128, 0, st>>>(D->ndof[ca], D->L1[a], D->cb1 + c0, (int)(c1 - c0), D->Lv); h->launches++; }
+    }
+    for (int a = 0; a < ncls; ++a)
+        for (int b = 0; b < ncls; ++b) {
+            const int na = D->nL2[a][b][0], nb = D->nL2[a][b][1];
+            const PairPat& P = D->pat[cgroup(a)][cgroup(b)];
+            if (na == 0 || nb == 0 || P.nnz == 0) continue;
+            TabDev T; T.n = (int)D->types.size();
+            for (int t = 0; t < T.n; ++t) {
+                const XuaType& Y = D->types[(size_t)t];
+                T.pbase[t] = (uint32_t)P.gbase[(size_t)t]; T.ni[t] = Y.n[cgroup(a)]; T.nj[t] = Y.n[cgroup(b)]; T.Np[t] = Y.Np; T.bi[t] = Y.base[a]; T.bj[t] = Y.base[b];
+                T.p[t] = (Y.has && (!acost || Y.acost)) ? Y.H : nullptr;
+            }
+            T.pbase[T.n] = (uint32_t)P.gbase[(size_t)T.n];
+            xua_gather2_kernel<<<dim3(nblk(P.nnz, 128), (unsigned)(na * nb)), 128, 0, st>>>(P.nnz, P.cstart, P.src, T, nb, D->L2[a][b]);
+            h->launches++;
+            const int64_t c0 = D->c2start[(size_t)(slot * 16 + 4 * a + b)], c1 = D->c2start[(size_t)(slot * 16 + 4 * a + b + 1)];
+            if (c1 > c0) { xua_addin2_kernel<<<nblk(P.nnz, 128), 128, 0, st>>>(P.nnz, D->L2[a][b], nb, D->cb2 + c0, (int)(c1 - c0), D->basm, D->nzval); h->launches++; }
+        }
+    for (XuaType& Y : D->types) if (!acost || Y.acost) Y.has = false;
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+
+/* assembleA!{:matrices} of the Acost packets and its addition into the A block (src/DirectXUA.jl:320-326); IA = 1 only */
+int32_t mb_xua_add_A(mb_handle* h) {
+    XUA_READY();
+    ARG(D->IA == 1, "IA = 0: there is no A block");
+    return xua_assemble_and_add(h, D, true, 0);
+}
+/* assemble!{:matrices}(out,…,state[iexp][istep]) from the packets set since the last call, then its finite-difference weighted addition into Lvv / Lv
+ * (src/DirectXUA.jl:328-353). iexp, istep 1-based. */
+int32_t mb_xua_add_step(mb_handle* h, int32_t iexp, int64_t istep) {
+    XUA_READY();
+    ARG(iexp >= 1 && iexp <= D->nexp && istep >= 1 && istep <= D->nstep[(size_t)iexp - 1], "no such step");
+    return xua_assemble_and_add(h, D, false, D->cum[(size_t)iexp - 1] + istep);
+}
+
+/* out of the last mb_xua_add_step / mb_xua_add_A: beta = 0 → L1[α][ader] (ndof α), else L2[α,β][ader,bder].nzval; classes and derivatives 1-based */
+int32_t mb_xua_get_out(mb_handle* h, int32_t alpha, int32_t beta, int32_t ader, int32_t bder, double* out) {
+    XUA_READY();
+    ARG(alpha >= 1 && alpha <= 4 && beta >= 0 && beta <= 4 && out, "bad argument");
+    const int a = alpha - 1;
+    if (beta == 0) {
+        ARG(ader >= 1 && ader <= std::max(D->nder[a], 0), "L1 has no such derivative");
+        const int64_t n = D->ndof[cgroup(a)];
+        if (n) CK(cudaMemcpyAsync(out, D->L1[a] + (int64_t)(ader - 1) * n, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        const int b = beta - 1;
+        ARG(ader >= 1 && ader <= D->nL2[a][b][0] && bder >= 1 && bder <= D->nL2[a][b][1], "L2 has no such block");
+        const int64_t n = D->pat[cgroup(a)][cgroup(b)].nnz;
+        if (n) CK(cudaMemcpyAsync(out, D->L2[a][b] + (int64_t)((ader - 1) * D->nL2[a][b][1] + (bder - 1)) * n, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return MB_OK;
+}
+/* size(out.L2[α,β]) (src/DirectXUA.jl:38-50) */
+int32_t mb_xua_out_shape(mb_handle* h, int32_t alpha, int32_t beta, int32_t* na, int32_t* nb) {
+    XUA_READY();
+    ARG(alpha >= 1 && alpha <= 4 && beta >= 1 && beta <= 4, "bad class");
+    if (na) *na = D->nL2[alpha - 1][beta - 1][0];
+    if (nb) *nb = D->nL2[alpha - 1][beta - 1][1];
+    return MB_OK;
+}
+
+int32_t mb_xua_get_big(mb_handle* h, double* Lvv_nzval, double* Lv) {
+    XUA_READY();
+    if (Lvv_nzval && D->nnzbig) CK(cudaMemcpyAsync(Lvv_nzval, D->nzval, (size_t)D->nnzbig * 8, cudaMemcpyDeviceToHost, st));
+    if (Lv && D->ngr) CK(cudaMemcpyAsync(Lv, D->Lv, (size_t)D->ngr * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MB_OK;
+}
+
+int32_t mb_xua_sparser(mb_handle* h, double rtol, int64_t* nnz_out) {
+    XUA_READY();
+    const int64_t nnz = D->nnzbig;
+    ARG(nnz > 0, "empty system");
+    if (!D->ccolptr) { CK(dalloc(h, &D->ccolptr, D->ngr + 1)); CK(dalloc(h, &D->crowval, nnz)); CK(dalloc(h, &D->cnzval, nnz)); }
+    double* dmax = nullptr; int64_t* pos = nullptr;
+    CK(dalloc(h, &dmax, 1)); CK(dalloc(h, &pos, nnz));
+    void* tmp = nullptr; size_t t1 = 0, t2 = 0;
+    cub::TransformInputIterator<double, AbsF, const double*> absit(D->nzval, AbsF{});
+    CK(cub::DeviceReduce::Max(nullptr, t1, absit, dmax, nnz, st));
+    cub::CountingInputIterator<int64_t> ids(0);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, cub::TransformInputIterator<int64_t, KeepF, cub::CountingInputIterator<int64_t>>(ids, KeepF{D->nzval, 0.}), pos, nnz, st));
+    size_t tsz = std::max(t1, t2) + 1;
+    CK(cudaMalloc(&tmp, tsz));
+    CK(cub::DeviceReduce::Max(tmp, tsz, absit, dmax, nnz, st));
+    double hmax = 0.;
+    CK(cudaMemcpyAsync(&hmax, dmax, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double atol = rtol * hmax;
+    tsz = std::max(t1, t2) + 1;
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tsz, cub::TransformInputIterator<int64_t, KeepF, cub::CountingInputIterator<int64_t>>(ids, KeepF{D->nzval, atol}), pos, nnz, st));
+    int64_t lastpos = 0; double lastv = 0.;
+    CK(cudaMemcpyAsync(&lastpos, pos + (nnz - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lastv, D->nzval + (nnz - 1), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t nkeep = lastpos + (fabs(lastv) >= atol ? 1 : 0);
+    sparser_scatter_kernel<<<nblk(nnz, 256), 256, 0, st>>>(nnz, D->nzval, D->rowval, pos, atol, D->cnzval, D->crowval);
+    sparser_colptr_kernel<<<nblk(D->ngr + 1, 256), 256, 0, st>>>(D->ngr, nnz, D->colptr, pos, nkeep, D->ccolptr);
+    h->launches += 4;
+    CK(cudaStreamSynchronize(st));
+    cudaFree(tmp); dfree(h, dmax); dfree(h, pos);
+    D->cnnz = nkeep;
+    if (nnz_out) *nnz_out = nkeep;
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+int32_t mb_xua_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval) {
+    XUA_READY();
+    ARG(D->cnnz >= 0, "call mb_xua_sparser first");
+    if (colptr) { CK(cudaMemcpy(colptr, D->ccolptr, (size_t)(D->ngr + 1) * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i <= D->ngr; ++i) colptr[i] += 1; }
+    if (rowval && D->cnnz) { CK(cudaMemcpy(rowval, D->crowval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost)); for (int64_t i = 0; i < D->cnnz; ++i) rowval[i] += 1; }
+    if (nzval && D->cnnz) CK(cudaMemcpy(nzval, D->cnzval, (size_t)D->cnnz * 8, cudaMemcpyDeviceToHost));
+    return MB_OK;
+}
+
+/* state[iexp][istep] (1-based): Λ (nX), X [(OX+1)][nX], U [(OU+1)][nU]; A (nA) is shared by all states (src/DirectXUA.jl:452). NULL leaves a part as it is. */
+int32_t mb_xua_set_state(mb_handle* h, int32_t iexp, int64_t istep, const double* Lambda, const double* X, const double* U, const double* A) {
+    XUA_READY();
+    ARG(iexp >= 1 && iexp <= D->nexp && istep >= 1 && istep <= D->nstep[(size_t)iexp - 1], "no such step");
+    const int64_t gs = D->cum[(size_t)iexp - 1] + istep - 1, nX = D->ndof[0], nU = D->ndof[1], nA = D->ndof[2];
+    if (Lambda && nX) CK(cudaMemcpyAsync(D->Lam + gs * nX, Lambda, (size_t)nX * 8, cudaMemcpyDefault, st));
+    if (X && nX) CK(cudaMemcpyAsync(D->X + gs * 3 * nX, X, (size_t)(nX * (D->OX + 1)) * 8, cudaMemcpyDefault, st));
+    if (U && nU) CK(cudaMemcpyAsync(D->U + gs * 3 * nU, U, (size_t)(nU * (D->OU + 1)) * 8, cudaMemcpyDefault, st));
+    if (A && nA) CK(cudaMemcpyAsync(D->A, A, (size_t)nA * 8, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    return MB_OK;
+}
+int32_t mb_xua_get_state(mb_handle* h, int32_t iexp, int64_t istep, double* Lambda, double* X, double* U, double* A) {
+    XUA_READY();
+    ARG(iexp >= 1 && iexp <= D->nexp && istep >= 1 && istep <= D->nstep[(size_t)iexp - 1], "no such step");
+    const int64_t gs = D->cum[(size_t)iexp - 1] + istep - 1, nX = D->ndof[0], nU = D->ndof[1], nA = D->ndof[2];
+    if (Lambda && nX) CK(cudaMemcpyAsync(Lambda, D->Lam + gs * nX, (size_t)nX * 8, cudaMemcpyDefault, st));
+    if (X && nX) CK(cudaMemcpyAsync(X, D->X + gs * 3 * nX, (size_t)(nX * (D->OX + 1)) * 8, cudaMemcpyDefault, st));
+    if (U && nU) CK(cudaMemcpyAsync(U, D->U + gs * 3 * nU, (size_t)(nU * (D->OU + 1)) * 8, cudaMemcpyDefault, st));
+    if (A && nA) CK(cudaMemcpyAsync(A, D->A, (size_t)nA * 8, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    return MB_OK;
+}
+int32_t mb_xua_set_dof_scale(mb_handle* h, const double* sL, const double* sX, const double* sU, const double* sA) {
+    XUA_READY();
+    const double* src[4] = {sL, sX, sU, sA};
+    for (int a = 0; a < 4; ++a) {
+        const int64_t n = D->ndof[cgroup(a)];
+        if (!src[a] || n == 0) continue;
+        if (!D->sc[a]) CK(dalloc(h, &D->sc[a], n));
+        CK(cudaMemcpyAsync(D->sc[a], src[a], (size_t)n * 8, cudaMemcpyDefault, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return MB_OK;
+}
+/* decrementbig!(state,Δ²,Lvdis,dofgr,Δv,nder,Δt,nstep) (src/DirectXUA.jl:357-383): dv = Δv (size of Lv, host or device) → Δ²[Λ,X,U,(A)] */
+int32_t mb_xua_decrement(mb_handle* h, const double* dv, double* delta2) {
+    XUA_READY();
+    ARG(dv, "dv missing");
+    const int64_t nX = D->ndof[0], nU = D->ndof[1], nA = D->ndof[2], W = 2 * nX + nU, nstot = D->cum[(size_t)D->nexp];
+    if (!D->dvbuf) CK(dalloc(h, &D->dvbuf, D->ngr));
+    CK(cudaMemcpyAsync(D->dvbuf, dv, (size_t)D->ngr * 8, cudaMemcpyDefault, st));
+    XDec X; X.nexp = D->nexp;
+    for (int e = 0; e < D->nexp; ++e) { X.cum[e] = D->cum[(size_t)e]; X.ns[e] = D->nstep[(size_t)e]; const double inv = 1. / D->dt[(size_t)e]; X.dtp[e][0] = 1.; X.dtp[e][1] = inv; X.dtp[e][2] = inv * inv; }
+    X.cum[D->nexp] = nstot;
+    X.nX = nX; X.nU = nU; X.W = W; X.OX = D->OX; X.OU = D->OU; X.nstot = nstot;
+    X.dv = D->dvbuf; X.Lam = D->Lam; X.X = D->X; X.U = D->U; X.scL = D->sc[0]; X.scX = D->sc[1]; X.scU = D->sc[2];
+    if (nstot * W > 0) { xua_decrement_kernel<<<nblk(nstot * W, 256), 256, 0, st>>>(X); h->launches++; }
+    if (D->IA && nA > 0) { xua_decrementA_kernel<<<nblk(nA, 256), 256, 0, st>>>(nA, D->dvbuf + nstot * W, D->sc[3], D->A); h->launches++; }
+    if (delta2) {
+        const int64_t nb3 = 3 * nstot, nbk = nb3 + (D->IA ? 1 : 0);
+        double* ss = nullptr; CK(dalloc(h, &ss, nbk));
+        xua_sumsq_kernel<<<(unsigned)nbk, 256, 0, st>>>(nX, nU, W, nb3, nA, D->dvbuf, ss); h->launches++;
+        std::vector<double> hs((size_t)nbk);
+        CK(cudaMemcpyAsync(hs.data(), ss, (size_t)nbk * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        dfree(h, ss);
+        for (int a = 0; a < 4; ++a) delta2[a] = 0.;
+        for (int64_t b = 0; b < nb3; ++b) delta2[b % 3] = std::max(delta2[b % 3], hs[(size_t)b]);
+        if (D->IA) delta2[3] = hs[(size_t)nb3];
+    }
+    CK(cudaGetLastError());
+    return MB_OK;
+}
+
+}  // extern "C"

@@ -344,3 +344,82 @@ class SingleDofCost(ElementType):
         c = Taylor2.lift(extra["cost"](Taylor2(x, 1., 0.), t, *extra["args"]))
         bc = lambda a: np.broadcast_to(np.asarray(a, float), np.shape(x)).copy()
         return bc(c.v), bc(c.d1), bc(c.d2)
+
+    @staticmethod
+    def lagrangian(eleobj, extra, Λ, X, U, A, t, SP):
+        """lagrangian(o::SingleDofCost,Λ,X,U,A,t,SP,dbg) (src/BasicElements.jl:203-208), derivative = 0 — the general DirectXUA path (xua.py)"""
+        dof = X[0][0] if extra["clas"] == "X" else U[0][0]
+        return extra["cost"](dof, t, *extra["args"])
+
+
+# ------------------------------------------------------------------------------------------------ element types of the general DirectXUA path (xua.py)
+class LagrangianElement(ElementType):
+    """Base of host-evaluated element types written against adiff2.D2: `residual(eleobj, extra, X, U, A, t, SP)` → [R₁…] or
+    `lagrangian(eleobj, extra, Λ, X, U, A, t, SP)` → L, with X[der][i], U[der][i], A[i], Λ[i] per-element arrays or D2 (xua.packets)."""
+    kind = "lagrangian"
+    no_second_order = False
+
+    @classmethod
+    def typekey(cls, **kw):
+        return (cls.__name__,) + tuple(sorted((k, id(v) if callable(v) else (tuple(v) if isinstance(v, (list, tuple)) else v)) for k, v in kw.items()
+                                              if k in getattr(cls, "type_parameters", ())))
+
+    @classmethod
+    def construct(cls, coords, **kw):
+        return np.zeros((coords[0].shape[0] if coords else 1, 0)), dict(kw)
+
+
+SingleDofCost.kind_general = "lagrangian"
+
+
+class SingleUdof(LagrangianElement):
+    """SingleUdof(nod;Xfield,Ufield,cost,costargs) (src/BasicElements.jl:239-248): L = cost(u,t,costargs...) − λ·u"""
+    type_parameters = ("Xfield", "Ufield", "cost")
+
+    @classmethod
+    def doflist(cls, Xfield, Ufield, **kw):
+        return (1, 1), ("X", "U"), (Xfield, Ufield)
+
+    @classmethod
+    def construct(cls, coords, Xfield, Ufield, cost, costargs=()):
+        return np.zeros((coords[0].shape[0], 0)), dict(cost=cost, args=tuple(costargs))
+
+    @staticmethod
+    def lagrangian(eleobj, extra, Λ, X, U, A, t, SP):
+        u = U[0][0]
+        return extra["cost"](u, t, *extra["args"]) - Λ[0] * u
+
+
+class Acost(LagrangianElement):
+    """Acost(nod;inod,field,cost,costargs) (src/BasicElements.jl:77-86): L = cost(A,costargs...), added once (assembleA!, src/Assemble.jl:507-520)"""
+    acost = True
+    type_parameters = ("inod", "field", "cost")
+
+    @classmethod
+    def doflist(cls, inod=(), field=(), **kw):
+        return tuple(inod), ("A",) * len(inod), tuple(field)
+
+    @classmethod
+    def construct(cls, coords, inod=(), field=(), cost=None, costargs=()):
+        return np.zeros((coords[0].shape[0] if coords else 1, 0)), dict(cost=cost, args=tuple(costargs))
+
+    @staticmethod
+    def lagrangian(eleobj, extra, Λ, X, U, A, t, SP):
+        return extra["cost"](A, *extra["args"])
+
+
+class SingleAcost(Acost):
+    """SingleAcost(nod;field,cost,costargs) (src/BasicElements.jl:163-167): an Acost on one A-dof, cost(a,costargs...)"""
+    type_parameters = ("field", "cost")
+
+    @classmethod
+    def doflist(cls, field, **kw):
+        return (1,), ("A",), (field,)
+
+    @classmethod
+    def construct(cls, coords, field, cost, costargs=()):
+        return np.zeros((coords[0].shape[0], 0)), dict(cost=cost, args=tuple(costargs))
+
+    @staticmethod
+    def lagrangian(eleobj, extra, Λ, X, U, A, t, SP):
+        return extra["cost"](A[0], *extra["args"])

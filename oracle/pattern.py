@@ -357,3 +357,107 @@ def decrementbig(states, dv, OX, OU, dt, nstep, nX, nU, scaleL, scaleX, scaleU):
                     if bder == 1:
                         d2[b - 1] = max(d2[b - 1], float((db * db).sum()))
     return d2
+
+
+# ------------------------------------------------------------------------------------------------ DirectXUA, general form (IA = 0/1, several experiments)
+def out_zeros(P):
+    """zero!(out::AssemblyDirect) with the shapes of prepare (src/DirectXUA.jl:22-56): L1[α] (nder α, ndof α); L2[(α,β)] (nα, nβ, nnz)"""
+    nnz = {ab: len(P["pat"][ab][3]) for ab in P["pat"]}
+    return dict(L1={a: np.zeros((P["nL1"][a], P["ndof"][a - 1])) for a in range(1, 5)},
+                L2={ab: np.zeros((P["nL2"][ab][0], P["nL2"][ab][1], nnz[ab])) for ab in P["pat"]})
+
+
+def lagrangian_addition(P, OX, OU, IA, ityp, gradL, hessL, out):
+    """DirectXUA_lagrangian_addition!{:matrices}  src/DirectXUA.jl:121-150 for every element of type `ityp` (0-based):
+    gradL (nele,Np), hessL (nele,Np,Np) = ∂{2,Np}(L) in the order of partials Λ, X₀…, U₀…, A.  Element loop outermost, as assemble_! runs it."""
+    asm = P["asm"]
+    nele = gradL.shape[0]
+    ndofe = [asm[arrnum(a)][ityp].shape[0] for a in range(1, 5)]          # Nx, Nx, Nu, Na
+    nder = (1, OX + 1, OU + 1, IA)
+    for e in range(nele):
+        pa = 0
+        for a in range(1, 5):
+            for i in range(1, nder[a - 1] + 1):
+                ia = pa + np.arange(ndofe[a - 1]); pa += ndofe[a - 1]
+                La = out["L1"][a]
+                if i <= La.shape[0]:
+                    av = asm[arrnum(a)][ityp][:, e]
+                    for k in range(ndofe[a - 1]):
+                        if av[k]: La[i - 1, av[k] - 1] += gradL[e, ia[k]]
+                pb = 0
+                for b in range(1, 5):
+                    for j in range(1, nder[b - 1] + 1):
+                        ib = pb + np.arange(ndofe[b - 1]); pb += ndofe[b - 1]
+                        Lab = out["L2"][(a, b)]
+                        if i <= Lab.shape[0] and j <= Lab.shape[1]:
+                            am = asm[arrnum(a, b)][ityp][:, e]
+                            ni = ndofe[a - 1]
+                            for kb in range(ndofe[b - 1]):
+                                for ka in range(ni):
+                                    inz = am[ka + ni * kb]
+                                    if inz: Lab[i - 1, j - 1, inz - 1] += hessL[e, ia[ka], ib[kb]]
+    return out
+
+
+def assemblebig_general(IA, nstep, dt, P, big, bigasm, pgr, outA, outs):
+    """assemblebig!{:matrices}  src/DirectXUA.jl:316-356, all experiments, IA = 0 or 1.
+    outA: the out of assembleA! (None when IA = 0); outs[iexp][istep-1]: the out of assemble! at that step (shapes of out_zeros).  → (Lvv.nzval, Lv)"""
+    nz = np.zeros(len(big["rowval"])); Lv = np.zeros(big["m"])
+    nL2 = P["nL2"]
+    Ablk = 3 * sum(nstep) + 1
+    if IA == 1:
+        addin_vec(pgr, Lv, outA["L1"][4][0], Ablk)
+        addin_block(bigasm, nz, outA["L2"][(4, 4)][0, 0], Ablk, Ablk)
+    classes = (1, 2, 3, 4) if IA == 1 else (1, 2, 3)
+    cumblk = 0
+    for iexp, ns in enumerate(nstep):
+        for istep in range(1, ns + 1):
+            out = outs[iexp][istep - 1]
+            for b in classes:
+                Lb = out["L1"][b]
+                for bder in range(1, Lb.shape[0] + 1):
+                    s = dt[iexp] ** (1 - bder)
+                    for (ds, w) in finitediff(bder - 1, ns, istep):
+                        blk = Ablk if b == 4 else cumblk + 3 * (istep + ds - 1) + b
+                        addin_vec(pgr, Lv, Lb[bder - 1], blk, w * s)
+            for a in classes:
+                for b in classes:
+                    Lab = out["L2"][(a, b)]
+                    for ad in range(1, Lab.shape[0] + 1):
+                        for bd in range(1, Lab.shape[1] + 1):
+                            s = dt[iexp] ** (2 - ad - bd)
+                            for (das, wa) in finitediff(ad - 1, ns, istep):
+                                for (dbs, wb) in finitediff(bd - 1, ns, istep):
+                                    ablk = Ablk if a == 4 else cumblk + 3 * (istep + das - 1) + a
+                                    bblk = Ablk if b == 4 else cumblk + 3 * (istep + dbs - 1) + b
+                                    addin_block(bigasm, nz, Lab[ad - 1, bd - 1], ablk, bblk, wa * wb * s)
+        cumblk += 3 * ns
+    return nz, Lv
+
+
+def decrementbig_general(states, A, dv, OX, OU, IA, dt, nstep, nX, nU, nA, scaleL, scaleX, scaleU, scaleA):
+    """decrementbig!  src/DirectXUA.jl:357-383, all experiments.  states[iexp][istep-1] = dict(L=[Λ], X=[X0..], U=[U0..]) mutated in place, A mutated in place
+    (all states share it); dv in the block order of Lv.  Returns Δ² (4 entries; the A entry is 0 when IA = 0)."""
+    W = 2 * nX + nU
+    off = {1: 0, 2: nX, 3: 2 * nX}; n = {1: nX, 2: nX, 3: nU}
+    key = {1: "L", 2: "X", 3: "U"}; sc = {1: scaleL, 2: scaleX, 3: scaleU}; nder = {1: 1, 2: OX + 1, 3: OU + 1}
+    d2 = np.zeros(4)
+    cum = 0
+    for iexp, ns in enumerate(nstep):
+        inv = 1.0 / dt[iexp]
+        dtp = [1.0, inv, inv * inv]
+        for istep in range(1, ns + 1):
+            for b in (1, 2, 3):
+                for bder in range(1, nder[b] + 1):
+                    for (ds, w) in finitediff(bder - 1, ns, istep):
+                        blk = (cum + istep + ds - 1) * W + off[b]
+                        db = dv[blk: blk + n[b]]
+                        states[iexp][istep - 1][key[b]][bder - 1] -= ((db * w) * dtp[bder - 1]) * sc[b]
+                        if bder == 1:
+                            d2[b - 1] = max(d2[b - 1], float((db * db).sum()))
+        cum += ns
+    if IA == 1:
+        da = dv[cum * W: cum * W + nA]
+        d2[3] = float((da * da).sum())
+        A -= da * scaleA
+    return d2

@@ -1,0 +1,98 @@
+"""General DirectXUA path, CPU side: the host's dual numbers (adiff2.D2), the element packets (xua.packets) and the oracle's restatement of
+DirectXUA_lagrangian_addition! / assemblebig! are pinned to the numbers test/TestDirectXUA.jl holds (out of the last assembled step, :93-108; assembleA!, :67-76)."""
+import numpy as np
+import pytest
+
+import muscade_b200 as mb
+from muscade_b200 import xua
+from muscade_b200.adiff2 import D2, exp10, sqrt, sin
+from oracle import pattern as OP
+
+import xua_models as XM
+
+
+def test_d2_against_closed_forms():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0.5, 2., (7, 3))
+    a, b, c = D2.variables(x, scale=[1., 2., 0.5])
+    f = a * b / c + exp10(a) * sqrt(b) - sin(c) ** 3 + 2. * a - b / 3. + 1.
+    X, Y, Z = x[:, 0], x[:, 1], x[:, 2]
+    L10 = np.log(10.)
+    v = X * Y / Z + 10 ** X * np.sqrt(Y) - np.sin(Z) ** 3 + 2 * X - Y / 3 + 1
+    g = np.stack([Y / Z + L10 * 10 ** X * np.sqrt(Y) + 2, X / Z + 10 ** X * .5 / np.sqrt(Y) - 1 / 3, -X * Y / Z ** 2 - 3 * np.sin(Z) ** 2 * np.cos(Z)], 1) * [1., 2., .5]
+    H = np.zeros((7, 3, 3))
+    H[:, 0, 0] = L10 ** 2 * 10 ** X * np.sqrt(Y); H[:, 0, 1] = 1 / Z + L10 * 10 ** X * .5 / np.sqrt(Y); H[:, 0, 2] = -Y / Z ** 2
+    H[:, 1, 1] = -10 ** X * .25 / Y ** 1.5; H[:, 1, 2] = -X / Z ** 2
+    H[:, 2, 2] = 2 * X * Y / Z ** 3 - 6 * np.sin(Z) * np.cos(Z) ** 2 + 3 * np.sin(Z) ** 3
+    H = H + np.triu(H, 1).transpose(0, 2, 1)
+    H = H * np.outer([1., 2., .5], [1., 2., .5])
+    assert np.allclose(f.v, v, rtol=1e-14) and np.allclose(f.grad(7, 3), g, rtol=1e-13) and np.allclose(f.hess(7, 3), H, rtol=1e-12, atol=1e-13)
+
+
+def _assemble_outs(model, dis, P, OX, OU, IA, states):
+    """oracle: out of assembleA! and of assemble! at every state"""
+    outA = None
+    if IA:
+        outA = OP.out_zeros(P)
+        for ityp, (et, ed) in enumerate(zip(model.ele, dis.dis)):
+            if getattr(et.ElType, "acost", False):
+                g, H = xua.packets(et, ed, OX, OU, IA, None, None, None, states[0][0].A, states[0][0].time, assembleA=True)
+                # an Acost carries A partials only: place them where DirectXUA.jl:70-84 adds them
+                na = ed.A.shape[1]
+                asmA = P["asm"][OP.arrnum(4)][ityp]; asmAA = P["asm"][OP.arrnum(4, 4)][ityp]
+                for e in range(et.nele):
+                    for k in range(na):
+                        outA["L1"][4][0, asmA[k, e] - 1] += g[e, k]
+                    for kb in range(na):
+                        for ka in range(na):
+                            outA["L2"][(4, 4)][0, 0, asmAA[ka + na * kb, e] - 1] += H[e, ka, kb]
+    outs = []
+    for exp_states in states:
+        row = []
+        for s in exp_states:
+            out = OP.out_zeros(P)
+            for ityp, (et, ed) in enumerate(zip(model.ele, dis.dis)):      # Acost types too: src/Assemble.jl:477 does not match Vector{<:Acost}
+                g, H = xua.packets(et, ed, OX, OU, IA, s.Λ[0], s.X, s.U, s.A, s.time)
+                OP.lagrangian_addition(P, OX, OU, IA, ityp, g, H, out)
+            row.append(out)
+        outs.append(row)
+    return outA, outs
+
+
+def test_packets_and_oracle_reproduce_testdirectxua_out():
+    """test/TestDirectXUA.jl:67-76 (assembleA!) and :93-108 (out after assemblebig!, i.e. of step 6 at t = 6)"""
+    OX, OU, IA, nstep = 2, 0, 1, 6
+    m = XM.model_testdirectxua()
+    s0 = mb.initialize(m)
+    dis = s0.dis
+    P = OP.prepare_direct(XM.dis_lists(dis), 2, 4, 6, OX, OU, IA)
+    st = s0.with_orders(1, OX + 1, OU + 1)
+    states = [[mb.State(1. * i, [v.copy() for v in st.Λ], [v.copy() for v in st.X], [v.copy() for v in st.U], st.A, None, m, dis) for i in range(1, nstep + 1)]]
+    outA, outs = _assemble_outs(m, dis, P, OX, OU, IA, states)
+    D = lambda colptr, rowval, nz, mm, nn: _dense(colptr, rowval, nz, mm, nn)
+    pat = P["pat"]
+    # prepareA_out (:67-76)
+    AA = D(pat[(4, 4)][2], pat[(4, 4)][3], outA["L2"][(4, 4)][0, 0], 6, 6)
+    assert np.allclose(AA, 2e-14 * np.eye(6), rtol=1e-12, atol=0) and not outA["L1"][4].any()
+    out = outs[0][-1]
+    assert np.allclose(out["L1"][1], [[0., 0.]])                                                                   # :94
+    assert np.allclose(out["L1"][2], [[0.055883099639785175, -0.1920340573300732], [0., 0.], [0., 0.]], rtol=1e-13)  # :95
+    assert not out["L1"][3].any() and not out["L1"][4].any()                                                       # :96-97
+    assert P["nL2"][(1, 1)] == (0, 0)                                                                              # :98
+    d = lambda a, b, i, j: D(pat[(a, b)][2], pat[(a, b)][3], out["L2"][(a, b)][i - 1, j - 1], pat[(a, b)][0], pat[(a, b)][1])
+    assert np.allclose(d(2, 2, 1, 1), [[2., 0.], [0., 2.]]) and not d(2, 2, 1, 2).any() and not d(2, 2, 1, 3).any()   # :99-101
+    assert np.allclose(d(2, 1, 1, 1), [[2.1, -1.1], [-1.1, 1.1]], rtol=1e-13)                                      # :102
+    assert np.allclose(d(2, 1, 2, 1), [[.05, 0.], [0., 0.]], rtol=1e-13)                                           # :103
+    assert np.allclose(d(2, 1, 3, 1), [[1., 0.], [0., 1.]], rtol=1e-13)                                            # :104
+    assert np.allclose(d(3, 3, 1, 1), np.diag([0., 0., 2., 2.]))                                                   # :105
+    assert not d(3, 4, 1, 1).any() and d(3, 4, 1, 1).shape == (4, 6)                                               # :106
+    # :107 — 2e-14·I after the LAST assemble!: the Acost elements went through it (src/Assemble.jl:477 does not match Vector{<:Acost})
+    assert np.allclose(d(4, 4, 1, 1), 2e-14 * np.eye(6), rtol=1e-12, atol=0)
+
+
+def _dense(colptr, rowval, nz, m, n):
+    A = np.zeros((m, n))
+    for j in range(n):
+        for k in range(colptr[j] - 1, colptr[j + 1] - 1):
+            A[rowval[k] - 1, j] = nz[k]
+    return A

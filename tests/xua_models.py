@@ -1,0 +1,115 @@
+"""Test elements and models of the general DirectXUA path: test/TestDirectXUA.jl:10-51 and test/SomeElements.jl:164-188 restated against adiff2.D2."""
+import numpy as np
+
+import muscade_b200 as mb
+from muscade_b200.adiff2 import D2, exp10, sqrt, sin, cos
+
+
+class El1(mb.LagrangianElement):
+    """El1 (test/TestDirectXUA.jl:10-21): r = −u + K·x + C·10^ΞC·x′ + M·10^ΞM·x″; no_second_order is the default Val(false)"""
+    type_parameters = ()
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1, 1, 1), ("X", "U", "A", "A"), ("tx1", "u", "ΞC", "ΞM")
+
+    @classmethod
+    def construct(cls, coords, K, C, M):
+        n = coords[0].shape[0]
+        return np.tile(np.array([[K, C, M]], float), (n, 1))
+
+    @staticmethod
+    def residual(o, extra, X, U, A, t, SP):
+        x, x1, x2, u, XC, XM = X[0][0], X[1][0], X[2][0], U[0][0], A[0], A[1]
+        return [-u + o[:, 0] * x + o[:, 1] * exp10(XC) * x1 + o[:, 2] * exp10(XM) * x2]
+
+
+class Spring1(mb.LagrangianElement):
+    """Spring{1} (test/SomeElements.jl:164-188), no_second_order = Val(false)"""
+    type_parameters = ()
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 2, 3, 3), ("X", "X", "A", "A"), ("tx1", "tx1", "ΞL₀", "ΞEI")
+
+    @classmethod
+    def construct(cls, coords, EA):
+        x1, x2 = coords[0][:, 0], coords[1][:, 0]
+        return np.stack([x1, x2, np.full_like(x1, EA), np.abs(x1 - x2)], axis=1)
+
+    @staticmethod
+    def residual(o, extra, X, U, A, t, SP):
+        L0 = o[:, 3] * exp10(A[0]); EA = o[:, 2] * exp10(A[1])
+        dx = (X[0][0] + o[:, 0]) - (X[0][1] + o[:, 1])
+        L = sqrt(dx * dx)
+        T = EA * (L - L0) / L0
+        F1 = dx / L * T
+        return [F1, -F1]
+
+
+def fa(a): return a ** 2 * 1e-14
+def fu(u, t): return u ** 2
+def l1(x, t): return (x - 0.1 * np.sin(t)) ** 2
+def l2(x, t): return (x - 0.1 * np.cos(t)) ** 2
+
+
+def model_testdirectxua():
+    """test/TestDirectXUA.jl:26-51"""
+    m = mb.Model("TrueModel")
+    n1 = mb.addnode(m, [0.]); n2 = mb.addnode(m, [1.]); n3 = mb.addnode(m, [])
+    mb.addelement(m, El1, [n1], K=1., C=0.05, M=1.)
+    mb.addelement(m, El1, [n2], K=0., C=0.0, M=1.)
+    mb.addelement(m, Spring1, [n1, n2, n3], EA=1.1)
+    mb.addelement(m, mb.SingleAcost, [n3], field="ΞL₀", cost=fa)
+    mb.addelement(m, mb.SingleAcost, [n3], field="ΞEI", cost=fa)
+    mb.addelement(m, mb.SingleAcost, [n1], field="ΞC", cost=fa)
+    mb.addelement(m, mb.SingleAcost, [n1], field="ΞM", cost=fa)
+    mb.addelement(m, mb.SingleAcost, [n2], field="ΞC", cost=fa)
+    mb.addelement(m, mb.SingleAcost, [n2], field="ΞM", cost=fa)
+    mb.addelement(m, mb.SingleUdof, [n1], Xfield="tx1", Ufield="utx1", cost=fu)
+    mb.addelement(m, mb.SingleUdof, [n2], Xfield="tx1", Ufield="utx1", cost=fu)
+    mb.addelement(m, mb.SingleDofCost, [n1], clas="X", field="tx1", cost=l1)
+    mb.addelement(m, mb.SingleDofCost, [n2], clas="X", field="tx1", cost=l2)
+    return m
+
+
+def dis_lists(dis):
+    """Disassembler → the oracle's `dis` (list of dicts of 1-based index arrays)"""
+    return [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+
+
+class El0(mb.LagrangianElement):
+    """El1 without the derivatives an analysis of lower order does not carry: r = −u + K·x (+ C·10^ΞC·x′ when ox ≥ 1); no_second_order = Val(true) to cover that branch"""
+    type_parameters = ("ox",)
+    no_second_order = True
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1, 1, 1), ("X", "U", "A", "A"), ("tx1", "u", "ΞC", "ΞM")
+
+    @classmethod
+    def construct(cls, coords, K, C, ox):
+        n = coords[0].shape[0]
+        return np.tile(np.array([[K, C, ox]], float), (n, 1))
+
+    @staticmethod
+    def residual(o, extra, X, U, A, t, SP):
+        r = -U[0][0] + o[:, 0] * X[0][0] * exp10(A[1])
+        if len(X) > 1:
+            r = r + o[:, 1] * exp10(A[0]) * X[1][0]
+        return [r]
+
+
+def model_chain(n, rng, ox=2):
+    """a longer model for the structures at size: n El1 oscillators on a line, springs between neighbours (each with its own A node), U-loads and costs"""
+    m = mb.Model("chain")
+    nod = mb.addnode(m, np.arange(n, dtype=float)[:, None])
+    anod = [mb.addnode(m, []) for _ in range(n - 1)]
+    if ox == 2: mb.addelement(m, El1, nod[:, None], K=1.3, C=0.07, M=0.9)
+    else: mb.addelement(m, El0, nod[:, None], K=1.3, C=0.07, ox=ox)
+    mb.addelement(m, Spring1, np.stack([nod[:-1], nod[1:], np.asarray(anod)], axis=1), EA=2.1)
+    for a in anod[::3]:
+        mb.addelement(m, mb.SingleAcost, [a], field="ΞL₀", cost=fa)
+    mb.addelement(m, mb.SingleUdof, nod[:, None], Xfield="tx1", Ufield="utx1", cost=fu)
+    mb.addelement(m, mb.SingleDofCost, nod[::2, None], clas="X", field="tx1", cost=l1)
+    return m
