@@ -419,4 +419,129 @@ comm_allreduce!(h::Ptr{Cvoid}, v::Vector{𝕣}, op=0)        = check(h, ccall((:
 "element-range shard of a large SweepX mesh: after `assemble!` with device-resident outputs, the interface rows go to / come from the neighbours"
 iface_exchange!(out::AssemblySweepXB200) = check(out.h, ccall((:mb_iface_exchange, LIB), Int32, (Ptr{Cvoid},), out.h))
 
+# ------------------------------------------------------------------------------------------------------------------ DirectXUA{OX,OU,IA}, general form
+"""
+    AssemblyXUAB200{OX,OU,IA}
+
+`AssemblyDirect{OX,OU,IA}` (src/DirectXUA.jl:18-56) with its maps, patterns, `Lvv`/`Lv`, `Lvvasm`/`Lvasm` on the device (`mb_xua_*`): any element type, A-dofs,
+several experiments.  Muscade differentiates the elements with its own dual numbers exactly as `addin!` does (src/DirectXUA.jl:70-171) and hands the partials over
+as packets; the hot loop of `assemblebig!` — scatter into `out`, finite-difference weighted addition into `Lvv`/`Lv` — `sparser!` and `decrementbig!` run on the GPU.
+"""
+mutable struct AssemblyXUAB200{OX,OU,IA} <: Assembly
+    h      :: Ptr{Cvoid}
+    nstep  :: Vector{Int64}
+    Δt     :: Vector{𝕣}
+    nbig   :: Int64
+    nnzbig :: Int64
+end
+function Muscade.prepare(::Type{AssemblyXUAB200{OX,OU,IA}}, model, dis; nstep::Vector{Int64}, Δt::Vector{𝕣}, device=0,
+                         Xwhite=false, XUindep=false, UAindep=false, XAindep=false) where {OX,OU,IA}
+    href = Ref{Ptr{Cvoid}}()
+    check(C_NULL, ccall((:mb_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, href))
+    h = href[]
+    for ieletyp = 1:getneletyp(model)
+        eleobj, d = model.eleobj[ieletyp], dis.dis[ieletyp]
+        idx(f, n) = Int64[getfield(d.index[iele], f)[i] for i = 1:n, iele = 1:length(eleobj)]
+        nx, nu, na = length(d.scale.X), length(d.scale.U), length(d.scale.A)
+        iX, iU, iA = idx(:X, nx), idx(:U, nu), idx(:A, na)
+        check(h, ccall((:mb_xua_add_eletyp, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int32, Ref{Int32}),
+                       h, length(eleobj), nx, nu, na, iX, iU, iA, eltype(eleobj) <: Muscade.Acost, Ref{Int32}()))
+    end
+    flags = Int32(Xwhite) | Int32(XUindep) << 1 | Int32(UAindep) << 2 | Int32(XAindep) << 3
+    nbig, nnz = Ref{Int64}(), Ref{Int64}()
+    check(h, ccall((:mb_xua_prepare, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int64, Int64, Int64, Int32, Ptr{Int64}, Ptr{𝕣}, Int32, Ref{Int64}, Ref{Int64}),
+                   h, OX, OU, IA, getndof(model, :X), getndof(model, :U), getndof(model, :A), length(nstep), nstep, Δt, flags, nbig, nnz))
+    check(h, ccall((:mb_xua_set_dof_scale, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), h, dis.scaleΛ, dis.scaleX, dis.scaleU, dis.scaleA))
+    out = AssemblyXUAB200{OX,OU,IA}(h, nstep, Δt, nbig[], nnz[])
+    finalizer(o -> ccall((:mb_destroy, LIB), Int32, (Ptr{Cvoid},), o.h), out)
+    return out
+end
+
+"""
+    g,H = packet(eleobj_vector, d, state, OX, OU, IA, SP, dbg; assembleA=false)
+
+∇L [Np × nele] and ∇²L [Np × Np × nele] (Julia column-major = the C ABI's row-major [nele][Np][Np], ∇²L being symmetric) of one element type at one state: the same
+calls `addin!` makes (src/DirectXUA.jl:70-84 for `assembleA`, :85-120 for `no_second_order` types — Λ row/column only —, :152-171 otherwise).
+"""
+function packet(eleobj::Vector{E}, d, state, OX, OU, IA, SP, dbg; assembleA=false) where {E}
+    nx, nu, na = length(d.scale.X), length(d.scale.U), length(d.scale.A)
+    Np = assembleA ? na : nx + nx * (OX + 1) + nu * (OU + 1) + na * IA
+    g, H = zeros(𝕣, Np, length(eleobj)), zeros(𝕣, Np, Np, length(eleobj))
+    for (iele, o) ∈ enumerate(eleobj)
+        index = d.index[iele]
+        Λe = state.Λ[1][index.X]; Xe = ntuple(i -> state.X[i][index.X], OX + 1); Ue = ntuple(i -> state.U[i][index.U], OU + 1); Ae = state.A[index.A]
+        if assembleA
+            C, _ = Muscade.lagrangian(o, nothing, nothing, nothing, Muscade.revariate{2}(Ae), nothing, nothing, dbg)
+            ∇C   = Muscade.∂{2,na}(C)
+            g[:, iele] .= Muscade.value{1}.(∇C); H[:, :, iele] .= Muscade.∂{1,na}(∇C)
+        elseif Muscade.no_second_order(E) == Val(true)
+            v = IA == 1 ? Muscade.revariate{1}((;X=Xe, U=Ue, A=Ae), (;X=d.scale.X, U=d.scale.U, A=d.scale.A)) : (Muscade.revariate{1}((;X=Xe, U=Ue), (;X=d.scale.X, U=d.scale.U))..., Ae)
+            R, _ = Muscade.residual(o, v[1], v[2], v[3], state.time, SP, dbg)
+            g[1:nx, iele] .= Muscade.value{1}.(R)
+            dR = Muscade.∂{1,Np - nx}(R)
+            H[1:nx, nx+1:Np, iele] .= dR; H[nx+1:Np, 1:nx, iele] .= dR'
+        else
+            v = IA == 1 ? Muscade.revariate{2}((;Λ=Λe, X=Xe, U=Ue, A=Ae), (;Λ=d.scale.Λ, X=d.scale.X, U=d.scale.U, A=d.scale.A)) :
+                          (Muscade.revariate{2}((;Λ=Λe, X=Xe, U=Ue), (;Λ=d.scale.Λ, X=d.scale.X, U=d.scale.U))..., Ae)
+            L, _ = Muscade.getlagrangian(o, v[1], v[2], v[3], v[4], state.time, SP, dbg)
+            ∇L   = Muscade.∂{2,Np}(L)
+            g[:, iele] .= Muscade.value{1}.(∇L); H[:, :, iele] .= Muscade.∂{1,Np}(∇L)
+        end
+    end
+    return g, H
+end
+
+"assemblebig!{:matrices} (src/DirectXUA.jl:316-356): state[iexp][istep]"
+function assemblebig!(out::AssemblyXUAB200{OX,OU,IA}, model, dis, state, SP, dbg) where {OX,OU,IA}
+    h = out.h
+    setp(ityp, g, H) = check(h, ccall((:mb_xua_set_packet, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{𝕣}, Ptr{𝕣}), h, ityp, g, H))
+    check(h, ccall((:mb_xua_zero, LIB), Int32, (Ptr{Cvoid},), h))
+    if IA == 1
+        for ityp = 1:getneletyp(model)
+            eltype(model.eleobj[ityp]) <: Muscade.Acost && setp(ityp, packet(model.eleobj[ityp], dis.dis[ityp], state[1][1], OX, OU, IA, SP, dbg; assembleA=true)...)
+        end
+        check(h, ccall((:mb_xua_add_A, LIB), Int32, (Ptr{Cvoid},), h))
+    end
+    for iexp = 1:length(out.nstep), istep = 1:out.nstep[iexp]
+        for ityp = 1:getneletyp(model)          # Acost vectors too: `assemble_!(…,eleobj::Acost,…) = nothing` (src/Assemble.jl:477) does not match them
+            setp(ityp, packet(model.eleobj[ityp], dis.dis[ityp], state[iexp][istep], OX, OU, IA, SP, (dbg..., step=istep))...)
+        end
+        check(h, ccall((:mb_xua_add_step, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h, iexp, istep))
+    end
+end
+
+"sparser!(cLvv,Lvv,rtol) on the device → SparseMatrixCSC for the factorisation, and Lv"
+function sparser(out::AssemblyXUAB200, rtol=1e-20)
+    n = Ref{Int64}()
+    check(out.h, ccall((:mb_xua_sparser, LIB), Int32, (Ptr{Cvoid}, 𝕣, Ref{Int64}), out.h, rtol, n))
+    colptr, rowval, nzval = Vector{Int64}(undef, out.nbig + 1), Vector{Int64}(undef, n[]), Vector{𝕣}(undef, n[])
+    check(out.h, ccall((:mb_xua_get_sparse, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{𝕣}), out.h, colptr, rowval, nzval))
+    Lv = Vector{𝕣}(undef, out.nbig)
+    check(out.h, ccall((:mb_xua_get_big, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Ptr{𝕣}), out.h, C_NULL, Lv))
+    return SparseMatrixCSC(out.nbig, out.nbig, colptr, rowval, nzval), Lv
+end
+
+"decrementbig! (src/DirectXUA.jl:357-383) on the device-resident states → Δ² (Λ,X,U,A); upload_states! / download_states! move state[iexp][istep]"
+function decrementbig!(out::AssemblyXUAB200, Δv::Vector{𝕣})
+    Δ² = zeros(𝕣, 4)
+    check(out.h, ccall((:mb_xua_decrement, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Ptr{𝕣}), out.h, Δv, Δ²))
+    return Δ²
+end
+function upload_states!(out::AssemblyXUAB200{OX,OU,IA}, state) where {OX,OU,IA}
+    for iexp = 1:length(out.nstep), istep = 1:out.nstep[iexp]
+        s = state[iexp][istep]
+        check(out.h, ccall((:mb_xua_set_state, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
+                           out.h, iexp, istep, s.Λ[1], reduce(vcat, s.X), reduce(vcat, s.U), s.A))
+    end
+end
+function download_states!(state, out::AssemblyXUAB200{OX,OU,IA}) where {OX,OU,IA}
+    for iexp = 1:length(out.nstep), istep = 1:out.nstep[iexp]
+        s = state[iexp][istep]
+        X, U = Vector{𝕣}(undef, (OX + 1) * length(s.X[1])), Vector{𝕣}(undef, (OU + 1) * length(s.U[1]))
+        check(out.h, ccall((:mb_xua_get_state, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), out.h, iexp, istep, s.Λ[1], X, U, s.A))
+        for i = 1:OX+1 s.X[i] .= view(X, (i-1)*length(s.X[1])+1:i*length(s.X[1])) end
+        for i = 1:OU+1 s.U[i] .= view(U, (i-1)*length(s.U[1])+1:i*length(s.U[1])) end
+    end
+end
+
 end # module

@@ -53,8 +53,11 @@ def l1(x, t): return (x - 0.1 * np.sin(t)) ** 2
 def l2(x, t): return (x - 0.1 * np.cos(t)) ** 2
 
 
-def model_testdirectxua():
-    """test/TestDirectXUA.jl:26-51"""
+def fa_stiff(a): return (a - 0.02) ** 2 * 0.5        # pulls every A-dof towards 0.02: the identified A is not zero
+
+
+def model_testdirectxua(fa=fa):
+    """test/TestDirectXUA.jl:26-51 (fa: the A-cost; the reference's 1e-14·a² leaves the all-steps system with a condition number of 8e15)"""
     m = mb.Model("TrueModel")
     n1 = mb.addnode(m, [0.]); n2 = mb.addnode(m, [1.]); n3 = mb.addnode(m, [])
     mb.addelement(m, El1, [n1], K=1., C=0.05, M=1.)
