@@ -22,6 +22,11 @@
 #include <cub/cub.cuh>
 #include "pattern_build.cuh"
 
+namespace mb {
+template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
+                                         unsigned long long nanbase, double* Wc, cudaStream_t s, const StepBatch& sb, int nb);
+}
+
 namespace {
 
 constexpr int XMAXT = 40;                       // element types of one model on this path
@@ -32,6 +37,9 @@ struct XuaType {
     int64_t nele = 0; int n[3] = {0, 0, 0}; int32_t* idx[3] = {nullptr, nullptr, nullptr}; int acost = 0;
     int Np = 0; int base[4] = {0, 0, 0, 0};     // first partial of class α in the packet; derivative d of α starts at base[α] + d·n[cgroup(α)]
     double *g = nullptr, *H = nullptr; bool has = false;
+    // device-evaluated type (EulerBeam3D of the handle, mb_xua_add_device_eletyp): outputs of the first-order kernels, and the ElementCost accelerator's strain-gauge cost
+    int devgroup = -1; double *dR = nullptr, *Rb = nullptr;
+    int ng = 0; double isig2 = 0.; double *G = nullptr, *epsm = nullptr, *J = nullptr, *e4 = nullptr, *cost = nullptr; bool epsm_per_element = false;
 };
 struct TabDev {                                  // per element type, for one (α,β) or α: by value into the gather kernels
     int n; uint32_t pbase[XMAXT + 1]; int ni[XMAXT], nj[XMAXT], Np[XMAXT], bi[XMAXT], bj[XMAXT]; const double* p[XMAXT];
@@ -198,6 +206,69 @@ __global__ void __launch_bounds__(256) xua_sumsq_kernel(int64_t nX, int64_t nU, 
     if (threadIdx.x == 0) out[b] = sh[0];
 }
 
+// ---- device element types in the general form
+// (R, dR) of the first-order kernels (beam_kernel.cuh K3: dR[e][p][i] = ∂R_i/∂seed_p, p over X₀ X₁ X₂ U₀, seeds scaled; R unscaled) → packet of a no_second_order type
+// (src/DirectXUA.jl:85-120): ∇L[Λ] = R, the Λ rows / columns of ∇²L = ∂R/∂β.  COSTED (an ElementCost wraps the type, :172-198 as intended: L = Λ∘₁R + cost with first-order R):
+// ∇L[Λ] = R·scale.Λ, ∇L[X_der] = Σᵢ Λᵢ·∂Rᵢ/∂X_der (likewise U), Λ rows / columns scaled by scale.Λ; the cost's own terms are added by gauge_cost_kernel.
+__global__ void beam_packet_kernel(int64_t nele, int npd, int Np, int nxd /* 12·(OX+1) */, int nu0 /* packet column of U₀ or −1 */, const double* __restrict__ R,
+                                   const double* __restrict__ dR, const int32_t* __restrict__ idxX, const double* __restrict__ Lam, const double* sLam12, bool costed,
+                                   double* __restrict__ g, double* __restrict__ H) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nele * npd) return;
+    const int64_t e = t / npd; const int p = (int)(t - e * npd);          // one thread per (element, seed p): column 12 + p' of the Λ rows
+    const int col = (p < nxd) ? 12 + p : nu0 + (p - nxd);
+    double* He = H + e * (int64_t)Np * Np; double* ge = g + e * (int64_t)Np;
+    double acc = 0.;
+    for (int i = 0; i < 12; ++i) {
+        double v = dR[(e * npd + p) * 12 + i];
+        if (costed) { acc += Lam[idxX[e * 12 + i]] * v; v *= sLam12[i]; }
+        He[i * Np + col] = v; He[col * Np + i] = v;
+    }
+    if (costed) ge[col] = acc;
+    if (p < 12) ge[p] = costed ? R[e * 12 + p] * sLam12[p] : R[e * 12 + p];
+}
+// requestables (εₐₓ, ♢κ) of EulerBeam3D (toolbox/BeamElement.jl:151-174) with their partials ∂/∂X₀ (scaled): one lane per (element, element dof), one-direction duals
+// through the forward kinematics only.  J[e][k][d], e4[e][k]  (k: εₐₓ, κ₁, κ₂, κ₃)
+__global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const double* __restrict__ X0, double* __restrict__ J, double* __restrict__ e4) {
+    using N = NumDual<1>; using T = Dual<1>;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 12; const int d = (int)(t - e * 12);
+    if (e >= g.nele) return;
+    BeamGeo geo; load_geo(g.geo + e * 16, geo);
+    T x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { x[i].v = X0[g.idxX[e * 12 + i]]; x[i].d[0] = (i == d) ? g.scaleX[i] : 0.; }
+    BeamFwd<N> f;
+    beam_forward<N, false>(geo, Vec3<T>{x[0], x[1], x[2]}, Vec3<T>{x[3], x[4], x[5]}, Vec3<T>{x[6], x[7], x[8]}, Vec3<T>{x[9], x[10], x[11]}, f);
+    const double k = 2. / geo.L;
+    const T q[4] = {f.eps, f.vl[0] * k, f.vl[2] * k, -(f.vl[1] * k)};          // ♢κ (BeamElement.jl:164-166)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { J[(e * 4 + i) * 12 + d] = q[i].d[0]; if (d == 0) e4[e * 4 + i] = q[i].v; }
+}
+// ElementCost accelerator for StrainGaugeOnEulerBeam3D (toolbox/StrainGaugeOnBeamElement.jl:70-76) under the quadratic cost Σ_g (ε_g − εm_g)²/(2σ²):
+// ε_g = G[g]·(εₐₓ,κ); ∇cost = Jᵀ·Gᵀ·r/σ², ∇²cost = Jᵀ·GᵀG·J/σ² (chainrule of the second-order cost with the first-order eleres: to_order{2} adds no curvature, :190-196).
+// One thread per (element, i): row i of the X₀-X₀ block and entry i of the X₀ gradient are ADDED to the packet.
+__global__ void gauge_cost_kernel(int64_t nele, int ng, int Np, const double* __restrict__ G, const double* __restrict__ epsm, bool per_element, double isig2,
+                                  const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ g, double* __restrict__ H, double* __restrict__ cost) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / 12; const int i = (int)(t - e * 12);
+    if (e >= nele) return;
+    double q[4] = {0., 0., 0., 0.}, M[4][4] = {{0.}}, c = 0.;
+    for (int a = 0; a < ng; ++a) {
+        const double* Ga = G + a * 4;
+        const double r = (((Ga[0] * e4[e * 4] + Ga[1] * e4[e * 4 + 1]) + Ga[2] * e4[e * 4 + 2]) + Ga[3] * e4[e * 4 + 3]) - epsm[(per_element ? e * ng : 0) + a];
+        c += r * r;
+        for (int k = 0; k < 4; ++k) { q[k] += Ga[k] * r; for (int l = 0; l < 4; ++l) M[k][l] += Ga[k] * Ga[l]; }
+    }
+    const double* Je = J + e * 48;
+    double gi = 0., MJ[4];
+    for (int k = 0; k < 4; ++k) { gi += Je[k * 12 + i] * q[k]; MJ[k] = ((M[k][0] * Je[i] + M[k][1] * Je[12 + i]) + M[k][2] * Je[24 + i]) + M[k][3] * Je[36 + i]; }
+    g[e * (int64_t)Np + 12 + i] += gi * isig2;
+    double* Hrow = H + (e * (int64_t)Np + 12 + i) * Np + 12;
+    for (int j = 0; j < 12; ++j) Hrow[j] += (((Je[j] * MJ[0] + Je[12 + j] * MJ[1]) + Je[24 + j] * MJ[2]) + Je[36 + j] * MJ[3]) * isig2;
+    if (i == 0 && cost) cost[e] = 0.5 * c * isig2;
+}
+
 }  // namespace
 
 struct XuaData {
@@ -220,6 +291,7 @@ struct XuaData {
     Combo2* cb2 = nullptr; Combo1* cb1 = nullptr;
     std::vector<int64_t> c2start, c1start;            // [(gs+1)·16 + 4α + β] → first combo (gs = −1: the A step), sentinel at the end; c1start: [(gs+1)·4 + β]
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;
+    double lamscale = 1.;
     double *Lam = nullptr, *X = nullptr, *U = nullptr, *A = nullptr, *sc[4] = {nullptr, nullptr, nullptr, nullptr}, *dvbuf = nullptr;
 };
 
@@ -623,6 +695,141 @@ static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_
         }
     for (XuaType& Y : D->types) if (!acost || Y.acost) Y.has = false;
     CK(cudaGetLastError());
+    return MB_OK;
+}
+
+/* An EulerBeam3D type of this handle (mb_add_eulerbeam3d; ieletyp_dev = its 1-based number among the handle's device types) as the next element type of the general
+ * form.  Its packets are produced on the device by mb_xua_eval_device — no host evaluation, no transfer. */
+int32_t mb_xua_add_device_eletyp(mb_handle* h, int32_t ieletyp_dev, int32_t* ieletyp_out) {
+    if (!h) return MB_ERR_ARG;
+    ARG(ieletyp_dev >= 1 && ieletyp_dev <= (int)h->groups.size() && h->groups[(size_t)ieletyp_dev - 1].kind == G_BEAM, "not an EulerBeam3D type of this handle");
+    CK(cudaSetDevice(h->device));
+    if (!h->xua) h->xua = new XuaData();
+    XuaData* D = h->xua;
+    ARG(!D->prepared, "element types must be added before mb_xua_prepare");
+    ARG((int)D->types.size() < XMAXT, "too many element types");
+    const Group& g = h->groups[(size_t)ieletyp_dev - 1];
+    XuaType T; T.nele = g.nele; T.n[0] = 12; T.n[1] = g.udof ? 3 : 0; T.n[2] = 0; T.idx[0] = g.idxX; T.idx[1] = g.udof ? g.idxU : nullptr; T.devgroup = ieletyp_dev - 1;
+    D->types.push_back(T);
+    if (ieletyp_out) *ieletyp_out = (int32_t)D->types.size();
+    return MB_OK;
+}
+/* ElementCost{StrainGaugeOnEulerBeam3D} on a device type: G [ngauge][4] = (E, K1, K2, K3) of every gauge (toolbox/StrainGaugeOnBeamElement.jl:62-65), cost
+ * Σ_g (ε_g − εm_g)²/(2σ²); lambda_scale = model.scaleΛ.  Measurements: epsm [ngauge] (the same for every element) or [nele][ngauge], host or device, per step. */
+int32_t mb_xua_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma, double lambda_scale) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].devgroup >= 0, "not a device element type");
+    ARG(ngauge >= 1 && ngauge <= 64 && G && sigma > 0., "bad gauge data");
+    CK(cudaSetDevice(h->device));
+    XuaType& T = D->types[(size_t)ieletyp - 1];
+    if (T.G) dfree(h, T.G);
+    if (T.epsm) { dfree(h, T.epsm); T.epsm = nullptr; }
+    T.ng = ngauge; T.isig2 = 1. / (sigma * sigma); D->lamscale = lambda_scale;
+    CK(dalloc(h, &T.G, (int64_t)ngauge * 4));
+    CK(cudaMemcpy(T.G, G, (size_t)ngauge * 4 * 8, cudaMemcpyDefault));
+    return MB_OK;
+}
+int32_t mb_xua_set_gauge_measurements(mb_handle* h, int32_t ieletyp, const double* epsm, int32_t per_element) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].ng > 0 && epsm, "set the gauge cost of this type first");
+    CK(cudaSetDevice(h->device));
+    XuaType& T = D->types[(size_t)ieletyp - 1];
+    const int64_t n = (int64_t)T.ng * (per_element ? T.nele : 1), cap = (int64_t)T.ng * std::max<int64_t>(T.nele, 1);
+    if (!T.epsm) CK(dalloc(h, &T.epsm, cap));
+    CK(cudaMemcpyAsync(T.epsm, epsm, (size_t)n * 8, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    T.epsm_per_element = per_element != 0;
+    return MB_OK;
+}
+/* Packets of every device element type at state[iexp][istep] (the device-resident state, mb_xua_set_state): first-order kernels of the beam path → (R, ∂R/∂X_der, ∂R/∂U),
+ * strain-gauge kernels where a cost is set.  Call before mb_xua_add_step, beside mb_xua_set_packet for the host-evaluated types. */
+int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo* where) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(D->prepared, "call mb_xua_prepare first");
+    ARG(iexp >= 1 && iexp <= D->nexp && istep >= 1 && istep <= D->nstep[(size_t)iexp - 1], "no such step");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t gs = D->cum[(size_t)iexp - 1] + istep - 1, nX = D->ndof[0], nU = D->ndof[1];
+    const int nd = D->OX + 1;
+    CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), st));
+    for (size_t it = 0; it < D->types.size(); ++it) {
+        XuaType& T = D->types[it];
+        if (T.devgroup < 0 || T.nele == 0) continue;
+        const Group& g = h->groups[(size_t)T.devgroup];
+        BeamGroupDev gd;
+        gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+        for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
+        for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+        const int npd = 12 * nd + (g.udof ? 3 : 0);
+        const int64_t ng = T.nele * T.Np, nh = ng * T.Np;
+        if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(dalloc(h, &T.H, nh)); }
+        if (!T.dR) { CK(dalloc(h, &T.dR, T.nele * 12 * npd)); CK(dalloc(h, &T.Rb, T.nele * 12)); }
+        CK(cudaMemsetAsync(T.g, 0, (size_t)ng * 8, st)); CK(cudaMemsetAsync(T.H, 0, (size_t)nh * 8, st));
+        DirectStateDev sd;
+        for (int d = 0; d < 3; ++d) sd.X[d] = D->X + (gs * 3 + d) * nX;
+        sd.U0 = nU ? D->U + gs * 3 * nU : nullptr;
+        StepBatch sb;
+        double* Wc = nullptr;
+        if (nd >= 2) {
+            const int64_t need = ((g.nele * 6 * nd + 31) / 32) * 32 * MB_NCOT;
+            if (h->Wc_len < need) { if (h->Wc) dfree(h, h->Wc); h->Wc = nullptr; h->Wc_len = 0; CK(dalloc(h, &h->Wc, need)); h->Wc_len = need; }
+            Wc = h->Wc; sb.sWc = need;
+        }
+        const unsigned long long nanbase = ((unsigned long long)it) << 40;
+        if (nd == 1) h->launches += launch_beam_direct<1>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
+        else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
+        else h->launches += launch_beam_direct<3>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
+        const bool costed = T.ng > 0;
+        double sL[12]; for (int i = 0; i < 12; ++i) sL[i] = g.scaleX[i] * D->lamscale;
+        double* dsL = nullptr;
+        if (costed) { CK(dalloc(h, &dsL, 12)); CK(cudaMemcpyAsync(dsL, sL, sizeof(sL), cudaMemcpyHostToDevice, st)); }
+        beam_packet_kernel<<<nblk(T.nele * npd, 128), 128, 0, st>>>(T.nele, npd, T.Np, 12 * nd, g.udof ? 12 + 12 * nd : -1, T.Rb, T.dR, g.idxX, D->Lam + gs * nX, dsL, costed, T.g, T.H);
+        h->launches++;
+        if (costed) {
+            ARG(T.epsm, "strain-gauge measurements of this step are not set (mb_xua_set_gauge_measurements)");
+            if (!T.J) { CK(dalloc(h, &T.J, T.nele * 48)); CK(dalloc(h, &T.e4, T.nele * 4)); CK(dalloc(h, &T.cost, T.nele)); }
+            beam_gauge_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(gd, sd.X[0], T.J, T.e4);
+            gauge_cost_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(T.nele, T.ng, T.Np, T.G, T.epsm, T.epsm_per_element, T.isig2, T.J, T.e4, T.g, T.H, T.cost);
+            h->launches += 2;
+            CK(cudaStreamSynchronize(st)); dfree(h, dsL);
+        }
+        T.has = true;
+    }
+    CK(cudaMemcpyAsync(h->nanflag_host, h->nanflag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (where) { where->kind = 0; where->ieletyp = 0; where->iele = 0; where->step = 0; }
+    const unsigned long long f = *h->nanflag_host;
+    if (f != ~0ULL) {
+        if (where) { where->kind = MB_ERR_NAN; where->ieletyp = (int32_t)((f >> 40) & 0x3F) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = istep; }
+        h->err = "residual(...) returned NaN in R, FB or derivatives";
+        return MB_ERR_NAN;
+    }
+    return MB_OK;
+}
+/* the packet of an element type as it stands (host-set or device-evaluated), and for a costed device type its requestables (εₐₓ,κ) [nele][4], their partials [nele][4][12], costs [nele] */
+int32_t mb_xua_get_packet(mb_handle* h, int32_t ieletyp, double* gradL, double* hessL) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].g, "no packet for this element type");
+    CK(cudaSetDevice(h->device));
+    const XuaType& T = D->types[(size_t)ieletyp - 1];
+    if (gradL) CK(cudaMemcpy(gradL, T.g, (size_t)(T.nele * T.Np) * 8, cudaMemcpyDeviceToHost));
+    if (hessL) CK(cudaMemcpy(hessL, T.H, (size_t)(T.nele * T.Np * T.Np) * 8, cudaMemcpyDeviceToHost));
+    return MB_OK;
+}
+int32_t mb_xua_get_gauge(mb_handle* h, int32_t ieletyp, double* e4, double* J, double* cost) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].J, "no strain-gauge evaluation for this element type yet");
+    CK(cudaSetDevice(h->device));
+    const XuaType& T = D->types[(size_t)ieletyp - 1];
+    if (e4) CK(cudaMemcpy(e4, T.e4, (size_t)T.nele * 4 * 8, cudaMemcpyDeviceToHost));
+    if (J) CK(cudaMemcpy(J, T.J, (size_t)T.nele * 48 * 8, cudaMemcpyDeviceToHost));
+    if (cost) CK(cudaMemcpy(cost, T.cost, (size_t)T.nele * 8, cudaMemcpyDeviceToHost));
     return MB_OK;
 }
 

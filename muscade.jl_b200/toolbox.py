@@ -423,3 +423,61 @@ class SingleAcost(Acost):
     @staticmethod
     def lagrangian(eleobj, extra, Λ, X, U, A, t, SP):
         return extra["cost"](A[0], *extra["args"])
+
+
+# ------------------------------------------------------------------------------------------------ strain gauges on beams, ElementCost (device accelerator, xua.py)
+class StrainGaugeOnEulerBeam3D(EulerBeam3D):
+    """StrainGaugeOnEulerBeam3D(nod;P,D,ElementType=EulerBeam3D,elementkwargs) (toolbox/StrainGaugeOnBeamElement.jl:47-67): wraps an EulerBeam3D, adds the requestables
+    εₐₓ, κ and ε = E·εₐₓ + K1·κ₁ + K2·κ₂ + K3·κ₃ (:70-76).  P, D: (3, Ngauge) position offsets (P[0,:] = 0) and directions of the gauges."""
+
+    @classmethod
+    def doflist(cls, P=None, D=None, elementkwargs=None, **kw):
+        return EulerBeam3D.doflist(**(elementkwargs or {}))
+
+    @classmethod
+    def typekey(cls, P=None, D=None, elementkwargs=None, **kw):
+        return ("StrainGaugeOnEulerBeam3D", np.asarray(P).shape[1]) + EulerBeam3D.typekey(**(elementkwargs or {}))
+
+    @staticmethod
+    def gauge_matrix(P, D):
+        """(Ngauge,4): E, K1, K2, K3 per gauge (:62-65)"""
+        P = np.asarray(P, float); D = np.asarray(D, float)
+        if not (P[0, :] == 0.).all():
+            raise ValueError("In arguments of StrainGaugeOnEulerBeam3D, P[1,:] must all be zero")
+        E = D[0, :] ** 2
+        K1 = D[0, :] * (D[2, :] * P[1, :] - D[1, :] * P[2, :])
+        K2 = -D[0, :] ** 2 * P[1, :]
+        K3 = -D[0, :] ** 2 * P[2, :]
+        return np.ascontiguousarray(np.stack([E, K1, K2, K3], axis=1))
+
+    @classmethod
+    def construct(cls, coords, P, D, elementkwargs):
+        return EulerBeam3D.construct(coords, **elementkwargs), dict(G=cls.gauge_matrix(P, D), P=np.asarray(P, float), D=np.asarray(D, float))
+
+
+class QuadraticGaugeCost:
+    """One of the cost functors the device evaluates for ElementCost: cost(eleres,t) = Δε·Δε/(2σ²), Δε = eleres.ε − εm(t) (the `straincost` of
+    test/TestBeamElementStrainGauge.jl:90-97).  measured(t) → (Ngauge,) for all elements, or (nele,Ngauge)."""
+
+    def __init__(self, sigma, measured):
+        self.sigma, self.measured = float(sigma), measured
+
+
+class ElementCost(ElementType):
+    """ElementCost(nod;req,cost,costargs,ElementType,elementkwargs) (src/BasicElements.jl:117-132): L = getlagrangian(target) + cost(eleres,t,costargs...).
+    On the device (csrc/mb_xua.cu, the accelerator of src/DirectXUA.jl:172-198): ElementType = StrainGaugeOnEulerBeam3D, req = ("ε",), cost = QuadraticGaugeCost."""
+    kind = "elementcost"
+
+    @classmethod
+    def doflist(cls, ElementType=None, elementkwargs=None, **kw):
+        return ElementType.doflist(**elementkwargs)
+
+    @classmethod
+    def typekey(cls, req=None, cost=None, ElementType=None, elementkwargs=None, **kw):
+        return ("ElementCost", tuple(req or ()), id(cost)) + ElementType.typekey(**elementkwargs)
+
+    @classmethod
+    def construct(cls, coords, req, cost, ElementType, elementkwargs, costargs=()):
+        built = ElementType.construct(coords, **elementkwargs)
+        eleobj, extra = built if isinstance(built, tuple) else (built, {})
+        return eleobj, dict(extra, req=tuple(req), cost=cost, costargs=tuple(costargs), target=ElementType)

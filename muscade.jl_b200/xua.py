@@ -20,7 +20,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import check, ptr
+from ._lib import check, ptr, ErrInfo, MB_ERR_NAN, MuscadeB200Error
 from .adiff2 import D2
 from .engine import Engine, _f64, _i64
 from .model import State, muscadeerror
@@ -112,12 +112,29 @@ class XUAEngine(Engine):
         self.nstep = [int(n) for n in nstep]; self.dt = [float(d) for d in dt]; self.nexp = len(self.nstep)
         self.nX, self.nU, self.nA = model.getndof(("X", "U", "A"))
         it = C.c_int32()
-        for et, ed in zip(model.ele, dis.dis):
-            if "lagrangian" not in (getattr(et.ElType, "kind", None), getattr(et.ElType, "kind_general", None)):
-                muscadeerror("the general DirectXUA path takes host-evaluated element types written against adiff2.D2 (kind = 'lagrangian'): %s" % (et.key,))
+        self.devtypes = {}                       # ityp (1-based) → QuadraticGaugeCost or None: element types evaluated by the device kernels
+        for ityp, (et, ed) in enumerate(zip(model.ele, dis.dis), 1):
+            T = et.ElType
+            target = et.extra.get("target") if (T.kind == "elementcost" and isinstance(et.extra, dict)) else None
+            if T.kind == "eulerbeam3d" or (target is not None and target.kind == "eulerbeam3d"):
+                udof = ed.U.shape[1] > 0
+                idev = self.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+                check(self.h, self.L.mb_xua_add_device_eletyp(self.h, idev, C.byref(it)))
+                cost = None
+                if target is not None:
+                    cost = et.extra["cost"]
+                    if not (hasattr(cost, "sigma") and hasattr(cost, "measured") and "G" in et.extra and et.extra["req"] == ("ε",)):
+                        muscadeerror("ElementCost on the device: ElementType = StrainGaugeOnEulerBeam3D, req = ('ε',), cost = QuadraticGaugeCost")
+                    G = _f64(et.extra["G"])
+                    check(self.h, self.L.mb_xua_set_gauge_cost(self.h, it.value, G.shape[0], ptr(G), cost.sigma, float(model.scaleΛ)))
+                self.devtypes[ityp] = cost
+                continue
+            if "lagrangian" not in (getattr(T, "kind", None), getattr(T, "kind_general", None)):
+                muscadeerror("the general DirectXUA path takes EulerBeam3D (device), ElementCost on strain-gauged beams (device) and host-evaluated element types "
+                             "written against adiff2.D2 (kind = 'lagrangian'): %s" % (et.key,))
             iX, iU, iA = _i64(ed.X), _i64(ed.U), _i64(ed.A)
             check(self.h, self.L.mb_xua_add_eletyp(self.h, et.nele, iX.shape[1], iU.shape[1], iA.shape[1], ptr(iX), ptr(iU), ptr(iA),
-                                                   1 if getattr(et.ElType, "acost", False) else 0, C.byref(it)))
+                                                   1 if getattr(T, "acost", False) else 0, C.byref(it)))
         flags = (1 if Xwhite else 0) | (2 if XUindep else 0) | (4 if UAindep else 0) | (8 if XAindep else 0)
         nbig, nnz = C.c_int64(), C.c_int64()
         ns = np.asarray(self.nstep, np.int64); dts = np.asarray(self.dt, float)
@@ -181,6 +198,20 @@ class XUAEngine(Engine):
     def set_packet(self, ityp, g, H):
         check(self.h, self.L.mb_xua_set_packet(self.h, ityp, ptr(_f64(g)), ptr(_f64(H))))
 
+    def get_packet(self, ityp):
+        et, ed = self.model.ele[ityp - 1], self.dis.dis[ityp - 1]
+        Np = ed.X.shape[1] * (self.OX + 2) + ed.U.shape[1] * (self.OU + 1) + ed.A.shape[1] * self.IA
+        g = np.zeros((et.nele, Np)); H = np.zeros((et.nele, Np, Np))
+        check(self.h, self.L.mb_xua_get_packet(self.h, ityp, ptr(g), ptr(H)))
+        return g, H
+
+    def get_gauge(self, ityp):
+        """(εₐₓ,κ) (nele,4), ∂(εₐₓ,κ)/∂X₀ (nele,4,12), cost (nele,) of a costed device type at the last evaluated step"""
+        n = self.model.ele[ityp - 1].nele
+        e4 = np.zeros((n, 4)); J = np.zeros((n, 4, 12)); c = np.zeros(n)
+        check(self.h, self.L.mb_xua_get_gauge(self.h, ityp, ptr(e4), ptr(J), ptr(c)))
+        return e4, J, c
+
     def add_A(self):
         check(self.h, self.L.mb_xua_add_A(self.h))
 
@@ -197,7 +228,20 @@ class XUAEngine(Engine):
 
     def assemble_step(self, iexp, istep, state, SP=None):
         """assemble!{:matrices}(out,…,state[iexp][istep],…) and its weighted addition into Lvv / Lv (src/DirectXUA.jl:328-353)"""
+        if self.devtypes:                        # device element types read the device-resident state
+            self.put_state(iexp, istep, state)
+            for ityp, cost in self.devtypes.items():
+                if cost is not None:
+                    em = _f64(cost.measured(state.time))
+                    check(self.h, self.L.mb_xua_set_gauge_measurements(self.h, ityp, ptr(em), 1 if em.ndim == 2 else 0))
+            where = ErrInfo()
+            rc = self.L.mb_xua_eval_device(self.h, iexp, istep, C.byref(where))
+            if rc == MB_ERR_NAN:
+                raise MuscadeB200Error("residual(...) returned NaN in R, FB or derivatives", dict(ieletyp=where.ieletyp, iele=where.iele, step=istep))
+            check(self.h, rc)
         for ityp, (et, ed) in enumerate(zip(self.model.ele, self.dis.dis), 1):           # Acost types included: see packets()
+            if ityp in self.devtypes:
+                continue
             g, H = packets(et, ed, self.OX, self.OU, self.IA, state.Λ[0], state.X, state.U, state.A, state.time, SP)
             self.set_packet(ityp, g, H)
         self.add_step(iexp, istep)
