@@ -70,6 +70,8 @@ int32_t mb_destroy(mb_handle* h) {
     cudaFreeHost(h->nanflag_host);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    for (cudaEvent_t ev : h->pipe_evx) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->pipe_ev) cudaEventDestroy(ev);
     if (h->gather_done) cudaEventDestroy(h->gather_done);
     if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
@@ -529,7 +531,29 @@ static int32_t build_pipeline(mb_handle* h) {
     for (int j = 0; j < C - 1; ++j) h->pipe_nz_end[(size_t)j] &= ~(int64_t)3;     // ranges of the 4-per-thread reduction start at multiples of 4
     h->pipe_nz_end[(size_t)C - 1] = h->nnz; h->pipe_vec_end[(size_t)C - 1] = h->ndofX;
     if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->h2d_stream) CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     while ((int)h->pipe_ev.size() < C) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); h->pipe_ev.push_back(ev); }
+    while ((int)h->pipe_evx.size() < C + 1) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); h->pipe_evx.push_back(ev); }
+    // dofs of the state an element chunk reads: one past the largest X-dof number of the chunks up to it (host-evaluated types do not read the device state)
+    {
+        h->pipe_x_need.assign((size_t)C, 0);
+        int32_t* dmax = nullptr; CK(dalloc(h, &dmax, 1));
+        void* tmp = nullptr; size_t tsz = 0;
+        for (const mb_handle::PipeItem& w : h->pipe_items) {
+            const Group& g = h->groups[(size_t)w.ig];
+            const int64_t n = (w.e1 - w.e0) * g.nx;
+            if (n <= 0 || !g.idxX) continue;
+            size_t need = 0;
+            CK(cub::DeviceReduce::Max(nullptr, need, g.idxX + w.e0 * g.nx, dmax, n, st));
+            if (need > tsz) { if (tmp) cudaFree(tmp); CK(cudaMalloc(&tmp, need)); tsz = need; }
+            CK(cub::DeviceReduce::Max(tmp, need, g.idxX + w.e0 * g.nx, dmax, n, st));
+            int32_t m = 0; CK(cudaMemcpyAsync(&m, dmax, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+            h->pipe_x_need[(size_t)w.chunk] = std::max<int64_t>(h->pipe_x_need[(size_t)w.chunk], (int64_t)m + 1);
+        }
+        if (tmp) cudaFree(tmp);
+        dfree(h, dmax);
+        for (int j = 1; j < C; ++j) h->pipe_x_need[(size_t)j] = std::max(h->pipe_x_need[(size_t)j], h->pipe_x_need[(size_t)j - 1]);
+    }
     h->pipe_state = 1;
     return MB_OK;
 }
@@ -626,22 +650,39 @@ int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const doub
     ARG(!X0 || ((OX < 1 || X1) && (OX < 2 || X2)), "state vectors missing for this OX");
     CK(cudaSetDevice(h->device));
     const size_t nb = (size_t)h->ndofX * sizeof(double);
-    if (X0) {                                      // X0 == NULL: assemble at the device-resident state (mb_sweepx_set_state / _newmark_decrement)
+    // chunked pipeline: with host nzval (D2H of the CSC values overlapped), or with host state in and host Lλ out (H2D of the state, the element kernels and the
+    // D2H of Lλ overlapped: the state arrives in ascending dof order and element chunk j starts as soon as the dofs it reads are there)
+    const bool want_pipe = (nzval != nullptr) || (X0 != nullptr && Llambda != nullptr);
+    if (h->pipe_state == 0 && want_pipe && h->nnz >= h->pipe_min_nnz) { int32_t rc = build_pipeline(h); if (rc) return rc; }
+    const bool piped = h->pipe_state == 1 && want_pipe;
+    const bool piped_in = piped && X0 != nullptr && !h->pipe_x_need.empty();
+    if (X0 && !piped_in) {                         // X0 == NULL: assemble at the device-resident state (mb_sweepx_set_state / _newmark_decrement)
         CK(cudaMemcpyAsync(h->X0, X0, nb, cudaMemcpyHostToDevice, h->stream));
         if (OX >= 1) CK(cudaMemcpyAsync(h->X1, X1, nb, cudaMemcpyHostToDevice, h->stream));
         if (OX >= 2) CK(cudaMemcpyAsync(h->X2, X2, nb, cudaMemcpyHostToDevice, h->stream));
     }
     if (U0 && h->ndofU > 0) CK(cudaMemcpyAsync(h->U0, U0, (size_t)h->ndofU * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (h->pipe_state == 0 && nzval && h->nnz >= h->pipe_min_nnz) { int32_t rc = build_pipeline(h); if (rc) return rc; }
-    if (h->pipe_state == 1 && nzval) {
+    if (piped) {
         // chunked: evaluate element range j, reduce the non-zeros / dofs it completes, ship them while range j+1 computes
         ARG(OX >= 0 && OX <= 2 && (mission == 0 || mission == 1) && newmark, "bad OX / mission / newmark");
         NewmarkDev nm{newmark[0], newmark[1], newmark[2], newmark[3], newmark[4], newmark[5], newmark[6]};
         const bool step = mission == 0 && OX > 0;
         CK(cudaMemsetAsync(h->nanflag, 0xFF, sizeof(unsigned long long), h->stream));
         const int C = h->pipe_chunks;
-        size_t it = 0; int64_t k0 = 0, d0 = 0;
+        size_t it = 0; int64_t k0 = 0, d0 = 0, x0 = 0;
+        if (piped_in) {                            // the state, in C pieces on its own stream (after whatever the engine's stream still does with the old state)
+            CK(cudaEventRecord(h->pipe_evx[(size_t)C], h->stream));
+            CK(cudaStreamWaitEvent(h->h2d_stream, h->pipe_evx[(size_t)C], 0));
+            const double* src[3] = {X0, X1, X2}; double* dst[3] = {h->X0, h->X1, h->X2};
+            for (int j = 0; j < C; ++j) {
+                const int64_t x1 = (j == C - 1) ? h->ndofX : std::min(h->ndofX, h->pipe_x_need[(size_t)j]);
+                if (x1 > x0) for (int d = 0; d <= OX; ++d) CK(cudaMemcpyAsync(dst[d] + x0, src[d] + x0, (size_t)(x1 - x0) * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
+                CK(cudaEventRecord(h->pipe_evx[(size_t)j], h->h2d_stream));
+                x0 = std::max(x0, x1);
+            }
+        }
         for (int j = 0; j < C; ++j) {
+            if (piped_in) CK(cudaStreamWaitEvent(h->stream, h->pipe_evx[(size_t)j], 0));
             for (; it < h->pipe_items.size() && h->pipe_items[it].chunk == j; ++it) {
                 const mb_handle::PipeItem& w = h->pipe_items[it];
                 int32_t rc = launch_group_range(h, (size_t)w.ig, w.e0, w.e1, OX, mission, nm, t);
@@ -651,7 +692,7 @@ int32_t mb_sweepx_assemble(mb_handle* h, int32_t OX, int32_t mission, const doub
             launch_gather_range(h, step, k0, k1, d0, d1);
             CK(cudaEventRecord(h->pipe_ev[(size_t)j], h->stream));
             CK(cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[(size_t)j], 0));
-            if (k1 > k0) CK(cudaMemcpyAsync(nzval + k0, h->nzval + k0, (size_t)(k1 - k0) * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (nzval && k1 > k0) CK(cudaMemcpyAsync(nzval + k0, h->nzval + k0, (size_t)(k1 - k0) * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
             if (Llambda && d1 > d0) CK(cudaMemcpyAsync(Llambda + d0, h->Ll + d0, (size_t)(d1 - d0) * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
             k0 = k1; d0 = d1;
         }

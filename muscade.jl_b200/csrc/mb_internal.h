@@ -77,9 +77,9 @@ struct mb_handle {
     std::vector<PipeItem> pipe_items;
     std::vector<int64_t> pipe_nz_end, pipe_vec_end;      // per chunk: non-zeros / dofs complete after it
     int pipe_state = 0;                                  // 0 not built, 1 ready, -1 not applicable
-    int pipe_chunks = 8; int64_t pipe_min_nnz = 1 << 22;
+    int pipe_chunks = 16; int64_t pipe_min_nnz = 1 << 22;
     cudaStream_t copy_stream = nullptr;
-    std::vector<cudaEvent_t> pipe_ev;
+    std::vector<cudaEvent_t> pipe_ev, pipe_evx; std::vector<int64_t> pipe_x_need; cudaStream_t h2d_stream = nullptr;      // host-state-in pipeline: events of the H2D pieces, dofs each chunk needs
     // device-resident path (mb_sweepx_assemble_dev), optional (MB_DEV_OVERLAP=1): the same chunk plan; the segmented reduction of chunk j on a
     // high-priority stream while the element kernels of chunk j+1 run.  Measured on B200 (10 M elements): 23.1 ms vs 23.0 ms serial — the
     // element CTAs hold the whole register file, the two kernels time-share the SMs instead of overlapping — so it is off by default.

@@ -204,3 +204,28 @@ def test_fused_epilogue_bit_identical(mb, engine_factory, monkeypatch, topology)
         assert np.array_equal(L, L2) and np.array_equal(nz, nz2)
         out.append((L, nz))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("shuffled", [False, True])
+@pytest.mark.parametrize("OX", [0, 2])
+def test_host_state_pipeline_bit_identical(mb, engine_factory, monkeypatch, OX, shuffled):
+    """mb_sweepx_assemble with host state in and host Lλ out (nzval left in HBM): the state is copied in pieces and element chunk j starts when the dofs it reads have
+    arrived; Lλ leaves range by range.  Same kernels on the same data ⇒ the bits of the one-shot call (MB_E2E_CHUNKS=1), also when the numbering gives the pipeline
+    nothing to overlap (shuffled: the first chunk already needs the whole state)."""
+    N = 60011
+    eleobj, idx, ndof = mb.synthetic.chain(N, dynamic=OX > 0)
+    if shuffled:
+        rng = np.random.default_rng(7)
+        perm = rng.permutation(ndof); idx = (perm[idx - 1] + 1).astype(np.int64)
+    X = mb.synthetic.state(ndof, nder=OX + 1)
+    nm = mb.synthetic.newmark_coefficients(OX, 0.3)
+    out = []
+    for chunks in ("1", "8"):
+        monkeypatch.setenv("MB_E2E_CHUNKS", chunks)
+        eng = engine_factory()
+        eng.add_eulerbeam3d(eleobj, idx, np.ones(12)); eng.sweepx_prepare(ndof)
+        L, _ = eng.sweepx_assemble(OX, "iter", X, nm, nzval_on_device=True)
+        L2, nz = eng.sweepx_assemble(OX, "iter", X, nm)                      # and with the CSC values copied out as well
+        assert np.array_equal(L, L2)
+        out.append((L, nz))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
