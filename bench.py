@@ -295,8 +295,14 @@ def run_sweepx(args, rank, world, local, comm, OX=None, N=None, steps=None, bloc
         res_ms = timed(lambda: eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval_on_device=True), reps)
         # (2) everything back to the host (a host sparse solver): + 8·nnz bytes of CSC values over PCIe, chunk-pipelined with the element kernels
         all_ms = timed(lambda: eng.sweepx_assemble(OX, "iter", X, nm, Llambda=Lh, nzval=nzh), reps)
+        # the ceiling of (1): the same bytes (state in, Llambda out) copied both ways at once with no kernel in between, every rank at the same time
+        barrier()
+        copy_ms = comm.max(eng.host_copy_ms(X[0], Lh, reps=3)) * (OX + 1)
         e2e = {"value": world * N / (res_ms * 1e-3), "unit": UNIT, "ms_per_step": res_ms,
                "h2d_bytes_per_step": int(8 * ndof * (OX + 1)), "d2h_bytes_per_step": int(8 * ndof),
+               "host_copy_only_ms": copy_ms,
+               "host_copy_note": "H2D of the state and D2H of Llambda alone, concurrently, all ranks at once (mb_measure_host_copy_ms): what the host's PCIe / memory gives "
+                                 "the %d GPU(s); the pipelined call cannot be faster than max(this, ms_per_step of the device-resident step)" % world,
                "note": "mb_sweepx_assemble through the C ABI with pinned HOST buffers, per rank: state.X in, Llambda out; the CSC values stay in HBM for the device "
                        "solver (mb_get_device_ptrs), as north_star specifies",
                "host_csc": {"value": world * N / (all_ms * 1e-3), "unit": UNIT, "ms_per_step": all_ms, "h2d_bytes_per_step": int(8 * ndof * (OX + 1)),

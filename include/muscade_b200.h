@@ -278,6 +278,8 @@ int32_t mb_sweepx_time_step_dev(mb_handle* h, int32_t OX, int32_t mission, doubl
 int32_t mb_measure_fp64_tflops(mb_handle* h, double* tflops);
 /* Device copy bandwidth (read+write bytes / time), GB/s. */
 int32_t mb_measure_copy_gbs(mb_handle* h, double* gbs);
+/* nbytes host→device and nbytes device→host at once from / to pinned host buffers (what mb_sweepx_assemble's host-state pipeline moves): ms per round, the e2e ceiling */
+int32_t mb_measure_host_copy_ms(mb_handle* h, const void* host_in, void* host_out, int64_t nbytes, int32_t reps, double* ms);
 int64_t mb_launch_count(const mb_handle* h);      /* kernels of this library launched so far on this handle */
 
 #ifdef __cplusplus

@@ -58,6 +58,7 @@ SYMBOLS = {
     "mb_sweepx_time_step_dev": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_double, f64p, C.c_int32, f32p]),
     "mb_measure_fp64_tflops": (C.c_int32, [H, C.POINTER(C.c_double)]),
     "mb_measure_copy_gbs": (C.c_int32, [H, C.POINTER(C.c_double)]),
+    "mb_measure_host_copy_ms": (C.c_int32, [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     "mb_launch_count": (C.c_int64, [H]),
     "mb_direct_prepare": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -868,6 +868,31 @@ int32_t mb_measure_fp64_tflops(mb_handle* h, double* tflops) {
     return MB_OK;
 }
 
+// the e2e path's ceiling: nbytes host→device and nbytes device→host at once (two copy engines, the streams of the host-state pipeline), pinned host buffers; wall-clock ms
+// of `reps` rounds after one warm-up.  With several ranks calling it together it measures what the HOST gives N GPUs in aggregate.
+int32_t mb_measure_host_copy_ms(mb_handle* h, const void* host_in, void* host_out, int64_t nbytes, int32_t reps, double* ms) {
+    if (!h || !host_in || !host_out || nbytes <= 0 || reps < 1 || !ms) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    void *din = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&din, (size_t)nbytes)); CK(cudaMalloc(&dout, (size_t)nbytes));
+    cudaStream_t s1, s2; CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cudaEvent_t a1, b1, a2, b2; CK(cudaEventCreate(&a1)); CK(cudaEventCreate(&b1)); CK(cudaEventCreate(&a2)); CK(cudaEventCreate(&b2));
+    double tot = 0.;
+    for (int r = 0; r <= reps; ++r) {
+        CK(cudaEventRecord(a1, s1)); CK(cudaEventRecord(a2, s2));
+        CK(cudaMemcpyAsync(din, host_in, (size_t)nbytes, cudaMemcpyHostToDevice, s1));
+        CK(cudaMemcpyAsync(host_out, dout, (size_t)nbytes, cudaMemcpyDeviceToHost, s2));
+        CK(cudaEventRecord(b1, s1)); CK(cudaEventRecord(b2, s2));
+        CK(cudaEventSynchronize(b1)); CK(cudaEventSynchronize(b2));
+        float m1, m2; CK(cudaEventElapsedTime(&m1, a1, b1)); CK(cudaEventElapsedTime(&m2, a2, b2));
+        if (r > 0) tot += (double)std::max(m1, m2);
+    }
+    *ms = tot / reps;
+    cudaFree(din); cudaFree(dout); cudaStreamDestroy(s1); cudaStreamDestroy(s2);
+    cudaEventDestroy(a1); cudaEventDestroy(b1); cudaEventDestroy(a2); cudaEventDestroy(b2);
+    return MB_OK;
+}
+
 int32_t mb_measure_copy_gbs(mb_handle* h, double* gbs) {
     if (!h || !gbs) return MB_ERR_ARG;
     CK(cudaSetDevice(h->device));

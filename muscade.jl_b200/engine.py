@@ -220,6 +220,12 @@ class Engine:
         check(self.h, self.L.mb_measure_copy_gbs(self.h, C.byref(v)))
         return v.value
 
+    def host_copy_ms(self, host_in, host_out, reps=3):
+        """ms per round of len(host_in) bytes H2D and as many D2H at once (pinned buffers): the ceiling of the host-buffer e2e path"""
+        v = C.c_double()
+        check(self.h, self.L.mb_measure_host_copy_ms(self.h, ptr(host_in), ptr(host_out), int(host_in.nbytes), int(reps), C.byref(v)))
+        return v.value
+
     def set_stream(self, cuda_stream):
         check(self.h, self.L.mb_set_stream(self.h, C.c_void_p(int(cuda_stream))))
 
