@@ -698,6 +698,64 @@ def run_scr(args, rank, world, local, comm, block=False):
     return line
 
 
+def run_gauges(args, rank, world, local, comm):
+    """The GENERAL DirectXUA form (mb_xua_*) with DEVICE element types and the ElementCost accelerator: N strain-gauged EulerBeam3D{Udof} (ElementCost{StrainGaugeOnEulerBeam3D},
+    quadratic strain cost, 5 gauges per element) x 6 time steps, DirectXUA{2,0,0}.  One bench step = one assemblebig! pass: per step the first-order beam kernels, the packet and
+    strain-gauge kernels, the segmented reductions into out and the weighted additions into Lvv / Lv.  Replicas only (the general form is not sharded): every rank runs the same problem."""
+    import ctypes as C
+    import muscade_b200 as mb
+    from muscade_b200 import xua
+    from muscade_b200._lib import check
+    N = int(args.nele) if args.nele else 100000
+    OX, nstep, dt = 2, 6, 0.1
+    P5 = np.array([[0., .5, 0.], [0., 0, .5], [0., -.5, 0.], [0., 0, -.5], [0., .5, 0.]]).T          # test/TestBeamElementStrainGauge.jl:10-11
+    D5 = np.array([[1., 0., 0.], [1., 0., 0.], [1., 0., 0.], [1., 0., 0.], [1 / np.sqrt(2), 0, 1 / np.sqrt(2)]]).T
+    m = mb.Model("gauged")
+    nod = mb.addnode(m, np.stack([np.arange(N + 1, dtype=float), np.zeros(N + 1), np.zeros(N + 1)], axis=1))
+    un = mb.addnode(m, np.zeros((N, 3)))
+    cost = mb.QuadraticGaugeCost(15e-6, lambda t: np.array([np.cos(t), 0., -np.cos(t), 0., np.cos(t) / 2]) * 0.001)
+    mb.addelement(m, mb.ElementCost, np.stack([nod[:-1], nod[1:], un], axis=1), req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e4, EI2=300., EI3=300., GJ=400., mu=1., iota1=1.), orient2=(0., 1., 0.), Udof=True)))
+    s0 = mb.initialize(m); dis = s0.dis
+    nX, nU, _ = m.getndof(("X", "U", "A"))
+    eng = xua.XUAEngine(local)
+    nbig, nnz = eng.prepare(m, dis, OX, 0, 0, [nstep], [dt])
+    st = s0.with_orders(1, OX + 1, 1)
+    for k in range(nstep):
+        s = mb.State(dt * k, [mb.synthetic.uniform_pm1(7 + k, nX)], [0.01 * mb.synthetic.uniform_pm1(20 + 3 * k + d, nX) for d in range(OX + 1)],
+                     [0.1 * mb.synthetic.uniform_pm1(90 + k, nU)], st.A, None, m, dis)
+        eng.put_state(1, k + 1, s)
+    em = np.ascontiguousarray(cost.measured(0.))
+    check(eng.h, eng.L.mb_xua_set_gauge_measurements(eng.h, 1, em.ctypes.data_as(C.c_void_p), 0))
+    ms = np.zeros(1, np.float32)
+    check(eng.h, eng.L.mb_xua_time_device_pass(eng.h, max(1, args.warmup), ms))
+    comm.barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    check(eng.h, eng.L.mb_xua_time_device_pass(eng.h, args.steps, ms))      # CUDA events on the engine's stream around `steps` whole passes (after one more warm-up pass)
+    step_ms = comm.max(float(ms[0]))
+    launches = (eng.launch_count() - launches0) * args.steps // (args.steps + 1)
+    clocks = sampler.stop() if sampler else None
+    line = None
+    if rank == 0:
+        Np = 12 + 12 * (OX + 1) + 3
+        bytes_step = N * (8 * Np * Np * 2 + 8 * 12 * (12 * (OX + 1) + 3) * 2) + 24 * nnz // nstep         # packets written + read, (R,dR) written + read, Lvv values read + written + map read
+        line = {"metric": "element-step assemblies/s (DirectXUA{2,0,0} assemblebig!, general form, ElementCost{StrainGaugeOnEulerBeam3D} on the device)",
+                "value": N * nstep / (step_ms * 1e-3), "unit": "element-step assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms, "ms_per_pass": step_ms, "higher_is_better": True, "scaling": "replicas", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "general DirectXUA{2,0,0} form (mb_xua_*): %d strain-gauged EulerBeam3D{Udof} (5 gauges each, quadratic strain cost: the ElementCost accelerator on "
+                                       "the device) x %d time steps; no host-evaluated type, states resident in HBM" % (N, nstep),
+                           "elements": N, "nstep": nstep, "lvv_size": int(nbig), "lvv_nnz": int(nnz), "l2": "packets (%.1f GB per step) and Lvv (%.1f GB) larger than L2" % (8e-9 * N * Np * Np, 8e-9 * nnz)},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": bytes_step * nstep / (step_ms * 1e-3) / 1e9, "peak": hbm_peak()[0], "peak_source": hbm_peak()[1],
+                             "frac": bytes_step * nstep / (step_ms * 1e-3) / 1e9 / hbm_peak()[0], "traffic": None,
+                             "bytes_per_step": int(bytes_step),
+                             "note": "whole pass against the HBM peak (MEASURED_PEAKS.json): dense packets of %d x %d partials per element are written by the element kernels and read by "
+                                     "the segmented reductions — the price of the general form; the beam-specialised path (directxua block) moves a tenth of it" % (Np, Np)}}
+    eng.close()
+    return line
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -718,6 +776,8 @@ def main():
         line = run_directxua_weak(args, rank, world, local, comm)
     elif args.workload == "scr":
         line = run_scr(args, rank, world, local, comm)
+    elif args.workload == "gauges":
+        line = run_gauges(args, rank, world, local, comm)
     else:
         line = run_sweepx(args, rank, world, local, comm)
         if not args.no_directxua and args.nele is None and args.ox == 0:

@@ -153,7 +153,7 @@ int32_t mb_direct_time_dev(mb_handle* h, int32_t reps, float* ms);
  * user Lagrangians): prepare(AssemblyDirect{OX,OU,IA}) (src/DirectXUA.jl:22-56: asmvec!/asmmat! for all class pairs), makepattern / preparebig (:245-315, with the
  * A block row / column and `for iexp`), SparseTools.prepare (src/SparseTools.jl:32-94: Lvv, Lvvasm, Lvasm — bit-identical structures), assembleA! (:320-326),
  * assemblebig!{:matrices} (:316-356), sparser! and decrementbig! (:357-383).  Classes are numbered 1 Λ, 2 X, 3 U, 4 A as `ind` (:14); experiments and steps 1-based.
- * Element derivatives come in as PACKETS per element type and step: ∇L [nele][Np] and ∇²L [nele][Np][Np] (row-major) in the order of partials of
+ * Element derivatives come in as PACKETS per element type and step: ∇L [nele][Np] and ∇²L [nele][Np][Np] (symmetric; the device reads entry (row,col) at [col][row]) in the order of partials of
  * DirectXUA_lagrangian_addition! (:121-150): Λ (nx), X₀…X_OX (nx each), U₀…U_OU (nu each), A (na, IA = 1 only), scaled as revariate(…,scale) scales them.  Which parts are
  * filled follows the reference's addin! method for the element type: no_second_order types (:85-120) fill ∇L[Λ] = R and the Λ-row / Λ-column of ∇²L only.
  * Acost types (acost = 1; only A dofs) are assembled by mb_xua_add_A from packets with Np = na (unscaled, :70-84) AND, like any type, by mb_xua_add_step from their
@@ -188,13 +188,15 @@ int32_t mb_xua_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double
  *                              DirectXUA_lagrangian_addition! a Lagrangian without Λ-partials, so the reference has no behaviour to copy there): L = Λ∘₁R + cost with first-order R
  *                              and eleres, second-order cost ⇒ ∇²L[X,X] = Jᵀ·∇²cost·J, no Λ·∂²R/∂X² term.
  *   mb_xua_set_gauge_measurements : εm of the step about to be evaluated, [ngauge] or [nele][ngauge].
- *   mb_xua_eval_device       : packets of all device types at the device-resident state[iexp][istep]; NaN → MB_ERR_NAN with the element.
+ *   mb_xua_eval_device       : packets of all device types at the device-resident state[iexp][istep]; NaN → MB_ERR_NAN with the element (where = NULL: asynchronous, no check).
  *   mb_xua_get_packet / mb_xua_get_gauge : the packet as it stands; (εₐₓ,κ) [nele][4], ∂(εₐₓ,κ)/∂X₀ [nele][4][12] (scaled), cost [nele] of a costed type. */
 int32_t mb_xua_add_device_eletyp(mb_handle* h, int32_t ieletyp_dev, int32_t* ieletyp_out);
 int32_t mb_xua_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma, double lambda_scale);
 int32_t mb_xua_set_gauge_measurements(mb_handle* h, int32_t ieletyp, const double* epsm, int32_t per_element);
 int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo* where);
 int32_t mb_xua_get_packet(mb_handle* h, int32_t ieletyp, double* gradL, double* hessL);
+/* CUDA-event time of whole assemblebig! passes over the device element types (eval_device + add_step for every step), ms per pass */
+int32_t mb_xua_time_device_pass(mb_handle* h, int32_t reps, float* ms);
 int32_t mb_xua_get_gauge(mb_handle* h, int32_t ieletyp, double* e4, double* J, double* cost);
 /* state[iexp][istep]: Λ (nX), X (OX+1)·nX, U (OU+1)·nU contiguous by derivative, A (nA) shared by all states (:452); NULL leaves a part untouched.
  * mb_xua_decrement: decrementbig! with dv = Δv in Lv's layout (host or device) → Δ² for Λ, X, U (max over steps of ΣΔβ²) and A. */

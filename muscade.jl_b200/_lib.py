@@ -95,6 +95,7 @@ SYMBOLS = {
     "mb_xua_set_gauge_measurements": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_int32]),
     "mb_xua_eval_device": (C.c_int32, [H, C.c_int32, C.c_int64, C.POINTER(ErrInfo)]),
     "mb_xua_get_packet": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_xua_time_device_pass": (C.c_int32, [H, C.c_int32, f32p]),
     "mb_xua_get_gauge": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_xua_zero": (C.c_int32, [H]),
     "mb_xua_set_packet": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -39,10 +39,11 @@ struct XuaType {
     double *g = nullptr, *H = nullptr; bool has = false;
     // device-evaluated type (EulerBeam3D of the handle, mb_xua_add_device_eletyp): outputs of the first-order kernels, and the ElementCost accelerator's strain-gauge cost
     int devgroup = -1; double *dR = nullptr, *Rb = nullptr;
-    int ng = 0; double isig2 = 0.; double *G = nullptr, *epsm = nullptr, *J = nullptr, *e4 = nullptr, *cost = nullptr; bool epsm_per_element = false;
+    int ng = 0; double isig2 = 0.; double *G = nullptr, *epsm = nullptr, *J = nullptr, *e4 = nullptr, *cost = nullptr, *sL = nullptr; bool epsm_per_element = false;
 };
 struct TabDev {                                  // per element type, for one (α,β) or α: by value into the gather kernels
     int n; uint32_t pbase[XMAXT + 1]; int ni[XMAXT], nj[XMAXT], Np[XMAXT], bi[XMAXT], bj[XMAXT]; const double* p[XMAXT];
+    uint16_t live[XMAXT];                    // per type: derivative blocks (i·nbd + j; for vectors: i) of this class pair its packet can be non-zero in
 };
 struct Combo2 { int i, j; double f; int64_t off; };      // L2[α,β][i,j]·f → Lvv.nzval[basm[off + l]]
 struct Combo1 { int i; double f; int64_t row0; };        // L1[β][i]·f → Lv[row0 + d]
@@ -53,33 +54,36 @@ __device__ __forceinline__ int find_type(const uint32_t* pbase, int n, uint32_t 
     return t;
 }
 // out[(i·nbd + j)·nnz + k] = Σ_contributors H[e][bi + ni·i + ia][bj + nj·j + ib]   (grid.y = i·nbd + j)
-__global__ void xua_gather2_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, TabDev T, int nbd, double* __restrict__ out) {
+// live: bit (i·nbd + j) set where some element type can contribute to L2[α,β][i,j]; the other blocks are written as zeros without reading anything
+__global__ void xua_gather2_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, TabDev T, int nbd, uint32_t live, double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     const int i = blockIdx.y / nbd, j = blockIdx.y - i * nbd;
     double acc = 0.;
+    if (!((live >> blockIdx.y) & 1u)) { out[(int64_t)blockIdx.y * nnz + k] = 0.; return; }
     for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
         const uint32_t id = src[s];
         const int t = find_type(T.pbase, T.n, id);
-        if (!T.p[t]) continue;
+        if (!T.p[t] || !((T.live[t] >> blockIdx.y) & 1u)) continue;
         const uint32_t r = id - T.pbase[t];
         const int n2 = T.ni[t] * T.nj[t];
         const int64_t e = r / n2; const int q = (int)(r - e * n2);
         const int ib = q / T.ni[t], ia = q - ib * T.ni[t];                      // entry ieledof + ni·(jeledof−1)  (src/Assemble.jl:389)
-        acc += T.p[t][(e * T.Np[t] + (T.bi[t] + T.ni[t] * i + ia)) * T.Np[t] + (T.bj[t] + T.nj[t] * j + ib)];
+        acc += T.p[t][(e * T.Np[t] + (T.bj[t] + T.nj[t] * j + ib)) * T.Np[t] + (T.bi[t] + T.ni[t] * i + ia)];      // ∇²L is symmetric: entry (α,β) read at [β][α], so that the rows ia of a column — consecutive non-zeros — are consecutive addresses
     }
     out[(int64_t)blockIdx.y * nnz + k] = acc;
 }
 // out[i·ndof + d] = Σ_contributors g[e][bi + ni·i + ia]   (grid.y = i)
-__global__ void xua_gather1_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, TabDev T, double* __restrict__ out) {
+__global__ void xua_gather1_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, TabDev T, uint32_t live, double* __restrict__ out) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
     const int i = blockIdx.y;
     double acc = 0.;
+    if (!((live >> i) & 1u)) { out[(int64_t)i * ndof + d] = 0.; return; }
     for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) {
         const uint32_t id = vsrc[s];
         const int t = find_type(T.pbase, T.n, id);
-        if (!T.p[t]) continue;
+        if (!T.p[t] || !((T.live[t] >> i) & 1u)) continue;
         const uint32_t r = id - T.pbase[t];
         const int64_t e = r / T.ni[t]; const int ia = (int)(r - e * T.ni[t]);
         acc += T.p[t][e * T.Np[t] + (T.bi[t] + T.ni[t] * i + ia)];
@@ -87,20 +91,23 @@ __global__ void xua_gather1_kernel(int64_t ndof, const uint32_t* __restrict__ vs
     out[(int64_t)i * ndof + d] = acc;
 }
 // addin!(asm,out,block,ibr,ibc,factor) (src/SparseTools.jl:101-122) for every (αder,βder,iα,iβ) of one class pair, in the reference's loop order, one thread per block entry
-__global__ void xua_addin2_kernel(int64_t nnz, const double* __restrict__ L2, int nbd, const Combo2* __restrict__ cb, int nc, const int64_t* __restrict__ basm, double* __restrict__ big) {
+// live: as in xua_gather2_kernel — blocks no element type contributes to hold zeros and are not added (x + 0 = x)
+__global__ void xua_addin2_kernel(int64_t nnz, const double* __restrict__ L2, int nbd, uint32_t live, const Combo2* __restrict__ cb, int nc, const int64_t* __restrict__ basm, double* __restrict__ big) {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nnz) return;
     for (int c = 0; c < nc; ++c) {
         const Combo2 q = cb[c];
+        if (!((live >> (q.i * nbd + q.j)) & 1u)) continue;
         double* dst = big + (basm[q.off + l] - 1);
         *dst = __dadd_rn(*dst, __dmul_rn(L2[(int64_t)(q.i * nbd + q.j) * nnz + l], q.f));
     }
 }
-__global__ void xua_addin1_kernel(int64_t ndof, const double* __restrict__ L1, const Combo1* __restrict__ cb, int nc, double* __restrict__ Lv) {
+__global__ void xua_addin1_kernel(int64_t ndof, const double* __restrict__ L1, uint32_t live, const Combo1* __restrict__ cb, int nc, double* __restrict__ Lv) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
     for (int c = 0; c < nc; ++c) {
         const Combo1 q = cb[c];
+        if (!((live >> q.i) & 1u)) continue;
         double* dst = Lv + q.row0 + d;
         *dst = __dadd_rn(*dst, __dmul_rn(L1[(int64_t)q.i * ndof + d], q.f));
     }
@@ -210,22 +217,38 @@ __global__ void __launch_bounds__(256) xua_sumsq_kernel(int64_t nX, int64_t nU, 
 // (R, dR) of the first-order kernels (beam_kernel.cuh K3: dR[e][p][i] = ∂R_i/∂seed_p, p over X₀ X₁ X₂ U₀, seeds scaled; R unscaled) → packet of a no_second_order type
 // (src/DirectXUA.jl:85-120): ∇L[Λ] = R, the Λ rows / columns of ∇²L = ∂R/∂β.  COSTED (an ElementCost wraps the type, :172-198 as intended: L = Λ∘₁R + cost with first-order R):
 // ∇L[Λ] = R·scale.Λ, ∇L[X_der] = Σᵢ Λᵢ·∂Rᵢ/∂X_der (likewise U), Λ rows / columns scaled by scale.Λ; the cost's own terms are added by gauge_cost_kernel.
-__global__ void beam_packet_kernel(int64_t nele, int npd, int Np, int nxd /* 12·(OX+1) */, int nu0 /* packet column of U₀ or −1 */, const double* __restrict__ R,
+__global__ void __launch_bounds__(128) beam_packet_kernel(int64_t nele, int npd, int Np, int nxd /* 12·(OX+1) */, int nu0 /* packet column of U₀ or −1 */, const double* __restrict__ R,
                                    const double* __restrict__ dR, const int32_t* __restrict__ idxX, const double* __restrict__ Lam, const double* sLam12, bool costed,
                                    double* __restrict__ g, double* __restrict__ H) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nele * npd) return;
-    const int64_t e = t / npd; const int p = (int)(t - e * npd);          // one thread per (element, seed p): column 12 + p' of the Λ rows
-    const int col = (p < nxd) ? 12 + p : nu0 + (p - nxd);
+    // one CTA per element: its ∂R/∂seed (npd × 12, contiguous) goes through shared memory so that BOTH copies — the Λ rows H[i][col] and the Λ columns H[col][i] — leave as
+    // contiguous runs (written straight from the [p][i] layout one of the two is a stride-Np scatter of 8-byte stores)
+    __shared__ double sm[39 * 12];
+    __shared__ double lam[12], sl[12];
+    const int64_t e = blockIdx.x;
+    const int n = npd * 12;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) sm[q] = dR[e * n + q];
+    if (threadIdx.x < 12) { lam[threadIdx.x] = costed ? Lam[idxX[e * 12 + threadIdx.x]] : 0.; sl[threadIdx.x] = costed ? sLam12[threadIdx.x] : 1.; }
+    __syncthreads();
     double* He = H + e * (int64_t)Np * Np; double* ge = g + e * (int64_t)Np;
-    double acc = 0.;
-    for (int i = 0; i < 12; ++i) {
-        double v = dR[(e * npd + p) * 12 + i];
-        if (costed) { acc += Lam[idxX[e * 12 + i]] * v; v *= sLam12[i]; }
-        He[i * Np + col] = v; He[col * Np + i] = v;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ columns: H[col][i], i fastest
+        const int p = q / 12, i = q - p * 12;
+        const int col = (p < nxd) ? 12 + p : nu0 + (p - nxd);
+        He[col * Np + i] = sm[q] * sl[i];
     }
-    if (costed) ge[col] = acc;
-    if (p < 12) ge[p] = costed ? R[e * 12 + p] * sLam12[p] : R[e * 12 + p];
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ rows: H[i][col], col fastest
+        const int i = q / npd, p = q - i * npd;
+        const int col = (p < nxd) ? 12 + p : nu0 + (p - nxd);
+        He[i * Np + col] = sm[p * 12 + i] * sl[i];
+    }
+    if (threadIdx.x < npd) {
+        const int p = threadIdx.x;
+        if (costed) {
+            double acc = 0.;
+            for (int i = 0; i < 12; ++i) acc += lam[i] * sm[p * 12 + i];
+            ge[(p < nxd) ? 12 + p : nu0 + (p - nxd)] = acc;
+        }
+        if (p < 12) ge[p] = R[e * 12 + p] * sl[p];
+    }
 }
 // requestables (εₐₓ, ♢κ) of EulerBeam3D (toolbox/BeamElement.jl:151-174) with their partials ∂/∂X₀ (scaled): one lane per (element, element dof), one-direction duals
 // through the forward kinematics only.  J[e][k][d], e4[e][k]  (k: εₐₓ, κ₁, κ₂, κ₃)
@@ -247,7 +270,7 @@ __global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const d
 }
 // ElementCost accelerator for StrainGaugeOnEulerBeam3D (toolbox/StrainGaugeOnBeamElement.jl:70-76) under the quadratic cost Σ_g (ε_g − εm_g)²/(2σ²):
 // ε_g = G[g]·(εₐₓ,κ); ∇cost = Jᵀ·Gᵀ·r/σ², ∇²cost = Jᵀ·GᵀG·J/σ² (chainrule of the second-order cost with the first-order eleres: to_order{2} adds no curvature, :190-196).
-// One thread per (element, i): row i of the X₀-X₀ block and entry i of the X₀ gradient are ADDED to the packet.
+// One thread per (element, i): entry i of the X₀ gradient is ADDED to the packet (beam_packet_kernel put Λᵀ∂R/∂X₀ there), row i of the X₀-X₀ block is written.
 __global__ void gauge_cost_kernel(int64_t nele, int ng, int Np, const double* __restrict__ G, const double* __restrict__ epsm, bool per_element, double isig2,
                                   const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ g, double* __restrict__ H, double* __restrict__ cost) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,7 +288,7 @@ __global__ void gauge_cost_kernel(int64_t nele, int ng, int Np, const double* __
     for (int k = 0; k < 4; ++k) { gi += Je[k * 12 + i] * q[k]; MJ[k] = ((M[k][0] * Je[i] + M[k][1] * Je[12 + i]) + M[k][2] * Je[24 + i]) + M[k][3] * Je[36 + i]; }
     g[e * (int64_t)Np + 12 + i] += gi * isig2;
     double* Hrow = H + (e * (int64_t)Np + 12 + i) * Np + 12;
-    for (int j = 0; j < 12; ++j) Hrow[j] += (((Je[j] * MJ[0] + Je[12 + j] * MJ[1]) + Je[24 + j] * MJ[2]) + Je[36 + j] * MJ[3]) * isig2;
+    for (int j = 0; j < 12; ++j) Hrow[j] = (((Je[j] * MJ[0] + Je[12 + j] * MJ[1]) + Je[24 + j] * MJ[2]) + Je[36 + j] * MJ[3]) * isig2;      // the whole X₀-X₀ block is the cost's (no Λ·∂²R/∂X²)
     if (i == 0 && cost) cost[e] = 0.5 * c * isig2;
 }
 
@@ -297,6 +320,21 @@ struct XuaData {
 
 void mb_xua_release(mb_handle* h) { delete h->xua; h->xua = nullptr; }
 
+// which derivative blocks of a type's packet can be non-zero: everything for host-set packets (unknown); for a device beam type what beam_packet_kernel / gauge_cost_kernel fill —
+// ∇L[Λ], the Λ rows / columns against X_d and U₀, and for a costed type ∇L[X_d], ∇L[U₀] and the X₀-X₀ block
+static inline bool xua_live1(const XuaType& T, int a, int i) {
+    if (T.devgroup < 0) return true;
+    if (a == 0) return true;
+    if (T.ng == 0) return false;
+    return a == 1 || (a == 2 && i == 0);
+}
+static inline bool xua_live2(const XuaType& T, int a, int b, int i, int j) {
+    if (T.devgroup < 0) return true;
+    if (a == 0 && b == 0) return false;
+    if (a == 0) return b == 1 || (b == 2 && j == 0);
+    if (b == 0) return a == 1 || (a == 2 && i == 0);
+    return T.ng > 0 && a == 1 && b == 1 && i == 0 && j == 0;
+}
 static const int FDN[3][3] = {{1, 1, 1}, {2, 2, 2}, {3, 3, 3}};
 static const int FDS[3][3][3] = {{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, {{0, 1, 0}, {-1, 0, 0}, {-1, 1, 0}}, {{0, 1, 2}, {-2, -1, 0}, {-1, 0, 1}}};
 static const double FDW[3][3][3] = {{{1., 0, 0}, {1., 0, 0}, {1., 0, 0}}, {{-1., 1., 0}, {-1., 1., 0}, {-.5, .5, 0}}, {{1., -2., 1.}, {1., -2., 1.}, {1., -2., 1.}}};
@@ -669,12 +707,15 @@ static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_
             const XuaType& Y = D->types[(size_t)t];
             T.pbase[t] = (uint32_t)D->vbase[ca][(size_t)t]; T.ni[t] = Y.n[ca]; T.nj[t] = 0; T.Np[t] = Y.Np; T.bi[t] = Y.base[a]; T.bj[t] = 0;
             T.p[t] = (Y.has && (!acost || Y.acost) && (a != 3 || D->IA)) ? Y.g : nullptr;
+            T.live[t] = 0;
+            if (T.p[t]) for (int i = 0; i < nd; ++i) if (Y.n[ca] > 0 && Y.nele > 0 && xua_live1(Y, a, i)) T.live[t] |= (uint16_t)(1u << i);
         }
+        uint32_t live = 0; for (int t = 0; t < T.n; ++t) live |= T.live[t];
         T.pbase[T.n] = (uint32_t)D->vbase[ca][(size_t)T.n];
-        xua_gather1_kernel<<<dim3(nblk(D->ndof[ca], 128), (unsigned)nd), 128, 0, st>>>(D->ndof[ca], D->vstart[ca], D->vsrc[ca], T, D->L1[a]);
+        xua_gather1_kernel<<<dim3(nblk(D->ndof[ca], 128), (unsigned)nd), 128, 0, st>>>(D->ndof[ca], D->vstart[ca], D->vsrc[ca], T, live, D->L1[a]);
         h->launches++;
         const int64_t c0 = D->c1start[(size_t)(slot * 4 + a)], c1 = D->c1start[(size_t)(slot * 4 + a + 1)];
-        if (c1 > c0) { xua_addin1_kernel<<<nblk(D->ndof[ca], 128), 128, 0, st>>>(D->ndof[ca], D->L1[a], D->cb1 + c0, (int)(c1 - c0), D->Lv); h->launches++; }
+        if (c1 > c0 && live) { xua_addin1_kernel<<<nblk(D->ndof[ca], 128), 128, 0, st>>>(D->ndof[ca], D->L1[a], live, D->cb1 + c0, (int)(c1 - c0), D->Lv); h->launches++; }
     }
     for (int a = 0; a < ncls; ++a)
         for (int b = 0; b < ncls; ++b) {
@@ -686,12 +727,16 @@ static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_
                 const XuaType& Y = D->types[(size_t)t];
                 T.pbase[t] = (uint32_t)P.gbase[(size_t)t]; T.ni[t] = Y.n[cgroup(a)]; T.nj[t] = Y.n[cgroup(b)]; T.Np[t] = Y.Np; T.bi[t] = Y.base[a]; T.bj[t] = Y.base[b];
                 T.p[t] = (Y.has && (!acost || Y.acost)) ? Y.H : nullptr;
+                T.live[t] = 0;
+                if (T.p[t] && Y.nele > 0 && T.ni[t] > 0 && T.nj[t] > 0)
+                    for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j) if (xua_live2(Y, a, b, i, j)) T.live[t] |= (uint16_t)(1u << (i * nb + j));
             }
+            uint32_t live = 0; for (int t = 0; t < T.n; ++t) live |= T.live[t];
             T.pbase[T.n] = (uint32_t)P.gbase[(size_t)T.n];
-            xua_gather2_kernel<<<dim3(nblk(P.nnz, 128), (unsigned)(na * nb)), 128, 0, st>>>(P.nnz, P.cstart, P.src, T, nb, D->L2[a][b]);
+            xua_gather2_kernel<<<dim3(nblk(P.nnz, 128), (unsigned)(na * nb)), 128, 0, st>>>(P.nnz, P.cstart, P.src, T, nb, live, D->L2[a][b]);
             h->launches++;
             const int64_t c0 = D->c2start[(size_t)(slot * 16 + 4 * a + b)], c1 = D->c2start[(size_t)(slot * 16 + 4 * a + b + 1)];
-            if (c1 > c0) { xua_addin2_kernel<<<nblk(P.nnz, 128), 128, 0, st>>>(P.nnz, D->L2[a][b], nb, D->cb2 + c0, (int)(c1 - c0), D->basm, D->nzval); h->launches++; }
+            if (c1 > c0 && live) { xua_addin2_kernel<<<nblk(P.nnz, 128), 128, 0, st>>>(P.nnz, D->L2[a][b], nb, live, D->cb2 + c0, (int)(c1 - c0), D->basm, D->nzval); h->launches++; }
         }
     for (XuaType& Y : D->types) if (!acost || Y.acost) Y.has = false;
     CK(cudaGetLastError());
@@ -765,9 +810,9 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
         for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
         const int npd = 12 * nd + (g.udof ? 3 : 0);
         const int64_t ng = T.nele * T.Np, nh = ng * T.Np;
-        if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(dalloc(h, &T.H, nh)); }
+        // the kernels below write every entry of the packet blocks a device type can fill (xua_live1 / xua_live2) and nothing else: the rest is zeroed once, here
+        if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(dalloc(h, &T.H, nh)); CK(cudaMemsetAsync(T.g, 0, (size_t)ng * 8, st)); CK(cudaMemsetAsync(T.H, 0, (size_t)nh * 8, st)); }
         if (!T.dR) { CK(dalloc(h, &T.dR, T.nele * 12 * npd)); CK(dalloc(h, &T.Rb, T.nele * 12)); }
-        CK(cudaMemsetAsync(T.g, 0, (size_t)ng * 8, st)); CK(cudaMemsetAsync(T.H, 0, (size_t)nh * 8, st));
         DirectStateDev sd;
         for (int d = 0; d < 3; ++d) sd.X[d] = D->X + (gs * 3 + d) * nX;
         sd.U0 = nU ? D->U + gs * 3 * nU : nullptr;
@@ -783,10 +828,11 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
         else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
         else h->launches += launch_beam_direct<3>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
         const bool costed = T.ng > 0;
-        double sL[12]; for (int i = 0; i < 12; ++i) sL[i] = g.scaleX[i] * D->lamscale;
-        double* dsL = nullptr;
-        if (costed) { CK(dalloc(h, &dsL, 12)); CK(cudaMemcpyAsync(dsL, sL, sizeof(sL), cudaMemcpyHostToDevice, st)); }
-        beam_packet_kernel<<<nblk(T.nele * npd, 128), 128, 0, st>>>(T.nele, npd, T.Np, 12 * nd, g.udof ? 12 + 12 * nd : -1, T.Rb, T.dR, g.idxX, D->Lam + gs * nX, dsL, costed, T.g, T.H);
+        if (costed && !T.sL) {                     // scale.Λ of the element dofs = scale.X·Λscale (src/Assemble.jl:55), once
+            double sL[12]; for (int i = 0; i < 12; ++i) sL[i] = g.scaleX[i] * D->lamscale;
+            CK(dalloc(h, &T.sL, 12)); CK(cudaMemcpy(T.sL, sL, sizeof(sL), cudaMemcpyHostToDevice));
+        }
+        beam_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, npd, T.Np, 12 * nd, g.udof ? 12 + 12 * nd : -1, T.Rb, T.dR, g.idxX, D->Lam + gs * nX, T.sL, costed, T.g, T.H);
         h->launches++;
         if (costed) {
             ARG(T.epsm, "strain-gauge measurements of this step are not set (mb_xua_set_gauge_measurements)");
@@ -794,21 +840,40 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
             beam_gauge_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(gd, sd.X[0], T.J, T.e4);
             gauge_cost_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(T.nele, T.ng, T.Np, T.G, T.epsm, T.epsm_per_element, T.isig2, T.J, T.e4, T.g, T.H, T.cost);
             h->launches += 2;
-            CK(cudaStreamSynchronize(st)); dfree(h, dsL);
         }
         T.has = true;
     }
+    CK(cudaGetLastError());
+    if (!where) return MB_OK;                     // asynchronous: the caller checks later (mb_sync reports a NaN of the last evaluated step)
     CK(cudaMemcpyAsync(h->nanflag_host, h->nanflag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    if (where) { where->kind = 0; where->ieletyp = 0; where->iele = 0; where->step = 0; }
+    where->kind = 0; where->ieletyp = 0; where->iele = 0; where->step = 0;
     const unsigned long long f = *h->nanflag_host;
     if (f != ~0ULL) {
-        if (where) { where->kind = MB_ERR_NAN; where->ieletyp = (int32_t)((f >> 40) & 0x3F) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = istep; }
+        where->kind = MB_ERR_NAN; where->ieletyp = (int32_t)((f >> 40) & 0x3F) + 1; where->iele = (int64_t)(f & ((1ULL << 40) - 1)) + 1; where->step = istep;
         h->err = "residual(...) returned NaN in R, FB or derivatives";
         return MB_ERR_NAN;
     }
     return MB_OK;
+}
+/* CUDA-event timing of whole passes of assemblebig! over the DEVICE element types (mb_xua_zero, then mb_xua_eval_device + mb_xua_add_step for every step of every
+ * experiment, at the device-resident states and the measurements last set): ms per pass.  Host-evaluated types contribute nothing here. */
+int32_t mb_xua_time_device_pass(mb_handle* h, int32_t reps, float* ms) {
+    if (!h || !h->xua || reps < 1 || !ms) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(D->prepared, "call mb_xua_prepare first");
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int32_t rc = MB_OK;
+    for (int r = 0; r <= reps && !rc; ++r) {       // pass 0 warms up (buffers, workspace)
+        if (r == 1) CK(cudaEventRecord(e0, h->stream));
+        rc = mb_xua_zero(h);
+        for (int e = 1; e <= D->nexp && !rc; ++e)
+            for (int64_t s = 1; s <= D->nstep[(size_t)e - 1] && !rc; ++s) { rc = mb_xua_eval_device(h, e, s, nullptr); if (!rc) rc = mb_xua_add_step(h, e, s); }
+    }
+    if (!rc) { CK(cudaEventRecord(e1, h->stream)); CK(cudaEventSynchronize(e1)); float a; CK(cudaEventElapsedTime(&a, e0, e1)); *ms = a / reps; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
 }
 /* the packet of an element type as it stands (host-set or device-evaluated), and for a costed device type its requestables (εₐₓ,κ) [nele][4], their partials [nele][4][12], costs [nele] */
 int32_t mb_xua_get_packet(mb_handle* h, int32_t ieletyp, double* gradL, double* hessL) {
