@@ -178,6 +178,9 @@ int32_t mb_xua_add_step(mb_handle* h, int32_t iexp, int64_t istep);
 int32_t mb_xua_get_out(mb_handle* h, int32_t alpha, int32_t beta, int32_t ader, int32_t bder, double* out);
 int32_t mb_xua_out_shape(mb_handle* h, int32_t alpha, int32_t beta, int32_t* na, int32_t* nb);
 int32_t mb_xua_get_big(mb_handle* h, double* Lvv_nzval, double* Lv);
+/* time shards of the general form: each rank adds its own steps into its copy of Lvv / Lv, then this sums them over the ranks (ncclAllReduce, mb_comm_init first) —
+ * with them the sums over steps of L1[A], L2[A,A] (src/DirectXUA.jl:321-326,332-352) */
+int32_t mb_xua_allreduce_big(mb_handle* h);
 int32_t mb_xua_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
 int32_t mb_xua_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
 /* DEVICE element types in the general form, and the ElementCost accelerator (src/DirectXUA.jl:172-198) for strain gauges on beams.

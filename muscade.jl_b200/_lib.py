@@ -103,6 +103,7 @@ SYMBOLS = {
     "mb_xua_add_step": (C.c_int32, [H, C.c_int32, C.c_int64]),
     "mb_xua_get_out": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mb_xua_out_shape": (C.c_int32, [H, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mb_xua_allreduce_big": (C.c_int32, [H]),
     "mb_xua_get_big": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
     "mb_xua_sparser": (C.c_int32, [H, C.c_double, C.POINTER(C.c_int64)]),
     "mb_xua_get_sparse": (C.c_int32, [H, C.c_void_p, C.c_void_p, C.c_void_p]),

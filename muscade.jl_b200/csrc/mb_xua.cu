@@ -947,6 +947,16 @@ int32_t mb_xua_get_big(mb_handle* h, double* Lvv_nzval, double* Lv) {
     return MB_OK;
 }
 
+/* Time shards of the general form: every rank holds the whole structure and adds only ITS steps (mb_xua_add_step for its share of (iexp,istep); the A step on rank 0 only);
+ * this sums Lvv.nzval and Lv over the ranks in place — ncclAllReduce on the handle's stream (mb_comm_init first).  The sums over steps of L1[A], L2[A,A] and of the A rows /
+ * columns (src/DirectXUA.jl:321-326,332-352) come with it.  The element work and the packet traffic divide by the number of ranks; Lvv itself is replicated. */
+int32_t mb_xua_allreduce_big(mb_handle* h) {
+    XUA_READY();
+    int32_t rc = mb_comm_allreduce_dev(h, D->nzval, D->nnzbig, 0);
+    if (!rc) rc = mb_comm_allreduce_dev(h, D->Lv, D->ngr, 0);
+    return rc;
+}
+
 int32_t mb_xua_sparser(mb_handle* h, double rtol, int64_t* nnz_out) {
     XUA_READY();
     const int64_t nnz = D->nnzbig;

@@ -255,6 +255,20 @@ class XUAEngine(Engine):
             for istep in range(self.nstep[iexp]):
                 self.assemble_step(iexp + 1, istep + 1, states[iexp][istep], SP)
 
+    def assemblebig_sharded(self, states, rank, world, SP=None):
+        """time shards: rank r of `world` evaluates and adds the steps (flattened over the experiments) s with s mod world == r — and the A step on rank 0 — then the
+        copies of Lvv / Lv are summed over the ranks (mb_xua_allreduce_big; comm_init first).  Every rank ends with the whole system."""
+        self.zero()
+        if self.IA == 1 and rank == 0:
+            self.assembleA(states[0][0], SP)
+        k = 0
+        for iexp in range(self.nexp):
+            for istep in range(self.nstep[iexp]):
+                if k % world == rank:
+                    self.assemble_step(iexp + 1, istep + 1, states[iexp][istep], SP)
+                k += 1
+        check(self.h, self.L.mb_xua_allreduce_big(self.h))
+
     def big(self):
         nz = np.zeros(self.nnzbig); Lv = np.zeros(self.nbig)
         check(self.h, self.L.mb_xua_get_big(self.h, ptr(nz), ptr(Lv)))
