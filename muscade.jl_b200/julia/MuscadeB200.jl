@@ -433,26 +433,55 @@ mutable struct AssemblyXUAB200{OX,OU,IA} <: Assembly
     Δt     :: Vector{𝕣}
     nbig   :: Int64
     nnzbig :: Int64
+    devtyp :: Dict{Int,Any}
 end
+"""
+    QuadraticGaugeCost(σ,εₘ)  — the strain cost the device evaluates:  cost(eleres,t) = Δε⋅Δε/(2σ²), Δε = eleres.ε − εₘ(t)  (test/TestBeamElementStrainGauge.jl:90-97)
+"""
+struct QuadraticGaugeCost{F} <: Muscade.Functor{:QuadraticGaugeCost} ; σ::𝕣 ; εₘ::F end
+(c::QuadraticGaugeCost)(eleres, t) = (Δε = eleres.ε - c.εₘ(t); (Δε ⋅ Δε) / (2c.σ^2))
+"which element types the device kernels evaluate inside the general form, and how to reach the wrapped beam"
+devicebeam(::Type) = nothing
+devicebeam(::Type{<:Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection}}) = (unwrap = identity, gauge = nothing)
+devicebeam(::Type{<:Muscade.ElementCost{<:Muscade.Toolbox.StrainGaugeOnEulerBeam3D{N,<:Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection}},R,<:QuadraticGaugeCost}}) where {N,R} =
+    (unwrap = o -> o.eleobj.eleobj, gauge = o -> (E = o.eleobj.E, K1 = o.eleobj.K1, K2 = o.eleobj.K2, K3 = o.eleobj.K3, σ = o.cost.σ, εₘ = o.cost.εₘ))
 function Muscade.prepare(::Type{AssemblyXUAB200{OX,OU,IA}}, model, dis; nstep::Vector{Int64}, Δt::Vector{𝕣}, device=0,
                          Xwhite=false, XUindep=false, UAindep=false, XAindep=false) where {OX,OU,IA}
     href = Ref{Ptr{Cvoid}}()
     check(C_NULL, ccall((:mb_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, href))
     h = href[]
+    devtyp = Dict{Int,Any}()                       # element types the DEVICE evaluates: ieletyp → nothing | (cost = the QuadraticGaugeCost functor's data)
     for ieletyp = 1:getneletyp(model)
         eleobj, d = model.eleobj[ieletyp], dis.dis[ieletyp]
         idx(f, n) = Int64[getfield(d.index[iele], f)[i] for i = 1:n, iele = 1:length(eleobj)]
         nx, nu, na = length(d.scale.X), length(d.scale.U), length(d.scale.A)
         iX, iU, iA = idx(:X, nx), idx(:U, nu), idx(:A, na)
+        E    = eltype(eleobj)
+        beam = devicebeam(E)                       # EulerBeam3D{BeamCrossSection}, or ElementCost{StrainGaugeOnEulerBeam3D{…,EulerBeam3D}} with a quadratic strain cost
+        if !isnothing(beam)
+            beams = beam.unwrap.(eleobj)           # the wrapped Vector{EulerBeam3D}: same memory image as mb_add_eulerbeam3d reads
+            idev, ityp = Ref{Int32}(), Ref{Int32}()
+            GC.@preserve beams iX iU check(h, ccall((:mb_add_eulerbeam3d, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+                h, length(beams), pointer(reinterpret(Float64, beams)), nu > 0, iX, nu > 0 ? pointer(iU) : C_NULL, collect(d.scale.X), nu > 0 ? collect(d.scale.U) : C_NULL, idev))
+            check(h, ccall((:mb_xua_add_device_eletyp, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int32}), h, idev[], ityp))
+            if !isnothing(beam.gauge)              # G = [E K1 K2 K3] of the gauges (toolbox/StrainGaugeOnBeamElement.jl:62-65), σ of the cost
+                g = beam.gauge(eleobj[1])
+                G = permutedims(hcat(g.E, g.K1, g.K2, g.K3))            # 4 × Ngauge column-major = [Ngauge][4] row-major
+                check(h, ccall((:mb_xua_set_gauge_cost, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{𝕣}, 𝕣, 𝕣), h, ityp[], length(g.E), G, g.σ, model.scaleΛ))
+            end
+            devtyp[ieletyp] = beam
+            continue
+        end
         check(h, ccall((:mb_xua_add_eletyp, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int32, Ref{Int32}),
-                       h, length(eleobj), nx, nu, na, iX, iU, iA, eltype(eleobj) <: Muscade.Acost, Ref{Int32}()))
+                       h, length(eleobj), nx, nu, na, iX, iU, iA, E <: Muscade.Acost, Ref{Int32}()))
     end
     flags = Int32(Xwhite) | Int32(XUindep) << 1 | Int32(UAindep) << 2 | Int32(XAindep) << 3
     nbig, nnz = Ref{Int64}(), Ref{Int64}()
     check(h, ccall((:mb_xua_prepare, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Int64, Int64, Int64, Int32, Ptr{Int64}, Ptr{𝕣}, Int32, Ref{Int64}, Ref{Int64}),
                    h, OX, OU, IA, getndof(model, :X), getndof(model, :U), getndof(model, :A), length(nstep), nstep, Δt, flags, nbig, nnz))
     check(h, ccall((:mb_xua_set_dof_scale, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), h, dis.scaleΛ, dis.scaleX, dis.scaleU, dis.scaleA))
-    out = AssemblyXUAB200{OX,OU,IA}(h, nstep, Δt, nbig[], nnz[])
+    out = AssemblyXUAB200{OX,OU,IA}(h, nstep, Δt, nbig[], nnz[], devtyp)
     finalizer(o -> ccall((:mb_destroy, LIB), Int32, (Ptr{Cvoid},), o.h), out)
     return out
 end
@@ -503,7 +532,19 @@ function assemblebig!(out::AssemblyXUAB200{OX,OU,IA}, model, dis, state, SP, dbg
         check(h, ccall((:mb_xua_add_A, LIB), Int32, (Ptr{Cvoid},), h))
     end
     for iexp = 1:length(out.nstep), istep = 1:out.nstep[iexp]
+        if !isempty(out.devtyp)                 # device element types: measurements of the step, then R, ∂R/∂X, ∂R/∂U (and the strain-gauge terms) → packets, all on the device
+            for (ityp, beam) ∈ out.devtyp
+                isnothing(beam.gauge) && continue
+                εₘ = collect(𝕣, beam.gauge(model.eleobj[ityp][1]).εₘ(state[iexp][istep].time))
+                check(h, ccall((:mb_xua_set_gauge_measurements, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{𝕣}, Int32), h, ityp, εₘ, 0))
+            end
+            where = Ref(ErrInfo(0, 0, 0, 0))
+            rc = ccall((:mb_xua_eval_device, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Ref{ErrInfo}), h, iexp, istep, where)   # reads the device-resident state (upload_states!)
+            rc == 3 && muscadeerror((dbg..., ieletyp=where[].ieletyp, iele=where[].iele, step=istep), "residual(...) returned NaN in R, FB or derivatives")
+            check(h, rc)
+        end
         for ityp = 1:getneletyp(model)          # Acost vectors too: `assemble_!(…,eleobj::Acost,…) = nothing` (src/Assemble.jl:477) does not match them
+            haskey(out.devtyp, ityp) && continue
             setp(ityp, packet(model.eleobj[ityp], dis.dis[ityp], state[iexp][istep], OX, OU, IA, SP, (dbg..., step=istep))...)
         end
         check(h, ccall((:mb_xua_add_step, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), h, iexp, istep))
