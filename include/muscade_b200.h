@@ -184,8 +184,9 @@ int32_t mb_xua_allreduce_big(mb_handle* h);
 int32_t mb_xua_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
 int32_t mb_xua_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
 /* DEVICE element types in the general form, and the ElementCost accelerator (src/DirectXUA.jl:172-198) for strain gauges on beams.
- *   mb_xua_add_device_eletyp : an EulerBeam3D type of this handle (mb_add_eulerbeam3d; 1-based number among the handle's device types) becomes the next element type; its
- *                              packets come from the first-order device kernels (R, ∂R/∂X_der, ∂R/∂U: no_second_order = Val(true), toolbox/BeamElement.jl:106) — no host work.
+ *   mb_xua_add_device_eletyp : an EulerBeam3D, Bar3D or SoilContact type of this handle (mb_add_*; 1-based number among the handle's device types) becomes the next element type;
+ *                              its packets come from the device kernels of the beam-specialised path (R, ∂R/∂X_der, ∂R/∂U: no_second_order = Val(true) for beams and bars,
+ *                              toolbox/BeamElement.jl:106, BarElement.jl:104; SoilContact on the second-order branch in closed form) — no host work.
  *   mb_xua_set_gauge_cost    : wraps the type in ElementCost{StrainGaugeOnEulerBeam3D} (toolbox/StrainGaugeOnBeamElement.jl) with the cost Σ_g (ε_g − εm_g)²/(2σ²),
  *                              ε_g = E_g·εₐₓ + K1_g·κ₁ + K2_g·κ₂ + K3_g·κ₃ (:62-65,73): G [ngauge][4] = (E,K1,K2,K3).  As the accelerator is meant (its code hands
  *                              DirectXUA_lagrangian_addition! a Lagrangian without Λ-partials, so the reference has no behaviour to copy there): L = Λ∘₁R + cost with first-order R
@@ -194,6 +195,9 @@ int32_t mb_xua_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double
  *   mb_xua_eval_device       : packets of all device types at the device-resident state[iexp][istep]; NaN → MB_ERR_NAN with the element (where = NULL: asynchronous, no check).
  *   mb_xua_get_packet / mb_xua_get_gauge : the packet as it stands; (εₐₓ,κ) [nele][4], ∂(εₐₓ,κ)/∂X₀ [nele][4][12] (scaled), cost [nele] of a costed type. */
 int32_t mb_xua_add_device_eletyp(mb_handle* h, int32_t ieletyp_dev, int32_t* ieletyp_out);
+/* model.scaleΛ for the device types on the second-order branch (SoilContact, costed beams); state[iexp][istep].time = t0 + (istep−1)·Δt[iexp] for Bar3D's weight ramp */
+int32_t mb_xua_set_lambda_scale(mb_handle* h, double lambda_scale);
+int32_t mb_xua_set_time0(mb_handle* h, int32_t iexp, double t0);
 int32_t mb_xua_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma, double lambda_scale);
 int32_t mb_xua_set_gauge_measurements(mb_handle* h, int32_t ieletyp, const double* epsm, int32_t per_element);
 int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo* where);

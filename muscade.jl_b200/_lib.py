@@ -91,6 +91,8 @@ SYMBOLS = {
     "mb_xua_big_pattern": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
     "mb_xua_big_asm": (C.c_int32, [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_xua_add_device_eletyp": (C.c_int32, [H, C.c_int32, C.POINTER(C.c_int32)]),
+    "mb_xua_set_lambda_scale": (C.c_int32, [H, C.c_double]),
+    "mb_xua_set_time0": (C.c_int32, [H, C.c_int32, C.c_double]),
     "mb_xua_set_gauge_cost": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double]),
     "mb_xua_set_gauge_measurements": (C.c_int32, [H, C.c_int32, C.c_void_p, C.c_int32]),
     "mb_xua_eval_device": (C.c_int32, [H, C.c_int32, C.c_int64, C.POINTER(ErrInfo)]),

@@ -25,6 +25,10 @@
 namespace mb {
 template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
                                          unsigned long long nanbase, double* Wc, cudaStream_t s, const StepBatch& sb, int nb);
+int launch_bar_direct(int ND, const BarGroupDev& g, const DirectStateDev& st, double t, double* dR, double* R, unsigned long long* nanflag,
+                      unsigned long long nanbase, cudaStream_t s, const StepBatch& sb, int nb);
+int launch_soil_direct(int ND, const SoilGroupDev& g, const DirectStateDev& st, const double* Lam, double lamscale, double* dR, double* R, double* GX,
+                       unsigned long long* nanflag, unsigned long long nanbase, cudaStream_t s, const StepBatch& sb, int nb);
 }
 
 namespace {
@@ -38,7 +42,7 @@ struct XuaType {
     int Np = 0; int base[4] = {0, 0, 0, 0};     // first partial of class α in the packet; derivative d of α starts at base[α] + d·n[cgroup(α)]
     double *g = nullptr, *H = nullptr; bool has = false;
     // device-evaluated type (EulerBeam3D of the handle, mb_xua_add_device_eletyp): outputs of the first-order kernels, and the ElementCost accelerator's strain-gauge cost
-    int devgroup = -1; double *dR = nullptr, *Rb = nullptr;
+    int devgroup = -1, devkind = 0; double *dR = nullptr, *Rb = nullptr, *GXb = nullptr;
     int ng = 0; double isig2 = 0.; double *G = nullptr, *epsm = nullptr, *J = nullptr, *e4 = nullptr, *cost = nullptr, *sL = nullptr; bool epsm_per_element = false;
 };
 struct TabDev {                                  // per element type, for one (α,β) or α: by value into the gather kernels
@@ -217,37 +221,41 @@ __global__ void __launch_bounds__(256) xua_sumsq_kernel(int64_t nX, int64_t nU, 
 // (R, dR) of the first-order kernels (beam_kernel.cuh K3: dR[e][p][i] = ∂R_i/∂seed_p, p over X₀ X₁ X₂ U₀, seeds scaled; R unscaled) → packet of a no_second_order type
 // (src/DirectXUA.jl:85-120): ∇L[Λ] = R, the Λ rows / columns of ∇²L = ∂R/∂β.  COSTED (an ElementCost wraps the type, :172-198 as intended: L = Λ∘₁R + cost with first-order R):
 // ∇L[Λ] = R·scale.Λ, ∇L[X_der] = Σᵢ Λᵢ·∂Rᵢ/∂X_der (likewise U), Λ rows / columns scaled by scale.Λ; the cost's own terms are added by gauge_cost_kernel.
-__global__ void __launch_bounds__(128) beam_packet_kernel(int64_t nele, int npd, int Np, int nxd /* 12·(OX+1) */, int nu0 /* packet column of U₀ or −1 */, const double* __restrict__ R,
-                                   const double* __restrict__ dR, const int32_t* __restrict__ idxX, const double* __restrict__ Lam, const double* sLam12, bool costed,
-                                   double* __restrict__ g, double* __restrict__ H) {
-    // one CTA per element: its ∂R/∂seed (npd × 12, contiguous) goes through shared memory so that BOTH copies — the Λ rows H[i][col] and the Λ columns H[col][i] — leave as
+// mode 0: no_second_order type (EulerBeam3D, Bar3D); 1: COSTED beam; 2: SoilContact — the second-order branch in closed form (bar_kernel.cuh: R already ·scale.Λ, ∂R/∂X already
+// ·scale.Λ·scale.X, GX[(e·nx+i)·nd+d] = ∂L/∂X_d,i): ∇L[Λ] = R, ∇L[X_d] = GX, Λ rows / columns = ∂R/∂X_d.
+__global__ void __launch_bounds__(128) elem_packet_kernel(int64_t nele, int nx, int nd, int npd, int Np, int nu0 /* packet column of U₀ or −1 */, const double* __restrict__ R,
+                                   const double* __restrict__ dR, const double* __restrict__ GX, const int32_t* __restrict__ idxX, const double* __restrict__ Lam,
+                                   const double* sLam, int mode, double* __restrict__ g, double* __restrict__ H) {
+    // one CTA per element: its ∂R/∂seed (npd × nx, contiguous) goes through shared memory so that BOTH copies — the Λ rows H[i][col] and the Λ columns H[col][i] — leave as
     // contiguous runs (written straight from the [p][i] layout one of the two is a stride-Np scatter of 8-byte stores)
     __shared__ double sm[39 * 12];
     __shared__ double lam[12], sl[12];
     const int64_t e = blockIdx.x;
-    const int n = npd * 12;
+    const int n = npd * nx, nxd = nx * nd;
+    const bool costed = mode == 1;
     for (int q = threadIdx.x; q < n; q += blockDim.x) sm[q] = dR[e * n + q];
-    if (threadIdx.x < 12) { lam[threadIdx.x] = costed ? Lam[idxX[e * 12 + threadIdx.x]] : 0.; sl[threadIdx.x] = costed ? sLam12[threadIdx.x] : 1.; }
+    if ((int)threadIdx.x < nx) { lam[threadIdx.x] = costed ? Lam[idxX[e * nx + threadIdx.x]] : 0.; sl[threadIdx.x] = costed ? sLam[threadIdx.x] : 1.; }
     __syncthreads();
     double* He = H + e * (int64_t)Np * Np; double* ge = g + e * (int64_t)Np;
     for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ columns: H[col][i], i fastest
-        const int p = q / 12, i = q - p * 12;
-        const int col = (p < nxd) ? 12 + p : nu0 + (p - nxd);
+        const int p = q / nx, i = q - p * nx;
+        const int col = (p < nxd) ? nx + p : nu0 + (p - nxd);
         He[col * Np + i] = sm[q] * sl[i];
     }
     for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ rows: H[i][col], col fastest
         const int i = q / npd, p = q - i * npd;
-        const int col = (p < nxd) ? 12 + p : nu0 + (p - nxd);
-        He[i * Np + col] = sm[p * 12 + i] * sl[i];
+        const int col = (p < nxd) ? nx + p : nu0 + (p - nxd);
+        He[i * Np + col] = sm[p * nx + i] * sl[i];
     }
-    if (threadIdx.x < npd) {
+    if ((int)threadIdx.x < npd) {
         const int p = threadIdx.x;
         if (costed) {
             double acc = 0.;
-            for (int i = 0; i < 12; ++i) acc += lam[i] * sm[p * 12 + i];
-            ge[(p < nxd) ? 12 + p : nu0 + (p - nxd)] = acc;
+            for (int i = 0; i < nx; ++i) acc += lam[i] * sm[p * nx + i];
+            ge[(p < nxd) ? nx + p : nu0 + (p - nxd)] = acc;
         }
-        if (p < 12) ge[p] = R[e * 12 + p] * sl[p];
+        if (mode == 2 && p < nxd) { const int d = p / nx, i = p - d * nx; ge[nx + p] = GX[(e * nx + i) * nd + d]; }
+        if (p < nx) ge[p] = R[e * nx + p] * sl[p];
     }
 }
 // requestables (εₐₓ, ♢κ) of EulerBeam3D (toolbox/BeamElement.jl:151-174) with their partials ∂/∂X₀ (scaled): one lane per (element, element dof), one-direction duals
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const d
 }
 // ElementCost accelerator for StrainGaugeOnEulerBeam3D (toolbox/StrainGaugeOnBeamElement.jl:70-76) under the quadratic cost Σ_g (ε_g − εm_g)²/(2σ²):
 // ε_g = G[g]·(εₐₓ,κ); ∇cost = Jᵀ·Gᵀ·r/σ², ∇²cost = Jᵀ·GᵀG·J/σ² (chainrule of the second-order cost with the first-order eleres: to_order{2} adds no curvature, :190-196).
-// One thread per (element, i): entry i of the X₀ gradient is ADDED to the packet (beam_packet_kernel put Λᵀ∂R/∂X₀ there), row i of the X₀-X₀ block is written.
+// One thread per (element, i): entry i of the X₀ gradient is ADDED to the packet (elem_packet_kernel put Λᵀ∂R/∂X₀ there), row i of the X₀-X₀ block is written.
 __global__ void gauge_cost_kernel(int64_t nele, int ng, int Np, const double* __restrict__ G, const double* __restrict__ epsm, bool per_element, double isig2,
                                   const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ g, double* __restrict__ H, double* __restrict__ cost) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -314,17 +322,18 @@ struct XuaData {
     Combo2* cb2 = nullptr; Combo1* cb1 = nullptr;
     std::vector<int64_t> c2start, c1start;            // [(gs+1)·16 + 4α + β] → first combo (gs = −1: the A step), sentinel at the end; c1start: [(gs+1)·4 + β]
     int64_t *ccolptr = nullptr, *crowval = nullptr; double* cnzval = nullptr; int64_t cnnz = -1;
-    double lamscale = 1.;
+    double lamscale = 1.; std::vector<double> t0;
     double *Lam = nullptr, *X = nullptr, *U = nullptr, *A = nullptr, *sc[4] = {nullptr, nullptr, nullptr, nullptr}, *dvbuf = nullptr;
 };
 
 void mb_xua_release(mb_handle* h) { delete h->xua; h->xua = nullptr; }
 
-// which derivative blocks of a type's packet can be non-zero: everything for host-set packets (unknown); for a device beam type what beam_packet_kernel / gauge_cost_kernel fill —
+// which derivative blocks of a type's packet can be non-zero: everything for host-set packets (unknown); for a device beam type what elem_packet_kernel / gauge_cost_kernel fill —
 // ∇L[Λ], the Λ rows / columns against X_d and U₀, and for a costed type ∇L[X_d], ∇L[U₀] and the X₀-X₀ block
 static inline bool xua_live1(const XuaType& T, int a, int i) {
     if (T.devgroup < 0) return true;
     if (a == 0) return true;
+    if (T.devkind == G_SOIL) return a == 1;                 // ∇L[X_d] = GX
     if (T.ng == 0) return false;
     return a == 1 || (a == 2 && i == 0);
 }
@@ -747,16 +756,33 @@ static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_
  * form.  Its packets are produced on the device by mb_xua_eval_device — no host evaluation, no transfer. */
 int32_t mb_xua_add_device_eletyp(mb_handle* h, int32_t ieletyp_dev, int32_t* ieletyp_out) {
     if (!h) return MB_ERR_ARG;
-    ARG(ieletyp_dev >= 1 && ieletyp_dev <= (int)h->groups.size() && h->groups[(size_t)ieletyp_dev - 1].kind == G_BEAM, "not an EulerBeam3D type of this handle");
+    ARG(ieletyp_dev >= 1 && ieletyp_dev <= (int)h->groups.size(), "no such device element type on this handle");
+    const Group& g = h->groups[(size_t)ieletyp_dev - 1];
+    ARG(g.kind == G_BEAM || g.kind == G_BAR || g.kind == G_SOIL, "not an EulerBeam3D, Bar3D or SoilContact type of this handle");
     CK(cudaSetDevice(h->device));
     if (!h->xua) h->xua = new XuaData();
     XuaData* D = h->xua;
     ARG(!D->prepared, "element types must be added before mb_xua_prepare");
     ARG((int)D->types.size() < XMAXT, "too many element types");
-    const Group& g = h->groups[(size_t)ieletyp_dev - 1];
-    XuaType T; T.nele = g.nele; T.n[0] = 12; T.n[1] = g.udof ? 3 : 0; T.n[2] = 0; T.idx[0] = g.idxX; T.idx[1] = g.udof ? g.idxU : nullptr; T.devgroup = ieletyp_dev - 1;
+    XuaType T; T.nele = g.nele; T.n[0] = g.nx; T.n[1] = g.udof ? 3 : 0; T.n[2] = 0; T.idx[0] = g.idxX; T.idx[1] = g.udof ? g.idxU : nullptr;
+    T.devgroup = ieletyp_dev - 1; T.devkind = g.kind;
     D->types.push_back(T);
     if (ieletyp_out) *ieletyp_out = (int32_t)D->types.size();
+    return MB_OK;
+}
+/* model.scaleΛ (setscale!(model;Λscale)): scale.Λ = scale.X·Λscale (src/Assemble.jl:55), read by the device types on the second-order branch (SoilContact, costed beams). Default 1. */
+int32_t mb_xua_set_lambda_scale(mb_handle* h, double lambda_scale) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    h->xua->lamscale = lambda_scale;
+    return MB_OK;
+}
+/* state[iexp][istep].time = t0 + (istep−1)·Δt[iexp] for the device types that read the time (Bar3D's weight ramp, toolbox/BarElement.jl:144); default t0 = 0 */
+int32_t mb_xua_set_time0(mb_handle* h, int32_t iexp, double t0) {
+    if (!h || !h->xua) return MB_ERR_ARG;
+    XuaData* D = h->xua;
+    ARG(D->prepared && iexp >= 1 && iexp <= D->nexp, "no such experiment");
+    if (D->t0.size() < (size_t)D->nexp) D->t0.assign((size_t)D->nexp, 0.);
+    D->t0[(size_t)iexp - 1] = t0;
     return MB_OK;
 }
 /* ElementCost{StrainGaugeOnEulerBeam3D} on a device type: G [ngauge][4] = (E, K1, K2, K3) of every gauge (toolbox/StrainGaugeOnBeamElement.jl:62-65), cost
@@ -764,7 +790,7 @@ int32_t mb_xua_add_device_eletyp(mb_handle* h, int32_t ieletyp_dev, int32_t* iel
 int32_t mb_xua_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma, double lambda_scale) {
     if (!h || !h->xua) return MB_ERR_ARG;
     XuaData* D = h->xua;
-    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].devgroup >= 0, "not a device element type");
+    ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].devgroup >= 0 && D->types[(size_t)ieletyp - 1].devkind == G_BEAM, "not a device EulerBeam3D type");
     ARG(ngauge >= 1 && ngauge <= 64 && G && sigma > 0., "bad gauge data");
     CK(cudaSetDevice(h->device));
     XuaType& T = D->types[(size_t)ieletyp - 1];
@@ -804,26 +830,45 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
         XuaType& T = D->types[it];
         if (T.devgroup < 0 || T.nele == 0) continue;
         const Group& g = h->groups[(size_t)T.devgroup];
-        BeamGroupDev gd;
-        gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
-        for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
-        for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
-        const int npd = 12 * nd + (g.udof ? 3 : 0);
+        const int nx = g.nx;
+        const int npd = nx * nd + (g.udof ? 3 : 0);
         const int64_t ng = T.nele * T.Np, nh = ng * T.Np;
         // the kernels below write every entry of the packet blocks a device type can fill (xua_live1 / xua_live2) and nothing else: the rest is zeroed once, here
         if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(dalloc(h, &T.H, nh)); CK(cudaMemsetAsync(T.g, 0, (size_t)ng * 8, st)); CK(cudaMemsetAsync(T.H, 0, (size_t)nh * 8, st)); }
-        if (!T.dR) { CK(dalloc(h, &T.dR, T.nele * 12 * npd)); CK(dalloc(h, &T.Rb, T.nele * 12)); }
+        if (!T.dR) { CK(dalloc(h, &T.dR, T.nele * nx * npd)); CK(dalloc(h, &T.Rb, T.nele * nx)); if (g.kind == G_SOIL) CK(dalloc(h, &T.GXb, T.nele * nx * nd)); }
         DirectStateDev sd;
         for (int d = 0; d < 3; ++d) sd.X[d] = D->X + (gs * 3 + d) * nX;
         sd.U0 = nU ? D->U + gs * 3 * nU : nullptr;
         StepBatch sb;
+        const unsigned long long nanbase = ((unsigned long long)it) << 40;
+        const double tnow = (D->t0.size() >= (size_t)iexp ? D->t0[(size_t)iexp - 1] : 0.) + (double)(istep - 1) * D->dt[(size_t)iexp - 1];
+        if (g.kind == G_BAR) {
+            BarGroupDev gd; gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.barmats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+            for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
+            for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
+            h->launches += launch_bar_direct(nd, gd, sd, tnow, T.dR, T.Rb, h->nanflag, nanbase, st, sb, 1);
+            elem_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, nx, nd, npd, T.Np, g.udof ? nx + nx * nd : -1, T.Rb, T.dR, nullptr, g.idxX, nullptr, nullptr, 0, T.g, T.H);
+            h->launches++; T.has = true;
+            continue;
+        }
+        if (g.kind == G_SOIL) {
+            SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
+            for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
+            h->launches += launch_soil_direct(nd, gd, sd, D->Lam + gs * nX, D->lamscale, T.dR, T.Rb, T.GXb, h->nanflag, nanbase, st, sb, 1);
+            elem_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, nx, nd, npd, T.Np, -1, T.Rb, T.dR, T.GXb, g.idxX, nullptr, nullptr, 2, T.g, T.H);
+            h->launches++; T.has = true;
+            continue;
+        }
+        BeamGroupDev gd;
+        gd.nele = g.nele; gd.geo = g.geo; gd.mats = g.mats; gd.mat_id = g.mat_id; gd.idxX = g.idxX; gd.idxU = g.idxU; gd.udof = g.udof;
+        for (int i = 0; i < 12; ++i) gd.scaleX[i] = g.scaleX[i];
+        for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
         double* Wc = nullptr;
         if (nd >= 2) {
             const int64_t need = ((g.nele * 6 * nd + 31) / 32) * 32 * MB_NCOT;
             if (h->Wc_len < need) { if (h->Wc) dfree(h, h->Wc); h->Wc = nullptr; h->Wc_len = 0; CK(dalloc(h, &h->Wc, need)); h->Wc_len = need; }
             Wc = h->Wc; sb.sWc = need;
         }
-        const unsigned long long nanbase = ((unsigned long long)it) << 40;
         if (nd == 1) h->launches += launch_beam_direct<1>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
         else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
         else h->launches += launch_beam_direct<3>(gd, sd, T.dR, T.Rb, h->nanflag, nanbase, Wc, st, sb, 1);
@@ -832,7 +877,7 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
             double sL[12]; for (int i = 0; i < 12; ++i) sL[i] = g.scaleX[i] * D->lamscale;
             CK(dalloc(h, &T.sL, 12)); CK(cudaMemcpy(T.sL, sL, sizeof(sL), cudaMemcpyHostToDevice));
         }
-        beam_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, npd, T.Np, 12 * nd, g.udof ? 12 + 12 * nd : -1, T.Rb, T.dR, g.idxX, D->Lam + gs * nX, T.sL, costed, T.g, T.H);
+        elem_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, 12, nd, npd, T.Np, g.udof ? 12 + 12 * nd : -1, T.Rb, T.dR, nullptr, g.idxX, D->Lam + gs * nX, T.sL, costed ? 1 : 0, T.g, T.H);
         h->launches++;
         if (costed) {
             ARG(T.epsm, "strain-gauge measurements of this step are not set (mb_xua_set_gauge_measurements)");

@@ -54,6 +54,26 @@ def packets(et, ed, OX, OU, IA, Λ, X, U, A, t, SP=None, assembleA=False):
         Ue = [U[d][ed.U[a:b] - 1] if nu else np.zeros((n, 0)) for d in range(OU + 1)]
         Le = Λ[ed.X[a:b] - 1] if nx else np.zeros((n, 0))
         Np = nx + nx * (OX + 1) + nu * (OU + 1) + na * IA
+        if getattr(T, "kind", None) == "host":
+            # X-class toolbox types with closed-form partials (Hold, DofLoad, DofConstraint: `residual(extra,X,t)` → R, ∂R/∂X₀, ∂R/∂X′, ∂R/∂X″ and `hessian` → Σ Λₖ∂²Rₖ/∂X²):
+            # the second-order branch L = Λ∘R written out (src/DirectXUA.jl:152-171) — ∇L[Λ] = R·sΛ, ∇L[X_d] = (∂R/∂X_d)ᵀΛ·sX, ∇²L[Λ,X_d] = ∂R/∂X_d·sΛ·sX, ∇²L[X₀,X₀] = hessian·sX·sX
+            Xs = [x for x in Xe]
+            R, K0, K1, K2 = T.residual(ex, Xs, t)
+            Hx = T.hessian(ex, Xs, Le, t) if hasattr(T, "hessian") else None
+            g = np.zeros((n, Np)); H = np.zeros((n, Np, Np))
+            sL, sX = ed.scaleΛ, ed.scaleX
+            g[:, :nx] = R * sL[None, :]
+            for d, K in enumerate([K0, K1, K2][:OX + 1]):
+                if K is None:
+                    continue
+                c0 = nx + nx * d
+                g[:, c0:c0 + nx] = np.einsum("ek,eki->ei", Le, K) * sX[None, :]
+                blk = K * sL[None, :, None] * sX[None, None, :]
+                H[:, :nx, c0:c0 + nx] = blk; H[:, c0:c0 + nx, :nx] = blk.transpose(0, 2, 1)
+            if Hx is not None:
+                H[:, nx:2 * nx, nx:2 * nx] = Hx * sX[None, :, None] * sX[None, None, :]
+            parts_g.append(g); parts_H.append(H)
+            continue
         if getattr(T, "no_second_order", False) and not hasattr(T, "lagrangian"):
             # :85-120 — revariate{1}((;X,U,A),scale); Lλ += R, Lλβ += ∂R/∂β, Lβλ += its transpose; nothing else
             vals = np.concatenate(Xe + Ue + ([Ae] if IA else []), axis=1)
@@ -116,6 +136,13 @@ class XUAEngine(Engine):
         for ityp, (et, ed) in enumerate(zip(model.ele, dis.dis), 1):
             T = et.ElType
             target = et.extra.get("target") if (T.kind == "elementcost" and isinstance(et.extra, dict)) else None
+            if T.kind in ("bar3d", "soilcontact"):
+                udof = ed.U.shape[1] > 0
+                idev = self.add_soilcontact(et.eleobj, ed.X, ed.scaleX) if T.kind == "soilcontact" else \
+                    self.add_bar3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+                check(self.h, self.L.mb_xua_add_device_eletyp(self.h, idev, C.byref(it)))
+                self.devtypes[ityp] = None
+                continue
             if T.kind == "eulerbeam3d" or (target is not None and target.kind == "eulerbeam3d"):
                 udof = ed.U.shape[1] > 0
                 idev = self.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
@@ -129,7 +156,7 @@ class XUAEngine(Engine):
                     check(self.h, self.L.mb_xua_set_gauge_cost(self.h, it.value, G.shape[0], ptr(G), cost.sigma, float(model.scaleΛ)))
                 self.devtypes[ityp] = cost
                 continue
-            if "lagrangian" not in (getattr(T, "kind", None), getattr(T, "kind_general", None)):
+            if "lagrangian" not in (getattr(T, "kind", None), getattr(T, "kind_general", None)) and T.kind != "host":
                 muscadeerror("the general DirectXUA path takes EulerBeam3D (device), ElementCost on strain-gauged beams (device) and host-evaluated element types "
                              "written against adiff2.D2 (kind = 'lagrangian'): %s" % (et.key,))
             iX, iU, iA = _i64(ed.X), _i64(ed.U), _i64(ed.A)
@@ -142,7 +169,12 @@ class XUAEngine(Engine):
         self.nbig, self.nnzbig = nbig.value, nnz.value
         self.ndofc = {1: self.nX, 2: self.nX, 3: self.nU, 4: self.nA}
         check(self.h, self.L.mb_xua_set_dof_scale(self.h, ptr(_f64(dis.scaleΛ)), ptr(_f64(dis.scaleX)), ptr(_f64(dis.scaleU)), ptr(_f64(dis.scaleA))))
+        check(self.h, self.L.mb_xua_set_lambda_scale(self.h, float(model.scaleΛ)))
         return self.nbig, self.nnzbig
+
+    def set_time0(self, iexp, t0):
+        """state[iexp][istep].time = t0 + (istep−1)·Δt[iexp] for the device types that read the time (Bar3D's weight ramp)"""
+        check(self.h, self.L.mb_xua_set_time0(self.h, int(iexp), float(t0)))
 
     # ---- structures (checked against the reference's goldens)
     def class_pattern(self, α, β):

@@ -288,6 +288,20 @@ def test_directxua_beam_bar_soil(mb, OX):
     z = np.array([st[s][0][0][dis.dis[2].X[:, 2] - 1] for s in range(nstep)])
     assert (z < 0).any() and (z >= 0).any()          # both SoilContact branches
     eng.close()
+    # the same three device types inside the GENERAL form (mb_xua_add_device_eletyp / mb_xua_eval_device)
+    from muscade_b200 import xua
+    g = xua.XUAEngine(0)
+    try:
+        g.prepare(model, dis, OX, OU, 0, [nstep], [dt])
+        g.set_time0(1, t0)
+        cp, rv = g.big_pattern()
+        assert np.array_equal(cp, big["colptr"]) and np.array_equal(rv, big["rowval"])
+        sts = [[mb.State(t0 + s * dt, [Lam[s]], st[s][0][: OX + 1], [st[s][1]], st0.A, None, model, dis) for s in range(nstep)]]
+        g.assemblebig(sts)
+        gLvv, gLv = g.big()
+        assert rel(gLvv, nz) <= TOL and rel(gLv, Lv, np.abs(nz).max()) <= TOL
+    finally:
+        g.close()
 
 
 def test_directxua_sparser_and_decrementbig(mb):

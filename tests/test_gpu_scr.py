@@ -238,3 +238,41 @@ def test_scr_oracle_loop_converges_on_cpu():
     ref = ora.solve(0, [np.zeros(ora.ndof)], STATIC_TIMES[:6], -np.inf, 1e-6)
     top_t1 = model.nod_dof[model.getidoftyp("X", "t1") - 1][node_lists[2][-1]] - 1
     assert abs(ref[-1][0][top_t1] - horiz_target(STATIC_TIMES[5])) < 1e-6
+
+
+@pytest.mark.gpu
+def test_scr_general_form_assembly_parity(mb):
+    """The same problem through the GENERAL DirectXUA form (mb_xua_*): every device type of the riser — EulerBeam3D{Udof} (first-order packets), SoilContact (second-order
+    branch in closed form) — evaluated by mb_xua_eval_device, Hold / DofConstraint / DofLoad through their closed-form partials and the U-costs through D2 on the host:
+    the structures are the oracle's bit for bit, Lvv values and Lv ≤ 1e-12."""
+    from muscade_b200 import xua
+    OX, OU, nstep, dt, t0, σu = 2, 0, 7, 0.3, -6.3, 50.
+    model, node_lists, weights = build(mb, udof=True)
+    unodes = np.concatenate([et.nodID[:, 2] for et in model.ele if et.ElType.__name__ == "EulerBeam3D"])
+    for f in ("t1", "t2", "t3"):
+        mb.addelement(model, mb.SingleDofCost, unodes[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / σu) ** 2)
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=30., t2=30., t3=30.)), Λscale=1e3)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU, nA = model.getndof(("X", "U", "A"))
+    time = t0 + dt * np.arange(nstep)
+    st = [([mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.2 if d == 0 else 0.3) for d in range(3)], 20. * mb.synthetic.uniform_pm1(99 + s, nU)) for s in range(nstep)]
+    Lam = [mb.synthetic.uniform_pm1(500 + s, nX) for s in range(nstep)]
+    odis = [dict(X=d.X, U=d.U, A=d.A) for d in dis.dis]
+    P = OP.prepare_direct(odis, nX, nU, nA, OX, OU, 0)
+    big, bigasm, pgr, pgc = OP.preparebig(0, [nstep], P["nL2"], P["pat"])
+    outs = [oracle_scr_direct_step(model, dis, weights, P, OX, OU, st[s][0], st[s][1], Lam[s], time[s], σu) for s in range(nstep)]
+    nz, Lv = OP.assemblebig(0, nstep, dt, P, big, bigasm, pgr, outs)
+    eng = xua.XUAEngine(0)
+    try:
+        nbig, nnz = eng.prepare(model, dis, OX, OU, 0, [nstep], [dt])
+        eng.set_time0(1, t0)
+        cp, rv = eng.big_pattern()
+        assert np.array_equal(cp, big["colptr"]) and np.array_equal(rv, big["rowval"])
+        states = [[mb.State(float(time[s]), [Lam[s]], st[s][0], [st[s][1]], st0.A, None, model, dis) for s in range(nstep)]]
+        eng.assemblebig(states)
+        Lvv, Lvec = eng.big()
+        scale = np.abs(nz).max()
+        assert np.abs(Lvv - nz).max() <= 1e-12 * scale
+        assert np.abs(Lvec - Lv).max() <= 1e-12 * max(scale, np.abs(Lv).max())
+    finally:
+        eng.close()
