@@ -62,3 +62,41 @@ def test_ten_million_elements_periodic_windows(mb, OX, mission):
         assert (float(nz2.sum()), float(np.abs(nz2).max()), float(L2.sum())) == chk and np.array_equal(nz[:10**6], nz2[:10**6])
     finally:
         eng.close()
+
+
+def test_general_form_equals_specialised_path_at_size(mb):
+    """A size the oracle's loops cannot do in seconds: 20 000 EulerBeam3D{Udof} × 6 steps, DirectXUA{2,0,0}.  The general form (mb_xua_*: packets from the device kernels, segmented
+    reductions, tabulated weighted adds through Lvvasm) and the beam-specialised path (mb_direct_*: block-implicit Lvv) implement the same assemblebig! by different means:
+    identical structures, Lvv values and Lv within 1e-13 of each other (the specialised path is the one checked against the oracle at small sizes)."""
+    from muscade_b200 import xua
+    Ne, OX, OU, nstep, dt = 20000, 2, 0, 6, 0.1
+    m = mb.Model("udof chain")
+    h = np.array([0.8, 0.6, 0.])
+    nod = mb.addnode(m, np.arange(Ne + 1, dtype=float)[:, None] * h[None, :])
+    un = mb.addnode(m, np.zeros((Ne, 0)))
+    mb.addelement(m, mb.EulerBeam3D, np.stack([nod[:-1], nod[1:], un], axis=1),
+                  mat=mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1., Ca2=169.6, Ca3=169.6, Cq2=235.2, Cq3=235.2), Udof=True)
+    mb.setscale(m, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=5., t2=5., t3=5.)))
+    s0 = mb.initialize(m); dis = s0.dis
+    nX, nU = m.getndof("X"), m.getndof("U")
+    st = [([mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.05 if d == 0 else 0.1) for d in range(3)], 0.5 * mb.synthetic.uniform_pm1(99 + s, nU)) for s in range(nstep)]
+    spec = mb.directxua.prepare(OX, OU, m, dis, nstep, dt)
+    gen = xua.XUAEngine(0)
+    try:
+        for s, (X, U) in enumerate(st):
+            spec.set_state(s, X, U)
+        Lvv = np.zeros(spec.nnzbig); Lv = np.zeros(spec.ncol)
+        spec.direct_assemble(Lvv=Lvv, Lv=Lv)
+        cp, rv = spec.big_pattern()
+        nbig, nnz = gen.prepare(m, dis, OX, OU, 0, [nstep], [dt])
+        assert nbig == spec.ncol and nnz == spec.nnzbig
+        gcp, grv = gen.big_pattern()
+        assert np.array_equal(cp, gcp) and np.array_equal(rv, grv)
+        states = [[mb.State(dt * s, [np.zeros(nX)], st[s][0], [st[s][1]], s0.A, None, m, dis) for s in range(nstep)]]
+        gen.assemblebig(states)
+        gLvv, gLv = gen.big()
+        scale = np.abs(Lvv).max()
+        assert np.abs(gLvv - Lvv).max() <= 1e-13 * scale and np.abs(gLv - Lv).max() <= 1e-13 * max(scale, np.abs(Lv).max())
+        assert np.count_nonzero(Lvv) > 0.2 * Lvv.size
+    finally:
+        spec.close(); gen.close()
