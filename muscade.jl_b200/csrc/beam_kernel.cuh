@@ -745,7 +745,13 @@ template <> struct StaticSymLaunch<1> {
                 if (!carved) { cudaFuncSetAttribute(beam_static_ap_kernel<MB_AP_MINB, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 40); carved = true; }
                 beam_static_ap_kernel<MB_AP_MINB, true, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, a.fz);
             }
-            else beam_static_ap_kernel<MB_AP_MINB, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, nofz);
+            else {
+                // MB_AP_CARVE (experiment): shared-memory carve-out in % for a kernel that uses none — what is left of the 256 KB is L1 for the spill lines.  10 M elements:
+                // default = 0 % = 6 % = 12 %: 14.25 ms; 100 % (smallest L1): 16.08 ms (tools/probe_carve.py)
+                static int carve = -2;
+                if (carve == -2) { const char* c = getenv("MB_AP_CARVE"); carve = c ? atoi(c) : -1; if (carve >= 0) cudaFuncSetAttribute(beam_static_ap_kernel<MB_AP_MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); }
+                beam_static_ap_kernel<MB_AP_MINB, true><<<nbw, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, nofz);
+            }
         } else if (a.static_sym == 2)
             beam_static_ap_kernel<MB_AP_MINB, false><<<nb, MB_BLOCK, 0, a.stream>>>(a.g, a.st, a.Ke, a.Re, a.nanflag, a.nanbase, FuseDev{nullptr, nullptr, nullptr, 0});
         else
