@@ -47,6 +47,50 @@ class Spring1(mb.LagrangianElement):
         return [F1, -F1]
 
 
+class Spring2(mb.LagrangianElement):
+    """Spring{2} (test/SomeElements.jl:164-188): two translations per node, A-dofs ΞL₀, ΞEI on a third node; no_second_order = Val(false)"""
+    type_parameters = ()
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1, 2, 2, 3, 3), ("X", "X", "X", "X", "A", "A"), ("tx1", "tx2", "tx1", "tx2", "ΞL₀", "ΞEI")
+
+    @classmethod
+    def construct(cls, coords, EA):
+        x1, x2 = coords[0], coords[1]
+        return np.concatenate([x1, x2, np.full((x1.shape[0], 1), float(EA)), np.sqrt(((x1 - x2) ** 2).sum(1))[:, None]], axis=1)
+
+    @staticmethod
+    def residual(o, extra, X, U, A, t, SP):
+        L0 = o[:, 5] * exp10(A[0]); EA = o[:, 4] * exp10(A[1])
+        d1 = (X[0][0] + o[:, 0]) - (X[0][2] + o[:, 2]); d2 = (X[0][1] + o[:, 1]) - (X[0][3] + o[:, 3])
+        L = sqrt(d1 * d1 + d2 * d2)
+        T = EA * (L - L0) / L0
+        F1, F2 = d1 / L * T, d2 / L * T
+        return [F1, F2, -F1, -F2]
+
+
+def model_testdirectxua001():
+    """test/TestDirectXUA001.jl:7-30"""
+    m = mb.Model("TestModel")
+    n1 = mb.addnode(m, [0., 0.]); n2 = mb.addnode(m, [10., 0.]); n3 = mb.addnode(m, [0., 10.]); n4 = mb.addnode(m, [])
+    mb.addelement(m, Spring2, [n1, n2, n4], EA=10)
+    mb.addelement(m, Spring2, [n1, n3, n4], EA=10)
+    load = lambda t: 0.1 * t
+    mb.addelement(m, mb.DofLoad, [n1], field="tx1", value=load)
+    mb.addelement(m, mb.DofLoad, [n1], field="tx2", value=load)
+    for n in (n2, n3):
+        for f in ("tx1", "tx2"):
+            mb.addelement(m, mb.Hold, [n], field=f)
+    meas = lambda x, t: 0.5 * ((x - 0.12 * t) / 0.01) ** 2
+    acost = lambda a: 0.5 * (a / .1) ** 2
+    mb.addelement(m, mb.SingleDofCost, [n1], clas="X", field="tx1", cost=meas)
+    mb.addelement(m, mb.SingleDofCost, [n1], clas="X", field="tx2", cost=meas)
+    mb.addelement(m, mb.SingleAcost, [n4], field="ΞL₀", cost=acost)
+    mb.addelement(m, mb.SingleAcost, [n4], field="ΞEI", cost=acost)
+    return m
+
+
 def fa(a): return a ** 2 * 1e-14
 def fu(u, t): return u ** 2
 def l1(x, t): return (x - 0.1 * np.sin(t)) ** 2
