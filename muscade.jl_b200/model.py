@@ -55,6 +55,8 @@ class EleTyp:
         """ElType.residual over all elements: X = [X₀,X′,…] of shape (nele,nx) each → (R, K0, K1, K2), K1/K2 None when no run has them.
         Element types that read U- or A-dofs (as plain values: an X-analysis does not differentiate with respect to them, src/SweepX.jl:45-96)
         declare `takes_UA = True` and receive U (nele,nu), A (nele,na) as keyword arguments."""
+        if getattr(self.ElType, "kind", None) == "lagrangian":
+            return self._residual_d2(X, t, U, A)
         if getattr(self.ElType, "takes_UA", False):
             parts = [self.ElType.residual(ex, [x[a:b] for x in X], t, U=None if U is None else U[a:b], A=None if A is None else A[a:b]) for a, b, ex in self._runs()]
         else:
@@ -70,6 +72,43 @@ class EleTyp:
             cols = [c if c is not None else np.zeros((b - a,) + ref.shape[1:]) for c, (a, b, _) in zip(cols, self._runs())]
             out.append(np.concatenate(cols))
         return tuple(out)
+
+    def _residual_d2(self, X, t, U, A):
+        """An X-analysis (SweepX) of an element type written against adiff2.D2 (toolbox.LagrangianElement): R and ∂R/∂X₀, ∂R/∂X′, ∂R/∂X″ by the host's dual numbers, U and A
+        as plain values.  A type that only has `lagrangian` gives R = ∂L/∂Λ, as getresidual derives it (src/Assemble.jl:660-680)."""
+        from .adiff2 import D2
+        T = self.ElType
+        nd, nx = len(X), X[0].shape[1]
+        outs = []
+        for a, b, ex in self._runs():
+            n = b - a
+            eo = self.eleobj[a:b] if self.eleobj is not None else None
+            Uv = [[U[a:b][:, i] for i in range(U.shape[1])]] if U is not None else [[]]
+            Av = [A[a:b][:, i] for i in range(A.shape[1])] if A is not None else []
+            Xval = np.concatenate([x[a:b] for x in X], axis=1)
+            R = np.zeros((n, nx)); K = [np.zeros((n, nx, nx)) for _ in range(nd)]
+            if hasattr(T, "lagrangian"):
+                v = D2.variables(np.concatenate([np.zeros((n, nx)), Xval], axis=1))
+                Xv = [v[nx + d * nx: nx + (d + 1) * nx] for d in range(nd)]
+                L = D2.lift(T.lagrangian(eo, ex, v[:nx], Xv, Uv, Av, t, None))
+                g, H = L.grad(n, nx * (nd + 1)), L.hess(n, nx * (nd + 1))
+                R = g[:, :nx]
+                for d in range(nd):
+                    K[d] = H[:, :nx, nx + d * nx: nx + (d + 1) * nx]
+            else:
+                v = D2.variables(Xval)
+                Xv = [v[d * nx: (d + 1) * nx] for d in range(nd)]
+                Rv = T.residual(eo, ex, Xv, Uv, Av, t, None)
+                for i in range(nx):
+                    Ri = D2.lift(Rv[i])
+                    R[:, i] = np.broadcast_to(Ri.v, (n,))
+                    gi = Ri.grad(n, nx * nd)
+                    for d in range(nd):
+                        K[d][:, i, :] = gi[:, d * nx: (d + 1) * nx]
+            outs.append((R, K))
+        R = np.concatenate([o[0] for o in outs])
+        Ks = [np.concatenate([o[1][d] for o in outs]) for d in range(nd)] + [None] * (3 - nd)
+        return R, Ks[0], Ks[1], Ks[2]
 
     def hessian(self, X, lam_e, t):
         fn = getattr(self.ElType, "hessian", None)

@@ -358,6 +358,7 @@ class LagrangianElement(ElementType):
     `lagrangian(eleobj, extra, Λ, X, U, A, t, SP)` → L, with X[der][i], U[der][i], A[i], Λ[i] per-element arrays or D2 (xua.packets)."""
     kind = "lagrangian"
     no_second_order = False
+    takes_UA = True            # in an X-analysis (SweepX) U and A reach the element as plain values (model.EleTyp._residual_d2)
 
     @classmethod
     def typekey(cls, **kw):

@@ -77,3 +77,36 @@ def test_sweepx1_exponential_decay_reference_states(mb):
     rx1 = [-2.85714, -2.04082, -1.45773, -1.04123, -0.743738, -0.531241, -0.379458, -0.271041, -0.193601, -0.138286, -0.098776, -0.0705543,
            -0.0503959, -0.0359971, -0.0257122, -0.0183659, -0.0131185, -0.00937034, -0.0066931, -0.00478079]
     assert np.linalg.norm(x - rx) <= 1e-5 * np.linalg.norm(rx) and np.linalg.norm(x1 - rx1) <= 1e-5 * np.linalg.norm(rx1)      # rtol of the reference test
+
+
+def test_assemble_turbine_anchorline_reference_values(mb):
+    """test/TestAssemble.jl:43-51,152-158 — assemble!{:iter}(out::AssemblySweepX{0},…) of a Turbine and an AnchorLine (toy elements of test/SomeElements.jl, written against
+    adiff2.D2, with A-dofs as plain values; the AnchorLine is given by its `lagrangian` only) at the zero state: the device scatter gives the reference's Lλ and Lλx"""
+    import xua_models as XM
+    m = mb.Model("TestModel")
+    n1 = mb.addnode(m, [0., 0., 100.]); n2 = mb.addnode(m, []); n3 = mb.addnode(m, [])
+    mb.addelement(m, XM.Turbine, [n1, n2], seadrag=2., sea=lambda t, x: (1., 0.), skydrag=3., sky=lambda t, x: (0., 1.))
+    mb.addelement(m, XM.AnchorLine, [n1, n3], Δxₘtop=[5., 0., 0.], xₘbot=[150., 0.], L=180., buoyancy=-1e3)
+    st = mb.initialize(m)
+    out, asm, dofgr = mb.sweepx.prepare(0, m, st.dis)
+    try:
+        assert asm[1, 1].tolist() == [[1], [2]] and asm[1, 2].tolist() == [[1], [2], [3]]                       # :121-122
+        assert asm[2, 1].tolist() == [[1], [2], [4], [5]] and asm[2, 2].ravel().tolist() == list(range(1, 10))  # :123-124
+        out.c = mb.sweepx.newmark_coefficients(0, 0.)
+        mb.sweepx.assemble("iter", out, asm, st.dis, m, st, 0.)
+        assert np.allclose(out.Lλ, [-152130.71199858442, -3.0, 0.0], rtol=1e-10, atol=1e-9)                    # :156
+        K = np.array([[10323.069597975566, 0., 0.], [0., 1049.1635310247202, 5245.8176551236], [0., 5245.817655123601, 786872.6482685402]])
+        assert np.allclose(out.Lλx.toarray(), K, rtol=1e-10, atol=1e-7)                                         # :157
+    finally:
+        out.engine.close()
+
+
+def test_sweepx0_turbine_moorings_reference_state(mb):
+    """test/TestSweepX0.jl:9-29 — solve(SweepX{0};time=[0.,1.]) of a turbine on three anchor lines: the converged X of step 1 is the reference's"""
+    import xua_models as XM
+    m = XM.model_testsweepx0()
+    st = mb.initialize(m)
+    states = mb.sweepx.solve(0, st, [0., 1.])
+    s = states[0]
+    assert np.allclose(s.X[0], [-5.332268523655259, 21.09778288272267, 0.011304253608808651], rtol=1e-7)       # :24 (Julia's ≈: rtol = √eps)
+    assert not s.Λ[0].any() and not s.A.any() and s.time == 0. and m.locked

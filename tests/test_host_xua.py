@@ -96,3 +96,27 @@ def _dense(colptr, rowval, nz, m, n):
         for k in range(colptr[j] - 1, colptr[j + 1] - 1):
             A[rowval[k] - 1, j] = nz[k]
     return A
+
+
+def test_turbine_and_anchorline_goldens():
+    """test/TestAssemble.jl:9-41 — the toy elements of test/SomeElements.jl restated against adiff2.D2 give the reference's R, ∇R and ∇L (diffed_residual / diffed_lagrangian{2})"""
+    m = mb.Model("t")
+    n1 = mb.addnode(m, [0., 0., -10.]); n2 = mb.addnode(m, [])
+    mb.addelement(m, XM.Turbine, [n1, n2], seadrag=2., sea=lambda t, x: (1., 0.), skydrag=3., sky=lambda t, x: (0., 1.))
+    s0 = mb.initialize(m)
+    s0.X[0][:] = [1., 2.]
+    XM.Turbine.no_second_order = True
+    try:
+        g, H = xua.packets(m.ele[0], s0.dis.dis[0], 0, 0, 1, s0.Λ[0], s0.X, s0.U, s0.A, 0.)
+    finally:
+        XM.Turbine.no_second_order = False
+    assert np.allclose(g[0, :2], [-2., -3.])                                        # R                      :19
+    assert np.allclose(H[0, :2, 2:4], 0.) and np.allclose(H[0, :2, 4:6], [[-2., 0.], [0., -3.]])      # ∇R wrt X, A            :20-22
+    m = mb.Model("a")
+    n1 = mb.addnode(m, [0., 0., 100.]); n3 = mb.addnode(m, [])
+    mb.addelement(m, XM.AnchorLine, [n1, n3], Δxₘtop=[0., 2., 0.], xₘbot=[94., 0.], L=170., buoyancy=-1.)
+    s0 = mb.initialize(m)
+    g, H = xua.packets(m.ele[0], s0.dis.dis[0], 0, 0, 1, np.ones(3), s0.X, s0.U, s0.A, 0.)
+    assert np.allclose(g[0, 0:3], [-12.25628901693551, 0.2607721067433087, 24.51257803387102], rtol=1e-10)      # ∇L[1][1]   :37
+    assert np.allclose(g[0, 3:6], [-0.91509745608786, 0.14708204066349, 1.3086506986891027], rtol=1e-10)        # ∇L[2][1]   :38
+    assert np.allclose(g[0, 6:8], [-156.06324599170992, 12.517061123678818], rtol=1e-10)                        # ∇L[4][1]   :40

@@ -91,6 +91,79 @@ def model_testdirectxua001():
     return m
 
 
+def horner(p, x):
+    y = 0.
+    for c in reversed(p):
+        y = c + x * y
+    return y
+
+
+class Turbine(mb.LagrangianElement):
+    """Turbine (test/SomeElements.jl:20-31): R = −sea(t,x)·seadrag·(1+A₁) − sky(t,x)·skydrag·(1+A₂); sea, sky return two components"""
+    type_parameters = ("sea", "sky")
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1, 2, 2), ("X", "X", "A", "A"), ("tx1", "tx2", "Δseadrag", "Δskydrag")
+
+    @classmethod
+    def construct(cls, coords, seadrag, sea, skydrag, sky):
+        n = coords[0].shape[0]
+        return np.concatenate([coords[0][:, :3], np.tile([[seadrag, skydrag]], (n, 1))], axis=1), dict(sea=sea, sky=sky)
+
+    @staticmethod
+    def residual(o, extra, X, U, A, t, SP):
+        x = [X[0][0] + o[:, 0], X[0][1] + o[:, 1]]
+        sea, sky = extra["sea"](t, x), extra["sky"](t, x)
+        return [-sea[i] * o[:, 3] * (1 + A[0]) - sky[i] * o[:, 4] * (1 + A[1]) for i in range(2)]
+
+
+ANCHOR_P = [2.82040487827, -24.86027164695, 153.69500343165, -729.52107422849, 2458.11921356871, -5856.85610233072, 9769.49700812681, -11141.12651712473,
+            8260.66447746395, -3582.36704093187, 687.83550335374]
+
+
+class AnchorLine(mb.LagrangianElement):
+    """AnchorLine (test/SomeElements.jl:62-103): a catenary mooring line given by its `lagrangian` only — L = Λ₁₂·Fd + Λ₃·m₃"""
+    type_parameters = ()
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1, 1, 2, 2), ("X", "X", "X", "A", "A"), ("tx1", "tx2", "rx3", "ΔL", "Δbuoyancy")
+
+    @classmethod
+    def construct(cls, coords, Δxₘtop, xₘbot, L, buoyancy):
+        n = coords[0].shape[0]
+        return np.concatenate([coords[0][:, :3], np.tile([list(Δxₘtop) + list(xₘbot) + [L, buoyancy]], (n, 1))], axis=1)
+
+    @staticmethod
+    def lagrangian(o, extra, Λ, X, U, A, t, SP):
+        L, buoy = o[:, 8] * (1 + A[0]), o[:, 9] * (1 + A[1])
+        x = X[0]
+        Xtop = [x[0] + o[:, 0], x[1] + o[:, 1], o[:, 2]]
+        c, s = cos(x[2]), sin(x[2])
+        dX = [c * o[:, 3] - s * o[:, 4], s * o[:, 3] + c * o[:, 4]]                  # arm of the fairlead
+        ch = [Xtop[0] + dX[0] - o[:, 6], Xtop[1] + dX[1] - o[:, 7]]                 # from anchor to fairlead
+        xaf = sqrt(ch[0] * ch[0] + ch[1] * ch[1])
+        cr = exp10(horner(ANCHOR_P, (L - xaf) / Xtop[2])) * Xtop[2]
+        Fh = -cr * buoy
+        Fd = [ch[0] / xaf * Fh, ch[1] / xaf * Fh]
+        m3 = dX[0] * Fd[1] - dX[1] * Fd[0]
+        return Λ[0] * Fd[0] + Λ[1] * Fd[1] + Λ[2] * m3
+
+
+def model_testsweepx0():
+    """test/TestSweepX0.jl:9-18"""
+    m = mb.Model("TestModel")
+    n1 = mb.addnode(m, [0., 0., 100.]); n2 = mb.addnode(m, []); n3 = mb.addnode(m, [])
+    sea = lambda t, x: (1. * t, 0. * t)
+    sky = lambda t, x: (0., 10.)
+    mb.addelement(m, Turbine, [n1, n2], seadrag=1e6, sea=sea, skydrag=1e5, sky=sky)
+    for i in range(3):
+        al = np.array([np.cos(i * 2 * np.pi / 3), np.sin(i * 2 * np.pi / 3)])
+        mb.addelement(m, AnchorLine, [n1, n3], Δxₘtop=list(5 * al) + [0.], xₘbot=list(250 * al), L=290., buoyancy=-5e3)
+    return m
+
+
 def fa(a): return a ** 2 * 1e-14
 def fu(u, t): return u ** 2
 def l1(x, t): return (x - 0.1 * np.sin(t)) ** 2
