@@ -739,19 +739,24 @@ def run_gauges(args, rank, world, local, comm):
     line = None
     if rank == 0:
         Np = 12 + 12 * (OX + 1) + 3
-        bytes_step = N * (8 * Np * Np * 2 + 8 * 12 * (12 * (OX + 1) + 3) * 2) + 24 * nnz // nstep         # packets written + read, (R,dR) written + read, Lvv values read + written + map read
+        npd = 12 * (OX + 1) + 3
+        nxx = 108 * N + 36                                                                   # non-zeros of the X-X class pattern of the chain (= Λ-X, X-Λ); Λ-U / U-Λ: 36 N
+        out_nz = (2 * (OX + 1) + 1) * nxx + 2 * 36 * N                                       # live blocks of out: L2[Λ,X_d], L2[X_d,Λ], L2[X₀,X₀], L2[Λ,U], L2[U,Λ]
+        add_nz = (2 * 6 + 1) * nxx + 2 * 36 * N                                              # block entries added into Lvv per step: 1+2+3 stencil points per derivative order
+        bytes_step = N * 8 * 12 * (npd + 1) * 2 + N * 8 * (Np + 12 + 144) * 2 + out_nz * 16 + add_nz * 24      # (R,dR), ∇L / cost terms, out written + read, Lvv read + written + Lvvasm
         line = {"metric": "element-step assemblies/s (DirectXUA{2,0,0} assemblebig!, general form, ElementCost{StrainGaugeOnEulerBeam3D} on the device)",
                 "value": N * nstep / (step_ms * 1e-3), "unit": "element-step assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "ms_per_pass": step_ms, "higher_is_better": True, "scaling": "replicas", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "general DirectXUA{2,0,0} form (mb_xua_*): %d strain-gauged EulerBeam3D{Udof} (5 gauges each, quadratic strain cost: the ElementCost accelerator on "
                                        "the device) x %d time steps; no host-evaluated type, states resident in HBM" % (N, nstep),
-                           "elements": N, "nstep": nstep, "lvv_size": int(nbig), "lvv_nnz": int(nnz), "l2": "packets (%.1f GB per step) and Lvv (%.1f GB) larger than L2" % (8e-9 * N * Np * Np, 8e-9 * nnz)},
+                           "elements": N, "nstep": nstep, "lvv_size": int(nbig), "lvv_nnz": int(nnz), "l2": "element outputs, out blocks (%.1f GB per step) and Lvv (%.1f GB) larger than L2" % (8e-9 * out_nz, 8e-9 * nnz)},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": bytes_step * nstep / (step_ms * 1e-3) / 1e9, "peak": hbm_peak()[0], "peak_source": hbm_peak()[1],
                              "frac": bytes_step * nstep / (step_ms * 1e-3) / 1e9 / hbm_peak()[0], "traffic": None,
                              "bytes_per_step": int(bytes_step),
-                             "note": "whole pass against the HBM peak (MEASURED_PEAKS.json): dense packets of %d x %d partials per element are written by the element kernels and read by "
-                                     "the segmented reductions — the price of the general form; the beam-specialised path (directxua block) moves a tenth of it" % (Np, Np)}}
+                             "note": "whole pass against the HBM peak (MEASURED_PEAKS.json); algorithmic bytes: element outputs (R, dR, gradient and cost terms) written and read, "
+                                     "the live blocks of out written by the segmented reductions and read by the weighted adds, Lvv values read + written with their Lvvasm "
+                                     "positions.  Device element types are reduced from the outputs of their kernels: no dense %d x %d packet is formed" % (Np, Np)}}
     eng.close()
     return line
 

@@ -43,11 +43,15 @@ struct XuaType {
     double *g = nullptr, *H = nullptr; bool has = false;
     // device-evaluated type (EulerBeam3D of the handle, mb_xua_add_device_eletyp): outputs of the first-order kernels, and the ElementCost accelerator's strain-gauge cost
     int devgroup = -1, devkind = 0; double *dR = nullptr, *Rb = nullptr, *GXb = nullptr;
-    int ng = 0; double isig2 = 0.; double *G = nullptr, *epsm = nullptr, *J = nullptr, *e4 = nullptr, *cost = nullptr, *sL = nullptr; bool epsm_per_element = false;
+    int ng = 0; double isig2 = 0.; double *G = nullptr, *epsm = nullptr, *J = nullptr, *e4 = nullptr, *cost = nullptr, *sL = nullptr, *gX = nullptr, *HXX = nullptr; bool epsm_per_element = false;
+    int npd = 0, nd = 0; int64_t last_gs = 0;
 };
 struct TabDev {                                  // per element type, for one (α,β) or α: by value into the gather kernels
     int n; uint32_t pbase[XMAXT + 1]; int ni[XMAXT], nj[XMAXT], Np[XMAXT], bi[XMAXT], bj[XMAXT]; const double* p[XMAXT];
     uint16_t live[XMAXT];                    // per type: derivative blocks (i·nbd + j; for vectors: i) of this class pair its packet can be non-zero in
+    // device element types are reduced straight from the outputs of their kernels, no dense packet: mode 1 → p = ∂R/∂seed [e][npd][nx] (beam_kernel.cuh K3), sl = scale.Λ of the
+    // element dofs (costed beams) or nullptr, hxx = the cost's X₀-X₀ block [e][nx][nx] or nullptr
+    uint8_t mode[XMAXT]; uint8_t npd[XMAXT]; const double* sl[XMAXT]; const double* hxx[XMAXT];
 };
 struct Combo2 { int i, j; double f; int64_t off; };      // L2[α,β][i,j]·f → Lvv.nzval[basm[off + l]]
 struct Combo1 { int i; double f; int64_t row0; };        // L1[β][i]·f → Lv[row0 + d]
@@ -59,7 +63,8 @@ __device__ __forceinline__ int find_type(const uint32_t* pbase, int n, uint32_t 
 }
 // out[(i·nbd + j)·nnz + k] = Σ_contributors H[e][bi + ni·i + ia][bj + nj·j + ib]   (grid.y = i·nbd + j)
 // live: bit (i·nbd + j) set where some element type can contribute to L2[α,β][i,j]; the other blocks are written as zeros without reading anything
-__global__ void xua_gather2_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, TabDev T, int nbd, uint32_t live, double* __restrict__ out) {
+__global__ void xua_gather2_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, TabDev T, int nbd, uint32_t live, int ca, int cb, int nd,
+                                   double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     const int i = blockIdx.y / nbd, j = blockIdx.y - i * nbd;
@@ -73,6 +78,14 @@ __global__ void xua_gather2_kernel(int64_t nnz, const uint32_t* __restrict__ cst
         const int n2 = T.ni[t] * T.nj[t];
         const int64_t e = r / n2; const int q = (int)(r - e * n2);
         const int ib = q / T.ni[t], ia = q - ib * T.ni[t];                      // entry ieledof + ni·(jeledof−1)  (src/Assemble.jl:389)
+        if (T.mode[t]) {                       // device type: (Λ,β) = ∂R_ia/∂seed_p(β,j,ib), (β,Λ) its transpose, (X₀,X₀) the cost's block (classes: 0 Λ, 1 X, 2 U)
+            double v;
+            if (ca == 0) { const int pp = (cb == 1 ? T.nj[t] * j : T.ni[t] * nd) + ib; v = T.p[t][(e * T.npd[t] + pp) * T.ni[t] + ia]; if (T.sl[t]) v *= T.sl[t][ia]; }
+            else if (cb == 0) { const int pp = (ca == 1 ? T.ni[t] * i : T.nj[t] * nd) + ia; v = T.p[t][(e * T.npd[t] + pp) * T.nj[t] + ib]; if (T.sl[t]) v *= T.sl[t][ib]; }
+            else v = T.hxx[t][(e * T.nj[t] + ib) * T.ni[t] + ia];
+            acc += v;
+            continue;
+        }
         acc += T.p[t][(e * T.Np[t] + (T.bj[t] + T.nj[t] * j + ib)) * T.Np[t] + (T.bi[t] + T.ni[t] * i + ia)];      // ∇²L is symmetric: entry (α,β) read at [β][α], so that the rows ia of a column — consecutive non-zeros — are consecutive addresses
     }
     out[(int64_t)blockIdx.y * nnz + k] = acc;
@@ -225,7 +238,8 @@ __global__ void __launch_bounds__(256) xua_sumsq_kernel(int64_t nX, int64_t nU, 
 // ·scale.Λ·scale.X, GX[(e·nx+i)·nd+d] = ∂L/∂X_d,i): ∇L[Λ] = R, ∇L[X_d] = GX, Λ rows / columns = ∂R/∂X_d.
 __global__ void __launch_bounds__(128) elem_packet_kernel(int64_t nele, int nx, int nd, int npd, int Np, int nu0 /* packet column of U₀ or −1 */, const double* __restrict__ R,
                                    const double* __restrict__ dR, const double* __restrict__ GX, const int32_t* __restrict__ idxX, const double* __restrict__ Lam,
-                                   const double* sLam, int mode, double* __restrict__ g, double* __restrict__ H) {
+                                   const double* sLam, int mode, const double* __restrict__ gX, const double* __restrict__ HXX, double* __restrict__ g, double* __restrict__ H) {
+    // H = nullptr: only ∇L — the reductions read the Λ rows / columns of a device type from dR itself (xua_gather2_kernel, mode 1); the dense ∇²L is built for mb_xua_get_packet only
     // one CTA per element: its ∂R/∂seed (npd × nx, contiguous) goes through shared memory so that BOTH copies — the Λ rows H[i][col] and the Λ columns H[col][i] — leave as
     // contiguous runs (written straight from the [p][i] layout one of the two is a stride-Np scatter of 8-byte stores)
     __shared__ double sm[39 * 12];
@@ -236,22 +250,27 @@ __global__ void __launch_bounds__(128) elem_packet_kernel(int64_t nele, int nx, 
     for (int q = threadIdx.x; q < n; q += blockDim.x) sm[q] = dR[e * n + q];
     if ((int)threadIdx.x < nx) { lam[threadIdx.x] = costed ? Lam[idxX[e * nx + threadIdx.x]] : 0.; sl[threadIdx.x] = costed ? sLam[threadIdx.x] : 1.; }
     __syncthreads();
-    double* He = H + e * (int64_t)Np * Np; double* ge = g + e * (int64_t)Np;
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ columns: H[col][i], i fastest
-        const int p = q / nx, i = q - p * nx;
-        const int col = (p < nxd) ? nx + p : nu0 + (p - nxd);
-        He[col * Np + i] = sm[q] * sl[i];
-    }
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ rows: H[i][col], col fastest
-        const int i = q / npd, p = q - i * npd;
-        const int col = (p < nxd) ? nx + p : nu0 + (p - nxd);
-        He[i * Np + col] = sm[p * nx + i] * sl[i];
+    double* ge = g + e * (int64_t)Np;
+    if (H) {
+        double* He = H + e * (int64_t)Np * Np;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ columns: H[col][i], i fastest
+            const int p = q / nx, i = q - p * nx;
+            const int col = (p < nxd) ? nx + p : nu0 + (p - nxd);
+            He[col * Np + i] = sm[q] * sl[i];
+        }
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {          // Λ rows: H[i][col], col fastest
+            const int i = q / npd, p = q - i * npd;
+            const int col = (p < nxd) ? nx + p : nu0 + (p - nxd);
+            He[i * Np + col] = sm[p * nx + i] * sl[i];
+        }
+        if (HXX) for (int q = threadIdx.x; q < nx * nx; q += blockDim.x) He[(nx + q / nx) * Np + nx + q % nx] = HXX[e * nx * nx + q];
     }
     if ((int)threadIdx.x < npd) {
         const int p = threadIdx.x;
         if (costed) {
             double acc = 0.;
             for (int i = 0; i < nx; ++i) acc += lam[i] * sm[p * nx + i];
+            if (gX && p < nx) acc += gX[e * nx + p];
             ge[(p < nxd) ? nx + p : nu0 + (p - nxd)] = acc;
         }
         if (mode == 2 && p < nxd) { const int d = p / nx, i = p - d * nx; ge[nx + p] = GX[(e * nx + i) * nd + d]; }
@@ -278,9 +297,9 @@ __global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const d
 }
 // ElementCost accelerator for StrainGaugeOnEulerBeam3D (toolbox/StrainGaugeOnBeamElement.jl:70-76) under the quadratic cost Σ_g (ε_g − εm_g)²/(2σ²):
 // ε_g = G[g]·(εₐₓ,κ); ∇cost = Jᵀ·Gᵀ·r/σ², ∇²cost = Jᵀ·GᵀG·J/σ² (chainrule of the second-order cost with the first-order eleres: to_order{2} adds no curvature, :190-196).
-// One thread per (element, i): entry i of the X₀ gradient is ADDED to the packet (elem_packet_kernel put Λᵀ∂R/∂X₀ there), row i of the X₀-X₀ block is written.
-__global__ void gauge_cost_kernel(int64_t nele, int ng, int Np, const double* __restrict__ G, const double* __restrict__ epsm, bool per_element, double isig2,
-                                  const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ g, double* __restrict__ H, double* __restrict__ cost) {
+// One thread per (element, i): entry i of ∇cost → gX[e][12], row i of ∇²cost → HXX[e][12][12] (the whole X₀-X₀ block of the packet is the cost's: no Λ·∂²R/∂X²).
+__global__ void gauge_cost_kernel(int64_t nele, int ng, const double* __restrict__ G, const double* __restrict__ epsm, bool per_element, double isig2,
+                                  const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ gX, double* __restrict__ HXX, double* __restrict__ cost) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t / 12; const int i = (int)(t - e * 12);
     if (e >= nele) return;
@@ -294,9 +313,9 @@ __global__ void gauge_cost_kernel(int64_t nele, int ng, int Np, const double* __
     const double* Je = J + e * 48;
     double gi = 0., MJ[4];
     for (int k = 0; k < 4; ++k) { gi += Je[k * 12 + i] * q[k]; MJ[k] = ((M[k][0] * Je[i] + M[k][1] * Je[12 + i]) + M[k][2] * Je[24 + i]) + M[k][3] * Je[36 + i]; }
-    g[e * (int64_t)Np + 12 + i] += gi * isig2;
-    double* Hrow = H + (e * (int64_t)Np + 12 + i) * Np + 12;
-    for (int j = 0; j < 12; ++j) Hrow[j] = (((Je[j] * MJ[0] + Je[12 + j] * MJ[1]) + Je[24 + j] * MJ[2]) + Je[36 + j] * MJ[3]) * isig2;      // the whole X₀-X₀ block is the cost's (no Λ·∂²R/∂X²)
+    gX[e * 12 + i] = gi * isig2;
+    double* Hrow = HXX + (e * 12 + i) * 12;
+    for (int j = 0; j < 12; ++j) Hrow[j] = (((Je[j] * MJ[0] + Je[12 + j] * MJ[1]) + Je[24 + j] * MJ[2]) + Je[36 + j] * MJ[3]) * isig2;
     if (i == 0 && cost) cost[e] = 0.5 * c * isig2;
 }
 
@@ -715,6 +734,7 @@ static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_
         for (int t = 0; t < T.n; ++t) {
             const XuaType& Y = D->types[(size_t)t];
             T.pbase[t] = (uint32_t)D->vbase[ca][(size_t)t]; T.ni[t] = Y.n[ca]; T.nj[t] = 0; T.Np[t] = Y.Np; T.bi[t] = Y.base[a]; T.bj[t] = 0;
+            T.mode[t] = 0; T.npd[t] = 0; T.sl[t] = nullptr; T.hxx[t] = nullptr;
             T.p[t] = (Y.has && (!acost || Y.acost) && (a != 3 || D->IA)) ? Y.g : nullptr;
             T.live[t] = 0;
             if (T.p[t]) for (int i = 0; i < nd; ++i) if (Y.n[ca] > 0 && Y.nele > 0 && xua_live1(Y, a, i)) T.live[t] |= (uint16_t)(1u << i);
@@ -735,14 +755,16 @@ static int32_t xua_assemble_and_add(mb_handle* h, XuaData* D, bool acost, int64_
             for (int t = 0; t < T.n; ++t) {
                 const XuaType& Y = D->types[(size_t)t];
                 T.pbase[t] = (uint32_t)P.gbase[(size_t)t]; T.ni[t] = Y.n[cgroup(a)]; T.nj[t] = Y.n[cgroup(b)]; T.Np[t] = Y.Np; T.bi[t] = Y.base[a]; T.bj[t] = Y.base[b];
-                T.p[t] = (Y.has && (!acost || Y.acost)) ? Y.H : nullptr;
+                T.p[t] = (Y.has && (!acost || Y.acost)) ? (Y.devgroup >= 0 ? Y.dR : Y.H) : nullptr;
+                T.mode[t] = Y.devgroup >= 0 ? 1 : 0; T.npd[t] = (uint8_t)Y.npd; T.sl[t] = (Y.devgroup >= 0 && Y.ng > 0) ? Y.sL : nullptr; T.hxx[t] = Y.HXX;
                 T.live[t] = 0;
                 if (T.p[t] && Y.nele > 0 && T.ni[t] > 0 && T.nj[t] > 0)
                     for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j) if (xua_live2(Y, a, b, i, j)) T.live[t] |= (uint16_t)(1u << (i * nb + j));
             }
             uint32_t live = 0; for (int t = 0; t < T.n; ++t) live |= T.live[t];
             T.pbase[T.n] = (uint32_t)P.gbase[(size_t)T.n];
-            xua_gather2_kernel<<<dim3(nblk(P.nnz, 128), (unsigned)(na * nb)), 128, 0, st>>>(P.nnz, P.cstart, P.src, T, nb, live, D->L2[a][b]);
+            xua_gather2_kernel<<<dim3(nblk(P.nnz, 128), (unsigned)(na * nb)), 128, 0, st>>>(P.nnz, P.cstart, P.src, T, nb, live, a == 0 ? 0 : cgroup(a) + 1, b == 0 ? 0 : cgroup(b) + 1, D->OX + 1,
+                                                                                              D->L2[a][b]);
             h->launches++;
             const int64_t c0 = D->c2start[(size_t)(slot * 16 + 4 * a + b)], c1 = D->c2start[(size_t)(slot * 16 + 4 * a + b + 1)];
             if (c1 > c0 && live) { xua_addin2_kernel<<<nblk(P.nnz, 128), 128, 0, st>>>(P.nnz, D->L2[a][b], nb, live, D->cb2 + c0, (int)(c1 - c0), D->basm, D->nzval); h->launches++; }
@@ -814,6 +836,15 @@ int32_t mb_xua_set_gauge_measurements(mb_handle* h, int32_t ieletyp, const doubl
     T.epsm_per_element = per_element != 0;
     return MB_OK;
 }
+// ∇L of a device type from the outputs of its kernels (H = nullptr), or its whole dense packet (mb_xua_get_packet)
+static void xua_device_packet(mb_handle* h, XuaData* D, XuaType& T, double* H) {
+    const Group& g = h->groups[(size_t)T.devgroup];
+    const int nx = g.nx, nd = T.nd, npd = T.npd;
+    const int mode = g.kind == G_SOIL ? 2 : (T.ng > 0 ? 1 : 0);
+    elem_packet_kernel<<<(unsigned)T.nele, 128, 0, h->stream>>>(T.nele, nx, nd, npd, T.Np, g.udof ? nx + nx * nd : -1, T.Rb, T.dR, T.GXb, g.idxX,
+                                                               D->Lam + T.last_gs * D->ndof[0], T.sL, mode, T.gX, T.HXX, T.g, H);
+    h->launches++;
+}
 /* Packets of every device element type at state[iexp][istep] (the device-resident state, mb_xua_set_state): first-order kernels of the beam path → (R, ∂R/∂X_der, ∂R/∂U),
  * strain-gauge kernels where a cost is set.  Call before mb_xua_add_step, beside mb_xua_set_packet for the host-evaluated types. */
 int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo* where) {
@@ -832,9 +863,9 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
         const Group& g = h->groups[(size_t)T.devgroup];
         const int nx = g.nx;
         const int npd = nx * nd + (g.udof ? 3 : 0);
-        const int64_t ng = T.nele * T.Np, nh = ng * T.Np;
-        // the kernels below write every entry of the packet blocks a device type can fill (xua_live1 / xua_live2) and nothing else: the rest is zeroed once, here
-        if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(dalloc(h, &T.H, nh)); CK(cudaMemsetAsync(T.g, 0, (size_t)ng * 8, st)); CK(cudaMemsetAsync(T.H, 0, (size_t)nh * 8, st)); }
+        const int64_t ng = T.nele * T.Np;
+        T.npd = npd; T.nd = nd; T.last_gs = gs;
+        if (!T.g) { CK(dalloc(h, &T.g, ng)); CK(cudaMemsetAsync(T.g, 0, (size_t)ng * 8, st)); }         // the entries a device type never fills stay zero
         if (!T.dR) { CK(dalloc(h, &T.dR, T.nele * nx * npd)); CK(dalloc(h, &T.Rb, T.nele * nx)); if (g.kind == G_SOIL) CK(dalloc(h, &T.GXb, T.nele * nx * nd)); }
         DirectStateDev sd;
         for (int d = 0; d < 3; ++d) sd.X[d] = D->X + (gs * 3 + d) * nX;
@@ -847,16 +878,14 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
             for (int i = 0; i < 6; ++i) gd.scaleX[i] = g.scaleX[i];
             for (int i = 0; i < 3; ++i) gd.scaleU[i] = g.scaleU[i];
             h->launches += launch_bar_direct(nd, gd, sd, tnow, T.dR, T.Rb, h->nanflag, nanbase, st, sb, 1);
-            elem_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, nx, nd, npd, T.Np, g.udof ? nx + nx * nd : -1, T.Rb, T.dR, nullptr, g.idxX, nullptr, nullptr, 0, T.g, T.H);
-            h->launches++; T.has = true;
+            xua_device_packet(h, D, T, nullptr); T.has = true;
             continue;
         }
         if (g.kind == G_SOIL) {
             SoilGroupDev gd; gd.nele = g.nele; gd.par = g.geo; gd.idxX = g.idxX;
             for (int i = 0; i < 3; ++i) gd.scaleX[i] = g.scaleX[i];
             h->launches += launch_soil_direct(nd, gd, sd, D->Lam + gs * nX, D->lamscale, T.dR, T.Rb, T.GXb, h->nanflag, nanbase, st, sb, 1);
-            elem_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, nx, nd, npd, T.Np, -1, T.Rb, T.dR, T.GXb, g.idxX, nullptr, nullptr, 2, T.g, T.H);
-            h->launches++; T.has = true;
+            xua_device_packet(h, D, T, nullptr); T.has = true;
             continue;
         }
         BeamGroupDev gd;
@@ -877,15 +906,14 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
             double sL[12]; for (int i = 0; i < 12; ++i) sL[i] = g.scaleX[i] * D->lamscale;
             CK(dalloc(h, &T.sL, 12)); CK(cudaMemcpy(T.sL, sL, sizeof(sL), cudaMemcpyHostToDevice));
         }
-        elem_packet_kernel<<<(unsigned)T.nele, 128, 0, st>>>(T.nele, 12, nd, npd, T.Np, g.udof ? 12 + 12 * nd : -1, T.Rb, T.dR, nullptr, g.idxX, D->Lam + gs * nX, T.sL, costed ? 1 : 0, T.g, T.H);
-        h->launches++;
         if (costed) {
             ARG(T.epsm, "strain-gauge measurements of this step are not set (mb_xua_set_gauge_measurements)");
-            if (!T.J) { CK(dalloc(h, &T.J, T.nele * 48)); CK(dalloc(h, &T.e4, T.nele * 4)); CK(dalloc(h, &T.cost, T.nele)); }
+            if (!T.J) { CK(dalloc(h, &T.J, T.nele * 48)); CK(dalloc(h, &T.e4, T.nele * 4)); CK(dalloc(h, &T.cost, T.nele)); CK(dalloc(h, &T.gX, T.nele * 12)); CK(dalloc(h, &T.HXX, T.nele * 144)); }
             beam_gauge_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(gd, sd.X[0], T.J, T.e4);
-            gauge_cost_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(T.nele, T.ng, T.Np, T.G, T.epsm, T.epsm_per_element, T.isig2, T.J, T.e4, T.g, T.H, T.cost);
+            gauge_cost_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(T.nele, T.ng, T.G, T.epsm, T.epsm_per_element, T.isig2, T.J, T.e4, T.gX, T.HXX, T.cost);
             h->launches += 2;
         }
+        xua_device_packet(h, D, T, nullptr);
         T.has = true;
     }
     CK(cudaGetLastError());
@@ -926,7 +954,13 @@ int32_t mb_xua_get_packet(mb_handle* h, int32_t ieletyp, double* gradL, double* 
     XuaData* D = h->xua;
     ARG(ieletyp >= 1 && ieletyp <= (int)D->types.size() && D->types[(size_t)ieletyp - 1].g, "no packet for this element type");
     CK(cudaSetDevice(h->device));
-    const XuaType& T = D->types[(size_t)ieletyp - 1];
+    XuaType& T = D->types[(size_t)ieletyp - 1];
+    if (T.devgroup >= 0 && hessL) {                // a device type keeps no dense ∇²L (the reductions read its kernels' outputs): built here, from the last evaluated step
+        const int64_t nh = T.nele * T.Np * T.Np;
+        if (!T.H) { CK(dalloc(h, &T.H, nh)); CK(cudaMemsetAsync(T.H, 0, (size_t)nh * 8, h->stream)); }
+        xua_device_packet(h, D, T, T.H);
+        CK(cudaStreamSynchronize(h->stream));
+    }
     if (gradL) CK(cudaMemcpy(gradL, T.g, (size_t)(T.nele * T.Np) * 8, cudaMemcpyDeviceToHost));
     if (hessL) CK(cudaMemcpy(hessL, T.H, (size_t)(T.nele * T.Np * T.Np) * 8, cudaMemcpyDeviceToHost));
     return MB_OK;
