@@ -26,10 +26,6 @@ from .engine import Engine, _f64, _i64
 from .model import State, muscadeerror
 
 
-def _values(v):
-    return v.v if isinstance(v, D2) else np.asarray(v, float)
-
-
 def packets(et, ed, OX, OU, IA, Λ, X, U, A, t, SP=None, assembleA=False):
     """∇L (nele,Np), ∇²L (nele,Np,Np) of every element of type `et` at one state, in the order of partials Λ, X₀…, U₀…, A (src/DirectXUA.jl:127-135), scaled by
     revariate's scales — filled as the reference's addin! method for the type fills out (Acost :70-84, no_second_order :85-120, second order :152-171).

@@ -9,7 +9,6 @@ from oracle import elements as OE
 from oracle import pattern as OP
 
 import xua_models as XM
-from test_host_xua import _assemble_outs
 
 pytestmark = pytest.mark.gpu
 

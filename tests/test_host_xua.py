@@ -1,7 +1,6 @@
 """General DirectXUA path, CPU side: the host's dual numbers (adiff2.D2), the element packets (xua.packets) and the oracle's restatement of
 DirectXUA_lagrangian_addition! / assemblebig! are pinned to the numbers test/TestDirectXUA.jl holds (out of the last assembled step, :93-108; assembleA!, :67-76)."""
 import numpy as np
-import pytest
 
 import muscade_b200 as mb
 from muscade_b200 import xua

@@ -2,7 +2,7 @@
 import numpy as np
 
 import muscade_b200 as mb
-from muscade_b200.adiff2 import D2, exp10, sqrt, sin, cos
+from muscade_b200.adiff2 import exp10, sqrt, sin, cos
 
 
 class El1(mb.LagrangianElement):
