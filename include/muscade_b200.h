@@ -87,7 +87,8 @@ int32_t mb_set_ndofU(mb_handle* h, int64_t ndofU);
  * bit-identical to the reference: the class-pair patterns/maps of asmmat! for Λ,X,U and the CSC structure of the owned columns of Lvv
  * (SparseTools.prepare).  bcolptr/browval: CSC over BLOCKS of the owned block columns (3 per step: Λ,X,U), block row = 3·step+class, as
  * makepattern (src/DirectXUA.jl:245-307) yields — computed by the host wrapper, a few entries per step.
- * Element types must be EulerBeam3D (with or without Udof) in this version; IA = 0. */
+ * Device element types: EulerBeam3D, Bar3D (with or without Udof), SoilContact; host-evaluated X-class types and U/X costs merged (below).  This beam-specialised path is
+ * IA = 0, one experiment per handle; IA = 1, A-dofs and experiments coupled through A go through the general form (mb_xua_*, further down). */
 int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, int64_t ndofU, int64_t nstep, int64_t step_lo, int64_t step_hi,
                           double dt, const int32_t* bcolptr, const int32_t* browval, int64_t* ncol_out, int64_t* nnz_out);
 /* class-pair patterns: which = 0 X×X (also Λ×X, X×Λ), 1 X×U (Λ×U), 2 U×X (U×Λ), 3 U×U ; 1-based CSC like SparseMatrixCSC */

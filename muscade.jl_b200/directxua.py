@@ -1,4 +1,4 @@
-"""DirectXUA on the B200 engine (IA = 0, no_second_order element types): host-side mirror of
+"""DirectXUA on the B200 engine, beam-specialised path (IA = 0; xua.py is the general form with IA = 1, A-dofs, several experiments): host-side mirror of
 
   prepare(AssemblyDirect{OX,OU,IA})     src/DirectXUA.jl:22-56    → class-pair patterns / maps built on the device
   makepattern / preparebig              src/DirectXUA.jl:245-315  → block pattern here (a few entries per step), Lvv structure on the device
