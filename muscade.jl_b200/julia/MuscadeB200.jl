@@ -436,15 +436,18 @@ mutable struct AssemblyXUAB200{OX,OU,IA} <: Assembly
     devtyp :: Dict{Int,Any}
 end
 """
-    QuadraticGaugeCost(σ,εₘ)  — the strain cost the device evaluates:  cost(eleres,t) = Δε⋅Δε/(2σ²), Δε = eleres.ε − εₘ(t)  (test/TestBeamElementStrainGauge.jl:90-97)
+The strain cost the device evaluates, declared in the input script with Muscade's own macro so that it is a `Functor` (src/Functors.jl:23-30), e.g.
+
+    @functor with(σ=15e-6, εₘ=measured) QuadraticGaugeCost(eleres,t) = (Δε = eleres.ε - εₘ(t); (Δε ⋅ Δε)/(2σ^2))        # test/TestBeamElementStrainGauge.jl:90-97
+
+`devicebeam` recognises an `ElementCost` whose cost is a `Functor{:QuadraticGaugeCost}` and reads σ and εₘ from what it captured.
 """
-struct QuadraticGaugeCost{F} <: Muscade.Functor{:QuadraticGaugeCost} ; σ::𝕣 ; εₘ::F end
-(c::QuadraticGaugeCost)(eleres, t) = (Δε = eleres.ε - c.εₘ(t); (Δε ⋅ Δε) / (2c.σ^2))
+const GaugeCostFunctor = Muscade.Functor{:QuadraticGaugeCost}
 "which element types the device kernels evaluate inside the general form, and how to reach the wrapped beam"
 devicebeam(::Type) = nothing
 devicebeam(::Type{<:Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection}}) = (unwrap = identity, gauge = nothing)
-devicebeam(::Type{<:Muscade.ElementCost{<:Muscade.Toolbox.StrainGaugeOnEulerBeam3D{N,<:Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection}},R,<:QuadraticGaugeCost}}) where {N,R} =
-    (unwrap = o -> o.eleobj.eleobj, gauge = o -> (E = o.eleobj.E, K1 = o.eleobj.K1, K2 = o.eleobj.K2, K3 = o.eleobj.K3, σ = o.cost.σ, εₘ = o.cost.εₘ))
+devicebeam(::Type{<:Muscade.ElementCost{<:Muscade.Toolbox.StrainGaugeOnEulerBeam3D{N,<:Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection}},R,<:GaugeCostFunctor}}) where {N,R} =
+    (unwrap = o -> o.eleobj.eleobj, gauge = o -> (E = o.eleobj.E, K1 = o.eleobj.K1, K2 = o.eleobj.K2, K3 = o.eleobj.K3, σ = o.cost.captured.σ, εₘ = o.cost.captured.εₘ))
 function Muscade.prepare(::Type{AssemblyXUAB200{OX,OU,IA}}, model, dis; nstep::Vector{Int64}, Δt::Vector{𝕣}, device=0,
                          Xwhite=false, XUindep=false, UAindep=false, XAindep=false) where {OX,OU,IA}
     href = Ref{Ptr{Cvoid}}()
