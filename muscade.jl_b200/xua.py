@@ -120,6 +120,18 @@ def packets(et, ed, OX, OU, IA, Λ, X, U, A, t, SP=None, assembleA=False):
     return g, H
 
 
+def shard_steps(nstep, rank, world):
+    """time shards of the general form: the (iexp, istep) pairs (0-based) rank `rank` of `world` evaluates — the steps of all experiments, flattened, dealt round-robin
+    (every rank gets steps of every part of the time axis: the end-of-series stencils cost the same as interior ones, so no balancing is needed beyond the count)"""
+    out, k = [], 0
+    for iexp, n in enumerate(nstep):
+        for istep in range(n):
+            if k % world == rank:
+                out.append((iexp, istep))
+            k += 1
+    return out
+
+
 class XUAEngine(Engine):
     """Engine + the mb_xua_* entry points"""
 
@@ -289,12 +301,8 @@ class XUAEngine(Engine):
         self.zero()
         if self.IA == 1 and rank == 0:
             self.assembleA(states[0][0], SP)
-        k = 0
-        for iexp in range(self.nexp):
-            for istep in range(self.nstep[iexp]):
-                if k % world == rank:
-                    self.assemble_step(iexp + 1, istep + 1, states[iexp][istep], SP)
-                k += 1
+        for iexp, istep in shard_steps(self.nstep, rank, world):
+            self.assemble_step(iexp + 1, istep + 1, states[iexp][istep], SP)
         check(self.h, self.L.mb_xua_allreduce_big(self.h))
 
     def big(self):

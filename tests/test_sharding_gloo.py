@@ -109,3 +109,54 @@ def test_directxua_window_plan(mb):
                 assert len(windows) - len(interior) <= (rank == 0) + (rank == world - 1)
                 seen += [s for lo, hi in windows for s in range(lo, hi)]
             assert seen == list(range(nstep))
+
+
+XUA_WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+    import torch, torch.distributed as dist
+    import muscade_b200 as mb
+    from muscade_b200 import xua
+    from oracle import pattern as OP
+    import xua_models as XM
+    from test_host_xua import _assemble_outs
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.default_rng(5)                       # the same model and states on every rank
+    OX, OU, IA, nsteps, dts = 2, 0, 1, [6, 7], [1., 0.5]
+    m = XM.model_testdirectxua(); s0 = mb.initialize(m); dis = s0.dis
+    st = s0.with_orders(1, OX + 1, OU + 1)
+    A = rng.normal(0, 0.1, st.A.shape)
+    states = [[mb.State(3. + dt * k, [rng.normal(0, .3, v.shape) for v in st.Λ], [rng.normal(0, .3, v.shape) for v in st.X], [rng.normal(0, .3, v.shape) for v in st.U], A, None, m, dis)
+               for k in range(n)] for n, dt in zip(nsteps, dts)]
+    P = OP.prepare_direct(XM.dis_lists(dis), 2, 4, 6, OX, OU, IA)
+    big, basm, pgr, _ = OP.preparebig(IA, nsteps, P["nL2"], P["pat"])
+    outA, outs = _assemble_outs(m, dis, P, OX, OU, IA, states)
+    nz_full, Lv_full = OP.assemblebig_general(IA, nsteps, dts, P, big, basm, pgr, outA, outs)
+    # my share: the outs of the other ranks' steps (and, off rank 0, of assembleA!) zeroed — what XUAEngine.assemblebig_sharded adds on this rank
+    mine = set(xua.shard_steps(nsteps, rank, world))
+    zero = OP.out_zeros(P)
+    outs_r = [[o if (ie, k) in mine else zero for k, o in enumerate(row)] for ie, row in enumerate(outs)]
+    nz, Lv = OP.assemblebig_general(IA, nsteps, dts, P, big, basm, pgr, outA if rank == 0 else zero, outs_r)
+    tnz, tLv = torch.from_numpy(nz), torch.from_numpy(Lv)
+    dist.all_reduce(tnz); dist.all_reduce(tLv)            # mb_xua_allreduce_big
+    ok = np.abs(tnz.numpy() - nz_full).max() <= 1e-14 * np.abs(nz_full).max() and np.abs(tLv.numpy() - Lv_full).max() <= 1e-14 * np.abs(nz_full).max()
+    cnt = torch.tensor([len(mine)]); dist.all_reduce(cnt)
+    ok &= cnt.item() == sum(nsteps)
+    flag = torch.tensor([1 if ok else 0]); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("XUA_SHARD_OK" if flag.item() == 1 else "XUA_SHARD_FAIL")
+    dist.destroy_process_group()
+''')
+
+
+def test_general_form_time_shards_world2(tmp_path):
+    """XUAEngine.assemblebig_sharded on two ranks, with the oracle in place of the device: each rank's share of the steps (the A step on rank 0) summed by all_reduce is the
+    whole assemblebig! (IA = 1, two experiments) — the plan mb_xua_allreduce_big rests on"""
+    script = tmp_path / "xua_worker.py"
+    script.write_text(XUA_WORKER % (ROOT, ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29733", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert "XUA_SHARD_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
