@@ -130,6 +130,13 @@ int32_t mb_direct_set_host_elements(mb_handle* h, int64_t step, int32_t ieletyp,
  * L2[X,X][1,1](i,j) += Σₖ Λₖ·∂²Rₖ/∂Xᵢ∂Xⱼ·scale.Xᵢ·scale.Xⱼ as triplets (1-based model X dofs), one per (i,j) — the caller sums its elements in element order.
  * Replaces what was set for this step; n = 0 clears. Merged into the (step,step) X-X block of Lvv by mb_direct_assemble. */
 int32_t mb_direct_set_host_xx(mb_handle* h, int64_t step, int64_t n, const int64_t* i, const int64_t* j, const double* v);
+/* ElementCost{StrainGaugeOnEulerBeam3D} with cost(eleres,t) = Σ_g (ε_g − εm_g(t))²/(2σ²) on an EulerBeam3D type of this (windowed) path — the accelerator
+ * addin!(…,eleobj::ElementCost,…) of src/DirectXUA.jl:172-198 as it is meant (L = Λ∘₁R + cost, first-order R and eleres; see mb_xua_set_gauge_cost for the general form).
+ * mb_direct_set_gauge_cost: between mb_add_eulerbeam3d and mb_direct_prepare; G [ngauge][4] with ε_g = G[g]·(εₐₓ,κ₁,κ₂,κ₃) (toolbox/StrainGaugeOnBeamElement.jl:70-76).
+ * mb_direct_set_gauge_measurements: measured strains of one stored step, [ngauge] for all elements or [nele][ngauge] (per_element, fixed by the first call); they are
+ * kept per stored step and move with mb_direct_rebase.  A costed type is evaluated one time step per launch set. */
+int32_t mb_direct_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma);
+int32_t mb_direct_set_gauge_measurements(mb_handle* h, int64_t step, int32_t ieletyp, const double* epsm, int32_t per_element);
 int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out);
 int32_t mb_direct_get_sparse(mb_handle* h, int64_t* colptr, int64_t* rowval, double* nzval);
 int32_t mb_direct_set_lambda(mb_handle* h, int64_t step, const double* Lambda);

@@ -79,6 +79,8 @@ SYMBOLS = {
     "mb_direct_big_pattern": (C.c_int32, [H, C.c_void_p, C.c_void_p]),
     "mb_direct_get_step_block": (C.c_int32, [H, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mb_direct_set_host_xx": (C.c_int32, [H, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_direct_set_gauge_cost": (C.c_int32, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_double]),
+    "mb_direct_set_gauge_measurements": (C.c_int32, [H, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
     "mb_direct_rebase": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_int64)]),
     "mb_direct_step_ptrs": (C.c_int32, [H, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

@@ -12,6 +12,7 @@
 #include "mb_internal.h"
 #include <cub/cub.cuh>
 #include "pattern_build.cuh"
+#include "gauge_kernels.cuh"
 
 namespace mb {
 template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStateDev& st, double* dR, double* R, unsigned long long* nanflag,
@@ -27,7 +28,8 @@ namespace {
 enum { P_XX = 0, P_XU = 1, P_UX = 2, P_UU = 3 };
 
 constexpr int MAXG = 32;    // element types of one model on the DirectXUA path (the SCR riser of configs[4] has 11)
-struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; int64_t gxbase[MAXG]; };
+struct DirGroups { int n; uint32_t pbase[P_UU + 1][MAXG + 1]; int64_t drbase[MAXG]; int64_t rbase[MAXG]; int np[MAXG]; int udof[MAXG]; int nx[MAXG]; int64_t gxbase[MAXG];
+                   int64_t hxxbase[MAXG]; };      // hxxbase: first element of a COSTED beam type in the strain-gauge scratch (gX [e][12], HXX [e][144], GU [e][3]), −1 otherwise
 
 // ---------------------------------------------------------------------------------------------------------------- per-step gathers
 __device__ __forceinline__ int find_group(const uint32_t* pbase, int n, uint32_t id) {
@@ -112,6 +114,55 @@ __global__ void vstart2_kernel(int64_t nvec, const uint32_t* __restrict__ keys, 
     if (s == nvec - 1) for (int64_t c = d + 1; c <= ndof; ++c) vstart[c] = (uint32_t)nvec;
 }
 
+// ---------------------------------------------------------------------------------------------------------------- ElementCost{StrainGaugeOnEulerBeam3D} on this path
+// A costed beam type takes the accelerator's route (src/DirectXUA.jl:172-198 as it is meant, see mb_xua.cu): L = Λ∘₁R + cost with first-order R.  From the outputs of the
+// first-order kernels (R unscaled, dR[e][p][i] with scaled seeds) of ONE element per CTA:
+//   GX[(e·12+i)·nd+d] = Σₖ Λₖ·∂Rₖ/∂X_d,i (+ ∇cost_i for d = 0) → L1[X][d+1];   GU[e][j] = Σₖ Λₖ·∂Rₖ/∂U_j → L1[U][1];   then R and the rows of dR are scaled by scale.Λ
+// (DirectXUA_lagrangian_addition! differentiates with respect to the scaled Λ), so that the reductions of the plain path give L1[Λ], L2[Λ,X], L2[X,Λ], L2[Λ,U], L2[U,Λ].
+struct SL12 { double v[12]; };
+__global__ void __launch_bounds__(128) costed_fill_kernel(int64_t nele, int nd, int npd, const int32_t* __restrict__ idxX, const double* __restrict__ Lam, SL12 sL,
+                                                          const double* __restrict__ gX, double* __restrict__ R, double* __restrict__ dR, double* __restrict__ GX, double* __restrict__ GU) {
+    __shared__ double sm[39 * 12];
+    __shared__ double lam[12], sl[12];
+    const int64_t e = blockIdx.x;
+    const int n = npd * 12;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) sm[q] = dR[e * n + q];
+    if (threadIdx.x < 12) { lam[threadIdx.x] = Lam[idxX[e * 12 + threadIdx.x]]; sl[threadIdx.x] = sL.v[threadIdx.x]; }
+    __syncthreads();
+    if ((int)threadIdx.x < npd) {
+        const int p = threadIdx.x;
+        double acc = 0.;
+        for (int k = 0; k < 12; ++k) acc += lam[k] * sm[p * 12 + k];
+        if (p < 12 * nd) { const int d = p / 12, i = p - 12 * d; GX[(e * 12 + i) * nd + d] = acc + (d == 0 ? gX[e * 12 + i] : 0.); }
+        else if (GU) GU[e * 3 + (p - 12 * nd)] = acc;
+    }
+    for (int q = threadIdx.x; q < n; q += blockDim.x) dR[e * n + q] = sm[q] * sl[q % 12];
+    if (threadIdx.x < 12) R[e * 12 + threadIdx.x] *= sl[threadIdx.x];
+}
+// L2[X,X][1,1] of one step from the costs' Gauss-Newton blocks HXX[e][12][12] (costed beam types only; the reference's accumulation order over the X-X pattern)
+__global__ void gather_xxc_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, const double* __restrict__ HXX, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    double a = 0.;
+    for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
+        const uint32_t id = src[s];
+        const int g = find_group(G.pbase[P_XX], G.n, id);
+        if (G.hxxbase[g] < 0) continue;
+        const uint32_t loc = id - G.pbase[P_XX][g];
+        const int64_t e = loc / 144; const int r = (int)(loc - e * 144); const int jj = r / 12, i = r - 12 * jj;
+        a += HXX[(G.hxxbase[g] + e) * 144 + jj * 12 + i];
+    }
+    out[k] = a;
+}
+// L1[U][1] of one step: contributors GU[q] of every U-dof of the costed types
+__global__ void gather_l1u_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ GU, double* __restrict__ out) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof) return;
+    double acc = 0.;
+    for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) acc += GU[vsrc[s]];
+    out[d] = acc;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- all-steps system
 struct BigDev {
     int64_t nX, nU, W;             // W = 2nX+nU rows per step
@@ -127,6 +178,7 @@ struct BigDev {
     const double* hostc;           // host-evaluated single-dof costs per stored step: gX(nX) hX(nX) gU(nU) hU(nU), or nullptr
     const double* L1X;             // L1[X][der] per stored step [step][der][nX] from second-order element types, or nullptr
     int64_t ehi;
+    const double *XXc, *L1U;       // costed beam types: L2[X,X][1,1] per stored step [step][nnz(X,X)], L1[U][1] per stored step [step][nU]; or nullptr
 };
 __device__ __forceinline__ int pat_of(int ca, int cb) { return (ca == 2 ? 2 : 0) + (cb == 2 ? 1 : 0); }   // class 2 = U
 __device__ __forceinline__ void decode_col(const BigDev& B, int64_t c, int64_t& step, int& cls, int64_t& lc) {
@@ -169,6 +221,7 @@ __global__ void big_fill_kernel(BigDev B, int64_t ncol, const int64_t* __restric
             const double* arr = nullptr; int64_t stride = 0, s = 0, t = 0; int nder = 0; int64_t nnzp = B.pnnz[p];
             if (ca == 0 && cb != 0) { s = trow; t = tcol; if (cb == 1) { arr = B.LX; stride = B.sLX; nder = B.OX + 1; } else { arr = B.LU; stride = B.sLU; nder = 1; } }
             else if (cb == 0 && ca != 0) { s = tcol; t = trow; if (ca == 1) { arr = B.XL; stride = B.sLX; nder = B.OX + 1; } else { arr = B.UL; stride = B.sUL; nder = 1; } }
+            else if (ca == 1 && cb == 1 && trow == tcol && B.XXc) { s = tcol; t = tcol; arr = B.XXc; stride = nnzp; nder = 1; }      // the costs' L2[X,X][1,1] of that step
             double wd[3]; bool on[3] = {false, false, false};
             double sc = 1.;
             for (int der = 0; der < nder; ++der) { double w = 0.; on[der] = fd_weight(der, B.nstep, s, t - s, w); wd[der] = w * sc; sc /= B.dt; }
@@ -218,6 +271,7 @@ __global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t
         const double* arr = nullptr; int64_t stride = 0, s = 0, t = 0;
         if (ca == 0 && cb != 0) { s = trow; t = tcol; if (cb == 1) { arr = B.LX; stride = B.sLX; d.nder = B.OX + 1; } else { arr = B.LU; stride = B.sLU; d.nder = 1; } }
         else if (cb == 0 && ca != 0) { s = tcol; t = trow; if (ca == 1) { arr = B.XL; stride = B.sLX; d.nder = B.OX + 1; } else { arr = B.UL; stride = B.sUL; d.nder = 1; } }
+        else if (ca == 1 && cb == 1 && trow == tcol && B.XXc) { s = tcol; t = tcol; arr = B.XXc; stride = d.nnzp; d.nder = 1; }      // the costs' L2[X,X][1,1] of that step
         double sc = 1.;
         for (int der = 0; der < d.nder; ++der) { double w = 0.; const bool on = fd_weight(der, B.nstep, s, t - s, w); d.wd[der] = on ? w * sc : 0.; sc /= B.dt; }
         if (arr) d.a = arr + (s - B.elo) * stride;
@@ -309,6 +363,7 @@ __global__ void big_vec_kernel(BigDev B, int64_t ncol, double* __restrict__ Lv) 
             }
             v = (B.hostc ? v : 0.) + acc;
         }
+        if (cls == 2 && B.L1U) v += B.L1U[(step - B.elo) * B.nU + lc];      // Λᵀ∂R/∂U of the costed types
     }
     Lv[c] = v;
 }
@@ -412,6 +467,14 @@ struct DirectData {
     int64_t *colptr = nullptr, *rowval = nullptr;       // rowval: global rows of the window the structure was BUILT for; + rowshift after mb_direct_rebase
     int64_t rowshift = 0;
     bool elements_only = false;                         // timing aid: direct_eval_steps launches the element kernels without the per-step reductions
+    // costed beam types (mb_direct_set_gauge_cost): per stored step L2[X,X][1,1] and L1[U][1]; scratch of one step (J, e4, gX, HXX, GU, costs); U-dof contributor lists;
+    // per type the measurements of every stored step [step][ng] or [step][nele][ng]
+    bool costed = false; int64_t ncost = 0;
+    double *XXc = nullptr, *L1U = nullptr, *cJ = nullptr, *ce4 = nullptr, *cgX = nullptr, *cHXX = nullptr, *cGU = nullptr, *ccost = nullptr, *csL = nullptr;
+    uint32_t *vstartU = nullptr, *vsrcU = nullptr;
+    struct Meas { double* eps = nullptr; int64_t stride = 0; bool per_element = false; std::vector<char> have; };
+    std::map<int, Meas> meas;
+    std::vector<int64_t> gubase;                        // first entry of a costed type with U-dofs in cGU, −1 otherwise
     double *nzval = nullptr, *Lv = nullptr;
 };
 
@@ -421,6 +484,8 @@ static int32_t build_pattern(mb_handle* h, PairPat& P, bool rowU, bool colU, int
     return build_pair_pattern(h, P, rows, cols, nrows, ncols);
 }
 
+// element types that contribute to L1[X][der]: the second-order branch (SoilContact, host-evaluated) and costed beams (Λᵀ∂R/∂X + ∇cost)
+static inline bool has_gx(const Group& g) { return g.kind == G_SOIL || g.kind == G_HOST || (g.kind == G_BEAM && g.ng > 0); }
 static BigDev make_bigdev(const DirectData* D) {
     BigDev B;
     B.nX = D->nX; B.nU = D->nU; B.W = 2 * D->nX + D->nU; B.nstep = D->nstep; B.lo = D->lo; B.hi = D->hi; B.elo = D->elo; B.OX = D->OX; B.OU = D->OU; B.dt = D->dt;
@@ -429,6 +494,7 @@ static BigDev make_bigdev(const DirectData* D) {
     B.LX = D->LX; B.XL = D->XL; B.LU = D->LU; B.UL = D->UL; B.L1L = D->L1L;
     B.sLX = (int64_t)(D->OX + 1) * D->pat[P_XX].nnz; B.sLU = D->pat[P_XU].nnz; B.sUL = D->pat[P_UX].nnz;
     B.hostc = D->hostc; B.L1X = D->L1X; B.ehi = D->ehi;
+    B.XXc = D->XXc; B.L1U = D->L1U;
     return B;
 }
 
@@ -492,7 +558,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     // second-order element types (SoilContact): contributor lists of their element dofs for L1[X][der]
     {
         int64_t nq = 0;
-        for (size_t ig = 0; ig < h->groups.size(); ++ig) { D->G.gxbase[ig] = nq; if (h->groups[ig].kind == G_SOIL || h->groups[ig].kind == G_HOST) nq += h->groups[ig].nele * h->groups[ig].nx; }
+        for (size_t ig = 0; ig < h->groups.size(); ++ig) { D->G.gxbase[ig] = nq; if (has_gx(h->groups[ig])) nq += h->groups[ig].nele * h->groups[ig].nx; }
         D->ngx = nq;
         if (nq > 0) {
             CK(dalloc(h, &D->vstart2, ndofX + 1)); CK(dalloc(h, &D->vsrc2, nq)); CK(dalloc(h, &D->GX, nq * (OX + 1)));
@@ -501,7 +567,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
             CK(dalloc(h, &keys, nq)); CK(dalloc(h, &keys2, nq)); CK(dalloc(h, &vals, nq));
             for (size_t ig = 0; ig < h->groups.size(); ++ig) {
                 const Group& g = h->groups[ig];
-                if ((g.kind != G_SOIL && g.kind != G_HOST) || g.nele == 0) continue;
+                if (!has_gx(g) || g.nele == 0) continue;
                 vec_keys_kernel<<<nblk(g.nele * g.nx, 256), 256, 0, st>>>(g.nele * g.nx, g.idxX, keys, vals, (uint32_t)D->G.gxbase[ig]);
                 h->launches++;
             }
@@ -531,6 +597,46 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
         want = std::min<int64_t>(std::min<int64_t>(want, cap), std::min<int64_t>(ns, 65535));
         if (const char* eb = getenv("MB_DIRECT_BATCH")) want = std::max<int64_t>(1, std::min<int64_t>(atoll(eb), std::min<int64_t>(ns, 65535)));
         D->batch = std::max<int64_t>(1, want); D->ndr = (ndr + 1) & ~int64_t(1); D->nvec = (nvec + 1) & ~int64_t(1);
+    }
+    // costed beam types (ElementCost accelerator): scratch of one step, contributor lists of their U-dofs, per-stored-step L2[X,X][1,1] and L1[U][1]; one step per launch set
+    {
+        int64_t nc = 0, nqu = 0;
+        D->gubase.assign(h->groups.size(), -1);
+        for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+            const Group& g = h->groups[ig];
+            D->G.hxxbase[ig] = -1;
+            if (g.kind != G_BEAM || g.ng == 0) continue;
+            D->G.hxxbase[ig] = nc; nc += g.nele;
+            if (g.udof) { D->gubase[ig] = nqu; nqu += g.nele * 3; }
+        }
+        D->ncost = nc; D->costed = nc > 0;
+        if (D->costed) {
+            D->batch = 1;
+            CK(dalloc(h, &D->cJ, nc * 48)); CK(dalloc(h, &D->ce4, nc * 4)); CK(dalloc(h, &D->cgX, nc * 12)); CK(dalloc(h, &D->cHXX, nc * 144)); CK(dalloc(h, &D->ccost, nc));
+            CK(dalloc(h, &D->XXc, ns * D->pat[P_XX].nnz)); CK(cudaMemsetAsync(D->XXc, 0, (size_t)(ns * D->pat[P_XX].nnz) * 8, st));
+            if (nqu > 0 && ndofU > 0) {
+                CK(dalloc(h, &D->cGU, nqu)); CK(dalloc(h, &D->L1U, ns * ndofU)); CK(cudaMemsetAsync(D->L1U, 0, (size_t)(ns * ndofU) * 8, st));
+                CK(dalloc(h, &D->vstartU, ndofU + 1)); CK(dalloc(h, &D->vsrcU, nqu));
+                CK(cudaMemsetAsync(D->vstartU, 0, (ndofU + 1) * sizeof(uint32_t), st));
+                uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
+                CK(dalloc(h, &keys, nqu)); CK(dalloc(h, &keys2, nqu)); CK(dalloc(h, &vals, nqu));
+                for (size_t ig = 0; ig < h->groups.size(); ++ig) {
+                    const Group& g = h->groups[ig];
+                    if (D->gubase[ig] < 0 || g.nele == 0) continue;
+                    vec_keys_kernel<<<nblk(g.nele * 3, 256), 256, 0, st>>>(g.nele * 3, g.idxU, keys, vals, (uint32_t)D->gubase[ig]);
+                    h->launches++;
+                }
+                int end_bit = 1; while (end_bit < 32 && ((uint64_t)ndofU >> end_bit)) ++end_bit;
+                void* tmp = nullptr; size_t tmpsz = 0;
+                CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpsz, keys, keys2, vals, D->vsrcU, nqu, 0, end_bit, st));
+                CK(cudaMalloc(&tmp, tmpsz ? tmpsz : 1));
+                CK(cub::DeviceRadixSort::SortPairs(tmp, tmpsz, keys, keys2, vals, D->vsrcU, nqu, 0, end_bit, st));
+                vstart2_kernel<<<nblk(nqu, 256), 256, 0, st>>>(nqu, keys2, ndofU, D->vstartU);
+                h->launches++;
+                CK(cudaStreamSynchronize(st)); cudaFree(tmp);
+                dfree(h, keys); dfree(h, keys2); dfree(h, vals);
+            }
+        }
     }
     CK(dalloc(h, &D->dR, D->ndr * D->batch)); CK(dalloc(h, &D->R, D->nvec * D->batch));
     if (D->ngx > 0 && D->batch > 1) { dfree(h, D->GX); CK(dalloc(h, &D->GX, ((D->ngx * (OX + 1) + 1) & ~int64_t(1)) * D->batch)); }
@@ -664,6 +770,19 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
             if (nd == 1) h->launches += launch_beam_direct<1>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
             else if (nd == 2) h->launches += launch_beam_direct<2>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
             else h->launches += launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
+            if (g.ng > 0) {                        // ElementCost accelerator: strains and their Jacobian, the cost's gradient and Gauss-Newton block, then the Lagrangian's own terms
+                auto mit = D->meas.find((int)ig);
+                ARG(mit != D->meas.end() && mit->second.eps && mit->second.have[(size_t)k], "strain-gauge measurements of a stored step are not set (mb_direct_set_gauge_measurements)");
+                const DirectData::Meas& m = mit->second;
+                const int64_t eb = D->G.hxxbase[ig];
+                beam_gauge_kernel<<<nblk(g.nele * 12, 128), 128, 0, st>>>(gd, sd.X[0], D->cJ + eb * 48, D->ce4 + eb * 4);
+                gauge_cost_kernel<<<nblk(g.nele * 12, 128), 128, 0, st>>>(g.nele, g.ng, g.gaugeG, m.eps + k * m.stride, m.per_element, g.isig2, D->cJ + eb * 48, D->ce4 + eb * 4,
+                                                                          D->cgX + eb * 12, D->cHXX + eb * 144, D->ccost + eb);
+                SL12 sl; for (int i = 0; i < 12; ++i) sl.v[i] = g.scaleX[i] * D->lamscale;
+                costed_fill_kernel<<<(unsigned)g.nele, 128, 0, st>>>(g.nele, nd, D->G.np[ig], g.idxX, D->Lam + k * D->nX, sl, D->cgX + eb * 12, R, dR, D->GX + D->G.gxbase[ig] * nd,
+                                                                     D->gubase[ig] >= 0 && D->cGU ? D->cGU + D->gubase[ig] : nullptr);
+                h->launches += 3;
+            }
         }
         if (D->elements_only) continue;
         const PairPat& XX = D->pat[P_XX];
@@ -675,10 +794,50 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         gather_l1_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX, nvec);
         h->launches++;
         if (D->ngx) { gather_l1x_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart2, D->vsrc2, D->GX, nd, D->L1X + k * nd * D->nX, ngxd); h->launches++; }
+        if (D->costed) {
+            if (XX.nnz) { gather_xxc_kernel<<<nblk(XX.nnz, 256), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, D->cHXX, D->XXc + k * XX.nnz); h->launches++; }
+            if (D->L1U) { gather_l1u_kernel<<<nblk(D->nU, 256), 256, 0, st>>>(D->nU, D->vstartU, D->vsrcU, D->cGU, D->L1U + k * D->nU); h->launches++; }
+        }
     }
     return MB_OK;
 }
 
+/* ElementCost{StrainGaugeOnEulerBeam3D} with cost(eleres,t) = Σ_g (ε_g − εm_g(t))²/(2σ²) on a beam type of the windowed path (the accelerator of src/DirectXUA.jl:172-198 as it is
+ * meant, see mb_xua_set_gauge_cost): call between mb_add_eulerbeam3d and mb_direct_prepare.  G [ngauge][4]: ε_g = G[g]·(εₐₓ, κ₁, κ₂, κ₃) (toolbox/StrainGaugeOnBeamElement.jl:70-76). */
+int32_t mb_direct_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma) {
+    if (!h) return MB_ERR_ARG;
+    ARG(!h->prepared && !h->direct, "set the gauge cost before mb_direct_prepare");
+    ARG(ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size() && h->groups[(size_t)ieletyp - 1].kind == G_BEAM, "not an EulerBeam3D element type");
+    ARG(ngauge >= 1 && ngauge <= 64 && G && sigma > 0., "bad gauge data");
+    CK(cudaSetDevice(h->device));
+    Group& g = h->groups[(size_t)ieletyp - 1];
+    if (g.gaugeG) dfree(h, g.gaugeG);
+    g.ng = ngauge; g.isig2 = 1. / (sigma * sigma);
+    CK(dalloc(h, &g.gaugeG, (int64_t)ngauge * 4));
+    CK(cudaMemcpy(g.gaugeG, G, (size_t)ngauge * 4 * 8, cudaMemcpyDefault));
+    return MB_OK;
+}
+/* Measured strains of one stored step: epsm [ngauge] shared by all elements of the type, or [nele][ngauge] (per_element; the choice is fixed by the first call).
+ * Kept per stored step (they move with mb_direct_rebase), to be set once for every step of a window before mb_direct_assemble. */
+int32_t mb_direct_set_gauge_measurements(mb_handle* h, int64_t step, int32_t ieletyp, const double* epsm, int32_t per_element) {
+    if (!h || !h->direct) return MB_ERR_ARG;
+    DirectData* D = h->direct;
+    ARG(ieletyp >= 1 && ieletyp <= (int32_t)h->groups.size() && h->groups[(size_t)ieletyp - 1].ng > 0 && epsm, "set the gauge cost of this element type first (mb_direct_set_gauge_cost)");
+    ARG(step >= D->elo && step < D->ehi, "step not stored on this handle");
+    CK(cudaSetDevice(h->device));
+    const Group& g = h->groups[(size_t)ieletyp - 1];
+    DirectData::Meas& m = D->meas[ieletyp - 1];
+    const int64_t ns = D->ehi - D->elo;
+    if (!m.eps) {
+        m.per_element = per_element != 0; m.stride = (int64_t)g.ng * (m.per_element ? std::max<int64_t>(g.nele, 1) : 1);
+        CK(dalloc(h, &m.eps, ns * m.stride)); m.have.assign((size_t)ns, 0);
+    }
+    ARG(m.per_element == (per_element != 0), "per_element differs from the first call for this element type");
+    CK(cudaMemcpyAsync(m.eps + (step - D->elo) * m.stride, epsm, (size_t)m.stride * 8, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    m.have[(size_t)(step - D->elo)] = 1;
+    return MB_OK;
+}
 int32_t mb_direct_set_lambda_scale(mb_handle* h, double lambda_scale) {
     if (!h || !h->direct) return MB_ERR_ARG;
     h->direct->lamscale = lambda_scale;
@@ -986,6 +1145,13 @@ int32_t mb_direct_rebase(mb_handle* h, int64_t new_lo, int64_t* row_shift_out) {
         const Group& g = h->groups[ig];
         const int64_t nR = g.nele * g.nx;
         arrs.push_back({D->hoststore[ig], nR + nR * g.nx * nd + nR * nd});
+    }
+    arrs.push_back({D->XXc, D->pat[P_XX].nnz}); arrs.push_back({D->L1U, D->nU});
+    for (auto& kv : D->meas) {
+        arrs.push_back({kv.second.eps, kv.second.stride});
+        std::vector<char> hv((size_t)ns, 0);
+        for (int64_t k = 0; k < ns; ++k) if (k + delta >= 0 && k + delta < ns) hv[(size_t)k] = kv.second.have[(size_t)(k + delta)];
+        kv.second.have.swap(hv);
     }
     const int64_t k0 = delta > 0 ? delta : 0, k1 = delta > 0 ? ns : ns + delta;      // old slots that stay stored
     for (const Arr& a : arrs) {

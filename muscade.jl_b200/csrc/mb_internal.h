@@ -35,6 +35,8 @@ struct Group {
     int64_t pair_base = 0;       // offset of this group's nx²·nele tangent entries in Ke_all
     int64_t vec_base = 0;        // offset of this group's nx·nele residual entries in Re_all
     int64_t maxX = 0, maxU = 0;  // largest 1-based dof numbers of the group (checked against ndofX / ndofU at prepare)
+    // ElementCost{StrainGaugeOnEulerBeam3D} with the quadratic strain cost on this beam type, DirectXUA (mb_direct_set_gauge_cost): gauge matrix [ng][4] on the device, 1/σ²
+    int ng = 0; double* gaugeG = nullptr; double isig2 = 0.;
 };
 
 struct mb_handle {

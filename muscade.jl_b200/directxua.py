@@ -143,6 +143,18 @@ class DirectEngine(Engine):
         i = np.ascontiguousarray(i, np.int64); j = np.ascontiguousarray(j, np.int64); v = _f64(np.asarray(v, float))
         check(self.h, self.L.mb_direct_set_host_xx(self.h, int(step), len(i), ptr(i), ptr(j), ptr(v)))
 
+    def set_gauge_measurements(self, step, ityp, epsm):
+        """measured strains of one stored step for a costed beam type: (Ngauge,) for all elements or (nele,Ngauge)"""
+        em = np.ascontiguousarray(epsm, np.float64)
+        check(self.h, self.L.mb_direct_set_gauge_measurements(self.h, int(step), int(ityp), ptr(em), 1 if em.ndim == 2 else 0))
+
+    def set_gauge_times(self, time):
+        """measurements of every stored step from the costs' own measured(t) (time[k] = time of step k)"""
+        elo, ehi = self.stored_range()
+        for ityp, cost in self.gauge_costs:
+            for k in range(elo, ehi):
+                self.set_gauge_measurements(k, ityp, cost.measured(float(time[k])))
+
     def set_host_cost(self, step, gX=None, hX=None, gU=None, hU=None):
         check(self.h, self.L.mb_direct_set_host_cost(self.h, int(step), ptr(_f64(gX)), ptr(_f64(hX)), ptr(_f64(gU)), ptr(_f64(hU))))
 
@@ -204,10 +216,20 @@ def prepare(OX, OU, model, dis, nstep, dt, lo=0, hi=None, device=0, t0=0.):
     eng = DirectEngine(device)
     eng.host_costs = []
     eng.host_types = []
+    eng.gauge_costs = []                             # (ityp, QuadraticGaugeCost): ElementCost on strain-gauged beams, evaluated by the device
     for et, ed in zip(model.ele, dis.dis):
         udof = ed.U.shape[1] > 0
+        target = et.extra.get("target") if (et.ElType.kind == "elementcost" and isinstance(et.extra, dict)) else None
         if et.ElType.kind == "eulerbeam3d":
             eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+        elif target is not None and target.kind == "eulerbeam3d":
+            cost = et.extra["cost"]
+            if not (hasattr(cost, "sigma") and hasattr(cost, "measured") and "G" in et.extra and et.extra["req"] == ("ε",)):
+                muscadeerror("ElementCost on the device: ElementType = StrainGaugeOnEulerBeam3D, req = ('ε',), cost = QuadraticGaugeCost")
+            ityp = eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
+            G = np.ascontiguousarray(et.extra["G"], np.float64)
+            check(eng.h, eng.L.mb_direct_set_gauge_cost(eng.h, ityp, G.shape[0], ptr(G), float(cost.sigma)))
+            eng.gauge_costs.append((ityp, cost))
         elif et.ElType.kind == "bar3d":
             eng.add_bar3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
         elif et.ElType.kind == "soilcontact":
@@ -294,6 +316,7 @@ def solve(OX, OU, initialstate, time, maxiter=50, maxΔλ=1e-5, maxΔx=1e-5, max
         eng.set_dof_scale(dis.scaleΛ, dis.scaleX, dis.scaleU)
         maxΔ2 = np.array([maxΔλ, maxΔx, maxΔu]) ** 2
         Lv = np.zeros(eng.ncol)
+        eng.set_gauge_times(time)
         for it in range(1, maxiter + 1):
             if eng.host_costs or eng.host_types:
                 for k in range(nstep):

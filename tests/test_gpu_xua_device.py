@@ -207,3 +207,158 @@ class HoldD2(mb.LagrangianElement):
     def residual(o, extra, X, U, A, t, SP):
         x, lam = X[0][0], X[0][1]
         return [-lam, -x]
+
+
+@pytest.mark.parametrize("OX,per_element", [(0, False), (2, True), (1, False)])
+def test_gauge_cost_in_the_windowed_path_equals_general_form(mb, OX, per_element):
+    """ElementCost{StrainGaugeOnEulerBeam3D} on the beam-specialised, windowed path (mb_direct_set_gauge_cost: the costed beam's ∇L[X_d], ∇L[U], Gauss-Newton X₀-X₀ block and
+    scale.Λ-scaled Λ rows enter the block-implicit Lvv / Lv) against the general form (mb_xua_*, itself checked against the oracle and the reference's goldens above):
+    same structure, Lvv values and Lv within 1e-12, with random Λ, X, X′, X″, U, host-evaluated single-dof costs beside the gauges, non-unit scales."""
+    rng = np.random.default_rng(11)
+    n, nstep, dt = 9, 7, 0.25
+    m = mb.Model("gauged chain")
+    nod = mb.addnode(m, np.cumsum(rng.uniform(0.5, 1.5, (n + 1, 3)), axis=0))
+    un = np.array([mb.addnode(m, np.zeros(3)) for _ in range(n)])
+    nodes = np.concatenate([np.stack([nod[:-1], nod[1:]], axis=1), un[:, None]], axis=1)
+    tgt = rng.normal(0., 1e-3, (n, 5))
+    meas = (lambda t: tgt * np.cos(t)) if per_element else (lambda t: tgt[0] * np.cos(t))
+    cost = mb.QuadraticGaugeCost(2e-3, meas)
+    mb.addelement(m, mb.ElementCost, nodes, req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e3, EI2=30., EI3=20., GJ=40., mu=1.5, iota1=0.7, Ca2=0.1), orient2=(0., 1., 0.), Udof=True)))
+    mb.addelement(m, mb.SingleDofCost, nod[::3, None], clas="X", field="t2", cost=XM.l1)
+    mb.addelement(m, mb.SingleDofCost, un[:, None], clas="U", field="t1", cost=XM.fu)
+    mb.setscale(m, scale=dict(X=dict(t1=2., t2=2., t3=2., r1=0.5, r2=0.5, r3=0.5), U=dict(t1=3., t2=3., t3=3.)), Λscale=7.)
+    s0 = mb.initialize(m); dis = s0.dis
+    nX, nU = m.getndof("X"), m.getndof("U")
+    time = 1. + dt * np.arange(nstep)
+    st = s0.with_orders(1, OX + 1, 1)
+    states = [[mb.State(time[k], [rng.normal(0, 1., nX)], [rng.normal(0, 0.05, nX) for _ in range(OX + 1)], [rng.normal(0, 0.5, nU)], st.A, None, m, dis) for k in range(nstep)]]
+    spec = mb.directxua.prepare(OX, 0, m, dis, nstep, dt, t0=time[0])
+    gen = xua.XUAEngine(0)
+    try:
+        assert len(spec.gauge_costs) == 1
+        for k, s in enumerate(states[0]):
+            spec.set_state(k, s.X, s.U[0]); spec.set_lambda(k, s.Λ[0])
+            spec.set_host_cost(k, *mb.directxua.host_costs(spec, k, s.X[0], s.U[0], time[k])[:4])
+        spec.set_gauge_times(time)
+        Lvv = np.zeros(spec.nnzbig); Lv = np.zeros(spec.ncol)
+        spec.direct_assemble(Lvv=Lvv, Lv=Lv)
+        cp, rv = spec.big_pattern()
+        nbig, nnz = gen.prepare(m, dis, OX, 0, 0, [nstep], [dt])
+        assert nbig == spec.ncol and nnz == spec.nnzbig
+        gcp, grv = gen.big_pattern()
+        assert np.array_equal(cp, gcp) and np.array_equal(rv, grv)
+        gen.assemblebig(states)
+        gLvv, gLv = gen.big()
+        scale = np.abs(gLvv).max()
+        assert np.abs(gLvv - Lvv).max() <= 1e-12 * scale
+        assert np.abs(gLv - Lv).max() <= 1e-12 * max(scale, np.abs(gLv).max())
+        # the cost is really there: X-X entries of the (step,step) blocks and the U part of Lv are non-zero
+        W = 2 * nX + nU
+        import scipy.sparse as sp
+        A = sp.csc_matrix((Lvv, rv - 1, cp - 1), shape=(nbig, nbig)).tocsr()
+        assert abs(A[nX:2 * nX, nX:2 * nX]).max() > 0 and np.abs(Lv[2 * nX:W]).max() > 0
+    finally:
+        spec.close(); gen.close()
+
+
+def test_gauge_cost_windowed_path_errors(mb):
+    """argument errors of the two entry points: cost on a non-beam type, after prepare, measurements missing at assembly, per_element flipped"""
+    import ctypes as C
+    from muscade_b200._lib import ptr
+    m = costed_beam_model([[0., 0, 0], [4., 0, 0], [8., 0, 0]], [[0, 1], [1, 2]]); s0 = mb.initialize(m)
+    eng = mb.directxua.prepare(0, 0, m, s0.dis, 6, 0.1)
+    try:
+        G = np.zeros((5, 4))
+        assert eng.L.mb_direct_set_gauge_cost(eng.h, 1, 5, ptr(G), 1.) != 0                # already prepared
+        with pytest.raises(mb.MuscadeB200Error, match="measurements"):
+            eng.direct_assemble()
+        eng.set_gauge_measurements(0, 1, np.zeros(5))
+        with pytest.raises(mb.MuscadeB200Error, match="per_element"):
+            eng.set_gauge_measurements(1, 1, np.zeros((2, 5)))
+        with pytest.raises(mb.MuscadeB200Error):
+            eng.set_gauge_measurements(99, 1, np.zeros(5))
+    finally:
+        eng.close()
+
+
+def test_gauge_identification_through_the_windowed_solver(mb):
+    """solve(DirectXUA{0,0,0}) of the gauged cantilever through the beam-specialised path (directxua.solve) and through the general form (xua.solve): same converged states"""
+    n, nstep = 8, 6
+    coords = np.stack([np.linspace(0., 8., n + 1), np.zeros(n + 1), np.zeros(n + 1)], axis=1)
+    m = mb.Model("cantilever")
+    nod = mb.addnode(m, coords)
+    un = np.array([mb.addnode(m, np.zeros(3)) for _ in range(n)])
+    nodes = np.concatenate([np.stack([nod[:-1], nod[1:]], axis=1), un[:, None]], axis=1)
+    target = np.zeros((n, 5)); target[:, 1] = -2e-4 * (1 - np.arange(n) / n); target[:, 3] = -target[:, 1]
+    cost = mb.QuadraticGaugeCost(1e-5, lambda t: target * (1. + 0.2 * t))
+    mb.addelement(m, mb.ElementCost, nodes, req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e4, EI2=300., EI3=300., GJ=400., mu=1., iota1=1.), orient2=(0., 1., 0.), Udof=True)))
+    for f in ("t1", "t2", "t3", "r1", "r2", "r3"):
+        mb.addelement(m, mb.Hold, [nod[0]], field=f)
+    mb.addelement(m, mb.SingleDofCost, un[:, None], clas="U", field="t1", cost=lambda u, t: u ** 2 * 1e-2)
+    mb.addelement(m, mb.SingleDofCost, un[:, None], clas="U", field="t2", cost=lambda u, t: u ** 2 * 1e-2)
+    mb.addelement(m, mb.SingleDofCost, un[:, None], clas="U", field="t3", cost=lambda u, t: u ** 2 * 1e-6)
+    s0 = mb.initialize(m)
+    time = np.linspace(0., 1., nstep)
+    a = mb.directxua.solve(0, 0, s0, time, maxiter=30, maxΔλ=1e-3, maxΔx=1e-7, maxΔu=1e-5)
+    b = xua.solve(0, 0, 0, [s0], [time], maxiter=30, maxΔλ=1e-3, maxΔx=1e-7, maxΔu=1e-5)[0]
+    umax = max(np.abs(s.U[0]).max() for s in b)
+    assert umax > 1e-3
+    for sa, sb in zip(a, b):
+        assert np.abs(sa.X[0] - sb.X[0]).max() <= 1e-6 * max(np.abs(sb.X[0]).max(), 1e-6)
+        assert np.abs(sa.U[0] - sb.U[0]).max() <= 1e-6 * umax
+    assert np.abs(a[-1].U[0]).max() > 1.1 * np.abs(a[0].U[0]).max()          # the measurements grow with t, and so does the identified load
+
+
+def test_gauge_cost_sliding_window(mb):
+    """the costed beam type inside mb_direct_rebase's sliding window (how BASELINE.json configs[3]-sized gauged models run: the general form materialises all steps, the
+    windowed path does not): each window's Lvv columns / Lv rows equal the full general-form assembly; the per-step L2[X,X], L1[U] and the measurements move with the window."""
+    rng = np.random.default_rng(5)
+    n, nstep, dt, OX, L = 6, 24, 0.1, 2, 5
+    m = mb.Model("gauged chain")
+    nod = mb.addnode(m, np.cumsum(rng.uniform(0.5, 1.5, (n + 1, 3)), axis=0))
+    un = np.array([mb.addnode(m, np.zeros(3)) for _ in range(n)])
+    nodes = np.concatenate([np.stack([nod[:-1], nod[1:]], axis=1), un[:, None]], axis=1)
+    tgt = rng.normal(0., 1e-3, 5)
+    cost = mb.QuadraticGaugeCost(2e-3, lambda t: tgt * np.cos(t))
+    mb.addelement(m, mb.ElementCost, nodes, req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e3, EI2=30., EI3=20., GJ=40., mu=1.5, iota1=0.7), orient2=(0., 1., 0.), Udof=True)))
+    mb.setscale(m, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=3., t2=3., t3=3.)), Λscale=3.)
+    s0 = mb.initialize(m); dis = s0.dis
+    nX, nU = m.getndof("X"), m.getndof("U")
+    W = 2 * nX + nU
+    time = dt * np.arange(nstep)
+    st = s0.with_orders(1, OX + 1, 1)
+    states = [[mb.State(time[k], [rng.normal(0, 1., nX)], [rng.normal(0, 0.05, nX) for _ in range(OX + 1)], [rng.normal(0, 0.5, nU)], st.A, None, m, dis) for k in range(nstep)]]
+    gen = xua.XUAEngine(0)
+    spec = mb.directxua.prepare(OX, 0, m, dis, nstep, dt, 4, 4 + L)
+    try:
+        gen.prepare(m, dis, OX, 0, 0, [nstep], [dt])
+        gcp, grv = gen.big_pattern()
+        gen.assemblebig(states)
+        nz, Lv = gen.big()
+        stored = set()
+
+        def check(lo):
+            c0, c1 = lo * W, (lo + L) * W
+            p0, p1 = gcp[c0] - 1, gcp[c1] - 1
+            cp, rv = spec.big_pattern()
+            assert np.array_equal(cp - 1, gcp[c0:c1 + 1] - 1 - p0) and np.array_equal(rv, grv[p0:p1])
+            for k in range(lo - 2, lo + L + 2):
+                if k in stored:
+                    continue
+                s = states[0][k]
+                spec.set_state(k, s.X, s.U[0]); spec.set_lambda(k, s.Λ[0]); spec.set_gauge_measurements(k, 1, cost.measured(time[k]))
+                spec.direct_assemble(eval_range=(k, k + 1), build_big=False)
+            a = np.zeros(spec.nnzbig); b = np.zeros(spec.ncol)
+            spec.direct_assemble(eval_range=(lo, lo), build_big=True, Lvv=a, Lv=b)
+            assert np.abs(a - nz[p0:p1]).max() <= 1e-12 * np.abs(nz).max() and np.abs(b - Lv[c0:c1]).max() <= 1e-12 * max(np.abs(nz).max(), np.abs(Lv).max())
+            stored.clear(); stored.update(range(lo - 2, lo + L + 2))
+
+        check(4)
+        spec.rebase(4 + L); check(4 + L)
+        spec.rebase(12); check(12)             # forward, overlapping
+        spec.rebase(7); check(7)               # backward
+    finally:
+        spec.close(); gen.close()
