@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--window", type=int, default=10)             # directxua: time steps per Lvv window
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gauged", action="store_true")              # directxua: the beams carry 5 strain gauges each and a quadratic strain cost (ElementCost accelerator, windowed path)
     ap.add_argument("--no-directxua", action="store_true")        # skip the configs[3] block of the default line
     ap.add_argument("--dx-passes", type=int, default=2)           # timed passes of the configs[3] block (after 1 warm-up pass)
     ap.add_argument("--scr-nstep", type=int, default=4000)        # scr: time steps of BASELINE.json configs[4]
@@ -371,6 +372,20 @@ def directxua_model(mb, N):
     return model
 
 
+def gauged_chain_model(mb, N):
+    """the same chain with ElementCost{StrainGaugeOnEulerBeam3D} on every beam: 5 gauges (test/TestBeamElementStrainGauge.jl:10-11), quadratic strain cost"""
+    P5 = np.array([[0., .5, 0.], [0., 0, .5], [0., -.5, 0.], [0., 0, -.5], [0., .5, 0.]]).T
+    D5 = np.array([[1., 0., 0.], [1., 0., 0.], [1., 0., 0.], [1., 0., 0.], [1 / np.sqrt(2), 0, 1 / np.sqrt(2)]]).T
+    model = mb.Model("gauged")
+    nod = mb.addnode(model, np.arange(N + 1)[:, None] * np.array([.8, .6, 0.])[None, :])
+    unod = mb.addnode(model, np.zeros((N, 0)))
+    cost = mb.QuadraticGaugeCost(15e-6, lambda t: np.array([np.cos(t), 0., -np.cos(t), 0., np.cos(t) / 2]) * 0.001)
+    mat = mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1., Ca2=169.6, Ca3=169.6, Cq2=235.2, Cq3=235.2)
+    mb.addelement(model, mb.ElementCost, np.stack([nod[:-1], nod[1:], unod], axis=1), req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mat, Udof=True)))
+    return model, cost
+
+
 def cpu_port_rate_direct(mb, nsample):
     """oracle (literal reference algorithm, DirectXUA.jl:85-120 with Np = 39 partials) on one time step of `nsample` elements, 1 thread"""
     from oracle import elements as OE, pattern as OP
@@ -398,7 +413,12 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
     L, H, Wn, windows, interior = mb.sharding.directxua_windows(nstep, rank, world, args.window)
     torch.cuda.set_device(local)
     stream = torch.cuda.current_stream().cuda_stream
-    model = directxua_model(mb, N)
+    gauged = bool(getattr(args, "gauged", False)) and not block
+    gcost = None
+    if gauged:
+        model, gcost = gauged_chain_model(mb, N)
+    else:
+        model = directxua_model(mb, N)
     st0 = mb.initialize(model)
     nX, nU = model.getndof("X"), model.getndof("U")
     dtm = 0.1
@@ -420,11 +440,21 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
     devU = [torch.from_numpy(u).cuda() for u in hostU]
     nset = [0]
 
+    if gauged:                                         # Λ of every step and the measured strains of that step (5 numbers) go in with the state
+        import ctypes as C
+        hostL = [mb.synthetic.uniform_pm1(200 + b, nX) for b in range(B)]
+        devL = [torch.from_numpy(x).cuda() for x in hostL]
+
     def set_dev(e, s):
         e.set_state_dev(s, [x.data_ptr() for x in devX[s % B]], devU[s % B].data_ptr()); nset[0] += 1
+        if gauged:
+            mb._lib.check(e.h, e.L.mb_direct_set_lambda(e.h, int(s), C.c_void_p(devL[s % B].data_ptr())))
+            e.set_gauge_measurements(s, 1, gcost.measured(dtm * s))
 
     def set_host(e, s):
         e.set_state(s, hostX[s % B], hostU[s % B]); nset[0] += 1
+        if gauged:
+            e.set_lambda(s, hostL[s % B]); e.set_gauge_measurements(s, 1, gcost.measured(dtm * s))
 
     def one_pass(setter, Lv_host=None):
         """every window of this rank once: new states in, new steps evaluated, owned Lvv columns and Lv rows built"""
@@ -485,6 +515,8 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
         for arrs in hostX:
             for x in arrs: et.pin(x)
         for u in hostU: et.pin(u)
+        if gauged:
+            for x in hostL: et.pin(x)
         et.pin(Lvh)
         e_int_valid[0] = False; one_pass(set_host, Lvh)
         barrier()
@@ -496,7 +528,7 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
         nset_pass = nset[0] - n0
         e2e_ms = comm.max(e2e_ms)
         e2e = {"value": N * nstep / (e2e_ms * 1e-3), "unit": "element-step assemblies/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(nset_pass * 8 * (3 * nX + nU)), "d2h_bytes_per_step": int(len(windows) * 8 * et.ncol),
+               "h2d_bytes_per_step": int(nset_pass * 8 * (3 * nX + nU + ((nX + 5) if gauged else 0))), "d2h_bytes_per_step": int(len(windows) * 8 * et.ncol),
                "note": "per rank: mb_direct_set_state from pinned host memory for every newly stored step, mb_direct_assemble with a host Lv; "
                        "Lvv stays in HBM (device-pointer hand-off to the solver)"}
     line = None
@@ -537,6 +569,13 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
                 "cpu_baseline": {"value": cpu_rate, "unit": "element-step assemblies/s", "cores": 1, "kind": "port",
                                  "sample": "one time step of %d elements, oracle literal restatement (39 partials), 1 thread (%.1f s)" % (nsamp, cpu_dt)},
                 "breakdown_ms": {"window_elements_and_step_blocks": a_ms, "window_lvv_build": b_ms, "window_element_kernels": el_ms, "windows_per_rank": len(windows)}}
+        if gauged:
+            line["metric"] = "element-step assemblies/s (DirectXUA{2,0,0} assemblebig!, ElementCost{StrainGaugeOnEulerBeam3D} on every beam, windowed path)"
+            line["config"]["workload"] = line["config"]["workload"].replace("load identification,", "load identification from strain gauges (5 gauges per beam, quadratic strain cost: the "
+                                                                            "ElementCost accelerator in the windowed path, mb_direct_set_gauge_cost),")
+            line["config"]["states"] += "; Λ from a bank of the same size, measured strains set per step"
+            line["roofline"]["note"] = "flop counts are those of the plain beam kernels (the 3 strain-gauge launches per step are not counted): kernel_ms covers all 6 element launches per step"
+            line["cpu_baseline"] = None
         if block:
             for k in ("cpu_baseline", "e2e", "higher_is_better", "vs_baseline", "dtype", "data", "clocks"):
                 line.pop(k, None)

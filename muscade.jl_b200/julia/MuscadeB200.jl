@@ -198,6 +198,7 @@ mutable struct AssemblyDirectB200{OX,OU,IA} <: Assembly
     Lv       :: Vector{𝕣}
     hosttyp  :: Vector{Int}                       # X-class types evaluated by Muscade's own addin! on the host (Hold, DofLoad, DofConstraint{:X})
     costtyp  :: Vector{Int}                       # SingleDofCost types (user closures) → mb_direct_set_host_cost
+    gaugetyp :: Vector{Tuple{Int,Int32}}          # (ieletyp, device type) of ElementCost{StrainGaugeOnEulerBeam3D} types with a quadratic strain cost (devicebeam below)
 end
 
 # finitediff(order,n,s) (src/FiniteDifferences.jl:8-31) is Muscade's own; only the block pattern of the OWNED columns is needed here:
@@ -233,7 +234,7 @@ function Muscade.prepare(::Type{AssemblyDirectB200{OX,OU,0}}, model, dis; nstep,
     href = Ref{Ptr{Cvoid}}()
     check(C_NULL, ccall((:mb_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, href))
     h = href[]
-    hosttyp, costtyp = Int[], Int[]
+    hosttyp, costtyp, gaugetyp = Int[], Int[], Tuple{Int,Int32}[]
     for ieletyp = 1:getneletyp(model)
         eleobj, d, E = model.eleobj[ieletyp], dis.dis[ieletyp], eltype(model.eleobj[ieletyp])
         nx   = length(d.scale.X)
@@ -241,6 +242,19 @@ function Muscade.prepare(::Type{AssemblyDirectB200{OX,OU,0}}, model, dis; nstep,
         udof = length(d.scale.U) > 0
         idxU = udof ? [d.index[iele].U[i] for i = 1:length(d.scale.U), iele = 1:length(eleobj)] : Matrix{Int64}(undef, 0, 0)
         ityp = Ref{Int32}()
+        beam = devicebeam(E)
+        if !isnothing(beam) && !isnothing(beam.gauge)             # ElementCost accelerator inside the windowed path (src/DirectXUA.jl:172-198 as it is meant)
+            beams = beam.unwrap.(eleobj)
+            GC.@preserve beams idxX idxU check(h, ccall((:mb_add_eulerbeam3d, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+                h, length(beams), pointer(reinterpret(Float64, beams)), udof, idxX, udof ? pointer(idxU) : C_NULL,
+                collect(d.scale.X), udof ? collect(d.scale.U) : C_NULL, ityp))
+            g = beam.gauge(eleobj[1])
+            G = permutedims(hcat(g.E, g.K1, g.K2, g.K3))          # [Ngauge][4] row-major
+            check(h, ccall((:mb_direct_set_gauge_cost, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{𝕣}, 𝕣), h, ityp[], length(g.E), G, g.σ))
+            push!(gaugetyp, (ieletyp, ityp[]))
+            continue
+        end
         if E <: Muscade.Toolbox.EulerBeam3D{Muscade.Toolbox.BeamCrossSection} || E <: Muscade.Toolbox.Bar3D{Muscade.Toolbox.AxisymmetricBarCrossSection}
             f = E <: Muscade.Toolbox.EulerBeam3D ? :mb_add_eulerbeam3d : :mb_add_bar3d
             GC.@preserve eleobj idxX idxU check(h, ccall((f, LIB), Int32,
@@ -269,7 +283,7 @@ function Muscade.prepare(::Type{AssemblyDirectB200{OX,OU,0}}, model, dis; nstep,
     check(h, ccall((:mb_direct_set_time0, LIB), Int32, (Ptr{Cvoid}, 𝕣), h, t₀))
     check(h, ccall((:mb_direct_set_lambda_scale, LIB), Int32, (Ptr{Cvoid}, 𝕣), h, model.scaleΛ))
     check(h, ccall((:mb_direct_set_dof_scale, LIB), Int32, (Ptr{Cvoid}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}), h, dis.scaleΛ, dis.scaleX, dis.scaleU))
-    out = AssemblyDirectB200{OX,OU,0}(h, nstep, lo, hi, ncol[], nnz[], zeros(𝕣, ncol[]), hosttyp, costtyp)
+    out = AssemblyDirectB200{OX,OU,0}(h, nstep, lo, hi, ncol[], nnz[], zeros(𝕣, ncol[]), hosttyp, costtyp, gaugetyp)
     finalizer(o -> ccall((:mb_destroy, LIB), Int32, (Ptr{Cvoid},), o.h), out)
     dofgr = (Muscade.allΛdofs(model, dis), allXdofs(model, dis), Muscade.allUdofs(model, dis), Muscade.allAdofs(model, dis))
     return out, nothing, dofgr
@@ -283,6 +297,16 @@ function upload_states!(out::AssemblyDirectB200{OX,OU}, state::Vector) where {OX
             check(out.h, ccall((:mb_direct_set_state, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}, Ptr{𝕣}),
                 out.h, s, X[1], OX ≥ 1 ? pointer(X[2]) : C_NULL, OX ≥ 2 ? pointer(X[3]) : C_NULL, isempty(st.U[1]) ? C_NULL : pointer(st.U[1])))
             check(out.h, ccall((:mb_direct_set_lambda, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{𝕣}), out.h, s, st.Λ[1]))
+        end
+    end
+end
+"measured strains εₘ(t) of every stored step for the costed beam types (the functor's captured εₘ, evaluated at the step's time): once per solve, and after a rebase for the new steps"
+function upload_gauge_measurements!(out::AssemblyDirectB200, model, state::Vector)
+    for (ieletyp, ityp) ∈ out.gaugetyp
+        εₘ = devicebeam(eltype(model.eleobj[ieletyp])).gauge(model.eleobj[ieletyp][1]).εₘ
+        for s = max(0, out.lo - 2):min(out.nstep, out.hi + 2)-1
+            e = collect(𝕣, εₘ(state[s+1].time))
+            check(out.h, ccall((:mb_direct_set_gauge_measurements, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{𝕣}, Int32), out.h, s, ityp, e, 0))
         end
     end
 end
@@ -397,6 +421,7 @@ function solve_direct_b200(OX, OU; initialstate, time, maxiter=50, maxΔλ=1e-5,
     out, _, _  = Muscade.prepare(AssemblyDirectB200{OX,OU,0}, model, dis; nstep, Δt, device, t₀=first(time))
     state      = [Muscade.State{1,OX+1,OU+1}(copy(initialstate, time=t)) for t ∈ time]
     upload_states!(out, state)
+    upload_gauge_measurements!(out, model, state)
     for iter = 1:maxiter
         assemblebig!(out, model, dis, state, (dbg..., iter=iter))
         colptr, rowval, nzval = sparser(out, 1e-20)
