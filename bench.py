@@ -649,14 +649,16 @@ def run_scr(args, rank, world, local, comm, block=False):
     halos.  The whole series fits one handle per rank (≈ 5·10⁴ Lvv non-zeros per step); the steps share launch sets (step batching).  One bench step = one pass."""
     import muscade_b200 as mb
     OX, OU, nstep, dt, t0, su = 2, 0, args.scr_nstep, 0.1, 0., 50.
-    model, node_lists, weights = mb.examples.scr_riser(mb, udof=True)
-    unodes = np.concatenate([et.nodID[:, 2] for et in model.ele if et.ElType.__name__ == "EulerBeam3D"])
+    gauged = bool(getattr(args, "gauged", False)) and not block
+    gcost = mb.QuadraticGaugeCost(2e-5, lambda t: 1e-4 * np.cos(0.5 * t) * np.array([1., 0.5, -1., -0.5])) if gauged else None
+    model, node_lists, weights = mb.examples.scr_riser(mb, udof=True, gauge_cost=gcost)
+    unodes = np.concatenate([et.nodID[:, 2] for et in model.ele if et.ElType.__name__ in ("EulerBeam3D", "ElementCost")])
     for f in ("t1", "t2", "t3"):
         mb.addelement(model, mb.SingleDofCost, unodes[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / su) ** 2)
     mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=30., t2=30., t3=30.)), Λscale=1e3)
     st0 = mb.initialize(model); dis = st0.dis
     nX, nU = model.getndof("X"), model.getndof("U")
-    nel_dev = sum(et.nele for et in model.ele if et.ElType.kind in ("eulerbeam3d", "soilcontact", "bar3d"))
+    nel_dev = sum(et.nele for et in model.ele if et.ElType.kind in ("eulerbeam3d", "soilcontact", "bar3d", "elementcost"))
     if nstep % world or nstep // world < 6:
         raise ValueError("the number of time steps must be a multiple of the number of ranks, at least 6 each")
     lo, hi = rank * nstep // world, (rank + 1) * nstep // world
@@ -676,6 +678,8 @@ def run_scr(args, rank, world, local, comm, block=False):
     upload()
     for s in range(a, b):                             # Λ and the host-evaluated types: the host's share of an iteration, set once (not device work)
         eng.set_lambda(s, bankL[s % B])
+    if gauged:
+        eng.set_gauge_times(t0 + dt * np.arange(nstep))
     for s in range(a, min(b, a + B)):                 # host contributions of the first B steps, reused round-robin through the bank (same states ⇒ same values up to t)
         eng.set_host_cost(s, *mb.directxua.host_costs(eng, s, bankX[s % B][0], bankU[s % B], t0 + s * dt)[:4])
         mb.directxua.host_elements(eng, s, bankX[s % B], bankL[s % B], t0 + s * dt, model.scaleΛ)
@@ -730,6 +734,10 @@ def run_scr(args, rank, world, local, comm, block=False):
                            "l2": "per-step blocks and Lvv (%.1f GB per GPU) larger than L2" % (16e-9 * eng.nnzbig)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "breakdown_ms": {"elements_and_step_blocks": a_ms, "lvv_build": b_ms, "element_kernels": el_ms}}
+        if gauged:
+            line["metric"] = "element-step assemblies/s (DirectXUA{2,0,0} assemblebig!, SCR riser with ElementCost{StrainGaugeOnEulerBeam3D} on every beam + SoilContact)"
+            line["config"]["workload"] = line["config"]["workload"].replace("(100 EulerBeam3D{Udof} in", "(100 EulerBeam3D{Udof}, each with 4 strain gauges and a quadratic strain cost — "
+                                                                            "the ElementCost accelerator in the windowed path, mb_direct_set_gauge_cost —, in")
         if block:
             for k in ("e2e", "higher_is_better", "vs_baseline", "dtype", "data", "clocks"):
                 line.pop(k, None)

@@ -134,7 +134,7 @@ int32_t mb_direct_set_host_xx(mb_handle* h, int64_t step, int64_t n, const int64
  * addin!(…,eleobj::ElementCost,…) of src/DirectXUA.jl:172-198 as it is meant (L = Λ∘₁R + cost, first-order R and eleres; see mb_xua_set_gauge_cost for the general form).
  * mb_direct_set_gauge_cost: between mb_add_eulerbeam3d and mb_direct_prepare; G [ngauge][4] with ε_g = G[g]·(εₐₓ,κ₁,κ₂,κ₃) (toolbox/StrainGaugeOnBeamElement.jl:70-76).
  * mb_direct_set_gauge_measurements: measured strains of one stored step, [ngauge] for all elements or [nele][ngauge] (per_element, fixed by the first call); they are
- * kept per stored step and move with mb_direct_rebase.  A costed type is evaluated one time step per launch set. */
+ * kept per stored step and move with mb_direct_rebase. */
 int32_t mb_direct_set_gauge_cost(mb_handle* h, int32_t ieletyp, int32_t ngauge, const double* G, double sigma);
 int32_t mb_direct_set_gauge_measurements(mb_handle* h, int64_t step, int32_t ieletyp, const double* epsm, int32_t per_element);
 int32_t mb_direct_sparser(mb_handle* h, double rtol, int64_t* nnz_out);

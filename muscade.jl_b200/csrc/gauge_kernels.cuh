@@ -7,8 +7,10 @@ namespace {
 
 // requestables (εₐₓ, ♢κ) of EulerBeam3D (toolbox/BeamElement.jl:151-174) with their partials ∂/∂X₀ (scaled): one lane per (element, element dof), one-direction duals
 // through the forward kinematics only.  J[e][k][d], e4[e][k]  (k: εₐₓ, κ₁, κ₂, κ₃)
-__global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const double* __restrict__ X0, double* __restrict__ J, double* __restrict__ e4) {
+// Step batching (mb_direct.cu): grid row = time step; sX = stride of the state per step, sE = elements of the scratch arrays per step (0, 0 for one step).
+__global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const double* __restrict__ X0, double* __restrict__ J, double* __restrict__ e4, int64_t sX = 0, int64_t sE = 0) {
     using N = NumDual<1>; using T = Dual<1>;
+    X0 += (int64_t)blockIdx.y * sX; J += (int64_t)blockIdx.y * sE * 48; e4 += (int64_t)blockIdx.y * sE * 4;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t / 12; const int d = (int)(t - e * 12);
     if (e >= g.nele) return;
@@ -27,7 +29,9 @@ __global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const d
 // ε_g = G[g]·(εₐₓ,κ); ∇cost = Jᵀ·Gᵀ·r/σ², ∇²cost = Jᵀ·GᵀG·J/σ² (chainrule of the second-order cost with the first-order eleres: to_order{2} adds no curvature, :190-196).
 // One thread per (element, i): entry i of ∇cost → gX[e][12], row i of ∇²cost → HXX[e][12][12] (the whole X₀-X₀ block of the packet is the cost's: no Λ·∂²R/∂X²).
 __global__ void gauge_cost_kernel(int64_t nele, int ng, const double* __restrict__ G, const double* __restrict__ epsm, bool per_element, double isig2,
-                                  const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ gX, double* __restrict__ HXX, double* __restrict__ cost) {
+                                  const double* __restrict__ J, const double* __restrict__ e4, double* __restrict__ gX, double* __restrict__ HXX, double* __restrict__ cost,
+                                  int64_t sEps = 0, int64_t sE = 0) {
+    { const int64_t b = blockIdx.y; epsm += b * sEps; J += b * sE * 48; e4 += b * sE * 4; gX += b * sE * 12; HXX += b * sE * 144; if (cost) cost += b * sE; }
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t / 12; const int i = (int)(t - e * 12);
     if (e >= nele) return;

@@ -121,9 +121,11 @@ __global__ void vstart2_kernel(int64_t nvec, const uint32_t* __restrict__ keys, 
 // (DirectXUA_lagrangian_addition! differentiates with respect to the scaled Λ), so that the reductions of the plain path give L1[Λ], L2[Λ,X], L2[X,Λ], L2[Λ,U], L2[U,Λ].
 struct SL12 { double v[12]; };
 __global__ void __launch_bounds__(128) costed_fill_kernel(int64_t nele, int nd, int npd, const int32_t* __restrict__ idxX, const double* __restrict__ Lam, SL12 sL,
-                                                          const double* __restrict__ gX, double* __restrict__ R, double* __restrict__ dR, double* __restrict__ GX, double* __restrict__ GU) {
+                                                          const double* __restrict__ gX, double* __restrict__ R, double* __restrict__ dR, double* __restrict__ GX, double* __restrict__ GU,
+                                                          StepBatch sb, int64_t sE, int64_t sGU) {
     __shared__ double sm[39 * 12];
     __shared__ double lam[12], sl[12];
+    { const int64_t b = blockIdx.y; Lam += b * sb.sLam; gX += b * sE * 12; R += b * sb.sR; dR += b * sb.sdR; GX += b * sb.sGX; if (GU) GU += b * sGU; }      // step batching: grid row = time step
     const int64_t e = blockIdx.x;
     const int n = npd * 12;
     for (int q = threadIdx.x; q < n; q += blockDim.x) sm[q] = dR[e * n + q];
@@ -140,9 +142,11 @@ __global__ void __launch_bounds__(128) costed_fill_kernel(int64_t nele, int nd, 
     if (threadIdx.x < 12) R[e * 12 + threadIdx.x] *= sl[threadIdx.x];
 }
 // L2[X,X][1,1] of one step from the costs' Gauss-Newton blocks HXX[e][12][12] (costed beam types only; the reference's accumulation order over the X-X pattern)
-__global__ void gather_xxc_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, const double* __restrict__ HXX, double* __restrict__ out) {
+__global__ void gather_xxc_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, const double* __restrict__ HXX, double* __restrict__ out,
+                                  int64_t sE) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
+    HXX += (int64_t)blockIdx.y * sE * 144; out += (int64_t)blockIdx.y * nnz;
     double a = 0.;
     for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
         const uint32_t id = src[s];
@@ -155,9 +159,10 @@ __global__ void gather_xxc_kernel(int64_t nnz, const uint32_t* __restrict__ csta
     out[k] = a;
 }
 // L1[U][1] of one step: contributors GU[q] of every U-dof of the costed types
-__global__ void gather_l1u_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ GU, double* __restrict__ out) {
+__global__ void gather_l1u_kernel(int64_t ndof, const uint32_t* __restrict__ vstart, const uint32_t* __restrict__ vsrc, const double* __restrict__ GU, double* __restrict__ out, int64_t sGU) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndof) return;
+    GU += (int64_t)blockIdx.y * sGU; out += (int64_t)blockIdx.y * ndof;
     double acc = 0.;
     for (uint32_t s = vstart[d]; s < vstart[d + 1]; ++s) acc += GU[vsrc[s]];
     out[d] = acc;
@@ -469,7 +474,7 @@ struct DirectData {
     bool elements_only = false;                         // timing aid: direct_eval_steps launches the element kernels without the per-step reductions
     // costed beam types (mb_direct_set_gauge_cost): per stored step L2[X,X][1,1] and L1[U][1]; scratch of one step (J, e4, gX, HXX, GU, costs); U-dof contributor lists;
     // per type the measurements of every stored step [step][ng] or [step][nele][ng]
-    bool costed = false; int64_t ncost = 0;
+    bool costed = false; int64_t ncost = 0, nqu = 0;
     double *XXc = nullptr, *L1U = nullptr, *cJ = nullptr, *ce4 = nullptr, *cgX = nullptr, *cHXX = nullptr, *cGU = nullptr, *ccost = nullptr, *csL = nullptr;
     uint32_t *vstartU = nullptr, *vsrcU = nullptr;
     struct Meas { double* eps = nullptr; int64_t stride = 0; bool per_element = false; std::vector<char> have; };
@@ -592,13 +597,14 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     {
         int64_t nel = 0; for (const Group& g : h->groups) nel += g.nele;
         int64_t want = nel > 0 ? (65536 + nel - 1) / nel : 1;
-        const int64_t bytes_per_step = 8 * (ndr + nvec + D->ngx * (OX + 1)) + 8 * 6 * (OX + 1) * nel * MB_NCOT;
+        int64_t ncst = 0; for (const Group& g : h->groups) if (g.kind == G_BEAM && g.ng > 0) ncst += g.nele;
+        const int64_t bytes_per_step = 8 * (ndr + nvec + D->ngx * (OX + 1)) + 8 * 6 * (OX + 1) * nel * MB_NCOT + 8 * ncst * (48 + 4 + 12 + 144 + 1 + 3);
         const int64_t cap = std::max<int64_t>(1, (int64_t(1) << 30) / std::max<int64_t>(1, bytes_per_step));
         want = std::min<int64_t>(std::min<int64_t>(want, cap), std::min<int64_t>(ns, 65535));
         if (const char* eb = getenv("MB_DIRECT_BATCH")) want = std::max<int64_t>(1, std::min<int64_t>(atoll(eb), std::min<int64_t>(ns, 65535)));
         D->batch = std::max<int64_t>(1, want); D->ndr = (ndr + 1) & ~int64_t(1); D->nvec = (nvec + 1) & ~int64_t(1);
     }
-    // costed beam types (ElementCost accelerator): scratch of one step, contributor lists of their U-dofs, per-stored-step L2[X,X][1,1] and L1[U][1]; one step per launch set
+    // costed beam types (ElementCost accelerator): scratch of one step, contributor lists of their U-dofs, per-stored-step L2[X,X][1,1] and L1[U][1]
     {
         int64_t nc = 0, nqu = 0;
         D->gubase.assign(h->groups.size(), -1);
@@ -611,11 +617,12 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
         }
         D->ncost = nc; D->costed = nc > 0;
         if (D->costed) {
-            D->batch = 1;
-            CK(dalloc(h, &D->cJ, nc * 48)); CK(dalloc(h, &D->ce4, nc * 4)); CK(dalloc(h, &D->cgX, nc * 12)); CK(dalloc(h, &D->cHXX, nc * 144)); CK(dalloc(h, &D->ccost, nc));
+            const int64_t nb = D->batch;
+            CK(dalloc(h, &D->cJ, nc * 48 * nb)); CK(dalloc(h, &D->ce4, nc * 4 * nb)); CK(dalloc(h, &D->cgX, nc * 12 * nb)); CK(dalloc(h, &D->cHXX, nc * 144 * nb)); CK(dalloc(h, &D->ccost, nc * nb));
             CK(dalloc(h, &D->XXc, ns * D->pat[P_XX].nnz)); CK(cudaMemsetAsync(D->XXc, 0, (size_t)(ns * D->pat[P_XX].nnz) * 8, st));
             if (nqu > 0 && ndofU > 0) {
-                CK(dalloc(h, &D->cGU, nqu)); CK(dalloc(h, &D->L1U, ns * ndofU)); CK(cudaMemsetAsync(D->L1U, 0, (size_t)(ns * ndofU) * 8, st));
+                D->nqu = nqu;
+                CK(dalloc(h, &D->cGU, nqu * D->batch)); CK(dalloc(h, &D->L1U, ns * ndofU)); CK(cudaMemsetAsync(D->L1U, 0, (size_t)(ns * ndofU) * 8, st));
                 CK(dalloc(h, &D->vstartU, ndofU + 1)); CK(dalloc(h, &D->vsrcU, nqu));
                 CK(cudaMemsetAsync(D->vstartU, 0, (ndofU + 1) * sizeof(uint32_t), st));
                 uint32_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr;
@@ -772,15 +779,16 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
             else h->launches += launch_beam_direct<3>(gd, sd, dR, R, h->nanflag, nanbase, Wc, st, sb, nb);
             if (g.ng > 0) {                        // ElementCost accelerator: strains and their Jacobian, the cost's gradient and Gauss-Newton block, then the Lagrangian's own terms
                 auto mit = D->meas.find((int)ig);
-                ARG(mit != D->meas.end() && mit->second.eps && mit->second.have[(size_t)k], "strain-gauge measurements of a stored step are not set (mb_direct_set_gauge_measurements)");
+                ARG(mit != D->meas.end() && mit->second.eps, "strain-gauge measurements of a stored step are not set (mb_direct_set_gauge_measurements)");
                 const DirectData::Meas& m = mit->second;
-                const int64_t eb = D->G.hxxbase[ig];
-                beam_gauge_kernel<<<nblk(g.nele * 12, 128), 128, 0, st>>>(gd, sd.X[0], D->cJ + eb * 48, D->ce4 + eb * 4);
-                gauge_cost_kernel<<<nblk(g.nele * 12, 128), 128, 0, st>>>(g.nele, g.ng, g.gaugeG, m.eps + k * m.stride, m.per_element, g.isig2, D->cJ + eb * 48, D->ce4 + eb * 4,
-                                                                          D->cgX + eb * 12, D->cHXX + eb * 144, D->ccost + eb);
+                for (int b = 0; b < nb; ++b) ARG(m.have[(size_t)(k + b)], "strain-gauge measurements of a stored step are not set (mb_direct_set_gauge_measurements)");
+                const int64_t eb = D->G.hxxbase[ig], nc = D->ncost;
+                beam_gauge_kernel<<<dim3(nblk(g.nele * 12, 128), nb), 128, 0, st>>>(gd, sd.X[0], D->cJ + eb * 48, D->ce4 + eb * 4, sb.sX, nc);
+                gauge_cost_kernel<<<dim3(nblk(g.nele * 12, 128), nb), 128, 0, st>>>(g.nele, g.ng, g.gaugeG, m.eps + k * m.stride, m.per_element, g.isig2, D->cJ + eb * 48, D->ce4 + eb * 4,
+                                                                                    D->cgX + eb * 12, D->cHXX + eb * 144, D->ccost + eb, m.stride, nc);
                 SL12 sl; for (int i = 0; i < 12; ++i) sl.v[i] = g.scaleX[i] * D->lamscale;
-                costed_fill_kernel<<<(unsigned)g.nele, 128, 0, st>>>(g.nele, nd, D->G.np[ig], g.idxX, D->Lam + k * D->nX, sl, D->cgX + eb * 12, R, dR, D->GX + D->G.gxbase[ig] * nd,
-                                                                     D->gubase[ig] >= 0 && D->cGU ? D->cGU + D->gubase[ig] : nullptr);
+                costed_fill_kernel<<<dim3((unsigned)g.nele, nb), 128, 0, st>>>(g.nele, nd, D->G.np[ig], g.idxX, D->Lam + k * D->nX, sl, D->cgX + eb * 12, R, dR, D->GX + D->G.gxbase[ig] * nd,
+                                                                               D->gubase[ig] >= 0 && D->cGU ? D->cGU + D->gubase[ig] : nullptr, sb, nc, D->nqu);
                 h->launches += 3;
             }
         }
@@ -795,8 +803,8 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         h->launches++;
         if (D->ngx) { gather_l1x_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart2, D->vsrc2, D->GX, nd, D->L1X + k * nd * D->nX, ngxd); h->launches++; }
         if (D->costed) {
-            if (XX.nnz) { gather_xxc_kernel<<<nblk(XX.nnz, 256), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, D->cHXX, D->XXc + k * XX.nnz); h->launches++; }
-            if (D->L1U) { gather_l1u_kernel<<<nblk(D->nU, 256), 256, 0, st>>>(D->nU, D->vstartU, D->vsrcU, D->cGU, D->L1U + k * D->nU); h->launches++; }
+            if (XX.nnz) { gather_xxc_kernel<<<dim3(nblk(XX.nnz, 256), nb), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, D->cHXX, D->XXc + k * XX.nnz, D->ncost); h->launches++; }
+            if (D->L1U) { gather_l1u_kernel<<<dim3(nblk(D->nU, 256), nb), 256, 0, st>>>(D->nU, D->vstartU, D->vsrcU, D->cGU, D->L1U + k * D->nU, D->nqu); h->launches++; }
         }
     }
     return MB_OK;

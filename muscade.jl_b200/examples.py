@@ -33,9 +33,20 @@ def vert_target(t): return np.exp(min(t, 0.)) * 303.1 + zmotion(t)              
 def ramp(t): return (min(t, -5.) + 10.) / 5.                                     # :119-121
 
 
-def scr_riser(mb, udof=False):
-    """udof: EulerBeam3D{Udof=true} with one U-node per element (unknown distributed loads, the XUA set-up of configs[4])"""
+def scr_riser(mb, udof=False, gauge_cost=None):
+    """udof: EulerBeam3D{Udof=true} with one U-node per element (unknown distributed loads, the XUA set-up of configs[4]).
+    gauge_cost: a QuadraticGaugeCost — every beam is wrapped in ElementCost{StrainGaugeOnEulerBeam3D} with four gauges round the pipe wall (load identification from strains)"""
     acc = np.concatenate([[0.], np.cumsum(SEGLEN)])
+
+    def addbeams(nodes, mat):
+        if gauge_cost is None:
+            mb.addelement(model, mb.EulerBeam3D, nodes, mat=mat, orient2=(0., 1., 0.), Udof=udof)
+        else:
+            r = 0.15
+            P = np.array([[0., r, 0.], [0., 0., r], [0., -r, 0.], [0., 0., -r]]).T
+            D = np.array([[1., 0., 0.]] * 4).T
+            mb.addelement(model, mb.ElementCost, nodes, req=("ε",), cost=gauge_cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                          elementkwargs=dict(P=P, D=D, elementkwargs=dict(mat=mat, orient2=(0., 1., 0.), Udof=udof)))
 
     def mesh(n1, n2):
         n1, n2 = np.atleast_1d(n1), np.atleast_1d(n2)
@@ -49,12 +60,12 @@ def scr_riser(mb, udof=False):
         c = np.stack([acc[seg] + np.arange(nn) / (nn - 1) * SEGLEN[seg], np.zeros(nn), -300. + np.zeros(nn)], axis=1)
         if seg == 0:
             nod = mb.addnode(model, c)
-            mb.addelement(model, mb.EulerBeam3D, mesh(nod[:-1], nod[1:]), mat=mats[0], orient2=(0., 1., 0.), Udof=udof)
+            addbeams(mesh(nod[:-1], nod[1:]), mats[0])
             last = nod[-1]
         else:
             nod = mb.addnode(model, c[1:])
-            mb.addelement(model, mb.EulerBeam3D, mesh(last, nod[0]), mat=mats[seg], orient2=(0., 1., 0.), Udof=udof)
-            mb.addelement(model, mb.EulerBeam3D, mesh(nod[:-1], nod[1:]), mat=mats[seg], orient2=(0., 1., 0.), Udof=udof)
+            addbeams(mesh(last, nod[0]), mats[seg])
+            addbeams(mesh(nod[:-1], nod[1:]), mats[seg])
             last = nod[-1]
         node_lists.append(nod)
     first = node_lists[0][0]

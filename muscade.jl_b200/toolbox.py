@@ -437,7 +437,8 @@ class StrainGaugeOnEulerBeam3D(EulerBeam3D):
 
     @classmethod
     def typekey(cls, P=None, D=None, elementkwargs=None, **kw):
-        return ("StrainGaugeOnEulerBeam3D", np.asarray(P).shape[1]) + EulerBeam3D.typekey(**(elementkwargs or {}))
+        # P and D are type data (the gauge matrix G lives in the type's `extra`): two calls with different gauges must not merge into one type
+        return ("StrainGaugeOnEulerBeam3D", np.asarray(P, float).shape[1], np.asarray(P, float).tobytes(), np.asarray(D, float).tobytes()) + EulerBeam3D.typekey(**(elementkwargs or {}))
 
     @staticmethod
     def gauge_matrix(P, D):

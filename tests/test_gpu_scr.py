@@ -276,3 +276,45 @@ def test_scr_general_form_assembly_parity(mb):
         assert np.abs(Lvec - Lv).max() <= 1e-12 * max(scale, np.abs(Lv).max())
     finally:
         eng.close()
+
+
+def test_gauged_scr_windowed_path_equals_general_form(mb):
+    """The SCR riser with ElementCost{StrainGaugeOnEulerBeam3D} on every beam (load identification from strain gauges; bench.py --workload scr --gauged): the beam-specialised
+    path with its step batching (mb_direct_set_gauge_cost; SoilContact, Hold / DofConstraint / DofLoad and the U-costs beside the costed beams) against the general form:
+    identical structure, Lvv values and Lv ≤ 1e-12."""
+    from muscade_b200 import xua
+    OX, OU, nstep, dt, t0, σu = 2, 0, 7, 0.3, -6.3, 50.
+    cost = mb.QuadraticGaugeCost(2e-5, lambda t: 1e-4 * np.cos(0.5 * t) * np.array([1., 0.5, -1., -0.5]))
+    model, node_lists, weights = mb.examples.scr_riser(mb, udof=True, gauge_cost=cost)
+    unodes = np.concatenate([et.nodID[:, 2] for et in model.ele if et.ElType.__name__ == "ElementCost"])
+    for f in ("t1", "t2", "t3"):
+        mb.addelement(model, mb.SingleDofCost, unodes[:, None], clas="U", field=f, cost=lambda u, t: 0.5 * (u / σu) ** 2)
+    mb.setscale(model, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=30., t2=30., t3=30.)), Λscale=1e3)
+    st0 = mb.initialize(model); dis = st0.dis
+    nX, nU = model.getndof("X"), model.getndof("U")
+    time = t0 + dt * np.arange(nstep)
+    st = [([mb.synthetic.uniform_pm1(10 + 3 * s + d, nX) * (0.2 if d == 0 else 0.3) for d in range(3)], 20. * mb.synthetic.uniform_pm1(99 + s, nU)) for s in range(nstep)]
+    Lam = [mb.synthetic.uniform_pm1(500 + s, nX) for s in range(nstep)]
+    spec = mb.directxua.prepare(OX, OU, model, dis, nstep, dt, t0=t0)
+    gen = xua.XUAEngine(0)
+    try:
+        for s in range(nstep):
+            spec.set_state(s, st[s][0], st[s][1]); spec.set_lambda(s, Lam[s])
+            spec.set_host_cost(s, *mb.directxua.host_costs(spec, s, st[s][0][0], st[s][1], time[s])[:4])
+            mb.directxua.host_elements(spec, s, st[s][0], Lam[s], time[s], model.scaleΛ)
+        spec.set_gauge_times(time)
+        Lvv = np.zeros(spec.nnzbig); Lv = np.zeros(spec.ncol)
+        spec.direct_assemble(Lvv=Lvv, Lv=Lv)
+        cp, rv = spec.big_pattern()
+        nbig, nnz = gen.prepare(model, dis, OX, OU, 0, [nstep], [dt])
+        gen.set_time0(1, t0)
+        gcp, grv = gen.big_pattern()
+        assert nbig == spec.ncol and np.array_equal(cp, gcp) and np.array_equal(rv, grv)
+        states = [[mb.State(float(time[s]), [Lam[s]], st[s][0], [st[s][1]], st0.A, None, model, dis) for s in range(nstep)]]
+        gen.assemblebig(states)
+        gLvv, gLv = gen.big()
+        scale = np.abs(gLvv).max()
+        assert np.abs(gLvv - Lvv).max() <= 1e-12 * scale
+        assert np.abs(gLv - Lv).max() <= 1e-12 * max(scale, np.abs(gLv).max())
+    finally:
+        spec.close(); gen.close()

@@ -119,3 +119,20 @@ def test_turbine_and_anchorline_goldens():
     assert np.allclose(g[0, 0:3], [-12.25628901693551, 0.2607721067433087, 24.51257803387102], rtol=1e-10)      # ∇L[1][1]   :37
     assert np.allclose(g[0, 3:6], [-0.91509745608786, 0.14708204066349, 1.3086506986891027], rtol=1e-10)        # ∇L[2][1]   :38
     assert np.allclose(g[0, 6:8], [-156.06324599170992, 12.517061123678818], rtol=1e-10)                        # ∇L[4][1]   :40
+
+
+def test_gauge_types_do_not_merge_across_different_gauges():
+    """ElementCost{StrainGaugeOnEulerBeam3D} types are keyed by their gauge positions / directions and by the cost: a second addelement with other gauges is another type
+    (its gauge matrix is type data), the same gauges and cost extend the first type"""
+    import muscade_b200 as mb
+    P = np.array([[0., .5, 0.], [0., 0, .5]]).T; D = np.array([[1., 0., 0.], [1., 0., 0.]]).T
+    cost = mb.QuadraticGaugeCost(1e-5, lambda t: np.zeros(2))
+    m = mb.Model("g")
+    nod = mb.addnode(m, np.arange(5)[:, None] * np.array([1., 0., 0.])[None, :])
+    kw = dict(req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D)
+    ek = dict(mat=mb.BeamCrossSection(EA=10., EI2=3., EI3=3., GJ=4., mu=1., iota1=1.), orient2=(0., 1., 0.))
+    mb.addelement(m, mb.ElementCost, np.stack([nod[:1], nod[1:2]], axis=1), elementkwargs=dict(P=P, D=D, elementkwargs=ek), **kw)
+    mb.addelement(m, mb.ElementCost, np.stack([nod[1:2], nod[2:3]], axis=1), elementkwargs=dict(P=P, D=D, elementkwargs=ek), **kw)
+    assert len(m.ele) == 1 and m.ele[0].nele == 2
+    mb.addelement(m, mb.ElementCost, np.stack([nod[2:3], nod[3:4]], axis=1), elementkwargs=dict(P=2 * P, D=D, elementkwargs=ek), **kw)
+    assert len(m.ele) == 2 and not np.array_equal(m.ele[0].extra["G"], m.ele[1].extra["G"])
