@@ -278,6 +278,7 @@ def test_scr_general_form_assembly_parity(mb):
         eng.close()
 
 
+@pytest.mark.gpu
 def test_gauged_scr_windowed_path_equals_general_form(mb):
     """The SCR riser with ElementCost{StrainGaugeOnEulerBeam3D} on every beam (load identification from strain gauges; bench.py --workload scr --gauged): the beam-specialised
     path with its step batching (mb_direct_set_gauge_cost; SoilContact, Hold / DofConstraint / DofLoad and the U-costs beside the costed beams) against the general form:
