@@ -82,7 +82,10 @@ def prepare(OX, model, dis, device=0):
     eng.set_ndofU(model.getndof("U"))
     host_types = []
     for k, (et, ed) in enumerate(zip(model.ele, dis.dis)):
-        if et.ElType.kind == "eulerbeam3d":
+        # ElementCost on a device beam: in an X-analysis R = ∂L/∂Λ of L = getlagrangian(target) + cost(eleres) is the target's own residual (src/BasicElements.jl:117-132,
+        # src/Assemble.jl:623-680), so the wrapped beams run through the beam kernels unchanged
+        target = et.extra.get("target") if (et.ElType.kind == "elementcost" and isinstance(et.extra, dict)) else None
+        if et.ElType.kind == "eulerbeam3d" or (target is not None and target.kind == "eulerbeam3d"):
             udof = ed.U.shape[1] > 0
             eng.add_eulerbeam3d(et.eleobj, ed.X, ed.scaleX, udof=udof, idxU=ed.U if udof else None, scaleU=ed.scaleU if udof else None)
         elif et.ElType.kind == "bar3d":

@@ -362,3 +362,36 @@ def test_gauge_cost_sliding_window(mb):
         spec.rebase(7); check(7)               # backward
     finally:
         spec.close(); gen.close()
+
+
+@pytest.mark.parametrize("OX", [0, 2])
+def test_sweepx_sees_a_costed_beam_as_its_target(mb, OX):
+    """An X-analysis of a model whose beams are wrapped in ElementCost (the SweepX run that provides DirectXUA's initial state): R = ∂L/∂Λ of L = getlagrangian(target) + cost
+    is the target's residual (src/BasicElements.jl:117-132), so Lλ and Lλx are those of the plain beams, bit for bit"""
+    rng = np.random.default_rng(2)
+    n = 7
+    coords = np.cumsum(rng.uniform(0.5, 1.5, (n + 1, 3)), axis=0)
+    mat = dict(EA=1e3, EI2=30., EI3=20., GJ=40., mu=1.5, iota1=0.7, Ca2=0.1)
+    res = []
+    for gauged in (False, True):
+        m = mb.Model("chain")
+        nod = mb.addnode(m, coords)
+        nodes = np.stack([nod[:-1], nod[1:]], axis=1)
+        if gauged:
+            mb.addelement(m, mb.ElementCost, nodes, req=("ε",), cost=mb.QuadraticGaugeCost(SIGMA, measured), ElementType=mb.StrainGaugeOnEulerBeam3D,
+                          elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(**mat), orient2=(0., 1., 0.))))
+        else:
+            mb.addelement(m, mb.EulerBeam3D, nodes, mat=mb.BeamCrossSection(**mat), orient2=(0., 1., 0.))
+        state = mb.initialize(m).with_orders(1, OX + 1, 1)
+        ndof = m.getndof("X")
+        for d in range(OX + 1):
+            state.X[d] = mb.synthetic.uniform_pm1(5 + d, ndof) * (0.1 if d == 0 else 0.3)
+        out, asm, gr = mb.sweepx.prepare(OX, m, state.dis)
+        try:
+            out.c = mb.synthetic.newmark_coefficients(OX, 0.3)
+            mb.sweepx.assemble("iter", out, asm, state.dis, m, state, 0.3)
+            res.append((out.Lλ.copy(), out.Lλx.data.copy(), out.Lλx.indices.copy()))
+        finally:
+            out.engine.close()
+    assert np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][1]).max() > 0
