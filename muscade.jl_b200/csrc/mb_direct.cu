@@ -250,11 +250,12 @@ constexpr int MB_BIG_MAXB = 48;          // ≥ 3 classes × 5 step offsets × (
 constexpr int MB_BIG_CPC = 128;          // pattern columns per CTA
 constexpr int MB_BIG_CAP = 6144;         // pattern entries of one kind per CTA chunk held in the column-of-entry table
 struct BlkDesc { const double* a; const int32_t* pc; double wd[3]; int64_t nnzp; int nder, kind, nA, nB; };
-__global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t* __restrict__ colptr, double* __restrict__ nzval) {
+__global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t* __restrict__ colptr, double* __restrict__ nzval, int big_sub) {
     __shared__ BlkDesc sd[MB_BIG_MAXB];
     __shared__ int64_t colbase[MB_BIG_CPC];
     __shared__ int32_t pst[2][MB_BIG_CPC + 1];           // pattern colptr of the chunk, kinds A (rows Λ/X) and B (rows U)
     __shared__ uint8_t colof[2][MB_BIG_CAP];
+    extern __shared__ int32_t drel[];                    // [nb][MB_BIG_CPC], sized by the launch (maxb blocks)
     // block column fastest: CTAs running together read the same chunk of the per-step source arrays for all their time offsets (L2 reuse)
     const int nbc = 3 * (int)(B.hi - B.lo);
     const int bc = (int)(blockIdx.x % (unsigned)nbc), cb = bc % 3;
@@ -295,22 +296,34 @@ __global__ void __launch_bounds__(256) big_values_kernel(BigDev B, const int64_t
             for (int kd = 0; kd < 2; ++kd)
                 for (int32_t k = pst[kd][c]; k < pst[kd][c + 1]; ++k) colof[kd][k - pst[kd][0]] = (uint8_t)c;
         __syncthreads();
+        // Sub-chunks of MB_BIG_SUB columns, blocks inside: the Lvv columns of a sub-chunk (a contiguous destination range) are completed before the next one is started, so the
+        // partially written sectors of all resident CTAs fit L2 (block-outer order left 276 KB per CTA in flight: written-back half-filled)
+        // destination of pattern entry k of block j in column c: colbase[c] + nA_j·sizeA(c) + nB_j·sizeB(c) + (k − pst[kd][c]) = nzbase + drel[j][c] + k with drel tabulated once
+        // per CTA (32-bit, relative to the chunk's first non-zero): the inner loop is one table look-up and an add
+        const int64_t nzbase = colbase[0];
+        for (int q = threadIdx.x; q < nb * nc; q += blockDim.x) {
+            const int j = q / nc, c = q - j * nc;
+            drel[j * MB_BIG_CPC + c] = (int32_t)(colbase[c] - nzbase) + sd[j].nA * (pst[0][c + 1] - pst[0][c]) + sd[j].nB * (pst[1][c + 1] - pst[1][c]) - pst[sd[j].kind][c];
+        }
+        __syncthreads();
+        for (int cs = 0; cs < nc; cs += big_sub)
         for (int j = 0; j < nb; ++j) {
             const int kd = sd[j].kind;
             const double* a = sd[j].a;
-            const int nder = sd[j].nder, nA = sd[j].nA, nBk = sd[j].nB; const int64_t nnzp = sd[j].nnzp;
+            const int nder = sd[j].nder; const int64_t nnzp = sd[j].nnzp;
             const double w0 = sd[j].wd[0], w1 = sd[j].wd[1], w2 = sd[j].wd[2];
-            const int32_t k0 = pst[kd][0], k1 = pst[kd][nc];
-            for (int32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+            const int ce = cs + big_sub < nc ? cs + big_sub : nc;
+            const int32_t k0 = pst[kd][0], ka = pst[kd][cs], k1 = pst[kd][ce];
+            const int32_t* dj = drel + j * MB_BIG_CPC;
+            double* out = nzval + nzbase;
+            const bool u0 = a && w0 != 0., u1 = a && nder > 1 && w1 != 0., u2 = a && nder > 2 && w2 != 0.;
+            for (int32_t k = ka + threadIdx.x; k < k1; k += blockDim.x) {
                 const int c = colof[kd][k - k0];
-                const int64_t dst = colbase[c] + (int64_t)nA * (pst[0][c + 1] - pst[0][c]) + (int64_t)nBk * (pst[1][c + 1] - pst[1][c]) + (k - pst[kd][c]);
                 double v = 0.;                                     // same order of additions as the reference (DirectXUA.jl:342-352)
-                if (a) {
-                    if (w0 != 0.) v += a[k] * w0;
-                    if (nder > 1 && w1 != 0.) v += a[nnzp + k] * w1;
-                    if (nder > 2 && w2 != 0.) v += a[2 * nnzp + k] * w2;
-                }
-                nzval[dst] = v;
+                if (u0) v += a[k] * w0;
+                if (u1) v += a[nnzp + k] * w1;
+                if (u2) v += a[2 * nnzp + k] * w2;
+                out[dj[c] + k] = v;
             }
         }
     } else {                                                       // very dense pattern columns: one warp per column
@@ -341,7 +354,11 @@ static void launch_big_values(const BigDev& B, int64_t ncol, const int64_t* colp
     const int64_t nbc = 3 * (B.hi - B.lo), ncls = B.nX > B.nU ? B.nX : B.nU;
     const int64_t nchunk = (ncls + MB_BIG_CPC - 1) / MB_BIG_CPC;
     if (maxb <= MB_BIG_MAXB && nchunk * nbc < (int64_t)INT32_MAX)
-        big_values_kernel<<<(unsigned)(nchunk * nbc), 256, 0, st>>>(B, colptr, nzval);
+    {
+        static int big_sub = -1;
+        if (big_sub < 0) { const char* e = getenv("MB_BIG_SUB"); big_sub = e ? std::max(1, atoi(e)) : 32; }
+        big_values_kernel<<<(unsigned)(nchunk * nbc), 256, (size_t)maxb * MB_BIG_CPC * sizeof(int32_t), st>>>(B, colptr, nzval, big_sub);
+    }
     else
         big_fill_kernel<false><<<nblk(ncol * 32, 256), 256, 0, st>>>(B, ncol, colptr, nullptr, nzval);
 }

@@ -102,6 +102,35 @@ def _direct_setup(mb, N=7, nstep=12):
     return model, st0.dis, nX, nU, states(mb, nX, nU, nstep)
 
 
+def _gauged_setup(mb, n=6, nstep=12, dt=0.05):
+    """chain of Udof beams wrapped in ElementCost{StrainGaugeOnEulerBeam3D} (5 gauges, quadratic strain cost), non-unit scales; random Λ, X, X′, X″, U per step"""
+    rng = np.random.default_rng(8)
+    P5 = np.array([[0., .5, 0.], [0., 0, .5], [0., -.5, 0.], [0., 0, -.5], [0., .5, 0.]]).T
+    D5 = np.array([[1., 0., 0.], [1., 0., 0.], [1., 0., 0.], [1., 0., 0.], [1 / np.sqrt(2), 0, 1 / np.sqrt(2)]]).T
+    m = mb.Model("gauged chain")
+    nod = mb.addnode(m, np.cumsum(rng.uniform(0.5, 1.5, (n + 1, 3)), axis=0))
+    un = np.array([mb.addnode(m, np.zeros(3)) for _ in range(n)])
+    nodes = np.concatenate([np.stack([nod[:-1], nod[1:]], axis=1), un[:, None]], axis=1)
+    tgt = rng.normal(0., 1e-3, 5)
+    cost = mb.QuadraticGaugeCost(2e-3, lambda t: tgt * np.cos(t))
+    mb.addelement(m, mb.ElementCost, nodes, req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e3, EI2=30., EI3=20., GJ=40., mu=1.5, iota1=0.7), orient2=(0., 1., 0.), Udof=True)))
+    mb.setscale(m, scale=dict(X=dict(t1=2., t2=2., t3=2.), U=dict(t1=3., t2=3., t3=3.)), Λscale=3.)
+    s0 = mb.initialize(m)
+    nX, nU = m.getndof("X"), m.getndof("U")
+    st = [([rng.normal(0, 0.05, nX) for _ in range(3)], rng.normal(0, 0.5, nU), rng.normal(0, 1., nX)) for _ in range(nstep)]
+    return m, s0.dis, nX, nU, st, dt * np.arange(nstep)
+
+
+def _gauged_engine(mb, m, dis, st, time, nstep, dt, lo, hi, device, own_only):
+    e = mb.directxua.prepare(2, 0, m, dis, nstep, dt, lo, hi, device=device)
+    a, b = (lo, hi) if own_only else e.stored_range()
+    for s in range(a, b):
+        e.set_state(s, st[s][0], st[s][1]); e.set_lambda(s, st[s][2])
+        e.set_gauge_measurements(s, 1, e.gauge_costs[0][1].measured(time[s]))
+    return e
+
+
 def test_directxua_time_shard_halo_blocks(mb):
     import torch
     OX, OU, nstep, dt, world = 2, 0, 12, 0.05, 3
@@ -210,6 +239,24 @@ WORKER = textwrap.dedent('''
     c0, c1 = lo * W, hi * W; p0, p1 = cpw[c0] - 1, cpw[c1] - 1
     ok = np.array_equal(a, Lvv[p0:p1]) and np.array_equal(b, Lv[c0:c1])
     assert e.comm_allreduce([1.0 if ok else 0.0], "min")[0] == 1.0, "directxua shard differs on rank %%d" %% rank
+    d.close()
+    # ---- the same with a strain-gauge cost on every beam (ElementCost accelerator in the windowed path): L1[X] of the costed beams travels with the halo, the costs' X-X blocks
+    # and L1[U] are read at the owned steps only
+    from test_gpu_multigpu import _gauged_setup, _gauged_engine
+    m, gdis, nX, nU, gst, gtime = _gauged_setup(mb, nstep=nstep, dt=dt)
+    W = 2 * nX + nU
+    whole = _gauged_engine(mb, m, gdis, gst, gtime, nstep, dt, 0, nstep, rank, False)
+    Lvv = np.zeros(whole.nnzbig); Lv = np.zeros(whole.ncol)
+    whole.direct_assemble(Lvv=Lvv, Lv=Lv); cpw, rvw = whole.big_pattern(); whole.close()
+    d = _gauged_engine(mb, m, gdis, gst, gtime, nstep, dt, lo, hi, rank, True)
+    d.comm_init_from(e)
+    d.direct_assemble(eval_range=(lo, hi), build_big=False)
+    d.halo_exchange()
+    a = np.zeros(d.nnzbig); b = np.zeros(d.ncol)
+    d.direct_assemble(eval_range=(lo, lo), build_big=True, Lvv=a, Lv=b)
+    c0, c1 = lo * W, hi * W; p0, p1 = cpw[c0] - 1, cpw[c1] - 1
+    ok = np.array_equal(a, Lvv[p0:p1]) and np.array_equal(b, Lv[c0:c1]) and np.abs(b).max() > 0
+    assert e.comm_allreduce([1.0 if ok else 0.0], "min")[0] == 1.0, "gauged directxua shard differs on rank %%d" %% rank
     d.close(); e.close()
     print("RANK_OK %%d" %% rank, flush=True)
 ''')
