@@ -209,8 +209,8 @@ class HoldD2(mb.LagrangianElement):
         return [-lam, -x]
 
 
-@pytest.mark.parametrize("OX,per_element", [(0, False), (2, True), (1, False)])
-def test_gauge_cost_in_the_windowed_path_equals_general_form(mb, OX, per_element):
+@pytest.mark.parametrize("OX,per_element,Udof", [(0, False, True), (2, True, True), (1, False, True), (2, False, False)])
+def test_gauge_cost_in_the_windowed_path_equals_general_form(mb, OX, per_element, Udof):
     """ElementCost{StrainGaugeOnEulerBeam3D} on the beam-specialised, windowed path (mb_direct_set_gauge_cost: the costed beam's ∇L[X_d], ∇L[U], Gauss-Newton X₀-X₀ block and
     scale.Λ-scaled Λ rows enter the block-implicit Lvv / Lv) against the general form (mb_xua_*, itself checked against the oracle and the reference's goldens above):
     same structure, Lvv values and Lv within 1e-12, with random Λ, X, X′, X″, U, host-evaluated single-dof costs beside the gauges, non-unit scales."""
@@ -218,15 +218,18 @@ def test_gauge_cost_in_the_windowed_path_equals_general_form(mb, OX, per_element
     n, nstep, dt = 9, 7, 0.25
     m = mb.Model("gauged chain")
     nod = mb.addnode(m, np.cumsum(rng.uniform(0.5, 1.5, (n + 1, 3)), axis=0))
-    un = np.array([mb.addnode(m, np.zeros(3)) for _ in range(n)])
-    nodes = np.concatenate([np.stack([nod[:-1], nod[1:]], axis=1), un[:, None]], axis=1)
+    nodes = np.stack([nod[:-1], nod[1:]], axis=1)
+    if Udof:
+        un = np.array([mb.addnode(m, np.zeros(3)) for _ in range(n)])
+        nodes = np.concatenate([nodes, un[:, None]], axis=1)
     tgt = rng.normal(0., 1e-3, (n, 5))
     meas = (lambda t: tgt * np.cos(t)) if per_element else (lambda t: tgt[0] * np.cos(t))
     cost = mb.QuadraticGaugeCost(2e-3, meas)
     mb.addelement(m, mb.ElementCost, nodes, req=("ε",), cost=cost, ElementType=mb.StrainGaugeOnEulerBeam3D,
-                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e3, EI2=30., EI3=20., GJ=40., mu=1.5, iota1=0.7, Ca2=0.1), orient2=(0., 1., 0.), Udof=True)))
+                  elementkwargs=dict(P=P5, D=D5, elementkwargs=dict(mat=mb.BeamCrossSection(EA=1e3, EI2=30., EI3=20., GJ=40., mu=1.5, iota1=0.7, Ca2=0.1), orient2=(0., 1., 0.), Udof=Udof)))
     mb.addelement(m, mb.SingleDofCost, nod[::3, None], clas="X", field="t2", cost=XM.l1)
-    mb.addelement(m, mb.SingleDofCost, un[:, None], clas="U", field="t1", cost=XM.fu)
+    if Udof:
+        mb.addelement(m, mb.SingleDofCost, un[:, None], clas="U", field="t1", cost=XM.fu)
     mb.setscale(m, scale=dict(X=dict(t1=2., t2=2., t3=2., r1=0.5, r2=0.5, r3=0.5), U=dict(t1=3., t2=3., t3=3.)), Λscale=7.)
     s0 = mb.initialize(m); dis = s0.dis
     nX, nU = m.getndof("X"), m.getndof("U")
@@ -257,7 +260,7 @@ def test_gauge_cost_in_the_windowed_path_equals_general_form(mb, OX, per_element
         W = 2 * nX + nU
         import scipy.sparse as sp
         A = sp.csc_matrix((Lvv, rv - 1, cp - 1), shape=(nbig, nbig)).tocsr()
-        assert abs(A[nX:2 * nX, nX:2 * nX]).max() > 0 and np.abs(Lv[2 * nX:W]).max() > 0
+        assert abs(A[nX:2 * nX, nX:2 * nX]).max() > 0 and (not Udof or np.abs(Lv[2 * nX:W]).max() > 0)
     finally:
         spec.close(); gen.close()
 
