@@ -4,7 +4,7 @@ Host-side mirror of the reference interface for this path (Model / addnode! / ad
 assemble! / solve(SweepX)), over the C ABI in include/muscade_b200.h.  The directory name contains a dot, so the package
 is imported through the loader `muscade_b200.py` at the repository root (`import muscade_b200`).
 """
-from . import _lib, toolbox, synthetic, model, sweepx, directxua, sharding, examples, adiff2, xua  # noqa: F401
+from . import _lib, toolbox, synthetic, model, sweepx, directxua, sharding, examples, adiff2, xua, eigx  # noqa: F401
 from ._lib import MuscadeB200Error, build  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .model import Model, addnode, addelement, setscale, initialize, Disassembler, State, getdof  # noqa: F401

@@ -333,6 +333,34 @@ function assemblebig!(out::AssemblyDirectB200{OX,OU}, model, dis, state::Vector,
     return
 end
 
+"""
+    K,C,M = step_matrices(out,step)
+
+`out.L2[ind.Λ,ind.X][1,1]`, `[1,2]`, `[1,3]` of one evaluated step as `SparseMatrixCSC` — what `solve(EigX{ℝ})` / `solve(EigX{ℂ})` read after their single
+`assemble!{:matrices}(out::AssemblyDirect{2,0,0},…)` (src/EigX.jl:33-40, 106-113): with `AssemblyDirectB200{2,0,0}` (nstep = 6, lo = 0, hi = 1, the state uploaded to step 0,
+`mb_direct_assemble(h,0,1,0,…)`) EigX runs on the device assembly.  Mirrors muscade.jl_b200/eigx.py, which the GPU tests run against test/TestEigX.jl's goldens.
+"""
+function step_matrices(out::AssemblyDirectB200{OX}, step=out.lo) where {OX}
+    n = Ref{Int64}()
+    check(out.h, ccall((:mb_direct_class_pattern, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int64}, Ptr{Int64}, Ptr{Int64}), out.h, 0, n, C_NULL, C_NULL))
+    nX     = getndofX(out)
+    colptr = Vector{Int64}(undef, nX + 1); rowval = Vector{Int64}(undef, n[])
+    check(out.h, ccall((:mb_direct_class_pattern, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int64}, Ptr{Int64}, Ptr{Int64}), out.h, 0, n, colptr, rowval))
+    mats = map(0:OX) do der
+        nz = Vector{𝕣}(undef, n[])
+        check(out.h, ccall((:mb_direct_get_step_block, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int32, Ptr{𝕣}), out.h, step, 1, der, nz))
+        SparseMatrixCSC(nX, nX, colptr, rowval, nz)
+    end
+    return mats
+end
+"number of X-dofs of the model behind a handle (mb_direct_get_state writes nX values per derivative; the shim reports it through the size of the L1[Λ] block)"
+function getndofX(out::AssemblyDirectB200)
+    p, n = Ref{Ptr{𝕣}}(), Ref{Int64}()
+    check(out.h, ccall((:mb_direct_step_ptrs, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{𝕣}}, Ref{Int64}, Ref{Ptr{𝕣}}, Ref{Int64}, Ref{Ptr{𝕣}}, Ref{Int64}),
+                     out.h, out.lo, Ref{Ptr{𝕣}}(), Ref{Int64}(), Ref{Ptr{𝕣}}(), Ref{Int64}(), p, n))
+    return Int(n[])
+end
+
 "cLvv = sparser!(Lvv,rtol) on the device (src/SparseTools.jl:172-199, called at src/DirectXUA.jl:486): the owned columns, global rows, compacted"
 function sparser(out::AssemblyDirectB200, rtol=1e-9)
     n = Ref{Int64}()

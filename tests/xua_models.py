@@ -233,3 +233,40 @@ def model_chain(n, rng, ox=2):
     mb.addelement(m, mb.SingleUdof, nod[:, None], Xfield="tx1", Ufield="utx1", cost=fu)
     mb.addelement(m, mb.SingleDofCost, nod[::2, None], clas="X", field="tx1", cost=l1)
     return m
+
+
+class SdofOscillator(mb.LagrangianElement):
+    """SdofOscillator (test/SomeElements.jl:191-207): R = −u + K₁x + K₂x² + C₁x′ + C₂x′² + M₁x″ + M₂x″²; dofs (X tx1, U tu1); the parameters are element data"""
+    type_parameters = ()
+
+    @classmethod
+    def doflist(cls, **kw):
+        return (1, 1), ("X", "U"), ("tx1", "tu1")
+
+    @classmethod
+    def construct(cls, coords, K1=0., K2=0., C1=0., C2=0., M1=0., M2=0.):
+        return np.tile(np.array([[K1, K2, C1, C2, M1, M2]], float), (coords[0].shape[0], 1))
+
+    @staticmethod
+    def residual(o, extra, X, U, A, t, SP):
+        x = X[0][0]
+        r = -U[0][0] + o[:, 0] * x + o[:, 1] * x * x
+        if len(X) > 1:
+            r = r + o[:, 2] * X[1][0] + o[:, 3] * X[1][0] * X[1][0]
+        if len(X) > 2:
+            r = r + o[:, 4] * X[2][0] + o[:, 5] * X[2][0] * X[2][0]
+        return [r]
+
+
+def model_testeigx():
+    """test/TestEigX.jl:6-24: 10 Spring{1} between 11 nodes on a line (A-dofs on a node of their own), a mass-damper on every node, a unit spring to ground at node 1"""
+    nel, L, EA = 10, 10., 1.
+    nnod = nel + 1
+    M, Cd = 10. / nnod, 3. / nnod
+    m = mb.Model("TestEigX")
+    xnod = mb.addnode(m, np.linspace(0., L, nnod)[:, None])
+    anod = mb.addnode(m, np.zeros((1, 0)))[0]
+    mb.addelement(m, Spring1, np.stack([xnod[:-1], xnod[1:], np.full(nel, anod)], axis=1), EA=EA)
+    mb.addelement(m, SdofOscillator, xnod[:, None], M1=M, C1=Cd)
+    mb.addelement(m, SdofOscillator, xnod[:1, None], K1=1.)
+    return m
