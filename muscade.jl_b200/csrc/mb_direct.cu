@@ -40,12 +40,15 @@ __device__ __forceinline__ int find_group(const uint32_t* pbase, int n, uint32_t
 // XX-type pattern: L2[Λ,X][1,der] and L2[X,Λ][der,1] of one step (add_∂!{1} and add_∂!{1,:plus,:transpose}, DirectXUA.jl:114-115)
 // Measured and dropped: one thread per pair of non-zeros with the pair / split descriptors of kernels.cuh instead of the cstart → src walk, all loads issued
 // before the sums: 0.30 ms per step of 10⁵ elements either way — the strided loads of the transposed block and the 2·nd stores bound it, not the index chain.
+// L2[X,Λ][der,1] is the transpose of L2[Λ,X][1,der] and the X-X class pattern is structurally symmetric (every element couples all its dofs both ways), with the contributors of
+// (i,j) and (j,i) the same elements in the same order: the thread of non-zero k = (i,j) stores its sum at XL[permT[k]], permT[k] = the non-zero (j,i) — bit-identical to summing
+// ∂R_j/∂X_i itself, without the strided loads of the transposed entries (a sector fetched per 8 bytes used)
 __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd,
-                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL, int64_t sdR) {
+                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL, int64_t sdR, const uint32_t* __restrict__ permT) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     dR += (int64_t)blockIdx.y * sdR; LX += (int64_t)blockIdx.y * nd * nnz; XL += (int64_t)blockIdx.y * nd * nnz;      // step batching: one grid row per time step
-    double a[3] = {0., 0., 0.}, b[3] = {0., 0., 0.};
+    double a[3] = {0., 0., 0.};
     for (uint32_t s = cstart[k]; s < cstart[k + 1]; ++s) {
         const uint32_t id = src[s];
         const int g = find_group(G.pbase[P_XX], G.n, id);
@@ -53,9 +56,21 @@ __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
         const int nx = G.nx[g], n2 = nx * nx;
         const int64_t e = loc / n2; const int r = (int)(loc - e * n2); const int jj = r / nx, i = r - nx * jj;
         const double* d = dR + G.drbase[g] + e * (int64_t)(nx * G.np[g]);
-        for (int der = 0; der < nd; ++der) { a[der] += d[(nx * der + jj) * nx + i]; b[der] += d[(nx * der + i) * nx + jj]; }
+        for (int der = 0; der < nd; ++der) a[der] += d[(nx * der + jj) * nx + i];
     }
-    for (int der = 0; der < nd; ++der) { LX[der * nnz + k] = a[der]; XL[der * nnz + k] = b[der]; }
+    const int64_t kt = permT[k];
+    for (int der = 0; der < nd; ++der) { LX[der * nnz + k] = a[der]; XL[der * nnz + kt] = a[der]; }
+}
+// permT of a structurally symmetric CSC pattern: one thread per column j, binary search of row j in column i for each of its rows i
+__global__ void transpose_perm_kernel(int64_t ncol, const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval, uint32_t* __restrict__ permT, unsigned long long* bad) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncol) return;
+    for (int32_t k = colptr[j]; k < colptr[j + 1]; ++k) {
+        const int32_t i = rowval[k];
+        int32_t lo = colptr[i], hi = colptr[i + 1];
+        while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (rowval[mid] < j) lo = mid + 1; else hi = mid; }
+        if (lo < colptr[i + 1] && rowval[lo] == j) permT[k] = (uint32_t)lo; else { permT[k] = (uint32_t)k; atomicAdd(bad, 1ULL); }
+    }
 }
 // XU-type (rows X dofs, cols U dofs): L2[Λ,U][1,1];  UX-type: L2[U,Λ][1,1].  Only ∂0(U) enters the toolbox elements.
 __global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd, int transposed,
@@ -491,6 +506,7 @@ struct DirectData {
     bool elements_only = false;                         // timing aid: direct_eval_steps launches the element kernels without the per-step reductions
     // costed beam types (mb_direct_set_gauge_cost): per stored step L2[X,X][1,1] and L1[U][1]; scratch of one step (J, e4, gX, HXX, GU, costs); U-dof contributor lists;
     // per type the measurements of every stored step [step][ng] or [step][nele][ng]
+    uint32_t* permT = nullptr;                          // X-X class pattern: position of the transposed non-zero (gather_xx_kernel)
     bool costed = false; int64_t ncost = 0, nqu = 0;
     double *XXc = nullptr, *L1U = nullptr, *cJ = nullptr, *ce4 = nullptr, *cgX = nullptr, *cHXX = nullptr, *cGU = nullptr, *ccost = nullptr, *csL = nullptr;
     uint32_t *vstartU = nullptr, *vsrcU = nullptr;
@@ -545,6 +561,15 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     if ((rc = build_pattern(h, D->pat[P_XU], false, true, ndofX, ndofU))) return rc;
     if ((rc = build_pattern(h, D->pat[P_UX], true, false, ndofU, ndofX))) return rc;
     if ((rc = build_pattern(h, D->pat[P_UU], true, true, ndofU, ndofU))) return rc;
+    if (D->pat[P_XX].nnz) {                              // transpose map of the (structurally symmetric) X-X pattern
+        const PairPat& XX = D->pat[P_XX];
+        CK(dalloc(h, &D->permT, XX.nnz));
+        unsigned long long* bad = nullptr; CK(dalloc(h, &bad, 1)); CK(cudaMemsetAsync(bad, 0, 8, st));
+        transpose_perm_kernel<<<nblk(ndofX, 256), 256, 0, st>>>(ndofX, XX.colptr0, XX.rowval0, D->permT, bad);
+        h->launches++;
+        unsigned long long nbad = 0; CK(cudaMemcpyAsync(&nbad, bad, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); dfree(h, bad);
+        ARG(nbad == 0, "internal: the X-X class pattern is not structurally symmetric");
+    }
     // vector contributors (asmvec! for the Λ group)
     int64_t nvec = 0, ndr = 0;
     D->G.n = (int)h->groups.size();
@@ -811,7 +836,7 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
         }
         if (D->elements_only) continue;
         const PairPat& XX = D->pat[P_XX];
-        if (XX.nnz) { gather_xx_kernel<<<dim3(nblk(XX.nnz, 256), nb), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz, ndr); h->launches++; }
+        if (XX.nnz) { gather_xx_kernel<<<dim3(nblk(XX.nnz, 256), nb), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz, ndr, D->permT); h->launches++; }
         const PairPat& XU = D->pat[P_XU];
         if (XU.nnz) { gather_xu_kernel<<<dim3(nblk(XU.nnz, 256), nb), 256, 0, st>>>(XU.nnz, XU.cstart, XU.src, D->G, nd, 0, D->dR, D->LU + k * XU.nnz, ndr); h->launches++; }
         const PairPat& UX = D->pat[P_UX];
