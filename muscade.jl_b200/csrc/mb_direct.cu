@@ -44,7 +44,8 @@ __device__ __forceinline__ int find_group(const uint32_t* pbase, int n, uint32_t
 // (i,j) and (j,i) the same elements in the same order: the thread of non-zero k = (i,j) stores its sum at XL[permT[k]], permT[k] = the non-zero (j,i) — bit-identical to summing
 // ∂R_j/∂X_i itself, without the strided loads of the transposed entries (a sector fetched per 8 bytes used)
 __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd,
-                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL, int64_t sdR, const uint32_t* __restrict__ permT) {
+                                 const double* __restrict__ dR, double* __restrict__ LX, double* __restrict__ XL, int64_t sdR, const uint32_t* __restrict__ permT,
+                                 const double* __restrict__ slrow) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     dR += (int64_t)blockIdx.y * sdR; LX += (int64_t)blockIdx.y * nd * nnz; XL += (int64_t)blockIdx.y * nd * nnz;      // step batching: one grid row per time step
@@ -56,7 +57,11 @@ __global__ void gather_xx_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
         const int nx = G.nx[g], n2 = nx * nx;
         const int64_t e = loc / n2; const int r = (int)(loc - e * n2); const int jj = r / nx, i = r - nx * jj;
         const double* d = dR + G.drbase[g] + e * (int64_t)(nx * G.np[g]);
-        for (int der = 0; der < nd; ++der) a[der] += d[(nx * der + jj) * nx + i];
+        if (G.hxxbase[g] >= 0) {                   // costed beam type: the Λ rows are differentiated with respect to the SCALED Λ (rows of ∂R/∂seed times scale.Λ)
+            const double sl = slrow[g * 12 + i];
+            for (int der = 0; der < nd; ++der) a[der] += d[(nx * der + jj) * nx + i] * sl;
+        } else
+            for (int der = 0; der < nd; ++der) a[der] += d[(nx * der + jj) * nx + i];
     }
     const int64_t kt = permT[k];
     for (int der = 0; der < nd; ++der) { LX[der * nnz + k] = a[der]; XL[der * nnz + kt] = a[der]; }
@@ -74,7 +79,7 @@ __global__ void transpose_perm_kernel(int64_t ncol, const int32_t* __restrict__ 
 }
 // XU-type (rows X dofs, cols U dofs): L2[Λ,U][1,1];  UX-type: L2[U,Λ][1,1].  Only ∂0(U) enters the toolbox elements.
 __global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, int nd, int transposed,
-                                 const double* __restrict__ dR, double* __restrict__ out, int64_t sdR) {
+                                 const double* __restrict__ dR, double* __restrict__ out, int64_t sdR, const double* __restrict__ slrow) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     dR += (int64_t)blockIdx.y * sdR; out += (int64_t)blockIdx.y * nnz;
@@ -89,7 +94,8 @@ __global__ void gather_xu_kernel(int64_t nnz, const uint32_t* __restrict__ cstar
         int ix, ju;
         if (!transposed) { ju = r / nx; ix = r - nx * ju; }      // rows X (nx), cols U (3): r = ix + nx·ju
         else { ix = r / 3; ju = r - 3 * ix; }                     // rows U (3), cols X (nx): r = ju + 3·ix
-        a += dR[G.drbase[g] + e * (int64_t)(nx * G.np[g]) + (nx * nd + ju) * nx + ix];
+        const double v = dR[G.drbase[g] + e * (int64_t)(nx * G.np[g]) + (nx * nd + ju) * nx + ix];
+        a += (G.hxxbase[g] >= 0) ? v * slrow[g * 12 + ix] : v;
     }
     out[k] = a;
 }
@@ -136,25 +142,33 @@ __global__ void vstart2_kernel(int64_t nvec, const uint32_t* __restrict__ keys, 
 // (DirectXUA_lagrangian_addition! differentiates with respect to the scaled Λ), so that the reductions of the plain path give L1[Λ], L2[Λ,X], L2[X,Λ], L2[Λ,U], L2[U,Λ].
 struct SL12 { double v[12]; };
 __global__ void __launch_bounds__(128) costed_fill_kernel(int64_t nele, int nd, int npd, const int32_t* __restrict__ idxX, const double* __restrict__ Lam, SL12 sL,
-                                                          const double* __restrict__ gX, double* __restrict__ R, double* __restrict__ dR, double* __restrict__ GX, double* __restrict__ GU,
+                                                          const double* __restrict__ gX, double* __restrict__ R, const double* __restrict__ dR, double* __restrict__ GX, double* __restrict__ GU,
                                                           StepBatch sb, int64_t sE, int64_t sGU) {
-    __shared__ double sm[39 * 12];
-    __shared__ double lam[12], sl[12];
+    // one WARP per element (a CTA per element left 89 of its 128 threads idle behind a barrier): lane p < npd owns row p of ∂R/∂seed — 12 consecutive doubles, six 16-byte loads
     { const int64_t b = blockIdx.y; Lam += b * sb.sLam; gX += b * sE * 12; R += b * sb.sR; dR += b * sb.sdR; GX += b * sb.sGX; if (GU) GU += b * sGU; }      // step batching: grid row = time step
-    const int64_t e = blockIdx.x;
-    const int n = npd * 12;
-    for (int q = threadIdx.x; q < n; q += blockDim.x) sm[q] = dR[e * n + q];
-    if (threadIdx.x < 12) { lam[threadIdx.x] = Lam[idxX[e * 12 + threadIdx.x]]; sl[threadIdx.x] = sL.v[threadIdx.x]; }
-    __syncthreads();
-    if ((int)threadIdx.x < npd) {
-        const int p = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= nele) return;
+    double lam = (lane < 12) ? Lam[idxX[e * 12 + lane]] : 0.;
+    double l[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) l[k] = __shfl_sync(0xffffffffu, lam, k);
+    const double* base = dR + e * (int64_t)(npd * 12);
+    const bool al = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    for (int p = lane; p < npd; p += 32) {
+        const double* row = base + p * 12;
         double acc = 0.;
-        for (int k = 0; k < 12; ++k) acc += lam[k] * sm[p * 12 + k];
+        if (al) {
+#pragma unroll
+            for (int k = 0; k < 12; k += 2) { const double2 v = *reinterpret_cast<const double2*>(row + k); acc += l[k] * v.x; acc += l[k + 1] * v.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc += l[k] * row[k];
+        }
         if (p < 12 * nd) { const int d = p / 12, i = p - 12 * d; GX[(e * 12 + i) * nd + d] = acc + (d == 0 ? gX[e * 12 + i] : 0.); }
         else if (GU) GU[e * 3 + (p - 12 * nd)] = acc;
     }
-    for (int q = threadIdx.x; q < n; q += blockDim.x) dR[e * n + q] = sm[q] * sl[q % 12];
-    if (threadIdx.x < 12) R[e * 12 + threadIdx.x] *= sl[threadIdx.x];
+    if (lane < 12) R[e * 12 + lane] *= sL.v[lane];      // the rows of ∂R/∂seed get their scale.Λ in the reductions (gather_xx / gather_xu_kernel): no rewrite of dR
 }
 // L2[X,X][1,1] of one step from the costs' Gauss-Newton blocks HXX[e][12][12] (costed beam types only; the reference's accumulation order over the X-X pattern)
 __global__ void gather_xxc_kernel(int64_t nnz, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ src, DirGroups G, const double* __restrict__ HXX, double* __restrict__ out,
@@ -506,6 +520,7 @@ struct DirectData {
     bool elements_only = false;                         // timing aid: direct_eval_steps launches the element kernels without the per-step reductions
     // costed beam types (mb_direct_set_gauge_cost): per stored step L2[X,X][1,1] and L1[U][1]; scratch of one step (J, e4, gX, HXX, GU, costs); U-dof contributor lists;
     // per type the measurements of every stored step [step][ng] or [step][nele][ng]
+    double* slrow = nullptr;                            // [group][12] scale.Λ of the residual rows of costed beam types (scale.X·Λscale), read by the reductions
     uint32_t* permT = nullptr;                          // X-X class pattern: position of the transposed non-zero (gather_xx_kernel)
     bool costed = false; int64_t ncost = 0, nqu = 0;
     double *XXc = nullptr, *L1U = nullptr, *cJ = nullptr, *ce4 = nullptr, *cgX = nullptr, *cHXX = nullptr, *cGU = nullptr, *ccost = nullptr, *csL = nullptr;
@@ -539,6 +554,8 @@ static BigDev make_bigdev(const DirectData* D) {
 void mb_direct_release(mb_handle* h) { if (h && h->direct) { delete h->direct; h->direct = nullptr; } }
 
 extern "C" {
+
+static int32_t upload_slrow(mb_handle* h);
 
 int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, int64_t ndofU, int64_t nstep, int64_t step_lo, int64_t step_hi, double dt,
                           const int32_t* bcolptr, const int32_t* browval, int64_t* ncol_out, int64_t* nnz_out) {
@@ -723,7 +740,7 @@ int32_t mb_direct_prepare(mb_handle* h, int32_t OX, int32_t OU, int64_t ndofX, i
     h->prepared = true;
     if (ncol_out) *ncol_out = D->ncol;
     if (nnz_out) *nnz_out = D->nnzbig;
-    return MB_OK;
+    return upload_slrow(h);
 }
 
 int32_t mb_direct_class_pattern(mb_handle* h, int32_t which, int64_t* nnz, int64_t* colptr, int64_t* rowval) {
@@ -829,18 +846,18 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
                 gauge_cost_kernel<<<dim3(nblk(g.nele * 12, 128), nb), 128, 0, st>>>(g.nele, g.ng, g.gaugeG, m.eps + k * m.stride, m.per_element, g.isig2, D->cJ + eb * 48, D->ce4 + eb * 4,
                                                                                     D->cgX + eb * 12, D->cHXX + eb * 144, D->ccost + eb, m.stride, nc);
                 SL12 sl; for (int i = 0; i < 12; ++i) sl.v[i] = g.scaleX[i] * D->lamscale;
-                costed_fill_kernel<<<dim3((unsigned)g.nele, nb), 128, 0, st>>>(g.nele, nd, D->G.np[ig], g.idxX, D->Lam + k * D->nX, sl, D->cgX + eb * 12, R, dR, D->GX + D->G.gxbase[ig] * nd,
+                costed_fill_kernel<<<dim3((unsigned)((g.nele + 3) / 4), nb), 128, 0, st>>>(g.nele, nd, D->G.np[ig], g.idxX, D->Lam + k * D->nX, sl, D->cgX + eb * 12, R, dR, D->GX + D->G.gxbase[ig] * nd,
                                                                                D->gubase[ig] >= 0 && D->cGU ? D->cGU + D->gubase[ig] : nullptr, sb, nc, D->nqu);
                 h->launches += 3;
             }
         }
         if (D->elements_only) continue;
         const PairPat& XX = D->pat[P_XX];
-        if (XX.nnz) { gather_xx_kernel<<<dim3(nblk(XX.nnz, 256), nb), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz, ndr, D->permT); h->launches++; }
+        if (XX.nnz) { gather_xx_kernel<<<dim3(nblk(XX.nnz, 256), nb), 256, 0, st>>>(XX.nnz, XX.cstart, XX.src, D->G, nd, D->dR, D->LX + k * nd * XX.nnz, D->XL + k * nd * XX.nnz, ndr, D->permT, D->slrow); h->launches++; }
         const PairPat& XU = D->pat[P_XU];
-        if (XU.nnz) { gather_xu_kernel<<<dim3(nblk(XU.nnz, 256), nb), 256, 0, st>>>(XU.nnz, XU.cstart, XU.src, D->G, nd, 0, D->dR, D->LU + k * XU.nnz, ndr); h->launches++; }
+        if (XU.nnz) { gather_xu_kernel<<<dim3(nblk(XU.nnz, 256), nb), 256, 0, st>>>(XU.nnz, XU.cstart, XU.src, D->G, nd, 0, D->dR, D->LU + k * XU.nnz, ndr, D->slrow); h->launches++; }
         const PairPat& UX = D->pat[P_UX];
-        if (UX.nnz) { gather_xu_kernel<<<dim3(nblk(UX.nnz, 256), nb), 256, 0, st>>>(UX.nnz, UX.cstart, UX.src, D->G, nd, 1, D->dR, D->UL + k * UX.nnz, ndr); h->launches++; }
+        if (UX.nnz) { gather_xu_kernel<<<dim3(nblk(UX.nnz, 256), nb), 256, 0, st>>>(UX.nnz, UX.cstart, UX.src, D->G, nd, 1, D->dR, D->UL + k * UX.nnz, ndr, D->slrow); h->launches++; }
         gather_l1_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart, D->vsrc, D->R, D->L1L + k * D->nX, nvec);
         h->launches++;
         if (D->ngx) { gather_l1x_kernel<<<dim3(nblk(D->nX, 256), nb), 256, 0, st>>>(D->nX, D->vstart2, D->vsrc2, D->GX, nd, D->L1X + k * nd * D->nX, ngxd); h->launches++; }
@@ -888,10 +905,22 @@ int32_t mb_direct_set_gauge_measurements(mb_handle* h, int64_t step, int32_t iel
     m.have[(size_t)(step - D->elo)] = 1;
     return MB_OK;
 }
+static int32_t upload_slrow(mb_handle* h) {
+    DirectData* D = h->direct;
+    if (!D->costed) return MB_OK;
+    std::vector<double> sl(h->groups.size() * 12, 1.);
+    for (size_t ig = 0; ig < h->groups.size(); ++ig)
+        if (h->groups[ig].kind == G_BEAM && h->groups[ig].ng > 0) for (int i = 0; i < 12; ++i) sl[ig * 12 + i] = h->groups[ig].scaleX[i] * D->lamscale;
+    if (!D->slrow) CK(dalloc(h, &D->slrow, (int64_t)sl.size()));
+    CK(cudaMemcpyAsync(D->slrow, sl.data(), sl.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MB_OK;
+}
 int32_t mb_direct_set_lambda_scale(mb_handle* h, double lambda_scale) {
     if (!h || !h->direct) return MB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
     h->direct->lamscale = lambda_scale;
-    return MB_OK;
+    return upload_slrow(h);
 }
 int32_t mb_direct_set_time0(mb_handle* h, double t0) {
     if (!h || !h->direct) return MB_ERR_ARG;
