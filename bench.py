@@ -82,6 +82,14 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def count(self):
+        """samples written so far"""
+        try:
+            with open(self.f.name) as f:
+                return sum(1 for line in f if line.count(",") >= 8)
+        except OSError:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -111,6 +119,15 @@ class ClockSampler:
         except OSError:
             pass
         return out
+
+
+def ensure_samples(sampler, comm, load):
+    """nvidia-smi samples every 100 ms and needs a moment to start: when fewer than two samples fell inside a short timed region, repeat the same launches UNTIMED under the
+    sampler (all ranks together) until it has them"""
+    for _ in range(8):
+        if comm.max(1. if (sampler is not None and sampler.count() < 2) else 0.) == 0.:
+            break
+        load()
 
 
 def cpu_port_rate(mb, OX, nsample, nthreads):
@@ -264,16 +281,21 @@ def run_sweepx(args, rank, world, local, comm, OX=None, N=None, steps=None, bloc
 
     # a step = mb_sweepx_assemble_dev (+ mb_iface_exchange on a shard), exactly as a solver issues it; mb_sweepx_time_step_dev runs `reps` of them
     # between two CUDA events on the engine's stream
+    # nvidia-smi samples every 100 ms and needs a moment to start, the timed region of 10 steps lasts 0.2 s: the sampler runs from the warm-up on (the same steps), and when
+    # fewer than two samples fell inside, the same steps are repeated UNTIMED under it (all ranks together: a step may hold an exchange) until it has them
+    sampler = ClockSampler(local) if rank == 0 else None
     eng.time_step_dev(OX, "iter", nm, reps=max(1, args.warmup))
     barrier()
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     step_ms = comm.max(eng.time_step_dev(OX, "iter", nm, reps=steps))
     barrier()
     wall = time.perf_counter() - t0
     launches = eng.launch_count() - launches0
+    ensure_samples(sampler, comm, lambda: (eng.time_step_dev(OX, "iter", nm, reps=steps), barrier()))
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up and timed steps (the same launches), plus untimed repeats of them when the region is shorter than two sampling periods"
     el_ms, ga_ms = eng.time_dev(OX, "iter", nm, reps=max(3, min(args.steps, 5)))      # same launch sets with an event between element kernels and reduction
     barrier()
     value = world * N / (step_ms * 1e-3)
@@ -703,6 +725,7 @@ def run_scr(args, rank, world, local, comm, block=False):
     a_ms, b_ms = eng.direct_time(reps=1)              # breakdown of the owned steps (CUDA events inside the engine)
     barrier()
     launches = eng.launch_count() - launches0
+    ensure_samples(sampler, comm, lambda: ([eng.direct_assemble() for _ in range(steps)], barrier()))
     clocks = sampler.stop() if sampler else None
     el_ms = eng.last_element_ms
     e2e = None
@@ -782,6 +805,7 @@ def run_gauges(args, rank, world, local, comm):
     check(eng.h, eng.L.mb_xua_time_device_pass(eng.h, args.steps, ms))      # CUDA events on the engine's stream around `steps` whole passes (after one more warm-up pass)
     step_ms = comm.max(float(ms[0]))
     launches = (eng.launch_count() - launches0) * args.steps // (args.steps + 1)
+    ensure_samples(sampler, comm, lambda: check(eng.h, eng.L.mb_xua_time_device_pass(eng.h, args.steps, ms)))
     clocks = sampler.stop() if sampler else None
     line = None
     if rank == 0:
