@@ -582,15 +582,18 @@ template <int ND> __device__ __forceinline__ void load_direct_state(const BeamGr
 #pragma unroll
     for (int i = 0; i < 3; ++i) { U[i].v = g.udof ? st.U0[g.idxU[e * 3 + i]] : 0.; U[i].d1 = 0.; }
 }
-template <int ND>
+// D1 (ND = 3): the launch of the X′-seeded lanes alone (thread t ↔ lane per + t), with the order-0 Taylor coefficients as plain values (NumJet1); the plain launch then covers
+// the X₀ lanes only.  One instantiation of the jet code per KERNEL: each stays inside the instruction cache.
+template <int ND, bool D1 = false>
 __global__ void __launch_bounds__(MB_BLOCK, MB_MINB)
 beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ Wc, StepBatch sb) {
     using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
     batch_state(st, sb); Wc += (int64_t)blockIdx.y * sb.sWc;
     constexpr int NDJ = (ND >= 3) ? 2 : ND;            // derivative orders that need their own time-jet lanes: X₀ and X′ (X″ comes with X₀)
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = g.nele * 6;
-    if (t >= per * NDJ) return;
+    if constexpr (ND >= 3) { if (t >= per) return; if (D1) t += per; }
+    else if (t >= per * NDJ) return;
     const int d = (int)(t / per);
     const int64_t r = t - d * per, e = r / 6;
     const int l = (int)(r - e * 6);
@@ -600,10 +603,12 @@ beam_direct_cot_kernel(BeamGroupDev g, DirectStateDev st, double* __restrict__ W
     TU Xu[3][6], U[3]; TR Xv[3][6];
     load_direct_state<ND>(g, st, e, d, l, Xu, Xv, U);
     Vec3<TS> xb[NGP], vsmb;
-    if constexpr (ND >= 3) {                           // one copy of the jet code for both lane kinds (two would leave the instruction cache)
+    if constexpr (ND >= 3 && D1) {
+        beam_dyn_cotangents<ND, N, false, true>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, nullptr, nullptr, l < 3);
+    } else if constexpr (ND >= 3) {
         Vec3<TS> xb2[NGP], vsmb2;
         beam_dyn_cotangents<ND, N, true>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, xb2, &vsmb2, l < 3);
-        if (d == 0) store_cot(Wc, 2 * per + t, xb2, vsmb2);        // the tile the X″ lane (2,e,l) of the linear kernel reads
+        store_cot(Wc, 2 * per + t, xb2, vsmb2);                    // the tile the X″ lane (2,e,l) of the linear kernel reads
     } else
         beam_dyn_cotangents<ND, N>(geo, m, Xu, Xv, g.udof != 0, U, xb, vsmb, nullptr, nullptr, l < 3);
     store_cot(Wc, t, xb, vsmb);
@@ -715,7 +720,11 @@ template <int ND> int launch_beam_direct(const BeamGroupDev& g, const DirectStat
                                             const StepBatch& sb, int nb) {                                                                    \
         const int64_t per = g.nele * 6, nlin = per * (ND_ - 1) + (g.udof ? 2 * g.nele : 0);                                                  \
         int n = 1;                                                                                                                            \
-        if (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<dim3((unsigned)((per * (ND_ >= 3 ? 2 : ND_) + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, Wc, sb); ++n; } \
+        if constexpr (ND_ >= 3) {                                                                                                             \
+            beam_direct_cot_kernel<(ND_ >= 3 ? ND_ : 3), false><<<dim3((unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, Wc, sb);  \
+            beam_direct_cot_kernel<(ND_ >= 3 ? ND_ : 3), true><<<dim3((unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, Wc, sb);   \
+            n += 2;                                                                                                                           \
+        } else if constexpr (ND_ >= 2) { beam_direct_cot_kernel<(ND_ >= 2 ? ND_ : 2)><<<dim3((unsigned)((per * ND_ + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, Wc, sb); ++n; } \
         beam_direct_b0_kernel<ND_><<<dim3((unsigned)((per + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, dR, R, nanflag, nanbase, Wc, sb);      \
         if (nlin) { beam_direct_lin_kernel<ND_><<<dim3((unsigned)((nlin + MB_BLOCK - 1) / MB_BLOCK), nb), MB_BLOCK, 0, s>>>(g, st, dR, nanflag, nanbase, Wc, sb); ++n; } \
         return n;                                                                                                                             \

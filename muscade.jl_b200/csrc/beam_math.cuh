@@ -19,6 +19,7 @@
 // Branches of the reference's special functions (sinc1 family thresholds, scac series, norm3 cutoff, drag sign)
 // are reproduced on VALUE, as the reference does (Adiff.jl:198-202).
 #pragma once
+#include <type_traits>
 #include "sdual.cuh"
 
 namespace mb {
@@ -111,6 +112,10 @@ template <int W> using NumDual = Num<Dual<W>, Dual<W>, Dual<W>>;
 using NumSD = Num<SD<true, false>, SD<false, true>, SD<true, true>>;
 using NumVal = Num<SD<false, false>, SD<false, false>, SD<false, false>>;     // plain values behind the SD interface
 template <class N> using NumJet = Num<Jet<typename N::TR>, Jet<typename N::TU>, Jet<typename N::TS>>;
+// time-jets of lanes whose seeds sit on the VELOCITIES (DirectXUA's ∂/∂X′ lanes): every order-0 coefficient is free of partials by construction, so it is a plain value
+// and products with it cost a direction less (the velocity and acceleration coefficients carry the partials)
+using PlainSD = SD<false, false>;
+template <class N> using NumJet1 = Num<Jet<PlainSD, typename N::TR, typename N::TR>, Jet<PlainSD, typename N::TU, typename N::TU>, Jet<PlainSD, typename N::TS, typename N::TS>>;
 
 // ------------------------------------------------------------------------------------------------ scratch (explicit spill space)
 // The reverse sweep needs rₛ₂ and Rodrigues(Δvᵧ) only at its very end; parking them in per-thread scratch (shared memory on the
@@ -618,7 +623,7 @@ template <class F, class S> MB_HD void beam_gp_reverse_f(const GpConst& c, doubl
 // strips the partial slots: the passive node's numbers
 MB_HD SD<false, false> strip(const SD<false, false>& x) { return x; }
 template <bool A, bool B> MB_HD SD<false, false> strip(const SD<A, B>& x) { SD<false, false> r; r.v = x.v; return r; }
-template <class T> MB_HD auto strip(const Jet<T>& x) -> Jet<decltype(strip(x.c0))> { Jet<decltype(strip(x.c0))> r; r.c0 = strip(x.c0); r.c1 = strip(x.c1); r.c2 = strip(x.c2); return r; }
+template <MB_J3(T)> MB_HD auto strip(const MB_JT(T)& x) -> Jet<decltype(strip(x.c0))> { Jet<decltype(strip(x.c0))> r; r.c0 = strip(x.c0); r.c1 = strip(x.c1); r.c2 = strip(x.c2); return r; }
 // MB_DYN_AP: the Newmark / DirectXUA lanes (NumSD: rotation dof l and translation dof l, both of node ⌊l/3⌋+1) run the active/passive formulation
 #ifndef MB_DYN_AP
 #define MB_DYN_AP 1
@@ -638,13 +643,13 @@ template <int ND, class N, bool DD, class F> MB_HD void beam_dyn_cot_tail(const 
                                                                           Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb,
                                                                           Vec3<typename N::TS>* xb2, Vec3<typename N::TS>* vsmb2) {
     using TR = typename N::TR; using S = typename N::TS;
-    using JS = Jet<S>;
+    using R0 = decltype(fj.r.a[0].c0);                    // TR, or a plain value for the velocity-seeded lanes (NumJet1)
     const double L = g.L;
-    Mat3<TR> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
+    Mat3<R0> r0; for (int i = 0; i < 9; ++i) r0.a[i] = fj.r.a[i].c0;
     MB_PRAGMA(unroll MB_GP_UNROLL_DYN)
     for (int gp = 0; gp < NGP; ++gp) {
         const GpConst c = gp_const(gp);
-        Vec3<JS> p = beam_gp_local(c, L, fj.ul, fj.vl);
+        auto p = beam_gp_local(c, L, fj.ul, fj.vl);
         Vec3<S> x1, x2;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -692,17 +697,21 @@ template <int ND, class N, bool DD, class F> MB_HD void beam_dyn_cot_tail(const 
     }
 }
 // n1: the lane's seeds belong to node 1 (lanes 0-2) or node 2 (lanes 3-5) — only read by the active/passive formulation (ApOk<N>)
-template <int ND, class N, bool DD = false> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
+// V1: the lane's seeds sit on X′ only (Xu[0], Xv[0], Xu[2], Xv[2] carry zero partials): the jets run in NumJet1<N>
+template <int ND, class N, bool DD = false, bool V1 = false> MB_HD void beam_dyn_cotangents(const BeamGeo& g, const BeamMat& m, const typename N::TU (*Xu)[6], const typename N::TR (*Xv)[6],
                                                          bool udof, const typename N::TU* U0, Vec3<typename N::TS>* xb, Vec3<typename N::TS>& vsmb,
                                                          Vec3<typename N::TS>* xb2 = nullptr, Vec3<typename N::TS>* vsmb2 = nullptr, bool n1 = true) {
     using TR = typename N::TR; using TU = typename N::TU;
-    using NJ = NumJet<N>;
+    static_assert(!V1 || (ND >= 3 && !DD), "velocity-seeded jets: DirectXUA{2,…} lanes of ∂/∂X′");
+    using NJ = std::conditional_t<V1, NumJet1<N>, NumJet<N>>;
     using JR = typename NJ::TR; using JU = typename NJ::TU;
     JU XuJ[6]; JR XvJ[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        XuJ[i].c0 = Xu[0][i]; XuJ[i].c1 = Xu[1][i]; XuJ[i].c2 = (ND >= 3) ? Xu[2][i] : Make<TU>::c(0.);
-        XvJ[i].c0 = Xv[0][i]; XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
+        if constexpr (V1) { XuJ[i].c0 = strip(Xu[0][i]); XvJ[i].c0 = strip(Xv[0][i]); }
+        else { XuJ[i].c0 = Xu[0][i]; XvJ[i].c0 = Xv[0][i]; }
+        XuJ[i].c1 = Xu[1][i]; XuJ[i].c2 = (ND >= 3) ? Xu[2][i] : Make<TU>::c(0.);
+        XvJ[i].c1 = Xv[1][i]; XvJ[i].c2 = (ND >= 3) ? Xv[2][i] : Make<TR>::c(0.);
     }
     // ND = 3 stays on the symmetric form: under the reference's x^0 rule (sqr_ref, dual.cuh) the SECOND time derivative of Rodrigues is not the derivative of a
     // rotation, so Rodrigues(Δvᵧ)·rₛ₁ = Rodrigues(Δvᵧ)ᵀ·rₛ₂ — which the active/passive form rests on for the lanes of node 1 — holds for values and velocities

@@ -134,46 +134,55 @@ template <int W> MB_HD Dual<W> mb_acos(const Dual<W>& a) { Dual<W> r; r.v = acos
 template <int K, int W> MB_HD Dual<W> sinc1k(const Dual<W>& a) { Dual<W> r; r.v = sinc1k<K>(a.v); double m = sinc1k<K + 1>(a.v); MB_FORW r.d[i] = m * a.d[i]; return r; }
 
 // ------------------------------------------------------------------------------------------------ Jet<S>  (q, q̇, q̈)
-template <class S> struct Jet {
-    S c0, c1, c2;
+// Jet<S0,S1,S2>: the three Taylor coefficients may have different number types.  Jet<S> = Jet<S,S,S> is the general case; Jet<V,S,S> with V a plain value serves lanes whose
+// seeds sit on the VELOCITIES (DirectXUA's ∂/∂X′ lanes): every order-0 coefficient is then free of partials by construction and no arithmetic is emitted for them.
+template <class S0, class S1 = S0, class S2 = S1> struct Jet {
+    S0 c0; S1 c1; S2 c2;
 };
-template <class S> struct Make<Jet<S>> {
-    static MB_HD Jet<S> c(double v) { Jet<S> r; r.c0 = Make<S>::c(v); r.c1 = Make<S>::c(0.); r.c2 = Make<S>::c(0.); return r; }
+template <class S0, class S1, class S2> struct Make<Jet<S0, S1, S2>> {
+    static MB_HD Jet<S0, S1, S2> c(double v) { Jet<S0, S1, S2> r; r.c0 = Make<S0>::c(v); r.c1 = Make<S1>::c(0.); r.c2 = Make<S2>::c(0.); return r; }
 };
-template <class S> MB_HD double value(const Jet<S>& a) { return value(a.c0); }
-template <class S1, class S2> MB_HD auto operator+(const Jet<S1>& a, const Jet<S2>& b) -> Jet<decltype(a.c0 + b.c0)> { Jet<decltype(a.c0 + b.c0)> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; r.c2 = a.c2 + b.c2; return r; }
-template <class S> MB_HD Jet<S> operator+(const Jet<S>& a, double b) { Jet<S> r = a; r.c0 = a.c0 + b; return r; }
-template <class S> MB_HD Jet<S> operator+(double a, const Jet<S>& b) { Jet<S> r = b; r.c0 = a + b.c0; return r; }
-template <class S1, class S2> MB_HD auto operator-(const Jet<S1>& a, const Jet<S2>& b) -> Jet<decltype(a.c0 - b.c0)> { Jet<decltype(a.c0 - b.c0)> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; r.c2 = a.c2 - b.c2; return r; }
-template <class S> MB_HD Jet<S> operator-(const Jet<S>& a, double b) { Jet<S> r = a; r.c0 = a.c0 - b; return r; }
-template <class S> MB_HD Jet<S> operator-(double a, const Jet<S>& b) { Jet<S> r; r.c0 = a - b.c0; r.c1 = -b.c1; r.c2 = -b.c2; return r; }
-template <class S> MB_HD Jet<S> operator-(const Jet<S>& a) { Jet<S> r; r.c0 = -a.c0; r.c1 = -a.c1; r.c2 = -a.c2; return r; }
-template <class S1, class S2> MB_HD auto operator*(const Jet<S1>& a, const Jet<S2>& b) -> Jet<decltype(a.c0 * b.c0)> {
-    Jet<decltype(a.c0 * b.c0)> r;
+#define MB_J3(X) class X##0, class X##1, class X##2
+#define MB_JT(X) Jet<X##0, X##1, X##2>
+template <MB_J3(S)> MB_HD double value(const MB_JT(S)& a) { return value(a.c0); }
+template <MB_J3(A), MB_J3(B)> MB_HD auto operator+(const MB_JT(A)& a, const MB_JT(B)& b) -> Jet<decltype(a.c0 + b.c0), decltype(a.c1 + b.c1), decltype(a.c2 + b.c2)> {
+    Jet<decltype(a.c0 + b.c0), decltype(a.c1 + b.c1), decltype(a.c2 + b.c2)> r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; r.c2 = a.c2 + b.c2; return r;
+}
+template <MB_J3(S)> MB_HD MB_JT(S) operator+(const MB_JT(S)& a, double b) { MB_JT(S) r = a; r.c0 = a.c0 + b; return r; }
+template <MB_J3(S)> MB_HD MB_JT(S) operator+(double a, const MB_JT(S)& b) { MB_JT(S) r = b; r.c0 = a + b.c0; return r; }
+template <MB_J3(A), MB_J3(B)> MB_HD auto operator-(const MB_JT(A)& a, const MB_JT(B)& b) -> Jet<decltype(a.c0 - b.c0), decltype(a.c1 - b.c1), decltype(a.c2 - b.c2)> {
+    Jet<decltype(a.c0 - b.c0), decltype(a.c1 - b.c1), decltype(a.c2 - b.c2)> r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; r.c2 = a.c2 - b.c2; return r;
+}
+template <MB_J3(S)> MB_HD MB_JT(S) operator-(const MB_JT(S)& a, double b) { MB_JT(S) r = a; r.c0 = a.c0 - b; return r; }
+template <MB_J3(S)> MB_HD MB_JT(S) operator-(double a, const MB_JT(S)& b) { MB_JT(S) r; r.c0 = a - b.c0; r.c1 = -b.c1; r.c2 = -b.c2; return r; }
+template <MB_J3(S)> MB_HD MB_JT(S) operator-(const MB_JT(S)& a) { MB_JT(S) r; r.c0 = -a.c0; r.c1 = -a.c1; r.c2 = -a.c2; return r; }
+template <MB_J3(A), MB_J3(B)> MB_HD auto operator*(const MB_JT(A)& a, const MB_JT(B)& b)
+    -> Jet<decltype(a.c0 * b.c0), decltype(a.c0 * b.c1 + a.c1 * b.c0), decltype((a.c0 * b.c2 + a.c2 * b.c0) + 2.0 * (a.c1 * b.c1))> {
+    Jet<decltype(a.c0 * b.c0), decltype(a.c0 * b.c1 + a.c1 * b.c0), decltype((a.c0 * b.c2 + a.c2 * b.c0) + 2.0 * (a.c1 * b.c1))> r;
     r.c0 = a.c0 * b.c0;
     r.c1 = a.c0 * b.c1 + a.c1 * b.c0;
     r.c2 = (a.c0 * b.c2 + a.c2 * b.c0) + 2.0 * (a.c1 * b.c1);
     return r;
 }
-template <class S> MB_HD Jet<S> operator*(const Jet<S>& a, double b) { Jet<S> r; r.c0 = a.c0 * b; r.c1 = a.c1 * b; r.c2 = a.c2 * b; return r; }
-template <class S> MB_HD Jet<S> operator*(double a, const Jet<S>& b) { Jet<S> r; r.c0 = a * b.c0; r.c1 = a * b.c1; r.c2 = a * b.c2; return r; }
-// compose a univariate function with S-valued derivatives f, f′, f″ taken at x.c0
-template <class S> MB_HD Jet<S> jet_compose(const Jet<S>& x, const S& f0, const S& f1, const S& f2) {
-    Jet<S> r; r.c0 = f0; r.c1 = f1 * x.c1; r.c2 = f2 * (x.c1 * x.c1) + f1 * x.c2; return r;
+template <MB_J3(S)> MB_HD MB_JT(S) operator*(const MB_JT(S)& a, double b) { MB_JT(S) r; r.c0 = a.c0 * b; r.c1 = a.c1 * b; r.c2 = a.c2 * b; return r; }
+template <MB_J3(S)> MB_HD MB_JT(S) operator*(double a, const MB_JT(S)& b) { MB_JT(S) r; r.c0 = a * b.c0; r.c1 = a * b.c1; r.c2 = a * b.c2; return r; }
+// compose a univariate function with derivatives f, f′, f″ (numbers of the type of x.c0) taken at x.c0
+template <MB_J3(S)> MB_HD MB_JT(S) jet_compose(const MB_JT(S)& x, const S0& f0, const S0& f1, const S0& f2) {
+    MB_JT(S) r; r.c0 = f0; r.c1 = f1 * x.c1; r.c2 = f2 * (x.c1 * x.c1) + f1 * x.c2; return r;
 }
-template <class S> MB_HD Jet<S> mb_rcp(const Jet<S>& a) { S f0 = mb_rcp(a.c0); S f1 = -(f0 * f0); S f2 = -2.0 * (f1 * f0); return jet_compose(a, f0, f1, f2); }
-template <class S1, class S2> MB_HD auto operator/(const Jet<S1>& a, const Jet<S2>& b) -> decltype(a * mb_rcp(b)) { return a * mb_rcp(b); }
-template <class S> MB_HD Jet<S> operator/(const Jet<S>& a, double b) { return a * (1.0 / b); }
-template <class S> MB_HD Jet<S> operator/(double a, const Jet<S>& b) { return a * mb_rcp(b); }
-template <class S> MB_HD Jet<S> mb_sqrt(const Jet<S>& a) { S f0 = mb_sqrt(a.c0); S f1 = 0.5 / f0; S f2 = -0.5 * (f1 / a.c0); return jet_compose(a, f0, f1, f2); }
-template <class S> MB_HD Jet<S> mb_acos(const Jet<S>& a) {
-    S f0 = mb_acos(a.c0);
-    S w = 1.0 / (1.0 - a.c0 * a.c0);          // 1/(1-x²)
-    S f1 = -mb_sqrt(w);                       // -1/√(1-x²)
-    S f2 = f1 * a.c0 * w;                     // -x/(1-x²)^{3/2}
+template <MB_J3(S)> MB_HD MB_JT(S) mb_rcp(const MB_JT(S)& a) { S0 f0 = mb_rcp(a.c0); S0 f1 = -(f0 * f0); S0 f2 = -2.0 * (f1 * f0); return jet_compose(a, f0, f1, f2); }
+template <MB_J3(A), MB_J3(B)> MB_HD auto operator/(const MB_JT(A)& a, const MB_JT(B)& b) -> decltype(a * mb_rcp(b)) { return a * mb_rcp(b); }
+template <MB_J3(S)> MB_HD MB_JT(S) operator/(const MB_JT(S)& a, double b) { return a * (1.0 / b); }
+template <MB_J3(S)> MB_HD MB_JT(S) operator/(double a, const MB_JT(S)& b) { return a * mb_rcp(b); }
+template <MB_J3(S)> MB_HD MB_JT(S) mb_sqrt(const MB_JT(S)& a) { S0 f0 = mb_sqrt(a.c0); S0 f1 = 0.5 / f0; S0 f2 = -0.5 * (f1 / a.c0); return jet_compose(a, f0, f1, f2); }
+template <MB_J3(S)> MB_HD MB_JT(S) mb_acos(const MB_JT(S)& a) {
+    S0 f0 = mb_acos(a.c0);
+    S0 w = 1.0 / (1.0 - a.c0 * a.c0);         // 1/(1-x²)
+    S0 f1 = -mb_sqrt(w);                      // -1/√(1-x²)
+    S0 f2 = f1 * a.c0 * w;                    // -x/(1-x²)^{3/2}
     return jet_compose(a, f0, f1, f2);
 }
-template <int K, class S> MB_HD Jet<S> sinc1k(const Jet<S>& a) { return jet_compose(a, sinc1k<K>(a.c0), sinc1k<K + 1>(a.c0), sinc1k<K + 2>(a.c0)); }
+template <int K, MB_J3(S)> MB_HD MB_JT(S) sinc1k(const MB_JT(S)& a) { return jet_compose(a, sinc1k<K>(a.c0), sinc1k<K + 1>(a.c0), sinc1k<K + 2>(a.c0)); }
 
 template <class T> MB_HD T sqr(const T& a) { return a * a; }
 
@@ -223,7 +232,7 @@ MB_HD void scac_pack(double x, double* C) {
 // f(x) for a number x of any of our types, given F[k] = f⁽ᵏ⁾(value(x)) for k up to the nesting depth of x
 MB_HD double apply_fn(double, const double* F) { return F[0]; }
 template <int W> MB_HD Dual<W> apply_fn(const Dual<W>& x, const double* F) { Dual<W> r; r.v = F[0]; MB_FORW r.d[i] = F[1] * x.d[i]; return r; }
-template <class S> MB_HD Jet<S> apply_fn(const Jet<S>& x, const double* F) { return jet_compose(x, apply_fn(x.c0, F), apply_fn(x.c0, F + 1), apply_fn(x.c0, F + 2)); }
+template <MB_J3(S)> MB_HD MB_JT(S) apply_fn(const MB_JT(S)& x, const double* F) { return jet_compose(x, apply_fn(x.c0, F), apply_fn(x.c0, F + 1), apply_fn(x.c0, F + 2)); }
 
 // widen<To>(x): embed a number into a type with more partial slots (missing slots are zero)
 template <class To, class From> struct Widen;
@@ -231,10 +240,10 @@ template <class T> struct Widen<T, T> { static MB_HD T w(const T& x) { return x;
 template <class To> struct Widen<To, double> { static MB_HD To w(double x) { return Make<To>::c(x); } };
 template <> struct Widen<double, double> { static MB_HD double w(double x) { return x; } };
 template <class To, class From> MB_HD To widen(const From& x) { return Widen<To, From>::w(x); }
-template <class S1, class S2> struct Widen<Jet<S1>, Jet<S2>> {
-    static MB_HD Jet<S1> w(const Jet<S2>& x) { Jet<S1> r; r.c0 = widen<S1>(x.c0); r.c1 = widen<S1>(x.c1); r.c2 = widen<S1>(x.c2); return r; }
+template <MB_J3(A), MB_J3(B)> struct Widen<MB_JT(A), MB_JT(B)> {
+    static MB_HD MB_JT(A) w(const MB_JT(B)& x) { MB_JT(A) r; r.c0 = widen<A0>(x.c0); r.c1 = widen<A1>(x.c1); r.c2 = widen<A2>(x.c2); return r; }
 };
-template <class S> struct Widen<Jet<S>, Jet<S>> { static MB_HD Jet<S> w(const Jet<S>& x) { return x; } };
+template <MB_J3(S)> struct Widen<MB_JT(S), MB_JT(S)> { static MB_HD MB_JT(S) w(const MB_JT(S)& x) { return x; } };
 
 // a^2 exactly as the reference evaluates it (src/Adiff.jl:230):  ∂ℝ(a.x^b, a.dx*b*a.x^(b-1))  with  b==0 ? zero(a).
 // On numbers nested three deep (time-packed by motion{P}, Taylor.jl:24-29, over the solver's ∂ℝ{1,Np}) the inner a.x^1 hits
@@ -243,8 +252,8 @@ template <class S> struct Widen<Jet<S>, Jet<S>> { static MB_HD Jet<S> w(const Je
 // Reproduced here because parity with the reference is the contract; plain numbers and Dual<W> square normally.
 MB_HD double sqr_ref(double a) { return a * a; }
 template <int W> MB_HD Dual<W> sqr_ref(const Dual<W>& a) { return a * a; }
-template <class S> MB_HD Jet<S> sqr_ref(const Jet<S>& a) {
-    Jet<S> r; r.c0 = a.c0 * a.c0; r.c1 = 2.0 * (a.c0 * a.c1); r.c2 = 2.0 * (a.c0 * a.c2); return r;
+template <MB_J3(S)> MB_HD MB_JT(S) sqr_ref(const MB_JT(S)& a) {
+    MB_JT(S) r; r.c0 = a.c0 * a.c0; r.c1 = 2.0 * (a.c0 * a.c1); r.c2 = 2.0 * (a.c0 * a.c2); return r;
 }
 
 }  // namespace mb
