@@ -558,9 +558,9 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
         flops = load_flops("directxua")
         falg = load_falg("directxua_200_udof")
         nown = et.hi - et.lo
-        roof = {"bound": "fp64", "kernel": "beam_direct_cot_kernel<3> + beam_direct_b0_kernel<3> + beam_direct_lin_kernel<3>", "unit": "TFLOP/s",
+        roof = {"bound": "fp64", "kernel": "beam_direct_cot_kernel<3,false> + <3,true> + beam_direct_b0_kernel<3> + beam_direct_lin_kernel<3>", "unit": "TFLOP/s",
                 "peak": et.fp64_tflops(), "peak_source": "measured live by mb_measure_fp64_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
-                "kernel_ms": el_ms, "kernel_ms_source": "CUDA events around the element kernels of one window (%d steps, 3 launches each) on the engine's stream" % nown,
+                "kernel_ms": el_ms, "kernel_ms_source": "CUDA events around the element kernels of one window (%d steps, 4 launches each) on the engine's stream" % nown,
                 "kernel_share_of_step": el_ms / (a_ms + b_ms), "traffic": None, "achieved": None, "frac": None}
         if flops:
             roof["flop_per_element"] = flops["flop"]; roof["fp64_inst_per_element"] = flops.get("fp64_inst")
@@ -570,7 +570,7 @@ def run_directxua(args, rank, world, local, comm, steps=None, warmup=None, block
                 roof["fp64_pipe_frac"] = N * nown * flops["fp64_inst"] * 2 / (el_ms * 1e-3) / 1e12 / roof["peak"]
             roof["frac_executed"] = roof["frac"]
             if flops.get("dram_bytes_per_element"):
-                roof["traffic"] = int(N * flops["dram_bytes_per_element"]); roof["traffic_unit"] = "bytes per time step (dram read+write of the three launches, ncu)"
+                roof["traffic"] = int(N * flops["dram_bytes_per_element"]); roof["traffic_unit"] = "bytes per time step (dram read+write of the four launches, ncu)"
         if falg:
             roof["alg_flop_per_element"] = falg["algorithmic"]["flop"]
             roof["achieved_alg"] = N * nown * falg["algorithmic"]["flop"] / (el_ms * 1e-3) / 1e12

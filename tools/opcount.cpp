@@ -158,7 +158,8 @@ int main() {
             }
             for (int i = 0; i < 3; ++i) { U[i].v = CR(0.1); U[i].d1 = CR(0.); }
             take();
-            beam_dyn_cotangents<3, N, true>(g, m, Xu, Xv, true, U, xbk[d][l], vsk[d][l], xb2[l], &vs2[l]);
+            if (d == 0) beam_dyn_cotangents<3, N, true>(g, m, Xu, Xv, true, U, xbk[d][l], vsk[d][l], xb2[l], &vs2[l]);
+            else beam_dyn_cotangents<3, N, false, true>(g, m, Xu, Xv, true, U, xbk[d][l], vsk[d][l]);          // X′ lanes: order-0 Taylor coefficients as plain values (beam_direct_cot_kernel<3,true>)
             lanes = plus(lanes, take());
         }
         for (int l = 0; l < 6; ++l) {                                        // b0: order-0 forward + reverse in SD arithmetic
