@@ -5,25 +5,34 @@
 
 namespace {
 
-// requestables (εₐₓ, ♢κ) of EulerBeam3D (toolbox/BeamElement.jl:151-174) with their partials ∂/∂X₀ (scaled): one lane per (element, element dof), one-direction duals
-// through the forward kinematics only.  J[e][k][d], e4[e][k]  (k: εₐₓ, κ₁, κ₂, κ₃)
+// requestables (εₐₓ, ♢κ) of EulerBeam3D (toolbox/BeamElement.jl:151-174) with their partials ∂/∂X₀ (scaled): six lanes per element through the forward kinematics only, lane l
+// with the two seeds of the element kernels (slot 0 the rotation dof l, slot 1 the translation dof l, statically sparse duals: κ depends on rotations only).
+// J[e][k][d], e4[e][k]  (k: εₐₓ, κ₁, κ₂, κ₃).  (A first version ran twelve one-direction lanes: 140 → 74 µs per step of 10⁵ elements, ncu.)
 // Step batching (mb_direct.cu): grid row = time step; sX = stride of the state per step, sE = elements of the scratch arrays per step (0, 0 for one step).
 __global__ void __launch_bounds__(128) beam_gauge_kernel(BeamGroupDev g, const double* __restrict__ X0, double* __restrict__ J, double* __restrict__ e4, int64_t sX = 0, int64_t sE = 0) {
-    using N = NumDual<1>; using T = Dual<1>;
+    using N = NumSD; using TR = N::TR; using TU = N::TU; using TS = N::TS;
     X0 += (int64_t)blockIdx.y * sX; J += (int64_t)blockIdx.y * sE * 48; e4 += (int64_t)blockIdx.y * sE * 4;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t e = t / 12; const int d = (int)(t - e * 12);
+    const int64_t e = t / 6; const int l = (int)(t - e * 6);
     if (e >= g.nele) return;
     BeamGeo geo; load_geo(g.geo + e * 16, geo);
-    T x[12];
+    TU Xu[6]; TR Xv[6];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { x[i].v = X0[g.idxX[e * 12 + i]]; x[i].d[0] = (i == d) ? g.scaleX[i] : 0.; }
+    for (int i = 0; i < 6; ++i) {
+        const int iu = (i < 3) ? i : i + 3, iv = iu + 3;
+        Xu[i].v = X0[g.idxX[e * 12 + iu]]; Xu[i].d1 = (i == l) ? g.scaleX[iu] : 0.;
+        Xv[i].v = X0[g.idxX[e * 12 + iv]]; Xv[i].d0 = (i == l) ? g.scaleX[iv] : 0.;
+    }
     BeamFwd<N> f;
-    beam_forward<N, false>(geo, Vec3<T>{x[0], x[1], x[2]}, Vec3<T>{x[3], x[4], x[5]}, Vec3<T>{x[6], x[7], x[8]}, Vec3<T>{x[9], x[10], x[11]}, f);
+    beam_forward<N, false>(geo, Vec3<TU>{Xu[0], Xu[1], Xu[2]}, Vec3<TR>{Xv[0], Xv[1], Xv[2]}, Vec3<TU>{Xu[3], Xu[4], Xu[5]}, Vec3<TR>{Xv[3], Xv[4], Xv[5]}, f);
     const double k = 2. / geo.L;
-    const T q[4] = {f.eps, f.vl[0] * k, f.vl[2] * k, -(f.vl[1] * k)};          // ♢κ (BeamElement.jl:164-166)
+    const TR kap[3] = {f.vl[0] * k, f.vl[2] * k, -(f.vl[1] * k)};               // ♢κ (BeamElement.jl:164-166)
+    const int cu = (l < 3) ? l : l + 3, cv = cu + 3;
+    double* Je = J + e * 48;
+    Je[cu] = sd1(f.eps); Je[cv] = sd0(f.eps);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { J[(e * 4 + i) * 12 + d] = q[i].d[0]; if (d == 0) e4[e * 4 + i] = q[i].v; }
+    for (int i = 0; i < 3; ++i) { Je[(i + 1) * 12 + cu] = 0.; Je[(i + 1) * 12 + cv] = kap[i].d0; }
+    if (l == 0) { e4[e * 4] = f.eps.v; for (int i = 0; i < 3; ++i) e4[e * 4 + 1 + i] = kap[i].v; }
 }
 // ElementCost accelerator for StrainGaugeOnEulerBeam3D (toolbox/StrainGaugeOnBeamElement.jl:70-76) under the quadratic cost Σ_g (ε_g − εm_g)²/(2σ²):
 // ε_g = G[g]·(εₐₓ,κ); ∇cost = Jᵀ·Gᵀ·r/σ², ∇²cost = Jᵀ·GᵀG·J/σ² (chainrule of the second-order cost with the first-order eleres: to_order{2} adds no curvature, :190-196).

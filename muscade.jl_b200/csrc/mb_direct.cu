@@ -842,7 +842,7 @@ static int32_t direct_eval_steps(mb_handle* h, int64_t s0, int64_t s1) {
                 const DirectData::Meas& m = mit->second;
                 for (int b = 0; b < nb; ++b) ARG(m.have[(size_t)(k + b)], "strain-gauge measurements of a stored step are not set (mb_direct_set_gauge_measurements)");
                 const int64_t eb = D->G.hxxbase[ig], nc = D->ncost;
-                beam_gauge_kernel<<<dim3(nblk(g.nele * 12, 128), nb), 128, 0, st>>>(gd, sd.X[0], D->cJ + eb * 48, D->ce4 + eb * 4, sb.sX, nc);
+                beam_gauge_kernel<<<dim3(nblk(g.nele * 6, 128), nb), 128, 0, st>>>(gd, sd.X[0], D->cJ + eb * 48, D->ce4 + eb * 4, sb.sX, nc);
                 gauge_cost_kernel<<<dim3(nblk(g.nele * 12, 128), nb), 128, 0, st>>>(g.nele, g.ng, g.gaugeG, m.eps + k * m.stride, m.per_element, g.isig2, D->cJ + eb * 48, D->ce4 + eb * 4,
                                                                                     D->cgX + eb * 12, D->cHXX + eb * 144, D->ccost + eb, m.stride, nc);
                 SL12 sl; for (int i = 0; i < 12; ++i) sl.v[i] = g.scaleX[i] * D->lamscale;

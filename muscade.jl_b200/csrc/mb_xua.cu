@@ -868,7 +868,7 @@ int32_t mb_xua_eval_device(mb_handle* h, int32_t iexp, int64_t istep, mb_errinfo
         if (costed) {
             ARG(T.epsm, "strain-gauge measurements of this step are not set (mb_xua_set_gauge_measurements)");
             if (!T.J) { CK(dalloc(h, &T.J, T.nele * 48)); CK(dalloc(h, &T.e4, T.nele * 4)); CK(dalloc(h, &T.cost, T.nele)); CK(dalloc(h, &T.gX, T.nele * 12)); CK(dalloc(h, &T.HXX, T.nele * 144)); }
-            beam_gauge_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(gd, sd.X[0], T.J, T.e4);
+            beam_gauge_kernel<<<nblk(T.nele * 6, 128), 128, 0, st>>>(gd, sd.X[0], T.J, T.e4);
             gauge_cost_kernel<<<nblk(T.nele * 12, 128), 128, 0, st>>>(T.nele, T.ng, T.G, T.epsm, T.epsm_per_element, T.isig2, T.J, T.e4, T.gX, T.HXX, T.cost);
             h->launches += 2;
         }
