@@ -9,5 +9,5 @@ from ._lib import MuscadeB200Error, build  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .model import Model, addnode, addelement, setscale, initialize, Disassembler, State, getdof  # noqa: F401
 from .toolbox import (BeamCrossSection, EulerBeam3D, AxisymmetricBarCrossSection, Bar3D, SoilContact, Hold, DofLoad, DofConstraint,
-                      ElementType, SingleDofCost, Taylor2, LagrangianElement, SingleUdof, Acost, SingleAcost, StrainGaugeOnEulerBeam3D, QuadraticGaugeCost, ElementCost)  # noqa: F401
+                      ElementType, SingleDofCost, Taylor2, LagrangianElement, SingleUdof, Acost, SingleAcost, StrainGaugeOnEulerBeam3D, QuadraticGaugeCost, ElementCost, ElementConstraint, equal, positive, off)  # noqa: F401
 from .adiff2 import D2  # noqa: F401

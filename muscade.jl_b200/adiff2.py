@@ -100,3 +100,26 @@ def sqrt(x): x = D2.lift(x); return x.apply(np.sqrt, lambda v: .5 / np.sqrt(v), 
 def sin(x): x = D2.lift(x); return x.apply(np.sin, np.cos, lambda v: -np.sin(v))
 def cos(x): x = D2.lift(x); return x.apply(np.cos, lambda v: -np.sin(v), lambda v: -np.cos(v))
 def absolute(x): x = D2.lift(x); return x.apply(np.abs, np.sign, lambda v: np.zeros_like(v))
+
+
+def KKT(lam, g, gamma):
+    """KKT(λ,g,γ) (src/BasicElements.jl:289-307): "a pseudo-potential with strange derivatives" — value 0, gradient λ·∇g + S·∇λ with the complementary slackness
+    S(λ,g,γ) = g·λ − γ, and as second derivative the derivative of THAT expression, as the reference's nested duals form it (entry [i][j] = ∂ⱼ of gradient entry i):
+    λⱼ·gᵢ + λ·gᵢⱼ + (gⱼ·λ + g·λⱼ)·λᵢ + S·λᵢⱼ — not symmetric."""
+    lam, g = D2.lift(lam), D2.lift(g)
+    v = np.zeros(np.broadcast(lam.v, g.v).shape)
+    if lam.g is None and g.g is None:
+        return D2(v)
+    S = g.v * lam.v - gamma
+    col = lambda a: np.asarray(a, float)[..., None]
+    Np = (lam.g if lam.g is not None else g.g).shape[-1]
+    zg = np.zeros(v.shape + (Np,))
+    lg = lam.g if lam.g is not None else zg
+    gg = g.g if g.g is not None else zg
+    grad = col(lam.v) * gg + col(S) * lg
+    H = gg[..., :, None] * lg[..., None, :] + (col(lam.v) * gg + col(g.v) * lg)[..., None, :] * lg[..., :, None]
+    if g.H is not None:
+        H = H + col(lam.v)[..., None] * g.H
+    if lam.H is not None:
+        H = H + col(S)[..., None] * lam.H
+    return D2(v, grad, H)

@@ -55,8 +55,9 @@ class EleTyp:
         """ElType.residual over all elements: X = [X₀,X′,…] of shape (nele,nx) each → (R, K0, K1, K2), K1/K2 None when no run has them.
         Element types that read U- or A-dofs (as plain values: an X-analysis does not differentiate with respect to them, src/SweepX.jl:45-96)
         declare `takes_UA = True` and receive U (nele,nu), A (nele,na) as keyword arguments."""
-        if getattr(self.ElType, "kind", None) == "lagrangian":
-            return self._residual_d2(X, t, U, A)
+        k = getattr(self.ElType, "kind", None)
+        if k == "lagrangian" or (k in ("elementcost", "elementconstraint") and getattr(self.ElType, "kind_general", None) == "lagrangian"):
+            return self._residual_d2(X, t, U, A)      # host-evaluated wrappers: R = ∂L/∂Λ is the target's residual, costs and multipliers do not enter an X-analysis
         if getattr(self.ElType, "takes_UA", False):
             parts = [self.ElType.residual(ex, [x[a:b] for x in X], t, U=None if U is None else U[a:b], A=None if A is None else A[a:b]) for a, b, ex in self._runs()]
         else:

@@ -465,10 +465,43 @@ class QuadraticGaugeCost:
         self.sigma, self.measured = float(sigma), measured
 
 
+class _Eleres:
+    """the requested element results handed to a cost / gap functor: attributes by name (`eleres.Fh`), only what `req` names"""
+
+    def __init__(self, d, req):
+        missing = [k for k in req if k not in d]
+        if missing:
+            from .model import muscadeerror
+            muscadeerror("the target element does not provide the requested result(s) %s" % (missing,))
+        for k in req:
+            setattr(self, k, d[k])
+
+
+def _target_lagrangian(T, o, extra, Λ, X, U, A, t, SP):
+    """getlagrangian(target,…,req) (src/Assemble.jl:690-740) for a host-evaluated target written against adiff2.D2: L and the dict of its element results.
+    The target provides `lagrangian_req` / `residual_req` (→ (L | [R…], dict)); plain `lagrangian` / `residual` give no results."""
+    if hasattr(T, "lagrangian_req"):
+        return T.lagrangian_req(o, extra, Λ, X, U, A, t, SP)
+    if hasattr(T, "residual_req"):
+        R, res = T.residual_req(o, extra, X, U, A, t, SP)
+    elif hasattr(T, "lagrangian"):
+        return T.lagrangian(o, extra, Λ, X, U, A, t, SP), {}
+    else:
+        R, res = T.residual(o, extra, X, U, A, t, SP), {}
+    L = 0.
+    for i, Ri in enumerate(R):                     # L = Λ ∘₁ R (src/Assemble.jl:721-726)
+        L = L + Λ[i] * Ri
+    return L, res
+
+
 class ElementCost(ElementType):
     """ElementCost(nod;req,cost,costargs,ElementType,elementkwargs) (src/BasicElements.jl:117-132): L = getlagrangian(target) + cost(eleres,t,costargs...).
-    On the device (csrc/mb_xua.cu, the accelerator of src/DirectXUA.jl:172-198): ElementType = StrainGaugeOnEulerBeam3D, req = ("ε",), cost = QuadraticGaugeCost."""
+    On the device (csrc/mb_xua.cu, csrc/mb_direct.cu: the accelerator of src/DirectXUA.jl:172-198): ElementType = StrainGaugeOnEulerBeam3D, req = ("ε",), cost = QuadraticGaugeCost.
+    Around a host-evaluated target (a LagrangianElement with `lagrangian_req` / `residual_req`): the generic second-order path, differentiated by adiff2.D2 (xua.packets);
+    pinned to test/TestElementCost.jl:29-33."""
     kind = "elementcost"
+    kind_general = "lagrangian"
+    takes_UA = True
 
     @classmethod
     def doflist(cls, ElementType=None, elementkwargs=None, **kw):
@@ -483,3 +516,57 @@ class ElementCost(ElementType):
         built = ElementType.construct(coords, **elementkwargs)
         eleobj, extra = built if isinstance(built, tuple) else (built, {})
         return eleobj, dict(extra, req=tuple(req), cost=cost, costargs=tuple(costargs), target=ElementType)
+
+    @staticmethod
+    def lagrangian(o, extra, Λ, X, U, A, t, SP):
+        L, res = _target_lagrangian(extra["target"], o, extra, Λ, X, U, A, t, SP)
+        return L + extra["cost"](_Eleres(res, extra["req"]), t, *extra["costargs"])
+
+
+def equal(t): return "equal"          # src/BasicElements.jl:310-345: the three constant mode functors
+def positive(t): return "positive"
+def off(t): return "off"
+
+
+class ElementConstraint(ElementType):
+    """ElementConstraint(nod;λinod,λfield,req,gap,gargs,mode,ElementType,elementkwargs) (src/BasicElements.jl:493-575): the target's dofs plus one U-dof λ on node λinod;
+    L = getlagrangian(target) − gap(eleres,t,gargs...)·λ (`equal`), − KKT(λ,gap,γ) (`positive`), − λ²/2 (`off`).  Host-evaluated through adiff2.D2 (the generic
+    second-order path; the reference's accelerator of src/DirectXUA.jl:199-241 carries its own TODO and is not restated); pinned to test/TestElementCost.jl:63-85."""
+    kind = "elementconstraint"
+    kind_general = "lagrangian"
+    takes_UA = True
+
+    @classmethod
+    def doflist(cls, λinod=None, λfield=None, ElementType=None, elementkwargs=None, **kw):
+        inod, clas, field = ElementType.doflist(**elementkwargs)
+        return tuple(inod) + (λinod,), tuple(clas) + ("U",), tuple(field) + (λfield,)
+
+    @classmethod
+    def typekey(cls, λinod=None, λfield=None, req=None, gap=None, mode=None, ElementType=None, elementkwargs=None, **kw):
+        return ("ElementConstraint", λinod, λfield, tuple(req or ()), id(gap), id(mode)) + ElementType.typekey(**elementkwargs)
+
+    @classmethod
+    def construct(cls, coords, λinod, λfield, req, gap, mode, ElementType, elementkwargs, gargs=()):
+        built = ElementType.construct(coords, **elementkwargs)
+        eleobj, extra = built if isinstance(built, tuple) else (built, {})
+        nu = sum(1 for c in ElementType.doflist(**elementkwargs)[1] if c == "U")
+        return eleobj, dict(extra, req=tuple(req), gap=gap, gargs=tuple(gargs), mode=mode, target=ElementType, Nu=nu)
+
+    @staticmethod
+    def lagrangian(o, extra, Λ, X, U, A, t, SP):
+        from .adiff2 import KKT
+        Nu = extra["Nu"]
+        u = [list(ud[:Nu]) for ud in U]
+        λ = U[0][Nu]
+        L, res = _target_lagrangian(extra["target"], o, extra, Λ, X, u, A, t, SP)
+        gap = extra["gap"](_Eleres(res, extra["req"]), t, *extra["gargs"])
+        m = extra["mode"](t)
+        γ = float((SP or {}).get("γ", 0.)) if isinstance(SP, dict) or SP is None else float(getattr(SP, "γ", 0.))
+        if m == "equal":
+            return L - gap * λ
+        if m == "positive":
+            return L - KKT(λ, gap, γ)
+        if m == "off":
+            return L - 0.5 * (λ * λ)
+        from .model import muscadeerror
+        muscadeerror("mode(t) must return 'equal', 'positive' or 'off'")

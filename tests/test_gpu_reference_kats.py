@@ -110,3 +110,13 @@ def test_sweepx0_turbine_moorings_reference_state(mb):
     s = states[0]
     assert np.allclose(s.X[0], [-5.332268523655259, 21.09778288272267, 0.011304253608808651], rtol=1e-7)       # :24 (Julia's ≈: rtol = √eps)
     assert not s.Λ[0].any() and not s.A.any() and s.time == 0. and m.locked
+
+
+def test_sweepx0_with_wrapped_anchor_lines_same_state(mb):
+    """the same analysis with two of the anchor lines wrapped in ElementCost / ElementConstraint: in an X-analysis R = ∂L/∂Λ is the target's residual (the cost and the
+    multiplier do not enter), so the converged state is the reference's of test/TestSweepX0.jl:24"""
+    import xua_models as XM
+    m = XM.model_mooring_wrapped()
+    st = mb.initialize(m)
+    s = mb.sweepx.solve(0, st, [0., 1.])[0]
+    assert np.allclose(s.X[0], [-5.332268523655259, 21.09778288272267, 0.011304253608808651], rtol=1e-7)

@@ -238,3 +238,30 @@ def test_argument_errors(xeng):
         eng2.add_A()
     with pytest.raises(mb.MuscadeB200Error, match="no such step"):
         eng2.add_step(1, 7)
+
+
+@pytest.mark.parametrize("IA", [0, 1])
+def test_elementcost_and_elementconstraint_wrappers_through_the_device_assembly(xeng, IA):
+    """ElementCost / ElementConstraint around a host-evaluated target (test/TestElementCost.jl's AnchorLine; src/BasicElements.jl:117-132, 493-575) in a DirectXUA{0,0,IA}
+    assembly: X-, U- (the constraint's multiplier) and A-dofs in one element, the generic second-order path — structures, out, Lvv.nzval and Lv bit-exact against the oracle"""
+    rng = np.random.default_rng(9)
+    m = XM.model_mooring_wrapped()
+    s0 = mb.initialize(m); dis = s0.dis
+    nX, nU, nA = m.getndof(("X", "U", "A"))
+    assert nU == 1
+    OX, OU, nsteps, dts = 0, 0, [4], [1.]
+    eng = xeng()
+    eng.prepare(m, dis, OX, OU, IA, nsteps, dts)
+    P = OP.prepare_direct(XM.dis_lists(dis), nX, nU, nA, OX, OU, IA)
+    big, basm_o, pgr_o, _ = OP.preparebig(IA, nsteps, P["nL2"], P["pat"])
+    colptr, rowval = eng.big_pattern()
+    assert np.array_equal(colptr, big["colptr"]) and np.array_equal(rowval, big["rowval"])
+    states = _states(m, dis, s0, OX, OU, [np.arange(4.)], rng)
+    eng.assemblebig(states)
+    outA, outs = _assemble_outs(m, dis, P, OX, OU, IA, states)
+    nz_o, Lv_o = OP.assemblebig_general(IA, nsteps, dts, P, big, basm_o, pgr_o, outA, outs)
+    nz, Lv = eng.big()
+    assert np.array_equal(nz, nz_o) and np.array_equal(Lv, Lv_o)
+    last = outs[-1][-1]
+    assert np.array_equal(eng.get_out(2, 3, 1, 1), last["L2"][(2, 3)][0, 0]) and np.abs(last["L2"][(2, 3)][0, 0]).max() > 0        # ∂²L/∂X∂λ = −∂gap/∂X
+    assert np.array_equal(eng.get_out(3, 0, 1), last["L1"][3][0]) and np.abs(last["L1"][3][0]).max() > 0                            # ∂L/∂λ = −gap

@@ -136,3 +136,62 @@ def test_gauge_types_do_not_merge_across_different_gauges():
     assert len(m.ele) == 1 and m.ele[0].nele == 2
     mb.addelement(m, mb.ElementCost, np.stack([nod[2:3], nod[3:4]], axis=1), elementkwargs=dict(P=2 * P, D=D, elementkwargs=ek), **kw)
     assert len(m.ele) == 2 and not np.array_equal(m.ele[0].extra["G"], m.ele[1].extra["G"])
+
+
+def _anchor_wrapped(kind):
+    """test/TestElementCost.jl:7-13, 63-68: AnchorLine wrapped in ElementCost (cost = Fh²) or ElementConstraint (gap = Fh², λ on node 1, mode equal)"""
+    import muscade_b200 as mb
+    m = mb.Model("TestModel")
+    n1 = mb.addnode(m, [0., 0., 100.]); n3 = mb.addnode(m, [])
+    ek = dict(Δxₘtop=[5., 0, 0], xₘbot=[250., 0], L=290., buoyancy=-5e3)
+    sq = lambda eleres, t: eleres.Fh * eleres.Fh
+    if kind == "cost":
+        mb.addelement(m, mb.ElementCost, [[n1, n3]], req=("Fh",), cost=sq, ElementType=XM.AnchorLine, elementkwargs=ek)
+    else:
+        mb.addelement(m, mb.ElementConstraint, [[n1, n3]], λinod=1, λfield="λ", req=("Fh",), gap=sq, mode=mb.equal, ElementType=XM.AnchorLine, elementkwargs=ek)
+    return m
+
+
+def test_elementcost_and_elementconstraint_reference_goldens():
+    """test/TestElementCost.jl:29-33 and :81-85: dof lists, L and ∇L (order Λ, X, U, A) of an AnchorLine wrapped in ElementCost / ElementConstraint at Λ = 0, X = 1, U = 1, A = 0 —
+    through the packets the device assembles (xua.packets: the generic second-order path, adiff2.D2 in the place of the reference's nested duals)"""
+    import muscade_b200 as mb
+    from muscade_b200 import xua
+    gold = {"cost": (1.926851845351649e11, [-438861.1307445675, 9278.602091074139, 1.8715107899328927e6, -2.322235123921358e10, 4.9097753633879846e8, 9.903105530914653e10,
+                                           -6.735986859485705e12, 3.853703690703298e11]),
+            "constraint": (-1.926851845351649e11, [-438861.1307445675, 9278.602091074139, 1.8715107899328927e6, 2.322235123921358e10, -4.9097753633879846e8, -9.903105530914653e10,
+                                                  -1.926851845351649e11, 6.735986859485705e12, -3.853703690703298e11])}
+    for kind in ("cost", "constraint"):
+        m = _anchor_wrapped(kind)
+        et = m.ele[0]
+        inod, clas, field = et.inod, et.clas, et.field
+        if kind == "cost":
+            assert (tuple(inod), tuple(clas), tuple(field)) == ((1, 1, 1, 2, 2), ("X", "X", "X", "A", "A"), ("tx1", "tx2", "rx3", "ΔL", "Δbuoyancy"))
+        else:
+            assert (tuple(inod), tuple(clas), tuple(field)) == ((1, 1, 1, 2, 2, 1), ("X", "X", "X", "A", "A", "U"), ("tx1", "tx2", "rx3", "ΔL", "Δbuoyancy", "λ"))
+        s0 = mb.initialize(m); dis = s0.dis
+        nX, nU, nA = m.getndof(("X", "U", "A"))
+        assert (nX, nU, nA) == (3, 0 if kind == "cost" else 1, 2)
+        Λ, X, U, A = np.zeros(nX), [np.ones(nX)], [np.ones(nU)], np.zeros(nA)
+        g, H = xua.packets(et, dis.dis[0], 0, 0, 1, Λ, X, U, A, 0.)
+        Lval, grad = gold[kind]
+        assert np.allclose(g[0], grad, rtol=1e-10)
+        ed = dis.dis[0]
+        L = et.ElType.lagrangian(et.eleobj, et.extra, list(Λ[ed.X[0] - 1][:, None] * np.ones(1)), [list(X[0][ed.X[0] - 1][:, None] * np.ones(1))],
+                                 [list(U[0][ed.U[0] - 1][:, None] * np.ones(1))] if nU else [[]], list(A[ed.A[0] - 1][:, None] * np.ones(1)), 0., None)
+        assert np.allclose(D2.lift(L).v, Lval, rtol=1e-12)
+        assert np.abs(H[0] - H[0].T).max() <= 1e-9 * np.abs(H[0]).max()          # equal mode: a true potential, symmetric Hessian
+
+
+def test_kkt_pseudo_potential_derivatives():
+    """KKT(λ,g,γ) (src/BasicElements.jl:289-307): value 0, gradient λ·∇g + (gλ − γ)·∇λ, second derivative = derivative of that expression (not symmetric)"""
+    from muscade_b200.adiff2 import D2, KKT
+    x = D2.variables(np.array([[0.7, 1.3, -0.4]]))
+    lam, g = x[0], x[1] * x[1] + x[2]                  # λ = z₀, g = z₁² + z₂
+    k = KKT(lam, g, 0.25)
+    gv, lv = 1.3 ** 2 - 0.4, 0.7
+    S = gv * lv - 0.25
+    assert k.v[0] == 0.
+    assert np.allclose(k.g[0], [S, lv * 2 * 1.3, lv])
+    # ∂ⱼ of gradient entry i, by hand: grad = (gλ − γ, 2λz₁, λ)
+    assert np.allclose(k.H[0], [[gv, lv * 2 * 1.3, lv], [2 * 1.3, 2 * lv, 0.], [1., 0., 0.]])

@@ -137,6 +137,11 @@ class AnchorLine(mb.LagrangianElement):
 
     @staticmethod
     def lagrangian(o, extra, Λ, X, U, A, t, SP):
+        return AnchorLine.lagrangian_req(o, extra, Λ, X, U, A, t, SP)[0]
+
+    @staticmethod
+    def lagrangian_req(o, extra, Λ, X, U, A, t, SP):
+        """→ L and the requestables (☼ of test/SomeElements.jl:80-88) for ElementCost / ElementConstraint"""
         L, buoy = o[:, 8] * (1 + A[0]), o[:, 9] * (1 + A[1])
         x = X[0]
         Xtop = [x[0] + o[:, 0], x[1] + o[:, 1], o[:, 2]]
@@ -148,7 +153,7 @@ class AnchorLine(mb.LagrangianElement):
         Fh = -cr * buoy
         Fd = [ch[0] / xaf * Fh, ch[1] / xaf * Fh]
         m3 = dX[0] * Fd[1] - dX[1] * Fd[0]
-        return Λ[0] * Fd[0] + Λ[1] * Fd[1] + Λ[2] * m3
+        return Λ[0] * Fd[0] + Λ[1] * Fd[1] + Λ[2] * m3, dict(Fh=Fh, cr=cr, xaf=xaf)
 
 
 def model_testsweepx0():
@@ -269,4 +274,21 @@ def model_testeigx():
     mb.addelement(m, Spring1, np.stack([xnod[:-1], xnod[1:], np.full(nel, anod)], axis=1), EA=EA)
     mb.addelement(m, SdofOscillator, xnod[:, None], M1=M, C1=Cd)
     mb.addelement(m, SdofOscillator, xnod[:1, None], K1=1.)
+    return m
+
+
+def model_mooring_wrapped():
+    """the moored turbine of test/TestSweepX0.jl:9-18 with its three AnchorLines wrapped as in test/TestElementCost.jl: one plain, one in ElementCost (cost on the horizontal
+    force), one in ElementConstraint (gap on the horizontal force, multiplier λ as a U-dof on the turbine node)"""
+    m = mb.Model("MooredTurbine")
+    n1 = mb.addnode(m, [0., 0., 100.]); n2 = mb.addnode(m, []); n3 = mb.addnode(m, [])
+    sea = lambda t, x: (1. * t, 0. * t)
+    sky = lambda t, x: (0., 10.)
+    mb.addelement(m, Turbine, [n1, n2], seadrag=1e6, sea=sea, skydrag=1e5, sky=sky)
+    ek = lambda i: dict(Δxₘtop=list(5 * np.array([np.cos(i * 2 * np.pi / 3), np.sin(i * 2 * np.pi / 3)])) + [0.],
+                        xₘbot=list(250 * np.array([np.cos(i * 2 * np.pi / 3), np.sin(i * 2 * np.pi / 3)])), L=290., buoyancy=-5e3)
+    mb.addelement(m, AnchorLine, [n1, n3], **ek(0))
+    mb.addelement(m, mb.ElementCost, [n1, n3], req=("Fh",), cost=lambda eleres, t: 1e-8 * (eleres.Fh - 4e5) * (eleres.Fh - 4e5), ElementType=AnchorLine, elementkwargs=ek(1))
+    mb.addelement(m, mb.ElementConstraint, [n1, n3], λinod=1, λfield="λ", req=("Fh", "cr"), gap=lambda eleres, t: 1e-5 * eleres.Fh - 0.05 * eleres.cr + t,
+                  mode=mb.equal, ElementType=AnchorLine, elementkwargs=ek(2))
     return m
