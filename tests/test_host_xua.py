@@ -195,3 +195,28 @@ def test_kkt_pseudo_potential_derivatives():
     assert np.allclose(k.g[0], [S, lv * 2 * 1.3, lv])
     # ∂ⱼ of gradient entry i, by hand: grad = (gλ − γ, 2λz₁, λ)
     assert np.allclose(k.H[0], [[gv, lv * 2 * 1.3, lv], [2 * 1.3, 2 * lv, 0.], [1., 0., 0.]])
+
+
+def test_dofconstraint_reference_goldens():
+    """test/TestDofConstraints.jl:27-86 — DofConstraint{:X} residual and ∂R/∂X in equal / off / positive (γ = 0) mode, in contact and with a gap (toolbox.DofConstraint's
+    closed forms); :96-157 — the U-class constraint's lagrangian −gap·λ / −λ²/2 / −KKT(λ,gap,γ) with γ = 1 and γ = 0 through adiff2.D2 and adiff2.KKT:
+    ∇L and its (non-symmetric) derivative"""
+    import muscade_b200 as mb
+    from muscade_b200.adiff2 import KKT
+    gap = lambda x, t: (.3 * x[:, 0] + .4 * x[:, 1], np.array([.3, .4]))
+    ctc, gp = np.array([[4., -3., 10.]]), np.array([[4., 3., 10.]])
+    E = np.array([[0, 0, -.3], [0, 0, -.4], [-.3, -.4, 0]])
+    P0 = lambda gv: np.array([[0, 0, -.3], [0, 0, -.4], [-3., -4., -gv]])
+    for mode, X, R, K in (("equal", ctc, [-3, -4, 0], E), ("equal", gp, [-3, -4, -2.4], E), ("off", ctc, [0, 0, -10], np.diag([0, 0, -1.])),
+                          ("positive", ctc, [-3, -4, 0], P0(0.)), ("positive", gp, [-3, -4, -24.], P0(2.4))):
+        r, k0, _, _ = mb.DofConstraint.residual(dict(gap=gap, gargs=(), mode=mode, Nx=2), [X], 0.)
+        assert np.allclose(r[0], R) and np.allclose(k0[0], K), mode
+    for γ, U, R, H in ((1., ctc, [-3., -4., 1.], P0(0.)), (1., gp, [-3., -4., -23.], P0(2.4)), (0., ctc, [-3, -4, 0], P0(0.)), (0., gp, [-3., -4., -24.], P0(2.4))):
+        u = D2.variables(U)
+        L = -KKT(u[2], .3 * u[0] + .4 * u[1], γ)
+        assert np.allclose(L.g[0], R) and np.allclose(L.H[0], H), γ
+    u = D2.variables(ctc)
+    L = -(.3 * u[0] + .4 * u[1]) * u[2]                                   # equal
+    assert np.allclose(L.g[0], [-3, -4, 0]) and np.allclose(L.H[0], E)
+    L = -0.5 * (u[2] * u[2])                                             # off
+    assert np.allclose(L.g[0], [0, 0, -10]) and np.allclose(L.H[0], np.diag([0, 0, -1.]))
